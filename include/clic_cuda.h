@@ -1,0 +1,255 @@
+/*
+ * clic_cuda.h — C ABI of the B200-native continuous-time fixed-lag smoothing core.
+ *
+ * This is the drop-in boundary for ONE path of APRIL-ZJU/clic: B-spline factor residual +
+ * analytic-Jacobian evaluation, normal-equation assembly, the LM/GN step and the
+ * marginalization Schur complement.  The reference has no FFI layer: its
+ * boundary is the C++ class clic::TrajectoryEstimator (src/estimator/trajectory_estimator.h:100-278)
+ * on top of ceres::Problem.  Every entry point below cites the reference method it replaces.
+ * include/clic/trajectory_estimator.hpp is a header-only C++ shim that reproduces the
+ * reference method names / argument order on top of this ABI.
+ *
+ * Two libraries implement this header with identical symbols:
+ *   clic_b200/lib/libclic_cuda.so   the product: hand-written sm_100a CUDA (no CPU path at all)
+ *   oracle/_build/libclic_oracle.so test infrastructure only: a scalar CPU restatement of the
+ *                                   reference arithmetic (see oracle/README.md)
+ *
+ * Conventions (SURVEY.md §8 "Conventions shared by all rows"):
+ *   - rotations are unit quaternions stored (x,y,z,w)                 (sophus_lib/so3.hpp:153-160)
+ *   - tangent update R <- R*exp(dtheta), p <- p + dp                    (factor/ceres_local_param.h:132-139)
+ *   - all host pointers are borrowed for the duration of the call only
+ *   - every function returns a clic_status; nothing throws or asserts across the ABI
+ *   - time stamps are double seconds exactly as the reference structs hold them
+ *     (lidar_feature.h:110-123 t_point, parameter_struct.h:52-58 timestamp); the library converts
+ *     with the reference's truncation time_ns = (int64)(t * 1e9) (trajectory_estimator.cpp:275)
+ *   - a measurement outside the window is silently dropped, exactly like
+ *     TrajectoryEstimator::MeasuredTimeToNs returning false (trajectory_estimator.cpp:272-292,717);
+ *     the number dropped is reported through an out-parameter
+ *
+ * Canonical tangent ordering of H and b (the reference never materialises one):
+ *   [ knot k_f : dtheta(3) dp(3) | knot k_f+1 ... | knot K-1 ]   k_f = fixed_index + 1
+ *   [ gyro bias slot 0..nb-1 (3 each) ]   if !lock_wb
+ *   [ accel bias slot 0..nb-1 (3 each) ]  if !lock_ab
+ *   [ t_offset IMU (1) ] if unlocked, [ t_offset camera (1) ] if unlocked
+ *   [ inverse depth of landmark 0..L-1 ]  only landmarks added with fixed_depth = 0
+ * H = sum J~^T J~, b = sum J~^T r~ with loss-corrected J~, r~ (marginalization_factor.cpp:38-61,138,144).
+ */
+#ifndef CLIC_CUDA_H_
+#define CLIC_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CLIC_API __attribute__((visibility("default")))
+#else
+#define CLIC_API
+#endif
+
+typedef enum {
+  CLIC_OK = 0,
+  CLIC_ERR_BAD_HANDLE = 1,
+  CLIC_ERR_BAD_ARGUMENT = 2,
+  CLIC_ERR_CUDA = 3,          /* a CUDA runtime call or kernel failed; see clic_last_error() */
+  CLIC_ERR_NO_DEVICE = 4,     /* no sm_100 device: the product path refuses to run (no CPU fallback) */
+  CLIC_ERR_NCCL = 5,
+  CLIC_ERR_NOT_POSITIVE_DEFINITE = 6,
+  CLIC_ERR_UNSUPPORTED = 7,
+  CLIC_ERR_NOTHING_TO_KEEP = 8 /* marginalization leaves no parameters (SaveMarginalizationInfo -> nullptr, trajectory_estimator.cpp:241-248) */
+} clic_status;
+
+/* SensorType, src/spline/trajectory.h:29-33 */
+enum { CLIC_SENSOR_IMU = 0, CLIC_SENSOR_LIDAR = 1, CLIC_SENSOR_CAMERA = 2 };
+/* GeometryType, src/lidar_odometry/lidar_feature.h:108 */
+enum { CLIC_GEO_LINE = 0, CLIC_GEO_PLANE = 1 };
+
+/* Parameter-block kinds a prior can refer to (the reference keys them by raw address,
+ * marginalization_factor.h:125-138; we key them by kind + stable id). */
+enum {
+  CLIC_BLOCK_KNOT_ROT = 0,  /* id = global knot index, size 4, local 3 */
+  CLIC_BLOCK_KNOT_POS = 1,  /* id = global knot index, size 3 */
+  CLIC_BLOCK_BIAS_GYRO = 2, /* id = global bias slot, size 3 */
+  CLIC_BLOCK_BIAS_ACCEL = 3,
+  CLIC_BLOCK_GRAVITY = 4,   /* id = 0, size 3 (ambient; only ever appears inside priors) */
+  CLIC_BLOCK_T_OFFSET = 5,  /* id = sensor, size 1 */
+  CLIC_BLOCK_INV_DEPTH = 6  /* id = landmark index, size 1 */
+};
+
+typedef struct clic_estimator clic_estimator;
+typedef struct clic_prior clic_prior;
+
+/* The trajectory window + the non-spline states one solve touches.
+ * Replaces: Trajectory (knot deques, src/spline/se3_spline.h; extrinsics EP_StoI_, trajectory.h:59-67),
+ * TrajectoryManager::all_imu_bias_ / gravity_ (trajectory_manager.cpp:599-605) and
+ * fea_id_inv_depths_ (:707), which the reference passes as raw double* parameter blocks. */
+typedef struct {
+  int64_t t0_ns;          /* time of the first uploaded knot's interval start = minTimeNs + knot_id0*dt_ns */
+  int64_t dt_ns;          /* knot spacing, (int64)(knot_distance*1e9) (trajectory.h:46-48) */
+  int32_t n_knots;        /* K >= 4 */
+  int32_t knot_id0;       /* global index of uploaded knot 0 (priors store global ids) */
+  const double* knot_q;   /* K*4, (x,y,z,w) */
+  const double* knot_p;   /* K*3 */
+  double S_LtoI[4], p_LinI[3]; /* unused by the adders (they take extrinsics explicitly like the reference) but kept for pose queries */
+  double S_CtoI[4], p_CinI[3]; /* ImageFeatureFactor::SetParam (image_feature_factor.h:270-284) */
+  double t_offset_ns[3];  /* per CLIC_SENSOR_*; ExtrinsicParam::t_offset_ns is a double (parameter_struct.h:108-150) */
+  double gravity[3];
+  int32_t n_bias;         /* number of bias slots (the reference uses 2 per solve: last scan, current scan) */
+  int32_t bias_id0;       /* global id of slot 0 */
+  const double* bias;     /* n_bias*6: gyro(3) accel(3) */
+  int32_t n_landmarks;
+  int32_t reserved0;
+  const double* inv_depth; /* n_landmarks */
+} clic_window_desc;
+
+/* Mirrors TrajectoryEstimatorOptions (trajectory_estimator_options.h:32-72) + execution knobs. */
+typedef struct {
+  int32_t lock_traj;
+  int32_t lock_ab, lock_wb, lock_g;     /* lock_g must be 1 for clic_solve (gravity uses a Ceres-internal
+                                           HomogeneousVectorParameterization; locked in every shipped call,
+                                           trajectory_manager.cpp:244,615) */
+  int32_t lock_t_offset[3];             /* per sensor */
+  int32_t is_marg_state;
+  int64_t t_offset_padding_ns;
+  int32_t ctrl_to_be_opt_now, ctrl_to_be_opt_later; /* global knot ids */
+  int32_t marg_bias_param, marg_gravity_param, marg_t_offset_param;
+  /* execution */
+  int32_t device;        /* CUDA device ordinal */
+  void* stream;          /* cudaStream_t to run on; NULL = library-owned stream */
+  int32_t deterministic; /* 1 (default): fixed reduction order */
+  int32_t reserved[7];
+} clic_options;
+
+/* POD replacement of ceres::Solver::Summary (trajectory_estimator.h:225-226). */
+enum { CLIC_TERM_CONVERGENCE = 0, CLIC_TERM_NO_CONVERGENCE = 1, CLIC_TERM_FAILURE = 2 };
+enum {
+  CLIC_REASON_MAX_ITERATIONS = 0, CLIC_REASON_GRADIENT_TOL = 1, CLIC_REASON_PARAMETER_TOL = 2,
+  CLIC_REASON_FUNCTION_TOL = 3, CLIC_REASON_MIN_RADIUS = 4, CLIC_REASON_INVALID_STEPS = 5
+};
+typedef struct {
+  int32_t iterations;            /* LM iterations after iteration 0 (successful + unsuccessful) */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t termination;
+  int32_t termination_reason;
+  int32_t num_jacobian_evals;
+  int32_t num_residual_evals;
+  int32_t reserved;
+  double initial_cost, final_cost, fixed_cost;
+  double final_radius, final_gradient_max_norm;
+} clic_summary;
+
+/* Where each parameter block sits in H/b (-1 = constant / absent). */
+typedef struct {
+  int32_t D;                 /* number of columns */
+  int32_t first_free_knot;   /* local knot index k_f; columns 6*(k-k_f) .. +5 = dtheta, dp */
+  int32_t n_free_knots;
+  int32_t col_bias_gyro;     /* + 3*slot */
+  int32_t col_bias_accel;    /* + 3*slot */
+  int32_t col_t_offset[3];
+  int32_t col_inv_depth;     /* + free-landmark rank */
+  int32_t n_free_landmarks;
+} clic_layout;
+
+CLIC_API const char* clic_last_error(void);
+CLIC_API const char* clic_backend(void); /* "cuda-sm100a" or "oracle-cpu" */
+CLIC_API void clic_default_options(clic_options* opt);
+
+/* TrajectoryEstimator::TrajectoryEstimator (trajectory_estimator.cpp:142-170). */
+CLIC_API int clic_create(const clic_window_desc* window, const clic_options* opt, clic_estimator** out);
+CLIC_API int clic_destroy(clic_estimator* h);
+
+/* TrajectoryEstimator::SetFixedIndex (trajectory_estimator.h:140); idx is a GLOBAL knot id;
+ * knots with id <= idx are constant (trajectory_estimator.cpp:191-193). */
+CLIC_API int clic_set_fixed_index(clic_estimator* h, int32_t idx);
+
+/* AddLoamMeasurementAnalytic (trajectory_estimator.cpp:712-750), batched over n PointCorrespondence
+ * records given as one array per struct field (lidar_feature.h:110-123).  geo_plane / geo_normal /
+ * geo_point may each be NULL when no record of that type is present.  No loss (":743").
+ * marg_this_factor routes to the marginalization set with the |r|/w < 0.05 gate (":733-741"). */
+CLIC_API int clic_add_loam(clic_estimator* h, int64_t n, const double* t_point, const double* point /*3n*/,
+                           const int32_t* geo_type, const double* geo_plane /*4n*/,
+                           const double* geo_normal /*3n*/, const double* geo_point /*3n*/,
+                           const double S_GtoM[4], const double p_GinM[3], const double S_LtoI[4],
+                           const double p_LinI[3], double weight, int32_t marg_this_factor,
+                           int64_t* n_dropped);
+
+/* AddIMUMeasurementAnalytic (trajectory_estimator.cpp:369-455), batched over IMUData
+ * (parameter_struct.h:52-58).  All samples of one call share a bias slot, like the reference's
+ * call sites (trajectory_manager.cpp:731-735).  Loss CauchyLoss(marg ? 3 : 10) (":426-430"). */
+CLIC_API int clic_add_imu(clic_estimator* h, int64_t n, const double* timestamp, const double* gyro /*3n*/,
+                          const double* accel /*3n*/, int32_t bias_slot, const double info_vec[6],
+                          int32_t marg_this_factor, int64_t* n_dropped);
+
+/* AddBiasFactor (trajectory_estimator.cpp:457-498). */
+CLIC_API int clic_add_bias(clic_estimator* h, int32_t slot_i, int32_t slot_j, double dt,
+                           const double info_vec[6], int32_t marg_this_factor, int32_t marg_all_bias);
+
+/* AddImageFeatureAnalytic (trajectory_estimator.cpp:752-829), batched; landmark[i] indexes
+ * clic_window_desc::inv_depth.  Loss CauchyLoss(marg ? 1 : 2) (":806-810"). */
+CLIC_API int clic_add_image(clic_estimator* h, int64_t n, const double* t_i, const double* p_i /*3n*/,
+                            const double* t_j, const double* p_j /*3n*/, const int32_t* landmark,
+                            int32_t fixed_depth, int32_t marg_this_feature, int64_t* n_dropped);
+
+/* AddMarginalizationFactor (trajectory_estimator.cpp:854-866).  The prior stays owned by the caller.
+ * In marg mode (is_marg_state) drop_blocks lists the prior blocks (indices into the prior's block list)
+ * to marginalize, mirroring PrepareMarginalizationInfo(RType_Prior, ...) (trajectory_manager.cpp:352-375). */
+CLIC_API int clic_add_prior(clic_estimator* h, const clic_prior* prior, int32_t n_drop, const int32_t* drop_blocks);
+
+/* Column layout of H/b for the factors added so far. */
+CLIC_API int clic_get_layout(clic_estimator* h, clic_layout* out);
+
+/* One fused residual + Jacobian + normal-equation pass at the current state:
+ * H (D*D row-major, symmetric, both triangles), b (D), cost = 1/2 sum rho(|r|^2) (excluding factors whose
+ * parameters are all constant, reported separately as fixed_cost like Ceres).  Any pointer may be NULL. */
+CLIC_API int clic_evaluate(clic_estimator* h, double* H, double* b, double* cost, double* fixed_cost);
+
+/* Bit-exact indexing probe (SplineSegmentMeta::computeTIndexNs, spline_segment.h:67-84):
+ * for the factors of one stream, in add order: local knot index s (-1 if the factor was dropped) and u.
+ * stream: 0 LiDAR, 1 IMU, 2 image time i, 3 image time j.  IMU/image use the current time offset. */
+CLIC_API int clic_get_indices(clic_estimator* h, int32_t stream, int64_t capacity, int32_t* s, double* u, int64_t* n_out);
+
+/* TrajectoryEstimator::Solve (trajectory_estimator.cpp:987-1031): Ceres-1.14 LM trust region,
+ * (H + D^2/mu) step by dense Cholesky.  State is updated in place on the device. */
+CLIC_API int clic_solve(clic_estimator* h, int32_t max_iterations, clic_summary* summary);
+
+/* Read the (updated) state back; any pointer may be NULL. */
+CLIC_API int clic_read_state(clic_estimator* h, double* knot_q, double* knot_p, double* bias,
+                             double* t_offset_ns /*3*/, double* inv_depth);
+/* Overwrite the state (e.g. to re-run from the same start). */
+CLIC_API int clic_write_state(clic_estimator* h, const double* knot_q, const double* knot_p, const double* bias,
+                              const double* t_offset_ns /*3*/, const double* inv_depth);
+
+/* SaveMarginalizationInfo (trajectory_estimator.cpp:234-249) = preMarginalize + marginalize
+ * (marginalization_factor.cpp:94-116,150-276) over the factors added with marg_* = 1. */
+CLIC_API int clic_marginalize(clic_estimator* h, clic_prior** out);
+
+/* Prior objects (MarginalizationInfo after marginalize(): linearized_jacobians J0 (n x n), linearized_residuals r0,
+ * keep_block_size/idx/data, marginalization_factor.h:125-142). */
+CLIC_API int clic_prior_create(int32_t n, const double* J0 /*n*n row-major*/, const double* r0, int32_t n_blocks,
+                               const int32_t* kind, const int32_t* id, const double* x0 /*4 per block*/,
+                               clic_prior** out);
+CLIC_API int clic_prior_dims(const clic_prior* p, int32_t* n, int32_t* n_blocks, int32_t* m_dropped);
+CLIC_API int clic_prior_read(const clic_prior* p, double* J0, double* r0, int32_t* kind, int32_t* id,
+                             int32_t* tangent_offset, double* x0);
+/* A = J0^T J0 and g = J0^T r0 of the prior (what parity compares: J0 itself has sign/rotation freedom). */
+CLIC_API int clic_prior_normal(const clic_prior* p, double* A, double* g);
+CLIC_API int clic_prior_release(clic_prior* p);
+
+/* Multi-GPU: factors are sharded across ranks by the caller (each rank adds its shard);
+ * H|b|cost are summed with one all-reduce per pass.  id is an ncclUniqueId (128 bytes). */
+CLIC_API int clic_comm_unique_id(uint8_t id[128]);
+CLIC_API int clic_comm_init(clic_estimator* h, int32_t n_ranks, int32_t rank, const uint8_t id[128]);
+
+/* Measurement hooks used by bench.py: repeat the fused pass `reps` times on the handle's stream without
+ * host synchronisation in between (CUDA events are recorded by the caller on that stream). */
+CLIC_API int clic_linearize_async(clic_estimator* h, int32_t reps);
+CLIC_API int clic_synchronize(clic_estimator* h);
+CLIC_API int clic_num_kernel_launches(clic_estimator* h, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIC_CUDA_H_ */
