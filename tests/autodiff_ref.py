@@ -1,0 +1,167 @@
+"""Independent auto-diff lineage for the oracle: residual functions written from the reference's AUTO-DIFF factors
+(src/estimator/factor/auto_diff/*.h + src/spline/ceres_spline_helper.h:103-218), differentiated with
+torch-float64 autograd at delta = 0 of the tangent R <- R exp(dtheta), p <- p + dp.  This is the same property the
+reference's only test asserts (analytic == auto-diff, src/app/test_analytic_factor.cpp:846-900), with
+torch.autograd standing in for ceres::Jet.
+"""
+import numpy as np
+import torch
+
+torch.set_default_dtype(torch.float64)
+
+M_CUM = torch.tensor([[6, 0, 0, 0], [5, 3, -3, 1], [1, 3, 3, -2], [0, 0, 0, 1]], dtype=torch.float64) / 6.0
+M_PLAIN = torch.tensor([[1, -3, 3, -1], [4, 0, -6, 3], [1, 3, 3, -3], [0, 0, 0, 1]], dtype=torch.float64) / 6.0
+
+
+def qmul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return torch.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                        aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def qconj(a):
+    return a * torch.tensor([-1.0, -1.0, -1.0, 1.0])
+
+
+def qrot(q, v):
+    qv = q[:3]
+    uv = 2.0 * torch.linalg.cross(qv, v)
+    return v + q[3] * uv + torch.linalg.cross(qv, uv)
+
+
+def qexp(w):
+    th2 = (w * w).sum()
+    small = th2 < 1e-16
+    th2s = torch.where(small, torch.ones_like(th2), th2)
+    th = torch.sqrt(th2s)
+    imag = torch.where(small, 0.5 - th2 / 48.0, torch.sin(0.5 * th) / th)
+    real = torch.where(small, 1.0 - th2 / 8.0, torch.cos(0.5 * th))
+    return torch.cat([imag * w, real.reshape(1)])
+
+
+def qlog(q):
+    v, w = q[:3], q[3]
+    n2 = (v * v).sum()
+    small = n2 < 1e-24
+    n2s = torch.where(small, torch.ones_like(n2), n2)
+    n = torch.sqrt(n2s)
+    f = torch.where(small, 2.0 / w - 2.0 * n2 / (w * w * w), 2.0 * torch.atan(n / w) / n)
+    return f * v
+
+
+def pows(u, deriv):
+    one, zero = torch.ones_like(u), torch.zeros_like(u)
+    if deriv == 0:
+        return torch.stack([one, u, u * u, u * u * u])
+    if deriv == 1:
+        return torch.stack([zero, one, 2 * u, 3 * u * u])
+    if deriv == 2:
+        return torch.stack([zero, zero, 2 * one, 6 * u])
+    return torch.stack([zero, zero, zero, 6 * one])
+
+
+class Spline:
+    """q: (K,4) perturbed quaternions (list of tensors), p: (K,3)."""
+
+    def __init__(self, t0_ns, dt_ns, q, p):
+        self.t0_ns, self.dt_ns, self.q, self.p = t0_ns, dt_ns, q, p
+        self.inv_dt = 1e9 / dt_ns
+
+    def su(self, t_ns_int, t_frac=None):
+        """t = t_ns_int (python int) + t_frac (differentiable ns)."""
+        st = t_ns_int - self.t0_ns
+        s = st // self.dt_ns
+        u = torch.tensor(float(st % self.dt_ns) / float(self.dt_ns))
+        if t_frac is not None:
+            u = u + t_frac / float(self.dt_ns)
+        return s, u
+
+    def pos(self, s, u, deriv=0):
+        c = (M_PLAIN @ pows(u, deriv)) * self.inv_dt ** deriv
+        return sum(c[i] * self.p[s + i] for i in range(4))
+
+    def rot_vel(self, s, u):
+        """R(t) quaternion and body angular velocity (ceres_spline_helper.h evaluate_lie)."""
+        c = M_CUM @ pows(u, 0)
+        dc = (M_CUM @ pows(u, 1)) * self.inv_dt
+        r = self.q[s]
+        w = torch.zeros(3)
+        for i in range(3):
+            d = qlog(qmul(qconj(self.q[s + i]), self.q[s + i + 1]))
+            e = qexp(c[i + 1] * d)
+            r = qmul(r, e)
+            w = qrot(qconj(e), w) + dc[i + 1] * d
+        return r, w
+
+
+def perturbed_spline(t0_ns, dt_ns, knot_q, knot_p, dth, dp):
+    K = knot_q.shape[0]
+    q = [qmul(torch.tensor(knot_q[k]), qexp(dth[k])) for k in range(K)]
+    p = [torch.tensor(knot_p[k]) + dp[k] for k in range(K)]
+    return Spline(t0_ns, dt_ns, q, p)
+
+
+def jac(fn, K, extras):
+    """Jacobian of fn(dth (K,3), dp (K,3), *extras) at dth = dp = 0 and the given extra values.
+    Returns residual, J_knots (m, K, 6) [dtheta, dp per knot], [J_extra...]."""
+    dth0, dp0 = torch.zeros(K, 3), torch.zeros(K, 3)
+    ex = [torch.tensor(np.atleast_1d(np.asarray(e, np.float64))) for e in extras]
+    r = fn(dth0, dp0, *ex)
+    J = torch.autograd.functional.jacobian(fn, (dth0, dp0, *ex))
+    Jk = torch.cat([J[0], J[1]], dim=-1)  # (m, K, 6)
+    return r.detach().numpy(), Jk.detach().numpy(), [j.detach().numpy() for j in J[2:]]
+
+
+# ---- residual definitions ----
+def lidar_residual(win, t_ns, point, geo_type, geo_plane, geo_normal, geo_point, S_GtoM, p_GinM, S_LtoI, p_LinI, weight):
+    """Point-to-plane / point-to-line distance (same geometry as auto_diff/lidar_feature_factor.h:84-104 with the map
+    frame given explicitly as in analytic LoamFeatureFactor)."""
+    def fn(dth, dp):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        s, u = sp.su(t_ns)
+        R, _ = sp.rot_vel(s, u)
+        p_I = qrot(torch.tensor(S_LtoI), torch.tensor(point)) + torch.tensor(p_LinI)
+        p_M = qrot(torch.tensor(S_GtoM), qrot(R, p_I) + sp.pos(s, u)) + torch.tensor(p_GinM)
+        if geo_type == 1:
+            dist = (p_M * torch.tensor(geo_plane[:3])).sum() + geo_plane[3]
+        else:
+            dist = torch.linalg.norm(torch.linalg.cross(p_M - torch.tensor(geo_point), torch.tensor(geo_normal)))
+        return (weight * dist).reshape(1)
+    return fn
+
+
+def imu_residual(win, t_ns, gyro, accel, info_vec):
+    """auto_diff/trajectory_value_factor.h:237-272; extras = (gyro_bias, accel_bias, gravity, t_offset_ns).
+    The offset is split like the analytic factor: integer part moves the index, the autograd variable is the
+    perturbation around it."""
+    def fn(dth, dp, bg, ba, g, toff):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        toff_int = int(toff.detach()[0])  # (int64) truncation, trajectory_value_factor.h:175
+        s, u = sp.su(t_ns + toff_int, toff[0] - toff.detach()[0])
+        R, w = sp.rot_vel(s, u)
+        a_w = sp.pos(s, u, 2)
+        r_g = w - torch.tensor(gyro) + bg
+        r_a = qrot(qconj(R), a_w + g) - torch.tensor(accel) + ba
+        return torch.cat([r_g, r_a]) * torch.tensor(info_vec)
+    return fn
+
+
+def image_residual(win, ti_ns, p_i, tj_ns, p_j, S_CtoI, p_CinI, sqrt_info=450.0 / 1.5):
+    """auto_diff/image_feature_factor.h:48-101; extras = (inv_depth, t_offset_ns)."""
+    def fn(dth, dp, rho, toff):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        toff_int = int(toff.detach()[0])
+        frac = toff[0] - toff.detach()[0]
+        si, ui = sp.su(ti_ns + toff_int, frac)
+        sj, uj = sp.su(tj_ns + toff_int, frac)
+        Ri, _ = sp.rot_vel(si, ui)
+        Rj, _ = sp.rot_vel(sj, uj)
+        qc = torch.tensor(S_CtoI)
+        x_ci = torch.tensor(p_i) / rho[0]
+        p_Ii = qrot(qc, x_ci) + torch.tensor(p_CinI)
+        p_G = qrot(Ri, p_Ii) + sp.pos(si, ui)
+        p_Ij = qrot(qconj(Rj), p_G - sp.pos(sj, uj))
+        x_j = qrot(qconj(qc), p_Ij - torch.tensor(p_CinI))
+        return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2]))
+    return fn

@@ -1,0 +1,150 @@
+"""Pins the oracle with the reference test's own property: analytic Jacobian == auto-diff Jacobian (max-abs 1e-6)
+on the hard-coded inputs of src/app/test_analytic_factor.cpp GenerateData (:903-1026), over a random trajectory
+with the statistics of Trajectory(0.1)+genRandomTrajectory(8) (:61-62).  Auto-diff = torch-f64 autograd of
+residuals written from the reference's auto_diff factors (tests/autodiff_ref.py).  CPU only."""
+import numpy as np
+import pytest
+
+import autodiff_ref as AD
+import oracle_lib
+from clic_b200 import estimator as E
+from clic_b200 import synthetic as S
+from clic_b200._abi import GEO_LINE, GEO_PLANE
+
+TOL = 1e-6  # test_analytic_factor.cpp:865
+
+
+def reference_test_trajectory(seed):
+    """Trajectory(0.1) seeds N=4 identity knots (trajectory.h:52-54), genRandomTrajectory(8) appends 8 random ones."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q = np.concatenate([np.tile([0, 0, 0, 1.0], (4, 1)), S.so3_exp(rng.uniform(-np.pi, np.pi, size=(8, 3)))])
+    p = np.concatenate([np.zeros((4, 3)), rng.uniform(-5, 5, size=(8, 3))])
+    S_LtoI = S.so3_exp(rng.uniform(-np.pi, np.pi, size=3))
+    S_CtoI = S.so3_exp(rng.uniform(-np.pi, np.pi, size=3))
+    return E.Window(t0_ns=0, dt_ns=100_000_000, knot_q=q, knot_p=p, S_LtoI=S_LtoI, p_LinI=np.array([0.15, 0.52, 0.35]),
+                    S_CtoI=S_CtoI, p_CinI=np.array([0.1, 0.2, 0.3]), t_offset_ns=np.array([1.0e6, 0.0, 1.0e6]),
+                    gravity=np.array([0, 0, 9.8]), bias=np.array([[0.1, 0.2, 0.3, 0.1, 0.2, 0.3]]),
+                    inv_depth=np.array([0.51]))
+
+
+def win_dict(w):
+    return dict(t0_ns=w.t0_ns, dt_ns=w.dt_ns, knot_q=w.knot_q, knot_p=w.knot_p)
+
+
+def knot_cols(Jk, layout):
+    """(m, K, 6) -> (m, 6*n_free) in canonical order."""
+    return Jk[:, layout.first_free_knot:, :].reshape(Jk.shape[0], -1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("geo", [GEO_PLANE, GEO_LINE])
+def test_loam_feature_factor(oracle, seed, geo):
+    w = reference_test_trajectory(seed)
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    plane = np.array([1, 2, 3, 4.0]) / np.linalg.norm([1, 2, 3, 4.0])
+    normal = np.array([3, 2, 1.0]) / np.linalg.norm([3, 2, 1.0])
+    gpoint = np.array([1, 2, 3.0])
+    point = np.array([1, 2, 3.0])
+    ident, zero = np.array([0, 0, 0, 1.0]), np.zeros(3)
+    est.AddLoamMeasurementAnalytic([0.55], [point], [geo], [plane], [normal], [gpoint], ident, zero, w.S_LtoI, w.p_LinI,
+                                   1.3)
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.lidar_residual(win_dict(w), int(0.55 * 1e9), point, geo, plane, normal, gpoint, ident, zero, w.S_LtoI,
+                           w.p_LinI, 1.3)
+    r_ad, Jk, _ = AD.jac(fn, w.n_knots, [])
+    assert np.allclose(r, r_ad, atol=1e-9)
+    assert np.abs(J - knot_cols(Jk, L)).max() < TOL
+    # and b = J^T r, H = J^T J of the single factor
+    H, b, cost, _ = est.Evaluate()
+    assert np.allclose(H, J.T @ J, rtol=1e-12, atol=1e-12)
+    assert np.allclose(b, J.T @ r, rtol=1e-12, atol=1e-12)
+    assert np.isclose(cost, 0.5 * float(r @ r))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_imu_factor(oracle, seed):
+    w = reference_test_trajectory(seed)
+    opt = E.default_options(oracle)
+    opt.lock_ab = opt.lock_wb = 0
+    opt.lock_t_offset[0] = 0
+    opt.t_offset_padding_ns = 100_000_000  # t_padding_ns_ = 1e8 (:907)
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    gyro, accel = np.array([0.1, 0.2, 0.3]), np.array([0.1, 0.2, -9.8])
+    info = np.full(6, 3.4)
+    assert est.AddIMUMeasurementAnalytic([0.55], [gyro], [accel], 0, info) == 0
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.imu_residual(win_dict(w), int(0.55 * 1e9), gyro, accel, info)
+    r_ad, Jk, Jx = AD.jac(fn, w.n_knots, [w.bias[0, :3], w.bias[0, 3:], w.gravity, [w.t_offset_ns[0]]])
+    assert np.allclose(r, r_ad, atol=1e-8)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL
+    assert np.abs(J[:, L.col_bias_gyro:L.col_bias_gyro + 3] - Jx[0]).max() < TOL
+    assert np.abs(J[:, L.col_bias_accel:L.col_bias_accel + 3] - Jx[1]).max() < TOL
+    assert np.abs(J[:, L.col_t_offset[0]] - Jx[3][:, 0]).max() < TOL
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("case", [0, 1])
+def test_image_feature_factor(oracle, seed, case):
+    w = reference_test_trajectory(seed)
+    ti, tj = [(0.13, 0.34), (0.11, 0.63)][case]  # :936-944
+    pi, pj = [(np.array([1, 2, 1.0]), np.array([4, 5, 1.0])), (np.array([4, 5, 1.0]), np.array([1, 2, 1.0]))][case]
+    opt = E.default_options(oracle)
+    opt.lock_t_offset[2] = 0
+    opt.t_offset_padding_ns = 100_000_000
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    assert est.AddImageFeatureAnalytic([ti], [pi], [tj], [pj], [0], fixed_depth=False) == 0
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.image_residual(win_dict(w), int(ti * 1e9), pi, int(tj * 1e9), pj, w.S_CtoI, w.p_CinI)
+    r_ad, Jk, Jx = AD.jac(fn, w.n_knots, [[w.inv_depth[0]], [w.t_offset_ns[2]]])
+    scale = max(1.0, np.abs(Jk).max())
+    assert np.allclose(r, r_ad, rtol=1e-9, atol=1e-7)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * scale
+    assert np.abs(J[:, L.col_inv_depth] - Jx[0][:, 0]).max() < TOL * scale
+    assert np.abs(J[:, L.col_t_offset[2]] - Jx[1][:, 0]).max() < TOL * scale
+
+
+def test_synthetic_window_factors(oracle):
+    """Same property on a realistic (small-rotation-increment) window, every factor type, a few factors each."""
+    sw = S.make_window(10, n_lidar=12, n_imu=6, n_landmarks=3, obs_per_landmark=3, line_fraction=0.5, seed=7)
+    w = sw.window
+    opt = E.default_options(oracle)
+    opt.lock_ab = opt.lock_wb = 0
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    S.add_all_factors(est, sw, bias_factor=False)
+    L = est.layout()
+    wd = win_dict(w)
+    blk = 0
+    Ld = sw.lidar
+    for i in range(len(Ld["t_point"])):
+        r, J = oracle_lib.block_jacobian(oracle, est, blk)
+        fn = AD.lidar_residual(wd, int(Ld["t_point"][i] * 1e9), Ld["point"][i], int(Ld["geo_type"][i]),
+                               Ld["geo_plane"][i], Ld["geo_normal"][i], Ld["geo_point"][i], Ld["S_GtoM"], Ld["p_GinM"],
+                               Ld["S_LtoI"], Ld["p_LinI"], Ld["weight"])
+        r_ad, Jk, _ = AD.jac(fn, w.n_knots, [])
+        assert np.allclose(r, r_ad, atol=1e-8)
+        assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * max(1, np.abs(J).max())
+        blk += 1
+    I = sw.image
+    for i in range(len(I["t_i"])):
+        r, J = oracle_lib.block_jacobian(oracle, est, blk)
+        fn = AD.image_residual(wd, int(I["t_i"][i] * 1e9), I["p_i"][i], int(I["t_j"][i] * 1e9), I["p_j"][i], w.S_CtoI,
+                               w.p_CinI)
+        r_ad, Jk, _ = AD.jac(fn, w.n_knots, [[w.inv_depth[I["landmark"][i]]], [0.0]])
+        assert np.allclose(r, r_ad, rtol=1e-8, atol=1e-6)
+        assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * max(1, np.abs(J).max())
+        blk += 1
+    M = sw.imu
+    for i in range(len(M["timestamp"])):
+        r, J = oracle_lib.block_jacobian(oracle, est, blk)
+        fn = AD.imu_residual(wd, int(M["timestamp"][i] * 1e9), M["gyro"][i], M["accel"][i], M["info_vec"])
+        slot = M["bias_slot"]
+        r_ad, Jk, Jx = AD.jac(fn, w.n_knots, [w.bias[slot, :3], w.bias[slot, 3:], w.gravity, [0.0]])
+        sc = max(1, np.abs(J).max())
+        assert np.allclose(r, r_ad, rtol=1e-9, atol=1e-6)
+        assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * sc
+        c = L.col_bias_gyro + 3 * slot
+        assert np.abs(J[:, c:c + 3] - Jx[0]).max() < TOL * sc
+        blk += 1
