@@ -1,0 +1,321 @@
+// Per-factor residual + analytic Jacobian rows, restructured for one-factor-per-thread evaluation on sm_100a.
+//
+// Reference arithmetic being replaced:
+//   So3SplineView::EvaluateRp / EvaluateRTp / VelocityBody / accelerationBody   analytic_diff/so3_spline_view.h:127-439
+//   RdSplineView::evaluate<D>                                                    analytic_diff/rd_spline_view.h:59-86
+//   SplitSpineView::Evaluate                                                     analytic_diff/split_spline_view.h:56-188
+//   LoamFeatureFactor / IMUFactor / ImageFeatureFactor ::Evaluate                lidar_feature_factor.h:65-159,
+//                                                                                trajectory_value_factor.h:162-294,
+//                                                                                image_feature_factor.h:67-268
+// What is different from a transliteration:
+//   * everything that depends on the knots only — delta_k = log(R_k^-1 R_k+1), |delta_k|, its unit axis and
+//     Jr^-1(delta_k) — is computed once per knot pair (PairData, staged in shared memory) instead of per factor;
+//   * exp(-lambda*delta) and lambda*Jr(+-lambda*delta) are written on the unit axis of delta_k, so a factor needs
+//     three sincos and no sqrt / division;
+//   * the LiDAR Jacobian chain is evaluated vector-first (a 1x3 row pushed through the 3x3 chain), never
+//     forming the 3x3 d_val_d_knot matrices.
+// Output of every evaluator is a set of "rows" of the local Jacobian J~ (loss-corrected) in the local column
+// order [knot s: dtheta(3) dp(3) | knot s+1 | knot s+2 | knot s+3 | extras... | r~], written through a Sink so the
+// same code feeds shared memory (GPU) or a plain array (host emulation test).
+#pragma once
+#include "clic_math.cuh"
+
+namespace clic {
+
+// Per knot pair k -> k+1.  17 doubles.
+struct PairData {
+  double delta[3];
+  double theta;
+  double inv_theta;  // 0 when theta == 0 (identical knots): every use degrades to the exact theta = 0 limit
+  double nhat[3];
+  double Jrinv[9];   // rightJacobianInvSO3(delta), row-major
+};
+constexpr int kPairDoubles = 17;
+
+CLIC_HD void compute_pair(const double* q0, const double* q1, PairData* P) {
+  Q4 a; a.x = q0[0]; a.y = q0[1]; a.z = q0[2]; a.w = q0[3];
+  Q4 b; b.x = q1[0]; b.y = q1[1]; b.z = q1[2]; b.w = q1[3];
+  V3 d = so3_log(so3_mul(qconj(a), b));  // (R0.inverse() * R1).log(), so3_spline_view.h:151
+  double th = sqrt(dot(d, d));
+  double inv = th > 0.0 ? 1.0 / th : 0.0;
+  P->delta[0] = d.x; P->delta[1] = d.y; P->delta[2] = d.z;
+  P->theta = th;
+  P->inv_theta = inv;
+  P->nhat[0] = d.x * inv; P->nhat[1] = d.y * inv; P->nhat[2] = d.z * inv;
+  M3 J = right_jacobian_inv(d);
+#pragma unroll
+  for (int i = 0; i < 9; i++) P->Jrinv[i] = J.m[i];
+}
+
+// Read-only view of the window state staged on chip.
+struct WindowView {
+  const double* kq;      // K*4
+  const double* kp;      // K*3
+  const PairData* pair;  // K-1
+};
+
+CLIC_HD Q4 ldq(const double* p) { Q4 q; q.x = p[0]; q.y = p[1]; q.z = p[2]; q.w = p[3]; return q; }
+CLIC_HD V3 ldv(const double* p) { return mk(p[0], p[1], p[2]); }
+
+// One cumulative-spline step on the unit axis: returns exp(-lambda*delta_k) and the two scalars of
+// lambda*Jr(+-lambda*delta_k) = lambda I -+ ca hat(n) + cb hat(n)^2   (ca = (1-cos th)/theta_k, cb = lambda - sin th/theta_k)
+CLIC_HD Q4 step_exp_neg(const PairData& P, double lam, double* ca, double* cb) {
+  double th = lam * P.theta;
+  double s, c;
+  sincos_hd(0.5 * th, &s, &c);
+  *ca = (2.0 * s * s) * P.inv_theta;
+  *cb = lam - (2.0 * s * c) * P.inv_theta;
+  Q4 e; e.x = -s * P.nhat[0]; e.y = -s * P.nhat[1]; e.z = -s * P.nhat[2]; e.w = c;
+  return e;
+}
+// row-vector w times lambda*Jr(sign*lambda*delta):  w*hat(n) = w x n
+CLIC_HD V3 row_times_lamJr(V3 w, const PairData& P, double lam, double ca, double cb, double sign) {
+  V3 n = ldv(P.nhat);
+  V3 x1 = cross(w, n);
+  V3 x2 = cross(x1, n);
+  return fma3(cb, x2, fma3(-sign * ca, x1, lam * w));
+}
+// matrix lambda*Jr(sign*lambda*delta)
+CLIC_HD M3 lamJr(const PairData& P, double lam, double ca, double cb, double sign) {
+  M3 K = hat(ldv(P.nhat));
+  M3 K2 = mmul(K, K);
+  M3 r;
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.m[i] = -sign * ca * K.m[i] + cb * K2.m[i];
+  r.m[0] += lam; r.m[4] += lam; r.m[8] += lam;
+  return r;
+}
+
+struct LoamShared {  // arguments of AddLoamMeasurementAnalytic shared by a batch (trajectory_estimator.cpp:712-716)
+  Q4 S_GtoM; V3 p_GinM; Q4 S_LtoI; V3 p_LinI; double weight;
+};
+
+// LoamFeatureFactor::Evaluate.  geo = plane (n.x n.y n.z d) or line (point xyz, direction xyz).
+// J[24] gets the local row [knot: dtheta(3) dp(3)] x 4; *r the weighted residual.  No loss (":743").
+CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plane, const double geo[6],
+                       const LoamShared& sh, bool want_jac, double* r_out, double J[24]) {
+  double lam[4], c[4];
+  blend_cum(u, lam);
+  blend_plain(u, c);
+  Q4 acc; acc.x = acc.y = acc.z = 0.0; acc.w = 1.0;
+  Q4 A[3];
+  double ca[3], cb[3];
+#pragma unroll
+  for (int i = 2; i >= 0; i--) {
+    Q4 e = step_exp_neg(W.pair[s + i], lam[i + 1], &ca[i], &cb[i]);
+    acc = qmul(acc, e);  // A_accum_inv *= exp(-kdelta)
+    A[i] = acc;
+  }
+  Q4 R = qmul(ldq(W.kq + 4 * s), qconj(acc));  // Ri * A_accum_inv.inverse()
+  V3 p_I = qrot(sh.S_LtoI, pL) + sh.p_LinI;
+  V3 pos = mk(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 4; i++) pos = fma3(c[i], ldv(W.kp + 3 * (s + i)), pos);
+  V3 p_M = qrot(sh.S_GtoM, qrot(R, p_I) + pos) + sh.p_GinM;
+  V3 Jpi;
+  double r;
+  if (is_plane) {
+    Jpi = mk(geo[0], geo[1], geo[2]);
+    r = dot(p_M, Jpi) + geo[3];
+  } else {
+    V3 gl = mk(geo[3], geo[4], geo[5]);
+    V3 dv = cross(p_M - mk(geo[0], geo[1], geo[2]), gl);
+    r = sqrt(dot(dv, dv));
+    Jpi = cross((-1.0 / r) * dv, gl);  // -dist_vec^T / r * hat(geo_normal), lidar_feature_factor.h:101
+  }
+  *r_out = r * sh.weight;
+  if (!want_jac) return;
+  V3 g = qrot_inv(sh.S_GtoM, Jpi);  // (J_pi^T S_GtoM)^T
+  V3 m = qrot_inv(R, g);            // (J_pi^T S_GtoM R)^T
+  V3 v = cross(p_I, m);             // J_pi^T (-S_GtoM R hat(p_I)) = p_I x m
+  // rows of d_val_d_knot chain, vector-first (so3_spline_view.h:170-180)
+  V3 w0 = qrot_inv(A[0], v), w1 = qrot_inv(A[1], v), w2 = qrot_inv(A[2], v);
+  V3 t0 = row_times_lamJr(w1, W.pair[s + 0], lam[1], ca[0], cb[0], +1.0);
+  V3 t1 = row_times_lamJr(w2, W.pair[s + 1], lam[2], ca[1], cb[1], +1.0);
+  V3 t2 = row_times_lamJr(v, W.pair[s + 2], lam[3], ca[2], cb[2], +1.0);
+  V3 j0 = w0 - vmat_t(t0, W.pair[s + 0].Jrinv);
+  V3 j1 = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
+  V3 j2 = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
+  V3 j3 = vmat(t2, W.pair[s + 2].Jrinv);
+  const double w = sh.weight;
+  J[0] = w * j0.x; J[1] = w * j0.y; J[2] = w * j0.z;
+  J[6] = w * j1.x; J[7] = w * j1.y; J[8] = w * j1.z;
+  J[12] = w * j2.x; J[13] = w * j2.y; J[14] = w * j2.z;
+  J[18] = w * j3.x; J[19] = w * j3.y; J[20] = w * j3.z;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    double wc = w * c[k];
+    J[6 * k + 3] = wc * g.x; J[6 * k + 4] = wc * g.y; J[6 * k + 5] = wc * g.z;
+  }
+}
+
+// ceres::CauchyLoss(a) + Corrector (marginalization_factor.cpp:38-61): rho'' < 0 always, so the correction is the
+// pure sqrt(rho') scaling of r and J.  Returns the scale; *rho = rho(s).
+CLIC_HD double cauchy_scale(double sq_norm, double a, double* rho) {
+  double b = a * a, cinv = 1.0 / b;
+  double sum = 1.0 + sq_norm * cinv;
+  double inv = 1.0 / sum;
+  *rho = b * log(sum);
+  return sqrt(inv);
+}
+
+struct ImuShared {  // per AddIMUMeasurementAnalytic batch
+  double info[6];
+  V3 bg, ba, gravity;
+  double loss_a;     // Cauchy parameter (10, or 3 when marginalised); <= 0: no loss
+  double inv_dt;     // 1e9 / dt_ns
+};
+
+// IMUFactor::Evaluate on SplitSpineView::Evaluate.  Emits 6 rows of NC = 32 (solve) or 40 (marg: + gravity) columns:
+//   [knot cols 0..23 | bg 24..26 | ba 27..29 | (solve) toff 30, r 31 | (marg) gravity 30..32, toff 33, r 34, pad]
+// through sink.put(row, col, value) (all columns of a row are written, zeros included), then sink.row_done(row).
+// Returns rho(|r|^2) (or |r|^2 without loss).
+template <bool MARG, class Sink>
+CLIC_HD double imu_eval(const WindowView& W, int s, double u, V3 gyro_m, V3 accel_m, const ImuShared& sh,
+                        bool want_jac, Sink& sink) {
+  constexpr int C_TOFF = MARG ? 33 : 30, C_R = MARG ? 34 : 31, NC = MARG ? 40 : 32;
+  double lamR[4], lamW[4], lamA[4];
+  blend_cum(u, lamR);
+  blend_cum_d1(u, sh.inv_dt, lamW);
+  blend_plain_d2(u, sh.inv_dt * sh.inv_dt, lamA);
+  V3 acc_w = mk(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc_w = fma3(lamA[i], ldv(W.kp + 3 * (s + i)), acc_w);
+  Q4 acc; acc.x = acc.y = acc.z = 0.0; acc.w = 1.0;
+  Q4 Ainv[3];
+  Q4 Aq[3];
+  double ca[3], cb[3];
+#pragma unroll
+  for (int i = 2; i >= 0; i--) {
+    Ainv[i] = step_exp_neg(W.pair[s + i], lamR[i + 1], &ca[i], &cb[i]);
+    acc = qmul(acc, Ainv[i]);
+    Aq[i] = acc;
+  }
+  V3 omega[4];
+  omega[0] = mk(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) omega[i + 1] = fma3(lamW[i + 1], ldv(W.pair[s + i].delta), qrot(Ainv[i], omega[i]));
+  Q4 q_s = ldq(W.kq + 4 * s);
+  Q4 R_inv = qmul(acc, qconj(q_s));
+  V3 ag = acc_w + sh.gravity;
+  V3 accel_b = qrot(R_inv, ag);
+  double res[6];
+  {
+    V3 rg = omega[3] - (gyro_m - sh.bg);
+    V3 ra = accel_b - (accel_m - sh.ba);
+    res[0] = sh.info[0] * rg.x; res[1] = sh.info[1] * rg.y; res[2] = sh.info[2] * rg.z;
+    res[3] = sh.info[3] * ra.x; res[4] = sh.info[4] * ra.y; res[5] = sh.info[5] * ra.z;
+  }
+  double sq = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) sq += res[i] * res[i];
+  double rho = sq, sc = 1.0;
+  if (sh.loss_a > 0) sc = cauchy_scale(sq, sh.loss_a, &rho);
+  if (!want_jac) return rho;
+
+  M3 Apost[4];
+#pragma unroll
+  for (int i = 0; i < 3; i++) Apost[i] = qmat(Aq[i]);
+  Apost[3].m[0] = Apost[3].m[4] = Apost[3].m[8] = 1.0;
+  Apost[3].m[1] = Apost[3].m[2] = Apost[3].m[3] = Apost[3].m[5] = Apost[3].m[6] = Apost[3].m[7] = 0.0;
+  M3 LJ[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) LJ[i] = lamJr(W.pair[s + i], lamR[i + 1], ca[i], cb[i], -1.0);  // lambda*Jr(-k_delta)
+  // d(omega)/d(delta_i)  (split_spline_view.h:140-150)
+  M3 dW[3];
+  dW[0] = mscale(lamW[1], Apost[1]);
+#pragma unroll
+  for (int i = 1; i < 3; i++)
+    dW[i] = madd(mmul(mmul(Apost[i], hat(omega[i])), LJ[i]), mscale(lamW[i + 1], Apost[i + 1]));
+  // d(accel)/d(delta_i)  (":160-186")
+  M3 Rinv_m = qmat(R_inv);
+  M3 lhs = mmul(Rinv_m, hat(ag));
+  M3 Racc = qmat(q_s);
+  M3 dA[3];
+  M3 lhsR0 = mmul(lhs, Racc);
+  dA[0] = mmul(lhsR0, LJ[0]);
+#pragma unroll
+  for (int i = 1; i < 3; i++) {
+    Racc = mmul_t(Racc, qmat(Ainv[i - 1]));  // R_accum[i] = R_accum[i-1] * A_rot_inv[i-1]^T
+    dA[i] = mmul(mmul(lhs, Racc), LJ[i]);
+  }
+  // time-offset column (trajectory_value_factor.h:268-291)
+  V3 jt_top = mk(0, 0, 0), jt_bot = mk(0, 0, 0);
+  {
+    double lamWW[4];
+    blend_cum_d2(u, sh.inv_dt * sh.inv_dt, lamWW);
+    V3 rv = mk(0, 0, 0), ra = mk(0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // So3SplineView::accelerationBody, so3_spline_view.h:396-439
+      V3 d = ldv(W.pair[s + i].delta);
+      rv = qrot(Ainv[i], rv);
+      V3 vc = lamW[i + 1] * d;
+      rv = rv + vc;
+      ra = qrot(Ainv[i], ra);
+      ra = ra + (lamWW[i + 1] * d + cross(rv, vc));
+    }
+    double cj[4];
+    blend_plain_d3(sh.inv_dt * sh.inv_dt * sh.inv_dt, cj);
+    V3 jerk = mk(0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 4; i++) jerk = fma3(cj[i], ldv(W.kp + 3 * (s + i)), jerk);
+    M3 rot = mtrans(Rinv_m);
+    M3 gh = hat(omega[3]);
+    M3 rot_dot = mmul(rot, gh);
+    M3 T1 = mmul(mtrans(rot_dot), rot_dot);
+    M3 T2 = mmul(mtrans(rot), madd(mmul(rot_dot, gh), mmul(rot, hat(ra))));
+    jt_top = mk(T1.m[7] + T2.m[7], T1.m[2] + T2.m[2], T1.m[3] + T2.m[3]);  // vee = (m21, m02, m10)
+    jt_bot = mvec(mmul(mtrans(rot_dot), rot), accel_b) + mvec(mtrans(rot), jerk);
+  }
+  // knot rotation blocks: J_rot[k] for k = 0..3, 3x3 each for gyro and accel rows
+  // [0] = X - d0 Jri0^T ; [1] = d0 Jri0 - d1 Jri1^T ; [2] = d1 Jri1 - d2 Jri2^T ; [3] = d2 Jri2   (X = 0 gyro, lhs*R0 accel)
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const M3* d = half == 0 ? dW : dA;
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+      const int row = half * 3 + rr;
+      const double sI = sc * sh.info[row];
+      V3 dr0 = mk(d[0].m[rr * 3], d[0].m[rr * 3 + 1], d[0].m[rr * 3 + 2]);
+      V3 dr1 = mk(d[1].m[rr * 3], d[1].m[rr * 3 + 1], d[1].m[rr * 3 + 2]);
+      V3 dr2 = mk(d[2].m[rr * 3], d[2].m[rr * 3 + 1], d[2].m[rr * 3 + 2]);
+      V3 x = half == 0 ? mk(0, 0, 0) : mk(lhsR0.m[rr * 3], lhsR0.m[rr * 3 + 1], lhsR0.m[rr * 3 + 2]);
+      V3 j[4];
+      j[0] = x - vmat_t(dr0, W.pair[s + 0].Jrinv);
+      j[1] = vmat(dr0, W.pair[s + 0].Jrinv) - vmat_t(dr1, W.pair[s + 1].Jrinv);
+      j[2] = vmat(dr1, W.pair[s + 1].Jrinv) - vmat_t(dr2, W.pair[s + 2].Jrinv);
+      j[3] = vmat(dr2, W.pair[s + 2].Jrinv);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        sink.put(row, 6 * k + 0, sI * j[k].x);
+        sink.put(row, 6 * k + 1, sI * j[k].y);
+        sink.put(row, 6 * k + 2, sI * j[k].z);
+        // position blocks: accel rows only, lambda_a[k] * R_inv (trajectory_value_factor.h:230-242)
+        double pc = half == 0 ? 0.0 : sI * lamA[k];
+        sink.put(row, 6 * k + 3, pc * Rinv_m.m[rr * 3 + 0]);
+        sink.put(row, 6 * k + 4, pc * Rinv_m.m[rr * 3 + 1]);
+        sink.put(row, 6 * k + 5, pc * Rinv_m.m[rr * 3 + 2]);
+      }
+      // bias blocks (":245-257")
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        sink.put(row, 24 + cc, (half == 0 && cc == rr) ? sI : 0.0);
+        sink.put(row, 27 + cc, (half == 1 && cc == rr) ? sI : 0.0);
+      }
+      if (MARG) {  // gravity block (":260-266"), ambient 3 columns
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) sink.put(row, 30 + cc, half == 1 ? sI * Rinv_m.m[rr * 3 + cc] : 0.0);
+      }
+      double jt = half == 0 ? (rr == 0 ? jt_top.x : rr == 1 ? jt_top.y : jt_top.z)
+                            : (rr == 0 ? jt_bot.x : rr == 1 ? jt_bot.y : jt_bot.z);
+      sink.put(row, C_TOFF, (1e-9 * sI) * jt);
+      sink.put(row, C_R, sc * res[row]);
+#pragma unroll
+      for (int cc = C_R + 1; cc < NC; cc++) sink.put(row, cc, 0.0);
+      sink.row_done(row);
+    }
+  }
+  return rho;
+}
+
+}  // namespace clic

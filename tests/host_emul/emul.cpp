@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE ONLY: compiles the product's __host__ __device__ factor math (clic_b200/csrc/*.cuh) with g++
+// so the CPU-only build box can check it against the oracle before GPU time is spent.  Never shipped or loaded
+// by the product.
+#include <cstring>
+#include <vector>
+
+#include "../../clic_b200/csrc/factor_eval.cuh"
+
+using namespace clic;
+
+struct HostWindow {
+  std::vector<PairData> pair;
+  WindowView view;
+  HostWindow(int K, const double* kq, const double* kp) : pair(K - 1) {
+    for (int k = 0; k + 1 < K; k++) compute_pair(kq + 4 * k, kq + 4 * (k + 1), &pair[k]);
+    view.kq = kq;
+    view.kp = kp;
+    view.pair = pair.data();
+  }
+};
+
+struct ArraySink {
+  double* out;
+  int nc;
+  void put(int row, int col, double v) { out[row * nc + col] = v; }
+  void row_done(int) {}
+};
+
+extern "C" {
+
+__attribute__((visibility("default"))) int emul_loam(int K, const double* kq, const double* kp, int64_t t0_ns,
+                                                      int64_t dt_ns, int64_t t_ns, const double* pL, int is_plane,
+                                                      const double* geo, const double* S_GtoM, const double* p_GinM,
+                                                      const double* S_LtoI, const double* p_LinI, double weight,
+                                                      double* r, double* J, int* s_out, double* u_out) {
+  HostWindow W(K, kq, kp);
+  int s;
+  double u;
+  if (!index_ns(t_ns, t0_ns, dt_ns, K, &s, &u)) return 1;
+  LoamShared sh;
+  sh.S_GtoM = ldq(S_GtoM); sh.p_GinM = ldv(p_GinM); sh.S_LtoI = ldq(S_LtoI); sh.p_LinI = ldv(p_LinI); sh.weight = weight;
+  loam_eval(W.view, s, u, ldv(pL), is_plane != 0, geo, sh, true, r, J);
+  *s_out = s;
+  *u_out = u;
+  return 0;
+}
+
+__attribute__((visibility("default"))) int emul_imu(int K, const double* kq, const double* kp, int64_t t0_ns,
+                                                     int64_t dt_ns, int64_t t_corrected_ns, const double* gyro,
+                                                     const double* accel, const double* info, const double* bg,
+                                                     const double* ba, const double* gravity, double loss_a, int marg,
+                                                     double* rows /*6*NC*/, double* rho, int* s_out) {
+  HostWindow W(K, kq, kp);
+  int s;
+  double u;
+  if (!index_ns(t_corrected_ns, t0_ns, dt_ns, K, &s, &u)) return 1;
+  ImuShared sh;
+  for (int i = 0; i < 6; i++) sh.info[i] = info[i];
+  sh.bg = ldv(bg); sh.ba = ldv(ba); sh.gravity = ldv(gravity); sh.loss_a = loss_a; sh.inv_dt = 1e9 / double(dt_ns);
+  if (marg) {
+    ArraySink sink{rows, 40};
+    *rho = imu_eval<true>(W.view, s, u, ldv(gyro), ldv(accel), sh, true, sink);
+  } else {
+    ArraySink sink{rows, 32};
+    *rho = imu_eval<false>(W.view, s, u, ldv(gyro), ldv(accel), sh, true, sink);
+  }
+  *s_out = s;
+  return 0;
+}
+}

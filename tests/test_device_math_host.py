@@ -1,0 +1,120 @@
+"""Host emulation of the product's __host__ __device__ factor math (clic_b200/csrc/factor_eval.cuh compiled with
+g++) against the oracle's per-factor Jacobians.  Catches restructuring mistakes (hoisting, unit-axis Jr,
+vector-first chains) on the CPU-only box; the real parity tests are the -m gpu ones through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from clic_b200 import estimator as E
+from clic_b200 import synthetic as S
+from clic_b200._abi import GEO_PLANE, dptr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL_DIR = os.path.join(HERE, "host_emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-C", EMUL_DIR], check=True, capture_output=True)
+    lib = C.CDLL(os.path.join(EMUL_DIR, "_build", "libclic_emul.so"))
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.emul_loam.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int, dp, dp, dp, dp, dp,
+                              C.c_double, dp, dp, ip, dp]
+    lib.emul_imu.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp, C.c_double,
+                             C.c_int, dp, dp, ip]
+    return lib
+
+
+def _windows():
+    # realistic small-increment window, the reference test's large random rotations + identical leading knots
+    from test_oracle_autodiff import reference_test_trajectory
+    sw = S.make_window(10, n_lidar=40, n_imu=25, line_fraction=0.5, seed=11)
+    yield "smooth", sw
+    sw2 = S.make_window(12, n_lidar=40, n_imu=25, line_fraction=0.5, seed=12)
+    w = reference_test_trajectory(5)
+    sw2.window.knot_q, sw2.window.knot_p = w.knot_q, w.knot_p
+    yield "random+identity", sw2
+
+
+@pytest.mark.parametrize("name,sw", list(_windows()))
+def test_loam_rows(oracle, emul, name, sw):
+    w = sw.window
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    L = sw.lidar
+    est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                   L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"])
+    s_or, u_or = est.indices(0)
+    kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
+    worst = 0.0
+    for i in range(len(L["t_point"])):
+        r_o, J_o = oracle_lib.block_jacobian(oracle, est, i)
+        t_ns = int(np.int64(L["t_point"][i] * 1e9))
+        is_plane = int(L["geo_type"][i] == GEO_PLANE)
+        geo = np.zeros(6)
+        if is_plane:
+            geo[:4] = L["geo_plane"][i]
+        else:
+            geo[:3], geo[3:] = L["geo_point"][i], L["geo_normal"][i]
+        r, J, s, u = np.zeros(1), np.zeros(24), C.c_int(0), np.zeros(1)
+        pL = np.ascontiguousarray(L["point"][i])
+        rc = emul.emul_loam(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, t_ns, dptr(pL), is_plane, dptr(geo),
+                            dptr(L["S_GtoM"]), dptr(L["p_GinM"]), dptr(L["S_LtoI"]), dptr(L["p_LinI"]),
+                            float(L["weight"]), dptr(r), dptr(J), C.byref(s), dptr(u))
+        assert rc == 0
+        assert s.value == s_or[i] and u[0] == u_or[i]  # indexing bit-exact
+        J_ref = J_o[0, 6 * s.value:6 * s.value + 24]
+        scale = max(1.0, np.abs(J_ref).max())
+        assert abs(r[0] - r_o[0]) <= 1e-10 * max(1.0, abs(r_o[0]))
+        worst = max(worst, np.abs(J - J_ref).max() / scale)
+        # nothing outside the 4-knot support
+        mask = np.ones(J_o.shape[1], bool)
+        mask[6 * s.value:6 * s.value + 24] = False
+        assert not J_o[0, mask].any()
+    assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("marg", [0, 1])
+@pytest.mark.parametrize("name,sw", list(_windows()))
+def test_imu_rows(oracle, emul, name, sw, marg):
+    w = sw.window
+    w.t_offset_ns = np.array([250_000.7, 0, 0])
+    opt = E.default_options(oracle)
+    opt.lock_ab = opt.lock_wb = 0
+    opt.lock_t_offset[0] = 0
+    opt.t_offset_padding_ns = 1_000_000
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    M = sw.imu
+    # keep samples away from the ends so the padding test keeps them
+    keep = (M["timestamp"] > 0.01) & (M["timestamp"] < (w.n_knots - 3) * 0.1 - 0.01)
+    ts, gy, ac = M["timestamp"][keep], M["gyro"][keep], M["accel"][keep]
+    assert est.AddIMUMeasurementAnalytic(ts, gy, ac, 1, M["info_vec"]) == 0
+    Lay = est.layout()
+    kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
+    NC = 40 if marg else 32
+    worst = 0.0
+    for i in range(len(ts)):
+        r_o, J_o = oracle_lib.block_jacobian(oracle, est, i, apply_loss=True)
+        t_ns = int(np.int64(ts[i] * 1e9)) + int(w.t_offset_ns[0])
+        rows, rho, s = np.zeros((6, NC)), np.zeros(1), C.c_int(0)
+        g, a = np.ascontiguousarray(gy[i]), np.ascontiguousarray(ac[i])
+        bg, ba = np.ascontiguousarray(w.bias[1, :3]), np.ascontiguousarray(w.bias[1, 3:])
+        rc = emul.emul_imu(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, t_ns, dptr(g), dptr(a),
+                           dptr(M["info_vec"]), dptr(bg), dptr(ba), dptr(w.gravity), 10.0, marg, dptr(rows),
+                           dptr(rho), C.byref(s))
+        assert rc == 0
+        sv = s.value
+        c_r = 34 if marg else 31
+        c_t = 33 if marg else 30
+        scale = max(1.0, np.abs(J_o).max())
+        d = [np.abs(rows[:, :24] - J_o[:, 6 * sv:6 * sv + 24]).max(),
+             np.abs(rows[:, 24:27] - J_o[:, Lay.col_bias_gyro + 3:Lay.col_bias_gyro + 6]).max(),
+             np.abs(rows[:, 27:30] - J_o[:, Lay.col_bias_accel + 3:Lay.col_bias_accel + 6]).max(),
+             np.abs(rows[:, c_t] - J_o[:, Lay.col_t_offset[0]]).max()]
+        worst = max(worst, max(d) / scale)
+        assert np.allclose(rows[:, c_r], r_o, rtol=1e-10, atol=1e-9)
+        assert not rows[:, c_r + 1:].any()
+    assert worst < 1e-11, worst
