@@ -1,0 +1,913 @@
+// libclic_cuda.so — the C ABI of include/clic_cuda.h on top of the sm_100a kernels.  Host code here only
+// stages inputs, launches kernels and copies results; there is no CPU implementation of any arithmetic of
+// the path (no fallback: without a CUDA device every compute entry point returns CLIC_ERR_NO_DEVICE).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/clic_cuda.h"
+#include "kernels.cuh"
+#include "solver.cuh"
+
+using namespace clic;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+#define CU(x)                                                                                          \
+  do {                                                                                                 \
+    cudaError_t e_ = (x);                                                                              \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(CLIC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Launch geometry + record buffers of one factor stream.
+struct StreamExec {
+  int64_t n = 0;
+  int grid = 0, slabs_per_warp = 0, n_warps = 0;
+  int NT = 4, rd = 640, n_keys = 0, P = 8;
+  DevBuf payload, key, cost, part, overflow;
+  int* overflow_flag = nullptr;
+  RecordBuf rb() const {
+    RecordBuf r;
+    r.payload = payload.as<double>();
+    r.key = key.as<int>();
+    r.cost = cost.as<double>();
+    r.overflow = overflow.as<double>();
+    r.overflow_flag = overflow_flag;
+    return r;
+  }
+};
+
+struct LoamBatch {
+  LoamStream st;
+  DevBuf t_ns, p[3], g[6], type;
+  int marg = 0;
+  StreamExec ex;
+};
+struct ImuBatch {
+  ImuStream st;
+  DevBuf t_ns, gy[3], ac[3];
+  int marg = 0;
+  StreamExec ex;
+};
+struct BiasFac {
+  int slot_i, slot_j;
+  double sqrt_info[6];
+  int marg = 0, marg_all = 0;
+};
+
+}  // namespace
+
+struct clic_prior {
+  int n = 0, m = 0;
+  std::vector<double> J0, r0;
+  struct Block {
+    int kind, id, size, idx;
+    double x0[4];
+  };
+  std::vector<Block> blocks;
+};
+
+struct clic_estimator {
+  // window
+  int64_t t0_ns, dt_ns;
+  int K, knot_id0, n_bias, bias_id0, n_lm;
+  double S_CtoI[4], p_CinI[3];
+  clic_options opt;
+  int fixed_index_global = -1;
+  StateLayout sl;
+  std::vector<double> h_state;  // host mirror used only for the add-time window test (needs t_offset)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int device = 0, n_sm = 148;
+  DevBuf d_state, d_cand, d_H, d_b, d_cost2, d_flags, d_counter;
+  DevBuf d_knot_col, d_col_knot, d_col_sub, d_descs;
+  DevBuf d_lm;  // LM workspace (solver.cuh)
+  std::vector<std::unique_ptr<LoamBatch>> loam;
+  std::vector<std::unique_ptr<ImuBatch>> imu;
+  std::vector<BiasFac> bias_f;
+  struct PriorRef {
+    const clic_prior* p;
+    std::vector<int> drop;
+    DevBuf J0, r0, x0, meta, A;  // device copies (+ A = J0^T J0)
+    std::vector<int> h_meta;
+  };
+  std::vector<std::unique_ptr<PriorRef>> priors;
+  std::vector<char> lm_free;
+  bool layout_dirty = true;
+  clic_layout L;
+  int n_desc = 0;
+  int64_t launches = 0;
+  bool bounds_toff[3] = {false, false, false};
+  double toff_lo[3], toff_hi[3];
+
+  int64_t minTimeNs() const { return t0_ns; }
+  int64_t maxTimeNs() const { return t0_ns + (int64_t)(K - 4 + 1) * dt_ns - 1; }
+  // trajectory.h:100-108 — double arithmetic exactly as the reference
+  double minTime(int s) const { return 1e-9 * minTimeNs() - 1e-9 * h_state[sl.off_toff() + s]; }
+  double maxTime(int s) const { return 1e-9 * maxTimeNs() - 1e-9 * h_state[sl.off_toff() + s]; }
+};
+
+namespace {
+
+bool have_device() {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+clic_layout compute_layout(const clic_estimator* E) {
+  clic_layout L;
+  int kf = E->fixed_index_global - E->knot_id0 + 1;
+  kf = std::max(0, std::min(E->K, kf));
+  if (E->opt.lock_traj) kf = E->K;
+  L.first_free_knot = kf;
+  L.n_free_knots = E->K - kf;
+  int c = 6 * L.n_free_knots;
+  L.col_bias_gyro = L.col_bias_accel = -1;
+  if (!E->opt.lock_wb && E->n_bias > 0) { L.col_bias_gyro = c; c += 3 * E->n_bias; }
+  if (!E->opt.lock_ab && E->n_bias > 0) { L.col_bias_accel = c; c += 3 * E->n_bias; }
+  for (int s = 0; s < 3; s++) L.col_t_offset[s] = -1;
+  if (!E->opt.lock_t_offset[CLIC_SENSOR_IMU]) L.col_t_offset[CLIC_SENSOR_IMU] = c++;
+  if (!E->opt.lock_t_offset[CLIC_SENSOR_CAMERA]) L.col_t_offset[CLIC_SENSOR_CAMERA] = c++;
+  L.col_inv_depth = -1;
+  L.n_free_landmarks = 0;
+  for (int i = 0; i < E->n_lm; i++) L.n_free_landmarks += E->lm_free[i] ? 1 : 0;
+  if (L.n_free_landmarks > 0) { L.col_inv_depth = c; c += L.n_free_landmarks; }
+  L.D = c;
+  return L;
+}
+
+int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm) {
+  ex.n = n;
+  ex.NT = NT;
+  ex.rd = n_tiles(NT) * 64;
+  ex.n_keys = E->K - 3;
+  const int64_t slabs = (n + 31) / 32;
+  const int max_ctas = E->n_sm * ctas_per_sm;
+  int64_t ctas = std::min<int64_t>(max_ctas, (slabs + kWarpsPerCta - 1) / kWarpsPerCta);
+  ctas = std::max<int64_t>(ctas, 1);
+  ex.slabs_per_warp = (int)((slabs + ctas * kWarpsPerCta - 1) / (ctas * kWarpsPerCta));
+  ex.slabs_per_warp = std::max(ex.slabs_per_warp, 1);
+  ex.grid = (int)((slabs + (int64_t)ex.slabs_per_warp * kWarpsPerCta - 1) / ((int64_t)ex.slabs_per_warp * kWarpsPerCta));
+  ex.grid = std::max(ex.grid, 1);
+  ex.n_warps = ex.grid * kWarpsPerCta;
+  const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
+  ex.P = (int)std::min<size_t>(8, std::max<size_t>(1, slots / 64));
+  CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
+  CU(ex.key.ensure(slots * sizeof(int)));
+  CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
+  CU(ex.part.ensure((size_t)ex.n_keys * ex.P * ex.rd * sizeof(double)));
+  CU(ex.overflow.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
+  ex.overflow_flag = E->d_flags.as<int>();
+  return CLIC_OK;
+}
+
+size_t factor_smem_bytes(int K, int NT) {
+  return (window_smem_doubles(K) + (size_t)kWarpsPerCta * 8 * NT * kJtStride) * sizeof(double);
+}
+
+// Column maps + stream descriptors for assemble_kernel.
+int ensure_layout(clic_estimator* E) {
+  if (!E->layout_dirty) return CLIC_OK;
+  E->L = compute_layout(E);
+  const clic_layout& L = E->L;
+  const int D = std::max(1, L.D), K = E->K;
+  std::vector<int> knot_col(K), col_knot(D, -1), col_sub(D, 0);
+  for (int k = 0; k < K; k++) {
+    knot_col[k] = k >= L.first_free_knot ? 6 * (k - L.first_free_knot) : -1;
+    if (knot_col[k] >= 0)
+      for (int c = 0; c < 6; c++) {
+        col_knot[knot_col[k] + c] = k;
+        col_sub[knot_col[k] + c] = c;
+      }
+  }
+  CU(E->d_knot_col.ensure(K * sizeof(int)));
+  CU(E->d_col_knot.ensure(D * sizeof(int)));
+  CU(E->d_col_sub.ensure(D * sizeof(int)));
+  CU(cudaMemcpyAsync(E->d_knot_col.p, knot_col.data(), K * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  CU(cudaMemcpyAsync(E->d_col_knot.p, col_knot.data(), D * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  CU(cudaMemcpyAsync(E->d_col_sub.p, col_sub.data(), D * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  std::vector<StreamDesc> descs;
+  for (auto& b : E->loam) {
+    if (b->marg) continue;
+    StreamDesc d{};
+    d.part = b->ex.part.as<double>();
+    d.overflow = b->ex.overflow.as<double>();
+    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 24;
+    d.n_extra = 0;
+    descs.push_back(d);
+  }
+  for (auto& b : E->imu) {
+    if (b->marg) continue;
+    StreamDesc d{};
+    d.part = b->ex.part.as<double>();
+    d.overflow = b->ex.overflow.as<double>();
+    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 31;
+    d.n_extra = 7;
+    for (int c = 0; c < 3; c++) {
+      d.extra_global[c] = L.col_bias_gyro >= 0 ? L.col_bias_gyro + 3 * b->st.bias_slot + c : -1;
+      d.extra_global[3 + c] = L.col_bias_accel >= 0 ? L.col_bias_accel + 3 * b->st.bias_slot + c : -1;
+    }
+    d.extra_global[6] = L.col_t_offset[CLIC_SENSOR_IMU];
+    descs.push_back(d);
+  }
+  E->n_desc = (int)descs.size();
+  CU(E->d_descs.ensure(std::max<size_t>(1, descs.size()) * sizeof(StreamDesc)));
+  if (!descs.empty())
+    CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
+  CU(E->d_H.ensure((size_t)D * D * sizeof(double)));
+  CU(E->d_b.ensure((size_t)D * sizeof(double)));
+  CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
+  E->layout_dirty = false;
+  return CLIC_OK;
+}
+
+
+int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* state, double* cost2, bool jac,
+                 const int* ctl) {
+  const int n = pr->p->n, nb = (int)pr->p->blocks.size();
+  const int D = std::max(1, E->L.D);
+  size_t smem = (size_t)3 * n * sizeof(double) + (size_t)n * sizeof(int);
+  prior_kernel<<<1, 256, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
+                                            pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->d_H.as<double>(),
+                                            E->d_b.as<double>(), D, cost2, jac ? 1 : 0, ctl);
+  E->launches++;
+  return CLIC_OK;
+}
+
+// column of a prior block under the current layout (same rule as every other block)
+int fill_prior_columns(clic_estimator* E) {
+  const clic_layout& L = E->L;
+  for (auto& pr : E->priors) {
+    const int nb = (int)pr->p->blocks.size();
+    for (int i = 0; i < nb; i++) {
+      const auto& b = pr->p->blocks[i];
+      int col = -1;
+      switch (b.kind) {
+        case CLIC_BLOCK_KNOT_ROT:
+        case CLIC_BLOCK_KNOT_POS: {
+          int k = b.id - E->knot_id0;
+          if (k >= L.first_free_knot) col = 6 * (k - L.first_free_knot) + (b.kind == CLIC_BLOCK_KNOT_POS ? 3 : 0);
+        } break;
+        case CLIC_BLOCK_BIAS_GYRO:
+          if (L.col_bias_gyro >= 0) col = L.col_bias_gyro + 3 * (b.id - E->bias_id0);
+          break;
+        case CLIC_BLOCK_BIAS_ACCEL:
+          if (L.col_bias_accel >= 0) col = L.col_bias_accel + 3 * (b.id - E->bias_id0);
+          break;
+        case CLIC_BLOCK_T_OFFSET: col = L.col_t_offset[b.id]; break;
+        default: col = -1;  // gravity: locked; inverse depth: fixed_depth only in this revision
+      }
+      pr->h_meta[4 * i + 3] = col;
+    }
+    CU(cudaMemcpyAsync(pr->meta.p, pr->h_meta.data(), pr->h_meta.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  }
+  if (!E->priors.empty()) CU(cudaStreamSynchronize(E->stream));
+  return CLIC_OK;
+}
+
+PassParams pass_params(const clic_estimator* E, const double* state, const int* ctl) {
+  PassParams pp;
+  pp.state = state;
+  pp.sl = E->sl;
+  pp.t0_ns = E->t0_ns;
+  pp.dt_ns = E->dt_ns;
+  pp.kf = E->L.first_free_knot;
+  pp.marg_mode = 0;
+  pp.marg_later_local = E->opt.ctrl_to_be_opt_later - E->knot_id0;
+  pp.ctl = ctl;
+  return pp;
+}
+
+template <class KernelT>
+int set_smem(KernelT k, size_t bytes) {
+  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CLIC_OK;
+}
+
+// One fused residual (+ Jacobian + normal-equation) pass over the solve problem at `state`.
+// jac = true: H, b, cost2 are produced; false: cost2 only.  ctl: optional device skip word.
+int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, const int* ctl) {
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  PassParams pp = pass_params(E, state, ctl);
+  CU(cudaMemsetAsync(cost2, 0, 2 * sizeof(double), E->stream));
+  const int D = E->L.D;
+  for (auto& b : E->loam) {
+    if (b->marg) continue;
+    StreamExec& ex = b->ex;
+    const size_t smem = factor_smem_bytes(E->K, 4);
+    if (jac) {
+      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+      loam_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      dim3 g(ex.n_keys, ex.P);
+      reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
+                                                      ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      E->launches += 2;
+    } else {
+      loam_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->launches += 1;
+    }
+    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
+    E->launches += 1;
+  }
+  for (auto& b : E->imu) {
+    if (b->marg) continue;
+    StreamExec& ex = b->ex;
+    const size_t smem = factor_smem_bytes(E->K, 4);
+    if (jac) {
+      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+      imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      dim3 g(ex.n_keys, ex.P);
+      reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
+                                                      ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      E->launches += 2;
+    } else {
+      imu_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->launches += 1;
+    }
+    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
+    E->launches += 1;
+  }
+  if (jac && D > 0) {
+    ColMaps cm;
+    cm.D = D;
+    cm.K = E->K;
+    cm.knot_col = E->d_knot_col.as<int>();
+    cm.col_knot = E->d_col_knot.as<int>();
+    cm.col_sub = E->d_col_sub.as<int>();
+    const int n_entries = D * (D + 1) / 2 + D;
+    assemble_kernel<<<(n_entries + 127) / 128, 128, 0, E->stream>>>(E->d_H.as<double>(), E->d_b.as<double>(), cm,
+                                                                    E->d_descs.as<StreamDesc>(), E->n_desc, ctl);
+    E->launches += 1;
+  }
+  for (auto& bf : E->bias_f) {
+    if (bf.marg) continue;
+    BiasFactorDesc d;
+    d.slot_i = bf.slot_i;
+    d.slot_j = bf.slot_j;
+    for (int i = 0; i < 6; i++) d.sqrt_info[i] = bf.sqrt_info[i];
+    d.col_gi = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_i : -1;
+    d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
+    d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
+    d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
+    bias_factor_kernel<<<1, 32, 0, E->stream>>>(d, state, E->sl, E->d_H.as<double>(), E->d_b.as<double>(), std::max(1, D),
+                                                cost2, jac ? 1 : 0, ctl);
+    E->launches += 1;
+  }
+  for (auto& pr : E->priors) {
+    if (E->opt.is_marg_state) continue;
+    if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl))) return rc;
+  }
+  CU(cudaGetLastError());
+  return CLIC_OK;
+}
+
+int upload_state(clic_estimator* E) {
+  CU(cudaMemcpyAsync(E->d_state.p, E->h_state.data(), E->h_state.size() * sizeof(double), cudaMemcpyHostToDevice,
+                     E->stream));
+  return CLIC_OK;
+}
+
+bool ok_handle(const clic_estimator* h) { return h != nullptr; }
+
+// copies a host array to a temporary device buffer on the estimator's stream
+template <class T>
+int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
+  CU(buf.ensure(std::max<size_t>(1, count) * sizeof(T)));
+  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, E->stream));
+  return CLIC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+CLIC_API const char* clic_last_error(void) { return g_err.c_str(); }
+CLIC_API const char* clic_backend(void) { return "cuda-sm100a"; }
+
+CLIC_API void clic_default_options(clic_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->lock_ab = o->lock_wb = o->lock_g = 1;
+  for (int s = 0; s < 3; s++) o->lock_t_offset[s] = 1;
+  o->t_offset_padding_ns = (int64_t)1e7;
+  o->marg_bias_param = o->marg_gravity_param = o->marg_t_offset_param = 1;
+  o->deterministic = 1;
+}
+
+CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, clic_estimator** out) {
+  if (!w || !opt || !out) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  if (w->n_knots < 4 || w->dt_ns <= 0) return fail(CLIC_ERR_BAD_ARGUMENT, "need >= 4 knots and dt > 0");
+  if (!have_device()) return fail(CLIC_ERR_NO_DEVICE, "no CUDA device: libclic_cuda has no CPU fallback");
+  std::unique_ptr<clic_estimator> E(new clic_estimator);
+  E->device = opt->device;
+  CU(cudaSetDevice(E->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, E->device));
+  if (prop.major < 10) return fail(CLIC_ERR_NO_DEVICE, "device is not sm_100 class (kernels are built for sm_100a only)");
+  E->n_sm = prop.multiProcessorCount;
+  E->t0_ns = w->t0_ns;
+  E->dt_ns = w->dt_ns;
+  E->K = w->n_knots;
+  E->knot_id0 = w->knot_id0;
+  E->n_bias = w->n_bias;
+  E->bias_id0 = w->bias_id0;
+  E->n_lm = w->n_landmarks;
+  std::memcpy(E->S_CtoI, w->S_CtoI, sizeof(E->S_CtoI));
+  std::memcpy(E->p_CinI, w->p_CinI, sizeof(E->p_CinI));
+  E->opt = *opt;
+  E->sl.K = E->K;
+  E->sl.nb = E->n_bias;
+  E->sl.L = E->n_lm;
+  E->h_state.assign(E->sl.size(), 0.0);
+  std::copy(w->knot_q, w->knot_q + 4 * E->K, E->h_state.begin() + E->sl.off_q());
+  std::copy(w->knot_p, w->knot_p + 3 * E->K, E->h_state.begin() + E->sl.off_p());
+  if (E->n_bias > 0) std::copy(w->bias, w->bias + 6 * E->n_bias, E->h_state.begin() + E->sl.off_bias());
+  for (int s = 0; s < 3; s++) E->h_state[E->sl.off_toff() + s] = w->t_offset_ns[s];
+  for (int a = 0; a < 3; a++) E->h_state[E->sl.off_grav() + a] = w->gravity[a];
+  if (E->n_lm > 0) std::copy(w->inv_depth, w->inv_depth + E->n_lm, E->h_state.begin() + E->sl.off_invd());
+  E->lm_free.assign(std::max(0, E->n_lm), 0);
+  if (opt->stream) {
+    E->stream = (cudaStream_t)opt->stream;
+  } else {
+    CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    E->own_stream = true;
+  }
+  CU(E->d_state.ensure(E->sl.size() * sizeof(double)));
+  CU(E->d_cand.ensure(E->sl.size() * sizeof(double)));
+  CU(E->d_cost2.ensure(8 * sizeof(double)));
+  CU(E->d_counter.ensure(sizeof(unsigned long long)));
+  CU(E->d_flags.ensure(16 * sizeof(int)));
+  CU(cudaMemsetAsync(E->d_flags.p, 0, 16 * sizeof(int), E->stream));
+  int rc = upload_state(E.get());
+  if (rc) return rc;
+  // opt in to > 48 KB dynamic shared memory once
+  size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
+  if ((rc = set_smem(loam_kernel<true>, smem4)) || (rc = set_smem(loam_kernel<false>, smem4)) ||
+      (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
+      (rc = set_smem(imu_kernel<true, true>, smem5)))
+    return rc;
+  CU(cudaStreamSynchronize(E->stream));
+  *out = E.release();
+  return CLIC_OK;
+}
+
+CLIC_API int clic_destroy(clic_estimator* h) {
+  if (!h) return CLIC_OK;
+  cudaStreamSynchronize(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_set_fixed_index(clic_estimator* h, int32_t idx) {
+  if (!ok_handle(h)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  h->fixed_index_global = idx;
+  h->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                           const int32_t* geo_type, const double* geo_plane, const double* geo_normal,
+                           const double* geo_point, const double S_GtoM[4], const double p_GinM[3],
+                           const double S_LtoI[4], const double p_LinI[3], double weight, int32_t marg_this_factor,
+                           int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n_dropped) *n_dropped = 0;
+  if (n <= 0) return CLIC_OK;
+  CU(cudaSetDevice(E->device));
+  std::unique_ptr<LoamBatch> B(new LoamBatch);
+  // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
+  const int S = CLIC_SENSOR_LIDAR;
+  int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  if (!E->opt.lock_t_offset[S]) {
+    t_min += E->opt.t_offset_padding_ns;
+    t_max -= E->opt.t_offset_padding_ns;
+  }
+  DevBuf r_t, r_pt, r_type, r_plane, r_normal, r_gpoint;
+  int rc;
+  if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
+      (rc = to_device(E, r_type, geo_type, n)))
+    return rc;
+  // a missing geometry array is only legal when no record of that type exists; the kernel never reads it then
+  bool has_plane = false, has_line = false;
+  for (int64_t i = 0; i < n; i++) (geo_type[i] == CLIC_GEO_PLANE ? has_plane : has_line) = true;
+  if ((has_plane && !geo_plane) || (has_line && (!geo_normal || !geo_point)))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "geometry array missing for a record type that is present");
+  if ((rc = to_device(E, r_plane, geo_plane, geo_plane ? 4 * n : 0)) ||
+      (rc = to_device(E, r_normal, geo_normal, geo_normal ? 3 * n : 0)) ||
+      (rc = to_device(E, r_gpoint, geo_point, geo_point ? 3 * n : 0)))
+    return rc;
+  CU(B->t_ns.ensure(n * sizeof(int64_t)));
+  for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
+  for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
+  CU(B->type.ensure(n));
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  prep_loam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+      n, r_t.as<double>(), r_pt.as<double>(), r_type.as<int32_t>(), r_plane.as<double>(), r_normal.as<double>(),
+      r_gpoint.as<double>(), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
+      B->p[2].as<double>(), B->g[0].as<double>(), B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(),
+      B->g[4].as<double>(), B->g[5].as<double>(), B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>());
+  E->launches++;
+  unsigned long long dropped = 0;
+  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));  // also keeps the temporary raw buffers alive until the kernel is done
+  if (n_dropped) *n_dropped = (int64_t)dropped;
+  B->st.n = n;
+  B->st.t_ns = B->t_ns.as<int64_t>();
+  for (int k = 0; k < 3; k++) B->st.p[k] = B->p[k].as<double>();
+  for (int k = 0; k < 6; k++) B->st.g[k] = B->g[k].as<double>();
+  B->st.type = B->type.as<uint8_t>();
+  B->st.sh.S_GtoM = ldq(S_GtoM);
+  B->st.sh.p_GinM = ldv(p_GinM);
+  B->st.sh.S_LtoI = ldq(S_LtoI);
+  B->st.sh.p_LinI = ldv(p_LinI);
+  B->st.sh.weight = weight;
+  B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  if ((rc = plan_stream(E, B->ex, n, 4, 2))) return rc;
+  E->loam.push_back(std::move(B));
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp, const double* gyro,
+                          const double* accel, int32_t bias_slot, const double info_vec[6],
+                          int32_t marg_this_factor, int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (bias_slot < 0 || bias_slot >= E->n_bias) return fail(CLIC_ERR_BAD_ARGUMENT, "bias slot out of range");
+  if (n_dropped) *n_dropped = 0;
+  if (n <= 0) return CLIC_OK;
+  CU(cudaSetDevice(E->device));
+  std::unique_ptr<ImuBatch> B(new ImuBatch);
+  const int S = CLIC_SENSOR_IMU;
+  const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
+  DevBuf r_t, r_g, r_a;
+  int rc;
+  if ((rc = to_device(E, r_t, timestamp, n)) || (rc = to_device(E, r_g, gyro, 3 * n)) ||
+      (rc = to_device(E, r_a, accel, 3 * n)))
+    return rc;
+  CU(B->t_ns.ensure(n * sizeof(int64_t)));
+  for (int k = 0; k < 3; k++) {
+    CU(B->gy[k].ensure(n * sizeof(double)));
+    CU(B->ac[k].ensure(n * sizeof(double)));
+  }
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  prep_imu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+      n, r_t.as<double>(), r_g.as<double>(), r_a.as<double>(), t_min, t_max, pad, B->t_ns.as<int64_t>(),
+      B->gy[0].as<double>(), B->gy[1].as<double>(), B->gy[2].as<double>(), B->ac[0].as<double>(),
+      B->ac[1].as<double>(), B->ac[2].as<double>(), E->d_counter.as<unsigned long long>());
+  E->launches++;
+  unsigned long long dropped = 0;
+  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  if (n_dropped) *n_dropped = (int64_t)dropped;
+  B->st.n = n;
+  B->st.t_ns = B->t_ns.as<int64_t>();
+  for (int k = 0; k < 3; k++) {
+    B->st.gyro[k] = B->gy[k].as<double>();
+    B->st.accel[k] = B->ac[k].as<double>();
+  }
+  for (int i = 0; i < 6; i++) B->st.info[i] = info_vec[i];
+  B->st.loss_a = marg_this_factor ? 3.0 : 10.0;  // trajectory_estimator.cpp:426-430
+  B->st.bias_slot = bias_slot;
+  B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  B->st.marg_always = (E->opt.marg_bias_param || E->opt.marg_gravity_param || E->opt.marg_t_offset_param) ? 1 : 0;
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:419-424
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
+    E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
+  }
+  if ((rc = plan_stream(E, B->ex, n, B->marg ? 5 : 4, 1))) return rc;
+  E->imu.push_back(std::move(B));
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, double dt, const double info_vec[6],
+                           int32_t marg_this_factor, int32_t marg_all_bias) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (slot_i < 0 || slot_i >= E->n_bias || slot_j < 0 || slot_j >= E->n_bias)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bias slot out of range");
+  BiasFac f;
+  f.slot_i = slot_i;
+  f.slot_j = slot_j;
+  const double sqrt_dt = sqrt(dt);  // BiasFactor ctor, trajectory_value_factor.h:67-71
+  for (int i = 0; i < 6; i++) f.sqrt_info[i] = info_vec[i] / sqrt_dt;
+  f.marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  f.marg_all = marg_all_bias;
+  E->bias_f.push_back(f);
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, const double* p_i, const double* t_j,
+                            const double* p_j, const int32_t* landmark, int32_t fixed_depth,
+                            int32_t marg_this_feature, int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  return fail(CLIC_ERR_UNSUPPORTED, "visual reprojection factors: CUDA kernel not built yet in this revision");
+}
+
+CLIC_API int clic_add_prior(clic_estimator* E, const clic_prior* prior, int32_t n_drop, const int32_t* drop_blocks) {
+  if (!ok_handle(E) || !prior) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  std::unique_ptr<clic_estimator::PriorRef> R(new clic_estimator::PriorRef);
+  R->p = prior;
+  if (n_drop > 0) R->drop.assign(drop_blocks, drop_blocks + n_drop);
+  if (E->opt.is_marg_state && n_drop <= 0) return CLIC_OK;  // trajectory_manager.cpp:367
+  const int nb = (int)prior->blocks.size();
+  std::vector<int> meta(4 * nb);  // per block: state offset, size, tangent idx, column (-1 const) [column filled per pass]
+  std::vector<double> x0(4 * nb);
+  for (int i = 0; i < nb; i++) {
+    const auto& b = prior->blocks[i];
+    int off = -1;
+    switch (b.kind) {
+      case CLIC_BLOCK_KNOT_ROT: {
+        int k = b.id - E->knot_id0;
+        if (k < 0 || k >= E->K) return fail(CLIC_ERR_BAD_ARGUMENT, "prior refers to a knot outside the window");
+        off = E->sl.off_q() + 4 * k;
+      } break;
+      case CLIC_BLOCK_KNOT_POS: {
+        int k = b.id - E->knot_id0;
+        if (k < 0 || k >= E->K) return fail(CLIC_ERR_BAD_ARGUMENT, "prior refers to a knot outside the window");
+        off = E->sl.off_p() + 3 * k;
+      } break;
+      case CLIC_BLOCK_BIAS_GYRO:
+      case CLIC_BLOCK_BIAS_ACCEL: {
+        int s = b.id - E->bias_id0;
+        if (s < 0 || s >= E->n_bias) return fail(CLIC_ERR_BAD_ARGUMENT, "prior refers to a bias slot outside the window");
+        off = E->sl.off_bias() + 6 * s + (b.kind == CLIC_BLOCK_BIAS_ACCEL ? 3 : 0);
+      } break;
+      case CLIC_BLOCK_GRAVITY: off = E->sl.off_grav(); break;
+      case CLIC_BLOCK_T_OFFSET: off = E->sl.off_toff() + b.id; break;
+      case CLIC_BLOCK_INV_DEPTH:
+        if (b.id < 0 || b.id >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "prior refers to an unknown landmark");
+        off = E->sl.off_invd() + b.id;
+        break;
+      default: return fail(CLIC_ERR_BAD_ARGUMENT, "unknown prior block kind");
+    }
+    meta[4 * i + 0] = off;
+    meta[4 * i + 1] = b.size;
+    meta[4 * i + 2] = b.idx;
+    meta[4 * i + 3] = -1;
+    for (int k = 0; k < 4; k++) x0[4 * i + k] = b.x0[k];
+  }
+  int rc;
+  if ((rc = to_device(E, R->J0, prior->J0.data(), prior->J0.size())) ||
+      (rc = to_device(E, R->r0, prior->r0.data(), prior->r0.size())) || (rc = to_device(E, R->x0, x0.data(), x0.size())) ||
+      (rc = to_device(E, R->meta, meta.data(), meta.size())))
+    return rc;
+  R->h_meta = meta;
+  CU(R->A.ensure((size_t)prior->n * prior->n * sizeof(double)));
+  {
+    dim3 blk(16, 16), grd((prior->n + 15) / 16, (prior->n + 15) / 16);
+    prior_gram_kernel<<<grd, blk, 0, E->stream>>>(R->J0.as<double>(), prior->n, R->A.as<double>());
+    E->launches++;
+  }
+  CU(cudaStreamSynchronize(E->stream));
+  E->priors.push_back(std::move(R));
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_get_layout(clic_estimator* E, clic_layout* out) {
+  if (!ok_handle(E) || !out) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  *out = compute_layout(E);
+  return CLIC_OK;
+}
+
+CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost, double* fixed_cost) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  rc = fill_prior_columns(E);
+  if (rc) return rc;
+  const bool jac = H || b;
+  rc = run_pass(E, E->d_state.as<double>(), jac, E->d_cost2.as<double>(), nullptr);
+  if (rc) return rc;
+  const int D = E->L.D;
+  double c2[2];
+  if (H && D > 0) CU(cudaMemcpyAsync(H, E->d_H.p, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  if (b && D > 0) CU(cudaMemcpyAsync(b, E->d_b.p, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(c2, E->d_cost2.p, sizeof(c2), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  if (cost) *cost = c2[0];
+  if (fixed_cost) *fixed_cost = c2[1];
+  return CLIC_OK;
+}
+
+CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacity, int32_t* s_out, double* u_out,
+                              int64_t* n_out) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (stream < 0 || stream > 3) return fail(CLIC_ERR_BAD_ARGUMENT, "stream");
+  CU(cudaSetDevice(E->device));
+  int64_t total = 0;
+  if (stream == 0) for (auto& b : E->loam) total += b->st.n;
+  if (stream == 1) for (auto& b : E->imu) total += b->st.n;
+  if (n_out) *n_out = total;
+  if (capacity <= 0 || total == 0) return CLIC_OK;
+  // current offset is read from the device state
+  double toff_d[3];
+  CU(cudaMemcpyAsync(toff_d, E->d_state.as<double>() + E->sl.off_toff(), sizeof(toff_d), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  DevBuf ds, du;
+  int64_t done = 0;
+  auto run = [&](int64_t n, const int64_t* t_ns, int64_t toff) -> int {
+    int64_t m = std::min(n, capacity - done);
+    if (m <= 0) return CLIC_OK;
+    CU(ds.ensure(m * sizeof(int32_t)));
+    CU(du.ensure(m * sizeof(double)));
+    index_probe_kernel<<<(unsigned)((m + 255) / 256), 256, 0, E->stream>>>(m, t_ns, toff, E->t0_ns, E->dt_ns, E->K,
+                                                                         ds.as<int32_t>(), du.as<double>());
+    E->launches++;
+    CU(cudaMemcpyAsync(s_out + done, ds.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaMemcpyAsync(u_out + done, du.p, m * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    done += m;
+    return CLIC_OK;
+  };
+  int rc = CLIC_OK;
+  if (stream == 0)
+    for (auto& b : E->loam) if ((rc = run(b->st.n, b->st.t_ns, 0))) return rc;
+  if (stream == 1)
+    for (auto& b : E->imu) if ((rc = run(b->st.n, b->st.t_ns, (int64_t)toff_d[CLIC_SENSOR_IMU]))) return rc;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_solve(clic_estimator* E, int32_t max_iterations, clic_summary* summary) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!E->opt.lock_g) return fail(CLIC_ERR_UNSUPPORTED, "gravity must be locked (lock_g = 1)");
+  CU(cudaSetDevice(E->device));
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  if ((rc = fill_prior_columns(E))) return rc;
+  return fail(CLIC_ERR_UNSUPPORTED, "LM solve: not built yet in this revision");
+}
+
+CLIC_API int clic_read_state(clic_estimator* E, double* knot_q, double* knot_p, double* bias, double* t_offset_ns,
+                             double* inv_depth) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  std::vector<double> h(E->sl.size());
+  CU(cudaMemcpyAsync(h.data(), E->d_state.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  E->h_state = h;
+  if (knot_q) std::copy(h.begin() + E->sl.off_q(), h.begin() + E->sl.off_q() + 4 * E->K, knot_q);
+  if (knot_p) std::copy(h.begin() + E->sl.off_p(), h.begin() + E->sl.off_p() + 3 * E->K, knot_p);
+  if (bias) std::copy(h.begin() + E->sl.off_bias(), h.begin() + E->sl.off_bias() + 6 * E->n_bias, bias);
+  if (t_offset_ns) std::copy(h.begin() + E->sl.off_toff(), h.begin() + E->sl.off_toff() + 3, t_offset_ns);
+  if (inv_depth) std::copy(h.begin() + E->sl.off_invd(), h.begin() + E->sl.off_invd() + E->n_lm, inv_depth);
+  return CLIC_OK;
+}
+
+CLIC_API int clic_write_state(clic_estimator* E, const double* knot_q, const double* knot_p, const double* bias,
+                              const double* t_offset_ns, const double* inv_depth) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  auto& h = E->h_state;
+  if (knot_q) std::copy(knot_q, knot_q + 4 * E->K, h.begin() + E->sl.off_q());
+  if (knot_p) std::copy(knot_p, knot_p + 3 * E->K, h.begin() + E->sl.off_p());
+  if (bias) std::copy(bias, bias + 6 * E->n_bias, h.begin() + E->sl.off_bias());
+  if (t_offset_ns) std::copy(t_offset_ns, t_offset_ns + 3, h.begin() + E->sl.off_toff());
+  if (inv_depth) std::copy(inv_depth, inv_depth + E->n_lm, h.begin() + E->sl.off_invd());
+  int rc = upload_state(E);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(E->stream));
+  return CLIC_OK;
+}
+
+CLIC_API int clic_marginalize(clic_estimator* E, clic_prior** out) {
+  if (!ok_handle(E) || !out) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  return fail(CLIC_ERR_UNSUPPORTED, "marginalization: CUDA kernel not built yet in this revision");
+}
+
+CLIC_API int clic_prior_create(int32_t n, const double* J0, const double* r0, int32_t n_blocks, const int32_t* kind,
+                               const int32_t* id, const double* x0, clic_prior** out) {
+  if (n <= 0 || !J0 || !r0 || !out) return fail(CLIC_ERR_BAD_ARGUMENT, "bad prior");
+  std::unique_ptr<clic_prior> P(new clic_prior);
+  P->n = n;
+  P->m = 0;
+  P->J0.assign(J0, J0 + (size_t)n * n);
+  P->r0.assign(r0, r0 + n);
+  int off = 0;
+  for (int i = 0; i < n_blocks; i++) {
+    clic_prior::Block b;
+    b.kind = kind[i];
+    b.id = id[i];
+    b.size = (b.kind == CLIC_BLOCK_KNOT_ROT) ? 4 : (b.kind <= CLIC_BLOCK_GRAVITY ? 3 : 1);
+    b.idx = off;
+    off += b.size == 4 ? 3 : b.size;
+    for (int k = 0; k < 4; k++) b.x0[k] = x0[4 * i + k];
+    P->blocks.push_back(b);
+  }
+  if (off != n) return fail(CLIC_ERR_BAD_ARGUMENT, "prior blocks do not add up to n");
+  *out = P.release();
+  return CLIC_OK;
+}
+
+CLIC_API int clic_prior_dims(const clic_prior* p, int32_t* n, int32_t* n_blocks, int32_t* m_dropped) {
+  if (!p) return fail(CLIC_ERR_BAD_HANDLE, "bad prior");
+  if (n) *n = p->n;
+  if (n_blocks) *n_blocks = (int32_t)p->blocks.size();
+  if (m_dropped) *m_dropped = p->m;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_prior_read(const clic_prior* p, double* J0, double* r0, int32_t* kind, int32_t* id,
+                             int32_t* tangent_offset, double* x0) {
+  if (!p) return fail(CLIC_ERR_BAD_HANDLE, "bad prior");
+  if (J0) std::copy(p->J0.begin(), p->J0.end(), J0);
+  if (r0) std::copy(p->r0.begin(), p->r0.end(), r0);
+  for (size_t i = 0; i < p->blocks.size(); i++) {
+    if (kind) kind[i] = p->blocks[i].kind;
+    if (id) id[i] = p->blocks[i].id;
+    if (tangent_offset) tangent_offset[i] = p->blocks[i].idx;
+    if (x0)
+      for (int k = 0; k < 4; k++) x0[4 * i + k] = p->blocks[i].x0[k];
+  }
+  return CLIC_OK;
+}
+
+// A = J0^T J0, g = J0^T r0: a read-back convenience on a small host-resident object (not on the solve path,
+// where the prior is applied by prior_kernel on the device).
+CLIC_API int clic_prior_normal(const clic_prior* p, double* A, double* g) {
+  if (!p) return fail(CLIC_ERR_BAD_HANDLE, "bad prior");
+  if (!have_device()) return fail(CLIC_ERR_NO_DEVICE, "no CUDA device");
+  const int n = p->n;
+  DevBuf dJ, dr, dA, dg;
+  CU(dJ.ensure((size_t)n * n * sizeof(double)));
+  CU(dr.ensure(n * sizeof(double)));
+  CU(dA.ensure((size_t)n * n * sizeof(double)));
+  CU(dg.ensure(n * sizeof(double)));
+  CU(cudaMemcpy(dJ.p, p->J0.data(), (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dr.p, p->r0.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  dim3 blk(16, 16), grd((n + 15) / 16, (n + 15) / 16);
+  prior_gram_kernel<<<grd, blk>>>(dJ.as<double>(), n, dA.as<double>());
+  prior_grad_kernel<<<(n + 127) / 128, 128>>>(dJ.as<double>(), dr.as<double>(), n, dg.as<double>());
+  if (A) CU(cudaMemcpy(A, dA.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (g) CU(cudaMemcpy(g, dg.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return CLIC_OK;
+}
+
+CLIC_API int clic_prior_release(clic_prior* p) {
+  delete p;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_comm_unique_id(uint8_t*) { return fail(CLIC_ERR_UNSUPPORTED, "multi-GPU: not built yet in this revision"); }
+CLIC_API int clic_comm_init(clic_estimator*, int32_t, int32_t, const uint8_t*) {
+  return fail(CLIC_ERR_UNSUPPORTED, "multi-GPU: not built yet in this revision");
+}
+
+CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  if ((rc = fill_prior_columns(E))) return rc;
+  for (int i = 0; i < reps; i++)
+    if ((rc = run_pass(E, E->d_state.as<double>(), true, E->d_cost2.as<double>(), nullptr))) return rc;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_synchronize(clic_estimator* E) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaStreamSynchronize(E->stream));
+  return CLIC_OK;
+}
+
+CLIC_API int clic_num_kernel_launches(clic_estimator* E, int64_t* l) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (l) *l = E->launches;
+  return CLIC_OK;
+}
+
+}  // extern "C"

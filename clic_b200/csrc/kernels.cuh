@@ -1,0 +1,573 @@
+// sm_100a kernels of the fused residual + Jacobian + normal-equation pass.
+//
+// Design:
+//   * one factor per thread; the knot window and the per-knot-pair PairData are staged in shared memory once
+//     per CTA (the whole window is <= 8 KB);
+//   * FP64 on B200 is one pipe (DFMA and DMMA measured at 36-37 TFLOP/s and NOT overlapping,
+//     profiles/r01_fp64_peaks.txt), so the J~^T J~ contraction goes through DMMA.8x8x4 only for its operand
+//     economy: a warp transposes its 32 Jacobian rows through a bank-conflict-free shared tile and issues the
+//     upper-triangular 8x8 tile products; the accumulators stay in registers across all slabs of the warp;
+//   * a warp flushes its accumulators into a private record slot when the knot interval (the "key") of its
+//     factors changes or at the end: no atomics, fixed order => bitwise run-to-run determinism;
+//   * reduce_records + assemble kernels turn records into the dense H, b (owner-computes, no atomics).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "factor_eval.cuh"
+
+namespace clic {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kJtStride = 36;  // doubles per column of the transposed tile: = 4 (mod 16) => conflict-free fragment loads
+constexpr int kSlotsPerWarp = 4;
+constexpr int64_t kDropped = INT64_MIN;  // t_ns sentinel of a measurement dropped by MeasuredTimeToNs
+
+__host__ __device__ constexpr int n_tiles(int NT) { return NT * (NT + 1) / 2; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// State vector layout on the device: [knot_q 4K | knot_p 3K | bias 6nb | t_offset 3 | gravity 3 | inv_depth L]
+struct StateLayout {
+  int K, nb, L;
+  __host__ __device__ int off_q() const { return 0; }
+  __host__ __device__ int off_p() const { return 4 * K; }
+  __host__ __device__ int off_bias() const { return 7 * K; }
+  __host__ __device__ int off_toff() const { return 7 * K + 6 * nb; }
+  __host__ __device__ int off_grav() const { return 7 * K + 6 * nb + 3; }
+  __host__ __device__ int off_invd() const { return 7 * K + 6 * nb + 6; }
+  __host__ __device__ int size() const { return 7 * K + 6 * nb + 6 + L; }
+};
+
+struct PassParams {
+  const double* state;  // state vector the pass is evaluated at
+  StateLayout sl;
+  int64_t t0_ns, dt_ns;
+  int kf;               // first free local knot (factors whose 4 knots are all < kf only add to fixed_cost)
+  int marg_mode;        // 1: marginalization set semantics (gates below), every block has a column
+  int marg_later_local; // ctrl_to_be_opt_later - knot_id0
+  const int* ctl;       // device control word (LM loop): ctl[0] != 0 => skip this pass
+};
+
+struct LoamStream {
+  int64_t n;
+  const int64_t* t_ns;
+  const double* p[3];
+  const double* g[6];
+  const uint8_t* type;  // 1 plane, 0 line
+  LoamShared sh;
+};
+
+// Per-warp output of a factor kernel.
+struct RecordBuf {
+  double* payload;  // [n_warps * kSlotsPerWarp][n_tiles * 64]
+  int* key;         // [n_warps * kSlotsPerWarp], -1 = unused
+  double* cost;     // [n_warps][2]: cost, fixed_cost
+  double* overflow; // [n_keys][n_tiles * 64] atomics fallback when a warp runs out of slots (unsorted input)
+  int* overflow_flag;
+};
+
+template <int NT>
+struct WarpAcc {
+  double c[n_tiles(NT)][2];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int t = 0; t < n_tiles(NT); t++) c[t][0] = c[t][1] = 0.0;
+  }
+  // Jt: this warp's transposed tile, Jt[col * kJtStride + row], rows 0..31 = the slab's Jacobian rows
+  __device__ __forceinline__ void accumulate(const double* Jt, int lane) {
+    const int r4 = lane & 3, c8 = lane >> 2;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      double a[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) a[t] = Jt[(8 * t + c8) * kJtStride + 4 * ks + r4];
+      int idx = 0;
+#pragma unroll
+      for (int ta = 0; ta < NT; ta++)
+#pragma unroll
+        for (int tb = ta; tb < NT; tb++) {
+          dmma884(c[idx][0], c[idx][1], a[ta], a[tb]);
+          idx++;
+        }
+    }
+  }
+  __device__ __forceinline__ void store(double* rec, int lane) const {
+#pragma unroll
+    for (int t = 0; t < n_tiles(NT); t++) {
+      double2 v = make_double2(c[t][0], c[t][1]);
+      *reinterpret_cast<double2*>(rec + t * 64 + 2 * lane) = v;  // row-major 8x8: (lane/4)*8 + (lane%4)*2
+    }
+  }
+  __device__ __forceinline__ void atomic_add(double* dst, int lane) const {
+#pragma unroll
+    for (int t = 0; t < n_tiles(NT); t++) {
+      atomicAdd(dst + t * 64 + 2 * lane, c[t][0]);
+      atomicAdd(dst + t * 64 + 2 * lane + 1, c[t][1]);
+    }
+  }
+};
+
+__device__ __forceinline__ int tile_index(int NT, int ta, int tb) {  // ta <= tb
+  return ta * NT - ta * (ta - 1) / 2 + (tb - ta);
+}
+
+// Shared-memory staging of the window: knots + PairData.  Returns the view; `rest` points past it.
+__device__ __forceinline__ WindowView stage_window(double* smem, const PassParams& pp, double** rest) {
+  const int K = pp.sl.K;
+  double* kq = smem;
+  double* kp = kq + 4 * K;
+  PairData* pair = reinterpret_cast<PairData*>(kp + 3 * K);
+  for (int i = threadIdx.x; i < 7 * K; i += blockDim.x) smem[i] = pp.state[i];  // off_q = 0, off_p = 4K contiguous
+  __syncthreads();
+  for (int k = threadIdx.x; k < K - 1; k += blockDim.x) compute_pair(kq + 4 * k, kq + 4 * (k + 1), &pair[k]);
+  __syncthreads();
+  WindowView W;
+  W.kq = kq;
+  W.kp = kp;
+  W.pair = pair;
+  *rest = reinterpret_cast<double*>(pair + (K - 1));
+  return W;
+}
+__host__ __device__ inline size_t window_smem_doubles(int K) { return (size_t)7 * K + (size_t)kPairDoubles * (K - 1); }
+
+template <int NT>
+__device__ __forceinline__ void flush_record(const WarpAcc<NT>& acc, int key, int& slot, int warp_global,
+                                             const RecordBuf& rb, int lane) {
+  if (key < 0) return;
+  if (slot < kSlotsPerWarp) {
+    int r = warp_global * kSlotsPerWarp + slot;
+    acc.store(rb.payload + (size_t)r * n_tiles(NT) * 64, lane);
+    if (lane == 0) rb.key[r] = key;
+    slot++;
+  } else {  // unsorted input: correct but unordered
+    acc.atomic_add(rb.overflow + (size_t)key * n_tiles(NT) * 64, lane);
+    if (lane == 0) *rb.overflow_flag = 1;
+  }
+}
+
+// K1: LoamFeatureFactor over a stream (lidar_feature_factor.h:65-159), fused with J~^T J~ / J~^T r~ accumulation.
+// Local columns: [knot s..s+3: dtheta(3) dp(3)] = 0..23, r = 24, zero pad to 32.
+template <bool JAC>
+__global__ void __launch_bounds__(kThreads, 2)
+loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
+  if (pp.ctl && pp.ctl[0]) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  double* Jt = rest + (size_t)warp * 32 * kJtStride;
+  if (JAC) {
+    for (int i = lane; i < 32 * kJtStride; i += 32) Jt[i] = 0.0;  // columns 25..31 stay zero
+    __syncwarp();
+  }
+  WarpAcc<4> acc;
+  acc.zero();
+  int acc_key = -1, slot = 0;
+  double cost = 0.0, fcost = 0.0;
+  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  for (int sl = 0; sl < slabs_per_warp; sl++) {
+    const int64_t idx = (slab0 + sl) * 32 + lane;
+    if ((slab0 + sl) * 32 >= st.n) break;
+    int64_t t = kDropped;
+    if (idx < st.n) t = st.t_ns[idx];
+    int s = -1;
+    double u = 0.0;
+    bool valid = (t != kDropped) && index_ns(t, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u);
+    V3 pL = mk(0, 0, 0);
+    double geo[6] = {0, 0, 0, 0, 0, 0};
+    bool is_plane = true;
+    if (valid) {
+      pL = mk(st.p[0][idx], st.p[1][idx], st.p[2][idx]);
+#pragma unroll
+      for (int k = 0; k < 6; k++) geo[k] = st.g[k][idx];
+      is_plane = st.type[idx] != 0;
+    }
+    if (pp.marg_mode && valid && s >= pp.marg_later_local) valid = false;  // empty drop set: not part of the prior
+    int key = valid ? s : -1;
+    // process the distinct keys present in this slab in ascending order (1 for time-sorted input)
+    unsigned pending = __ballot_sync(0xffffffffu, key >= 0);
+    while (pending) {
+      int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
+      bool mine = (key == kmin) && ((pending >> lane) & 1);
+      double r = 0.0;
+      double J[24];
+      bool contributes = false;
+      if (mine) {
+        loam_eval(W, s, u, pL, is_plane, geo, st.sh, JAC, &r, J);
+        contributes = true;
+        if (pp.marg_mode) {  // trajectory_estimator.cpp:729-741: only |r| / w < 0.05 enters the prior
+          double dist = fabs(r / st.sh.weight);
+          if (!(dist < 0.05)) contributes = false;
+        }
+        if (contributes) {
+          if (s + 3 >= pp.kf || pp.marg_mode) cost += 0.5 * r * r; else fcost += 0.5 * r * r;
+        }
+      }
+      if (JAC) {
+        if (kmin != acc_key) {
+          flush_record<4>(acc, acc_key, slot, warp_global, rb, lane);
+          acc.zero();
+          acc_key = kmin;
+        }
+#pragma unroll
+        for (int c = 0; c < 24; c++) Jt[c * kJtStride + lane] = contributes ? J[c] : 0.0;
+        Jt[24 * kJtStride + lane] = contributes ? r : 0.0;
+        __syncwarp();
+        acc.accumulate(Jt, lane);
+        __syncwarp();
+      }
+      pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+  if (JAC) {
+    flush_record<4>(acc, acc_key, slot, warp_global, rb, lane);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32)
+      if (sidx >= slot) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
+  // deterministic butterfly
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
+  }
+  if (lane == 0) {
+    rb.cost[2 * warp_global] = cost;
+    rb.cost[2 * warp_global + 1] = fcost;
+  }
+}
+
+// Level-1 reduction: CTA (key, part) sums, in record order, the payloads whose key matches over its share of
+// the record slots.  out[(key * P + part) * RD + e].
+__global__ void reduce_records_kernel(const double* payload, const int* key, int n_slots, int rec_doubles, int P,
+                                      double* out, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  const int k = blockIdx.x, part = blockIdx.y;
+  const int chunk = (n_slots + P - 1) / P;
+  const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
+  for (int e = threadIdx.x; e < rec_doubles; e += blockDim.x) {
+    double acc = 0.0;
+    for (int r = r0; r < r1; r++)
+      if (key[r] == k) acc += payload[(size_t)r * rec_doubles + e];
+    out[((size_t)k * P + part) * rec_doubles + e] = acc;
+  }
+}
+
+// Sum of per-warp costs in warp order (single CTA, deterministic tree over fixed positions).
+__global__ void reduce_cost_kernel(const double* warp_cost, int n_warps, double* out2, int accumulate, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  __shared__ double sh[2][256];
+  double c = 0, f = 0;
+  for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
+    c += warp_cost[2 * i];
+    f += warp_cost[2 * i + 1];
+  }
+  sh[0][threadIdx.x] = c;
+  sh[1][threadIdx.x] = f;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (accumulate) {
+      out2[0] += sh[0][0];
+      out2[1] += sh[1][0];
+    } else {
+      out2[0] = sh[0][0];
+      out2[1] = sh[1][0];
+    }
+  }
+}
+
+}  // namespace clic
+
+namespace clic {
+
+// ---------------- K2: IMUFactor over a stream ----------------
+struct ImuStream {
+  int64_t n;
+  const int64_t* t_ns;  // measurement time (without offset); kDropped if dropped at add time
+  const double* gyro[3];
+  const double* accel[3];
+  double info[6];
+  double loss_a;
+  int bias_slot;
+  int marg_always;  // marg mode: a non-knot block of these factors is dropped, so they all enter the prior
+};
+
+template <int NT>
+struct SmemRowSink {
+  double* Jt;
+  int lane;
+  bool on;
+  WarpAcc<NT>* acc;
+  __device__ __forceinline__ void put(int, int col, double v) { Jt[col * kJtStride + lane] = on ? v : 0.0; }
+  __device__ __forceinline__ void row_done(int) {
+    __syncwarp();
+    acc->accumulate(Jt, lane);
+    __syncwarp();
+  }
+};
+struct NullSink {
+  __device__ __forceinline__ void put(int, int, double) {}
+  __device__ __forceinline__ void row_done(int) {}
+};
+
+// Local columns (solve, NT=4): [knots 0..23 | bg 24..26 | ba 27..29 | toff 30 | r 31]
+//               (marg,  NT=5): [knots 0..23 | bg | ba | gravity 30..32 | toff 33 | r 34 | pad]
+template <bool JAC, bool MARG>
+__global__ void __launch_bounds__(kThreads, 1)
+imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
+  constexpr int NT = MARG ? 5 : 4;
+  if (pp.ctl && pp.ctl[0]) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
+  ImuShared sh;
+#pragma unroll
+  for (int i = 0; i < 6; i++) sh.info[i] = st.info[i];
+  const double* bias = pp.state + pp.sl.off_bias() + 6 * st.bias_slot;
+  sh.bg = mk(bias[0], bias[1], bias[2]);
+  sh.ba = mk(bias[3], bias[4], bias[5]);
+  const double* gr = pp.state + pp.sl.off_grav();
+  sh.gravity = mk(gr[0], gr[1], gr[2]);
+  sh.loss_a = st.loss_a;
+  sh.inv_dt = 1e9 / double(pp.dt_ns);
+  const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 0];  // (int64_t)time_offset_in_ns, trajectory_value_factor.h:175
+
+  WarpAcc<NT> acc;
+  acc.zero();
+  int acc_key = -1, slot = 0;
+  double cost = 0.0, fcost = 0.0;
+  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  for (int sl = 0; sl < slabs_per_warp; sl++) {
+    if ((slab0 + sl) * 32 >= st.n) break;
+    const int64_t idx = (slab0 + sl) * 32 + lane;
+    int64_t t = kDropped;
+    if (idx < st.n) t = st.t_ns[idx];
+    int s = -1;
+    double u = 0.0;
+    bool valid = (t != kDropped) && index_ns(t + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u);
+    V3 gy = mk(0, 0, 0), ac = mk(0, 0, 0);
+    if (valid) {
+      gy = mk(st.gyro[0][idx], st.gyro[1][idx], st.gyro[2][idx]);
+      ac = mk(st.accel[0][idx], st.accel[1][idx], st.accel[2][idx]);
+    }
+    // marg set membership: the drop set is non-empty iff an extra block is dropped (marg_always) or one of the
+    // knots is older than ctrl_to_be_opt_later (trajectory_estimator.cpp:208-232)
+    if (MARG && valid && !st.marg_always && s >= pp.marg_later_local) valid = false;
+    int key = valid ? s : -1;
+    unsigned pending = __ballot_sync(0xffffffffu, key >= 0);
+    while (pending) {
+      int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
+      bool mine = (key == kmin) && ((pending >> lane) & 1);
+      if (JAC) {
+        if (kmin != acc_key) {
+          flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+          acc.zero();
+          acc_key = kmin;
+        }
+        SmemRowSink<NT> sink;
+        sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
+        double rho = imu_eval<MARG>(W, mine ? s : kmin, mine ? u : 0.0, gy, ac, sh, true, sink);
+        if (mine) cost += 0.5 * rho;  // an IMU factor always has a free (or marginalised) parameter in shipped use
+      } else {
+        if (mine) {
+          NullSink sink;
+          cost += 0.5 * imu_eval<MARG>(W, s, u, gy, ac, sh, false, sink);
+        }
+      }
+      pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+  if (JAC) {
+    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
+  }
+  if (lane == 0) {
+    rb.cost[2 * warp_global] = cost;
+    rb.cost[2 * warp_global + 1] = fcost;
+  }
+}
+
+// ---------------- assembly of the dense normal equations ----------------
+// One descriptor per factor stream whose records were reduced to per-key blocks.
+struct StreamDesc {
+  const double* part;    // [n_keys][P][rd]
+  const double* overflow;  // [n_keys][rd] atomics fallback accumulators (all zero for time-sorted input)
+  int n_keys, P, NT, rd;
+  int r_col;             // local column holding r~
+  int n_extra;           // local columns 24 .. 24+n_extra-1 map to extra_global[] (-1: constant, dropped)
+  int extra_global[12];
+};
+
+struct ColMaps {
+  int D, K;
+  const int* knot_col;   // [K] column of knot's dtheta (dp = +3), -1 if constant
+  const int* col_knot;   // [D] knot of a column (-1: not a knot column)
+  const int* col_sub;    // [D] 0..5 within the knot
+};
+
+__device__ __forceinline__ double block_entry(const double* blk, int NT, int la, int lb) {
+  int ta = la >> 3, tb = lb >> 3;
+  if (ta > tb) { int t = ta; ta = tb; tb = t; t = la; la = lb; lb = t; }
+  return blk[tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7)];
+}
+
+// H[gi][gj] (upper, mirrored) and b[gi]: owner-computes gather over the per-key blocks.  One thread per entry.
+__global__ void assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs, int n_desc, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  const int D = cm.D;
+  const int n_upper = D * (D + 1) / 2;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_upper + D) return;
+  int gi, gj;
+  bool is_b = tid >= n_upper;
+  if (is_b) {
+    gi = tid - n_upper;
+    gj = -1;
+  } else {  // unrank (gi <= gj) from row-major upper-triangular index
+    int rem = tid;
+    gi = 0;
+    while (rem >= D - gi) { rem -= D - gi; gi++; }
+    gj = gi + rem;
+  }
+  const int ki = cm.col_knot[gi], ci = cm.col_sub[gi];
+  const int kj = is_b ? -1 : cm.col_knot[gj], cj = is_b ? 0 : cm.col_sub[gj];
+  double acc = 0.0;
+  for (int d = 0; d < n_desc; d++) {
+    const StreamDesc& sd = descs[d];
+    // local column candidates of gi / gj inside a block with key s
+    int ei = -1, ej = -1;  // extra local columns
+    for (int e = 0; e < sd.n_extra; e++) {
+      if (sd.extra_global[e] == gi) ei = 24 + e;
+      if (!is_b && sd.extra_global[e] == gj) ej = 24 + e;
+    }
+    if (ki < 0 && ei < 0) continue;
+    if (!is_b && kj < 0 && ej < 0) continue;
+    int s_lo = 0, s_hi = sd.n_keys - 1;
+    if (ki >= 0) { s_lo = max(s_lo, ki - 3); s_hi = min(s_hi, ki); }
+    if (!is_b && kj >= 0) { s_lo = max(s_lo, kj - 3); s_hi = min(s_hi, kj); }
+    for (int s = s_lo; s <= s_hi; s++) {
+      const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
+      const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
+      const double* blk = sd.part + (size_t)s * sd.P * sd.rd;
+      for (int p = 0; p < sd.P; p++) acc += block_entry(blk + (size_t)p * sd.rd, sd.NT, la, lb);
+      acc += block_entry(sd.overflow + (size_t)s * sd.rd, sd.NT, la, lb);
+    }
+  }
+  if (is_b) {
+    b[gi] = acc;
+  } else {
+    H[(size_t)gi * D + gj] = acc;
+    H[(size_t)gj * D + gi] = acc;
+  }
+}
+
+// BiasFactor (trajectory_value_factor.h:65-126) added to H, b, cost by one thread (6 residuals, +-I Jacobians).
+struct BiasFactorDesc {
+  int slot_i, slot_j;
+  double sqrt_info[6];   // info / sqrt(dt)
+  int col_gi, col_gj, col_ai, col_aj;  // columns (-1 constant)
+};
+__global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, StateLayout sl, double* H, double* b, int D,
+                                   double* cost2, int jac, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double* bi = state + sl.off_bias() + 6 * bf.slot_i;
+  const double* bj = state + sl.off_bias() + 6 * bf.slot_j;
+  double c = 0.0;
+  bool any_free = bf.col_gi >= 0 || bf.col_gj >= 0 || bf.col_ai >= 0 || bf.col_aj >= 0;
+  for (int r = 0; r < 6; r++) {
+    const double w = bf.sqrt_info[r];
+    const double res = w * (bj[r] - bi[r]);
+    c += res * res;
+    if (!jac) continue;
+    const int ci = (r < 3 ? bf.col_gi : bf.col_ai), cj = (r < 3 ? bf.col_gj : bf.col_aj);
+    const int o = r % 3;
+    if (ci >= 0) {
+      H[(size_t)(ci + o) * D + ci + o] += w * w;
+      b[ci + o] += -w * res;
+    }
+    if (cj >= 0) {
+      H[(size_t)(cj + o) * D + cj + o] += w * w;
+      b[cj + o] += w * res;
+    }
+    if (ci >= 0 && cj >= 0) {
+      H[(size_t)(ci + o) * D + cj + o] += -w * w;
+      H[(size_t)(cj + o) * D + ci + o] += -w * w;
+    }
+  }
+  cost2[any_free ? 0 : 1] += 0.5 * c;
+}
+
+// K0 at add time: double seconds -> int64 ns with the reference's truncation and window test
+// (trajectory_estimator.cpp:272-292); AoS(3n) -> planar.
+__global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* point, const int32_t* geo_type,
+                                 const double* geo_plane, const double* geo_normal, const double* geo_point,
+                                 int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0, double* p1, double* p2,
+                                 double* g0, double* g1, double* g2, double* g3, double* g4, double* g5, uint8_t* type,
+                                 unsigned long long* n_dropped) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = (int64_t)(t_s[i] * 1e9);
+  bool ok = !(t < t_lo || t >= t_hi);
+  t_ns[i] = ok ? t : kDropped;
+  if (!ok) atomicAdd(n_dropped, 1ULL);
+  p0[i] = point[3 * i]; p1[i] = point[3 * i + 1]; p2[i] = point[3 * i + 2];
+  const bool plane = geo_type[i] == 1;
+  type[i] = plane ? 1 : 0;
+  if (plane) {
+    g0[i] = geo_plane[4 * i]; g1[i] = geo_plane[4 * i + 1]; g2[i] = geo_plane[4 * i + 2]; g3[i] = geo_plane[4 * i + 3];
+    g4[i] = 0.0; g5[i] = 0.0;
+  } else {
+    g0[i] = geo_point[3 * i]; g1[i] = geo_point[3 * i + 1]; g2[i] = geo_point[3 * i + 2];
+    g3[i] = geo_normal[3 * i]; g4[i] = geo_normal[3 * i + 1]; g5[i] = geo_normal[3 * i + 2];
+  }
+}
+
+__global__ void prep_imu_kernel(int64_t n, const double* t_s, const double* gyro, const double* accel, int64_t t_lo,
+                                int64_t t_hi, int64_t pad, int64_t* t_ns, double* g0, double* g1, double* g2,
+                                double* a0, double* a1, double* a2, unsigned long long* n_dropped) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = (int64_t)(t_s[i] * 1e9);
+  bool ok = !(t - pad < t_lo || t + pad >= t_hi);
+  t_ns[i] = ok ? t : kDropped;
+  if (!ok) atomicAdd(n_dropped, 1ULL);
+  g0[i] = gyro[3 * i]; g1[i] = gyro[3 * i + 1]; g2[i] = gyro[3 * i + 2];
+  a0[i] = accel[3 * i]; a1[i] = accel[3 * i + 1]; a2[i] = accel[3 * i + 2];
+}
+
+// Index probe (clic_get_indices): s, u per factor of a stream at the current offset.
+__global__ void index_probe_kernel(int64_t n, const int64_t* t_ns, int64_t toff, int64_t t0_ns, int64_t dt_ns, int K,
+                                   int32_t* s_out, double* u_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = -1;
+  double u = 0.0;
+  int64_t t = t_ns[i];
+  if (t == kDropped || !index_ns(t + toff, t0_ns, dt_ns, K, &s, &u)) { s = -1; u = 0.0; }
+  s_out[i] = s;
+  u_out[i] = u;
+}
+
+}  // namespace clic

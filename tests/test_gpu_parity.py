@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same seeded synthetic windows.
+Bar (BASELINE.json north_star): indices bit-exact; H and b within 1e-9 relative (FP64)."""
+import numpy as np
+import pytest
+
+from clic_b200 import estimator as E
+from clic_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000):
+    opt = E.default_options(lib)
+    if unlock_bias:
+        opt.lock_ab = opt.lock_wb = 0
+    if unlock_toff:
+        opt.lock_t_offset[0] = 0
+        opt.t_offset_padding_ns = pad
+    est = E.TrajectoryEstimator(sw.window, opt, lib)
+    est.SetFixedIndex(fixed)
+    dropped = S.add_all_factors(est, sw, bias_factor=bias_factor)
+    return est, dropped
+
+
+def compare_eval(cuda, oracle, sw, **kw):
+    eg, dg = build(cuda, sw, **kw)
+    eo, do = build(oracle, sw, **kw)
+    assert dg == do
+    Lg, Lo = eg.layout(), eo.layout()
+    assert Lg.D == Lo.D
+    for stream in (0, 1):
+        sg, ug = eg.indices(stream)
+        so, uo = eo.indices(stream)
+        assert np.array_equal(sg, so)          # feature-to-knot indexing: bit-exact
+        assert np.array_equal(ug, uo)
+    Hg, bg, cg, fg = eg.Evaluate()
+    Ho, bo, co, fo = eo.Evaluate()
+    assert rel(Hg, Ho) < REL, rel(Hg, Ho)
+    assert rel(bg, bo) < REL, rel(bg, bo)
+    assert abs(cg - co) <= REL * abs(co)
+    assert abs(fg - fo) <= REL * max(abs(fo), 1.0)
+    assert np.array_equal(Hg, Hg.T)
+    return Hg, bg
+
+
+def test_c1_lidar_planes_imu(cuda, oracle):
+    """BASELINE config 1: 10 knots, 2k point-to-plane + 200 IMU, everything but the knots locked."""
+    compare_eval(cuda, oracle, S.config(1), bias_factor=False)
+
+
+def test_c1_fixed_knots_and_bias(cuda, oracle):
+    compare_eval(cuda, oracle, S.config(1), fixed=3, unlock_bias=True)
+
+
+def test_lidar_only_lines(cuda, oracle):
+    sw = S.make_window(10, n_lidar=3000, n_imu=0, line_fraction=1.0, seed=5)
+    compare_eval(cuda, oracle, sw)
+
+
+def test_c2_mixed_time_offset(cuda, oracle):
+    """BASELINE config 2 at 1/10 size: planes+lines, Cauchy IMU, IMU time offset unlocked (arrow column)."""
+    sw = S.config(2, 0.1)
+    compare_eval(cuda, oracle, sw, unlock_bias=True, unlock_toff=True)
+
+
+def test_large_rotations_random_knots(cuda, oracle):
+    sw = S.make_window(12, n_lidar=1500, n_imu=150, line_fraction=0.4, seed=9, random_knots=True)
+    compare_eval(cuda, oracle, sw, unlock_bias=True)
+
+
+def test_ragged_and_out_of_window(cuda, oracle):
+    """Counts that are not multiples of 32, measurements outside the window (silently dropped identically)."""
+    sw = S.make_window(10, n_lidar=777, n_imu=45, line_fraction=0.5, seed=3)
+    sw.lidar["t_point"] = sw.lidar["t_point"].copy()
+    sw.lidar["t_point"][:5] = -0.01
+    sw.lidar["t_point"][-7:] = 0.7 + np.arange(7) * 1e-3
+    sw.imu["timestamp"] = sw.imu["timestamp"].copy()
+    sw.imu["timestamp"][-3:] = 0.71
+    compare_eval(cuda, oracle, sw)
+
+
+def test_single_factor_and_tiny(cuda, oracle):
+    sw = S.make_window(10, n_lidar=1, n_imu=1, seed=4)
+    compare_eval(cuda, oracle, sw)
+
+
+def test_unsorted_input(cuda, oracle):
+    """Time-unsorted factors exercise the multi-key warp loop and the atomics overflow path."""
+    sw = S.make_window(10, n_lidar=4000, n_imu=300, line_fraction=0.3, seed=8)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(4000)
+    for k in ("t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point"):
+        sw.lidar[k] = np.ascontiguousarray(sw.lidar[k][perm])
+    perm = rng.permutation(300)
+    for k in ("timestamp", "gyro", "accel"):
+        sw.imu[k] = np.ascontiguousarray(sw.imu[k][perm])
+    eg, _ = build(cuda, sw)
+    eo, _ = build(oracle, sw)
+    Hg, bg, cg, _ = eg.Evaluate()
+    Ho, bo, co, _ = eo.Evaluate()
+    assert rel(Hg, Ho) < REL and rel(bg, bo) < REL and abs(cg - co) <= REL * abs(co)
+
+
+def test_40_knot_window(cuda, oracle):
+    """BASELINE config 4 geometry (40 knots, D = 240) without the prior."""
+    compare_eval(cuda, oracle, S.config(4, 0.25), fixed=-1)
+
+
+def test_deterministic(cuda):
+    sw = S.config(1)
+    e1, _ = build(cuda, sw)
+    H1, b1, c1, _ = e1.Evaluate()
+    for _ in range(3):
+        H2, b2, c2, _ = e1.Evaluate()
+        assert np.array_equal(H1, H2) and np.array_equal(b1, b2) and c1 == c2
+
+
+def test_prior_factor(cuda, oracle):
+    """MarginalizationFactor contribution with a synthetic dense prior over knots + bias."""
+    from clic_b200._abi import BLOCK_BIAS_ACCEL, BLOCK_BIAS_GYRO, BLOCK_KNOT_POS, BLOCK_KNOT_ROT
+    sw = S.config(1)
+    rng = np.random.default_rng(1)
+    kinds, ids, x0 = [], [], []
+    for k in range(2, 7):
+        kinds += [BLOCK_KNOT_ROT, BLOCK_KNOT_POS]
+        ids += [k, k]
+        q = S.qmul(sw.window.knot_q[k], S.so3_exp(rng.normal(0, 0.01, 3)))
+        x0 += [q, np.concatenate([sw.window.knot_p[k] + rng.normal(0, 0.01, 3), [0]])]
+    kinds += [BLOCK_BIAS_GYRO, BLOCK_BIAS_ACCEL]
+    ids += [1, 1]
+    x0 += [np.concatenate([sw.window.bias[1, :3] + 1e-3, [0]]), np.concatenate([sw.window.bias[1, 3:] - 1e-3, [0]])]
+    n = 5 * 6 + 6
+    J0 = rng.normal(size=(n, n)) * 30
+    r0 = rng.normal(size=n)
+    res = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        pr = E.Prior.create(lib, J0, r0, kinds, ids, np.array(x0))
+        opt = E.default_options(lib)
+        opt.lock_ab = opt.lock_wb = 0
+        est = E.TrajectoryEstimator(sw.window, opt, lib)
+        est.SetFixedIndex(3)
+        est.AddMarginalizationFactor(pr)
+        S.add_all_factors(est, sw)
+        res[name] = est.Evaluate()
+        A, g = pr.normal()
+        res[name + "n"] = (A, g)
+    assert rel(res["g"][0], res["o"][0]) < REL
+    assert rel(res["g"][1], res["o"][1]) < REL
+    assert abs(res["g"][2] - res["o"][2]) <= REL * abs(res["o"][2])
+    assert rel(res["gn"][0], res["on"][0]) < 1e-12 and rel(res["gn"][1], res["on"][1]) < 1e-12
