@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — factor residual+Jacobian evals/s of the fused pass on a synthetic fixed-lag window.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle restatement of the reference
+                                                           # arithmetic on the host cores (the reference itself
+                                                           # cannot be built: it needs Eigen + Ceres)
+A "step" is one fused residual + Jacobian + normal-equation pass (K1-K5) over the whole window, inputs resident
+in HBM; `e2e` repeats the step through the C ABI from pinned host buffers (create estimator, add factors = H2D,
+evaluate, read H and b back = D2H).  Workload: BASELINE.json configs[4] (the one north_star's target is quoted on):
+1M LiDAR features (70 % plane / 30 % line) + 200k IMU samples + 20k visual observations, 10-knot window.
+With N > 1 the factors are sharded contiguously in time across ranks and H|b|cost is all-reduced (strong scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from clic_b200 import synthetic as S  # noqa: E402
+
+METRIC = "factor_evals_per_s"
+UNIT = "factor-evals/s"
+FULL = dict(n_knots=10, n_lidar=1_000_000, n_imu=200_000, n_landmarks=2000, obs_per_landmark=10, line_fraction=0.3,
+            seed=20230220)
+WORKLOAD = "C5: 10-knot window, 1M LiDAR (70% plane / 30% line) + 200k IMU (Cauchy) + 20k visual, biases free"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_workload(scale=1.0, with_visual=True):
+    kw = dict(FULL)
+    kw["n_lidar"] = max(64, int(kw["n_lidar"] * scale))
+    kw["n_imu"] = max(16, int(kw["n_imu"] * scale))
+    kw["n_landmarks"] = max(2, int(kw["n_landmarks"] * scale)) if with_visual else 0
+    return S.make_window(name="C5", **kw)
+
+
+def shard(sw, rank, world):
+    """Contiguous-in-time shard of every factor stream."""
+    if world == 1:
+        return sw
+    import copy
+    out = copy.copy(sw)
+
+    def cut(d, keys):
+        n = len(d[keys[0]])
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        r = dict(d)
+        for k in keys:
+            r[k] = np.ascontiguousarray(d[k][lo:hi])
+        return r
+    out.lidar = cut(sw.lidar, ["t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point"])
+    out.imu = cut(sw.imu, ["timestamp", "gyro", "accel"])
+    if len(sw.image.get("t_i", ())):
+        out.image = cut(sw.image, ["t_i", "p_i", "t_j", "p_j", "landmark"])
+    return out
+
+
+def algorithmic_bytes(sw):
+    """packed-SoA minimum per factor, read once."""
+    gt = sw.lidar["geo_type"]
+    n_plane = int((gt == 1).sum())
+    n_line = int(len(gt) - n_plane)
+    n_imu = len(sw.imu.get("timestamp", ()))
+    n_vis = len(sw.image.get("t_i", ()))
+    return dict(lidar=64 * n_plane + 80 * n_line, imu=56 * n_imu, visual=56 * n_vis,
+                n_plane=n_plane, n_line=n_line, n_imu=n_imu, n_vis=n_vis)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def pinned(a):
+    """Copy a numpy array into page-locked host memory (the e2e path copies from pinned buffers)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy(), t
+
+
+def cpu_arm(sw, threads, reps):
+    """Oracle (CPU restatement of the reference arithmetic) timed on the host cores: factor-evals/s of one fused pass."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from clic_b200 import estimator as E
+    lib = oracle_lib.load()
+    lib.clic_oracle_set_threads(int(threads))
+    opt = E.default_options(lib)
+    opt.lock_ab = opt.lock_wb = 0
+    est = E.TrajectoryEstimator(sw.window, opt, lib)
+    est.SetFixedIndex(-1)
+    S.add_all_factors(est, sw)
+    n = sw.n_factors
+    est.linearize_async(1)  # warm
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        est.linearize_async(1)
+        ts.append(time.perf_counter() - t0)
+    est.close()
+    lib.clic_oracle_set_threads(1)
+    return n / min(ts), n / (sum(ts) / len(ts)), ts
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frac = 0.05
+    sw = make_workload(frac, with_visual=HAVE_VISUAL)
+    n = sw.n_factors
+    # W warm-up + K timed steps, each a pass over the bounded sample with all host threads
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from clic_b200 import estimator as E
+    lib = oracle_lib.load()
+    lib.clic_oracle_set_threads(cores)
+    opt = E.default_options(lib)
+    opt.lock_ab = opt.lock_wb = 0
+    est = E.TrajectoryEstimator(sw.window, opt, lib)
+    est.SetFixedIndex(-1)
+    S.add_all_factors(est, sw)
+    for _ in range(args.warmup):
+        est.linearize_async(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        est.linearize_async(1)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{frac:.0%} of the workload per step ({n} factors)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} factors per step ({frac:.0%} of C5), oracle restatement, std::thread x{cores}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference needs Eigen+Ceres (absent, no network): CPU arm = oracle restatement of its arithmetic",
+    }
+    print(json.dumps(line))
+
+
+HAVE_VISUAL = False  # flipped once the visual kernel lands
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; invalidates the number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from clic_b200 import estimator as E
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = E.cuda_library()
+    stream = torch.cuda.Stream()
+
+    sw_full = make_workload(args.scale, with_visual=HAVE_VISUAL)
+    sw = shard(sw_full, rank, world)
+    n_total = sw_full.n_factors
+    ab = algorithmic_bytes(sw)
+
+    def new_estimator(srcs=None):
+        opt = E.default_options(lib)
+        opt.lock_ab = opt.lock_wb = 0
+        opt.device = local_rank
+        opt.stream = C.c_void_p(stream.cuda_stream)
+        est = E.TrajectoryEstimator(sw.window, opt, lib)
+        est.SetFixedIndex(-1)
+        S.add_all_factors(est, srcs or sw, bias_factor=(rank == 0))
+        return est
+
+    est = new_estimator()
+    if world > 1:
+        est.comm_init_torch(dist, rank, world)
+    D = est.layout().D
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            est.linearize_async(1)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = est.num_kernel_launches()
+        est.profile_enable(True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev:
+            flush.fill_(1)  # evict the 126 MB L2 between timed iterations (not timed)
+            a.record(stream)
+            est.linearize_async(1)
+            b.record(stream)
+        barrier()
+        step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+        prof_ms, prof_n = est.profile_read()
+        est.profile_enable(False)
+        launches = est.num_kernel_launches() - launches0
+        clocks = sampler.stop()
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n_total * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers -> estimator -> H, b back, every step ----
+    keep = []
+    src = type(sw)(window=sw.window, gt_knot_q=sw.gt_knot_q, gt_knot_p=sw.gt_knot_p, name=sw.name)
+    h2d = 0
+    for name in ("lidar", "imu", "image"):
+        d = dict(getattr(sw, name))
+        for k, v in d.items():
+            if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] > 16:
+                d[k], t = pinned(v)
+                keep.append(t)
+                h2d += d[k].nbytes
+        setattr(src, name, d)
+    h2d += 8 * (7 * sw.window.n_knots + sw.window.bias.size + 6)
+    e2e_steps = max(3, min(args.steps, 10))
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            e = new_estimator(src)
+            e.Evaluate()
+            e.close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e = new_estimator(src)
+            if world > 1:
+                e.comm_init_torch(dist, rank, world)
+            H, b, cost, _ = e.Evaluate()
+            e.close()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_total * e2e_steps / e2e_s
+    d2h = 8 * (D * D + D + 2)
+
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peaks()
+    loam_ms = prof_ms[0] / max(prof_n[0], 1)
+    roofline = {
+        "bound": "hbm", "kernel": "loam_kernel<true> (LiDAR factor eval + DMMA J^T J)",
+        "achieved": ab["lidar"] / (loam_ms * 1e-3) / 1e9 if loam_ms > 0 else None, "peak": peak, "unit": "GB/s",
+        "frac": (ab["lidar"] / (loam_ms * 1e-3) / 1e9 / peak) if loam_ms > 0 else None, "traffic": None,
+        "peak_kind": f"of {peak_kind}", "algorithmic_bytes_per_launch": ab["lidar"], "kernel_ms": loam_ms,
+        "kernel_share_of_step": float(prof_ms[0] / prof_ms.sum()) if prof_ms.sum() > 0 else None,
+        "per_class_ms_per_step": {k: float(prof_ms[i] / args.steps) for i, k in enumerate(
+            ["lidar", "imu", "visual", "reduce_assemble", "prior_bias", "lm_step", "allreduce", "marginalize"])},
+        "note": "binding limit is the FP64 pipe, not HBM (SURVEY.md §7 hard part 1); FP64 DFMA/DMMA peak measured "
+                "36.3/37.1 TFLOP/s on one shared pipe (profiles/r01_fp64_peaks.txt)",
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.scale == 1.0 else f"DEBUG scale={args.scale} of " + WORKLOAD,
+                   "factors": {"lidar_plane": ab["n_plane"] * 1, "lidar_line": ab["n_line"], "imu": ab["n_imu"],
+                               "visual": ab["n_vis"], "total_all_ranks": n_total},
+                   "D": D, "l2": "flushed between timed iterations (256 MiB write)", "visual_kernel": HAVE_VISUAL,
+                   "sharding": f"contiguous-in-time over {world} rank(s), H|b|cost all-reduce"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        frac = 0.05
+        sample = make_workload(frac * args.scale, with_visual=HAVE_VISUAL)
+        best_mt, _, ts_mt = cpu_arm(sample, cores, 3)
+        best_1t, _, ts_1t = cpu_arm(sample, 1, 2)
+        line["cpu_baseline"] = {"value": best_mt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{sample.n_factors} factors ({frac:.0%} of the workload), oracle restatement "
+                                          f"of the reference arithmetic (not Ceres), best of 3 passes",
+                                "single_thread_value": best_1t}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

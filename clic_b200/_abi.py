@@ -137,6 +137,8 @@ PROTOTYPES = {
     "clic_linearize_async": (C.c_int, [H, C.c_int32]),
     "clic_synchronize": (C.c_int, [H]),
     "clic_num_kernel_launches": (C.c_int, [H, c_int64_p]),
+    "clic_profile_enable": (C.c_int, [H, C.c_int32]),
+    "clic_profile_read": (C.c_int, [H, c_double_p, c_int64_p]),
 }
 
 

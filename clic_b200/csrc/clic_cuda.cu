@@ -30,20 +30,30 @@ int fail(int code, const std::string& m) {
       return fail(CLIC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
   } while (0)
 
+// Device buffer from the stream-ordered memory pool (cudaMallocAsync): an estimator is built per solve like the
+// reference's (trajectory_manager.cpp:637), so allocations must be cheap; the pool keeps freed blocks cached.
+thread_local cudaStream_t g_alloc_stream = nullptr;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  cudaStream_t st = nullptr;
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
   cudaError_t ensure(size_t n) {
     if (n <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
     bytes = 0;
-    cudaError_t e = cudaMalloc(&p, n);
+    st = g_alloc_stream;
+    cudaError_t e = cudaMallocAsync(&p, n, st);
     if (e == cudaSuccess) bytes = n;
     return e;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct AllocScope {  // every ABI entry point that may allocate names the estimator's stream
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t s) : prev(g_alloc_stream) { g_alloc_stream = s; }
+  ~AllocScope() { g_alloc_stream = prev; }
 };
 
 // Launch geometry + record buffers of one factor stream.
@@ -126,6 +136,27 @@ struct clic_estimator {
   int64_t launches = 0;
   bool bounds_toff[3] = {false, false, false};
   double toff_lo[3], toff_hi[3];
+  // profiling (clic_profile_*)
+  bool prof_on = false;
+  struct ProfSpan { int kind; cudaEvent_t a, b; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t new_event() {
+    cudaEvent_t e;
+    if (!ev_pool.empty()) { e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+  }
+  void prof_begin(int kind) {
+    if (!prof_on) return;
+    ProfSpan s{kind, new_event(), new_event()};
+    cudaEventRecord(s.a, stream);
+    prof_spans.push_back(s);
+  }
+  void prof_end() {
+    if (!prof_on) return;
+    cudaEventRecord(prof_spans.back().b, stream);
+  }
 
   int64_t minTimeNs() const { return t0_ns; }
   int64_t maxTimeNs() const { return t0_ns + (int64_t)(K - 4 + 1) * dt_ns - 1; }
@@ -327,16 +358,24 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     const size_t smem = factor_smem_bytes(E->K, 4);
     if (jac) {
       CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+      E->prof_begin(0);
       loam_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->prof_end();
+      E->prof_begin(3);
       dim3 g(ex.n_keys, ex.P);
       reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
                                                       ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      E->prof_end();
       E->launches += 2;
     } else {
+      E->prof_begin(0);
       loam_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->prof_end();
       E->launches += 1;
     }
+    E->prof_begin(3);
     reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
+    E->prof_end();
     E->launches += 1;
   }
   for (auto& b : E->imu) {
@@ -345,16 +384,24 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     const size_t smem = factor_smem_bytes(E->K, 4);
     if (jac) {
       CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+      E->prof_begin(1);
       imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->prof_end();
+      E->prof_begin(3);
       dim3 g(ex.n_keys, ex.P);
       reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
                                                       ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      E->prof_end();
       E->launches += 2;
     } else {
+      E->prof_begin(1);
       imu_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      E->prof_end();
       E->launches += 1;
     }
+    E->prof_begin(3);
     reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
+    E->prof_end();
     E->launches += 1;
   }
   if (jac && D > 0) {
@@ -365,8 +412,10 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     cm.col_knot = E->d_col_knot.as<int>();
     cm.col_sub = E->d_col_sub.as<int>();
     const int n_entries = D * (D + 1) / 2 + D;
+    E->prof_begin(3);
     assemble_kernel<<<(n_entries + 127) / 128, 128, 0, E->stream>>>(E->d_H.as<double>(), E->d_b.as<double>(), cm,
                                                                     E->d_descs.as<StreamDesc>(), E->n_desc, ctl);
+    E->prof_end();
     E->launches += 1;
   }
   for (auto& bf : E->bias_f) {
@@ -461,6 +510,13 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     E->own_stream = true;
   }
+  {
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, E->device));
+    uint64_t thr = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  AllocScope alloc_scope(E->stream);
   CU(E->d_state.ensure(E->sl.size() * sizeof(double)));
   CU(E->d_cand.ensure(E->sl.size() * sizeof(double)));
   CU(E->d_cost2.ensure(8 * sizeof(double)));
@@ -482,9 +538,17 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
 
 CLIC_API int clic_destroy(clic_estimator* h) {
   if (!h) return CLIC_OK;
-  cudaStreamSynchronize(h->stream);
-  if (h->own_stream) cudaStreamDestroy(h->stream);
-  delete h;
+  cudaSetDevice(h->device);
+  cudaStream_t st = h->stream;
+  const bool own = h->own_stream;
+  cudaStreamSynchronize(st);
+  for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  delete h;  // buffers go back to the stream-ordered pool
+  if (own) {
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
   return CLIC_OK;
 }
 
@@ -504,6 +568,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   std::unique_ptr<LoamBatch> B(new LoamBatch);
   // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
   const int S = CLIC_SENSOR_LIDAR;
@@ -566,6 +631,7 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   std::unique_ptr<ImuBatch> B(new ImuBatch);
   const int S = CLIC_SENSOR_IMU;
   const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
@@ -638,6 +704,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
 CLIC_API int clic_add_prior(clic_estimator* E, const clic_prior* prior, int32_t n_drop, const int32_t* drop_blocks) {
   if (!ok_handle(E) || !prior) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   std::unique_ptr<clic_estimator::PriorRef> R(new clic_estimator::PriorRef);
   R->p = prior;
   if (n_drop > 0) R->drop.assign(drop_blocks, drop_blocks + n_drop);
@@ -706,6 +773,7 @@ CLIC_API int clic_get_layout(clic_estimator* E, clic_layout* out) {
 CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost, double* fixed_cost) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   int rc = ensure_layout(E);
   if (rc) return rc;
   rc = fill_prior_columns(E);
@@ -729,6 +797,7 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (stream < 0 || stream > 3) return fail(CLIC_ERR_BAD_ARGUMENT, "stream");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   int64_t total = 0;
   if (stream == 0) for (auto& b : E->loam) total += b->st.n;
   if (stream == 1) for (auto& b : E->imu) total += b->st.n;
@@ -766,6 +835,7 @@ CLIC_API int clic_solve(clic_estimator* E, int32_t max_iterations, clic_summary*
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (!E->opt.lock_g) return fail(CLIC_ERR_UNSUPPORTED, "gravity must be locked (lock_g = 1)");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   int rc = ensure_layout(E);
   if (rc) return rc;
   if ((rc = fill_prior_columns(E))) return rc;
@@ -776,6 +846,7 @@ CLIC_API int clic_read_state(clic_estimator* E, double* knot_q, double* knot_p, 
                              double* inv_depth) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   std::vector<double> h(E->sl.size());
   CU(cudaMemcpyAsync(h.data(), E->d_state.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
@@ -792,6 +863,7 @@ CLIC_API int clic_write_state(clic_estimator* E, const double* knot_q, const dou
                               const double* t_offset_ns, const double* inv_depth) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   auto& h = E->h_state;
   if (knot_q) std::copy(knot_q, knot_q + 4 * E->K, h.begin() + E->sl.off_q());
   if (knot_p) std::copy(knot_p, knot_p + 3 * E->K, h.begin() + E->sl.off_p());
@@ -890,6 +962,7 @@ CLIC_API int clic_comm_init(clic_estimator*, int32_t, int32_t, const uint8_t*) {
 CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
   int rc = ensure_layout(E);
   if (rc) return rc;
   if ((rc = fill_prior_columns(E))) return rc;
@@ -901,6 +974,29 @@ CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
 CLIC_API int clic_synchronize(clic_estimator* E) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaStreamSynchronize(E->stream));
+  return CLIC_OK;
+}
+
+CLIC_API int clic_profile_enable(clic_estimator* E, int32_t enable) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  CU(cudaStreamSynchronize(E->stream));
+  for (auto& sp : E->prof_spans) { E->ev_pool.push_back(sp.a); E->ev_pool.push_back(sp.b); }
+  E->prof_spans.clear();
+  E->prof_on = enable != 0;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_profile_read(clic_estimator* E, double ms[8], int64_t launches[8]) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  CU(cudaStreamSynchronize(E->stream));
+  for (int i = 0; i < 8; i++) { if (ms) ms[i] = 0; if (launches) launches[i] = 0; }
+  for (auto& sp : E->prof_spans) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+    if (sp.kind >= 0 && sp.kind < 8) { if (ms) ms[sp.kind] += t; if (launches) launches[sp.kind] += 1; }
+  }
   return CLIC_OK;
 }
 

@@ -243,6 +243,14 @@ class TrajectoryEstimator:
     def synchronize(self):
         _check(self.lib, self.lib.clic_synchronize(self.h))
 
+    def profile_enable(self, on=True):
+        _check(self.lib, self.lib.clic_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        ms, cnt = np.zeros(8), np.zeros(8, np.int64)
+        _check(self.lib, self.lib.clic_profile_read(self.h, dptr(ms), cnt.ctypes.data_as(_abi.c_int64_p)))
+        return ms, cnt
+
     def num_kernel_launches(self):
         n = C.c_int64(0)
         _check(self.lib, self.lib.clic_num_kernel_launches(self.h, C.byref(n)))

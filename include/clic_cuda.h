@@ -248,6 +248,12 @@ CLIC_API int clic_comm_init(clic_estimator* h, int32_t n_ranks, int32_t rank, co
 CLIC_API int clic_linearize_async(clic_estimator* h, int32_t reps);
 CLIC_API int clic_synchronize(clic_estimator* h);
 CLIC_API int clic_num_kernel_launches(clic_estimator* h, int64_t* launches);
+/* Per-kernel-class device time, measured with CUDA events on the handle's stream while enabled (bench.py's
+ * roofline line).  Classes: 0 LiDAR factor kernel, 1 IMU factor kernel, 2 visual factor kernel,
+ * 3 record reduction + assembly, 4 prior / bias terms, 5 LM step (scaling, Cholesky, solves, update), 6 all-reduce,
+ * 7 marginalization.  clic_profile_read synchronizes and returns the sums since the last enable. */
+CLIC_API int clic_profile_enable(clic_estimator* h, int32_t enable);
+CLIC_API int clic_profile_read(clic_estimator* h, double ms[8], int64_t launches[8]);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,12 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
+def rel_scaled(Hg, Ho):
+    """Scale-invariant error of H: |dH_ij| / sqrt(H_ii H_jj) (max-norm alone is dominated by the largest block)."""
+    d = np.sqrt(np.maximum(np.diag(Ho), 1e-300))
+    return (np.abs(Hg - Ho) / np.outer(d, d)).max()
+
+
 def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000):
     opt = E.default_options(lib)
     if unlock_bias:
@@ -42,6 +48,7 @@ def compare_eval(cuda, oracle, sw, **kw):
     Hg, bg, cg, fg = eg.Evaluate()
     Ho, bo, co, fo = eo.Evaluate()
     assert rel(Hg, Ho) < REL, rel(Hg, Ho)
+    assert rel_scaled(Hg, Ho) < REL, rel_scaled(Hg, Ho)
     assert rel(bg, bo) < REL, rel(bg, bo)
     assert abs(cg - co) <= REL * abs(co)
     assert abs(fg - fo) <= REL * max(abs(fo), 1.0)
