@@ -282,6 +282,19 @@ int ensure_layout(clic_estimator* E) {
 }
 
 
+int launch_reduce(clic_estimator* E, const StreamExec& ex, const int* ctl) {
+  dim3 g(ex.n_keys, ex.P);
+  const int n_slots = ex.n_warps * kSlotsPerWarp;
+  const size_t smem = (size_t)8 * ex.rd * sizeof(double);
+  switch (ex.NT) {
+    case 4: reduce_records_kernel<20><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 5: reduce_records_kernel<30><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 7: reduce_records_kernel<56><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    default: return 1;
+  }
+  return 0;
+}
+
 int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* state, double* cost2, bool jac,
                  const int* ctl) {
   const int n = pr->p->n, nb = (int)pr->p->blocks.size();
@@ -362,9 +375,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
       loam_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->prof_begin(3);
-      dim3 g(ex.n_keys, ex.P);
-      reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
-                                                      ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
       E->prof_end();
       E->launches += 2;
     } else {
@@ -388,9 +399,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
       imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->prof_begin(3);
-      dim3 g(ex.n_keys, ex.P);
-      reduce_records_kernel<<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(),
-                                                      ex.n_warps * kSlotsPerWarp, ex.rd, ex.P, ex.part.as<double>(), ctl);
+      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
       E->prof_end();
       E->launches += 2;
     } else {
@@ -530,6 +539,9 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   if ((rc = set_smem(loam_kernel<true>, smem4)) || (rc = set_smem(loam_kernel<false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, true>, smem5)))
+    return rc;
+  if ((rc = set_smem(reduce_records_kernel<20>, 8 * 640 * 8)) || (rc = set_smem(reduce_records_kernel<30>, 8 * 960 * 8)) ||
+      (rc = set_smem(reduce_records_kernel<56>, 8 * 1792 * 8)))
     return rc;
   CU(cudaStreamSynchronize(E->stream));
   *out = E.release();

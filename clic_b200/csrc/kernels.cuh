@@ -243,19 +243,44 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
   }
 }
 
-// Level-1 reduction: CTA (key, part) sums, in record order, the payloads whose key matches over its share of
-// the record slots.  out[(key * P + part) * RD + e].
-__global__ void reduce_records_kernel(const double* payload, const int* key, int n_slots, int rec_doubles, int P,
-                                      double* out, const int* ctl) {
+// Level-1 reduction: CTA (key, part) sums the payloads whose key matches over its share of the record slots.
+// Warp w of the CTA takes slots r0+w, r0+w+8, ... (lanes stride the payload, coalesced); the 8 warp sums are then
+// combined through shared memory in warp order: fixed assignment + fixed order => deterministic.
+// out[(key * P + part) * RD + e].  RD <= 32 * kMaxRdPerLane.
+constexpr int kMaxRdPerLane = 56;  // RD = 1792 (NT = 7, visual) / 32
+template <int RDL>                 // doubles per lane = RD / 32
+__global__ void __launch_bounds__(256)
+reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const int* ctl) {
   if (ctl && ctl[0]) return;
+  constexpr int RD = RDL * 32;
+  extern __shared__ double red[];  // [8][RD]
   const int k = blockIdx.x, part = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = (n_slots + P - 1) / P;
   const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
-  for (int e = threadIdx.x; e < rec_doubles; e += blockDim.x) {
-    double acc = 0.0;
-    for (int r = r0; r < r1; r++)
-      if (key[r] == k) acc += payload[(size_t)r * rec_doubles + e];
-    out[((size_t)k * P + part) * rec_doubles + e] = acc;
+  double acc[RDL];
+#pragma unroll
+  for (int i = 0; i < RDL; i++) acc[i] = 0.0;
+  for (int rb = r0 + warp * 32; rb < r1; rb += 8 * 32) {
+    // each lane looks at one slot key, then the warp walks the matching slots in order
+    const int r = rb + lane;
+    unsigned m = __ballot_sync(0xffffffffu, r < r1 && key[r] == k);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const double* src = payload + (size_t)(rb + j) * RD;
+#pragma unroll
+      for (int i = 0; i < RDL; i++) acc[i] += src[i * 32 + lane];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RDL; i++) red[warp * RD + i * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < RD; e += blockDim.x) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w * RD + e];
+    out[((size_t)k * P + part) * RD + e] = s;
   }
 }
 
