@@ -363,7 +363,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
   int rc = ensure_layout(E);
   if (rc) return rc;
   PassParams pp = pass_params(E, state, ctl);
-  CU(cudaMemsetAsync(cost2, 0, 2 * sizeof(double), E->stream));
+  zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
+  E->launches += 1;
   const int D = E->L.D;
   for (auto& b : E->loam) {
     if (b->marg) continue;
@@ -446,6 +447,118 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl))) return rc;
   }
   CU(cudaGetLastError());
+  return CLIC_OK;
+}
+
+// clic_solve: the LM loop runs on the device; the host only enqueues kernels (and, for bounded problems, polls the
+// line-search flag once per sample).
+int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
+  const clic_layout& Lh = E->L;
+  const int D = Lh.D;
+  if (D <= 0) return fail(CLIC_ERR_BAD_ARGUMENT, "nothing to optimise (every parameter block is constant)");
+  const size_t nst = E->sl.size();
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_scale = take(D * 8), o_diag = take(D * 8), o_step = take(D * 8), o_delta = take(D * 8),
+               o_A = take((size_t)D * D * 8), o_tmp = take(nst * 8), o_act = take(D * 4), o_st = take(sizeof(LmState));
+  CU(E->d_lm.ensure(off));
+  char* base = E->d_lm.as<char>();
+  LmBufs B;
+  B.H = E->d_H.as<double>();
+  B.b = E->d_b.as<double>();
+  B.cost_x = E->d_cost2.as<double>();
+  B.cost_c = E->d_cost2.as<double>() + 2;
+  B.scale = (double*)(base + o_scale);
+  B.diagonal = (double*)(base + o_diag);
+  B.step = (double*)(base + o_step);
+  B.delta = (double*)(base + o_delta);
+  B.A = (double*)(base + o_A);
+  B.tmp = (double*)(base + o_tmp);
+  B.active = (int*)(base + o_act);
+  B.x = E->d_state.as<double>();
+  B.cand = E->d_cand.as<double>();
+  B.st = (LmState*)(base + o_st);
+  LayoutDev L;
+  L.D = D; L.K = E->K; L.kf = Lh.first_free_knot; L.nb = E->n_bias; L.L = E->n_lm;
+  L.col_bias_gyro = Lh.col_bias_gyro; L.col_bias_accel = Lh.col_bias_accel;
+  bool constrained = false;
+  for (int s = 0; s < 3; s++) {
+    L.col_toff[s] = Lh.col_t_offset[s];
+    L.has_bounds[s] = E->bounds_toff[s] ? 1 : 0;
+    L.lo[s] = E->toff_lo[s];
+    L.hi[s] = E->toff_hi[s];
+    if (L.col_toff[s] >= 0 && E->bounds_toff[s]) constrained = true;
+  }
+  L.sl = E->sl;
+  LmConst C;
+  const int* ctl_res = &B.st->skip_res;
+  const int* ctl_jac = &B.st->skip_jac;
+  const size_t sm_small = 1024 * sizeof(double);
+  size_t sm_step = (size_t)(512 + 2 * D) * sizeof(double);
+  int a_in_smem = 0;
+  if (sm_step + (size_t)D * D * sizeof(double) <= 200 * 1024) {
+    a_in_smem = 1;
+    sm_step += (size_t)D * D * sizeof(double);
+  }
+  CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_step));
+  int rc;
+  if (constrained) {
+    lm_project_kernel<<<1, 256, 0, E->stream>>>(B, L);
+    E->launches++;
+  }
+  if ((rc = run_pass(E, B.x, true, B.cost_x, nullptr))) return rc;
+  E->prof_begin(5);
+  lm_init_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C, max_iterations, constrained ? 1 : 0);
+  E->prof_end();
+  E->launches++;
+  const int max_ls = 20;  // Ceres default max_num_line_search_step_size_iterations
+  for (int it = 0; it <= max_iterations; it++) {
+    E->prof_begin(5);
+    lm_step_kernel<<<1, 512, sm_step, E->stream>>>(B, L, C, a_in_smem, constrained ? 1 : 0);
+    E->prof_end();
+    E->launches++;
+    if (it == max_iterations) break;  // the last launch only records the max-iterations termination
+    if ((rc = run_pass(E, B.cand, false, B.cost_c, ctl_res))) return rc;
+    if (constrained) {
+      for (int ls = 0; ls < max_ls + 1; ls++) {
+        lm_linesearch_kernel<<<1, 256, 0, E->stream>>>(B, L, max_ls);
+        E->launches++;
+        if ((rc = run_pass(E, B.cand, false, B.cost_c, ctl_res))) return rc;
+        int active = 0;
+        CU(cudaMemcpyAsync(&active, &B.st->ls_active, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+        CU(cudaStreamSynchronize(E->stream));
+        if (!active) break;
+      }
+    }
+    E->prof_begin(5);
+    lm_accept_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C);
+    E->prof_end();
+    E->launches++;
+    if ((rc = run_pass(E, B.x, true, B.cost_x, ctl_jac))) return rc;
+    E->prof_begin(5);
+    lm_post_kernel<<<1, 256, sm_small, E->stream>>>(B, L);
+    E->prof_end();
+    E->launches++;
+  }
+  LmState st;
+  CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  CU(cudaGetLastError());
+  if (summary) {
+    std::memset(summary, 0, sizeof(*summary));
+    summary->iterations = st.iteration;
+    summary->num_successful_steps = st.n_succ;
+    summary->num_unsuccessful_steps = st.n_unsucc;
+    summary->termination = st.termination;
+    summary->termination_reason = st.reason;
+    summary->num_jacobian_evals = st.n_jac;
+    summary->num_residual_evals = st.n_res;
+    summary->initial_cost = st.initial_cost;
+    summary->final_cost = st.x_cost + st.fixed_cost;
+    summary->fixed_cost = st.fixed_cost;
+    summary->final_radius = st.radius;
+    summary->final_gradient_max_norm = st.gmax;
+  }
   return CLIC_OK;
 }
 
@@ -851,7 +964,7 @@ CLIC_API int clic_solve(clic_estimator* E, int32_t max_iterations, clic_summary*
   int rc = ensure_layout(E);
   if (rc) return rc;
   if ((rc = fill_prior_columns(E))) return rc;
-  return fail(CLIC_ERR_UNSUPPORTED, "LM solve: not built yet in this revision");
+  return lm_solve(E, max_iterations, summary);
 }
 
 CLIC_API int clic_read_state(clic_estimator* E, double* knot_q, double* knot_p, double* bias, double* t_offset_ns,

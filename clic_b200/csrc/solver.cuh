@@ -92,3 +92,483 @@ __global__ void prior_kernel(const double* J0, const double* A, const double* r0
 }
 
 }  // namespace clic
+
+namespace clic {
+
+// ---------------- Levenberg-Marquardt on the device (Ceres 1.14 TrustRegionMinimizer semantics) ----------------
+// The constants are Ceres defaults (solver.h); the loop mirrors oracle/clic_oracle.cpp solve() line by line.
+struct LmConst {
+  double min_relative_decrease = 1e-3, min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
+  double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  double max_radius = 1e16, min_radius = 1e-32, initial_radius = 1e4;
+  int max_consecutive_invalid = 5;
+};
+
+struct LmState {
+  double radius, decrease_factor;
+  double x_cost, cand_cost, model_cost_change;
+  double x_norm, gmax, step_norm;
+  double initial_cost, fixed_cost;
+  double ls_g0, ls_dmax, ls_cur, ls_fcur;  // projected line search (bounded problems)
+  int reuse_diagonal, iteration, invalid, done, termination, reason;
+  int n_succ, n_unsucc, n_jac, n_res;
+  int skip_jac;  // control word of the Jacobian pass (1 = skip)
+  int skip_res;  // control word of the residual-only pass
+  int step_valid, max_iterations;
+  int ls_active, ls_iter, ls_success;
+};
+
+struct LayoutDev {
+  int D, K, kf, nb, L;
+  int col_bias_gyro, col_bias_accel, col_toff[3];
+  int has_bounds[3];
+  double lo[3], hi[3];
+  StateLayout sl;
+};
+
+// x (+) delta for the whole state, one thread per block (ceres_local_param.h:132-139 + ParameterBlock::Plus box
+// projection).  alpha scales delta (line search).
+__device__ __forceinline__ void plus_state(const double* x, const double* delta, double alpha, double* out,
+                                           const LayoutDev& L) {
+  const int n_state = L.sl.size();
+  for (int i = threadIdx.x; i < n_state; i += blockDim.x) out[i] = x[i];
+  __syncthreads();
+  for (int k = L.kf + threadIdx.x; k < L.K; k += blockDim.x) {
+    const int c = 6 * (k - L.kf);
+    Q4 q = ldq(x + L.sl.off_q() + 4 * k);
+    Q4 r = so3_mul(q, so3_exp(mk(alpha * delta[c], alpha * delta[c + 1], alpha * delta[c + 2])));
+    double* oq = out + L.sl.off_q() + 4 * k;
+    oq[0] = r.x; oq[1] = r.y; oq[2] = r.z; oq[3] = r.w;
+    double* op = out + L.sl.off_p() + 3 * k;
+    const double* xp = x + L.sl.off_p() + 3 * k;
+    for (int a = 0; a < 3; a++) op[a] = xp[a] + alpha * delta[c + 3 + a];
+  }
+  for (int j = threadIdx.x; j < L.nb; j += blockDim.x) {
+    const double* xb = x + L.sl.off_bias() + 6 * j;
+    double* ob = out + L.sl.off_bias() + 6 * j;
+    if (L.col_bias_gyro >= 0)
+      for (int a = 0; a < 3; a++) ob[a] = xb[a] + alpha * delta[L.col_bias_gyro + 3 * j + a];
+    if (L.col_bias_accel >= 0)
+      for (int a = 0; a < 3; a++) ob[3 + a] = xb[3 + a] + alpha * delta[L.col_bias_accel + 3 * j + a];
+  }
+  if (threadIdx.x < 3) {
+    const int s = threadIdx.x;
+    if (L.col_toff[s] >= 0) {
+      double v = x[L.sl.off_toff() + s] + alpha * delta[L.col_toff[s]];
+      if (L.has_bounds[s]) {
+        v = fmax(v, L.lo[s]);
+        v = fmin(v, L.hi[s]);
+      }
+      out[L.sl.off_toff() + s] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// block-wide sums / max (blockDim.x <= 1024), fixed tree => deterministic
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  __syncthreads();
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  __syncthreads();
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// |x|^2, |x-y|^2, |x-y|_inf in the ambient space of the active (non-constant, used) blocks.
+__device__ __forceinline__ void ambient_diff(const double* x, const double* y, const int* active, const LayoutDev& L,
+                                             double* sh, double* xs_out, double* ds_out, double* dm_out) {
+  double xs = 0, ds = 0, dm = 0;
+  auto acc = [&](const double* a, const double* b, int n) {
+    for (int i = 0; i < n; i++) {
+      xs += a[i] * a[i];
+      double d = a[i] - b[i];
+      ds += d * d;
+      dm = fmax(dm, fabs(d));
+    }
+  };
+  for (int k = L.kf + threadIdx.x; k < L.K; k += blockDim.x) {
+    const int c = 6 * (k - L.kf);
+    if (active[c]) acc(x + L.sl.off_q() + 4 * k, y + L.sl.off_q() + 4 * k, 4);
+    if (active[c + 3]) acc(x + L.sl.off_p() + 3 * k, y + L.sl.off_p() + 3 * k, 3);
+  }
+  for (int j = threadIdx.x; j < L.nb; j += blockDim.x) {
+    if (L.col_bias_gyro >= 0 && active[L.col_bias_gyro + 3 * j])
+      acc(x + L.sl.off_bias() + 6 * j, y + L.sl.off_bias() + 6 * j, 3);
+    if (L.col_bias_accel >= 0 && active[L.col_bias_accel + 3 * j])
+      acc(x + L.sl.off_bias() + 6 * j + 3, y + L.sl.off_bias() + 6 * j + 3, 3);
+  }
+  if (threadIdx.x < 3 && L.col_toff[threadIdx.x] >= 0 && active[L.col_toff[threadIdx.x]])
+    acc(x + L.sl.off_toff() + threadIdx.x, y + L.sl.off_toff() + threadIdx.x, 1);
+  double a = block_sum(xs, sh), b = block_sum(ds, sh), c = block_max(dm, sh);
+  if (xs_out) *xs_out = a;
+  if (ds_out) *ds_out = b;
+  if (dm_out) *dm_out = c;
+}
+
+struct LmBufs {
+  double* H;       // D*D unscaled normal matrix (from the pass)
+  double* b;       // D   unscaled gradient
+  double* cost_x;  // [2] cost, fixed_cost of the pass at x
+  double* cost_c;  // [2] of the residual-only pass at the candidate
+  double* scale;   // D
+  double* diagonal;  // D
+  double* step;    // D
+  double* delta;   // D
+  double* A;       // D*D scratch (used when it does not fit shared memory)
+  double* tmp;     // state-sized scratch (gradient-norm Plus)
+  int* active;     // D
+  double* x;       // state
+  double* cand;    // candidate state
+  LmState* st;
+};
+
+// gradient_max_norm = |x - Plus(x, -g)|_inf and |x| (TrustRegionMinimizer::EvaluateGradientAndJacobian)
+__device__ __forceinline__ void gradient_norms(const LmBufs& B, const LayoutDev& L, double* sh) {
+  for (int i = threadIdx.x; i < L.D; i += blockDim.x) B.step[i] = -B.b[i];  // step is free scratch here
+  __syncthreads();
+  plus_state(B.x, B.step, 1.0, B.tmp, L);
+  double xs, dm;
+  ambient_diff(B.x, B.tmp, B.active, L, sh, &xs, nullptr, &dm);
+  if (threadIdx.x == 0) {
+    B.st->x_norm = sqrt(xs);
+    B.st->gmax = dm;
+  }
+  __syncthreads();
+}
+
+// IterationZero of a bounded problem: x <- Plus(x, 0) projects the start point onto the feasible set.
+__global__ void lm_project_kernel(LmBufs B, LayoutDev L) {
+  for (int i = threadIdx.x; i < L.D; i += blockDim.x) B.step[i] = 0.0;
+  __syncthreads();
+  plus_state(B.x, B.step, 1.0, B.tmp, L);
+  const int n_state = L.sl.size();
+  for (int i = threadIdx.x; i < n_state; i += blockDim.x) B.x[i] = B.tmp[i];
+}
+
+__global__ void zero_cost_kernel(double* cost2, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  if (threadIdx.x < 2) cost2[threadIdx.x] = 0.0;
+}
+
+// After the iteration-0 Jacobian pass: Jacobi scaling, active mask, norms, LM state.
+__global__ void lm_init_kernel(LmBufs B, LayoutDev L, LmConst C, int max_iterations, int is_constrained) {
+  extern __shared__ double sh[];
+  const int D = L.D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const double d = B.H[(size_t)i * D + i];
+    B.active[i] = d > 0.0 ? 1 : 0;
+    B.scale[i] = 1.0 / (1.0 + sqrt(d));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LmState* s = B.st;
+    s->radius = C.initial_radius;
+    s->decrease_factor = 2.0;
+    s->x_cost = B.cost_x[0];
+    s->fixed_cost = B.cost_x[1];
+    s->initial_cost = B.cost_x[0] + B.cost_x[1];
+    s->reuse_diagonal = 0;
+    s->iteration = 0;
+    s->invalid = 0;
+    s->done = 0;
+    s->termination = 1;
+    s->reason = 0;
+    s->n_succ = s->n_unsucc = 0;
+    s->n_jac = 1;
+    s->n_res = 0;
+    s->skip_jac = 1;
+    s->skip_res = 1;
+    s->step_valid = 0;
+    s->max_iterations = max_iterations;
+    s->ls_active = 0;
+    s->ls_iter = 0;
+    s->ls_success = 1;
+  }
+  __syncthreads();
+  gradient_norms(B, L, sh);
+}
+
+// One LM iteration, first half: termination tests, damping, Cholesky, step, model decrease, candidate = x (+) delta.
+// A lives in shared memory when it fits (a_in_smem), else in global scratch.
+__global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmConst C, int a_in_smem, int is_constrained) {
+  extern __shared__ double sh[];
+  LmState* s = B.st;
+  const int D = L.D;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int go;
+  if (tid == 0) {
+    go = 1;
+    s->skip_res = 1;
+    s->step_valid = 0;
+    if (s->done) {
+      go = 0;
+    } else if (s->iteration >= s->max_iterations) {
+      s->done = 1; s->termination = 1; s->reason = 0; go = 0;   // NO_CONVERGENCE / max iterations
+    } else if (s->gmax <= C.gradient_tolerance) {
+      s->done = 1; s->termination = 0; s->reason = 1; go = 0;
+    } else if (s->radius <= C.min_radius) {
+      s->done = 1; s->termination = 0; s->reason = 4; go = 0;
+    } else {
+      s->iteration++;
+    }
+  }
+  __syncthreads();
+  if (!go) return;
+  double* red = sh;               // 512 doubles of reduction scratch
+  double* gs = sh + 512;          // D scaled gradient
+  double* y = gs + D;             // D
+  double* A = a_in_smem ? (y + D) : B.A;
+  const double radius = s->radius;
+  const int reuse = s->reuse_diagonal;
+  // LevenbergMarquardtStrategy::ComputeStep: diagonal = clamp(diag(J~^T J~)), A = H~ + diag(diagonal / radius)
+  for (int i = tid; i < D; i += nt) {
+    const double si = B.scale[i];
+    gs[i] = B.b[i] * si;
+    if (!reuse) {
+      double d = B.H[(size_t)i * D + i] * si * si;
+      B.diagonal[i] = fmin(fmax(d, C.min_lm_diagonal), C.max_lm_diagonal);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < D * D; e += nt) {
+    const int i = e / D, j = e % D;
+    double v = B.H[e] * B.scale[i] * B.scale[j];
+    if (i == j) {
+      double lm = sqrt(B.diagonal[i] / radius);
+      v += lm * lm;
+    }
+    A[e] = v;
+  }
+  __syncthreads();
+  // dense Cholesky A = L L^T (lower, in place), right-looking
+  __shared__ int ok;
+  if (tid == 0) ok = 1;
+  __syncthreads();
+  for (int j = 0; j < D; j++) {
+    __shared__ double piv;
+    if (tid == 0) {
+      double d = A[(size_t)j * D + j];
+      if (!(d > 0.0) || !isfinite(d)) { ok = 0; d = 1.0; }
+      piv = sqrt(d);
+      A[(size_t)j * D + j] = piv;
+    }
+    __syncthreads();
+    if (!ok) break;
+    for (int i = j + 1 + tid; i < D; i += nt) A[(size_t)i * D + j] = A[(size_t)i * D + j] / piv;
+    __syncthreads();
+    // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i
+    const int m = D - j - 1;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) A[(size_t)i * D + k] -= A[(size_t)i * D + j] * A[(size_t)k * D + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  int valid = ok;
+  // forward / backward substitution: (L L^T) z = g~, step = -z
+  if (valid) {
+    for (int i = tid; i < D; i += nt) y[i] = gs[i];
+    __syncthreads();
+    for (int j = 0; j < D; j++) {
+      if (tid == 0) y[j] = y[j] / A[(size_t)j * D + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = j + 1 + tid; i < D; i += nt) y[i] -= A[(size_t)i * D + j] * yj;
+      __syncthreads();
+    }
+    for (int j = D - 1; j >= 0; j--) {
+      if (tid == 0) y[j] = y[j] / A[(size_t)j * D + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = tid; i < j; i += nt) y[i] -= A[(size_t)j * D + i] * yj;
+      __syncthreads();
+    }
+    double bad = 0.0;
+    for (int i = tid; i < D; i += nt) {
+      double v = -y[i];
+      B.step[i] = v;
+      if (!isfinite(v)) bad = 1.0;
+    }
+    if (block_max(bad, red) > 0.0) valid = 0;
+  }
+  __syncthreads();
+  double mcc = 0.0;
+  if (valid) {
+    // model_cost_change = -(g~^T s + 1/2 s^T H~ s)
+    double part = 0.0;
+    for (int i = tid; i < D; i += nt) {
+      double row = 0.0;
+      const double si = B.scale[i];
+      for (int j = 0; j < D; j++) row += (B.H[(size_t)i * D + j] * si * B.scale[j]) * B.step[j];
+      part += gs[i] * B.step[i] + 0.5 * B.step[i] * row;
+    }
+    mcc = -block_sum(part, red);
+    if (!(mcc > 0.0)) valid = 0;
+  }
+  if (tid == 0) s->reuse_diagonal = 1;
+  if (!valid) {
+    if (tid == 0) {  // HandleInvalidStep
+      s->invalid++;
+      if (s->invalid >= C.max_consecutive_invalid) {
+        s->done = 1; s->termination = 2; s->reason = 5;
+      } else {
+        s->radius = s->radius / s->decrease_factor;
+        s->decrease_factor *= 2.0;
+        s->n_unsucc++;
+      }
+    }
+    return;
+  }
+  for (int i = tid; i < D; i += nt) B.delta[i] = B.step[i] * B.scale[i];
+  __syncthreads();
+  plus_state(B.x, B.delta, 1.0, B.cand, L);
+  double g0p = 0.0, dmx = 0.0;
+  for (int i = tid; i < D; i += nt) {
+    g0p += B.b[i] * B.delta[i];
+    dmx = fmax(dmx, fabs(B.delta[i]));
+  }
+  const double g0 = block_sum(g0p, red), dmax = block_max(dmx, red);
+  if (tid == 0) {
+    s->invalid = 0;
+    s->model_cost_change = mcc;
+    s->step_valid = 1;
+    s->skip_res = 0;
+    s->n_res++;
+    s->ls_g0 = g0;
+    s->ls_dmax = dmax;
+    s->ls_cur = 1.0;
+    s->ls_iter = 0;
+    s->ls_success = 1;
+    s->ls_active = is_constrained;
+  }
+}
+
+// Projected Armijo line search of bounded problems (TrustRegionMinimizer::DoLineSearch).  Called by the host loop
+// after each residual pass at cand = x (+) cur*delta while s->ls_active: decides accept / contract (oracle: quadratic
+// interpolation with Ceres' contraction clamps), and writes the next candidate.
+__global__ void lm_linesearch_kernel(LmBufs B, LayoutDev L, int max_ls_iterations) {
+  LmState* s = B.st;
+  if (s->done || !s->step_valid || !s->ls_active) return;
+  __shared__ int next;
+  __shared__ double alpha;
+  if (threadIdx.x == 0) {
+    const double fcur = B.cost_c[0], cur = s->ls_cur, g0 = s->ls_g0, f0 = s->x_cost;
+    next = 0;
+    alpha = cur;
+    if (!isfinite(fcur) || fcur > f0 + 1e-4 * g0 * cur) {
+      s->ls_iter++;
+      if (s->ls_iter >= max_ls_iterations) {
+        s->ls_success = 0;
+      } else {
+        double denom = 2.0 * (fcur - f0 - g0 * cur);
+        double q = (denom > 0 && isfinite(denom)) ? (-g0 * cur * cur / denom) : 0.6 * cur;
+        q = fmin(fmax(q, 1e-3 * cur), 0.6 * cur);
+        if (q * s->ls_dmax < 1e-9) {
+          s->ls_success = 0;
+        } else {
+          s->ls_cur = q;
+          alpha = q;
+          next = 1;
+          s->n_res++;
+        }
+      }
+      if (!next) alpha = 1.0;  // failure: delta unchanged (Ceres scales delta only on success)
+    } else {
+      alpha = cur;             // success: delta *= optimal step
+    }
+    if (!next) s->ls_active = 0;
+  }
+  __syncthreads();
+  const double a = alpha;
+  if (!next) {
+    for (int i = threadIdx.x; i < L.D; i += blockDim.x) B.delta[i] *= a;
+    __syncthreads();
+    plus_state(B.x, B.delta, 1.0, B.cand, L);
+    // the final candidate needs its cost: identical to the last sample when a == ls_cur, otherwise re-evaluated
+    if (threadIdx.x == 0) s->skip_res = (a == s->ls_cur && s->ls_success) ? 1 : 0;
+  } else {
+    plus_state(B.x, B.delta, a, B.cand, L);
+    if (threadIdx.x == 0) s->skip_res = 0;
+  }
+}
+
+// Second half of the iteration, after the residual-only pass at the candidate.
+__global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
+  extern __shared__ double sh[];
+  LmState* s = B.st;
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    s->skip_jac = 1;
+    go = (!s->done && s->step_valid) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!go) return;
+  double ds;
+  ambient_diff(B.x, B.cand, B.active, L, sh, nullptr, &ds, nullptr);
+  __shared__ int accept;
+  if (threadIdx.x == 0) {
+    accept = 0;
+    double cand_cost = B.cost_c[0];
+    if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+    s->cand_cost = cand_cost;
+    s->step_norm = sqrt(ds);
+    const double cost_change = s->x_cost - cand_cost;
+    if (s->step_norm <= C.parameter_tolerance * (s->x_norm + C.parameter_tolerance)) {
+      s->done = 1; s->termination = 0; s->reason = 2;
+    } else if (fabs(cost_change) <= C.function_tolerance * s->x_cost) {
+      s->done = 1; s->termination = 0; s->reason = 3;
+    } else {
+      const double rd = cost_change / s->model_cost_change;
+      if (rd > C.min_relative_decrease) {
+        accept = 1;
+        s->n_succ++;
+        s->radius = s->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rd - 1.0, 3));
+        s->radius = fmin(C.max_radius, s->radius);
+        s->decrease_factor = 2.0;
+        s->reuse_diagonal = 0;
+        s->skip_jac = 0;
+        s->n_jac++;
+      } else {
+        s->n_unsucc++;
+        s->radius = s->radius / s->decrease_factor;
+        s->decrease_factor *= 2.0;
+        s->reuse_diagonal = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (accept) {
+    const int n_state = L.sl.size();
+    for (int i = threadIdx.x; i < n_state; i += blockDim.x) B.x[i] = B.cand[i];
+  }
+}
+
+// After the (conditional) Jacobian pass at the accepted point.
+__global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
+  extern __shared__ double sh[];
+  LmState* s = B.st;
+  if (s->done || s->skip_jac) return;
+  if (threadIdx.x == 0) s->x_cost = B.cost_x[0];
+  __syncthreads();
+  gradient_norms(B, L, sh);
+}
+
+}  // namespace clic
