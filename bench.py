@@ -184,7 +184,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-HAVE_VISUAL = False  # flipped once the visual kernel lands
+HAVE_VISUAL = True
 
 
 def main():

@@ -86,6 +86,13 @@ struct ImuBatch {
   int marg = 0;
   StreamExec ex;
 };
+struct ImageBatch {
+  ImageStream st;
+  DevBuf ti, tj, pi[3], pj[2], lm;
+  std::vector<int64_t> perm;  // sorted position -> add order
+  int marg = 0;
+  StreamExec ex;
+};
 struct BiasFac {
   int slot_i, slot_j;
   double sqrt_info[6];
@@ -121,6 +128,7 @@ struct clic_estimator {
   DevBuf d_lm;  // LM workspace (solver.cuh)
   std::vector<std::unique_ptr<LoamBatch>> loam;
   std::vector<std::unique_ptr<ImuBatch>> imu;
+  std::vector<std::unique_ptr<ImageBatch>> image;
   std::vector<BiasFac> bias_f;
   struct PriorRef {
     const clic_prior* p;
@@ -194,11 +202,11 @@ clic_layout compute_layout(const clic_estimator* E) {
   return L;
 }
 
-int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm) {
+int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm, bool pair_keys = false) {
   ex.n = n;
   ex.NT = NT;
   ex.rd = n_tiles(NT) * 64;
-  ex.n_keys = E->K - 3;
+  ex.n_keys = pair_keys ? (E->K - 3) * (E->K - 3) : E->K - 3;
   const int64_t slabs = (n + 31) / 32;
   const int max_ctas = E->n_sm * ctas_per_sm;
   int64_t ctas = std::min<int64_t>(max_ctas, (slabs + kWarpsPerCta - 1) / kWarpsPerCta);
@@ -209,7 +217,7 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.grid = std::max(ex.grid, 1);
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
-  ex.P = (int)std::min<size_t>(8, std::max<size_t>(1, slots / 64));
+  ex.P = pair_keys ? 1 : (int)std::min<size_t>(8, std::max<size_t>(1, slots / 64));
   CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
   CU(ex.key.ensure(slots * sizeof(int)));
   CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
@@ -253,6 +261,9 @@ int ensure_layout(clic_estimator* E) {
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 24;
     d.n_extra = 0;
+    d.extra_base = 24;
+    d.kind = 0;
+    d.kdim = E->K - 3;
     descs.push_back(d);
   }
   for (auto& b : E->imu) {
@@ -263,11 +274,28 @@ int ensure_layout(clic_estimator* E) {
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 31;
     d.n_extra = 7;
+    d.extra_base = 24;
+    d.kind = 0;
+    d.kdim = E->K - 3;
     for (int c = 0; c < 3; c++) {
       d.extra_global[c] = L.col_bias_gyro >= 0 ? L.col_bias_gyro + 3 * b->st.bias_slot + c : -1;
       d.extra_global[3 + c] = L.col_bias_accel >= 0 ? L.col_bias_accel + 3 * b->st.bias_slot + c : -1;
     }
     d.extra_global[6] = L.col_t_offset[CLIC_SENSOR_IMU];
+    descs.push_back(d);
+  }
+  for (auto& b : E->image) {
+    if (b->marg) continue;
+    StreamDesc d{};
+    d.part = b->ex.part.as<double>();
+    d.overflow = b->ex.overflow.as<double>();
+    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 49;
+    d.n_extra = 1;
+    d.extra_base = 48;
+    d.kind = 1;
+    d.kdim = E->K - 3;
+    d.extra_global[0] = L.col_t_offset[CLIC_SENSOR_CAMERA];
     descs.push_back(d);
   }
   E->n_desc = (int)descs.size();
@@ -414,6 +442,37 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     E->prof_end();
     E->launches += 1;
   }
+  for (auto& b : E->image) {
+    if (b->marg) continue;
+    StreamExec& ex = b->ex;
+    const size_t smem = factor_smem_bytes(E->K, 7);
+    ImageShared ish;
+    ish.S_CtoI = ldq(E->S_CtoI);
+    ish.p_CinI = ldv(E->p_CinI);
+    ish.sqrt_info = 450.0 / 1.5;
+    ish.loss_a = b->st.loss_a;
+    ish.inv_dt = 1e9 / double(E->dt_ns);
+    ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
+    if (jac) {
+      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+      E->prof_begin(2);
+      image_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+      E->prof_end();
+      E->prof_begin(3);
+      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
+      E->prof_end();
+      E->launches += 2;
+    } else {
+      E->prof_begin(2);
+      image_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+      E->prof_end();
+      E->launches += 1;
+    }
+    E->prof_begin(3);
+    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
+    E->prof_end();
+    E->launches += 1;
+  }
   if (jac && D > 0) {
     ColMaps cm;
     cm.D = D;
@@ -423,7 +482,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     cm.col_sub = E->d_col_sub.as<int>();
     const int n_entries = D * (D + 1) / 2 + D;
     E->prof_begin(3);
-    assemble_kernel<<<(n_entries + 127) / 128, 128, 0, E->stream>>>(E->d_H.as<double>(), E->d_b.as<double>(), cm,
+    assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(E->d_H.as<double>(), E->d_b.as<double>(), cm,
                                                                     E->d_descs.as<StreamDesc>(), E->n_desc, ctl);
     E->prof_end();
     E->launches += 1;
@@ -651,7 +710,8 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
   if ((rc = set_smem(loam_kernel<true>, smem4)) || (rc = set_smem(loam_kernel<false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
-      (rc = set_smem(imu_kernel<true, true>, smem5)))
+      (rc = set_smem(imu_kernel<true, true>, smem5)) || (rc = set_smem(image_kernel<true>, factor_smem_bytes(E->K, 7))) ||
+      (rc = set_smem(image_kernel<false>, factor_smem_bytes(E->K, 7))))
     return rc;
   if ((rc = set_smem(reduce_records_kernel<20>, 8 * 640 * 8)) || (rc = set_smem(reduce_records_kernel<30>, 8 * 960 * 8)) ||
       (rc = set_smem(reduce_records_kernel<56>, 8 * 1792 * 8)))
@@ -791,6 +851,7 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   B->st.loss_a = marg_this_factor ? 3.0 : 10.0;  // trajectory_estimator.cpp:426-430
   B->st.bias_slot = bias_slot;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  B->st.extras_free = (!E->opt.lock_wb || !E->opt.lock_ab || !E->opt.lock_t_offset[S]) ? 1 : 0;
   B->st.marg_always = (E->opt.marg_bias_param || E->opt.marg_gravity_param || E->opt.marg_t_offset_param) ? 1 : 0;
   if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:419-424
     E->bounds_toff[S] = true;
@@ -823,7 +884,75 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
                             const double* p_j, const int32_t* landmark, int32_t fixed_depth,
                             int32_t marg_this_feature, int64_t* n_dropped) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
-  return fail(CLIC_ERR_UNSUPPORTED, "visual reprojection factors: CUDA kernel not built yet in this revision");
+  if (n_dropped) *n_dropped = 0;
+  if (n <= 0) return CLIC_OK;
+  if (!fixed_depth)
+    return fail(CLIC_ERR_UNSUPPORTED,
+                "fixed_depth = false (free inverse depths) is not built on the GPU yet; the shipped pipeline always "
+                "fixes them (trajectory_manager.cpp:709)");
+  if (E->opt.is_marg_state && marg_this_feature)
+    return fail(CLIC_ERR_UNSUPPORTED, "marginalising visual factors (UpdateVisualOffsetPrior) is not built yet");
+  for (int64_t i = 0; i < n; i++)
+    if (landmark[i] < 0 || landmark[i] >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  std::unique_ptr<ImageBatch> B(new ImageBatch);
+  const int S = CLIC_SENSOR_CAMERA;
+  const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
+  // Order by (t_i, t_j): the (s_i, s_j) key of consecutive factors then changes rarely, so a warp's accumulators
+  // are flushed rarely.  (The visual stream is small; this is a host-side permutation of the inputs only.)
+  B->perm.resize(n);
+  for (int64_t i = 0; i < n; i++) B->perm[i] = i;
+  std::stable_sort(B->perm.begin(), B->perm.end(), [&](int64_t a, int64_t b) {
+    return t_i[a] != t_i[b] ? t_i[a] < t_i[b] : t_j[a] < t_j[b];
+  });
+  std::vector<double> s_ti(n), s_tj(n), s_pi(3 * n), s_pj(3 * n);
+  std::vector<int32_t> s_lm(n);
+  for (int64_t k = 0; k < n; k++) {
+    const int64_t i = B->perm[k];
+    s_ti[k] = t_i[i];
+    s_tj[k] = t_j[i];
+    for (int c = 0; c < 3; c++) { s_pi[3 * k + c] = p_i[3 * i + c]; s_pj[3 * k + c] = p_j[3 * i + c]; }
+    s_lm[k] = landmark[i];
+  }
+  DevBuf r_ti, r_tj, r_pi, r_pj;
+  int rc;
+  if ((rc = to_device(E, r_ti, s_ti.data(), n)) || (rc = to_device(E, r_tj, s_tj.data(), n)) ||
+      (rc = to_device(E, r_pi, s_pi.data(), 3 * n)) || (rc = to_device(E, r_pj, s_pj.data(), 3 * n)) ||
+      (rc = to_device(E, B->lm, s_lm.data(), n)))
+    return rc;
+  CU(B->ti.ensure(n * sizeof(int64_t)));
+  CU(B->tj.ensure(n * sizeof(int64_t)));
+  for (int k = 0; k < 3; k++) CU(B->pi[k].ensure(n * sizeof(double)));
+  for (int k = 0; k < 2; k++) CU(B->pj[k].ensure(n * sizeof(double)));
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  prep_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+      n, r_ti.as<double>(), r_tj.as<double>(), r_pi.as<double>(), r_pj.as<double>(), t_min, t_max, pad,
+      B->ti.as<int64_t>(), B->tj.as<int64_t>(), B->pi[0].as<double>(), B->pi[1].as<double>(), B->pi[2].as<double>(),
+      B->pj[0].as<double>(), B->pj[1].as<double>(), E->d_counter.as<unsigned long long>());
+  E->launches++;
+  unsigned long long dropped = 0;
+  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  if (n_dropped) *n_dropped = (int64_t)dropped;
+  B->st.n = n;
+  B->st.ti_ns = B->ti.as<int64_t>();
+  B->st.tj_ns = B->tj.as<int64_t>();
+  for (int k = 0; k < 3; k++) B->st.pi[k] = B->pi[k].as<double>();
+  for (int k = 0; k < 2; k++) B->st.pj[k] = B->pj[k].as<double>();
+  B->st.landmark = B->lm.as<int32_t>();
+  B->st.loss_a = marg_this_feature ? 1.0 : 2.0;  // trajectory_estimator.cpp:806-810
+  B->marg = 0;
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:795-800
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
+    E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
+  }
+  if ((rc = plan_stream(E, B->ex, n, 7, 1, true))) return rc;
+  E->image.push_back(std::move(B));
+  E->layout_dirty = true;
+  return CLIC_OK;
 }
 
 CLIC_API int clic_add_prior(clic_estimator* E, const clic_prior* prior, int32_t n_drop, const int32_t* drop_blocks) {
@@ -926,6 +1055,7 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   int64_t total = 0;
   if (stream == 0) for (auto& b : E->loam) total += b->st.n;
   if (stream == 1) for (auto& b : E->imu) total += b->st.n;
+  if (stream >= 2) for (auto& b : E->image) total += b->st.n;
   if (n_out) *n_out = total;
   if (capacity <= 0 || total == 0) return CLIC_OK;
   // current offset is read from the device state
@@ -953,6 +1083,17 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
     for (auto& b : E->loam) if ((rc = run(b->st.n, b->st.t_ns, 0))) return rc;
   if (stream == 1)
     for (auto& b : E->imu) if ((rc = run(b->st.n, b->st.t_ns, (int64_t)toff_d[CLIC_SENSOR_IMU]))) return rc;
+  if (stream >= 2)
+    for (auto& b : E->image) {
+      const int64_t base = done;
+      if ((rc = run(b->st.n, stream == 2 ? b->st.ti_ns : b->st.tj_ns, (int64_t)toff_d[CLIC_SENSOR_CAMERA]))) return rc;
+      // the stream is stored sorted by (t_i, t_j): report in add order
+      const int64_t m = done - base;
+      std::vector<int32_t> ts(s_out + base, s_out + base + m);
+      std::vector<double> tu(u_out + base, u_out + base + m);
+      if (m == b->st.n)
+        for (int64_t k = 0; k < m; k++) { s_out[base + b->perm[k]] = ts[k]; u_out[base + b->perm[k]] = tu[k]; }
+    }
   return CLIC_OK;
 }
 

@@ -318,4 +318,166 @@ CLIC_HD double imu_eval(const WindowView& W, int s, double u, V3 gyro_m, V3 acce
   return rho;
 }
 
+// Vector-first Jacobian rows of a cumulative SO(3) spline value through a 1x3 row `a`.
+//   RP  (EvaluateRp,  so3_spline_view.h:127-183):  rows of  a * d_val_d_knot[k],  d from A_post_inv (inverse accumulation)
+//   RTP (EvaluateRTp, so3_spline_view.h:193-256):  rows of  a * d_val_d_knot[k],  d from Ri_A_pre (forward accumulation)
+struct So3Chain {
+  Q4 R;          // R(t)
+  Q4 acc[3];     // RP: A_accum_inv after steps i = 2,1,0 stored at [i];  RTP: prefix products P_1..P_3 at [0..2]
+  double lam[4], ca[3], cb[3];
+};
+CLIC_HD void so3_chain_rp(const WindowView& W, int s, double u, So3Chain* C) {
+  blend_cum(u, C->lam);
+  Q4 acc; acc.x = acc.y = acc.z = 0.0; acc.w = 1.0;
+#pragma unroll
+  for (int i = 2; i >= 0; i--) {
+    Q4 e = step_exp_neg(W.pair[s + i], C->lam[i + 1], &C->ca[i], &C->cb[i]);
+    acc = qmul(acc, e);
+    C->acc[i] = acc;
+  }
+  C->R = qmul(ldq(W.kq + 4 * s), qconj(acc));
+}
+CLIC_HD void so3_rows_rp(const WindowView& W, int s, const So3Chain& C, V3 a, V3 j[4]) {
+  V3 w0 = qrot_inv(C.acc[0], a), w1 = qrot_inv(C.acc[1], a), w2 = qrot_inv(C.acc[2], a);
+  V3 t0 = row_times_lamJr(w1, W.pair[s + 0], C.lam[1], C.ca[0], C.cb[0], +1.0);
+  V3 t1 = row_times_lamJr(w2, W.pair[s + 1], C.lam[2], C.ca[1], C.cb[1], +1.0);
+  V3 t2 = row_times_lamJr(a, W.pair[s + 2], C.lam[3], C.ca[2], C.cb[2], +1.0);
+  j[0] = w0 - vmat_t(t0, W.pair[s + 0].Jrinv);
+  j[1] = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
+  j[2] = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
+  j[3] = vmat(t2, W.pair[s + 2].Jrinv);
+}
+// forward accumulation: P_0 = R_s, P_{i+1} = P_i * exp(+lambda_{i+1} delta_i);  R(t) = P_3
+CLIC_HD void so3_chain_rtp(const WindowView& W, int s, double u, So3Chain* C, Q4 P[4]) {
+  blend_cum(u, C->lam);
+  P[0] = ldq(W.kq + 4 * s);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Q4 e = qconj(step_exp_neg(W.pair[s + i], C->lam[i + 1], &C->ca[i], &C->cb[i]));
+    P[i + 1] = qmul(P[i], e);
+  }
+  C->R = P[3];
+}
+CLIC_HD void so3_rows_rtp(const WindowView& W, int s, const So3Chain& C, const Q4 P[4], V3 a, V3 j[4]) {
+  V3 w0 = qrot_inv(P[0], a), w1 = qrot_inv(P[1], a), w2 = qrot_inv(P[2], a);
+  V3 t0 = row_times_lamJr(w0, W.pair[s + 0], C.lam[1], C.ca[0], C.cb[0], -1.0);
+  V3 t1 = row_times_lamJr(w1, W.pair[s + 1], C.lam[2], C.ca[1], C.cb[1], -1.0);
+  V3 t2 = row_times_lamJr(w2, W.pair[s + 2], C.lam[3], C.ca[2], C.cb[2], -1.0);
+  j[0] = w0 - vmat_t(t0, W.pair[s + 0].Jrinv);
+  j[1] = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
+  j[2] = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
+  j[3] = vmat(t2, W.pair[s + 2].Jrinv);
+}
+// So3SplineView::VelocityBody without Jacobian (so3_spline_view.h:330-394): omega_body(t)
+CLIC_HD V3 so3_velocity_body(const WindowView& W, int s, double u, double inv_dt) {
+  double lam[4], dl[4];
+  blend_cum(u, lam);
+  blend_cum_d1(u, inv_dt, dl);
+  V3 w = mk(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double ca, cb;
+    Q4 e = step_exp_neg(W.pair[s + i], lam[i + 1], &ca, &cb);
+    w = fma3(dl[i + 1], ldv(W.pair[s + i].delta), qrot(e, w));
+  }
+  return w;
+}
+
+struct ImageShared {
+  Q4 S_CtoI; V3 p_CinI;
+  double sqrt_info;  // 450 / 1.5, image_feature_factor.h:277-278
+  double loss_a;     // CauchyLoss(2) (1 when marginalised), trajectory_estimator.cpp:806-810
+  double inv_dt;
+  bool want_toff;    // camera time offset unlocked
+};
+
+// ImageFeatureFactor::Evaluate (image_feature_factor.h:67-268), inverse depth held constant (fixed_depth = true, the
+// only mode the shipped pipeline uses, trajectory_manager.cpp:709).  Emits 2 rows of 56 columns:
+//   [window of t_i: 0..23 | window of t_j: 24..47 | camera t_offset 48 | r 49 | pad]
+template <class Sink>
+CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double uj, V3 p_i, V3 p_j, double d_inv,
+                          const ImageShared& sh, bool want_jac, Sink& sink) {
+  V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
+  V3 p_Ii = qrot(sh.S_CtoI, x_ci) + sh.p_CinI;
+  So3Chain Ci, Cj;
+  Q4 Pj[4];
+  so3_chain_rp(W, si, ui, &Ci);
+  so3_chain_rtp(W, sj, uj, &Cj, Pj);
+  double ci[4], cj[4];
+  blend_plain(ui, ci);
+  blend_plain(uj, cj);
+  V3 pos_i = mk(0, 0, 0), pos_j = mk(0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    pos_i = fma3(ci[k], ldv(W.kp + 3 * (si + k)), pos_i);
+    pos_j = fma3(cj[k], ldv(W.kp + 3 * (sj + k)), pos_j);
+  }
+  V3 p_G = qrot(Ci.R, p_Ii) + pos_i;
+  Q4 S_ItoC = qconj(sh.S_CtoI);
+  Q4 S_GtoCj = qmul(S_ItoC, qconj(Cj.R));  // S_ItoC * S_GtoIj
+  V3 dG = p_G - pos_j;
+  V3 x_j = qrot(S_GtoCj, dG) - qrot(S_ItoC, sh.p_CinI);
+  const double dinv = 1.0 / x_j.z;
+  double res[2] = {sh.sqrt_info * (x_j.x * dinv - p_j.x), sh.sqrt_info * (x_j.y * dinv - p_j.y)};
+  const double sq = res[0] * res[0] + res[1] * res[1];
+  double rho = sq, sc = 1.0;
+  if (sh.loss_a > 0) sc = cauchy_scale(sq, sh.loss_a, &rho);
+  if (!want_jac) return rho;
+  // J_v rows (2x3)
+  V3 Jv[2] = {mk(dinv, 0.0, -dinv * dinv * x_j.x), mk(0.0, dinv, -dinv * dinv * x_j.y)};
+  V3 jt = mk(0, 0, 0);
+  if (sh.want_toff) {  // image_feature_factor.h:250-263
+    V3 gyro_i = so3_velocity_body(W, si, ui, sh.inv_dt), gyro_j = so3_velocity_body(W, sj, uj, sh.inv_dt);
+    double di[4], dj[4];
+    blend_plain_d1(ui, sh.inv_dt, di);
+    blend_plain_d1(uj, sh.inv_dt, dj);
+    V3 vel_i = mk(0, 0, 0), vel_j = mk(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      vel_i = fma3(di[k], ldv(W.kp + 3 * (si + k)), vel_i);
+      vel_j = fma3(dj[k], ldv(W.kp + 3 * (sj + k)), vel_j);
+    }
+    // J_tj = S_ItoC * Rj_dot^T * (p_G - p_Ij) - S_GtoCj * vel_j,  Rj_dot^T v = -(omega_j x (Rj^T v))
+    V3 J_tj = qrot(S_ItoC, -cross(gyro_j, qrot_inv(Cj.R, dG))) - qrot(S_GtoCj, vel_j);
+    // J_ti = S_GtoCj * (Ri_dot * p_Ii + vel_i),  Ri_dot p = Ri (omega_i x p)
+    V3 J_ti = qrot(S_GtoCj, qrot(Ci.R, cross(gyro_i, p_Ii)) + vel_i);
+    jt = J_ti + J_tj;
+  }
+#pragma unroll
+  for (int row = 0; row < 2; row++) {
+    const double sI = sc * sh.sqrt_info;
+    // g = (J_v S_GtoCj)^T  -> jac_lhs_P[0] = g, jac_lhs_P[1] = -g
+    V3 g = qrot_inv(S_GtoCj, Jv[row]);
+    // jac_lhs_R[0] = -J_v (S_GtoCj S_IitoG) hat(p_Ii):  with m = (J_v S_GtoCj R_i)^T, row = -(m x p_Ii) = p_Ii x m
+    V3 m = qrot_inv(Ci.R, g);
+    V3 a_i = cross(p_Ii, m);
+    // jac_lhs_R[1] = J_v S_GtoCj hat(p_G - p_Ij):  row = g x dG
+    V3 a_j = cross(g, dG);
+    V3 ji[4], jj[4];
+    so3_rows_rp(W, si, Ci, a_i, ji);
+    so3_rows_rtp(W, sj, Cj, Pj, a_j, jj);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      sink.put(row, 6 * k + 0, sI * ji[k].x);
+      sink.put(row, 6 * k + 1, sI * ji[k].y);
+      sink.put(row, 6 * k + 2, sI * ji[k].z);
+      sink.put(row, 6 * k + 3, sI * ci[k] * g.x);
+      sink.put(row, 6 * k + 4, sI * ci[k] * g.y);
+      sink.put(row, 6 * k + 5, sI * ci[k] * g.z);
+      sink.put(row, 24 + 6 * k + 0, sI * jj[k].x);
+      sink.put(row, 24 + 6 * k + 1, sI * jj[k].y);
+      sink.put(row, 24 + 6 * k + 2, sI * jj[k].z);
+      sink.put(row, 24 + 6 * k + 3, -sI * cj[k] * g.x);
+      sink.put(row, 24 + 6 * k + 4, -sI * cj[k] * g.y);
+      sink.put(row, 24 + 6 * k + 5, -sI * cj[k] * g.z);
+    }
+    sink.put(row, 48, sh.want_toff ? (1e-9 * sI) * dot(Jv[row], jt) : 0.0);
+    sink.put(row, 49, sc * res[row]);
+#pragma unroll
+    for (int cc = 50; cc < 56; cc++) sink.put(row, cc, 0.0);
+    sink.row_done(row);
+  }
+  return rho;
+}
+
 }  // namespace clic

@@ -327,6 +327,7 @@ struct ImuStream {
   double info[6];
   double loss_a;
   int bias_slot;
+  int extras_free;  // a bias / time-offset block of these factors is a free parameter (options, known at add time)
   int marg_always;  // marg mode: a non-knot block of these factors is dropped, so they all enter the prior
 };
 
@@ -408,11 +409,12 @@ imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
         SmemRowSink<NT> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
         double rho = imu_eval<MARG>(W, mine ? s : kmin, mine ? u : 0.0, gy, ac, sh, true, sink);
-        if (mine) cost += 0.5 * rho;  // an IMU factor always has a free (or marginalised) parameter in shipped use
+        if (mine) { if (s + 3 >= pp.kf || st.extras_free || MARG) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       } else {
         if (mine) {
           NullSink sink;
-          cost += 0.5 * imu_eval<MARG>(W, s, u, gy, ac, sh, false, sink);
+          const double rho = imu_eval<MARG>(W, s, u, gy, ac, sh, false, sink);
+          if (s + 3 >= pp.kf || st.extras_free || MARG) cost += 0.5 * rho; else fcost += 0.5 * rho;
         }
       }
       pending &= ~__ballot_sync(0xffffffffu, mine);
@@ -433,6 +435,110 @@ imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
   }
 }
 
+// ---------------- K3: ImageFeatureFactor over a stream ----------------
+struct ImageStream {
+  int64_t n;
+  const int64_t* ti_ns;  // kDropped if either time was outside the window at add time
+  const int64_t* tj_ns;
+  const double* pi[3];
+  const double* pj[2];
+  const int32_t* landmark;
+  double loss_a;
+};
+
+// Local columns (NT = 7): [window of t_i 0..23 | window of t_j 24..47 | camera t_offset 48 | r 49 | pad]; key = s_i*(K-3)+s_j
+template <bool JAC>
+__global__ void __launch_bounds__(kThreads, 1)
+image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, ImageShared sh) {
+  constexpr int NT = 7;
+  if (pp.ctl && pp.ctl[0]) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
+  const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 2];  // camera offset, image_feature_factor.h:75-76
+  const double* invd = pp.state + pp.sl.off_invd();
+  const int nk = pp.sl.K - 3;
+  WarpAcc<NT> acc;
+  acc.zero();
+  int acc_key = -1, slot = 0;
+  double cost = 0.0, fcost = 0.0;
+  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  for (int sl = 0; sl < slabs_per_warp; sl++) {
+    if ((slab0 + sl) * 32 >= st.n) break;
+    const int64_t idx = (slab0 + sl) * 32 + lane;
+    int64_t ti = kDropped, tj = kDropped;
+    if (idx < st.n) { ti = st.ti_ns[idx]; tj = st.tj_ns[idx]; }
+    int si = 0, sj = 0;
+    double ui = 0.0, uj = 0.0;
+    bool valid = (ti != kDropped) && (tj != kDropped) && index_ns(ti + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &si, &ui) &&
+                 index_ns(tj + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &sj, &uj);
+    V3 p_i = mk(0, 0, 1), p_j = mk(0, 0, 1);
+    double rho_inv = 1.0;
+    if (valid) {
+      p_i = mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]);
+      p_j = mk(st.pj[0][idx], st.pj[1][idx], 1.0);
+      rho_inv = invd[st.landmark[idx]];
+    }
+    int key = valid ? si * nk + sj : -1;
+    unsigned pending = __ballot_sync(0xffffffffu, key >= 0);
+    while (pending) {
+      int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
+      bool mine = (key == kmin) && ((pending >> lane) & 1);
+      // a visual factor touches knots of both windows: it has a free parameter unless both windows are all constant
+      const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff;
+      if (JAC) {
+        if (kmin != acc_key) {
+          flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+          acc.zero();
+          acc_key = kmin;
+        }
+        SmemRowSink<NT> sink;
+        sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
+        double rho = image_eval(W, mine ? si : kmin / nk, mine ? ui : 0.0, mine ? sj : kmin % nk, mine ? uj : 0.0, p_i,
+                                p_j, rho_inv, sh, true, sink);
+        if (mine) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
+      } else {
+        if (mine) {
+          NullSink sink;
+          double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, false, sink);
+          if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho;
+        }
+      }
+      pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+  if (JAC) {
+    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
+  }
+  if (lane == 0) {
+    rb.cost[2 * warp_global] = cost;
+    rb.cost[2 * warp_global + 1] = fcost;
+  }
+}
+
+__global__ void prep_image_kernel(int64_t n, const double* ti_s, const double* tj_s, const double* p_i, const double* p_j,
+                                  int64_t t_lo, int64_t t_hi, int64_t pad, int64_t* ti_ns, int64_t* tj_ns, double* pi0,
+                                  double* pi1, double* pi2, double* pj0, double* pj1, unsigned long long* n_dropped) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t a = (int64_t)(ti_s[i] * 1e9), b = (int64_t)(tj_s[i] * 1e9);
+  bool ok = !(a - pad < t_lo || a + pad >= t_hi) && !(b - pad < t_lo || b + pad >= t_hi);
+  ti_ns[i] = ok ? a : kDropped;
+  tj_ns[i] = ok ? b : kDropped;
+  if (!ok) atomicAdd(n_dropped, 1ULL);
+  pi0[i] = p_i[3 * i]; pi1[i] = p_i[3 * i + 1]; pi2[i] = p_i[3 * i + 2];
+  pj0[i] = p_j[3 * i]; pj1[i] = p_j[3 * i + 1];
+}
+
 // ---------------- assembly of the dense normal equations ----------------
 // One descriptor per factor stream whose records were reduced to per-key blocks.
 struct StreamDesc {
@@ -440,7 +546,10 @@ struct StreamDesc {
   const double* overflow;  // [n_keys][rd] atomics fallback accumulators (all zero for time-sorted input)
   int n_keys, P, NT, rd;
   int r_col;             // local column holding r~
-  int n_extra;           // local columns 24 .. 24+n_extra-1 map to extra_global[] (-1: constant, dropped)
+  int n_extra;           // local columns extra_base .. extra_base+n_extra-1 map to extra_global[] (-1: constant)
+  int extra_base;        // 24 (one knot window) or 48 (two windows)
+  int kind;              // 0: key = interval s (LiDAR / IMU);  1: key = s_i * kdim + s_j (visual, two knot windows)
+  int kdim;
   int extra_global[12];
 };
 
@@ -457,20 +566,23 @@ __device__ __forceinline__ double block_entry(const double* blk, int NT, int la,
   return blk[tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7)];
 }
 
-// H[gi][gj] (upper, mirrored) and b[gi]: owner-computes gather over the per-key blocks.  One thread per entry.
-__global__ void assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs, int n_desc, const int* ctl) {
+// H[gi][gj] (upper, mirrored) and b[gi]: owner-computes gather over the per-key blocks.  One WARP per entry: the
+// lanes stride the (block, partial) contribution list in a fixed assignment and are combined by a fixed butterfly,
+// so the sum order never changes between runs.
+__global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
+                                                       int n_desc, const int* ctl) {
   if (ctl && ctl[0]) return;
   const int D = cm.D;
   const int n_upper = D * (D + 1) / 2;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n_upper + D) return;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_upper + D) return;
   int gi, gj;
-  bool is_b = tid >= n_upper;
+  const bool is_b = wid >= n_upper;
   if (is_b) {
-    gi = tid - n_upper;
+    gi = wid - n_upper;
     gj = -1;
-  } else {  // unrank (gi <= gj) from row-major upper-triangular index
-    int rem = tid;
+  } else {  // unrank (gi <= gj) from the row-major upper-triangular index
+    int rem = wid;
     gi = 0;
     while (rem >= D - gi) { rem -= D - gi; gi++; }
     gj = gi + rem;
@@ -480,30 +592,64 @@ __global__ void assemble_kernel(double* H, double* b, ColMaps cm, const StreamDe
   double acc = 0.0;
   for (int d = 0; d < n_desc; d++) {
     const StreamDesc& sd = descs[d];
-    // local column candidates of gi / gj inside a block with key s
     int ei = -1, ej = -1;  // extra local columns
     for (int e = 0; e < sd.n_extra; e++) {
-      if (sd.extra_global[e] == gi) ei = 24 + e;
-      if (!is_b && sd.extra_global[e] == gj) ej = 24 + e;
+      if (sd.extra_global[e] == gi) ei = sd.extra_base + e;
+      if (!is_b && sd.extra_global[e] == gj) ej = sd.extra_base + e;
     }
     if (ki < 0 && ei < 0) continue;
     if (!is_b && kj < 0 && ej < 0) continue;
-    int s_lo = 0, s_hi = sd.n_keys - 1;
-    if (ki >= 0) { s_lo = max(s_lo, ki - 3); s_hi = min(s_hi, ki); }
-    if (!is_b && kj >= 0) { s_lo = max(s_lo, kj - 3); s_hi = min(s_hi, kj); }
-    for (int s = s_lo; s <= s_hi; s++) {
-      const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
-      const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
-      const double* blk = sd.part + (size_t)s * sd.P * sd.rd;
-      for (int p = 0; p < sd.P; p++) acc += block_entry(blk + (size_t)p * sd.rd, sd.NT, la, lb);
-      acc += block_entry(sd.overflow + (size_t)s * sd.rd, sd.NT, la, lb);
+    const int PP = sd.P + 1;  // partials + the overflow block
+    if (sd.kind == 0) {
+      int s_lo = 0, s_hi = sd.n_keys - 1;
+      if (ki >= 0) { s_lo = max(s_lo, ki - 3); s_hi = min(s_hi, ki); }
+      if (!is_b && kj >= 0) { s_lo = max(s_lo, kj - 3); s_hi = min(s_hi, kj); }
+      const int n_items = max(0, s_hi - s_lo + 1) * PP;
+      for (int it = lane; it < n_items; it += 32) {
+        const int s = s_lo + it / PP, p = it % PP;
+        const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
+        const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
+        const double* blk = p < sd.P ? sd.part + ((size_t)s * sd.P + p) * sd.rd : sd.overflow + (size_t)s * sd.rd;
+        acc += block_entry(blk, sd.NT, la, lb);
+      }
+    } else {
+      // two knot windows: a global knot column may appear in window i, window j or both (overlap): J_g = sum of locals
+      const int nk = sd.kdim;
+      const int n_items = nk * nk * PP;
+      for (int it = lane; it < n_items; it += 32) {
+        const int key = it / PP, p = it % PP;
+        const int si = key / nk, sj = key % nk;
+        int la[2], lb[2], na = 0, nb = 0;
+        if (ki >= 0) {
+          if (ki - si >= 0 && ki - si <= 3) la[na++] = 6 * (ki - si) + ci;
+          if (ki - sj >= 0 && ki - sj <= 3) la[na++] = 24 + 6 * (ki - sj) + ci;
+        } else {
+          la[na++] = ei;
+        }
+        if (is_b) {
+          lb[nb++] = sd.r_col;
+        } else if (kj >= 0) {
+          if (kj - si >= 0 && kj - si <= 3) lb[nb++] = 6 * (kj - si) + cj;
+          if (kj - sj >= 0 && kj - sj <= 3) lb[nb++] = 24 + 6 * (kj - sj) + cj;
+        } else {
+          lb[nb++] = ej;
+        }
+        if (na == 0 || nb == 0) continue;
+        const double* blk = p < sd.P ? sd.part + ((size_t)key * sd.P + p) * sd.rd : sd.overflow + (size_t)key * sd.rd;
+        for (int x = 0; x < na; x++)
+          for (int y = 0; y < nb; y++) acc += block_entry(blk, sd.NT, la[x], lb[y]);
+      }
     }
   }
-  if (is_b) {
-    b[gi] = acc;
-  } else {
-    H[(size_t)gi * D + gj] = acc;
-    H[(size_t)gj * D + gi] = acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (is_b) {
+      b[gi] = acc;
+    } else {
+      H[(size_t)gi * D + gj] = acc;
+      H[(size_t)gj * D + gi] = acc;
+    }
   }
 }
 

@@ -67,4 +67,23 @@ __attribute__((visibility("default"))) int emul_imu(int K, const double* kq, con
   *s_out = s;
   return 0;
 }
+
+__attribute__((visibility("default"))) int emul_image(int K, const double* kq, const double* kp, int64_t t0_ns,
+                                                       int64_t dt_ns, int64_t ti_ns, int64_t tj_ns, const double* p_i,
+                                                       const double* p_j, double d_inv, const double* S_CtoI,
+                                                       const double* p_CinI, double loss_a, int want_toff,
+                                                       double* rows /*2*56*/, double* rho, int* si_out, int* sj_out) {
+  HostWindow W(K, kq, kp);
+  int si, sj;
+  double ui, uj;
+  if (!index_ns(ti_ns, t0_ns, dt_ns, K, &si, &ui) || !index_ns(tj_ns, t0_ns, dt_ns, K, &sj, &uj)) return 1;
+  ImageShared sh;
+  sh.S_CtoI = ldq(S_CtoI); sh.p_CinI = ldv(p_CinI); sh.sqrt_info = 450.0 / 1.5; sh.loss_a = loss_a;
+  sh.inv_dt = 1e9 / double(dt_ns); sh.want_toff = want_toff != 0;
+  ArraySink sink{rows, 56};
+  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink);
+  *si_out = si;
+  *sj_out = sj;
+  return 0;
+}
 }

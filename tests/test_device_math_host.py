@@ -26,6 +26,8 @@ def emul():
                               C.c_double, dp, dp, ip, dp]
     lib.emul_imu.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp, C.c_double,
                              C.c_int, dp, dp, ip]
+    lib.emul_image.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp, C.c_double, dp, dp,
+                               C.c_double, C.c_int, dp, dp, ip, ip]
     return lib
 
 
@@ -117,4 +119,45 @@ def test_imu_rows(oracle, emul, name, sw, marg):
         worst = max(worst, max(d) / scale)
         assert np.allclose(rows[:, c_r], r_o, rtol=1e-10, atol=1e-9)
         assert not rows[:, c_r + 1:].any()
+    assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("unlock_toff", [False, True])
+def test_image_rows(oracle, emul, unlock_toff):
+    sw = S.make_window(10, n_lidar=0, n_imu=0, n_landmarks=12, obs_per_landmark=6, seed=31, time_margin_ns=3_000_000)
+    w = sw.window
+    if unlock_toff:
+        w.t_offset_ns = np.array([0, 0, 120_000.4])
+    opt = E.default_options(oracle)
+    if unlock_toff:
+        opt.lock_t_offset[2] = 0
+        opt.t_offset_padding_ns = 1_000_000
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    I = sw.image
+    assert est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], True) == 0
+    Lay = est.layout()
+    kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
+    worst = 0.0
+    overlaps = 0
+    for i in range(len(I["t_i"])):
+        r_o, J_o = oracle_lib.block_jacobian(oracle, est, i, apply_loss=True)
+        toff = int(w.t_offset_ns[2])
+        ti = int(np.int64(I["t_i"][i] * 1e9)) + toff
+        tj = int(np.int64(I["t_j"][i] * 1e9)) + toff
+        rows, rho, si, sj = np.zeros((2, 56)), np.zeros(1), C.c_int(0), C.c_int(0)
+        pi, pj = np.ascontiguousarray(I["p_i"][i]), np.ascontiguousarray(I["p_j"][i])
+        rc = emul.emul_image(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, ti, tj, dptr(pi), dptr(pj),
+                             float(w.inv_depth[I["landmark"][i]]), dptr(w.S_CtoI), dptr(w.p_CinI), 2.0,
+                             int(unlock_toff), dptr(rows), dptr(rho), C.byref(si), C.byref(sj))
+        assert rc == 0
+        J = np.zeros_like(J_o)
+        J[:, 6 * si.value:6 * si.value + 24] += rows[:, :24]
+        J[:, 6 * sj.value:6 * sj.value + 24] += rows[:, 24:48]   # overlapping windows add up
+        if unlock_toff:
+            J[:, Lay.col_t_offset[2]] += rows[:, 48]
+        overlaps += abs(si.value - sj.value) < 4
+        scale = max(1.0, np.abs(J_o).max())
+        worst = max(worst, np.abs(J - J_o).max() / scale)
+        assert np.allclose(rows[:, 49], r_o, rtol=1e-10, atol=1e-9)
+    assert overlaps > 0
     assert worst < 1e-11, worst

@@ -21,12 +21,16 @@ def rel_scaled(Hg, Ho):
     return (np.abs(Hg - Ho) / np.outer(d, d)).max()
 
 
-def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000):
+def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000,
+          unlock_cam_toff=False):
     opt = E.default_options(lib)
     if unlock_bias:
         opt.lock_ab = opt.lock_wb = 0
     if unlock_toff:
         opt.lock_t_offset[0] = 0
+        opt.t_offset_padding_ns = pad
+    if unlock_cam_toff:
+        opt.lock_t_offset[2] = 0
         opt.t_offset_padding_ns = pad
     est = E.TrajectoryEstimator(sw.window, opt, lib)
     est.SetFixedIndex(fixed)
@@ -40,7 +44,7 @@ def compare_eval(cuda, oracle, sw, **kw):
     assert dg == do
     Lg, Lo = eg.layout(), eo.layout()
     assert Lg.D == Lo.D
-    for stream in (0, 1):
+    for stream in (0, 1, 2, 3):
         sg, ug = eg.indices(stream)
         so, uo = eo.indices(stream)
         assert np.array_equal(sg, so)          # feature-to-knot indexing: bit-exact
@@ -161,3 +165,25 @@ def test_prior_factor(cuda, oracle):
     assert rel(res["g"][1], res["o"][1]) < REL
     assert abs(res["g"][2] - res["o"][2]) <= REL * abs(res["o"][2])
     assert rel(res["gn"][0], res["on"][0]) < 1e-12 and rel(res["gn"][1], res["on"][1]) < 1e-12
+
+
+def test_c3_lidar_inertial_camera(cuda, oracle):
+    """BASELINE config 3 at 1/10 size: LiDAR + 2k-scale visual reprojection factors (inverse-depth landmarks, fixed) +
+    IMU with bias factor.  Visual factors create the only off-band H blocks."""
+    sw = S.config(3, 0.1)
+    assert len(sw.image["t_i"]) > 100
+    compare_eval(cuda, oracle, sw, unlock_bias=True)
+
+
+def test_visual_only_camera_time_offset(cuda, oracle):
+    sw = S.make_window(10, n_lidar=0, n_imu=0, n_landmarks=60, obs_per_landmark=8, seed=41, time_margin_ns=3_000_000,
+                       t_offset_ns=(0.0, 0.0, 150_000.3))
+    compare_eval(cuda, oracle, sw, unlock_cam_toff=True, pad=1_000_000, bias_factor=False)
+
+
+def test_visual_unsorted_and_fixed_knots(cuda, oracle):
+    sw = S.make_window(10, n_lidar=300, n_imu=40, n_landmarks=80, obs_per_landmark=7, seed=43)
+    perm = np.random.default_rng(2).permutation(len(sw.image["t_i"]))
+    for k in ("t_i", "p_i", "t_j", "p_j", "landmark"):
+        sw.image[k] = np.ascontiguousarray(sw.image[k][perm])
+    compare_eval(cuda, oracle, sw, fixed=4)

@@ -67,3 +67,8 @@ def test_single_iteration_and_zero(cuda, oracle):
 
 def test_40_knot_solve(cuda, oracle):
     solve_both(cuda, oracle, S.config(4, 0.25), 6, unlock_bias=True)
+
+
+def test_c3_solve(cuda, oracle):
+    """BASELINE config 3 at 1/10 size: LiDAR-inertial-camera solve."""
+    solve_both(cuda, oracle, S.config(3, 0.1), 8, unlock_bias=True)
