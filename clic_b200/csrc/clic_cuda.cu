@@ -217,7 +217,9 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.grid = std::max(ex.grid, 1);
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
-  ex.P = pair_keys ? 1 : (int)std::min<size_t>(8, std::max<size_t>(1, slots / 64));
+  // reduction parts: ~256 record slots (8 CTAs) each, so no (key, part) CTA walks more than a handful of records
+  ex.P = (int)std::min<size_t>(pair_keys ? 8 : 64, std::max<size_t>(1, slots / 256));
+  ex.P = std::max<int>(ex.P, (int)((slots + kMaxChunk - 1) / kMaxChunk));
   CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
   CU(ex.key.ensure(slots * sizeof(int)));
   CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
@@ -313,11 +315,11 @@ int ensure_layout(clic_estimator* E) {
 int launch_reduce(clic_estimator* E, const StreamExec& ex, const int* ctl) {
   dim3 g(ex.n_keys, ex.P);
   const int n_slots = ex.n_warps * kSlotsPerWarp;
-  const size_t smem = (size_t)8 * ex.rd * sizeof(double);
+  const size_t smem = 0;
   switch (ex.NT) {
-    case 4: reduce_records_kernel<20><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
-    case 5: reduce_records_kernel<30><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
-    case 7: reduce_records_kernel<56><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 4: reduce_records_kernel<640><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 5: reduce_records_kernel<960><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 7: reduce_records_kernel<1792><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
     default: return 1;
   }
   return 0;
@@ -712,9 +714,6 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, true>, smem5)) || (rc = set_smem(image_kernel<true>, factor_smem_bytes(E->K, 7))) ||
       (rc = set_smem(image_kernel<false>, factor_smem_bytes(E->K, 7))))
-    return rc;
-  if ((rc = set_smem(reduce_records_kernel<20>, 8 * 640 * 8)) || (rc = set_smem(reduce_records_kernel<30>, 8 * 960 * 8)) ||
-      (rc = set_smem(reduce_records_kernel<56>, 8 * 1792 * 8)))
     return rc;
   CU(cudaStreamSynchronize(E->stream));
   *out = E.release();

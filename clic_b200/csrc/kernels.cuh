@@ -131,10 +131,14 @@ __device__ __forceinline__ WindowView stage_window(double* smem, const PassParam
   W.kq = kq;
   W.kp = kp;
   W.pair = pair;
-  *rest = reinterpret_cast<double*>(pair + (K - 1));
+  size_t used = (size_t)7 * K + (size_t)kPairDoubles * (K - 1);
+  used = (used + 1) & ~(size_t)1;  // keep what follows 16-byte aligned (double2 accesses)
+  *rest = smem + used;
   return W;
 }
-__host__ __device__ inline size_t window_smem_doubles(int K) { return (size_t)7 * K + (size_t)kPairDoubles * (K - 1); }
+__host__ __device__ inline size_t window_smem_doubles(int K) {
+  return (((size_t)7 * K + (size_t)kPairDoubles * (K - 1)) + 1) & ~(size_t)1;
+}
 
 template <int NT>
 __device__ __forceinline__ void flush_record(const WarpAcc<NT>& acc, int key, int& slot, int warp_global,
@@ -148,6 +152,52 @@ __device__ __forceinline__ void flush_record(const WarpAcc<NT>& acc, int key, in
   } else {  // unsorted input: correct but unordered
     acc.atomic_add(rb.overflow + (size_t)key * n_tiles(NT) * 64, lane);
     if (lane == 0) *rb.overflow_flag = 1;
+  }
+}
+
+// End of a factor kernel: the live accumulators of the CTA's warps that share the key of the first live warp (all
+// of them, for time-sorted input) are summed through shared memory in warp order and written as ONE record; the
+// others are flushed individually.  8x fewer records for the reduction stage, still no atomics, still fixed order.
+// `scratch` (>= n_tiles(NT)*64 doubles) may alias the Jt tiles: they are dead by now.
+template <int NT>
+__device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT>& acc, int acc_key, int& slot, int warp, int lane,
+                                                    int warp_global, const RecordBuf& rb, double* scratch) {
+  __shared__ int s_key, s_first;
+  __syncthreads();
+  if (threadIdx.x == 0) { s_key = -1; s_first = -1; }
+  __syncthreads();
+  for (int w = 0; w < kWarpsPerCta; w++) {
+    if (warp == w && lane == 0 && s_key < 0 && acc_key >= 0) { s_key = acc_key; s_first = w; }
+    __syncthreads();
+  }
+  const int kc = s_key, w_first = s_first;
+  const bool merged = acc_key >= 0 && acc_key == kc;
+  for (int w = 0; w < kWarpsPerCta; w++) {
+    if (warp == w && merged) {
+#pragma unroll
+      for (int t = 0; t < n_tiles(NT); t++) {
+        double2* dst = reinterpret_cast<double2*>(scratch + t * 64 + 2 * lane);
+        double2 v = make_double2(acc.c[t][0], acc.c[t][1]);
+        if (w != w_first) { double2 o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (!merged) {
+    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+  } else if (warp == w_first) {
+    if (slot < kSlotsPerWarp) {
+      const int r = warp_global * kSlotsPerWarp + slot;
+      double* dst = rb.payload + (size_t)r * n_tiles(NT) * 64;
+      for (int i = lane; i < n_tiles(NT) * 64; i += 32) dst[i] = scratch[i];
+      if (lane == 0) rb.key[r] = kc;
+      slot++;
+    } else {
+      double* dst = rb.overflow + (size_t)kc * n_tiles(NT) * 64;
+      for (int i = lane; i < n_tiles(NT) * 64; i += 32) atomicAdd(dst + i, scratch[i]);
+      if (lane == 0) *rb.overflow_flag = 1;
+    }
   }
 }
 
@@ -227,9 +277,8 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
     }
   }
   if (JAC) {
-    flush_record<4>(acc, acc_key, slot, warp_global, rb, lane);
-    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32)
-      if (sidx >= slot) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+    cta_merge_and_flush<4>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
   }
   // deterministic butterfly
 #pragma unroll
@@ -244,43 +293,61 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
 }
 
 // Level-1 reduction: CTA (key, part) sums the payloads whose key matches over its share of the record slots.
-// Warp w of the CTA takes slots r0+w, r0+w+8, ... (lanes stride the payload, coalesced); the 8 warp sums are then
-// combined through shared memory in warp order: fixed assignment + fixed order => deterministic.
-// out[(key * P + part) * RD + e].  RD <= 32 * kMaxRdPerLane.
-constexpr int kMaxRdPerLane = 56;  // RD = 1792 (NT = 7, visual) / 32
-template <int RDL>                 // doubles per lane = RD / 32
+// Warp 0 first builds the ordered list of matching slots; then every thread owns RD/256 payload elements and walks
+// the list in order, issuing the loads of four records before their adds (memory-level parallelism without
+// changing the summation order => deterministic).  out[(key * P + part) * RD + e].
+constexpr int kMaxChunk = 1024;
+template <int RD>
 __global__ void __launch_bounds__(256)
 reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const int* ctl) {
   if (ctl && ctl[0]) return;
-  constexpr int RD = RDL * 32;
-  extern __shared__ double red[];  // [8][RD]
+  constexpr int EPT = (RD + 255) / 256;
+  __shared__ int list[kMaxChunk];
+  __shared__ int n_match;
   const int k = blockIdx.x, part = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = (n_slots + P - 1) / P;
   const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
-  double acc[RDL];
-#pragma unroll
-  for (int i = 0; i < RDL; i++) acc[i] = 0.0;
-  for (int rb = r0 + warp * 32; rb < r1; rb += 8 * 32) {
-    // each lane looks at one slot key, then the warp walks the matching slots in order
-    const int r = rb + lane;
-    unsigned m = __ballot_sync(0xffffffffu, r < r1 && key[r] == k);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const double* src = payload + (size_t)(rb + j) * RD;
-#pragma unroll
-      for (int i = 0; i < RDL; i++) acc[i] += src[i * 32 + lane];
+  if (warp == 0) {
+    int cnt = 0;
+    for (int rb = r0; rb < r1; rb += 32) {
+      const int r = rb + lane;
+      const bool hit = r < r1 && key[r] == k;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < kMaxChunk) list[pos] = r;
+      }
+      cnt += __popc(m);
     }
+    if (lane == 0) n_match = min(cnt, kMaxChunk);
+  }
+  __syncthreads();
+  const int n = n_match;
+  double acc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; i++) acc[i] = 0.0;
+  for (int j = 0; j < n; j += 4) {
+    double v[4][EPT];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const bool on = j + q < n;
+      const double* src = payload + (size_t)(on ? list[j + q] : 0) * RD;
+#pragma unroll
+      for (int i = 0; i < EPT; i++) {
+        const int e = threadIdx.x + i * 256;
+        v[q][i] = (on && e < RD) ? src[e] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
   }
 #pragma unroll
-  for (int i = 0; i < RDL; i++) red[warp * RD + i * 32 + lane] = acc[i];
-  __syncthreads();
-  for (int e = threadIdx.x; e < RD; e += blockDim.x) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) s += red[w * RD + e];
-    out[((size_t)k * P + part) * RD + e] = s;
+  for (int i = 0; i < EPT; i++) {
+    const int e = threadIdx.x + i * 256;
+    if (e < RD) out[((size_t)k * P + part) * RD + e] = acc[i];
   }
 }
 
@@ -421,7 +488,7 @@ imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
     }
   }
   if (JAC) {
-    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
     for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
   }
 #pragma unroll
@@ -511,7 +578,7 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
     }
   }
   if (JAC) {
-    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
     for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
   }
 #pragma unroll
