@@ -511,6 +511,15 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
   return CLIC_OK;
 }
 
+// copies a host array to a temporary device buffer on the estimator's stream
+template <class T>
+int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
+  CU(buf.ensure(std::max<size_t>(1, count) * sizeof(T)));
+  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, E->stream));
+  return CLIC_OK;
+}
+
+
 // clic_solve: the LM loop runs on the device; the host only enqueues kernels (and, for bounded problems, polls the
 // line-search flag once per sample).
 int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
@@ -623,6 +632,237 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   return CLIC_OK;
 }
 
+// clic_marginalize: preMarginalize + marginalize (marginalization_factor.cpp:94-116, 150-276) on the device.
+int marginalize_impl(clic_estimator* E, clic_prior** out) {
+  const int K = E->K;
+  const int later_local = E->opt.ctrl_to_be_opt_later - E->knot_id0;
+  const bool drop_knots = E->opt.ctrl_to_be_opt_later > E->opt.ctrl_to_be_opt_now;  // trajectory_estimator.cpp:214
+  PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
+  pp.marg_mode = 1;
+  pp.kf = 0;
+  pp.marg_later_local = drop_knots ? later_local : 0;  // no knot is dropped => only factors with other dropped blocks stay
+  int rc;
+  DevBuf d_present;
+  CU(d_present.ensure((size_t)(K - 3) * sizeof(int)));
+  std::vector<char> knot_used(K, 0);
+  std::vector<int> present(K - 3);
+  auto mark = [&](const StreamExec& ex, int r_col) -> int {
+    key_presence_kernel<<<(ex.n_keys + 63) / 64, 64, 0, E->stream>>>(ex.part.as<double>(), ex.overflow.as<double>(),
+                                                                    ex.n_keys, ex.P, ex.rd, ex.NT, r_col,
+                                                                    d_present.as<int>());
+    E->launches++;
+    CU(cudaMemcpyAsync(present.data(), d_present.p, ex.n_keys * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    for (int s = 0; s < ex.n_keys; s++)
+      if (present[s])
+        for (int k = s; k < s + 4; k++) knot_used[k] = 1;
+    return CLIC_OK;
+  };
+  bool any_imu = false;
+  std::vector<char> bias_used(2 * std::max(1, E->n_bias), 0), bias_drop(2 * std::max(1, E->n_bias), 0);
+  E->prof_begin(7);
+  for (auto& b : E->loam) {
+    if (!b->marg) continue;
+    StreamExec& ex = b->ex;
+    CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+    loam_kernel<true><<<ex.grid, kThreads, factor_smem_bytes(K, 4), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    if (launch_reduce(E, ex, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
+    E->launches += 2;
+    if ((rc = mark(ex, 24))) return rc;
+  }
+  for (auto& b : E->imu) {
+    if (!b->marg) continue;
+    StreamExec& ex = b->ex;
+    CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
+    imu_kernel<true, true><<<ex.grid, kThreads, factor_smem_bytes(K, 5), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    if (launch_reduce(E, ex, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
+    E->launches += 2;
+    if ((rc = mark(ex, 34))) return rc;
+    bool used = false;
+    for (int s = 0; s < ex.n_keys; s++) used = used || present[s];
+    if (used) {
+      any_imu = true;
+      bias_used[b->st.bias_slot] = bias_used[E->n_bias + b->st.bias_slot] = 1;
+      if (E->opt.marg_bias_param) bias_drop[b->st.bias_slot] = bias_drop[E->n_bias + b->st.bias_slot] = 1;
+    }
+  }
+  for (auto& bf : E->bias_f) {
+    if (!bf.marg) continue;
+    for (int sl : {bf.slot_i, bf.slot_j}) bias_used[sl] = bias_used[E->n_bias + sl] = 1;
+    if (E->opt.marg_bias_param) {  // trajectory_estimator.cpp:483-489
+      bias_drop[bf.slot_i] = bias_drop[E->n_bias + bf.slot_i] = 1;
+      if (bf.marg_all) bias_drop[bf.slot_j] = bias_drop[E->n_bias + bf.slot_j] = 1;
+    }
+  }
+  // ---- blocks in canonical order, dropped first (marginalization_factor.cpp:154-166) ----
+  struct Blk { int kind, id, size, used, drop, idx; };
+  std::vector<Blk> blocks;
+  std::vector<char> knot_drop(K, 0);
+  bool grav_used = any_imu, grav_drop = any_imu && E->opt.marg_gravity_param;
+  bool toff_used[3] = {any_imu, false, false}, toff_drop[3] = {any_imu && E->opt.marg_t_offset_param != 0, false, false};
+  for (auto& pr : E->priors) {
+    std::vector<char> dropped(pr->p->blocks.size(), 0);
+    for (int d : pr->drop) if (d >= 0 && d < (int)dropped.size()) dropped[d] = 1;
+    for (size_t i = 0; i < pr->p->blocks.size(); i++) {
+      const auto& b = pr->p->blocks[i];
+      switch (b.kind) {
+        case CLIC_BLOCK_KNOT_ROT:
+        case CLIC_BLOCK_KNOT_POS: knot_used[b.id - E->knot_id0] = 1; if (dropped[i]) knot_drop[b.id - E->knot_id0] = 1; break;
+        case CLIC_BLOCK_BIAS_GYRO: bias_used[b.id - E->bias_id0] = 1; if (dropped[i]) bias_drop[b.id - E->bias_id0] = 1; break;
+        case CLIC_BLOCK_BIAS_ACCEL: bias_used[E->n_bias + b.id - E->bias_id0] = 1; if (dropped[i]) bias_drop[E->n_bias + b.id - E->bias_id0] = 1; break;
+        case CLIC_BLOCK_GRAVITY: grav_used = true; if (dropped[i]) grav_drop = true; break;
+        case CLIC_BLOCK_T_OFFSET: toff_used[b.id] = true; if (dropped[i]) toff_drop[b.id] = true; break;
+        default: return fail(CLIC_ERR_UNSUPPORTED, "inverse-depth blocks in a prior are not built on the GPU yet");
+      }
+    }
+  }
+  for (int k = 0; k < K; k++) {
+    if (!knot_used[k]) continue;
+    const int drop = (drop_knots && k < later_local) || knot_drop[k] ? 1 : 0;
+    blocks.push_back({CLIC_BLOCK_KNOT_ROT, k, 4, 1, drop, -1});
+    blocks.push_back({CLIC_BLOCK_KNOT_POS, k, 3, 1, drop, -1});
+  }
+  for (int j = 0; j < E->n_bias; j++) if (bias_used[j]) blocks.push_back({CLIC_BLOCK_BIAS_GYRO, j, 3, 1, bias_drop[j], -1});
+  for (int j = 0; j < E->n_bias; j++)
+    if (bias_used[E->n_bias + j]) blocks.push_back({CLIC_BLOCK_BIAS_ACCEL, j, 3, 1, bias_drop[E->n_bias + j], -1});
+  if (grav_used) blocks.push_back({CLIC_BLOCK_GRAVITY, 0, 3, 1, grav_drop ? 1 : 0, -1});
+  for (int sn = 0; sn < 3; sn++) if (toff_used[sn]) blocks.push_back({CLIC_BLOCK_T_OFFSET, sn, 1, 1, toff_drop[sn] ? 1 : 0, -1});
+  int pos = 0;
+  for (auto& b : blocks) if (b.drop) { b.idx = pos; pos += b.size == 4 ? 3 : b.size; }
+  const int m = pos;
+  for (auto& b : blocks) if (!b.drop) { b.idx = pos; pos += b.size == 4 ? 3 : b.size; }
+  const int n = pos - m;
+  if (n <= 0 || blocks.empty()) return fail(CLIC_ERR_NOTHING_TO_KEEP, "marginalization leaves no parameters");
+  auto find = [&](int kind, int id) -> int {
+    for (auto& b : blocks) if (b.kind == kind && b.id == id) return b.idx;
+    return -1;
+  };
+  // ---- column maps of the marg system ----
+  std::vector<int> knot_col(K, -1), col_knot(pos, -1), col_sub(pos, 0);
+  for (int k = 0; k < K; k++) {
+    int c = find(CLIC_BLOCK_KNOT_ROT, k);
+    knot_col[k] = c;
+    if (c >= 0) for (int a = 0; a < 6; a++) { col_knot[c + a] = k; col_sub[c + a] = a; }
+  }
+  DevBuf d_kc, d_ck, d_cs, d_desc, d_A, d_b, d_J0, d_r0, d_status, d_cost;
+  if ((rc = to_device(E, d_kc, knot_col.data(), K)) || (rc = to_device(E, d_ck, col_knot.data(), pos)) ||
+      (rc = to_device(E, d_cs, col_sub.data(), pos)))
+    return rc;
+  std::vector<StreamDesc> descs;
+  for (auto& b : E->loam) {
+    if (!b->marg) continue;
+    StreamDesc d{};
+    d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
+    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 24; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    descs.push_back(d);
+  }
+  for (auto& b : E->imu) {
+    if (!b->marg) continue;
+    StreamDesc d{};
+    d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
+    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 34; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    const int cg = find(CLIC_BLOCK_BIAS_GYRO, b->st.bias_slot), ca = find(CLIC_BLOCK_BIAS_ACCEL, b->st.bias_slot),
+              cgr = find(CLIC_BLOCK_GRAVITY, 0), ct = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU);
+    for (int c = 0; c < 3; c++) {
+      d.extra_global[c] = cg >= 0 ? cg + c : -1;
+      d.extra_global[3 + c] = ca >= 0 ? ca + c : -1;
+      d.extra_global[6 + c] = cgr >= 0 ? cgr + c : -1;
+    }
+    d.extra_global[9] = ct;
+    descs.push_back(d);
+  }
+  if ((rc = to_device(E, d_desc, descs.data(), descs.size()))) return rc;
+  CU(d_A.ensure((size_t)pos * pos * sizeof(double)));
+  CU(d_b.ensure((size_t)pos * sizeof(double)));
+  CU(d_J0.ensure((size_t)n * n * sizeof(double)));
+  CU(d_r0.ensure((size_t)n * sizeof(double)));
+  CU(d_status.ensure(sizeof(int)));
+  CU(d_cost.ensure(2 * sizeof(double)));
+  CU(cudaMemsetAsync(d_cost.p, 0, 2 * sizeof(double), E->stream));
+  ColMaps cm;
+  cm.D = pos; cm.K = K;
+  cm.knot_col = d_kc.as<int>(); cm.col_knot = d_ck.as<int>(); cm.col_sub = d_cs.as<int>();
+  const int n_entries = pos * (pos + 1) / 2 + pos;
+  assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(d_A.as<double>(), d_b.as<double>(), cm,
+                                                              d_desc.as<StreamDesc>(), (int)descs.size(), nullptr);
+  E->launches++;
+  for (auto& bf : E->bias_f) {
+    if (!bf.marg) continue;
+    BiasFactorDesc d;
+    d.slot_i = bf.slot_i; d.slot_j = bf.slot_j;
+    for (int i = 0; i < 6; i++) d.sqrt_info[i] = bf.sqrt_info[i];
+    d.col_gi = find(CLIC_BLOCK_BIAS_GYRO, bf.slot_i); d.col_gj = find(CLIC_BLOCK_BIAS_GYRO, bf.slot_j);
+    d.col_ai = find(CLIC_BLOCK_BIAS_ACCEL, bf.slot_i); d.col_aj = find(CLIC_BLOCK_BIAS_ACCEL, bf.slot_j);
+    bias_factor_kernel<<<1, 32, 0, E->stream>>>(d, E->d_state.as<double>(), E->sl, d_A.as<double>(), d_b.as<double>(), pos,
+                                                d_cost.as<double>(), 1, nullptr);
+    E->launches++;
+  }
+  for (auto& pr : E->priors) {
+    const int nb = (int)pr->p->blocks.size();
+    for (int i = 0; i < nb; i++) {
+      const auto& b = pr->p->blocks[i];
+      int id = b.id;
+      if (b.kind == CLIC_BLOCK_KNOT_ROT || b.kind == CLIC_BLOCK_KNOT_POS) id -= E->knot_id0;
+      if (b.kind == CLIC_BLOCK_BIAS_GYRO || b.kind == CLIC_BLOCK_BIAS_ACCEL) id -= E->bias_id0;
+      pr->h_meta[4 * i + 3] = find(b.kind, id);
+    }
+    CU(cudaMemcpyAsync(pr->meta.p, pr->h_meta.data(), pr->h_meta.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    const int pn = pr->p->n;
+    size_t smem = (size_t)3 * pn * sizeof(double) + (size_t)pn * sizeof(int);
+    prior_kernel<<<1, 256, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
+                                              pr->x0.as<double>(), pr->meta.as<int>(), pn, nb, E->d_state.as<double>(),
+                                              d_A.as<double>(), d_b.as<double>(), pos, d_cost.as<double>(), 1, nullptr);
+    E->launches++;
+    CU(cudaStreamSynchronize(E->stream));  // h_meta is reused by the solve path
+  }
+  int status = -1;
+  CU(cudaMemsetAsync(d_status.p, 0xff, sizeof(int), E->stream));
+  schur_kernel<<<1, 512, 0, E->stream>>>(d_A.as<double>(), d_b.as<double>(), m, n, d_J0.as<double>(), d_r0.as<double>(),
+                                         d_status.as<int>());
+  E->launches++;
+  E->prof_end();
+  std::unique_ptr<clic_prior> P(new clic_prior);
+  P->n = n;
+  P->m = m;
+  P->J0.resize((size_t)n * n);
+  P->r0.resize(n);
+  std::vector<double> h(E->sl.size());
+  CU(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(P->J0.data(), d_J0.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(P->r0.data(), d_r0.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(h.data(), E->d_state.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  CU(cudaGetLastError());
+  if (status == 6)
+    return fail(CLIC_ERR_NOT_POSITIVE_DEFINITE,
+                "marginalization: A_mm or the Schur complement is not positive definite (rank-deficient blocks need the "
+                "eigen-decomposition path of marginalization_factor.cpp:208-264, not built on the GPU yet)");
+  if (status != 0) return fail(CLIC_ERR_CUDA, "schur kernel did not complete");
+  for (auto& b : blocks) {
+    if (b.drop) continue;
+    clic_prior::Block pb;
+    pb.kind = b.kind;
+    pb.size = b.size;
+    pb.idx = b.idx - m;
+    pb.id = b.id;
+    const double* src = nullptr;
+    switch (b.kind) {
+      case CLIC_BLOCK_KNOT_ROT: pb.id += E->knot_id0; src = &h[E->sl.off_q() + 4 * b.id]; break;
+      case CLIC_BLOCK_KNOT_POS: pb.id += E->knot_id0; src = &h[E->sl.off_p() + 3 * b.id]; break;
+      case CLIC_BLOCK_BIAS_GYRO: pb.id += E->bias_id0; src = &h[E->sl.off_bias() + 6 * b.id]; break;
+      case CLIC_BLOCK_BIAS_ACCEL: pb.id += E->bias_id0; src = &h[E->sl.off_bias() + 6 * b.id + 3]; break;
+      case CLIC_BLOCK_GRAVITY: src = &h[E->sl.off_grav()]; break;
+      default: src = &h[E->sl.off_toff() + b.id]; break;
+    }
+    for (int k = 0; k < 4; k++) pb.x0[k] = k < b.size ? src[k] : 0.0;
+    P->blocks.push_back(pb);
+  }
+  *out = P.release();
+  return CLIC_OK;
+}
+
 int upload_state(clic_estimator* E) {
   CU(cudaMemcpyAsync(E->d_state.p, E->h_state.data(), E->h_state.size() * sizeof(double), cudaMemcpyHostToDevice,
                      E->stream));
@@ -630,14 +870,6 @@ int upload_state(clic_estimator* E) {
 }
 
 bool ok_handle(const clic_estimator* h) { return h != nullptr; }
-
-// copies a host array to a temporary device buffer on the estimator's stream
-template <class T>
-int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
-  CU(buf.ensure(std::max<size_t>(1, count) * sizeof(T)));
-  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, E->stream));
-  return CLIC_OK;
-}
 
 }  // namespace
 
@@ -1143,7 +1375,11 @@ CLIC_API int clic_write_state(clic_estimator* E, const double* knot_q, const dou
 
 CLIC_API int clic_marginalize(clic_estimator* E, clic_prior** out) {
   if (!ok_handle(E) || !out) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
-  return fail(CLIC_ERR_UNSUPPORTED, "marginalization: CUDA kernel not built yet in this revision");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  return marginalize_impl(E, out);
 }
 
 CLIC_API int clic_prior_create(int32_t n, const double* J0, const double* r0, int32_t n_blocks, const int32_t* kind,

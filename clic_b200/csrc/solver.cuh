@@ -572,3 +572,123 @@ __global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
 }
 
 }  // namespace clic
+
+namespace clic {
+
+// ---------------- K8: marginalization (MarginalizationInfo::marginalize, marginalization_factor.cpp:150-276) ----------------
+// In-place lower Cholesky of the n x n block at A (leading dimension ld) by one CTA.  *ok = 0 on a non-positive pivot.
+__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double piv_s;
+  for (int j = 0; j < n; j++) {
+    if (tid == 0) {
+      double d = A[(size_t)j * ld + j];
+      if (!(d > 0.0) || !isfinite(d)) { *ok = 0; d = 1.0; }
+      piv_s = sqrt(d);
+      A[(size_t)j * ld + j] = piv_s;
+    }
+    __syncthreads();
+    const double piv = piv_s;
+    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * ld + j] = A[(size_t)i * ld + j] / piv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j];
+    }
+    __syncthreads();
+  }
+}
+
+// Schur complement of the first m (dropped) tangent dimensions of the pos x pos system (A, b), then the prior's
+// square-root form.  The reference inverts A_mm and factors the result by symmetric eigendecompositions with an
+// eigenvalue cut of 1e-15 (":208-264"); for the positive-definite systems of a well-constrained window the Cholesky
+// route below gives the same A' = A_rr - A_rm A_mm^-1 A_mr, b' and the same prior energy with
+// J0 = L'^T, r0 = L'^-1 b' (J0^T J0 = A', J0^T r0 = b').  A rank-deficient block reports status 6.
+//   A: pos x pos row-major, symmetric (both triangles valid); overwritten.   J0: n x n, r0: n.   status[0] = 0 ok.
+__global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m, int n, double* J0, double* r0, int* status) {
+  const int pos = m + n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int ok;
+  if (tid == 0) ok = 1;
+  __syncthreads();
+  if (m > 0) {
+    // Amm = 0.5 (A_mm + A_mm^T)  (":208")
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = e / m, j = e % m;
+      if (j < i) {
+        const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
+        A[(size_t)i * pos + j] = v;
+      }
+    }
+    __syncthreads();
+    cta_cholesky(A, pos, m, &ok);
+    __syncthreads();
+    if (!ok) {
+      if (tid == 0) status[0] = 6;
+      return;
+    }
+    // X = L^-1 A_mr (m x n) in place, one column per thread; y = L^-1 b_m
+    for (int c = tid; c < n + 1; c += nt) {
+      for (int i = 0; i < m; i++) {
+        double v = c < n ? A[(size_t)i * pos + m + c] : b[i];
+        for (int k = 0; k < i; k++) v -= A[(size_t)i * pos + k] * (c < n ? A[(size_t)k * pos + m + c] : b[k]);
+        v /= A[(size_t)i * pos + i];
+        if (c < n) A[(size_t)i * pos + m + c] = v; else b[i] = v;
+      }
+    }
+    __syncthreads();
+    // A_rr -= X^T X (lower triangle), b_r -= X^T y
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e % n;
+      if (j <= i) {
+        double acc = 0.0;
+        for (int k = 0; k < m; k++) acc += A[(size_t)k * pos + m + i] * A[(size_t)k * pos + m + j];
+        A[(size_t)(m + i) * pos + m + j] -= acc;
+      }
+    }
+    for (int i = tid; i < n; i += nt) {
+      double acc = 0.0;
+      for (int k = 0; k < m; k++) acc += A[(size_t)k * pos + m + i] * b[k];
+      b[m + i] -= acc;
+    }
+    __syncthreads();
+  }
+  // A' = L' L'^T on the kept block; J0 = L'^T, r0 = L'^-1 b'
+  double* Ar = A + (size_t)m * pos + m;
+  cta_cholesky(Ar, pos, n, &ok);
+  __syncthreads();
+  if (!ok) {
+    if (tid == 0) status[0] = 6;
+    return;
+  }
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, j = e % n;
+    J0[e] = j >= i ? Ar[(size_t)j * pos + i] : 0.0;  // J0[i][j] = L'[j][i]
+  }
+  if (tid == 0) {
+    for (int i = 0; i < n; i++) {
+      double v = b[m + i];
+      for (int k = 0; k < i; k++) v -= Ar[(size_t)i * pos + k] * r0[k];
+      r0[i] = v / Ar[(size_t)i * pos + i];
+    }
+    status[0] = 0;
+  }
+}
+
+// which interval keys received contributions: present[s] = (block diagonal of key s is non-zero)
+__global__ void key_presence_kernel(const double* part, const double* overflow, int n_keys, int P, int rd, int NT,
+                                    int r_col, int* present) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_keys) return;
+  bool any = false;
+  // the (0,0) .. diagonal entries of tile (0,0) and the r~ column are enough: a contributing factor has r != 0 or J != 0
+  for (int p = 0; p <= P && !any; p++) {
+    const double* blk = p < P ? part + ((size_t)s * P + p) * rd : overflow + (size_t)s * rd;
+    for (int l = 0; l < 24 && !any; l++) any = block_entry(blk, NT, l, l) != 0.0;
+    any = any || block_entry(blk, NT, r_col, r_col) != 0.0;
+  }
+  present[s] = any ? 1 : 0;
+}
+
+}  // namespace clic
