@@ -302,6 +302,10 @@ def main():
     e2e_value = n_total * e2e_steps / e2e_s
     d2h = 8 * (D * D + D + 2)
 
+    est.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_kind = measured_peaks()

@@ -2,6 +2,7 @@
 // stages inputs, launches kernels and copies results; there is no CPU implementation of any arithmetic of
 // the path (no fallback: without a CUDA device every compute entry point returns CLIC_ERR_NO_DEVICE).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -29,6 +30,41 @@ int fail(int code, const std::string& m) {
     if (e_ != cudaSuccess)                                                                             \
       return fail(CLIC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
   } while (0)
+
+// ---- NCCL, resolved at run time (the library must load on boxes without NCCL; torch's bundled libnccl.so.2 is
+// already mapped in a torchrun process and is what dlopen returns) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+      api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce;
+    }
+  }
+  return api;
+}
+// One communicator per process, shared by every estimator (an estimator is built per solve; ncclCommInitRank is not).
+struct ProcessComm {
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+} g_comm;
+constexpr int kNcclDouble = 8, kNcclSum = 0;
 
 // Device buffer from the stream-ordered memory pool (cudaMallocAsync): an estimator is built per solve like the
 // reference's (trajectory_manager.cpp:637), so allocations must be cheap; the pool keeps freed blocks cached.
@@ -123,7 +159,18 @@ struct clic_estimator {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int device = 0, n_sm = 148;
-  DevBuf d_state, d_cand, d_H, d_b, d_cost2, d_flags, d_counter;
+  DevBuf d_state, d_cand, d_flags, d_counter;
+  // normal equations: [H D*D | b D | cost_x 2 | cost_cand 2]; `loc` is what this rank's kernels write, `glb` the
+  // all-reduced copy every consumer reads (the same buffer when there is one rank)
+  DevBuf d_nrm_loc, d_nrm_glb;
+  bool use_comm = false;
+  double* H_loc() const { return d_nrm_loc.as<double>(); }
+  double* b_loc() const { return d_nrm_loc.as<double>() + (size_t)std::max(1, L.D) * std::max(1, L.D); }
+  double* cost_loc() const { return b_loc() + std::max(1, L.D); }
+  double* nrm_glb() const { return use_comm ? d_nrm_glb.as<double>() : d_nrm_loc.as<double>(); }
+  double* H_glb() const { return nrm_glb(); }
+  double* b_glb() const { return nrm_glb() + (size_t)std::max(1, L.D) * std::max(1, L.D); }
+  double* cost_glb() const { return b_glb() + std::max(1, L.D); }
   DevBuf d_knot_col, d_col_knot, d_col_sub, d_descs;
   DevBuf d_lm;  // LM workspace (solver.cuh)
   std::vector<std::unique_ptr<LoamBatch>> loam;
@@ -304,8 +351,8 @@ int ensure_layout(clic_estimator* E) {
   CU(E->d_descs.ensure(std::max<size_t>(1, descs.size()) * sizeof(StreamDesc)));
   if (!descs.empty())
     CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
-  CU(E->d_H.ensure((size_t)D * D * sizeof(double)));
-  CU(E->d_b.ensure((size_t)D * sizeof(double)));
+  CU(E->d_nrm_loc.ensure(((size_t)D * D + D + 8) * sizeof(double)));
+  if (E->use_comm) CU(E->d_nrm_glb.ensure(((size_t)D * D + D + 8) * sizeof(double)));
   CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
   E->layout_dirty = false;
   return CLIC_OK;
@@ -331,8 +378,8 @@ int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* 
   const int D = std::max(1, E->L.D);
   size_t smem = (size_t)3 * n * sizeof(double) + (size_t)n * sizeof(int);
   prior_kernel<<<1, 256, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
-                                            pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->d_H.as<double>(),
-                                            E->d_b.as<double>(), D, cost2, jac ? 1 : 0, ctl);
+                                            pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->H_loc(),
+                                            E->b_loc(), D, cost2, jac ? 1 : 0, ctl);
   E->launches++;
   return CLIC_OK;
 }
@@ -389,9 +436,10 @@ int set_smem(KernelT k, size_t bytes) {
 
 // One fused residual (+ Jacobian + normal-equation) pass over the solve problem at `state`.
 // jac = true: H, b, cost2 are produced; false: cost2 only.  ctl: optional device skip word.
-int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, const int* ctl) {
+int run_pass(clic_estimator* E, const double* state, bool jac, int which, const int* ctl) {
   int rc = ensure_layout(E);
   if (rc) return rc;
+  double* cost2 = E->cost_loc() + 2 * which;  // slot 0: pass at x, slot 1: pass at the LM candidate
   PassParams pp = pass_params(E, state, ctl);
   zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
   E->launches += 1;
@@ -484,7 +532,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     cm.col_sub = E->d_col_sub.as<int>();
     const int n_entries = D * (D + 1) / 2 + D;
     E->prof_begin(3);
-    assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(E->d_H.as<double>(), E->d_b.as<double>(), cm,
+    assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(E->H_loc(), E->b_loc(), cm,
                                                                     E->d_descs.as<StreamDesc>(), E->n_desc, ctl);
     E->prof_end();
     E->launches += 1;
@@ -499,7 +547,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
     d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
     d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
-    bias_factor_kernel<<<1, 32, 0, E->stream>>>(d, state, E->sl, E->d_H.as<double>(), E->d_b.as<double>(), std::max(1, D),
+    bias_factor_kernel<<<1, 32, 0, E->stream>>>(d, state, E->sl, E->H_loc(), E->b_loc(), std::max(1, D),
                                                 cost2, jac ? 1 : 0, ctl);
     E->launches += 1;
   }
@@ -508,6 +556,20 @@ int run_pass(clic_estimator* E, const double* state, bool jac, double* cost2, co
     if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl))) return rc;
   }
   CU(cudaGetLastError());
+  if (E->use_comm) {
+    // the single exchange step of the path: sum of H | b | cost over the ranks' factor shards.
+    // Out of place (loc -> glb): a pass skipped by `ctl` leaves loc untouched and the sum is simply recomputed.
+    E->prof_begin(6);
+    NcclApi& nc = nccl_api();
+    const size_t DD = (size_t)std::max(1, D) * std::max(1, D) + std::max(1, D);
+    int e;
+    if (jac)
+      e = nc.AllReduce(E->d_nrm_loc.p, E->d_nrm_glb.p, DD + 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+    else
+      e = nc.AllReduce(E->cost_loc() + 2 * which, E->cost_glb() + 2 * which, 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+    E->prof_end();
+    if (e != 0) return fail(CLIC_ERR_NCCL, std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "?"));
+  }
   return CLIC_OK;
 }
 
@@ -534,10 +596,10 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   CU(E->d_lm.ensure(off));
   char* base = E->d_lm.as<char>();
   LmBufs B;
-  B.H = E->d_H.as<double>();
-  B.b = E->d_b.as<double>();
-  B.cost_x = E->d_cost2.as<double>();
-  B.cost_c = E->d_cost2.as<double>() + 2;
+  B.H = E->H_glb();
+  B.b = E->b_glb();
+  B.cost_x = E->cost_glb();
+  B.cost_c = E->cost_glb() + 2;
   B.scale = (double*)(base + o_scale);
   B.diagonal = (double*)(base + o_diag);
   B.step = (double*)(base + o_step);
@@ -576,7 +638,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     lm_project_kernel<<<1, 256, 0, E->stream>>>(B, L);
     E->launches++;
   }
-  if ((rc = run_pass(E, B.x, true, B.cost_x, nullptr))) return rc;
+  if ((rc = run_pass(E, B.x, true, 0, nullptr))) return rc;
   E->prof_begin(5);
   lm_init_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C, max_iterations, constrained ? 1 : 0);
   E->prof_end();
@@ -588,12 +650,12 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     E->prof_end();
     E->launches++;
     if (it == max_iterations) break;  // the last launch only records the max-iterations termination
-    if ((rc = run_pass(E, B.cand, false, B.cost_c, ctl_res))) return rc;
+    if ((rc = run_pass(E, B.cand, false, 1, ctl_res))) return rc;
     if (constrained) {
       for (int ls = 0; ls < max_ls + 1; ls++) {
         lm_linesearch_kernel<<<1, 256, 0, E->stream>>>(B, L, max_ls);
         E->launches++;
-        if ((rc = run_pass(E, B.cand, false, B.cost_c, ctl_res))) return rc;
+        if ((rc = run_pass(E, B.cand, false, 1, ctl_res))) return rc;
         int active = 0;
         CU(cudaMemcpyAsync(&active, &B.st->ls_active, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
         CU(cudaStreamSynchronize(E->stream));
@@ -604,7 +666,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     lm_accept_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C);
     E->prof_end();
     E->launches++;
-    if ((rc = run_pass(E, B.x, true, B.cost_x, ctl_jac))) return rc;
+    if ((rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
     E->prof_begin(5);
     lm_post_kernel<<<1, 256, sm_small, E->stream>>>(B, L);
     E->prof_end();
@@ -934,7 +996,6 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   AllocScope alloc_scope(E->stream);
   CU(E->d_state.ensure(E->sl.size() * sizeof(double)));
   CU(E->d_cand.ensure(E->sl.size() * sizeof(double)));
-  CU(E->d_cost2.ensure(8 * sizeof(double)));
   CU(E->d_counter.ensure(sizeof(unsigned long long)));
   CU(E->d_flags.ensure(16 * sizeof(int)));
   CU(cudaMemsetAsync(E->d_flags.p, 0, 16 * sizeof(int), E->stream));
@@ -1264,13 +1325,13 @@ CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost
   rc = fill_prior_columns(E);
   if (rc) return rc;
   const bool jac = H || b;
-  rc = run_pass(E, E->d_state.as<double>(), jac, E->d_cost2.as<double>(), nullptr);
+  rc = run_pass(E, E->d_state.as<double>(), jac, 0, nullptr);
   if (rc) return rc;
   const int D = E->L.D;
   double c2[2];
-  if (H && D > 0) CU(cudaMemcpyAsync(H, E->d_H.p, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
-  if (b && D > 0) CU(cudaMemcpyAsync(b, E->d_b.p, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaMemcpyAsync(c2, E->d_cost2.p, sizeof(c2), cudaMemcpyDeviceToHost, E->stream));
+  if (H && D > 0) CU(cudaMemcpyAsync(H, E->H_glb(), (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  if (b && D > 0) CU(cudaMemcpyAsync(b, E->b_glb(), (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(c2, E->cost_glb(), sizeof(c2), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   if (cost) *cost = c2[0];
   if (fixed_cost) *fixed_cost = c2[1];
@@ -1455,9 +1516,38 @@ CLIC_API int clic_prior_release(clic_prior* p) {
   return CLIC_OK;
 }
 
-CLIC_API int clic_comm_unique_id(uint8_t*) { return fail(CLIC_ERR_UNSUPPORTED, "multi-GPU: not built yet in this revision"); }
-CLIC_API int clic_comm_init(clic_estimator*, int32_t, int32_t, const uint8_t*) {
-  return fail(CLIC_ERR_UNSUPPORTED, "multi-GPU: not built yet in this revision");
+CLIC_API int clic_comm_unique_id(uint8_t id[128]) {
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(CLIC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  int e = nc.GetUniqueId(&u);
+  if (e != 0) return fail(CLIC_ERR_NCCL, "ncclGetUniqueId failed");
+  std::memcpy(id, u.internal, 128);
+  return CLIC_OK;
+}
+
+// Attaches the estimator to the process communicator, creating it on the first call (collective over all ranks);
+// later estimators of the same process reuse it and ignore `id`.
+CLIC_API int clic_comm_init(clic_estimator* E, int32_t n_ranks, int32_t rank, const uint8_t id[128]) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n_ranks <= 1) return CLIC_OK;
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(CLIC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  CU(cudaSetDevice(E->device));
+  if (!g_comm.comm) {
+    if (!id) return fail(CLIC_ERR_BAD_ARGUMENT, "unique id required for the first clic_comm_init of the process");
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    int e = nc.CommInitRank(&g_comm.comm, n_ranks, u, rank);
+    if (e != 0) return fail(CLIC_ERR_NCCL, std::string("ncclCommInitRank: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "?"));
+    g_comm.n_ranks = n_ranks;
+    g_comm.rank = rank;
+  } else if (g_comm.n_ranks != n_ranks || g_comm.rank != rank) {
+    return fail(CLIC_ERR_BAD_ARGUMENT, "the process communicator was created with another size / rank");
+  }
+  E->use_comm = true;
+  E->layout_dirty = true;
+  return CLIC_OK;
 }
 
 CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
@@ -1468,7 +1558,7 @@ CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
   if (rc) return rc;
   if ((rc = fill_prior_columns(E))) return rc;
   for (int i = 0; i < reps; i++)
-    if ((rc = run_pass(E, E->d_state.as<double>(), true, E->d_cost2.as<double>(), nullptr))) return rc;
+    if ((rc = run_pass(E, E->d_state.as<double>(), true, 0, nullptr))) return rc;
   return CLIC_OK;
 }
 

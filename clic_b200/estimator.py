@@ -236,6 +236,18 @@ class TrajectoryEstimator:
         _check(self.lib, st)
         return Prior(self.lib, h)
 
+    # ---- multi-GPU: this rank's estimator holds a shard of the factors ----
+    def comm_init_torch(self, dist, rank, world):
+        """Create / attach the process NCCL communicator; the unique id travels over torch.distributed."""
+        import torch
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(self.lib, self.lib.clic_comm_unique_id(ident))
+        t = torch.tensor(list(ident), dtype=torch.uint8, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        _check(self.lib, self.lib.clic_comm_init(self.h, int(world), int(rank), ident))
+
     # ---- measurement hooks ----
     def linearize_async(self, reps=1):
         _check(self.lib, self.lib.clic_linearize_async(self.h, int(reps)))
