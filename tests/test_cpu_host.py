@@ -1,0 +1,141 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/clic_cuda.h and refuses to compute
+without a GPU; host-side sharding logic (world_size 2, gloo); oracle self-consistency (LM, marginalization)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from clic_b200 import _abi
+from clic_b200 import estimator as E
+from clic_b200 import synthetic as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_bound_and_exported():
+    """Every CLIC_API function the header declares has a ctypes prototype, and both libraries export it."""
+    hdr = open(os.path.join(ROOT, "include", "clic_cuda.h")).read()
+    declared = set(re.findall(r"CLIC_API\s+[\w\s\*]+?\b(clic_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_abi.PROTOTYPES), declared ^ set(_abi.PROTOTYPES)
+    cuda = E.cuda_library()          # loads on a CPU-only box (static cudart, NCCL resolved lazily)
+    assert cuda.clic_backend() == b"cuda-sm100a"
+    import oracle_lib
+    assert oracle_lib.load().clic_backend() == b"oracle-cpu"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a GPU")
+def test_product_fails_loudly_without_gpu():
+    sw = S.make_window(10, n_lidar=10, n_imu=4, seed=1)
+    with pytest.raises(_abi.ClicError) as e:
+        E.TrajectoryEstimator(sw.window, None, E.cuda_library())
+    assert e.value.status == 4  # CLIC_ERR_NO_DEVICE: there is no CPU fallback
+
+
+def test_package_never_references_the_oracle():
+    """The product package must not import / load anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "clic_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "libclic_oracle" not in txt and "oracle/" not in txt.replace(
+                    "oracle/clic_oracle.cpp solve()", ""), f
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from bench import shard
+    lib = oracle_lib.load()
+    sw = S.make_window(10, n_lidar=3000, n_imu=300, n_landmarks=30, obs_per_landmark=6, line_fraction=0.3, seed=55)
+    mine = shard(sw, rank, world)
+    opt = E.default_options(lib)
+    opt.lock_ab = opt.lock_wb = 0
+    est = E.TrajectoryEstimator(mine.window, opt, lib)
+    S.add_all_factors(est, mine, bias_factor=(rank == 0))
+    H, b, cost, _ = est.Evaluate()
+    D = H.shape[0]
+    t = torch.from_numpy(np.concatenate([H.ravel(), b, [cost]]))
+    dist.all_reduce(t)  # the path's single exchange step: H | b | cost
+    if rank == 0:
+        full = E.TrajectoryEstimator(sw.window, opt, lib)
+        S.add_all_factors(full, sw)
+        Hf, bf, cf, _ = full.Evaluate()
+        Hs, bs, cs = t[:D * D].numpy().reshape(D, D), t[D * D:D * D + D].numpy(), float(t[-1])
+        ok = (np.abs(Hs - Hf).max() <= 1e-12 * np.abs(Hf).max() and np.abs(bs - bf).max() <= 1e-12 * np.abs(bf).max()
+              and abs(cs - cf) <= 1e-12 * abs(cf))
+        open(os.path.join(out_dir, "ok"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_factor_sharding_world_size_2_gloo(tmp_path):
+    """N > 1 path on CPU: contiguous-in-time shards + one all-reduce reproduce the full-window normal equations."""
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok").read() == "1"
+
+
+def test_oracle_lm_and_summary(oracle):
+    sw = S.config(1, 0.25)
+    est = E.TrajectoryEstimator(sw.window, E.default_options(oracle), oracle)
+    S.add_all_factors(est, sw, bias_factor=False)
+    s = est.Solve(50)
+    assert s["termination"] == 0 and s["final_cost"] < 0.05 * s["initial_cost"]
+    assert s["iterations"] == s["num_successful_steps"] + s["num_unsuccessful_steps"] + (1 if s["termination_reason"] in (2, 3) else 0)
+    x = est.read_state()
+    assert np.abs(x["knot_p"][1:-1] - sw.gt_knot_p[1:-1]).max() < 0.03
+    assert np.allclose(np.linalg.norm(x["knot_q"], axis=1), 1.0, atol=1e-12)
+
+
+def test_oracle_prior_energy_and_schur_consistency(oracle):
+    """Marginalising everything but a few knots must leave a prior whose optimum is the full problem's optimum for
+    those knots (Schur complement property), here checked on the gradient: at the full optimum g_prior ~ 0."""
+    sw = S.make_window(12, n_lidar=1500, n_imu=0, seed=61, init_noise=(1e-3, 2e-3))
+    lib = oracle
+    # bring the state to the optimum of the LiDAR-only problem first
+    e0 = E.TrajectoryEstimator(sw.window, E.default_options(lib), lib)
+    S.add_all_factors(e0, sw, bias_factor=False)
+    e0.Solve(30)
+    x = e0.read_state()
+    sw.window.knot_q, sw.window.knot_p = x["knot_q"], x["knot_p"]
+    opt = E.default_options(lib)
+    opt.is_marg_state = 1
+    opt.ctrl_to_be_opt_later = 5
+    em = E.TrajectoryEstimator(sw.window, opt, lib)
+    L = sw.lidar
+    em.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                  L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], True)
+    pr = em.SaveMarginalizationInfo()
+    n, nb, m = pr.dims()
+    assert m == 5 * 6 and n == 3 * 6           # knots 0..4 dropped, 5..7 kept (factors with s < 5 touch knots <= 7)
+    A, g = pr.normal()
+    assert np.allclose(A, A.T, atol=1e-8 * np.abs(A).max())
+    assert np.linalg.eigvalsh(A).min() > -1e-8 * np.abs(A).max()
+    # the factors used (s < 5) are a subset, so g is not exactly 0; it must be small against |A| * typical step
+    assert np.abs(g).max() < 1e-2 * np.abs(A).max()
+    # prior-only estimator: cost at the linearisation point is 1/2 |r0|^2
+    ep = E.TrajectoryEstimator(sw.window, E.default_options(lib), lib)
+    ep.AddMarginalizationFactor(pr)
+    _, _, cost, _ = ep.Evaluate()
+    r0 = pr.read()["r0"]
+    assert abs(cost - 0.5 * r0 @ r0) <= 1e-9 * max(1.0, abs(cost))
+
+
+def test_oracle_drops_out_of_window_like_reference(oracle):
+    sw = S.make_window(10, n_lidar=50, n_imu=10, seed=2)
+    est = E.TrajectoryEstimator(sw.window, E.default_options(oracle), oracle)
+    t = np.array([-1e-9, 0.0, 0.35, 0.7 - 2e-9, 0.7, 0.75])  # window is [0, 0.7): MeasuredTimeToNs, trajectory_estimator.cpp:272-292
+    n = len(t)
+    L = sw.lidar
+    d = est.AddLoamMeasurementAnalytic(t, L["point"][:n], L["geo_type"][:n], L["geo_plane"][:n], L["geo_normal"][:n],
+                                       L["geo_point"][:n], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], 50.0)
+    s, u = est.indices(0)
+    assert d == 3 and list(s) == [-1, 0, 3, 6, -1, -1]
