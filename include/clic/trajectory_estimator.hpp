@@ -1,0 +1,412 @@
+// Header-only C++ shim: the reference's clic::TrajectoryEstimator surface
+// (src/estimator/trajectory_estimator.h:100-278) on top of the C ABI of include/clic_cuda.h.
+//
+// Method names, argument order and parameter-block semantics follow the reference: parameter blocks are
+// caller-owned raw double* (knots inside the Trajectory, biases, inverse depths) that are updated in place when
+// Solve() returns.  Per-measurement Add* calls only append to host staging arrays; the batched ABI calls (and the
+// host->device upload) happen inside Solve() / SaveMarginalizationInfo().  No Ceres, no Eigen: small POD vector
+// types replace Eigen::Vector3d / Sophus::SO3d (same memory layout: 3 doubles / 4 doubles x,y,z,w).
+// Link against libclic_cuda.so (product) — or, in tests only, the oracle library, which exports the same symbols.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../clic_cuda.h"
+
+namespace clic {
+
+using Vec3d = std::array<double, 3>;
+using Vec6d = std::array<double, 6>;
+struct SO3d {  // unit quaternion (x,y,z,w): Sophus::SO3d::data() layout (src/sophus_lib/so3.hpp:153-160)
+  std::array<double, 4> q{{0, 0, 0, 1}};
+  const double* data() const { return q.data(); }
+};
+
+enum SensorType { IMUSensor = 0, LiDARSensor, CameraSensor };  // src/spline/trajectory.h:29-33
+enum GeometryType { Line = 0, Plane };                         // src/lidar_odometry/lidar_feature.h:108
+
+struct PointCorrespondence {  // src/lidar_odometry/lidar_feature.h:110-123
+  double t_point = 0, t_map = 0;
+  Vec3d point{};
+  GeometryType geo_type = Plane;
+  std::array<double, 4> geo_plane{};
+  Vec3d geo_normal{};
+  Vec3d geo_point{};
+};
+struct IMUData {  // src/utils/parameter_struct.h:52-58
+  double timestamp = 0;
+  Vec3d gyro{}, accel{};
+};
+struct ExtrinsicParam {  // src/utils/parameter_struct.h:108-150 (the fields the hot path reads)
+  SO3d so3;
+  Vec3d p{};
+  double t_offset_ns = 0;
+};
+
+// Knot storage + extrinsics: the part of clic::Trajectory (src/spline/trajectory.h, se3_spline.h) the estimator needs.
+struct Trajectory {
+  typedef std::shared_ptr<Trajectory> Ptr;
+  int64_t t0_ns = 0, dt_ns = 0;
+  int knot_id0 = 0;  // global index of knots_*[0]
+  std::vector<std::array<double, 4>> knots_so3;
+  std::vector<Vec3d> knots_pos;
+  std::map<SensorType, ExtrinsicParam> EP_StoI;
+  Trajectory(double time_interval, double start_time = 0)
+      : t0_ns((int64_t)(start_time * 1e9)), dt_ns((int64_t)(time_interval * 1e9)) {
+    EP_StoI[IMUSensor] = ExtrinsicParam();
+    EP_StoI[LiDARSensor] = ExtrinsicParam();
+    EP_StoI[CameraSensor] = ExtrinsicParam();
+  }
+  size_t numKnots() const { return knots_so3.size(); }
+  double* getKnotSO3(size_t i) { return knots_so3[i].data(); }
+  double* getKnotPos(size_t i) { return knots_pos[i].data(); }
+};
+
+struct LockExtrinsic {  // trajectory_estimator_options.h:26-30
+  bool lock_P = true, lock_R = true, lock_t_offset = true;
+};
+struct TrajectoryEstimatorOptions {  // trajectory_estimator_options.h:32-72
+  TrajectoryEstimatorOptions() {
+    lock_EPs[IMUSensor] = LockExtrinsic();
+    lock_EPs[LiDARSensor] = LockExtrinsic();
+    lock_EPs[CameraSensor] = LockExtrinsic();
+  }
+  std::map<SensorType, LockExtrinsic> lock_EPs;
+  bool use_auto_diff = false;
+  int64_t t_offset_padding_ns = (int64_t)1e7;
+  bool lock_traj = false;
+  bool lock_ab = true, lock_wb = true, lock_g = true;
+  bool is_marg_state = false;
+  int ctrl_to_be_opt_now = 0, ctrl_to_be_opt_later = 0;
+  bool marg_bias_param = true, marg_gravity_param = true, marg_t_offset_param = true;
+  bool show_residual_summary = false;
+  // execution (not in the reference)
+  int device = 0;
+  void* stream = nullptr;
+};
+
+// POD stand-in for ceres::Solver::Summary (the fields the reference reads: trajectory_manager.cpp:753-756)
+struct Summary {
+  clic_summary raw{};
+  int num_successful_steps = 0, num_unsuccessful_steps = 0;
+  double initial_cost = 0, final_cost = 0;
+  std::string BriefReport() const {
+    static const char* term[] = {"CONVERGENCE", "NO_CONVERGENCE", "FAILURE"};
+    return "clic_b200 report: iterations: " + std::to_string(raw.iterations + 1) + ", initial cost: " +
+           std::to_string(initial_cost) + ", final cost: " + std::to_string(final_cost) +
+           ", termination: " + term[raw.termination < 0 || raw.termination > 2 ? 2 : raw.termination];
+  }
+};
+
+// MarginalizationInfo (marginalization_factor.h:100-142): owns a clic_prior; the kept parameter blocks are
+// returned to the caller as raw pointers exactly like getParameterBlocks() (marginalization_factor.cpp:301-317).
+struct MarginalizationInfo {
+  typedef std::shared_ptr<MarginalizationInfo> Ptr;
+  clic_prior* prior = nullptr;
+  int m = 0, n = 0;
+  ~MarginalizationInfo() {
+    if (prior) clic_prior_release(prior);
+  }
+};
+
+class TrajectoryEstimator {
+ public:
+  typedef std::shared_ptr<TrajectoryEstimator> Ptr;
+
+  TrajectoryEstimator(Trajectory::Ptr trajectory, TrajectoryEstimatorOptions& option, std::string descri = "")
+      : trajectory_(trajectory), options(option), descri_(descri), fixed_control_point_index_(-1) {}
+  ~TrajectoryEstimator() {
+    if (h_) clic_destroy(h_);
+  }
+
+  void SetFixedIndex(int idx) { fixed_control_point_index_ = idx; }  // trajectory_estimator.h:140
+
+  // trajectory_estimator.h:153-156
+  void AddIMUMeasurementAnalytic(const IMUData& imu_data, double* gyro_bias, double* accel_bias, double* gravity,
+                                 const Vec6d& info_vec, bool marg_this_factor = false) {
+    gravity_ = gravity;
+    const int slot = bias_slot(gyro_bias, accel_bias);
+    if (imu_.empty() || imu_.back().slot != slot || imu_.back().info != info_vec || imu_.back().marg != marg_this_factor) {
+      ImuBatch b;
+      b.slot = slot;
+      b.info = info_vec;
+      b.marg = marg_this_factor;
+      imu_.push_back(b);
+    }
+    ImuBatch& b = imu_.back();
+    b.t.push_back(imu_data.timestamp);
+    b.gyro.insert(b.gyro.end(), imu_data.gyro.begin(), imu_data.gyro.end());
+    b.accel.insert(b.accel.end(), imu_data.accel.begin(), imu_data.accel.end());
+  }
+
+  // trajectory_estimator.h:159-162
+  void AddBiasFactor(double* bias_gyr_i, double* bias_gyr_j, double* bias_acc_i, double* bias_acc_j, double dt,
+                     const Vec6d& info_vec, bool marg_this_factor = false, bool marg_all_bias = false) {
+    BiasFac f;
+    f.i = bias_slot(bias_gyr_i, bias_acc_i);
+    f.j = bias_slot(bias_gyr_j, bias_acc_j);
+    f.dt = dt;
+    f.info = info_vec;
+    f.marg = marg_this_factor;
+    f.marg_all = marg_all_bias;
+    bias_f_.push_back(f);
+  }
+
+  // trajectory_estimator.h:188-193
+  void AddLoamMeasurementAnalytic(const PointCorrespondence& pc, const SO3d& S_GtoM, const Vec3d& p_GinM,
+                                  const SO3d& S_LtoI, const Vec3d& p_LinI, double weight,
+                                  bool marg_this_factor = false) {
+    if (loam_.empty() || loam_.back().S_GtoM.q != S_GtoM.q || loam_.back().p_GinM != p_GinM ||
+        loam_.back().S_LtoI.q != S_LtoI.q || loam_.back().p_LinI != p_LinI || loam_.back().weight != weight ||
+        loam_.back().marg != marg_this_factor) {
+      LoamBatch b;
+      b.S_GtoM = S_GtoM; b.p_GinM = p_GinM; b.S_LtoI = S_LtoI; b.p_LinI = p_LinI; b.weight = weight;
+      b.marg = marg_this_factor;
+      loam_.push_back(b);
+    }
+    LoamBatch& b = loam_.back();
+    b.t.push_back(pc.t_point);
+    b.point.insert(b.point.end(), pc.point.begin(), pc.point.end());
+    b.type.push_back((int32_t)pc.geo_type);
+    b.plane.insert(b.plane.end(), pc.geo_plane.begin(), pc.geo_plane.end());
+    b.normal.insert(b.normal.end(), pc.geo_normal.begin(), pc.geo_normal.end());
+    b.gpoint.insert(b.gpoint.end(), pc.geo_point.begin(), pc.geo_point.end());
+  }
+
+  // trajectory_estimator.h:196-199
+  void AddImageFeatureAnalytic(const double ti, const Vec3d& pi, const double tj, const Vec3d& pj, double* inv_depth,
+                               bool fixed_depth = false, bool marg_this_fearure = false) {
+    if (image_.empty() || image_.back().fixed != fixed_depth || image_.back().marg != marg_this_fearure) {
+      ImageBatch b;
+      b.fixed = fixed_depth;
+      b.marg = marg_this_fearure;
+      image_.push_back(b);
+    }
+    ImageBatch& b = image_.back();
+    auto it = landmark_.find(inv_depth);
+    if (it == landmark_.end()) {
+      it = landmark_.emplace(inv_depth, (int)landmark_ptr_.size()).first;
+      landmark_ptr_.push_back(inv_depth);
+    }
+    b.ti.push_back(ti);
+    b.tj.push_back(tj);
+    b.pi.insert(b.pi.end(), pi.begin(), pi.end());
+    b.pj.insert(b.pj.end(), pj.begin(), pj.end());
+    b.lm.push_back(it->second);
+  }
+
+  // trajectory_estimator.h:207-209.  In marg mode `drop_blocks` mirrors the drop_set the reference computes at
+  // trajectory_manager.cpp:352-375 (indices into the prior's block list).
+  void AddMarginalizationFactor(MarginalizationInfo::Ptr last_marginalization_info,
+                                std::vector<double*>& /*last_marginalization_parameter_blocks*/,
+                                const std::vector<int>& drop_blocks = {}) {
+    priors_.push_back({last_marginalization_info, drop_blocks});
+  }
+
+  // trajectory_estimator.h:225-226
+  Summary Solve(int max_iterations = 50, bool /*progress*/ = false, int /*num_threads*/ = -1) {
+    build();
+    clic_summary s{};
+    check(clic_solve(h_, max_iterations, &s));
+    write_back();
+    Summary out;
+    out.raw = s;
+    out.num_successful_steps = s.num_successful_steps;
+    out.num_unsuccessful_steps = s.num_unsuccessful_steps;
+    out.initial_cost = s.initial_cost;
+    out.final_cost = s.final_cost;
+    return out;
+  }
+
+  // trajectory_estimator.h:234-235
+  void SaveMarginalizationInfo(MarginalizationInfo::Ptr& marg_info_out, std::vector<double*>& marg_param_blocks_out) {
+    build();
+    clic_prior* p = nullptr;
+    int rc = clic_marginalize(h_, &p);
+    marg_param_blocks_out.clear();
+    if (rc == CLIC_ERR_NOTHING_TO_KEEP) {  // trajectory_estimator.cpp:241-248
+      marg_info_out = nullptr;
+      return;
+    }
+    check(rc);
+    marg_info_out = std::make_shared<MarginalizationInfo>();
+    marg_info_out->prior = p;
+    int32_t n = 0, nb = 0, m = 0;
+    check(clic_prior_dims(p, &n, &nb, &m));
+    marg_info_out->n = n;
+    marg_info_out->m = m;
+    std::vector<int32_t> kind(nb), id(nb);
+    check(clic_prior_read(p, nullptr, nullptr, kind.data(), id.data(), nullptr, nullptr));
+    for (int i = 0; i < nb; i++) marg_param_blocks_out.push_back(block_address(kind[i], id[i]));
+  }
+
+  // one fused pass, for tests / parity probes (not in the reference API)
+  void Evaluate(std::vector<double>* H, std::vector<double>* b, double* cost) {
+    build();
+    clic_layout L;
+    check(clic_get_layout(h_, &L));
+    if (H) H->assign((size_t)L.D * L.D, 0.0);
+    if (b) b->assign(L.D, 0.0);
+    check(clic_evaluate(h_, H ? H->data() : nullptr, b ? b->data() : nullptr, cost, nullptr));
+  }
+
+  TrajectoryEstimatorOptions options;
+
+ private:
+  struct LoamBatch {
+    std::vector<double> t, point, plane, normal, gpoint;
+    std::vector<int32_t> type;
+    SO3d S_GtoM, S_LtoI;
+    Vec3d p_GinM{}, p_LinI{};
+    double weight = 1;
+    bool marg = false;
+  };
+  struct ImuBatch {
+    std::vector<double> t, gyro, accel;
+    int slot = 0;
+    Vec6d info{};
+    bool marg = false;
+  };
+  struct ImageBatch {
+    std::vector<double> ti, tj, pi, pj;
+    std::vector<int32_t> lm;
+    bool fixed = true, marg = false;
+  };
+  struct BiasFac {
+    int i, j;
+    double dt;
+    Vec6d info;
+    bool marg, marg_all;
+  };
+  struct PriorRef {
+    MarginalizationInfo::Ptr info;
+    std::vector<int> drop;
+  };
+
+  static void check(int rc) {
+    if (rc != CLIC_OK) throw std::runtime_error(std::string("clic: ") + clic_last_error());
+  }
+  int bias_slot(double* gyro, double* accel) {
+    for (size_t i = 0; i < bias_ptr_.size(); i++)
+      if (bias_ptr_[i].first == gyro) return (int)i;
+    bias_ptr_.push_back({gyro, accel});
+    return (int)bias_ptr_.size() - 1;
+  }
+  double* block_address(int kind, int id) {
+    switch (kind) {
+      case CLIC_BLOCK_KNOT_ROT: return trajectory_->getKnotSO3(id - trajectory_->knot_id0);
+      case CLIC_BLOCK_KNOT_POS: return trajectory_->getKnotPos(id - trajectory_->knot_id0);
+      case CLIC_BLOCK_BIAS_GYRO: return bias_ptr_.at(id).first;
+      case CLIC_BLOCK_BIAS_ACCEL: return bias_ptr_.at(id).second;
+      case CLIC_BLOCK_GRAVITY: return gravity_;
+      case CLIC_BLOCK_T_OFFSET: return &trajectory_->EP_StoI[(SensorType)id].t_offset_ns;
+      default: return landmark_ptr_.at(id);
+    }
+  }
+
+  // create the handle and push every staged batch through the batched ABI
+  void build() {
+    if (h_) return;
+    const size_t K = trajectory_->numKnots();
+    std::vector<double> kq(4 * K), kp(3 * K), bias(6 * bias_ptr_.size()), invd(landmark_ptr_.size());
+    for (size_t k = 0; k < K; k++) {
+      std::memcpy(&kq[4 * k], trajectory_->knots_so3[k].data(), 4 * sizeof(double));
+      std::memcpy(&kp[3 * k], trajectory_->knots_pos[k].data(), 3 * sizeof(double));
+    }
+    for (size_t i = 0; i < bias_ptr_.size(); i++) {
+      std::memcpy(&bias[6 * i], bias_ptr_[i].first, 3 * sizeof(double));
+      std::memcpy(&bias[6 * i + 3], bias_ptr_[i].second, 3 * sizeof(double));
+    }
+    for (size_t i = 0; i < landmark_ptr_.size(); i++) invd[i] = *landmark_ptr_[i];
+    clic_window_desc w{};
+    w.t0_ns = trajectory_->t0_ns;
+    w.dt_ns = trajectory_->dt_ns;
+    w.n_knots = (int32_t)K;
+    w.knot_id0 = trajectory_->knot_id0;
+    w.knot_q = kq.data();
+    w.knot_p = kp.data();
+    const ExtrinsicParam& epl = trajectory_->EP_StoI[LiDARSensor];
+    const ExtrinsicParam& epc = trajectory_->EP_StoI[CameraSensor];
+    std::memcpy(w.S_LtoI, epl.so3.data(), sizeof(w.S_LtoI));
+    std::memcpy(w.p_LinI, epl.p.data(), sizeof(w.p_LinI));
+    std::memcpy(w.S_CtoI, epc.so3.data(), sizeof(w.S_CtoI));
+    std::memcpy(w.p_CinI, epc.p.data(), sizeof(w.p_CinI));
+    for (int s = 0; s < 3; s++) w.t_offset_ns[s] = trajectory_->EP_StoI[(SensorType)s].t_offset_ns;
+    if (gravity_) std::memcpy(w.gravity, gravity_, sizeof(w.gravity));
+    w.n_bias = (int32_t)bias_ptr_.size();
+    w.bias = bias.data();
+    w.n_landmarks = (int32_t)invd.size();
+    w.inv_depth = invd.data();
+    clic_options o;
+    clic_default_options(&o);
+    o.lock_traj = options.lock_traj;
+    o.lock_ab = options.lock_ab;
+    o.lock_wb = options.lock_wb;
+    o.lock_g = options.lock_g;
+    for (int s = 0; s < 3; s++) o.lock_t_offset[s] = options.lock_EPs.at((SensorType)s).lock_t_offset;
+    o.is_marg_state = options.is_marg_state;
+    o.t_offset_padding_ns = options.t_offset_padding_ns;
+    o.ctrl_to_be_opt_now = options.ctrl_to_be_opt_now;
+    o.ctrl_to_be_opt_later = options.ctrl_to_be_opt_later;
+    o.marg_bias_param = options.marg_bias_param;
+    o.marg_gravity_param = options.marg_gravity_param;
+    o.marg_t_offset_param = options.marg_t_offset_param;
+    o.device = options.device;
+    o.stream = options.stream;
+    check(clic_create(&w, &o, &h_));
+    check(clic_set_fixed_index(h_, fixed_control_point_index_));
+    // the reference's call order: prior, LiDAR, image, IMU, bias (trajectory_manager.cpp:659-750)
+    for (auto& p : priors_)
+      check(clic_add_prior(h_, p.info->prior, (int32_t)p.drop.size(), p.drop.empty() ? nullptr : p.drop.data()));
+    for (auto& b : loam_)
+      check(clic_add_loam(h_, (int64_t)b.t.size(), b.t.data(), b.point.data(), b.type.data(), b.plane.data(),
+                          b.normal.data(), b.gpoint.data(), b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(),
+                          b.p_LinI.data(), b.weight, b.marg, nullptr));
+    for (auto& b : image_)
+      check(clic_add_image(h_, (int64_t)b.ti.size(), b.ti.data(), b.pi.data(), b.tj.data(), b.pj.data(), b.lm.data(),
+                           b.fixed, b.marg, nullptr));
+    for (auto& b : imu_)
+      check(clic_add_imu(h_, (int64_t)b.t.size(), b.t.data(), b.gyro.data(), b.accel.data(), b.slot, b.info.data(),
+                         b.marg, nullptr));
+    for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
+  }
+
+  // Ceres updates the caller's parameter blocks in place; so do we
+  void write_back() {
+    const size_t K = trajectory_->numKnots();
+    std::vector<double> kq(4 * K), kp(3 * K), bias(6 * bias_ptr_.size() + 1), invd(landmark_ptr_.size() + 1);
+    double toff[3];
+    check(clic_read_state(h_, kq.data(), kp.data(), bias.data(), toff, invd.data()));
+    for (size_t k = 0; k < K; k++) {
+      std::memcpy(trajectory_->knots_so3[k].data(), &kq[4 * k], 4 * sizeof(double));
+      std::memcpy(trajectory_->knots_pos[k].data(), &kp[3 * k], 3 * sizeof(double));
+    }
+    for (size_t i = 0; i < bias_ptr_.size(); i++) {
+      std::memcpy(bias_ptr_[i].first, &bias[6 * i], 3 * sizeof(double));
+      std::memcpy(bias_ptr_[i].second, &bias[6 * i + 3], 3 * sizeof(double));
+    }
+    for (int s = 0; s < 3; s++) trajectory_->EP_StoI[(SensorType)s].t_offset_ns = toff[s];
+  }
+
+  Trajectory::Ptr trajectory_;
+  std::string descri_;
+  int fixed_control_point_index_;
+  clic_estimator* h_ = nullptr;
+  double* gravity_ = nullptr;
+  std::vector<LoamBatch> loam_;
+  std::vector<ImuBatch> imu_;
+  std::vector<ImageBatch> image_;
+  std::vector<BiasFac> bias_f_;
+  std::vector<PriorRef> priors_;
+  std::vector<std::pair<double*, double*>> bias_ptr_;
+  std::map<double*, int> landmark_;
+  std::vector<double*> landmark_ptr_;
+};
+
+}  // namespace clic
