@@ -184,7 +184,7 @@ class SyntheticWindow:
 def make_window(n_knots=10, n_lidar=2000, n_imu=200, n_landmarks=0, obs_per_landmark=10, line_fraction=0.0,
                 seed=20230216, dt_ns=100_000_000, random_knots=False, init_noise=(0.02, 0.05), n_bias=2,
                 t_offset_ns=(0.0, 0.0, 0.0), bias_true=(0.01, -0.02, 0.015, 0.05, -0.03, 0.04), name="",
-                time_margin_ns=0):
+                time_margin_ns=0, meas_seed=None):
     """One synthetic LiDAR(-inertial(-camera)) window.  `time_margin_ns` keeps measurements that far inside the
     valid range (needed when a time offset is unlocked: the padding test of MeasuredTimeToNs)."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -214,6 +214,8 @@ def make_window(n_knots=10, n_lidar=2000, n_imu=200, n_landmarks=0, obs_per_land
     bias0 = np.tile(bias_true, (n_bias, 1)) + rng.normal(0, 1e-3, size=(n_bias, 6)) if n_bias else np.zeros((0, 6))
 
     sw = SyntheticWindow(window=None, gt_knot_q=gt_q, gt_knot_p=gt_p, name=name)
+    if meas_seed is not None:  # same window state, different measurements (one shard per rank under weak scaling)
+        rng = np.random.Generator(np.random.PCG64(meas_seed))
 
     if n_lidar:
         t_ns = np.sort(rng.integers(lo, hi + 1, size=n_lidar, dtype=np.int64))
