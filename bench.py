@@ -336,12 +336,15 @@ def main():
             e.close()
         barrier()
         t0 = time.perf_counter()
+        e2e_each = []
         for _ in range(e2e_steps):
+            t1 = time.perf_counter()
             e = new_estimator(src)
             if world > 1:
                 e.comm_init_torch(dist, rank, world)
             H, b, cost, _ = e.Evaluate()
             e.close()
+            e2e_each.append((time.perf_counter() - t1) * 1e3)
         barrier()
         e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -382,7 +385,7 @@ def main():
                    "strong_scaling_c5": strong},
         "gn_iterations": gn,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_each": [round(x, 2) for x in e2e_each]},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -956,10 +956,16 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   std::unique_ptr<clic_estimator> E(new clic_estimator);
   E->device = opt->device;
   CU(cudaSetDevice(E->device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, E->device));
-  if (prop.major < 10) return fail(CLIC_ERR_NO_DEVICE, "device is not sm_100 class (kernels are built for sm_100a only)");
-  E->n_sm = prop.multiProcessorCount;
+  // device queries are slow (~ms): once per process and device
+  static int cached_dev = -1, cached_major = 0, cached_sms = 0;
+  if (cached_dev != E->device) {
+    int major = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, E->device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device));
+    cached_dev = E->device; cached_major = major; cached_sms = sms;
+  }
+  if (cached_major < 10) return fail(CLIC_ERR_NO_DEVICE, "device is not sm_100 class (kernels are built for sm_100a only)");
+  E->n_sm = cached_sms;
   E->t0_ns = w->t0_ns;
   E->dt_ns = w->dt_ns;
   E->K = w->n_knots;
@@ -987,11 +993,13 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     E->own_stream = true;
   }
-  {
+  static int pool_dev = -1;
+  if (pool_dev != E->device) {
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, E->device));
     uint64_t thr = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    pool_dev = E->device;
   }
   AllocScope alloc_scope(E->stream);
   CU(E->d_state.ensure(E->sl.size() * sizeof(double)));
@@ -1003,11 +1011,16 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   if (rc) return rc;
   // opt in to > 48 KB dynamic shared memory once
   size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
+  static int attr_K = -1, attr_dev = -1;  // the opt-in is per function and device; only grows with K
+  if (attr_dev != E->device || E->K > attr_K) {
   if ((rc = set_smem(loam_kernel<true>, smem4)) || (rc = set_smem(loam_kernel<false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, true>, smem5)) || (rc = set_smem(image_kernel<true>, factor_smem_bytes(E->K, 7))) ||
       (rc = set_smem(image_kernel<false>, factor_smem_bytes(E->K, 7))))
     return rc;
+  attr_K = E->K;
+  attr_dev = E->device;
+  }
   CU(cudaStreamSynchronize(E->stream));
   *out = E.release();
   return CLIC_OK;
