@@ -17,7 +17,16 @@
 
 using namespace clic;
 
+#ifndef CLIC_LOAM_WARPS
+#define CLIC_LOAM_WARPS 8
+#endif
+#ifndef CLIC_LOAM_MINB
+#define CLIC_LOAM_MINB 1
+#endif
+
 namespace {
+
+constexpr int kLoamWarps = CLIC_LOAM_WARPS, kLoamMinB = CLIC_LOAM_MINB;
 
 thread_local std::string g_err;
 int fail(int code, const std::string& m) {
@@ -95,7 +104,7 @@ struct AllocScope {  // every ABI entry point that may allocate names the estima
 // Launch geometry + record buffers of one factor stream.
 struct StreamExec {
   int64_t n = 0;
-  int grid = 0, slabs_per_warp = 0, n_warps = 0;
+  int grid = 0, slabs_per_warp = 0, n_warps = 0, warps_per_cta = kWarpsPerCta;
   int NT = 4, rd = 640, n_keys = 0, P = 8;
   DevBuf payload, key, cost, part, overflow;
   int* overflow_flag = nullptr;
@@ -249,10 +258,13 @@ clic_layout compute_layout(const clic_estimator* E) {
   return L;
 }
 
-int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm, bool pair_keys = false) {
+int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm, bool pair_keys = false,
+                int extra = 0, int warps_per_cta = kWarpsPerCta) {
+  const int kWarpsPerCta = warps_per_cta;  // shadows the global default for this stream
+  ex.warps_per_cta = warps_per_cta;
   ex.n = n;
   ex.NT = NT;
-  ex.rd = n_tiles(NT) * 64;
+  ex.rd = rec_doubles(NT, extra);
   ex.n_keys = pair_keys ? (E->K - 3) * (E->K - 3) : E->K - 3;
   const int64_t slabs = (n + 31) / 32;
   const int max_ctas = E->n_sm * ctas_per_sm;
@@ -277,7 +289,16 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
 }
 
 size_t factor_smem_bytes(int K, int NT) {
-  return (window_smem_doubles(K) + (size_t)kWarpsPerCta * 8 * NT * kJtStride) * sizeof(double);
+  // NT column tiles of the transposed Jacobian tile per warp; the end-of-kernel merge scratch aliases it
+  size_t jt = (size_t)kWarpsPerCta * 8 * NT * kJtStride;
+  jt = std::max<size_t>(jt, (size_t)rec_doubles(NT, 1));
+  return (window_smem_doubles(K) + jt) * sizeof(double);
+}
+
+size_t loam_smem_bytes(int K) {
+  size_t jt = (size_t)kLoamWarps * 24 * kJtStride;
+  jt = std::max<size_t>(jt, (size_t)rec_doubles(3, 1));
+  return (window_smem_doubles(K) + jt) * sizeof(double);
 }
 
 // Column maps + stream descriptors for assemble_kernel.
@@ -308,7 +329,8 @@ int ensure_layout(clic_estimator* E) {
     d.part = b->ex.part.as<double>();
     d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
-    d.r_col = 24;
+    d.r_col = -1;
+    d.b_off = 384;
     d.n_extra = 0;
     d.extra_base = 24;
     d.kind = 0;
@@ -322,6 +344,7 @@ int ensure_layout(clic_estimator* E) {
     d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 31;
+    d.b_off = -1;
     d.n_extra = 7;
     d.extra_base = 24;
     d.kind = 0;
@@ -340,6 +363,7 @@ int ensure_layout(clic_estimator* E) {
     d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 49;
+    d.b_off = -1;
     d.n_extra = 1;
     d.extra_base = 48;
     d.kind = 1;
@@ -364,6 +388,7 @@ int launch_reduce(clic_estimator* E, const StreamExec& ex, const int* ctl) {
   const int n_slots = ex.n_warps * kSlotsPerWarp;
   const size_t smem = 0;
   switch (ex.NT) {
+    case 3: reduce_records_kernel<416><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
     case 4: reduce_records_kernel<640><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
     case 5: reduce_records_kernel<960><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
     case 7: reduce_records_kernel<1792><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
@@ -447,11 +472,11 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
-    const size_t smem = factor_smem_bytes(E->K, 4);
+    const size_t smem = loam_smem_bytes(E->K);
     if (jac) {
       CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
       E->prof_begin(0);
-      loam_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->prof_begin(3);
       if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
@@ -459,7 +484,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->launches += 2;
     } else {
       E->prof_begin(0);
-      loam_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      loam_kernel<false, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->launches += 1;
     }
@@ -727,10 +752,10 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     if (!b->marg) continue;
     StreamExec& ex = b->ex;
     CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
-    loam_kernel<true><<<ex.grid, kThreads, factor_smem_bytes(K, 4), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
     if (launch_reduce(E, ex, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
     E->launches += 2;
-    if ((rc = mark(ex, 24))) return rc;
+    if ((rc = mark(ex, -1))) return rc;
   }
   for (auto& b : E->imu) {
     if (!b->marg) continue;
@@ -816,7 +841,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     StreamDesc d{};
     d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
-    d.r_col = 24; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    d.r_col = -1; d.b_off = 384; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     descs.push_back(d);
   }
   for (auto& b : E->imu) {
@@ -824,7 +849,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     StreamDesc d{};
     d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
-    d.r_col = 34; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    d.r_col = 34; d.b_off = -1; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     const int cg = find(CLIC_BLOCK_BIAS_GYRO, b->st.bias_slot), ca = find(CLIC_BLOCK_BIAS_ACCEL, b->st.bias_slot),
               cgr = find(CLIC_BLOCK_GRAVITY, 0), ct = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU);
     for (int c = 0; c < 3; c++) {
@@ -1013,7 +1038,8 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
   static int attr_K = -1, attr_dev = -1;  // the opt-in is per function and device; only grows with K
   if (attr_dev != E->device || E->K > attr_K) {
-  if ((rc = set_smem(loam_kernel<true>, smem4)) || (rc = set_smem(loam_kernel<false>, smem4)) ||
+  if ((rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, true>, smem5)) || (rc = set_smem(image_kernel<true>, factor_smem_bytes(E->K, 7))) ||
       (rc = set_smem(image_kernel<false>, factor_smem_bytes(E->K, 7))))
@@ -1106,8 +1132,10 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   B->st.sh.S_LtoI = ldq(S_LtoI);
   B->st.sh.p_LinI = ldv(p_LinI);
   B->st.sh.weight = weight;
+  B->st.sh.gm_identity = S_GtoM[0] == 0.0 && S_GtoM[1] == 0.0 && S_GtoM[2] == 0.0 && S_GtoM[3] == 1.0 &&
+                         p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
-  if ((rc = plan_stream(E, B->ex, n, 4, 2))) return rc;
+  if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;

@@ -254,8 +254,20 @@ CLIC_HD void blend_plain_d3(double s, double c[4]) {
 CLIC_HD bool index_ns(int64_t t_ns, int64_t t0_ns, int64_t dt_ns, int n_knots, int* s, double* u) {
   if (t_ns < t0_ns || t_ns >= t0_ns + (int64_t)(n_knots - 3) * dt_ns) return false;
   int64_t st = t_ns - t0_ns;
+#if defined(__CUDA_ARCH__)
+  // 64-bit integer division is emulated (~100 instructions): estimate the quotient with one FP64 multiply by the
+  // (loop-invariant) reciprocal and repair it with an integer multiply; exact for st, dt < 2^52, so still bit-exact.
+  const double inv_dt = 1.0 / (double)dt_ns;
+  int64_t q = (int64_t)((double)st * inv_dt);
+  int64_t r = st - q * dt_ns;
+  if (r < 0) { q -= 1; r += dt_ns; }
+  else if (r >= dt_ns) { q += 1; r -= dt_ns; }
+  *s = (int)q;
+  *u = double(r) / double(dt_ns);
+#else
   *s = (int)(st / dt_ns);
   *u = double(st % dt_ns) / double(dt_ns);
+#endif
   return true;
 }
 

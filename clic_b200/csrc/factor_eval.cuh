@@ -88,12 +88,14 @@ CLIC_HD M3 lamJr(const PairData& P, double lam, double ca, double cb, double sig
 
 struct LoamShared {  // arguments of AddLoamMeasurementAnalytic shared by a batch (trajectory_estimator.cpp:712-716)
   Q4 S_GtoM; V3 p_GinM; Q4 S_LtoI; V3 p_LinI; double weight;
+  bool gm_identity;  // S_GtoM = I, p_GinM = 0: every production call (trajectory_manager.cpp:676-680) -> skip two rotations
 };
 
 // LoamFeatureFactor::Evaluate.  geo = plane (n.x n.y n.z d) or line (point xyz, direction xyz).
 // J[24] gets the local row [knot: dtheta(3) dp(3)] x 4; *r the weighted residual.  No loss (":743").
+// `jscale` multiplies the emitted Jacobian row (sh.weight for a contributing factor, 0 to mask a lane out).
 CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plane, const double geo[6],
-                       const LoamShared& sh, bool want_jac, double* r_out, double J[24]) {
+                       const LoamShared& sh, bool want_jac, double* r_out, double J[24], double jscale) {
   double lam[4], c[4];
   blend_cum(u, lam);
   blend_plain(u, c);
@@ -111,7 +113,8 @@ CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plan
   V3 pos = mk(0, 0, 0);
 #pragma unroll
   for (int i = 0; i < 4; i++) pos = fma3(c[i], ldv(W.kp + 3 * (s + i)), pos);
-  V3 p_M = qrot(sh.S_GtoM, qrot(R, p_I) + pos) + sh.p_GinM;
+  V3 p_G = qrot(R, p_I) + pos;
+  V3 p_M = sh.gm_identity ? p_G : qrot(sh.S_GtoM, p_G) + sh.p_GinM;
   V3 Jpi;
   double r;
   if (is_plane) {
@@ -125,7 +128,7 @@ CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plan
   }
   *r_out = r * sh.weight;
   if (!want_jac) return;
-  V3 g = qrot_inv(sh.S_GtoM, Jpi);  // (J_pi^T S_GtoM)^T
+  V3 g = sh.gm_identity ? Jpi : qrot_inv(sh.S_GtoM, Jpi);  // (J_pi^T S_GtoM)^T
   V3 m = qrot_inv(R, g);            // (J_pi^T S_GtoM R)^T
   V3 v = cross(p_I, m);             // J_pi^T (-S_GtoM R hat(p_I)) = p_I x m
   // rows of d_val_d_knot chain, vector-first (so3_spline_view.h:170-180)
@@ -137,7 +140,7 @@ CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plan
   V3 j1 = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
   V3 j2 = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
   V3 j3 = vmat(t2, W.pair[s + 2].Jrinv);
-  const double w = sh.weight;
+  const double w = jscale;
   J[0] = w * j0.x; J[1] = w * j0.y; J[2] = w * j0.z;
   J[6] = w * j1.x; J[7] = w * j1.y; J[8] = w * j1.z;
   J[12] = w * j2.x; J[13] = w * j2.y; J[14] = w * j2.z;

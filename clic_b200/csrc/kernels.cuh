@@ -72,12 +72,17 @@ struct RecordBuf {
   int* overflow_flag;
 };
 
-template <int NT>
+// Record size in doubles: the upper-triangular 8x8 tiles + (EXTRA) one double per lane (LiDAR: b = J~^T r~, 24 used)
+__host__ __device__ constexpr int rec_doubles(int NT, int EXTRA) { return n_tiles(NT) * 64 + 32 * EXTRA; }
+
+template <int NT, int EXTRA = 0>
 struct WarpAcc {
   double c[n_tiles(NT)][2];
+  double extra;
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int t = 0; t < n_tiles(NT); t++) c[t][0] = c[t][1] = 0.0;
+    extra = 0.0;
   }
   // Jt: this warp's transposed tile, Jt[col * kJtStride + row], rows 0..31 = the slab's Jacobian rows
   __device__ __forceinline__ void accumulate(const double* Jt, int lane) {
@@ -103,6 +108,7 @@ struct WarpAcc {
       double2 v = make_double2(c[t][0], c[t][1]);
       *reinterpret_cast<double2*>(rec + t * 64 + 2 * lane) = v;  // row-major 8x8: (lane/4)*8 + (lane%4)*2
     }
+    if (EXTRA) rec[n_tiles(NT) * 64 + lane] = extra;
   }
   __device__ __forceinline__ void atomic_add(double* dst, int lane) const {
 #pragma unroll
@@ -110,6 +116,7 @@ struct WarpAcc {
       atomicAdd(dst + t * 64 + 2 * lane, c[t][0]);
       atomicAdd(dst + t * 64 + 2 * lane + 1, c[t][1]);
     }
+    if (EXTRA) atomicAdd(dst + n_tiles(NT) * 64 + lane, extra);
   }
 };
 
@@ -140,17 +147,17 @@ __host__ __device__ inline size_t window_smem_doubles(int K) {
   return (((size_t)7 * K + (size_t)kPairDoubles * (K - 1)) + 1) & ~(size_t)1;
 }
 
-template <int NT>
-__device__ __forceinline__ void flush_record(const WarpAcc<NT>& acc, int key, int& slot, int warp_global,
+template <int NT, int EXTRA = 0>
+__device__ __forceinline__ void flush_record(const WarpAcc<NT, EXTRA>& acc, int key, int& slot, int warp_global,
                                              const RecordBuf& rb, int lane) {
   if (key < 0) return;
   if (slot < kSlotsPerWarp) {
     int r = warp_global * kSlotsPerWarp + slot;
-    acc.store(rb.payload + (size_t)r * n_tiles(NT) * 64, lane);
+    acc.store(rb.payload + (size_t)r * rec_doubles(NT, EXTRA), lane);
     if (lane == 0) rb.key[r] = key;
     slot++;
   } else {  // unsorted input: correct but unordered
-    acc.atomic_add(rb.overflow + (size_t)key * n_tiles(NT) * 64, lane);
+    acc.atomic_add(rb.overflow + (size_t)key * rec_doubles(NT, EXTRA), lane);
     if (lane == 0) *rb.overflow_flag = 1;
   }
 }
@@ -159,20 +166,21 @@ __device__ __forceinline__ void flush_record(const WarpAcc<NT>& acc, int key, in
 // of them, for time-sorted input) are summed through shared memory in warp order and written as ONE record; the
 // others are flushed individually.  8x fewer records for the reduction stage, still no atomics, still fixed order.
 // `scratch` (>= n_tiles(NT)*64 doubles) may alias the Jt tiles: they are dead by now.
-template <int NT>
-__device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT>& acc, int acc_key, int& slot, int warp, int lane,
+template <int NT, int EXTRA = 0, int WARPS = kWarpsPerCta>
+__device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT, EXTRA>& acc, int acc_key, int& slot, int warp, int lane,
                                                     int warp_global, const RecordBuf& rb, double* scratch) {
+  constexpr int RD = rec_doubles(NT, EXTRA);
   __shared__ int s_key, s_first;
   __syncthreads();
   if (threadIdx.x == 0) { s_key = -1; s_first = -1; }
   __syncthreads();
-  for (int w = 0; w < kWarpsPerCta; w++) {
+  for (int w = 0; w < WARPS; w++) {
     if (warp == w && lane == 0 && s_key < 0 && acc_key >= 0) { s_key = acc_key; s_first = w; }
     __syncthreads();
   }
   const int kc = s_key, w_first = s_first;
   const bool merged = acc_key >= 0 && acc_key == kc;
-  for (int w = 0; w < kWarpsPerCta; w++) {
+  for (int w = 0; w < WARPS; w++) {
     if (warp == w && merged) {
 #pragma unroll
       for (int t = 0; t < n_tiles(NT); t++) {
@@ -181,103 +189,167 @@ __device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT>& acc, int 
         if (w != w_first) { double2 o = *dst; v.x += o.x; v.y += o.y; }
         *dst = v;
       }
+      if (EXTRA) {
+        double* dst = scratch + n_tiles(NT) * 64 + lane;
+        *dst = (w != w_first) ? *dst + acc.extra : acc.extra;
+      }
     }
     __syncthreads();
   }
   if (!merged) {
-    flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+    flush_record<NT, EXTRA>(acc, acc_key, slot, warp_global, rb, lane);
   } else if (warp == w_first) {
     if (slot < kSlotsPerWarp) {
       const int r = warp_global * kSlotsPerWarp + slot;
-      double* dst = rb.payload + (size_t)r * n_tiles(NT) * 64;
-      for (int i = lane; i < n_tiles(NT) * 64; i += 32) dst[i] = scratch[i];
+      double* dst = rb.payload + (size_t)r * RD;
+      for (int i = lane; i < RD; i += 32) dst[i] = scratch[i];
       if (lane == 0) rb.key[r] = kc;
       slot++;
     } else {
-      double* dst = rb.overflow + (size_t)kc * n_tiles(NT) * 64;
-      for (int i = lane; i < n_tiles(NT) * 64; i += 32) atomicAdd(dst + i, scratch[i]);
+      double* dst = rb.overflow + (size_t)kc * RD;
+      for (int i = lane; i < RD; i += 32) atomicAdd(dst + i, scratch[i]);
       if (lane == 0) *rb.overflow_flag = 1;
     }
   }
 }
 
-// K1: LoamFeatureFactor over a stream (lidar_feature_factor.h:65-159), fused with J~^T J~ / J~^T r~ accumulation.
-// Local columns: [knot s..s+3: dtheta(3) dp(3)] = 0..23, r = 24, zero pad to 32.
-template <bool JAC>
-__global__ void __launch_bounds__(kThreads, 2)
+// Lane L returns the sum over the warp of v[L] (v[24..31] are implicit zeros): the classic transpose-reduce, 31
+// add + shuffle steps instead of 24 x 5.
+__device__ __forceinline__ double warp_transpose_reduce24(const double (&v)[24], int lane) {
+  double a[16];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const double lo_v = v[i], hi_v = (i + 16 < 24) ? v[i + 16] : 0.0;
+      const double send = hi ? lo_v : hi_v, keep = hi ? hi_v : lo_v;
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  double b8[8];
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const double send = hi ? a[i] : a[i + 8], keep = hi ? a[i + 8] : a[i];
+      b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  double c4[4];
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double send = hi ? b8[i] : b8[i + 4], keep = hi ? b8[i + 4] : b8[i];
+      c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  double d2[2];
+  {
+    const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const double send = hi ? c4[i] : c4[i + 2], keep = hi ? c4[i + 2] : c4[i];
+      d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool hi = lane & 1;
+  const double send = hi ? d2[0] : d2[1], keep = hi ? d2[1] : d2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// K1: LoamFeatureFactor over a stream (lidar_feature_factor.h:65-159), fused with the normal-equation accumulation.
+// Local columns: [knot s..s+3: dtheta(3) dp(3)] = 0..23.  J~^T J~ goes through 6 DMMA tiles (NT = 3); J~^T r~ is a
+// warp transpose-reduce (FP64 DMMA and DFMA share one pipe on B200, so the 4th tile column would cost 3x more pipe
+// time than the 24 multiplies + 31 adds); sum r~^2 is the cost.  Evaluation is divergence-free: every lane evaluates,
+// masked lanes with a zero scale.  The loads of the next slab are issued before the DMMA phase of the current one.
+template <bool JAC, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
   if (pp.ctl && pp.ctl[0]) return;
   extern __shared__ double smem[];
   double* rest;
   WindowView W = stage_window(smem, pp, &rest);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
-  double* Jt = rest + (size_t)warp * 32 * kJtStride;
-  if (JAC) {
-    for (int i = lane; i < 32 * kJtStride; i += 32) Jt[i] = 0.0;  // columns 25..31 stay zero
-    __syncwarp();
-  }
-  WarpAcc<4> acc;
+  const int warp_global = blockIdx.x * WARPS + warp;
+  double* Jt = rest + (size_t)warp * 24 * kJtStride;
+  WarpAcc<3, 1> acc;
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
   const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  // software pipeline registers (next slab)
+  int64_t n_t = kDropped;
+  double n_p0 = 0, n_p1 = 0, n_p2 = 0, n_g0 = 0, n_g1 = 0, n_g2 = 0, n_g3 = 0, n_g4 = 0, n_g5 = 0;
+  unsigned char n_ty = 1;
+  auto prefetch = [&](int64_t idx) {
+    n_t = kDropped;
+    if (idx < st.n) {
+      n_t = st.t_ns[idx];
+      n_p0 = st.p[0][idx]; n_p1 = st.p[1][idx]; n_p2 = st.p[2][idx];
+      n_g0 = st.g[0][idx]; n_g1 = st.g[1][idx]; n_g2 = st.g[2][idx];
+      n_g3 = st.g[3][idx]; n_g4 = st.g[4][idx]; n_g5 = st.g[5][idx];
+      n_ty = st.type[idx];
+    }
+  };
+  prefetch(slab0 * 32 + lane);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
-    const int64_t idx = (slab0 + sl) * 32 + lane;
     if ((slab0 + sl) * 32 >= st.n) break;
-    int64_t t = kDropped;
-    if (idx < st.n) t = st.t_ns[idx];
-    int s = -1;
+    const int64_t next_idx = (sl + 1 < slabs_per_warp) ? (slab0 + sl + 1) * 32 + lane : st.n;
+    const int64_t t = n_t;
+    int s = 0;
     double u = 0.0;
     bool valid = (t != kDropped) && index_ns(t, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u);
-    V3 pL = mk(0, 0, 0);
-    double geo[6] = {0, 0, 0, 0, 0, 0};
-    bool is_plane = true;
-    if (valid) {
-      pL = mk(st.p[0][idx], st.p[1][idx], st.p[2][idx]);
-#pragma unroll
-      for (int k = 0; k < 6; k++) geo[k] = st.g[k][idx];
-      is_plane = st.type[idx] != 0;
-    }
+    // masked lanes evaluate a harmless dummy (plane with zero normal at s = 0)
+    const V3 pL = valid ? mk(n_p0, n_p1, n_p2) : mk(0, 0, 0);
+    double geo[6];
+    geo[0] = valid ? n_g0 : 0.0; geo[1] = valid ? n_g1 : 0.0; geo[2] = valid ? n_g2 : 0.0;
+    geo[3] = valid ? n_g3 : 0.0; geo[4] = valid ? n_g4 : 0.0; geo[5] = valid ? n_g5 : 0.0;
+    const bool is_plane = valid ? (n_ty != 0) : true;
+    if (!valid) { s = 0; u = 0.0; }
     if (pp.marg_mode && valid && s >= pp.marg_later_local) valid = false;  // empty drop set: not part of the prior
-    int key = valid ? s : -1;
-    // process the distinct keys present in this slab in ascending order (1 for time-sorted input)
+    const int key = valid ? s : -1;
+    bool prefetched = false;
+    if (!JAC) { prefetch(next_idx); prefetched = true; }
+    // distinct keys of the slab in ascending order (one, for time-sorted input)
     unsigned pending = __ballot_sync(0xffffffffu, key >= 0);
     while (pending) {
-      int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
-      bool mine = (key == kmin) && ((pending >> lane) & 1);
-      double r = 0.0;
+      const int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
+      const bool mine = (key == kmin) && ((pending >> lane) & 1);
+      double r;
       double J[24];
-      bool contributes = false;
-      if (mine) {
-        loam_eval(W, s, u, pL, is_plane, geo, st.sh, JAC, &r, J);
-        contributes = true;
-        if (pp.marg_mode) {  // trajectory_estimator.cpp:729-741: only |r| / w < 0.05 enters the prior
-          double dist = fabs(r / st.sh.weight);
-          if (!(dist < 0.05)) contributes = false;
-        }
-        if (contributes) {
-          if (s + 3 >= pp.kf || pp.marg_mode) cost += 0.5 * r * r; else fcost += 0.5 * r * r;
-        }
-      }
+      // every lane evaluates; the scale masks it out.  (marg gate: trajectory_estimator.cpp:729-741, |r| / w < 0.05)
+      loam_eval(W, s, u, pL, is_plane, geo, st.sh, JAC, &r, J, mine ? st.sh.weight : 0.0);
+      bool contributes = mine;
+      if (pp.marg_mode && mine && !(fabs(r / st.sh.weight) < 0.05)) contributes = false;
+      const double r_eff = contributes ? r : 0.0;
+      if (s + 3 >= pp.kf || pp.marg_mode) cost += 0.5 * r_eff * r_eff; else fcost += 0.5 * r_eff * r_eff;
       if (JAC) {
         if (kmin != acc_key) {
-          flush_record<4>(acc, acc_key, slot, warp_global, rb, lane);
+          flush_record<3, 1>(acc, acc_key, slot, warp_global, rb, lane);
           acc.zero();
           acc_key = kmin;
         }
+        const double keep = (contributes == mine) ? 1.0 : 0.0;  // only the marg gate can zero a `mine` row after the fact
+        double pb[24];
 #pragma unroll
-        for (int c = 0; c < 24; c++) Jt[c * kJtStride + lane] = contributes ? J[c] : 0.0;
-        Jt[24 * kJtStride + lane] = contributes ? r : 0.0;
+        for (int c = 0; c < 24; c++) {
+          const double jc = (pp.marg_mode ? keep : 1.0) * J[c];
+          Jt[c * kJtStride + lane] = jc;
+          pb[c] = jc * r_eff;
+        }
+        acc.extra += warp_transpose_reduce24(pb, lane);
         __syncwarp();
+        if (!prefetched) { prefetch(next_idx); prefetched = true; }
         acc.accumulate(Jt, lane);
         __syncwarp();
       }
       pending &= ~__ballot_sync(0xffffffffu, mine);
     }
+    if (!prefetched) prefetch(next_idx);
   }
   if (JAC) {
-    cta_merge_and_flush<4>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    cta_merge_and_flush<3, 1, WARPS>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
     for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
   }
   // deterministic butterfly
@@ -612,7 +684,8 @@ struct StreamDesc {
   const double* part;    // [n_keys][P][rd]
   const double* overflow;  // [n_keys][rd] atomics fallback accumulators (all zero for time-sorted input)
   int n_keys, P, NT, rd;
-  int r_col;             // local column holding r~
+  int r_col;             // local column holding r~ (when b lives in the tiles)
+  int b_off;             // >= 0: b = J~^T r~ is stored as a plain vector at this offset of the record (LiDAR)
   int n_extra;           // local columns extra_base .. extra_base+n_extra-1 map to extra_global[] (-1: constant)
   int extra_base;        // 24 (one knot window) or 48 (two windows)
   int kind;              // 0: key = interval s (LiDAR / IMU);  1: key = s_i * kdim + s_j (visual, two knot windows)
@@ -677,7 +750,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
         const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
         const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
         const double* blk = p < sd.P ? sd.part + ((size_t)s * sd.P + p) * sd.rd : sd.overflow + (size_t)s * sd.rd;
-        acc += block_entry(blk, sd.NT, la, lb);
+        acc += (is_b && sd.b_off >= 0) ? blk[sd.b_off + la] : block_entry(blk, sd.NT, la, lb);
       }
     } else {
       // two knot windows: a global knot column may appear in window i, window j or both (overlap): J_g = sum of locals

@@ -20,6 +20,10 @@ def cuda_library():
     """The product library.  No fallback: a missing .so is an error."""
     global _lib
     if _lib is None:
+        path = os.environ.get("CLIC_CUDA_LIB", _LIB_PATH)  # developer override: kernel-tuning variants of the same library
+        if path != _LIB_PATH:
+            _lib = _abi.bind(path)
+            return _lib
         if not os.path.exists(_LIB_PATH):
             raise ImportError(
                 f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
