@@ -331,6 +331,7 @@ int ensure_layout(clic_estimator* E) {
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = -1;
     d.b_off = 384;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
     d.n_extra = 0;
     d.extra_base = 24;
     d.kind = 0;
@@ -345,6 +346,7 @@ int ensure_layout(clic_estimator* E) {
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 31;
     d.b_off = -1;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)(l < 32 ? imu_phys_col<false>(l) : l);
     d.n_extra = 7;
     d.extra_base = 24;
     d.kind = 0;
@@ -364,6 +366,7 @@ int ensure_layout(clic_estimator* E) {
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 49;
     d.b_off = -1;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
     d.n_extra = 1;
     d.extra_base = 48;
     d.kind = 1;
@@ -842,6 +845,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = -1; d.b_off = 384; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
     descs.push_back(d);
   }
   for (auto& b : E->imu) {
@@ -850,6 +854,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
     d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 34; d.b_off = -1; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)(l < 40 ? imu_phys_col<true>(l) : l);
     const int cg = find(CLIC_BLOCK_BIAS_GYRO, b->st.bias_slot), ca = find(CLIC_BLOCK_BIAS_ACCEL, b->st.bias_slot),
               cgr = find(CLIC_BLOCK_GRAVITY, 0), ct = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU);
     for (int c = 0; c < 3; c++) {

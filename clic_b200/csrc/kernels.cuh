@@ -84,21 +84,23 @@ struct WarpAcc {
     for (int t = 0; t < n_tiles(NT); t++) c[t][0] = c[t][1] = 0.0;
     extra = 0.0;
   }
-  // Jt: this warp's transposed tile, Jt[col * kJtStride + row], rows 0..31 = the slab's Jacobian rows
+  // Jt: this warp's transposed tile, Jt[col * kJtStride + row], rows 0..31 = the slab's Jacobian rows.
+  // NA: only the first NA column tiles of these rows are non-zero (the others are skipped, not even read).
+  template <int NA = NT>
   __device__ __forceinline__ void accumulate(const double* Jt, int lane) {
     const int r4 = lane & 3, c8 = lane >> 2;
 #pragma unroll
     for (int ks = 0; ks < 8; ks++) {
-      double a[NT];
+      double a[NA];
 #pragma unroll
-      for (int t = 0; t < NT; t++) a[t] = Jt[(8 * t + c8) * kJtStride + 4 * ks + r4];
-      int idx = 0;
+      for (int t = 0; t < NA; t++) a[t] = Jt[(8 * t + c8) * kJtStride + 4 * ks + r4];
 #pragma unroll
-      for (int ta = 0; ta < NT; ta++)
+      for (int ta = 0; ta < NA; ta++)
 #pragma unroll
-        for (int tb = ta; tb < NT; tb++) {
+        for (int tb = ta; tb < NA; tb++) {
+          constexpr int dummy = 0; (void)dummy;
+          const int idx = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
           dmma884(c[idx][0], c[idx][1], a[ta], a[tb]);
-          idx++;
         }
     }
   }
@@ -483,6 +485,42 @@ struct SmemRowSink {
     __syncwarp();
   }
 };
+
+// IMU rows are stored in a PHYSICAL column order that packs the columns the gyro rows touch into the first three
+// tiles:  [dtheta x12 | bg | t_off | r | ba | (gravity) | dp x12 | pad].  Gyro rows (0..2) have zero dp / ba /
+// gravity blocks, so their last tile(s) are skipped: 6 instead of 10 (15 in marg mode) tile products.
+// Logical order (what factor_eval emits, what the assembly addresses): [knot k: dtheta dp] x4 | bg | ba | (g) | t_off | r.
+template <bool MARG>
+__host__ __device__ constexpr int imu_phys_col(int l) {
+  if (l < 24) return (l % 6 < 3) ? (l / 6) * 3 + l % 6 : (MARG ? 23 : 20) + (l / 6) * 3 + (l % 6 - 3);
+  if (l < 27) return 12 + (l - 24);                       // bg
+  if (l < 30) return 17 + (l - 27);                       // ba
+  if (MARG) {
+    if (l < 33) return 20 + (l - 30);                     // gravity
+    if (l == 33) return 15;                               // t_off
+    if (l == 34) return 16;                               // r
+    return l;                                             // pad 35..39
+  }
+  return l == 30 ? 15 : 16;                               // t_off, r
+}
+template <bool MARG>
+struct ImuRowSink {
+  static constexpr int NT = MARG ? 5 : 4;
+  double* Jt;
+  int lane;
+  bool on;
+  WarpAcc<NT>* acc;
+  __device__ __forceinline__ void put(int row, int col, double v) {
+    const int pc = imu_phys_col<MARG>(col);
+    if (row < 3 && pc >= 24) return;  // never read for gyro rows
+    Jt[pc * kJtStride + lane] = on ? v : 0.0;
+  }
+  __device__ __forceinline__ void row_done(int row) {
+    __syncwarp();
+    if (row < 3) acc->template accumulate<3>(Jt, lane); else acc->template accumulate<NT>(Jt, lane);
+    __syncwarp();
+  }
+};
 struct NullSink {
   __device__ __forceinline__ void put(int, int, double) {}
   __device__ __forceinline__ void row_done(int) {}
@@ -545,7 +583,7 @@ imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
           acc.zero();
           acc_key = kmin;
         }
-        SmemRowSink<NT> sink;
+        ImuRowSink<MARG> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
         double rho = imu_eval<MARG>(W, mine ? s : kmin, mine ? u : 0.0, gy, ac, sh, true, sink);
         if (mine) { if (s + 3 >= pp.kf || st.extras_free || MARG) cost += 0.5 * rho; else fcost += 0.5 * rho; }
@@ -691,6 +729,7 @@ struct StreamDesc {
   int kind;              // 0: key = interval s (LiDAR / IMU);  1: key = s_i * kdim + s_j (visual, two knot windows)
   int kdim;
   int extra_global[12];
+  unsigned char perm[64]; // logical local column -> physical column inside the record tiles
 };
 
 struct ColMaps {
@@ -701,7 +740,7 @@ struct ColMaps {
 };
 
 __device__ __forceinline__ double block_entry(const double* blk, int NT, int la, int lb) {
-  int ta = la >> 3, tb = lb >> 3;
+  int ta = la >> 3, tb = lb >> 3;  // la, lb: PHYSICAL columns
   if (ta > tb) { int t = ta; ta = tb; tb = t; t = la; la = lb; lb = t; }
   return blk[tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7)];
 }
@@ -750,7 +789,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
         const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
         const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
         const double* blk = p < sd.P ? sd.part + ((size_t)s * sd.P + p) * sd.rd : sd.overflow + (size_t)s * sd.rd;
-        acc += (is_b && sd.b_off >= 0) ? blk[sd.b_off + la] : block_entry(blk, sd.NT, la, lb);
+        acc += (is_b && sd.b_off >= 0) ? blk[sd.b_off + la] : block_entry(blk, sd.NT, sd.perm[la], sd.perm[lb]);
       }
     } else {
       // two knot windows: a global knot column may appear in window i, window j or both (overlap): J_g = sum of locals
@@ -777,7 +816,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
         if (na == 0 || nb == 0) continue;
         const double* blk = p < sd.P ? sd.part + ((size_t)key * sd.P + p) * sd.rd : sd.overflow + (size_t)key * sd.rd;
         for (int x = 0; x < na; x++)
-          for (int y = 0; y < nb; y++) acc += block_entry(blk, sd.NT, la[x], lb[y]);
+          for (int y = 0; y < nb; y++) acc += block_entry(blk, sd.NT, sd.perm[la[x]], sd.perm[lb[y]]);
       }
     }
   }
