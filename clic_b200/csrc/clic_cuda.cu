@@ -386,17 +386,21 @@ int ensure_layout(clic_estimator* E) {
 }
 
 
-int launch_reduce(clic_estimator* E, const StreamExec& ex, const int* ctl) {
-  dim3 g(ex.n_keys, ex.P);
+int launch_reduce(clic_estimator* E, const StreamExec& ex, double* cost2, bool first_stream, const int* ctl) {
+  dim3 g(ex.n_keys + 1, ex.P);  // + 1: the cost-reduction CTA
   const int n_slots = ex.n_warps * kSlotsPerWarp;
-  const size_t smem = 0;
+#define CLIC_RR(RD)                                                                                             \
+  reduce_records_kernel<RD><<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P,  \
+                                                      ex.part.as<double>(), ex.cost.as<double>(), ex.n_warps, cost2, \
+                                                      first_stream ? 1 : 0, ctl)
   switch (ex.NT) {
-    case 3: reduce_records_kernel<416><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
-    case 4: reduce_records_kernel<640><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
-    case 5: reduce_records_kernel<960><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
-    case 7: reduce_records_kernel<1792><<<g, 256, smem, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P, ex.part.as<double>(), ctl); break;
+    case 3: CLIC_RR(416); break;
+    case 4: CLIC_RR(640); break;
+    case 5: CLIC_RR(960); break;
+    case 7: CLIC_RR(1792); break;
     default: return 1;
   }
+#undef CLIC_RR
   return 0;
 }
 
@@ -469,9 +473,20 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   if (rc) return rc;
   double* cost2 = E->cost_loc() + 2 * which;  // slot 0: pass at x, slot 1: pass at the LM candidate
   PassParams pp = pass_params(E, state, ctl);
-  zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
-  E->launches += 1;
   const int D = E->L.D;
+  bool first = true;  // the first stream of the pass stores cost2, the others add to it
+  auto finish_stream = [&](StreamExec& ex) -> int {
+    E->prof_begin(3);
+    if (jac) {
+      if (launch_reduce(E, ex, cost2, first, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
+    } else {
+      reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, first ? 0 : 1, ctl);
+    }
+    E->prof_end();
+    E->launches += 1;
+    first = false;
+    return CLIC_OK;
+  };
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
@@ -481,20 +496,14 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_begin(0);
       loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
-      E->prof_begin(3);
-      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
-      E->prof_end();
-      E->launches += 2;
+      E->launches += 1;
     } else {
       E->prof_begin(0);
       loam_kernel<false, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->launches += 1;
     }
-    E->prof_begin(3);
-    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
-    E->prof_end();
-    E->launches += 1;
+    if ((rc = finish_stream(ex))) return rc;
   }
   for (auto& b : E->imu) {
     if (b->marg) continue;
@@ -505,20 +514,14 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_begin(1);
       imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
-      E->prof_begin(3);
-      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
-      E->prof_end();
-      E->launches += 2;
+      E->launches += 1;
     } else {
       E->prof_begin(1);
       imu_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
       E->launches += 1;
     }
-    E->prof_begin(3);
-    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
-    E->prof_end();
-    E->launches += 1;
+    if ((rc = finish_stream(ex))) return rc;
   }
   for (auto& b : E->image) {
     if (b->marg) continue;
@@ -536,19 +539,17 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_begin(2);
       image_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
       E->prof_end();
-      E->prof_begin(3);
-      if (launch_reduce(E, ex, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
-      E->prof_end();
-      E->launches += 2;
+      E->launches += 1;
     } else {
       E->prof_begin(2);
       image_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
       E->prof_end();
       E->launches += 1;
     }
-    E->prof_begin(3);
-    reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, 1, ctl);
-    E->prof_end();
+    if ((rc = finish_stream(ex))) return rc;
+  }
+  if (first) {  // no factor stream at all (prior-only problem)
+    zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
     E->launches += 1;
   }
   if (jac && D > 0) {
@@ -756,7 +757,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     StreamExec& ex = b->ex;
     CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
     loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
-    if (launch_reduce(E, ex, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
+    if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
     E->launches += 2;
     if ((rc = mark(ex, -1))) return rc;
   }
@@ -765,7 +766,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     StreamExec& ex = b->ex;
     CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
     imu_kernel<true, true><<<ex.grid, kThreads, factor_smem_bytes(K, 5), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
-    if (launch_reduce(E, ex, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
+    if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
     E->launches += 2;
     if ((rc = mark(ex, 34))) return rc;
     bool used = false;

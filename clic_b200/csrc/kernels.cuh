@@ -371,13 +371,40 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
 // the list in order, issuing the loads of four records before their adds (memory-level parallelism without
 // changing the summation order => deterministic).  out[(key * P + part) * RD + e].
 constexpr int kMaxChunk = 1024;
+// The extra CTA (blockIdx.x == gridDim.x - 1, part 0) sums the per-warp costs in a fixed tree and adds (or, for the
+// first stream of a pass, stores) them into cost2 — one launch less per stream than a separate cost kernel.
 template <int RD>
 __global__ void __launch_bounds__(256)
-reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const int* ctl) {
+reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const double* warp_cost,
+                      int n_warps, double* cost2, int first_stream, const int* ctl) {
   if (ctl && ctl[0]) return;
   constexpr int EPT = (RD + 255) / 256;
   __shared__ int list[kMaxChunk];
   __shared__ int n_match;
+  if (blockIdx.x == gridDim.x - 1) {
+    if (blockIdx.y != 0) return;
+    __shared__ double sh[2][256];
+    double c = 0, f = 0;
+    for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
+      c += warp_cost[2 * i];
+      f += warp_cost[2 * i + 1];
+    }
+    sh[0][threadIdx.x] = c;
+    sh[1][threadIdx.x] = f;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) {
+        sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+        sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      cost2[0] = (first_stream ? 0.0 : cost2[0]) + sh[0][0];
+      cost2[1] = (first_stream ? 0.0 : cost2[1]) + sh[1][0];
+    }
+    return;
+  }
   const int k = blockIdx.x, part = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = (n_slots + P - 1) / P;
@@ -841,32 +868,39 @@ struct BiasFactorDesc {
 __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, StateLayout sl, double* H, double* b, int D,
                                    double* cost2, int jac, const int* ctl) {
   if (ctl && ctl[0]) return;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double* bi = state + sl.off_bias() + 6 * bf.slot_i;
-  const double* bj = state + sl.off_bias() + 6 * bf.slot_j;
+  // one lane per residual row: rows touch disjoint H / b entries (row r -> offset r % 3 of the gyro or accel blocks)
+  const int r = threadIdx.x;
   double c = 0.0;
-  bool any_free = bf.col_gi >= 0 || bf.col_gj >= 0 || bf.col_ai >= 0 || bf.col_aj >= 0;
-  for (int r = 0; r < 6; r++) {
+  if (r < 6) {
+    const double* bi = state + sl.off_bias() + 6 * bf.slot_i;
+    const double* bj = state + sl.off_bias() + 6 * bf.slot_j;
     const double w = bf.sqrt_info[r];
     const double res = w * (bj[r] - bi[r]);
-    c += res * res;
-    if (!jac) continue;
-    const int ci = (r < 3 ? bf.col_gi : bf.col_ai), cj = (r < 3 ? bf.col_gj : bf.col_aj);
-    const int o = r % 3;
-    if (ci >= 0) {
-      H[(size_t)(ci + o) * D + ci + o] += w * w;
-      b[ci + o] += -w * res;
-    }
-    if (cj >= 0) {
-      H[(size_t)(cj + o) * D + cj + o] += w * w;
-      b[cj + o] += w * res;
-    }
-    if (ci >= 0 && cj >= 0) {
-      H[(size_t)(ci + o) * D + cj + o] += -w * w;
-      H[(size_t)(cj + o) * D + ci + o] += -w * w;
+    c = res * res;
+    if (jac) {
+      const int ci = (r < 3 ? bf.col_gi : bf.col_ai), cj = (r < 3 ? bf.col_gj : bf.col_aj);
+      const int o = r % 3;
+      if (ci >= 0) {
+        H[(size_t)(ci + o) * D + ci + o] += w * w;
+        b[ci + o] += -w * res;
+      }
+      if (cj >= 0) {
+        H[(size_t)(cj + o) * D + cj + o] += w * w;
+        b[cj + o] += w * res;
+      }
+      if (ci >= 0 && cj >= 0) {
+        H[(size_t)(ci + o) * D + cj + o] += -w * w;
+        H[(size_t)(cj + o) * D + ci + o] += -w * w;
+      }
     }
   }
-  cost2[any_free ? 0 : 1] += 0.5 * c;
+  // fixed-order sum of the 6 terms
+  double tot = 0.0;
+  for (int k = 0; k < 6; k++) tot += __shfl_sync(0xffffffffu, c, k);
+  if (r == 0) {
+    const bool any_free = bf.col_gi >= 0 || bf.col_gj >= 0 || bf.col_ai >= 0 || bf.col_aj >= 0;
+    cost2[any_free ? 0 : 1] += 0.5 * tot;
+  }
 }
 
 // K0 at add time: double seconds -> int64 ns with the reference's truncation and window test
