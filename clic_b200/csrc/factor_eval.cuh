@@ -94,8 +94,14 @@ struct LoamShared {  // arguments of AddLoamMeasurementAnalytic shared by a batc
 // LoamFeatureFactor::Evaluate.  geo = plane (n.x n.y n.z d) or line (point xyz, direction xyz).
 // J[24] gets the local row [knot: dtheta(3) dp(3)] x 4; *r the weighted residual.  No loss (":743").
 // `jscale` multiplies the emitted Jacobian row (sh.weight for a contributing factor, 0 to mask a lane out).
-CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plane, const double geo[6],
-                       const LoamShared& sh, bool want_jac, double* r_out, double J[24], double jscale) {
+// Out: out.put(col, value) for the 24 local columns (an array writer on the host, a shared-memory writer in the kernel).
+struct ArrayOut24 {
+  double* J;
+  CLIC_HD void put(int c, double v) { J[c] = v; }
+};
+template <class Out>
+CLIC_HD void loam_eval_to(const WindowView& W, int s, double u, V3 pL, bool is_plane, const double geo[6],
+                          const LoamShared& sh, bool want_jac, double* r_out, Out& out, double jscale) {
   double lam[4], c[4];
   blend_cum(u, lam);
   blend_plain(u, c);
@@ -141,15 +147,21 @@ CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plan
   V3 j2 = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
   V3 j3 = vmat(t2, W.pair[s + 2].Jrinv);
   const double w = jscale;
-  J[0] = w * j0.x; J[1] = w * j0.y; J[2] = w * j0.z;
-  J[6] = w * j1.x; J[7] = w * j1.y; J[8] = w * j1.z;
-  J[12] = w * j2.x; J[13] = w * j2.y; J[14] = w * j2.z;
-  J[18] = w * j3.x; J[19] = w * j3.y; J[20] = w * j3.z;
+  out.put(0, w * j0.x); out.put(1, w * j0.y); out.put(2, w * j0.z);
+  out.put(6, w * j1.x); out.put(7, w * j1.y); out.put(8, w * j1.z);
+  out.put(12, w * j2.x); out.put(13, w * j2.y); out.put(14, w * j2.z);
+  out.put(18, w * j3.x); out.put(19, w * j3.y); out.put(20, w * j3.z);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     double wc = w * c[k];
-    J[6 * k + 3] = wc * g.x; J[6 * k + 4] = wc * g.y; J[6 * k + 5] = wc * g.z;
+    out.put(6 * k + 3, wc * g.x); out.put(6 * k + 4, wc * g.y); out.put(6 * k + 5, wc * g.z);
   }
+}
+CLIC_HD void loam_eval(const WindowView& W, int s, double u, V3 pL, bool is_plane, const double geo[6],
+                       const LoamShared& sh, bool want_jac, double* r_out, double J[24], double jscale) {
+  ArrayOut24 o;
+  o.J = J;
+  loam_eval_to(W, s, u, pL, is_plane, geo, sh, want_jac, r_out, o, jscale);
 }
 
 // ceres::CauchyLoss(a) + Corrector (marginalization_factor.cpp:38-61): rho'' < 0 always, so the correction is the
@@ -216,32 +228,12 @@ CLIC_HD double imu_eval(const WindowView& W, int s, double u, V3 gyro_m, V3 acce
   if (sh.loss_a > 0) sc = cauchy_scale(sq, sh.loss_a, &rho);
   if (!want_jac) return rho;
 
-  M3 Apost[4];
-#pragma unroll
-  for (int i = 0; i < 3; i++) Apost[i] = qmat(Aq[i]);
-  Apost[3].m[0] = Apost[3].m[4] = Apost[3].m[8] = 1.0;
-  Apost[3].m[1] = Apost[3].m[2] = Apost[3].m[3] = Apost[3].m[5] = Apost[3].m[6] = Apost[3].m[7] = 0.0;
-  M3 LJ[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) LJ[i] = lamJr(W.pair[s + i], lamR[i + 1], ca[i], cb[i], -1.0);  // lambda*Jr(-k_delta)
-  // d(omega)/d(delta_i)  (split_spline_view.h:140-150)
-  M3 dW[3];
-  dW[0] = mscale(lamW[1], Apost[1]);
-#pragma unroll
-  for (int i = 1; i < 3; i++)
-    dW[i] = madd(mmul(mmul(Apost[i], hat(omega[i])), LJ[i]), mscale(lamW[i + 1], Apost[i + 1]));
-  // d(accel)/d(delta_i)  (":160-186")
+  // Row-wise (vector-first) evaluation: a residual row only needs ROWS of the rotation matrices involved, pushed as
+  // 1x3 vectors through lambda*Jr(-k_delta) and Jr^-1 — no 3x3 matrix products, short register live ranges.
+  //   A_post_inv[i] = mat(Aq[i]) (A_post_inv[3] = I),  R_accum[i] = mat(P_i), P_0 = R_s, P_i+1 = P_i * exp(+k_delta_i)
+  const Q4 P1 = qmul(q_s, qconj(Ainv[0]));
+  const Q4 P2 = qmul(P1, qconj(Ainv[1]));
   M3 Rinv_m = qmat(R_inv);
-  M3 lhs = mmul(Rinv_m, hat(ag));
-  M3 Racc = qmat(q_s);
-  M3 dA[3];
-  M3 lhsR0 = mmul(lhs, Racc);
-  dA[0] = mmul(lhsR0, LJ[0]);
-#pragma unroll
-  for (int i = 1; i < 3; i++) {
-    Racc = mmul_t(Racc, qmat(Ainv[i - 1]));  // R_accum[i] = R_accum[i-1] * A_rot_inv[i-1]^T
-    dA[i] = mmul(mmul(lhs, Racc), LJ[i]);
-  }
   // time-offset column (trajectory_value_factor.h:268-291)
   V3 jt_top = mk(0, 0, 0), jt_bot = mk(0, 0, 0);
   {
@@ -262,32 +254,42 @@ CLIC_HD double imu_eval(const WindowView& W, int s, double u, V3 gyro_m, V3 acce
     V3 jerk = mk(0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 4; i++) jerk = fma3(cj[i], ldv(W.kp + 3 * (s + i)), jerk);
-    M3 rot = mtrans(Rinv_m);
-    M3 gh = hat(omega[3]);
-    M3 rot_dot = mmul(rot, gh);
-    M3 T1 = mmul(mtrans(rot_dot), rot_dot);
-    M3 T2 = mmul(mtrans(rot), madd(mmul(rot_dot, gh), mmul(rot, hat(ra))));
-    jt_top = mk(T1.m[7] + T2.m[7], T1.m[2] + T2.m[2], T1.m[3] + T2.m[3]);  // vee = (m21, m02, m10)
-    jt_bot = mvec(mmul(mtrans(rot_dot), rot), accel_b) + mvec(mtrans(rot), jerk);
+    // With rot = R(t), rot_dot = R hat(omega):  vee(rot_dot^T rot_dot) + vee(rot^T (rot_dot hat(omega) + rot hat(ra)))
+    // = vee(-hat(omega)^2) + vee(hat(omega)^2 + hat(ra)) = ra   (the symmetric parts cancel; the reference forms the
+    // 3x3 products, equal to 1e-16 relative), and rot_dot^T rot a_b + rot^T jerk = a_b x omega + R^-1 jerk.
+    jt_top = ra;
+    jt_bot = cross(accel_b, omega[3]) + qrot(R_inv, jerk);
   }
-  // knot rotation blocks: J_rot[k] for k = 0..3, 3x3 each for gyro and accel rows
-  // [0] = X - d0 Jri0^T ; [1] = d0 Jri0 - d1 Jri1^T ; [2] = d1 Jri1 - d2 Jri2^T ; [3] = d2 Jri2   (X = 0 gyro, lhs*R0 accel)
+  // knot rotation blocks, one residual row at a time:
+  //   gyro  rows (split_spline_view.h:137-157): dW_i = lamR_i+1 A_post_inv[i] hat(omega_i) Jr(-kd_i) + lamW_i+1 A_post_inv[i+1]
+  //   accel rows (":160-186"):                  dA_i = lamR_i+1 lhs R_accum[i] Jr(-kd_i),  lhs = R_inv hat(a_w + g)
+  //   J[0] = X - d_0 Jri_0^T ; J[k] = d_k-1 Jri_k-1 - d_k Jri_k^T ; J[3] = d_2 Jri_2      (X = 0 | lhs R_s)
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    const M3* d = half == 0 ? dW : dA;
 #pragma unroll
     for (int rr = 0; rr < 3; rr++) {
       const int row = half * 3 + rr;
       const double sI = sc * sh.info[row];
-      V3 dr0 = mk(d[0].m[rr * 3], d[0].m[rr * 3 + 1], d[0].m[rr * 3 + 2]);
-      V3 dr1 = mk(d[1].m[rr * 3], d[1].m[rr * 3 + 1], d[1].m[rr * 3 + 2]);
-      V3 dr2 = mk(d[2].m[rr * 3], d[2].m[rr * 3 + 1], d[2].m[rr * 3 + 2]);
-      V3 x = half == 0 ? mk(0, 0, 0) : mk(lhsR0.m[rr * 3], lhsR0.m[rr * 3 + 1], lhsR0.m[rr * 3 + 2]);
+      V3 d0, d1, d2, x;
+      if (half == 0) {
+        const V3 e = mk(rr == 0 ? 1.0 : 0.0, rr == 1 ? 1.0 : 0.0, rr == 2 ? 1.0 : 0.0);
+        const V3 a1 = qrot_inv(Aq[1], e), a2 = qrot_inv(Aq[2], e);  // rows rr of A_post_inv[1], [2]; [3] = I -> e
+        x = mk(0, 0, 0);
+        d0 = lamW[1] * a1;
+        d1 = fma3(lamW[2], a2, row_times_lamJr(cross(a1, omega[1]), W.pair[s + 1], lamR[2], ca[1], cb[1], -1.0));
+        d2 = fma3(lamW[3], e, row_times_lamJr(cross(a2, omega[2]), W.pair[s + 2], lamR[3], ca[2], cb[2], -1.0));
+      } else {
+        const V3 v = cross(mk(Rinv_m.m[rr * 3], Rinv_m.m[rr * 3 + 1], Rinv_m.m[rr * 3 + 2]), ag);  // row rr of lhs
+        x = qrot_inv(q_s, v);                                                                       // row rr of lhs * R_s
+        d0 = row_times_lamJr(x, W.pair[s + 0], lamR[1], ca[0], cb[0], -1.0);
+        d1 = row_times_lamJr(qrot_inv(P1, v), W.pair[s + 1], lamR[2], ca[1], cb[1], -1.0);
+        d2 = row_times_lamJr(qrot_inv(P2, v), W.pair[s + 2], lamR[3], ca[2], cb[2], -1.0);
+      }
       V3 j[4];
-      j[0] = x - vmat_t(dr0, W.pair[s + 0].Jrinv);
-      j[1] = vmat(dr0, W.pair[s + 0].Jrinv) - vmat_t(dr1, W.pair[s + 1].Jrinv);
-      j[2] = vmat(dr1, W.pair[s + 1].Jrinv) - vmat_t(dr2, W.pair[s + 2].Jrinv);
-      j[3] = vmat(dr2, W.pair[s + 2].Jrinv);
+      j[0] = x - vmat_t(d0, W.pair[s + 0].Jrinv);
+      j[1] = vmat(d0, W.pair[s + 0].Jrinv) - vmat_t(d1, W.pair[s + 1].Jrinv);
+      j[2] = vmat(d1, W.pair[s + 1].Jrinv) - vmat_t(d2, W.pair[s + 2].Jrinv);
+      j[3] = vmat(d2, W.pair[s + 2].Jrinv);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         sink.put(row, 6 * k + 0, sI * j[k].x);

@@ -319,9 +319,15 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
       const int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
       const bool mine = (key == kmin) && ((pending >> lane) & 1);
       double r;
-      double J[24];
-      // every lane evaluates; the scale masks it out.  (marg gate: trajectory_estimator.cpp:729-741, |r| / w < 0.05)
-      loam_eval(W, s, u, pL, is_plane, geo, st.sh, JAC, &r, J, mine ? st.sh.weight : 0.0);
+      // every lane evaluates; the scale masks it out.  The 24 Jacobian columns are streamed to the warp's transposed
+      // shared tile as they are produced (short register live ranges).
+      struct SmemOut24 {
+        double* Jt;
+        __device__ __forceinline__ void put(int c, double v) { Jt[c * kJtStride] = v; }
+      } jout;
+      jout.Jt = Jt + lane;
+      loam_eval_to(W, s, u, pL, is_plane, geo, st.sh, JAC, &r, jout, mine ? st.sh.weight : 0.0);
+      // marg gate (trajectory_estimator.cpp:729-741): only |r| / w < 0.05 enters the prior
       bool contributes = mine;
       if (pp.marg_mode && mine && !(fabs(r / st.sh.weight) < 0.05)) contributes = false;
       const double r_eff = contributes ? r : 0.0;
@@ -332,14 +338,13 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
           acc.zero();
           acc_key = kmin;
         }
-        const double keep = (contributes == mine) ? 1.0 : 0.0;  // only the marg gate can zero a `mine` row after the fact
         double pb[24];
+        if (pp.marg_mode && contributes != mine) {  // gated out after the fact: zero the row
 #pragma unroll
-        for (int c = 0; c < 24; c++) {
-          const double jc = (pp.marg_mode ? keep : 1.0) * J[c];
-          Jt[c * kJtStride + lane] = jc;
-          pb[c] = jc * r_eff;
+          for (int c = 0; c < 24; c++) Jt[c * kJtStride + lane] = 0.0;
         }
+#pragma unroll
+        for (int c = 0; c < 24; c++) pb[c] = Jt[c * kJtStride + lane] * r_eff;
         acc.extra += warp_transpose_reduce24(pb, lane);
         __syncwarp();
         if (!prefetched) { prefetch(next_idx); prefetched = true; }
