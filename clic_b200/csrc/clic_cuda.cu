@@ -259,14 +259,14 @@ clic_layout compute_layout(const clic_estimator* E) {
 }
 
 int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_per_sm, bool pair_keys = false,
-                int extra = 0, int warps_per_cta = kWarpsPerCta) {
+                int extra = 0, int warps_per_cta = kWarpsPerCta, int factors_per_slab = 32) {
   const int kWarpsPerCta = warps_per_cta;  // shadows the global default for this stream
   ex.warps_per_cta = warps_per_cta;
   ex.n = n;
   ex.NT = NT;
   ex.rd = rec_doubles(NT, extra);
   ex.n_keys = pair_keys ? (E->K - 3) * (E->K - 3) : E->K - 3;
-  const int64_t slabs = (n + 31) / 32;
+  const int64_t slabs = (n + factors_per_slab - 1) / factors_per_slab;
   const int max_ctas = E->n_sm * ctas_per_sm;
   int64_t ctas = std::min<int64_t>(max_ctas, (slabs + kWarpsPerCta - 1) / kWarpsPerCta);
   ctas = std::max<int64_t>(ctas, 1);
@@ -1288,7 +1288,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
     E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
   }
-  if ((rc = plan_stream(E, B->ex, n, 7, 1, true))) return rc;
+  if ((rc = plan_stream(E, B->ex, n, 7, 1, true, 0, kWarpsPerCta, kImageFactorsPerSlab))) return rc;
   E->image.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;

@@ -399,9 +399,11 @@ struct ImageShared {
 // ImageFeatureFactor::Evaluate (image_feature_factor.h:67-268), inverse depth held constant (fixed_depth = true, the
 // only mode the shipped pipeline uses, trajectory_manager.cpp:709).  Emits 2 rows of 56 columns:
 //   [window of t_i: 0..23 | window of t_j: 24..47 | camera t_offset 48 | r 49 | pad]
+// `row_sel` (0 | 1) selects which of the two residual rows this call emits: the kernel gives row 0 to lanes 0-15 and
+// row 1 to lanes 16-31 of the same 16 factors (data-dependent only, no divergent code), the host test calls it twice.
 template <class Sink>
 CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double uj, V3 p_i, V3 p_j, double d_inv,
-                          const ImageShared& sh, bool want_jac, Sink& sink) {
+                          const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
   V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
   V3 p_Ii = qrot(sh.S_CtoI, x_ci) + sh.p_CinI;
   So3Chain Ci, Cj;
@@ -428,8 +430,9 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
   double rho = sq, sc = 1.0;
   if (sh.loss_a > 0) sc = cauchy_scale(sq, sh.loss_a, &rho);
   if (!want_jac) return rho;
-  // J_v rows (2x3)
-  V3 Jv[2] = {mk(dinv, 0.0, -dinv * dinv * x_j.x), mk(0.0, dinv, -dinv * dinv * x_j.y)};
+  // J_v row (1x3 of the 2x3): row 0 = (1/z, 0, -x/z^2), row 1 = (0, 1/z, -y/z^2)
+  const bool r0 = row_sel == 0;
+  const V3 Jvr = mk(r0 ? dinv : 0.0, r0 ? 0.0 : dinv, -dinv * dinv * (r0 ? x_j.x : x_j.y));
   V3 jt = mk(0, 0, 0);
   if (sh.want_toff) {  // image_feature_factor.h:250-263
     V3 gyro_i = so3_velocity_body(W, si, ui, sh.inv_dt), gyro_j = so3_velocity_body(W, sj, uj, sh.inv_dt);
@@ -448,11 +451,11 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
     V3 J_ti = qrot(S_GtoCj, qrot(Ci.R, cross(gyro_i, p_Ii)) + vel_i);
     jt = J_ti + J_tj;
   }
-#pragma unroll
-  for (int row = 0; row < 2; row++) {
+  {
+    const int row = row_sel;
     const double sI = sc * sh.sqrt_info;
     // g = (J_v S_GtoCj)^T  -> jac_lhs_P[0] = g, jac_lhs_P[1] = -g
-    V3 g = qrot_inv(S_GtoCj, Jv[row]);
+    V3 g = qrot_inv(S_GtoCj, Jvr);
     // jac_lhs_R[0] = -J_v (S_GtoCj S_IitoG) hat(p_Ii):  with m = (J_v S_GtoCj R_i)^T, row = -(m x p_Ii) = p_Ii x m
     V3 m = qrot_inv(Ci.R, g);
     V3 a_i = cross(p_Ii, m);
@@ -476,8 +479,8 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
       sink.put(row, 24 + 6 * k + 4, -sI * cj[k] * g.y);
       sink.put(row, 24 + 6 * k + 5, -sI * cj[k] * g.z);
     }
-    sink.put(row, 48, sh.want_toff ? (1e-9 * sI) * dot(Jv[row], jt) : 0.0);
-    sink.put(row, 49, sc * res[row]);
+    sink.put(row, 48, sh.want_toff ? (1e-9 * sI) * dot(Jvr, jt) : 0.0);
+    sink.put(row, 49, sc * (r0 ? res[0] : res[1]));
 #pragma unroll
     for (int cc = 50; cc < 56; cc++) sink.put(row, cc, 0.0);
     sink.row_done(row);

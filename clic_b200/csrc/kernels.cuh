@@ -655,7 +655,11 @@ struct ImageStream {
   double loss_a;
 };
 
-// Local columns (NT = 7): [window of t_i 0..23 | window of t_j 24..47 | camera t_offset 48 | r 49 | pad]; key = s_i*(K-3)+s_j
+// Local columns (NT = 7): [window of t_i 0..23 | window of t_j 24..47 | camera t_offset 48 | r 49 | pad]; key = s_i*(K-3)+s_j.
+// A slab is 16 factors x 2 residual rows: lanes 0-15 evaluate row 0, lanes 16-31 row 1 of the same factors, so one
+// 32-row tile accumulation covers a slab and each lane builds one Jacobian row only (this stream is small and
+// latency-bound: shorter per-lane work + twice as many slabs to spread over the SMs).
+constexpr int kImageFactorsPerSlab = 16;
 template <bool JAC>
 __global__ void __launch_bounds__(kThreads, 1)
 image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, ImageShared sh) {
@@ -666,6 +670,7 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
   WindowView W = stage_window(smem, pp, &rest);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  const int row_sel = lane >> 4;
   double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
   const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 2];  // camera offset, image_feature_factor.h:75-76
   const double* invd = pp.state + pp.sl.off_invd();
@@ -676,8 +681,8 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
   double cost = 0.0, fcost = 0.0;
   const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
   for (int sl = 0; sl < slabs_per_warp; sl++) {
-    if ((slab0 + sl) * 32 >= st.n) break;
-    const int64_t idx = (slab0 + sl) * 32 + lane;
+    if ((slab0 + sl) * kImageFactorsPerSlab >= st.n) break;
+    const int64_t idx = (slab0 + sl) * kImageFactorsPerSlab + (lane & 15);
     int64_t ti = kDropped, tj = kDropped;
     if (idx < st.n) { ti = st.ti_ns[idx]; tj = st.tj_ns[idx]; }
     int si = 0, sj = 0;
@@ -690,6 +695,8 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
       p_i = mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]);
       p_j = mk(st.pj[0][idx], st.pj[1][idx], 1.0);
       rho_inv = invd[st.landmark[idx]];
+    } else {
+      si = sj = 0; ui = uj = 0.0;
     }
     int key = valid ? si * nk + sj : -1;
     unsigned pending = __ballot_sync(0xffffffffu, key >= 0);
@@ -698,6 +705,7 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
       bool mine = (key == kmin) && ((pending >> lane) & 1);
       // a visual factor touches knots of both windows: it has a free parameter unless both windows are all constant
       const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff;
+      const bool counts = mine && row_sel == 0;  // the factor's cost is counted once
       if (JAC) {
         if (kmin != acc_key) {
           flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
@@ -706,15 +714,12 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
         }
         SmemRowSink<NT> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
-        double rho = image_eval(W, mine ? si : kmin / nk, mine ? ui : 0.0, mine ? sj : kmin % nk, mine ? uj : 0.0, p_i,
-                                p_j, rho_inv, sh, true, sink);
-        if (mine) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
+        double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel);
+        if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       } else {
-        if (mine) {
-          NullSink sink;
-          double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, false, sink);
-          if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho;
-        }
+        NullSink sink;
+        double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, false, sink, row_sel);
+        if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       }
       pending &= ~__ballot_sync(0xffffffffu, mine);
     }

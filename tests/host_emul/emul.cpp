@@ -82,7 +82,8 @@ __attribute__((visibility("default"))) int emul_image(int K, const double* kq, c
   sh.S_CtoI = ldq(S_CtoI); sh.p_CinI = ldv(p_CinI); sh.sqrt_info = 450.0 / 1.5; sh.loss_a = loss_a;
   sh.inv_dt = 1e9 / double(dt_ns); sh.want_toff = want_toff != 0;
   ArraySink sink{rows, 56};
-  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink);
+  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0);
+  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1);
   *si_out = si;
   *sj_out = sj;
   return 0;
