@@ -268,12 +268,10 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.n_keys = pair_keys ? (E->K - 3) * (E->K - 3) : E->K - 3;
   const int64_t slabs = (n + factors_per_slab - 1) / factors_per_slab;
   const int max_ctas = E->n_sm * ctas_per_sm;
+  // a full grid whenever there is at least one slab per warp; the kernels split the slabs evenly over its warps
   int64_t ctas = std::min<int64_t>(max_ctas, (slabs + kWarpsPerCta - 1) / kWarpsPerCta);
-  ctas = std::max<int64_t>(ctas, 1);
-  ex.slabs_per_warp = (int)((slabs + ctas * kWarpsPerCta - 1) / (ctas * kWarpsPerCta));
-  ex.slabs_per_warp = std::max(ex.slabs_per_warp, 1);
-  ex.grid = (int)((slabs + (int64_t)ex.slabs_per_warp * kWarpsPerCta - 1) / ((int64_t)ex.slabs_per_warp * kWarpsPerCta));
-  ex.grid = std::max(ex.grid, 1);
+  ex.grid = (int)std::max<int64_t>(ctas, 1);
+  ex.slabs_per_warp = (int)slabs;  // = total slabs (kernel argument)
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
   // reduction parts: ~256 record slots (8 CTAs) each, so no (key, part) CTA walks more than a handful of records

@@ -267,7 +267,7 @@ __device__ __forceinline__ double warp_transpose_reduce24(const double (&v)[24],
 // masked lanes with a zero scale.  The loads of the next slab are issued before the DMMA phase of the current one.
 template <bool JAC, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
+loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   if (pp.ctl && pp.ctl[0]) return;
   extern __shared__ double smem[];
   double* rest;
@@ -279,7 +279,10 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
-  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  // balanced contiguous split of the slabs over all warps of the grid (sizes differ by at most one)
+  const int64_t n_warps_grid = (int64_t)gridDim.x * WARPS;
+  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
+  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   // software pipeline registers (next slab)
   int64_t n_t = kDropped;
   double n_p0 = 0, n_p1 = 0, n_p2 = 0, n_g0 = 0, n_g1 = 0, n_g2 = 0, n_g3 = 0, n_g4 = 0, n_g5 = 0;
@@ -294,10 +297,14 @@ loam_kernel(LoamStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
       n_ty = st.type[idx];
     }
   };
-  prefetch(slab0 * 32 + lane);
+#ifndef CLIC_LOAM_PREFETCH
+#define CLIC_LOAM_PREFETCH 1
+#endif
+  if (CLIC_LOAM_PREFETCH) prefetch(slab0 * 32 + lane);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * 32 >= st.n) break;
-    const int64_t next_idx = (sl + 1 < slabs_per_warp) ? (slab0 + sl + 1) * 32 + lane : st.n;
+    if (!CLIC_LOAM_PREFETCH) prefetch((slab0 + sl) * 32 + lane);  // plain load at use (more resident warps hide it)
+    const int64_t next_idx = (CLIC_LOAM_PREFETCH && sl + 1 < slabs_per_warp) ? (slab0 + sl + 1) * 32 + lane : st.n;
     const int64_t t = n_t;
     int s = 0;
     double u = 0.0;
@@ -562,7 +569,7 @@ struct NullSink {
 //               (marg,  NT=5): [knots 0..23 | bg | ba | gravity 30..32 | toff 33 | r 34 | pad]
 template <bool JAC, bool MARG>
 __global__ void __launch_bounds__(kThreads, 1)
-imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
+imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   constexpr int NT = MARG ? 5 : 4;
   if (pp.ctl && pp.ctl[0]) return;
   extern __shared__ double smem[];
@@ -587,7 +594,9 @@ imu_kernel(ImuStream st, PassParams pp, int slabs_per_warp, RecordBuf rb) {
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
-  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  const int64_t n_warps_grid = (int64_t)gridDim.x * kWarpsPerCta;
+  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
+  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * 32 >= st.n) break;
     const int64_t idx = (slab0 + sl) * 32 + lane;
@@ -662,7 +671,7 @@ struct ImageStream {
 constexpr int kImageFactorsPerSlab = 16;
 template <bool JAC>
 __global__ void __launch_bounds__(kThreads, 1)
-image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, ImageShared sh) {
+image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, ImageShared sh) {
   constexpr int NT = 7;
   if (pp.ctl && pp.ctl[0]) return;
   extern __shared__ double smem[];
@@ -679,7 +688,9 @@ image_kernel(ImageStream st, PassParams pp, int slabs_per_warp, RecordBuf rb, Im
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
-  const int64_t slab0 = (int64_t)warp_global * slabs_per_warp;
+  const int64_t n_warps_grid = (int64_t)gridDim.x * kWarpsPerCta;
+  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
+  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * kImageFactorsPerSlab >= st.n) break;
     const int64_t idx = (slab0 + sl) * kImageFactorsPerSlab + (lane & 15);
