@@ -653,7 +653,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   const int* ctl_res = &B.st->skip_res;
   const int* ctl_jac = &B.st->skip_jac;
   const size_t sm_small = 1024 * sizeof(double);
-  size_t sm_step = (size_t)(512 + 2 * D) * sizeof(double);
+  size_t sm_step = (size_t)(512 + 2 * D + ((D + 7) / 8) * 64) * sizeof(double);
   int a_in_smem = 0;
   if (sm_step + (size_t)D * D * sizeof(double) <= 200 * 1024) {
     a_in_smem = 1;

@@ -95,6 +95,162 @@ __global__ void prior_kernel(const double* J0, const double* A, const double* r0
 
 namespace clic {
 
+// ---------------- dense FP64 Cholesky / triangular solves, one CTA, blocked by 8 ----------------
+// Right-looking, panel width kNB: (1) the kNB x kNB diagonal block is factored by warp 0 (warp-synchronous),
+// (2) the panel below it is solved row-parallel, (3) the trailing lower triangle is updated entry-parallel.
+// Three block-wide barriers per 8 columns instead of three per column.  A is n x n row-major (leading dimension ld),
+// in shared memory when it fits, else in L2-resident global scratch; only the lower triangle is referenced.
+constexpr int kNB = 8;
+
+// Warp 0, lane l < nb holds row l of the kNB x kNB diagonal block in registers; columns are eliminated with warp
+// shuffles (no shared-memory round trips on the serial critical path).  Writes L back and, if Li != nullptr, the
+// inverse of the block (row-major kNB x kNB, zero padded) used by the panel and triangular solves.
+__device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* Li, int* ok, int lane) {
+  const unsigned full = 0xffffffffu;
+  double a[kNB];
+#pragma unroll
+  for (int c = 0; c < kNB; c++) a[c] = (lane < nb && c <= lane) ? A[(size_t)(kb + lane) * ld + kb + c] : 0.0;
+#pragma unroll
+  for (int j = 0; j < kNB; j++) {
+    double d = __shfl_sync(full, a[j], j);
+    if (j < nb) {
+      if (!(d > 0.0) || !isfinite(d)) {
+        if (lane == 0) *ok = 0;
+        d = 1.0;
+      }
+    } else {
+      d = 1.0;
+    }
+    const double piv = sqrt(d), inv = 1.0 / piv;
+    if (lane == j) a[j] = piv; else if (lane > j) a[j] = a[j] * inv;
+    const double lij = a[j];
+#pragma unroll
+    for (int c = j + 1; c < kNB; c++) {
+      const double lcj = __shfl_sync(full, lij, c);
+      if (lane >= c) a[c] -= lij * lcj;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kNB; c++)
+    if (lane < nb && c <= lane) A[(size_t)(kb + lane) * ld + kb + c] = a[c];
+  if (Li) {
+    // lane l computes column l of L^-1 by forward substitution on e_l
+    double x[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; i++) {
+      const double lii = __shfl_sync(full, a[i], i);
+      double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; k++) {
+        const double lik = __shfl_sync(full, a[k], i);
+        if (k >= lane) acc -= lik * x[k];
+      }
+      x[i] = (i >= lane && i < nb) ? acc / lii : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < kNB; i++)
+      if (lane < kNB) Li[i * kNB + lane] = (lane < nb) ? x[i] : 0.0;
+  }
+}
+
+// Linv: nullptr (panel by substitution) or ceil(n/kNB) * 64 doubles receiving the inverses of the diagonal blocks.
+__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* Linv = nullptr) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int kb = 0; kb < n; kb += kNB) {
+    const int nb = min(kNB, n - kb);
+    double* Li = Linv ? Linv + (size_t)(kb / kNB) * kNB * kNB : nullptr;
+    if (tid < 32) warp_diag_block(A, ld, kb, nb, Li, ok, tid);
+    __syncthreads();
+    if (!*ok) return;
+    for (int i = kb + nb + tid; i < n; i += nt) {
+      double x[kNB];
+      if (Li) {  // L[i, panel] = A[i, panel] * Lkk^-T : x[c] = sum_{k <= c} A[i][kb+k] * Linv[c][k]
+        double ai[kNB];
+#pragma unroll
+        for (int k = 0; k < kNB; k++) ai[k] = k < nb ? A[(size_t)i * ld + kb + k] : 0.0;
+#pragma unroll
+        for (int c = 0; c < kNB; c++) {
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < kNB; k++)
+            if (k <= c) v += ai[k] * Li[c * kNB + k];
+          x[c] = v;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kNB; c++) {
+          if (c < nb) {
+            double v = A[(size_t)i * ld + kb + c];
+#pragma unroll
+            for (int k = 0; k < kNB; k++)
+              if (k < c) v -= x[k] * A[(size_t)(kb + c) * ld + kb + k];
+            x[c] = v / A[(size_t)(kb + c) * ld + kb + c];
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kNB; c++)
+        if (c < nb) A[(size_t)i * ld + kb + c] = x[c];
+    }
+    __syncthreads();
+    const int m = n - kb - nb;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = kb + nb + e / m, j = kb + nb + e % m;
+      if (j <= i) {
+        double acc = 0.0;
+        for (int c = 0; c < nb; c++) acc += A[(size_t)i * ld + kb + c] * A[(size_t)j * ld + kb + c];
+        A[(size_t)i * ld + j] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// y <- L^-1 y then y <- L^-T y (L from cta_cholesky with Linv), blocked by kNB: the diagonal step is an 8-lane
+// mat-vec with the block inverse, the off-diagonal update is row-parallel.
+__device__ __forceinline__ void cta_cholesky_solve(const double* A, int ld, int n, double* y, const double* Linv) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double t8[kNB];
+  for (int kb = 0; kb < n; kb += kNB) {
+    const int nb = min(kNB, n - kb);
+    const double* Li = Linv + (size_t)(kb / kNB) * kNB * kNB;
+    if (tid < kNB) {
+      double v = 0.0;
+      for (int c = 0; c < nb; c++) v += Li[tid * kNB + c] * y[kb + c];
+      t8[tid] = v;
+    }
+    __syncthreads();
+    if (tid < nb) y[kb + tid] = t8[tid];
+    for (int i = kb + nb + tid; i < n; i += nt) {
+      double acc = 0.0;
+      for (int c = 0; c < nb; c++) acc += A[(size_t)i * ld + kb + c] * t8[c];
+      y[i] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+    const int nb = min(kNB, n - kb);
+    const double* Li = Linv + (size_t)(kb / kNB) * kNB * kNB;
+    if (tid < kNB) {
+      double v = 0.0;
+      for (int c = 0; c < nb; c++) v += Li[c * kNB + tid] * y[kb + c];  // Lkk^-T
+      t8[tid] = v;
+    }
+    __syncthreads();
+    if (tid < nb) y[kb + tid] = t8[tid];
+    for (int i = tid; i < kb; i += nt) {
+      double acc = 0.0;
+      for (int c = 0; c < nb; c++) acc += A[(size_t)(kb + c) * ld + i] * t8[c];
+      y[i] -= acc;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace clic
+
+namespace clic {
+
 // ---------------- Levenberg-Marquardt on the device (Ceres 1.14 TrustRegionMinimizer semantics) ----------------
 // The constants are Ceres defaults (solver.h); the loop mirrors oracle/clic_oracle.cpp solve() line by line.
 struct LmConst {
@@ -334,7 +490,8 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   double* red = sh;               // 512 doubles of reduction scratch
   double* gs = sh + 512;          // D scaled gradient
   double* y = gs + D;             // D
-  double* A = a_in_smem ? (y + D) : B.A;
+  double* Linv = y + D;                 // ceil(D / 8) * 64 doubles: inverses of the diagonal blocks
+  double* A = a_in_smem ? (Linv + ((D + kNB - 1) / kNB) * kNB * kNB) : B.A;
   const double radius = s->radius;
   const int reuse = s->reuse_diagonal;
   // LevenbergMarquardtStrategy::ComputeStep: diagonal = clamp(diag(J~^T J~)), A = H~ + diag(diagonal / radius)
@@ -357,50 +514,18 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     A[e] = v;
   }
   __syncthreads();
-  // dense Cholesky A = L L^T (lower, in place), right-looking
+  // dense Cholesky A = L L^T (lower, in place), blocked right-looking (cta_cholesky)
   __shared__ int ok;
   if (tid == 0) ok = 1;
   __syncthreads();
-  for (int j = 0; j < D; j++) {
-    __shared__ double piv;
-    if (tid == 0) {
-      double d = A[(size_t)j * D + j];
-      if (!(d > 0.0) || !isfinite(d)) { ok = 0; d = 1.0; }
-      piv = sqrt(d);
-      A[(size_t)j * D + j] = piv;
-    }
-    __syncthreads();
-    if (!ok) break;
-    for (int i = j + 1 + tid; i < D; i += nt) A[(size_t)i * D + j] = A[(size_t)i * D + j] / piv;
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i
-    const int m = D - j - 1;
-    for (int e = tid; e < m * m; e += nt) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) A[(size_t)i * D + k] -= A[(size_t)i * D + j] * A[(size_t)k * D + j];
-    }
-    __syncthreads();
-  }
+  cta_cholesky(A, D, D, &ok, Linv);
   __syncthreads();
   int valid = ok;
   // forward / backward substitution: (L L^T) z = g~, step = -z
   if (valid) {
     for (int i = tid; i < D; i += nt) y[i] = gs[i];
     __syncthreads();
-    for (int j = 0; j < D; j++) {
-      if (tid == 0) y[j] = y[j] / A[(size_t)j * D + j];
-      __syncthreads();
-      const double yj = y[j];
-      for (int i = j + 1 + tid; i < D; i += nt) y[i] -= A[(size_t)i * D + j] * yj;
-      __syncthreads();
-    }
-    for (int j = D - 1; j >= 0; j--) {
-      if (tid == 0) y[j] = y[j] / A[(size_t)j * D + j];
-      __syncthreads();
-      const double yj = y[j];
-      for (int i = tid; i < j; i += nt) y[i] -= A[(size_t)j * D + i] * yj;
-      __syncthreads();
-    }
+    cta_cholesky_solve(A, D, D, y, Linv);
     double bad = 0.0;
     for (int i = tid; i < D; i += nt) {
       double v = -y[i];
@@ -576,30 +701,6 @@ __global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
 namespace clic {
 
 // ---------------- K8: marginalization (MarginalizationInfo::marginalize, marginalization_factor.cpp:150-276) ----------------
-// In-place lower Cholesky of the n x n block at A (leading dimension ld) by one CTA.  *ok = 0 on a non-positive pivot.
-__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  __shared__ double piv_s;
-  for (int j = 0; j < n; j++) {
-    if (tid == 0) {
-      double d = A[(size_t)j * ld + j];
-      if (!(d > 0.0) || !isfinite(d)) { *ok = 0; d = 1.0; }
-      piv_s = sqrt(d);
-      A[(size_t)j * ld + j] = piv_s;
-    }
-    __syncthreads();
-    const double piv = piv_s;
-    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * ld + j] = A[(size_t)i * ld + j] / piv;
-    __syncthreads();
-    const int m = n - j - 1;
-    for (int e = tid; e < m * m; e += nt) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j];
-    }
-    __syncthreads();
-  }
-}
-
 // Schur complement of the first m (dropped) tangent dimensions of the pos x pos system (A, b), then the prior's
 // square-root form.  The reference inverts A_mm and factors the result by symmetric eigendecompositions with an
 // eigenvalue cut of 1e-15 (":208-264"); for the positive-definite systems of a well-constrained window the Cholesky
