@@ -232,7 +232,7 @@ def main():
         opt.stream = C.c_void_p(stream.cuda_stream)
         est = E.TrajectoryEstimator(sw.window, opt, lib)
         est.SetFixedIndex(-1)
-        S.add_all_factors(est, srcs or sw, bias_factor=(rank == 0))
+        S.add_all_factors(est, srcs or sw, bias_factor=(rank == 0), count_dropped=(srcs is None))
         return est
 
     est = new_estimator()
@@ -327,6 +327,10 @@ def main():
     h2d = 0
     for name in ("lidar", "imu", "image"):
         d = dict(getattr(sw, name))
+        if name == "lidar":  # the packed input records of clic_add_loam_packed (what the C++ shim stages per call)
+            for k in ("t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point"):
+                d.pop(k)
+            d.update(S.pack_lidar(sw.lidar))
         for k, v in d.items():
             if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] > 16:
                 d[k], t = pinned(v)

@@ -701,8 +701,11 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   }
   LmState st;
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, E->stream));
+  int in_flags[2] = {0, 0};
+  CU(cudaMemcpyAsync(in_flags, E->d_flags.p, sizeof(in_flags), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
+  if (in_flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
   if (summary) {
     std::memset(summary, 0, sizeof(*summary));
     summary->iterations = st.iteration;
@@ -1102,11 +1105,8 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
       (rc = to_device(E, r_type, geo_type, n)))
     return rc;
-  // a missing geometry array is only legal when no record of that type exists; the kernel never reads it then
-  bool has_plane = false, has_line = false;
-  for (int64_t i = 0; i < n; i++) (geo_type[i] == CLIC_GEO_PLANE ? has_plane : has_line) = true;
-  if ((has_plane && !geo_plane) || (has_line && (!geo_normal || !geo_point)))
-    return fail(CLIC_ERR_BAD_ARGUMENT, "geometry array missing for a record type that is present");
+  // a missing geometry array is only legal when no record of that type exists: checked on the device by the prep
+  // kernel (flag word 1), reported by the next evaluate / solve
   if ((rc = to_device(E, r_plane, geo_plane, geo_plane ? 4 * n : 0)) ||
       (rc = to_device(E, r_normal, geo_normal, geo_normal ? 3 * n : 0)) ||
       (rc = to_device(E, r_gpoint, geo_point, geo_point ? 3 * n : 0)))
@@ -1120,12 +1120,74 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
       n, r_t.as<double>(), r_pt.as<double>(), r_type.as<int32_t>(), r_plane.as<double>(), r_normal.as<double>(),
       r_gpoint.as<double>(), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
       B->p[2].as<double>(), B->g[0].as<double>(), B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(),
-      B->g[4].as<double>(), B->g[5].as<double>(), B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>());
+      B->g[4].as<double>(), B->g[5].as<double>(), B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>(),
+      E->d_flags.as<int>() + 1);
   E->launches++;
-  unsigned long long dropped = 0;
-  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaStreamSynchronize(E->stream));  // also keeps the temporary raw buffers alive until the kernel is done
-  if (n_dropped) *n_dropped = (int64_t)dropped;
+  if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
+    unsigned long long dropped = 0;
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    *n_dropped = (int64_t)dropped;
+  }  // the temporary raw buffers are freed in stream order (cudaFreeAsync), no host wait needed
+  B->st.n = n;
+  B->st.t_ns = B->t_ns.as<int64_t>();
+  for (int k = 0; k < 3; k++) B->st.p[k] = B->p[k].as<double>();
+  for (int k = 0; k < 6; k++) B->st.g[k] = B->g[k].as<double>();
+  B->st.type = B->type.as<uint8_t>();
+  B->st.sh.S_GtoM = ldq(S_GtoM);
+  B->st.sh.p_GinM = ldv(p_GinM);
+  B->st.sh.S_LtoI = ldq(S_LtoI);
+  B->st.sh.p_LinI = ldv(p_LinI);
+  B->st.sh.weight = weight;
+  B->st.sh.gm_identity = S_GtoM[0] == 0.0 && S_GtoM[1] == 0.0 && S_GtoM[2] == 0.0 && S_GtoM[3] == 1.0 &&
+                         p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
+  B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
+  E->loam.push_back(std::move(B));
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                  const uint8_t* geo_type, const double* geo, const double S_GtoM[4],
+                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n_dropped) *n_dropped = 0;
+  if (n <= 0) return CLIC_OK;
+  if (!t_point || !point || !geo_type || !geo) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_packed: null array");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  std::unique_ptr<LoamBatch> B(new LoamBatch);
+  // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
+  const int S = CLIC_SENSOR_LIDAR;
+  int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  if (!E->opt.lock_t_offset[S]) {
+    t_min += E->opt.t_offset_padding_ns;
+    t_max -= E->opt.t_offset_padding_ns;
+  }
+  DevBuf r_t, r_pt, r_type, r_geo;
+  int rc;
+  if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
+      (rc = to_device(E, r_type, geo_type, n)) || (rc = to_device(E, r_geo, geo, 6 * n)))
+    return rc;
+  CU(B->t_ns.ensure(n * sizeof(int64_t)));
+  for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
+  for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
+  CU(B->type.ensure(n));
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+      n, r_t.as<double>(), r_pt.as<double>(), r_type.as<uint8_t>(), r_geo.as<double>(), t_min, t_max,
+      B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
+      B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
+      B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>());
+  E->launches++;
+  if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
+    unsigned long long dropped = 0;
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    *n_dropped = (int64_t)dropped;
+  }  // the temporary raw buffers are freed in stream order (cudaFreeAsync), no host wait needed
   B->st.n = n;
   B->st.t_ns = B->t_ns.as<int64_t>();
   for (int k = 0; k < 3; k++) B->st.p[k] = B->p[k].as<double>();
@@ -1174,10 +1236,12 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
       B->gy[0].as<double>(), B->gy[1].as<double>(), B->gy[2].as<double>(), B->ac[0].as<double>(),
       B->ac[1].as<double>(), B->ac[2].as<double>(), E->d_counter.as<unsigned long long>());
   E->launches++;
-  unsigned long long dropped = 0;
-  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaStreamSynchronize(E->stream));
-  if (n_dropped) *n_dropped = (int64_t)dropped;
+  if (n_dropped) {
+    unsigned long long dropped = 0;
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    *n_dropped = (int64_t)dropped;
+  }
   B->st.n = n;
   B->st.t_ns = B->t_ns.as<int64_t>();
   for (int k = 0; k < 3; k++) {
@@ -1269,10 +1333,13 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
       B->ti.as<int64_t>(), B->tj.as<int64_t>(), B->pi[0].as<double>(), B->pi[1].as<double>(), B->pi[2].as<double>(),
       B->pj[0].as<double>(), B->pj[1].as<double>(), E->d_counter.as<unsigned long long>());
   E->launches++;
-  unsigned long long dropped = 0;
-  CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaStreamSynchronize(E->stream));
-  if (n_dropped) *n_dropped = (int64_t)dropped;
+  // the sorted staging vectors above are pageable host memory: cudaMemcpyAsync from them is staged before it returns
+  if (n_dropped) {
+    unsigned long long dropped = 0;
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    *n_dropped = (int64_t)dropped;
+  }
   B->st.n = n;
   B->st.ti_ns = B->ti.as<int64_t>();
   B->st.tj_ns = B->tj.as<int64_t>();
@@ -1377,7 +1444,10 @@ CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost
   if (H && D > 0) CU(cudaMemcpyAsync(H, E->H_glb(), (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   if (b && D > 0) CU(cudaMemcpyAsync(b, E->b_glb(), (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaMemcpyAsync(c2, E->cost_glb(), sizeof(c2), cudaMemcpyDeviceToHost, E->stream));
+  int flags[2] = {0, 0};
+  CU(cudaMemcpyAsync(flags, E->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
+  if (flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
   if (cost) *cost = c2[0];
   if (fixed_cost) *fixed_cost = c2[1];
   return CLIC_OK;

@@ -930,7 +930,7 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
                                  const double* geo_plane, const double* geo_normal, const double* geo_point,
                                  int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0, double* p1, double* p2,
                                  double* g0, double* g1, double* g2, double* g3, double* g4, double* g5, uint8_t* type,
-                                 unsigned long long* n_dropped) {
+                                 unsigned long long* n_dropped, int* bad_input) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t t = (int64_t)(t_s[i] * 1e9);
@@ -940,6 +940,12 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
   p0[i] = point[3 * i]; p1[i] = point[3 * i + 1]; p2[i] = point[3 * i + 2];
   const bool plane = geo_type[i] == 1;
   type[i] = plane ? 1 : 0;
+  if ((plane && !geo_plane) || (!plane && (!geo_normal || !geo_point))) {  // record type present, its array missing
+    *bad_input = 1;
+    t_ns[i] = kDropped;
+    g0[i] = g1[i] = g2[i] = g3[i] = g4[i] = g5[i] = 0.0;
+    return;
+  }
   if (plane) {
     g0[i] = geo_plane[4 * i]; g1[i] = geo_plane[4 * i + 1]; g2[i] = geo_plane[4 * i + 2]; g3[i] = geo_plane[4 * i + 3];
     g4[i] = 0.0; g5[i] = 0.0;
@@ -947,6 +953,22 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
     g0[i] = geo_point[3 * i]; g1[i] = geo_point[3 * i + 1]; g2[i] = geo_point[3 * i + 2];
     g3[i] = geo_normal[3 * i]; g4[i] = geo_normal[3 * i + 1]; g5[i] = geo_normal[3 * i + 2];
   }
+}
+
+__global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const double* point, const uint8_t* geo_type,
+                                        const double* geo, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
+                                        double* p1, double* p2, double* g0, double* g1, double* g2, double* g3,
+                                        double* g4, double* g5, uint8_t* type, unsigned long long* n_dropped) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = (int64_t)(t_s[i] * 1e9);
+  bool ok = !(t < t_lo || t >= t_hi);
+  t_ns[i] = ok ? t : kDropped;
+  if (!ok) atomicAdd(n_dropped, 1ULL);
+  p0[i] = point[3 * i]; p1[i] = point[3 * i + 1]; p2[i] = point[3 * i + 2];
+  type[i] = geo_type[i] == 1 ? 1 : 0;
+  g0[i] = geo[6 * i]; g1[i] = geo[6 * i + 1]; g2[i] = geo[6 * i + 2];
+  g3[i] = geo[6 * i + 3]; g4[i] = geo[6 * i + 4]; g5[i] = geo[6 * i + 5];
 }
 
 __global__ void prep_imu_kernel(int64_t n, const double* t_s, const double* gyro, const double* accel, int64_t t_lo,

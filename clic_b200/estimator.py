@@ -149,7 +149,8 @@ class TrajectoryEstimator:
 
     # ---- trajectory_estimator.h:188-193 (batched) ----
     def AddLoamMeasurementAnalytic(self, t_point, point, geo_type, geo_plane, geo_normal, geo_point, S_GtoM, p_GinM,
-                                   S_LtoI, p_LinI, weight, marg_this_factor=False):
+                                   S_LtoI, p_LinI, weight, marg_this_factor=False, count_dropped=True):
+        """count_dropped=False keeps the call asynchronous (no read-back of the number of dropped measurements)."""
         t_point, point = f64(t_point), f64(point)
         geo_type = i32(geo_type)
         geo_plane, geo_normal, geo_point = f64(geo_plane), f64(geo_normal), f64(geo_point)
@@ -158,16 +159,31 @@ class TrajectoryEstimator:
         _check(self.lib, self.lib.clic_add_loam(self.h, len(t_point), dptr(t_point), dptr(point), iptr(geo_type),
                                                 dptr(geo_plane), dptr(geo_normal), dptr(geo_point), dptr(S_GtoM),
                                                 dptr(p_GinM), dptr(S_LtoI), dptr(p_LinI), float(weight),
-                                                int(bool(marg_this_factor)), C.byref(dropped)))
+                                                int(bool(marg_this_factor)),
+                                                C.byref(dropped) if count_dropped else None))
+        return dropped.value
+
+    def AddLoamMeasurementPacked(self, t_point, point, geo_type_u8, geo6, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                                 marg_this_factor=False, count_dropped=True):
+        """Packed input of the same factors: geo_type as uint8, geo6 = plane (n, d, 0, 0) | line (point, direction)."""
+        t_point, point, geo6 = f64(t_point), f64(point), f64(geo6)
+        geo_type_u8 = np.ascontiguousarray(geo_type_u8, dtype=np.uint8)
+        S_GtoM, p_GinM, S_LtoI, p_LinI = f64(S_GtoM), f64(p_GinM), f64(S_LtoI), f64(p_LinI)
+        dropped = C.c_int64(0)
+        _check(self.lib, self.lib.clic_add_loam_packed(
+            self.h, len(t_point), dptr(t_point), dptr(point), geo_type_u8.ctypes.data_as(C.POINTER(C.c_uint8)),
+            dptr(geo6), dptr(S_GtoM), dptr(p_GinM), dptr(S_LtoI), dptr(p_LinI), float(weight),
+            int(bool(marg_this_factor)), C.byref(dropped) if count_dropped else None))
         return dropped.value
 
     # ---- trajectory_estimator.h:153-156 (batched; gravity is the window's) ----
-    def AddIMUMeasurementAnalytic(self, timestamp, gyro, accel, bias_slot, info_vec, marg_this_factor=False):
+    def AddIMUMeasurementAnalytic(self, timestamp, gyro, accel, bias_slot, info_vec, marg_this_factor=False,
+                                  count_dropped=True):
         timestamp, gyro, accel, info_vec = f64(timestamp), f64(gyro), f64(accel), f64(info_vec)
         dropped = C.c_int64(0)
         _check(self.lib, self.lib.clic_add_imu(self.h, len(timestamp), dptr(timestamp), dptr(gyro), dptr(accel),
                                                int(bias_slot), dptr(info_vec), int(bool(marg_this_factor)),
-                                               C.byref(dropped)))
+                                               C.byref(dropped) if count_dropped else None))
         return dropped.value
 
     # ---- trajectory_estimator.h:159-162 ----
@@ -177,13 +193,14 @@ class TrajectoryEstimator:
                                                 int(bool(marg_this_factor)), int(bool(marg_all_bias))))
 
     # ---- trajectory_estimator.h:196-199 (batched) ----
-    def AddImageFeatureAnalytic(self, ti, pi, tj, pj, landmark, fixed_depth=True, marg_this_feature=False):
+    def AddImageFeatureAnalytic(self, ti, pi, tj, pj, landmark, fixed_depth=True, marg_this_feature=False,
+                                count_dropped=True):
         ti, pi, tj, pj = f64(ti), f64(pi), f64(tj), f64(pj)
         landmark = i32(landmark)
         dropped = C.c_int64(0)
         _check(self.lib, self.lib.clic_add_image(self.h, len(ti), dptr(ti), dptr(pi), dptr(tj), dptr(pj),
                                                  iptr(landmark), int(bool(fixed_depth)), int(bool(marg_this_feature)),
-                                                 C.byref(dropped)))
+                                                 C.byref(dropped) if count_dropped else None))
         return dropped.value
 
     # ---- trajectory_estimator.h:207-209 ----

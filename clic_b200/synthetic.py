@@ -275,22 +275,36 @@ def make_window(n_knots=10, n_lidar=2000, n_imu=200, n_landmarks=0, obs_per_land
     return sw
 
 
-def add_all_factors(est, sw, marg=False, fixed_depth=True, bias_factor=True):
+def pack_lidar(L):
+    """PointCorrespondence field arrays -> the packed input of clic_add_loam_packed."""
+    plane = L["geo_type"] == GEO_PLANE
+    geo6 = np.where(plane[:, None], np.concatenate([L["geo_plane"], np.zeros((len(plane), 2))], axis=1),
+                    np.concatenate([L["geo_point"], L["geo_normal"]], axis=1))
+    return dict(t_point=L["t_point"], point=L["point"], geo_type_u8=L["geo_type"].astype(np.uint8),
+                geo6=np.ascontiguousarray(geo6))
+
+
+def add_all_factors(est, sw, marg=False, fixed_depth=True, bias_factor=True, count_dropped=True):
     """Feed a synthetic window to an estimator in the reference's call order
     (trajectory_manager.cpp:682-750: LiDAR, image, IMU, bias)."""
     dropped = 0
-    if len(sw.lidar.get("t_point", ())):
+    if len(sw.lidar.get("t_point", ())) and "geo6" in sw.lidar:
+        L = sw.lidar
+        dropped += est.AddLoamMeasurementPacked(L["t_point"], L["point"], L["geo_type_u8"], L["geo6"], L["S_GtoM"],
+                                                L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
+    elif len(sw.lidar.get("t_point", ())):
         L = sw.lidar
         dropped += est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"],
                                                   L["geo_normal"], L["geo_point"], L["S_GtoM"], L["p_GinM"],
-                                                  L["S_LtoI"], L["p_LinI"], L["weight"], marg)
+                                                  L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
     if len(sw.image.get("t_i", ())):
         I = sw.image
-        dropped += est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], fixed_depth, marg)
+        dropped += est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], fixed_depth, marg,
+                                               count_dropped)
     if len(sw.imu.get("timestamp", ())):
         M = sw.imu
         dropped += est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], M["bias_slot"],
-                                                 M["info_vec"], marg)
+                                                 M["info_vec"], marg, count_dropped)
     nb = sw.window.bias.shape[0]
     if bias_factor and nb >= 2:
         # trajectory_manager.cpp:738-750: cov = delta_time/dt * dt^2, sqrt_info = bias_info_vec / sqrt(cov), dt arg = 1

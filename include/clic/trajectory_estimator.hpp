@@ -173,10 +173,16 @@ class TrajectoryEstimator {
     LoamBatch& b = loam_.back();
     b.t.push_back(pc.t_point);
     b.point.insert(b.point.end(), pc.point.begin(), pc.point.end());
-    b.type.push_back((int32_t)pc.geo_type);
-    b.plane.insert(b.plane.end(), pc.geo_plane.begin(), pc.geo_plane.end());
-    b.normal.insert(b.normal.end(), pc.geo_normal.begin(), pc.geo_normal.end());
-    b.gpoint.insert(b.gpoint.end(), pc.geo_point.begin(), pc.geo_point.end());
+    b.type.push_back((uint8_t)pc.geo_type);
+    // packed geometry record of clic_add_loam_packed: plane (n, d, 0, 0) | line (point, direction)
+    if (pc.geo_type == Plane) {
+      b.geo.insert(b.geo.end(), pc.geo_plane.begin(), pc.geo_plane.end());
+      b.geo.push_back(0.0);
+      b.geo.push_back(0.0);
+    } else {
+      b.geo.insert(b.geo.end(), pc.geo_point.begin(), pc.geo_point.end());
+      b.geo.insert(b.geo.end(), pc.geo_normal.begin(), pc.geo_normal.end());
+    }
   }
 
   // trajectory_estimator.h:196-199
@@ -260,8 +266,8 @@ class TrajectoryEstimator {
 
  private:
   struct LoamBatch {
-    std::vector<double> t, point, plane, normal, gpoint;
-    std::vector<int32_t> type;
+    std::vector<double> t, point, geo;
+    std::vector<uint8_t> type;
     SO3d S_GtoM, S_LtoI;
     Vec3d p_GinM{}, p_LinI{};
     double weight = 1;
@@ -365,9 +371,9 @@ class TrajectoryEstimator {
     for (auto& p : priors_)
       check(clic_add_prior(h_, p.info->prior, (int32_t)p.drop.size(), p.drop.empty() ? nullptr : p.drop.data()));
     for (auto& b : loam_)
-      check(clic_add_loam(h_, (int64_t)b.t.size(), b.t.data(), b.point.data(), b.type.data(), b.plane.data(),
-                          b.normal.data(), b.gpoint.data(), b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(),
-                          b.p_LinI.data(), b.weight, b.marg, nullptr));
+      check(clic_add_loam_packed(h_, (int64_t)b.t.size(), b.t.data(), b.point.data(), b.type.data(), b.geo.data(),
+                                 b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
+                                 nullptr));
     for (auto& b : image_)
       check(clic_add_image(h_, (int64_t)b.ti.size(), b.ti.data(), b.pi.data(), b.tj.data(), b.pj.data(), b.lm.data(),
                            b.fixed, b.marg, nullptr));

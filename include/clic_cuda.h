@@ -176,6 +176,14 @@ CLIC_API int clic_add_loam(clic_estimator* h, int64_t n, const double* t_point, 
                            const double p_LinI[3], double weight, int32_t marg_this_factor,
                            int64_t* n_dropped);
 
+/* Same factors, packed input (81 instead of 116 bytes per record over PCIe): geo_type as one byte, and one
+ * 6-double geometry record per feature — plane: (n.x, n.y, n.z, d, 0, 0) = geo_plane; line: (geo_point, geo_normal).
+ * This is what include/clic/trajectory_estimator.hpp stages per AddLoamMeasurementAnalytic call. */
+CLIC_API int clic_add_loam_packed(clic_estimator* h, int64_t n, const double* t_point, const double* point /*3n*/,
+                                  const uint8_t* geo_type, const double* geo /*6n*/, const double S_GtoM[4],
+                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped);
+
 /* AddIMUMeasurementAnalytic (trajectory_estimator.cpp:369-455), batched over IMUData
  * (parameter_struct.h:52-58).  All samples of one call share a bias slot, like the reference's
  * call sites (trajectory_manager.cpp:731-735).  Loss CauchyLoss(marg ? 3 : 10) (":426-430"). */

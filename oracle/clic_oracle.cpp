@@ -1110,6 +1110,24 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   return CLIC_OK;
 }
 
+CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                  const uint8_t* geo_type, const double* geo, const double S_GtoM[4],
+                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped) {
+  std::vector<int32_t> type(n);
+  std::vector<double> plane(4 * (size_t)n), normal(3 * (size_t)n), gpoint(3 * (size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    type[i] = geo_type[i];
+    for (int k = 0; k < 4; k++) plane[4 * i + k] = geo[6 * i + k];
+    for (int k = 0; k < 3; k++) {
+      gpoint[3 * i + k] = geo[6 * i + k];
+      normal[3 * i + k] = geo[6 * i + 3 + k];
+    }
+  }
+  return clic_add_loam(E, n, t_point, point, type.data(), plane.data(), normal.data(), gpoint.data(), S_GtoM, p_GinM,
+                       S_LtoI, p_LinI, weight, marg_this_factor, n_dropped);
+}
+
 CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp, const double* gyro,
                           const double* accel, int32_t bias_slot, const double info_vec[6],
                           int32_t marg_this_factor, int64_t* n_dropped) {

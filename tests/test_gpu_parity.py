@@ -187,3 +187,27 @@ def test_visual_unsorted_and_fixed_knots(cuda, oracle):
     for k in ("t_i", "p_i", "t_j", "p_j", "landmark"):
         sw.image[k] = np.ascontiguousarray(sw.image[k][perm])
     compare_eval(cuda, oracle, sw, fixed=4)
+
+
+@pytest.mark.gpu
+def test_packed_lidar_input_is_identical(cuda):
+    """clic_add_loam_packed (81 B/record) builds bit-identical normal equations to clic_add_loam."""
+    sw = S.make_window(12, n_lidar=5000, n_imu=0, line_fraction=0.4, seed=77)
+    L = sw.lidar
+    out = []
+    for packed in (False, True):
+        est = E.TrajectoryEstimator(sw.window, E.default_options(cuda), cuda)
+        est.SetFixedIndex(1)
+        if packed:
+            P = S.pack_lidar(L)
+            nd = est.AddLoamMeasurementPacked(P["t_point"], P["point"], P["geo_type_u8"], P["geo6"], L["S_GtoM"],
+                                              L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"])
+        else:
+            nd = est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"],
+                                                L["geo_normal"], L["geo_point"], L["S_GtoM"], L["p_GinM"],
+                                                L["S_LtoI"], L["p_LinI"], L["weight"])
+        out.append((nd,) + tuple(est.Evaluate()))
+        est.close()
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
