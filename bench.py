@@ -240,6 +240,15 @@ def main():
         est.comm_init_torch(dist, rank, world)
     D = est.layout().D
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush_mode = os.environ.get("CLIC_BENCH_FLUSH", "write")
+
+    def flush_l2():
+        """Evict the 126 MB L2 between timed iterations (outside the timed events)."""
+        if flush_mode == "none":
+            return
+        flush.fill_(1)
+        if flush_mode == "write_read":  # drain the dirty lines the write left behind: cold AND clean L2
+            flush.view(torch.int64).sum()
 
     def barrier():
         if world > 1:
@@ -255,7 +264,7 @@ def main():
         launches0 = est.num_kernel_launches()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for a, b in ev:
-            flush.fill_(1)  # evict the 126 MB L2 between timed iterations (not timed)
+            flush_l2()
             a.record(stream)
             est.linearize_async(1)
             b.record(stream)
@@ -266,7 +275,7 @@ def main():
         # kept out of the timed region above): per-class times for the roofline line
         est.profile_enable(True)
         for _ in range(args.steps):
-            flush.fill_(1)
+            flush_l2()
             est.linearize_async(1)
         barrier()
         prof_ms, prof_n = est.profile_read()
@@ -309,7 +318,7 @@ def main():
             barrier()
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
             for a, b in evs:
-                flush.fill_(1)
+                flush_l2()
                 a.record(stream)
                 es.linearize_async(1)
                 b.record(stream)
@@ -340,7 +349,7 @@ def main():
     h2d += 8 * (7 * sw.window.n_knots + sw.window.bias.size + 6)
     e2e_steps = max(3, min(args.steps, 10))
     with torch.cuda.stream(stream):
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             e = new_estimator(src)
             e.Evaluate()
             e.close()
@@ -350,11 +359,16 @@ def main():
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
             e = new_estimator(src)
+            t2 = time.perf_counter()
             if world > 1:
                 e.comm_init_torch(dist, rank, world)
             H, b, cost, _ = e.Evaluate()
+            t3 = time.perf_counter()
             e.close()
             e2e_each.append((time.perf_counter() - t1) * 1e3)
+            if os.environ.get("CLIC_BENCH_E2E_TRACE"):
+                print("e2e trace ms: create+add %.2f evaluate %.2f close %.2f" % (
+                    (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3), file=sys.stderr)
         barrier()
         e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -5,10 +5,13 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/clic_cuda.h"
@@ -101,12 +104,36 @@ struct AllocScope {  // every ABI entry point that may allocate names the estima
   ~AllocScope() { g_alloc_stream = prev; }
 };
 
+// CLIC_TRACE=1: host time of every traced ABI call (stderr), for chasing host-side stalls.
+struct ScopedTrace {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  static bool on() { static const bool v = getenv("CLIC_TRACE") != nullptr; return v; }
+  explicit ScopedTrace(const char* n) : name(n) { if (on()) t0 = std::chrono::steady_clock::now(); }
+  void lap(const char* what) {
+    if (!on()) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[clic trace] %s/%s %.3f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+  ~ScopedTrace() { lap("end"); }
+};
+
 // Launch geometry + record buffers of one factor stream.
 struct StreamExec {
   int64_t n = 0;
   int grid = 0, slabs_per_warp = 0, n_warps = 0, warps_per_cta = kWarpsPerCta;
   int NT = 4, rd = 640, n_keys = 0, P = 8;
   DevBuf payload, key, cost, part, overflow;
+  DevBuf fin, ticket;  // solve path: per-key final blocks and the last-part tickets of reduce_all_kernel
+  // The adders upload on the estimator's copy stream; `ready` marks the batch complete there and the compute stream
+  // waits for it once, right before the first kernel that reads the batch (H2D of later batches overlaps compute).
+  cudaEvent_t ready = nullptr;
+  bool ready_waited = true;
+  StreamExec() = default;
+  StreamExec(const StreamExec&) = delete;
+  StreamExec& operator=(const StreamExec&) = delete;
+  ~StreamExec() { if (ready) cudaEventDestroy(ready); }
   int* overflow_flag = nullptr;
   RecordBuf rb() const {
     RecordBuf r;
@@ -122,18 +149,22 @@ struct StreamExec {
 struct LoamBatch {
   LoamStream st;
   DevBuf t_ns, p[3], g[6], type;
+  DevBuf raw[6];  // the arrays as uploaded (kept until destroy, see the adders)
   int marg = 0;
   StreamExec ex;
 };
 struct ImuBatch {
   ImuStream st;
   DevBuf t_ns, gy[3], ac[3];
+  DevBuf raw[3];
   int marg = 0;
   StreamExec ex;
 };
 struct ImageBatch {
   ImageStream st;
   DevBuf ti, tj, pi[3], pj[2], lm;
+  DevBuf raw[4];
+  DevBuf id_i, id_j, pack_t;  // pose packs (st.n_packs > 0)
   std::vector<int64_t> perm;  // sorted position -> add order
   int marg = 0;
   StreamExec ex;
@@ -166,6 +197,7 @@ struct clic_estimator {
   StateLayout sl;
   std::vector<double> h_state;  // host mirror used only for the add-time window test (needs t_offset)
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of measurement batches + their prep kernels (process-wide, per device)
   bool own_stream = false;
   int device = 0, n_sm = 148;
   DevBuf d_state, d_cand, d_flags, d_counter;
@@ -197,6 +229,9 @@ struct clic_estimator {
   bool layout_dirty = true;
   clic_layout L;
   int n_desc = 0;
+  DevBuf d_jobs;
+  bool packs_fit = true;  // the packed visual kernel's shared memory fits this window
+  int n_jobs = 0, n_part_ctas = 0;
   int64_t launches = 0;
   bool bounds_toff[3] = {false, false, false};
   double toff_lo[3], toff_hi[3];
@@ -282,6 +317,11 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
   CU(ex.part.ensure((size_t)ex.n_keys * ex.P * ex.rd * sizeof(double)));
   CU(ex.overflow.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
+  CU(ex.fin.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
+  CU(ex.ticket.ensure((size_t)ex.n_keys * sizeof(unsigned)));
+  // reduce_all_kernel folds the atomics-fallback block into fin and re-zeroes it, and re-arms the tickets
+  CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), g_alloc_stream));
+  CU(cudaMemsetAsync(ex.ticket.p, 0, (size_t)ex.n_keys * sizeof(unsigned), g_alloc_stream));
   ex.overflow_flag = E->d_flags.as<int>();
   return CLIC_OK;
 }
@@ -293,10 +333,35 @@ size_t factor_smem_bytes(int K, int NT) {
   return (window_smem_doubles(K) + jt) * sizeof(double);
 }
 
+size_t image_smem_bytes(int K, int n_packs) {
+  return factor_smem_bytes(K, 7) + (size_t)n_packs * kPackDoubles * sizeof(double);
+}
+
 size_t loam_smem_bytes(int K) {
   size_t jt = (size_t)kLoamWarps * 24 * kJtStride;
   jt = std::max<size_t>(jt, (size_t)rec_doubles(3, 1));
   return (window_smem_doubles(K) + jt) * sizeof(double);
+}
+
+// End of an adder: the batch is complete on the copy stream when `ready` fires.
+int mark_ready(clic_estimator* E, StreamExec& ex) {
+  if (!ex.ready) CU(cudaEventCreateWithFlags(&ex.ready, cudaEventDisableTiming));
+  CU(cudaEventRecord(ex.ready, E->copy_stream));
+  ex.ready_waited = false;
+  return CLIC_OK;
+}
+int wait_ready(clic_estimator* E, StreamExec& ex) {
+  if (ex.ready_waited) return CLIC_OK;
+  CU(cudaStreamWaitEvent(E->stream, ex.ready, 0));
+  ex.ready_waited = true;
+  return CLIC_OK;
+}
+int join_adds(clic_estimator* E) {
+  int rc;
+  for (auto& b : E->loam) if ((rc = wait_ready(E, b->ex))) return rc;
+  for (auto& b : E->imu) if ((rc = wait_ready(E, b->ex))) return rc;
+  for (auto& b : E->image) if ((rc = wait_ready(E, b->ex))) return rc;
+  return CLIC_OK;
 }
 
 // Column maps + stream descriptors for assemble_kernel.
@@ -321,12 +386,30 @@ int ensure_layout(clic_estimator* E) {
   CU(cudaMemcpyAsync(E->d_col_knot.p, col_knot.data(), D * sizeof(int), cudaMemcpyHostToDevice, E->stream));
   CU(cudaMemcpyAsync(E->d_col_sub.p, col_sub.data(), D * sizeof(int), cudaMemcpyHostToDevice, E->stream));
   std::vector<StreamDesc> descs;
+  std::vector<ReduceJob> jobs;
+  int n_part_ctas = 0;
+  auto add_job = [&](StreamExec& ex) {
+    ReduceJob j{};
+    j.payload = ex.payload.as<double>();
+    j.key = ex.key.as<int>();
+    j.part = ex.part.as<double>();
+    j.fin = ex.fin.as<double>();
+    j.overflow = ex.overflow.as<double>();
+    j.warp_cost = ex.cost.as<double>();
+    j.ticket = ex.ticket.as<unsigned>();
+    j.n_slots = ex.n_warps * kSlotsPerWarp;
+    j.P = ex.P; j.n_keys = ex.n_keys; j.rd = ex.rd; j.n_warps = ex.n_warps;
+    j.cta0 = n_part_ctas;
+    n_part_ctas += ex.n_keys * ex.P;
+    jobs.push_back(j);
+  };
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.part.as<double>();
-    d.overflow = b->ex.overflow.as<double>();
-    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
+    d.overflow = nullptr;
+    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    add_job(b->ex);
     d.r_col = -1;
     d.b_off = 384;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
@@ -339,9 +422,10 @@ int ensure_layout(clic_estimator* E) {
   for (auto& b : E->imu) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.part.as<double>();
-    d.overflow = b->ex.overflow.as<double>();
-    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
+    d.overflow = nullptr;
+    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    add_job(b->ex);
     d.r_col = 31;
     d.b_off = -1;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)(l < 32 ? imu_phys_col<false>(l) : l);
@@ -359,9 +443,10 @@ int ensure_layout(clic_estimator* E) {
   for (auto& b : E->image) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.part.as<double>();
-    d.overflow = b->ex.overflow.as<double>();
-    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
+    d.overflow = nullptr;
+    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    add_job(b->ex);
     d.r_col = 49;
     d.b_off = -1;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
@@ -376,6 +461,11 @@ int ensure_layout(clic_estimator* E) {
   CU(E->d_descs.ensure(std::max<size_t>(1, descs.size()) * sizeof(StreamDesc)));
   if (!descs.empty())
     CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
+  E->n_jobs = (int)jobs.size();
+  E->n_part_ctas = n_part_ctas;
+  CU(E->d_jobs.ensure(std::max<size_t>(1, jobs.size()) * sizeof(ReduceJob)));
+  if (!jobs.empty())
+    CU(cudaMemcpyAsync(E->d_jobs.p, jobs.data(), jobs.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice, E->stream));
   CU(E->d_nrm_loc.ensure(((size_t)D * D + D + 8) * sizeof(double)));
   if (E->use_comm) CU(E->d_nrm_glb.ensure(((size_t)D * D + D + 8) * sizeof(double)));
   CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
@@ -472,25 +562,12 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   double* cost2 = E->cost_loc() + 2 * which;  // slot 0: pass at x, slot 1: pass at the LM candidate
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
-  bool first = true;  // the first stream of the pass stores cost2, the others add to it
-  auto finish_stream = [&](StreamExec& ex) -> int {
-    E->prof_begin(3);
-    if (jac) {
-      if (launch_reduce(E, ex, cost2, first, ctl)) return fail(CLIC_ERR_CUDA, "reduce launch");
-    } else {
-      reduce_cost_kernel<<<1, 256, 0, E->stream>>>(ex.cost.as<double>(), ex.n_warps, cost2, first ? 0 : 1, ctl);
-    }
-    E->prof_end();
-    E->launches += 1;
-    first = false;
-    return CLIC_OK;
-  };
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
+    if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = loam_smem_bytes(E->K);
     if (jac) {
-      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
       E->prof_begin(0);
       loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
@@ -501,14 +578,13 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_end();
       E->launches += 1;
     }
-    if ((rc = finish_stream(ex))) return rc;
   }
   for (auto& b : E->imu) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
+    if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 4);
     if (jac) {
-      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
       E->prof_begin(1);
       imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
       E->prof_end();
@@ -519,11 +595,11 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_end();
       E->launches += 1;
     }
-    if ((rc = finish_stream(ex))) return rc;
   }
   for (auto& b : E->image) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
+    if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 7);
     ImageShared ish;
     ish.S_CtoI = ldq(E->S_CtoI);
@@ -532,24 +608,25 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     ish.loss_a = b->st.loss_a;
     ish.inv_dt = 1e9 / double(E->dt_ns);
     ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
-    if (jac) {
-      CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
-      E->prof_begin(2);
-      image_kernel<true><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
-      E->prof_end();
-      E->launches += 1;
-    } else {
-      E->prof_begin(2);
-      image_kernel<false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
-      E->prof_end();
-      E->launches += 1;
-    }
-    if ((rc = finish_stream(ex))) return rc;
-  }
-  if (first) {  // no factor stream at all (prior-only problem)
-    zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
+    const bool packed = b->st.n_packs > 0;
+    const size_t smem_p = image_smem_bytes(E->K, b->st.n_packs);
+    E->prof_begin(2);
+    if (jac && packed) image_kernel<true, true><<<ex.grid, kThreads, smem_p, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    else if (jac) image_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    else if (packed) image_kernel<false, true><<<ex.grid, kThreads, smem_p, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    else image_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    E->prof_end();
     E->launches += 1;
   }
+  if (E->n_jobs == 0) {  // no factor stream at all (prior-only problem)
+    zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
+  } else {  // every stream's records -> per-key blocks, and the pass cost, in one launch (cost only without jac)
+    const int part_ctas = jac ? E->n_part_ctas : 0;
+    E->prof_begin(3);
+    reduce_all_kernel<<<part_ctas + 1, 256, 0, E->stream>>>(E->d_jobs.as<ReduceJob>(), E->n_jobs, part_ctas, cost2, ctl);
+    E->prof_end();
+  }
+  E->launches += 1;
   if (jac && D > 0) {
     ColMaps cm;
     cm.D = D;
@@ -603,10 +680,13 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
 // copies a host array to a temporary device buffer on the estimator's stream
 template <class T>
 int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
-  CU(buf.ensure(std::max<size_t>(1, count) * sizeof(T)));
-  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, E->stream));
+  CU(buf.ensure(std::max<size_t>(1, count) * sizeof(T)));  // from g_alloc_stream's pool: the copy goes there too
+  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, g_alloc_stream));
+  (void)E;
   return CLIC_OK;
 }
+
+
 
 
 // clic_solve: the LM loop runs on the device; the host only enqueues kernels (and, for bounded problems, polls the
@@ -729,6 +809,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   const int K = E->K;
   const int later_local = E->opt.ctrl_to_be_opt_later - E->knot_id0;
   const bool drop_knots = E->opt.ctrl_to_be_opt_later > E->opt.ctrl_to_be_opt_now;  // trajectory_estimator.cpp:214
+  if (int jrc = join_adds(E)) return jrc;
   PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
   pp.marg_mode = 1;
   pp.kf = 0;
@@ -982,6 +1063,7 @@ CLIC_API void clic_default_options(clic_options* o) {
 }
 
 CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, clic_estimator** out) {
+  ScopedTrace trace("clic_create");
   if (!w || !opt || !out) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
   if (w->n_knots < 4 || w->dt_ns <= 0) return fail(CLIC_ERR_BAD_ARGUMENT, "need >= 4 knots and dt > 0");
   if (!have_device()) return fail(CLIC_ERR_NO_DEVICE, "no CUDA device: libclic_cuda has no CPU fallback");
@@ -1025,6 +1107,12 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     E->own_stream = true;
   }
+  {  // one copy stream per process and device, shared by every estimator (ordering is by per-batch events)
+    static std::vector<cudaStream_t> copy_streams;
+    if ((int)copy_streams.size() <= E->device) copy_streams.resize(E->device + 1, nullptr);
+    if (!copy_streams[E->device]) CU(cudaStreamCreateWithFlags(&copy_streams[E->device], cudaStreamNonBlocking));
+    E->copy_stream = copy_streams[E->device];
+  }
   static int pool_dev = -1;
   if (pool_dev != E->device) {
     cudaMemPool_t pool;
@@ -1048,8 +1136,13 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   if ((rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
       (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
-      (rc = set_smem(imu_kernel<true, true>, smem5)) || (rc = set_smem(image_kernel<true>, factor_smem_bytes(E->K, 7))) ||
-      (rc = set_smem(image_kernel<false>, factor_smem_bytes(E->K, 7))))
+      (rc = set_smem(imu_kernel<true, true>, smem5)) ||
+      (rc = set_smem(image_kernel<true, false>, factor_smem_bytes(E->K, 7))) ||
+      (rc = set_smem(image_kernel<false, false>, factor_smem_bytes(E->K, 7))))
+    return rc;
+  E->packs_fit = image_smem_bytes(E->K, kMaxPosePacks) <= (size_t)227 * 1024;
+  if (E->packs_fit && ((rc = set_smem(image_kernel<true, true>, image_smem_bytes(E->K, kMaxPosePacks))) ||
+                       (rc = set_smem(image_kernel<false, true>, image_smem_bytes(E->K, kMaxPosePacks)))))
     return rc;
   attr_K = E->K;
   attr_dev = E->device;
@@ -1060,10 +1153,12 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
 }
 
 CLIC_API int clic_destroy(clic_estimator* h) {
+  ScopedTrace trace("clic_destroy");
   if (!h) return CLIC_OK;
   cudaSetDevice(h->device);
   cudaStream_t st = h->stream;
   const bool own = h->own_stream;
+  cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -1091,7 +1186,8 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
   CU(cudaSetDevice(E->device));
-  AllocScope alloc_scope(E->stream);
+  cudaStream_t cs = E->copy_stream;
+  AllocScope alloc_scope(cs);
   std::unique_ptr<LoamBatch> B(new LoamBatch);
   // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
   const int S = CLIC_SENSOR_LIDAR;
@@ -1100,7 +1196,9 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
     t_min += E->opt.t_offset_padding_ns;
     t_max -= E->opt.t_offset_padding_ns;
   }
-  DevBuf r_t, r_pt, r_type, r_plane, r_normal, r_gpoint;
+  // raw (as-uploaded) arrays stay with the batch until the estimator is destroyed: freeing them while their copy is
+  // still in flight makes the stream-ordered pool's next large allocation unpredictably slow (measured: 1-30 ms)
+  DevBuf &r_t = B->raw[0], &r_pt = B->raw[1], &r_type = B->raw[2], &r_plane = B->raw[3], &r_normal = B->raw[4], &r_gpoint = B->raw[5];
   int rc;
   if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
       (rc = to_device(E, r_type, geo_type, n)))
@@ -1115,8 +1213,8 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
   for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
   CU(B->type.ensure(n));
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
-  prep_loam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
+  prep_loam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_pt.as<double>(), r_type.as<int32_t>(), r_plane.as<double>(), r_normal.as<double>(),
       r_gpoint.as<double>(), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
       B->p[2].as<double>(), B->g[0].as<double>(), B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(),
@@ -1125,8 +1223,8 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   E->launches++;
   if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
     unsigned long long dropped = 0;
-    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     *n_dropped = (int64_t)dropped;
   }  // the temporary raw buffers are freed in stream order (cudaFreeAsync), no host wait needed
   B->st.n = n;
@@ -1143,6 +1241,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
+  if ((rc = mark_ready(E, B->ex))) return rc;
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1152,12 +1251,14 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
                                   const uint8_t* geo_type, const double* geo, const double S_GtoM[4],
                                   const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
                                   int32_t marg_this_factor, int64_t* n_dropped) {
+  ScopedTrace trace("clic_add_loam_packed");
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
   if (!t_point || !point || !geo_type || !geo) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_packed: null array");
   CU(cudaSetDevice(E->device));
-  AllocScope alloc_scope(E->stream);
+  cudaStream_t cs = E->copy_stream;
+  AllocScope alloc_scope(cs);
   std::unique_ptr<LoamBatch> B(new LoamBatch);
   // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
   const int S = CLIC_SENSOR_LIDAR;
@@ -1166,7 +1267,7 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
     t_min += E->opt.t_offset_padding_ns;
     t_max -= E->opt.t_offset_padding_ns;
   }
-  DevBuf r_t, r_pt, r_type, r_geo;
+  DevBuf &r_t = B->raw[0], &r_pt = B->raw[1], &r_type = B->raw[2], &r_geo = B->raw[3];
   int rc;
   if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
       (rc = to_device(E, r_type, geo_type, n)) || (rc = to_device(E, r_geo, geo, 6 * n)))
@@ -1175,8 +1276,8 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
   for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
   CU(B->type.ensure(n));
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
-  prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
+  prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_pt.as<double>(), r_type.as<uint8_t>(), r_geo.as<double>(), t_min, t_max,
       B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
       B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
@@ -1184,8 +1285,8 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   E->launches++;
   if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
     unsigned long long dropped = 0;
-    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     *n_dropped = (int64_t)dropped;
   }  // the temporary raw buffers are freed in stream order (cudaFreeAsync), no host wait needed
   B->st.n = n;
@@ -1202,6 +1303,7 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
+  if ((rc = mark_ready(E, B->ex))) return rc;
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1210,17 +1312,19 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
 CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp, const double* gyro,
                           const double* accel, int32_t bias_slot, const double info_vec[6],
                           int32_t marg_this_factor, int64_t* n_dropped) {
+  ScopedTrace trace("clic_add_imu");
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (bias_slot < 0 || bias_slot >= E->n_bias) return fail(CLIC_ERR_BAD_ARGUMENT, "bias slot out of range");
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
   CU(cudaSetDevice(E->device));
-  AllocScope alloc_scope(E->stream);
+  cudaStream_t cs = E->copy_stream;
+  AllocScope alloc_scope(cs);
   std::unique_ptr<ImuBatch> B(new ImuBatch);
   const int S = CLIC_SENSOR_IMU;
   const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
   const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
-  DevBuf r_t, r_g, r_a;
+  DevBuf &r_t = B->raw[0], &r_g = B->raw[1], &r_a = B->raw[2];
   int rc;
   if ((rc = to_device(E, r_t, timestamp, n)) || (rc = to_device(E, r_g, gyro, 3 * n)) ||
       (rc = to_device(E, r_a, accel, 3 * n)))
@@ -1230,16 +1334,16 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
     CU(B->gy[k].ensure(n * sizeof(double)));
     CU(B->ac[k].ensure(n * sizeof(double)));
   }
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
-  prep_imu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
+  prep_imu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_g.as<double>(), r_a.as<double>(), t_min, t_max, pad, B->t_ns.as<int64_t>(),
       B->gy[0].as<double>(), B->gy[1].as<double>(), B->gy[2].as<double>(), B->ac[0].as<double>(),
       B->ac[1].as<double>(), B->ac[2].as<double>(), E->d_counter.as<unsigned long long>());
   E->launches++;
   if (n_dropped) {
     unsigned long long dropped = 0;
-    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     *n_dropped = (int64_t)dropped;
   }
   B->st.n = n;
@@ -1260,6 +1364,7 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
     E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
   }
   if ((rc = plan_stream(E, B->ex, n, B->marg ? 5 : 4, 1))) return rc;
+  if ((rc = mark_ready(E, B->ex))) return rc;
   E->imu.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1284,6 +1389,7 @@ CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, do
 CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, const double* p_i, const double* t_j,
                             const double* p_j, const int32_t* landmark, int32_t fixed_depth,
                             int32_t marg_this_feature, int64_t* n_dropped) {
+  ScopedTrace trace("clic_add_image");
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
@@ -1296,20 +1402,59 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   for (int64_t i = 0; i < n; i++)
     if (landmark[i] < 0 || landmark[i] >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
   CU(cudaSetDevice(E->device));
-  AllocScope alloc_scope(E->stream);
+  cudaStream_t cs = E->copy_stream;
+  AllocScope alloc_scope(cs);
   std::unique_ptr<ImageBatch> B(new ImageBatch);
   const int S = CLIC_SENSOR_CAMERA;
   const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
   const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
-  // Order by (t_i, t_j): the (s_i, s_j) key of consecutive factors then changes rarely, so a warp's accumulators
-  // are flushed rarely.  (The visual stream is small; this is a host-side permutation of the inputs only.)
+  // Order by the (s_i, s_j) knot-interval key (stable counting sort, O(n)): consecutive factors then share their key
+  // and a warp's accumulators are flushed rarely.  The key here only orders the inputs (host arithmetic at the
+  // current offset); the kernels recompute the exact indices.
   B->perm.resize(n);
-  for (int64_t i = 0; i < n; i++) B->perm[i] = i;
-  std::stable_sort(B->perm.begin(), B->perm.end(), [&](int64_t a, int64_t b) {
-    return t_i[a] != t_i[b] ? t_i[a] < t_i[b] : t_j[a] < t_j[b];
-  });
-  std::vector<double> s_ti(n), s_tj(n), s_pi(3 * n), s_pj(3 * n);
-  std::vector<int32_t> s_lm(n);
+  {
+    const int nk = std::max(1, E->K - 3);
+    const int64_t toff = (int64_t)E->h_state[E->sl.off_toff() + S];
+    auto interval = [&](double t) {
+      const int64_t q = ((int64_t)(t * 1e9) + toff - E->t0_ns) / E->dt_ns;
+      return (int)std::min<int64_t>(nk - 1, std::max<int64_t>(0, q));
+    };
+    std::vector<int> key(n);
+    std::vector<int64_t> start((size_t)nk * nk + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+      key[i] = interval(t_i[i]) * nk + interval(t_j[i]);
+      start[key[i] + 1]++;
+    }
+    for (size_t k = 0; k < (size_t)nk * nk; k++) start[k + 1] += start[k];
+    for (int64_t i = 0; i < n; i++) B->perm[start[key[i]]++] = i;
+  }
+  // Permuted copies go through a page-locked staging arena (process-wide, grown on demand, guarded by the event of
+  // its last upload): a cudaMemcpyAsync from pageable vectors would block this thread until every earlier copy on
+  // the stream (the LiDAR batch) has drained.
+  static std::mutex arena_mu;
+  static void* arena = nullptr;
+  static size_t arena_bytes = 0;
+  static cudaEvent_t arena_done = nullptr;
+  std::lock_guard<std::mutex> arena_lock(arena_mu);
+  const size_t need = (size_t)n * (8 * sizeof(double) + 3 * sizeof(int32_t)) + kMaxPosePacks * sizeof(int64_t);
+  if (arena_done) CU(cudaEventSynchronize(arena_done));
+  trace.lap("arena wait");
+  if (need > arena_bytes) {
+    if (arena) cudaFreeHost(arena);
+    arena = nullptr;
+    arena_bytes = 0;
+    CU(cudaHostAlloc(&arena, need + need / 2, cudaHostAllocDefault));
+    arena_bytes = need + need / 2;
+  }
+  if (!arena_done) CU(cudaEventCreateWithFlags(&arena_done, cudaEventDisableTiming));
+  double* s_ti = reinterpret_cast<double*>(arena);
+  double* s_tj = s_ti + n;
+  double* s_pi = s_tj + n;
+  double* s_pj = s_pi + 3 * n;
+  int64_t* s_pack_t = reinterpret_cast<int64_t*>(s_pj + 3 * n);
+  int32_t* s_lm = reinterpret_cast<int32_t*>(s_pack_t + kMaxPosePacks);
+  int32_t* s_idi = s_lm + n;
+  int32_t* s_idj = s_idi + n;
   for (int64_t k = 0; k < n; k++) {
     const int64_t i = B->perm[k];
     s_ti[k] = t_i[i];
@@ -1317,27 +1462,68 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     for (int c = 0; c < 3; c++) { s_pi[3 * k + c] = p_i[3 * i + c]; s_pj[3 * k + c] = p_j[3 * i + c]; }
     s_lm[k] = landmark[i];
   }
-  DevBuf r_ti, r_tj, r_pi, r_pj;
+  trace.lap("sort+stage");
+  // Distinct (timestamp, role) pairs -> pose packs (tiny open-addressing table; abandoned beyond kMaxPosePacks,
+  // e.g. rolling-shutter data with per-feature times, which then takes the per-factor chain kernel).
+  int n_pack_i = 0, n_pack_j = 0;
+  bool use_packs = E->packs_fit && !getenv("CLIC_NO_POSE_PACKS");
+  {
+    constexpr int kTab = 512;
+    int64_t tab_t[2][kTab] = {};
+    int tab_id[2][kTab];
+    for (int r = 0; r < 2; r++) for (int q = 0; q < kTab; q++) tab_id[r][q] = -1;
+    int64_t pack_t_i[kMaxPosePacks], pack_t_j[kMaxPosePacks];
+    auto lookup = [&](int r, int64_t t, int& count, int64_t* list) -> int {
+      unsigned h = (unsigned)(((uint64_t)t * 0x9E3779B97F4A7C15ull) >> 55) & (kTab - 1);
+      while (tab_id[r][h] >= 0 && tab_t[r][h] != t) h = (h + 1) & (kTab - 1);
+      if (tab_id[r][h] < 0) {
+        if (n_pack_i + n_pack_j >= kMaxPosePacks) return -1;
+        tab_t[r][h] = t;
+        tab_id[r][h] = count;
+        list[count++] = t;
+      }
+      return tab_id[r][h];
+    };
+    for (int64_t k = 0; k < n && use_packs; k++) {
+      const int a = lookup(0, (int64_t)(s_ti[k] * 1e9), n_pack_i, pack_t_i);
+      const int b = a < 0 ? -1 : lookup(1, (int64_t)(s_tj[k] * 1e9), n_pack_j, pack_t_j);
+      if (a < 0 || b < 0) { use_packs = false; break; }
+      s_idi[k] = a;
+      s_idj[k] = b;
+    }
+    if (use_packs) {
+      for (int64_t k = 0; k < n; k++) s_idj[k] += n_pack_i;
+      for (int q = 0; q < n_pack_i; q++) s_pack_t[q] = pack_t_i[q];
+      for (int q = 0; q < n_pack_j; q++) s_pack_t[n_pack_i + q] = pack_t_j[q];
+    }
+  }
+  trace.lap("packs");
+  DevBuf &r_ti = B->raw[0], &r_tj = B->raw[1], &r_pi = B->raw[2], &r_pj = B->raw[3];
   int rc;
-  if ((rc = to_device(E, r_ti, s_ti.data(), n)) || (rc = to_device(E, r_tj, s_tj.data(), n)) ||
-      (rc = to_device(E, r_pi, s_pi.data(), 3 * n)) || (rc = to_device(E, r_pj, s_pj.data(), 3 * n)) ||
-      (rc = to_device(E, B->lm, s_lm.data(), n)))
+  if (use_packs && ((rc = to_device(E, B->id_i, s_idi, n)) || (rc = to_device(E, B->id_j, s_idj, n)) ||
+                    (rc = to_device(E, B->pack_t, s_pack_t, n_pack_i + n_pack_j))))
     return rc;
+  if ((rc = to_device(E, r_ti, s_ti, n)) || (rc = to_device(E, r_tj, s_tj, n)) ||
+      (rc = to_device(E, r_pi, s_pi, 3 * n)) || (rc = to_device(E, r_pj, s_pj, 3 * n)) ||
+      (rc = to_device(E, B->lm, s_lm, n)))
+    return rc;
+  CU(cudaEventRecord(arena_done, cs));
+  trace.lap("uploads");
   CU(B->ti.ensure(n * sizeof(int64_t)));
   CU(B->tj.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) CU(B->pi[k].ensure(n * sizeof(double)));
   for (int k = 0; k < 2; k++) CU(B->pj[k].ensure(n * sizeof(double)));
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
-  prep_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(
+  trace.lap("ensures");
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
+  prep_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_ti.as<double>(), r_tj.as<double>(), r_pi.as<double>(), r_pj.as<double>(), t_min, t_max, pad,
       B->ti.as<int64_t>(), B->tj.as<int64_t>(), B->pi[0].as<double>(), B->pi[1].as<double>(), B->pi[2].as<double>(),
       B->pj[0].as<double>(), B->pj[1].as<double>(), E->d_counter.as<unsigned long long>());
   E->launches++;
-  // the sorted staging vectors above are pageable host memory: cudaMemcpyAsync from them is staged before it returns
   if (n_dropped) {
     unsigned long long dropped = 0;
-    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
+    CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     *n_dropped = (int64_t)dropped;
   }
   B->st.n = n;
@@ -1346,6 +1532,11 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   for (int k = 0; k < 3; k++) B->st.pi[k] = B->pi[k].as<double>();
   for (int k = 0; k < 2; k++) B->st.pj[k] = B->pj[k].as<double>();
   B->st.landmark = B->lm.as<int32_t>();
+  B->st.id_i = B->id_i.as<int32_t>();
+  B->st.id_j = B->id_j.as<int32_t>();
+  B->st.pack_t_ns = B->pack_t.as<int64_t>();
+  B->st.n_pack_i = use_packs ? n_pack_i : 0;
+  B->st.n_packs = use_packs ? n_pack_i + n_pack_j : 0;
   B->st.loss_a = marg_this_feature ? 1.0 : 2.0;  // trajectory_estimator.cpp:806-810
   B->marg = 0;
   if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:795-800
@@ -1353,7 +1544,10 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
     E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
   }
+  trace.lap("prep");
   if ((rc = plan_stream(E, B->ex, n, 7, 1, true, 0, kWarpsPerCta, kImageFactorsPerSlab))) return rc;
+  trace.lap("plan");
+  if ((rc = mark_ready(E, B->ex))) return rc;
   E->image.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1429,6 +1623,7 @@ CLIC_API int clic_get_layout(clic_estimator* E, clic_layout* out) {
 }
 
 CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost, double* fixed_cost) {
+  ScopedTrace trace("clic_evaluate");
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));
   AllocScope alloc_scope(E->stream);
@@ -1465,6 +1660,7 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   if (stream >= 2) for (auto& b : E->image) total += b->st.n;
   if (n_out) *n_out = total;
   if (capacity <= 0 || total == 0) return CLIC_OK;
+  if (int jrc = join_adds(E)) return jrc;
   // current offset is read from the device state
   double toff_d[3];
   CU(cudaMemcpyAsync(toff_d, E->d_state.as<double>() + E->sl.off_toff(), sizeof(toff_d), cudaMemcpyDeviceToHost, E->stream));
@@ -1679,6 +1875,7 @@ CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
 
 CLIC_API int clic_synchronize(clic_estimator* E) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaStreamSynchronize(E->copy_stream));
   CU(cudaStreamSynchronize(E->stream));
   return CLIC_OK;
 }

@@ -396,32 +396,132 @@ struct ImageShared {
   bool want_toff;    // camera time offset unlocked
 };
 
+// ---- the two spline poses of a visual factor: where R, p, the blend weights, the vector-first Jacobian rows and the
+// body velocities come from.  ImageChainPoses evaluates the cumulative chain per factor (what the reference does);
+// ImagePackPoses reads per-timestamp "pose packs" shared by every feature of a camera frame. ----
+struct ImageChainPoses {
+  const WindowView& W;
+  int si, sj;
+  double ui, uj, inv_dt;
+  So3Chain Ci, Cj;
+  Q4 Pj[4];
+  CLIC_HD ImageChainPoses(const WindowView& W_, int si_, double ui_, int sj_, double uj_, double inv_dt_)
+      : W(W_), si(si_), sj(sj_), ui(ui_), uj(uj_), inv_dt(inv_dt_) {
+    so3_chain_rp(W, si, ui, &Ci);
+    so3_chain_rtp(W, sj, uj, &Cj, Pj);
+  }
+  CLIC_HD Q4 Ri() const { return Ci.R; }
+  CLIC_HD Q4 Rj() const { return Cj.R; }
+  CLIC_HD void coeff_i(double c[4]) const { blend_plain(ui, c); }
+  CLIC_HD void coeff_j(double c[4]) const { blend_plain(uj, c); }
+  CLIC_HD V3 pos_i() const {
+    double c[4];
+    blend_plain(ui, c);
+    V3 p = mk(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) p = fma3(c[k], ldv(W.kp + 3 * (si + k)), p);
+    return p;
+  }
+  CLIC_HD V3 pos_j() const {
+    double c[4];
+    blend_plain(uj, c);
+    V3 p = mk(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) p = fma3(c[k], ldv(W.kp + 3 * (sj + k)), p);
+    return p;
+  }
+  CLIC_HD void rows_i(V3 a, V3 j[4]) const { so3_rows_rp(W, si, Ci, a, j); }
+  CLIC_HD void rows_j(V3 a, V3 j[4]) const { so3_rows_rtp(W, sj, Cj, Pj, a, j); }
+  CLIC_HD static V3 lin_vel(const WindowView& W, int s, double u, double inv_dt) {
+    double d[4];
+    blend_plain_d1(u, inv_dt, d);
+    V3 v = mk(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) v = fma3(d[k], ldv(W.kp + 3 * (s + k)), v);
+    return v;
+  }
+  CLIC_HD V3 gyro_i() const { return so3_velocity_body(W, si, ui, inv_dt); }
+  CLIC_HD V3 gyro_j() const { return so3_velocity_body(W, sj, uj, inv_dt); }
+  CLIC_HD V3 vel_i() const { return lin_vel(W, si, ui, inv_dt); }
+  CLIC_HD V3 vel_j() const { return lin_vel(W, sj, uj, inv_dt); }
+};
+
+// Pose pack of one timestamp in one role (i: anchor frame, RP chain; j: observing frame, RTP chain):
+//   q[4] | pos[3] | c[4] | G[4][3][3] | gyro[3] | vel[3]      with  rows(a)[k] = a^T G[k]  (the rows are linear in a)
+constexpr int kPackQ = 0, kPackPos = 4, kPackC = 7, kPackG = 11, kPackGyro = 47, kPackVel = 50, kPackDoubles = 54;
+// One call fills the row `c` (0..2) of every G[k]; the call with c == 0 also fills the other fields.
+CLIC_HD void compute_pose_pack(const WindowView& W, int s, double u, int role_j, double inv_dt, int c, double* pack) {
+  So3Chain C;
+  Q4 P[4];
+  if (role_j) so3_chain_rtp(W, s, u, &C, P); else so3_chain_rp(W, s, u, &C);
+  const V3 e = mk(c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0);
+  V3 j[4];
+  if (role_j) so3_rows_rtp(W, s, C, P, e, j); else so3_rows_rp(W, s, C, e, j);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    pack[kPackG + 9 * k + 3 * c + 0] = j[k].x;
+    pack[kPackG + 9 * k + 3 * c + 1] = j[k].y;
+    pack[kPackG + 9 * k + 3 * c + 2] = j[k].z;
+  }
+  if (c != 0) return;
+  pack[kPackQ + 0] = C.R.x; pack[kPackQ + 1] = C.R.y; pack[kPackQ + 2] = C.R.z; pack[kPackQ + 3] = C.R.w;
+  double cc[4];
+  blend_plain(u, cc);
+  V3 pos = mk(0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    pos = fma3(cc[k], ldv(W.kp + 3 * (s + k)), pos);
+    pack[kPackC + k] = cc[k];
+  }
+  pack[kPackPos + 0] = pos.x; pack[kPackPos + 1] = pos.y; pack[kPackPos + 2] = pos.z;
+  const V3 g = so3_velocity_body(W, s, u, inv_dt), v = ImageChainPoses::lin_vel(W, s, u, inv_dt);
+  pack[kPackGyro + 0] = g.x; pack[kPackGyro + 1] = g.y; pack[kPackGyro + 2] = g.z;
+  pack[kPackVel + 0] = v.x; pack[kPackVel + 1] = v.y; pack[kPackVel + 2] = v.z;
+}
+struct ImagePackPoses {
+  const double* A;  // pack of t_i (role i)
+  const double* B;  // pack of t_j (role j)
+  CLIC_HD Q4 Ri() const { return ldq(A + kPackQ); }
+  CLIC_HD Q4 Rj() const { return ldq(B + kPackQ); }
+  CLIC_HD void coeff_i(double c[4]) const { for (int k = 0; k < 4; k++) c[k] = A[kPackC + k]; }
+  CLIC_HD void coeff_j(double c[4]) const { for (int k = 0; k < 4; k++) c[k] = B[kPackC + k]; }
+  CLIC_HD V3 pos_i() const { return ldv(A + kPackPos); }
+  CLIC_HD V3 pos_j() const { return ldv(B + kPackPos); }
+  CLIC_HD static void rows(const double* G, V3 a, V3 j[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double* g = G + 9 * k;
+      j[k].x = a.x * g[0] + a.y * g[3] + a.z * g[6];
+      j[k].y = a.x * g[1] + a.y * g[4] + a.z * g[7];
+      j[k].z = a.x * g[2] + a.y * g[5] + a.z * g[8];
+    }
+  }
+  CLIC_HD void rows_i(V3 a, V3 j[4]) const { rows(A + kPackG, a, j); }
+  CLIC_HD void rows_j(V3 a, V3 j[4]) const { rows(B + kPackG, a, j); }
+  CLIC_HD V3 gyro_i() const { return ldv(A + kPackGyro); }
+  CLIC_HD V3 gyro_j() const { return ldv(B + kPackGyro); }
+  CLIC_HD V3 vel_i() const { return ldv(A + kPackVel); }
+  CLIC_HD V3 vel_j() const { return ldv(B + kPackVel); }
+};
+
 // ImageFeatureFactor::Evaluate (image_feature_factor.h:67-268), inverse depth held constant (fixed_depth = true, the
 // only mode the shipped pipeline uses, trajectory_manager.cpp:709).  Emits 2 rows of 56 columns:
 //   [window of t_i: 0..23 | window of t_j: 24..47 | camera t_offset 48 | r 49 | pad]
 // `row_sel` (0 | 1) selects which of the two residual rows this call emits: the kernel gives row 0 to lanes 0-15 and
 // row 1 to lanes 16-31 of the same 16 factors (data-dependent only, no divergent code), the host test calls it twice.
-template <class Sink>
-CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double uj, V3 p_i, V3 p_j, double d_inv,
-                          const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
+template <class Poses, class Sink>
+CLIC_HD double image_eval_with(const Poses& PS, V3 p_i, V3 p_j, double d_inv, const ImageShared& sh, bool want_jac,
+                               Sink& sink, int row_sel) {
   V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
   V3 p_Ii = qrot(sh.S_CtoI, x_ci) + sh.p_CinI;
-  So3Chain Ci, Cj;
-  Q4 Pj[4];
-  so3_chain_rp(W, si, ui, &Ci);
-  so3_chain_rtp(W, sj, uj, &Cj, Pj);
+  const Q4 Ri = PS.Ri(), Rj = PS.Rj();
   double ci[4], cj[4];
-  blend_plain(ui, ci);
-  blend_plain(uj, cj);
-  V3 pos_i = mk(0, 0, 0), pos_j = mk(0, 0, 0);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    pos_i = fma3(ci[k], ldv(W.kp + 3 * (si + k)), pos_i);
-    pos_j = fma3(cj[k], ldv(W.kp + 3 * (sj + k)), pos_j);
-  }
-  V3 p_G = qrot(Ci.R, p_Ii) + pos_i;
+  PS.coeff_i(ci);
+  PS.coeff_j(cj);
+  const V3 pos_i = PS.pos_i(), pos_j = PS.pos_j();
+  V3 p_G = qrot(Ri, p_Ii) + pos_i;
   Q4 S_ItoC = qconj(sh.S_CtoI);
-  Q4 S_GtoCj = qmul(S_ItoC, qconj(Cj.R));  // S_ItoC * S_GtoIj
+  Q4 S_GtoCj = qmul(S_ItoC, qconj(Rj));  // S_ItoC * S_GtoIj
   V3 dG = p_G - pos_j;
   V3 x_j = qrot(S_GtoCj, dG) - qrot(S_ItoC, sh.p_CinI);
   const double dinv = 1.0 / x_j.z;
@@ -435,20 +535,11 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
   const V3 Jvr = mk(r0 ? dinv : 0.0, r0 ? 0.0 : dinv, -dinv * dinv * (r0 ? x_j.x : x_j.y));
   V3 jt = mk(0, 0, 0);
   if (sh.want_toff) {  // image_feature_factor.h:250-263
-    V3 gyro_i = so3_velocity_body(W, si, ui, sh.inv_dt), gyro_j = so3_velocity_body(W, sj, uj, sh.inv_dt);
-    double di[4], dj[4];
-    blend_plain_d1(ui, sh.inv_dt, di);
-    blend_plain_d1(uj, sh.inv_dt, dj);
-    V3 vel_i = mk(0, 0, 0), vel_j = mk(0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      vel_i = fma3(di[k], ldv(W.kp + 3 * (si + k)), vel_i);
-      vel_j = fma3(dj[k], ldv(W.kp + 3 * (sj + k)), vel_j);
-    }
+    const V3 gyro_i = PS.gyro_i(), gyro_j = PS.gyro_j(), vel_i = PS.vel_i(), vel_j = PS.vel_j();
     // J_tj = S_ItoC * Rj_dot^T * (p_G - p_Ij) - S_GtoCj * vel_j,  Rj_dot^T v = -(omega_j x (Rj^T v))
-    V3 J_tj = qrot(S_ItoC, -cross(gyro_j, qrot_inv(Cj.R, dG))) - qrot(S_GtoCj, vel_j);
+    V3 J_tj = qrot(S_ItoC, -cross(gyro_j, qrot_inv(Rj, dG))) - qrot(S_GtoCj, vel_j);
     // J_ti = S_GtoCj * (Ri_dot * p_Ii + vel_i),  Ri_dot p = Ri (omega_i x p)
-    V3 J_ti = qrot(S_GtoCj, qrot(Ci.R, cross(gyro_i, p_Ii)) + vel_i);
+    V3 J_ti = qrot(S_GtoCj, qrot(Ri, cross(gyro_i, p_Ii)) + vel_i);
     jt = J_ti + J_tj;
   }
   {
@@ -457,13 +548,13 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
     // g = (J_v S_GtoCj)^T  -> jac_lhs_P[0] = g, jac_lhs_P[1] = -g
     V3 g = qrot_inv(S_GtoCj, Jvr);
     // jac_lhs_R[0] = -J_v (S_GtoCj S_IitoG) hat(p_Ii):  with m = (J_v S_GtoCj R_i)^T, row = -(m x p_Ii) = p_Ii x m
-    V3 m = qrot_inv(Ci.R, g);
+    V3 m = qrot_inv(Ri, g);
     V3 a_i = cross(p_Ii, m);
     // jac_lhs_R[1] = J_v S_GtoCj hat(p_G - p_Ij):  row = g x dG
     V3 a_j = cross(g, dG);
     V3 ji[4], jj[4];
-    so3_rows_rp(W, si, Ci, a_i, ji);
-    so3_rows_rtp(W, sj, Cj, Pj, a_j, jj);
+    PS.rows_i(a_i, ji);
+    PS.rows_j(a_j, jj);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       sink.put(row, 6 * k + 0, sI * ji[k].x);
@@ -486,6 +577,20 @@ CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double
     sink.row_done(row);
   }
   return rho;
+}
+template <class Sink>
+CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double uj, V3 p_i, V3 p_j, double d_inv,
+                          const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
+  const ImageChainPoses PS(W, si, ui, sj, uj, sh.inv_dt);
+  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel);
+}
+template <class Sink>
+CLIC_HD double image_eval_packed(const double* pack_i, const double* pack_j, V3 p_i, V3 p_j, double d_inv,
+                                 const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
+  ImagePackPoses PS;
+  PS.A = pack_i;
+  PS.B = pack_j;
+  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel);
 }
 
 }  // namespace clic

@@ -385,42 +385,37 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
 constexpr int kMaxChunk = 1024;
 // The extra CTA (blockIdx.x == gridDim.x - 1, part 0) sums the per-warp costs in a fixed tree and adds (or, for the
 // first stream of a pass, stores) them into cost2 — one launch less per stream than a separate cost kernel.
+// Fixed-tree sum of the per-warp (cost, fixed_cost) pairs by one 256-thread CTA; valid in thread 0.
+__device__ __forceinline__ void cta_cost_sum(const double* warp_cost, int n_warps, double* c_out, double* f_out) {
+  __shared__ double sh[2][256];
+  double c = 0, f = 0;
+  for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
+    c += warp_cost[2 * i];
+    f += warp_cost[2 * i + 1];
+  }
+  __syncthreads();  // sh may still be read by a previous call
+  sh[0][threadIdx.x] = c;
+  sh[1][threadIdx.x] = f;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  *c_out = sh[0][0];
+  *f_out = sh[1][0];
+}
+
+// CTA (key k, part): ordered sum of the record payloads with key k among slots [r0, r1) -> out[e], e < RD.
 template <int RD>
-__global__ void __launch_bounds__(256)
-reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const double* warp_cost,
-                      int n_warps, double* cost2, int first_stream, const int* ctl) {
-  if (ctl && ctl[0]) return;
+__device__ __forceinline__ void reduce_part_body(const double* payload, const int* key, int r0, int r1, int k,
+                                                 double* out) {
   constexpr int EPT = (RD + 255) / 256;
   __shared__ int list[kMaxChunk];
   __shared__ int n_match;
-  if (blockIdx.x == gridDim.x - 1) {
-    if (blockIdx.y != 0) return;
-    __shared__ double sh[2][256];
-    double c = 0, f = 0;
-    for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
-      c += warp_cost[2 * i];
-      f += warp_cost[2 * i + 1];
-    }
-    sh[0][threadIdx.x] = c;
-    sh[1][threadIdx.x] = f;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) {
-        sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-        sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      cost2[0] = (first_stream ? 0.0 : cost2[0]) + sh[0][0];
-      cost2[1] = (first_stream ? 0.0 : cost2[1]) + sh[1][0];
-    }
-    return;
-  }
-  const int k = blockIdx.x, part = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = (n_slots + P - 1) / P;
-  const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
   if (warp == 0) {
     int cnt = 0;
     for (int rb = r0; rb < r1; rb += 32) {
@@ -460,8 +455,94 @@ reduce_records_kernel(const double* payload, const int* key, int n_slots, int P,
 #pragma unroll
   for (int i = 0; i < EPT; i++) {
     const int e = threadIdx.x + i * 256;
-    if (e < RD) out[((size_t)k * P + part) * RD + e] = acc[i];
+    if (e < RD) out[e] = acc[i];
   }
+}
+
+template <int RD>
+__global__ void __launch_bounds__(256)
+reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const double* warp_cost,
+                      int n_warps, double* cost2, int first_stream, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  if (blockIdx.x == gridDim.x - 1) {
+    if (blockIdx.y != 0) return;
+    double c, f;
+    cta_cost_sum(warp_cost, n_warps, &c, &f);
+    if (threadIdx.x == 0) {
+      cost2[0] = (first_stream ? 0.0 : cost2[0]) + c;
+      cost2[1] = (first_stream ? 0.0 : cost2[1]) + f;
+    }
+    return;
+  }
+  const int k = blockIdx.x, part = blockIdx.y;
+  const int chunk = (n_slots + P - 1) / P;
+  const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
+  reduce_part_body<RD>(payload, key, r0, r1, k, out + ((size_t)k * P + part) * RD);
+}
+
+// All factor streams of a pass in ONE launch.  CTA (job, key, part) writes its ordered partial sum; the CTA that
+// finishes a key last (ticket) folds the P partials (fixed order) and the atomics-fallback block into fin[key] and
+// re-arms both.  The extra last CTA sums every job's per-warp costs.  jac == 0: only that CTA is launched.
+struct ReduceJob {
+  const double* payload;
+  const int* key;
+  double* part;      // [n_keys][P][rd]
+  double* fin;       // [n_keys][rd]
+  double* overflow;  // [n_keys][rd], folded into fin and zeroed again
+  const double* warp_cost;
+  unsigned* ticket;  // [n_keys], zero between launches
+  int n_slots, P, n_keys, rd, n_warps;
+  int cta0;          // first CTA of the job in the flattened grid
+};
+__global__ void __launch_bounds__(256)
+reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_part_ctas, double* cost2, const int* ctl) {
+  if (ctl && ctl[0]) return;
+  if ((int)blockIdx.x == n_part_ctas) {
+    double c_tot = 0.0, f_tot = 0.0;
+    for (int j = 0; j < n_jobs; j++) {
+      double c, f;
+      cta_cost_sum(jobs[j].warp_cost, jobs[j].n_warps, &c, &f);
+      c_tot += c;
+      f_tot += f;
+    }
+    if (threadIdx.x == 0) {
+      cost2[0] = c_tot;
+      cost2[1] = f_tot;
+    }
+    return;
+  }
+  int j = 0;
+  while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].cta0) j++;
+  const ReduceJob& J = jobs[j];
+  const int local = blockIdx.x - J.cta0;
+  const int k = local / J.P, part = local % J.P;
+  const int chunk = (J.n_slots + J.P - 1) / J.P;
+  const int r0 = part * chunk, r1 = min(J.n_slots, r0 + chunk);
+  double* out = J.part + ((size_t)k * J.P + part) * J.rd;
+  switch (J.rd) {
+    case 416: reduce_part_body<416>(J.payload, J.key, r0, r1, k, out); break;
+    case 640: reduce_part_body<640>(J.payload, J.key, r0, r1, k, out); break;
+    case 960: reduce_part_body<960>(J.payload, J.key, r0, r1, k, out); break;
+    default: reduce_part_body<1792>(J.payload, J.key, r0, r1, k, out); break;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&J.ticket[k], 1u) == (unsigned)(J.P - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* parts = J.part + (size_t)k * J.P * J.rd;
+  double* ov = J.overflow + (size_t)k * J.rd;
+  double* fin = J.fin + (size_t)k * J.rd;
+  for (int e = threadIdx.x; e < J.rd; e += 256) {
+    double a = 0.0;
+    for (int p = 0; p < J.P; p++) a += __ldcg(parts + (size_t)p * J.rd + e);
+    const double o = ov[e];
+    if (o != 0.0) ov[e] = 0.0;
+    fin[e] = a + o;
+  }
+  if (threadIdx.x == 0) J.ticket[k] = 0u;
 }
 
 // Sum of per-warp costs in warp order (single CTA, deterministic tree over fixed positions).
@@ -662,14 +743,21 @@ struct ImageStream {
   const double* pj[2];
   const int32_t* landmark;
   double loss_a;
+  // Pose packs (n_packs > 0): every feature of a camera frame shares its timestamp, so the spline poses and their
+  // Jacobian maps are evaluated once per distinct (timestamp, role) by each CTA and the factors only compose them.
+  const int32_t* id_i;       // per factor: pack of t_i (0 .. n_pack_i-1)
+  const int32_t* id_j;       // per factor: pack of t_j (n_pack_i .. n_packs-1)
+  const int64_t* pack_t_ns;  // [n_packs] distinct times (ns, without offset)
+  int n_pack_i, n_packs;
 };
+constexpr int kMaxPosePacks = 96;
 
 // Local columns (NT = 7): [window of t_i 0..23 | window of t_j 24..47 | camera t_offset 48 | r 49 | pad]; key = s_i*(K-3)+s_j.
 // A slab is 16 factors x 2 residual rows: lanes 0-15 evaluate row 0, lanes 16-31 row 1 of the same factors, so one
 // 32-row tile accumulation covers a slab and each lane builds one Jacobian row only (this stream is small and
 // latency-bound: shorter per-lane work + twice as many slabs to spread over the SMs).
 constexpr int kImageFactorsPerSlab = 16;
-template <bool JAC>
+template <bool JAC, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 1)
 image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, ImageShared sh) {
   constexpr int NT = 7;
@@ -680,8 +768,21 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kWarpsPerCta + warp;
   const int row_sel = lane >> 4;
-  double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
   const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 2];  // camera offset, image_feature_factor.h:75-76
+  const double* packs = rest;
+  if (PACKED) {  // thread (pack, c): row c of the pack's Jacobian maps; c == 0 also the pose itself
+    double* pk = rest;
+    for (int t = threadIdx.x; t < 3 * st.n_packs; t += blockDim.x) {
+      const int id = t / 3, c = t % 3;
+      int s = 0;
+      double u = 0.0;
+      if (!index_ns(st.pack_t_ns[id] + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u)) { s = 0; u = 0.0; }  // unused pack
+      compute_pose_pack(W, s, u, id >= st.n_pack_i ? 1 : 0, sh.inv_dt, c, pk + (size_t)id * kPackDoubles);
+    }
+    rest += (size_t)st.n_packs * kPackDoubles;  // even: what follows stays 16-byte aligned
+    __syncthreads();
+  }
+  double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
   const double* invd = pp.state + pp.sl.off_invd();
   const int nk = pp.sl.K - 3;
   WarpAcc<NT> acc;
@@ -702,10 +803,12 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
                  index_ns(tj + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &sj, &uj);
     V3 p_i = mk(0, 0, 1), p_j = mk(0, 0, 1);
     double rho_inv = 1.0;
+    int pack_i = 0, pack_j = 0;
     if (valid) {
       p_i = mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]);
       p_j = mk(st.pj[0][idx], st.pj[1][idx], 1.0);
       rho_inv = invd[st.landmark[idx]];
+      if (PACKED) { pack_i = st.id_i[idx]; pack_j = st.id_j[idx]; }
     } else {
       si = sj = 0; ui = uj = 0.0;
     }
@@ -725,11 +828,15 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
         }
         SmemRowSink<NT> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
-        double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel);
+        double rho = PACKED ? image_eval_packed(packs + (size_t)pack_i * kPackDoubles, packs + (size_t)pack_j * kPackDoubles,
+                                                p_i, p_j, rho_inv, sh, true, sink, row_sel)
+                            : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel);
         if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       } else {
         NullSink sink;
-        double rho = image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, false, sink, row_sel);
+        double rho = PACKED ? image_eval_packed(packs + (size_t)pack_i * kPackDoubles, packs + (size_t)pack_j * kPackDoubles,
+                                                p_i, p_j, rho_inv, sh, false, sink, row_sel)
+                            : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, false, sink, row_sel);
         if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       }
       pending &= ~__ballot_sync(0xffffffffu, mine);
@@ -826,7 +933,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
     }
     if (ki < 0 && ei < 0) continue;
     if (!is_b && kj < 0 && ej < 0) continue;
-    const int PP = sd.P + 1;  // partials + the overflow block
+    const int PP = sd.P + (sd.overflow ? 1 : 0);  // partials (+ the overflow block when it was not folded in)
     if (sd.kind == 0) {
       int s_lo = 0, s_hi = sd.n_keys - 1;
       if (ki >= 0) { s_lo = max(s_lo, ki - 3); s_hi = min(s_hi, ki); }

@@ -88,4 +88,28 @@ __attribute__((visibility("default"))) int emul_image(int K, const double* kq, c
   *sj_out = sj;
   return 0;
 }
+// same factor through per-timestamp pose packs (the packed visual kernel's path)
+__attribute__((visibility("default"))) int emul_image_packed(int K, const double* kq, const double* kp, int64_t t0_ns,
+                                                              int64_t dt_ns, int64_t ti_ns, int64_t tj_ns,
+                                                              const double* p_i, const double* p_j, double d_inv,
+                                                              const double* S_CtoI, const double* p_CinI,
+                                                              double loss_a, int want_toff, double* rows /*2*56*/,
+                                                              double* rho) {
+  HostWindow W(K, kq, kp);
+  int si, sj;
+  double ui, uj;
+  if (!index_ns(ti_ns, t0_ns, dt_ns, K, &si, &ui) || !index_ns(tj_ns, t0_ns, dt_ns, K, &sj, &uj)) return 1;
+  ImageShared sh;
+  sh.S_CtoI = ldq(S_CtoI); sh.p_CinI = ldv(p_CinI); sh.sqrt_info = 450.0 / 1.5; sh.loss_a = loss_a;
+  sh.inv_dt = 1e9 / double(dt_ns); sh.want_toff = want_toff != 0;
+  double pa[kPackDoubles], pb[kPackDoubles];
+  for (int c = 0; c < 3; c++) {
+    compute_pose_pack(W.view, si, ui, 0, sh.inv_dt, c, pa);
+    compute_pose_pack(W.view, sj, uj, 1, sh.inv_dt, c, pb);
+  }
+  ArraySink sink{rows, 56};
+  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0);
+  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1);
+  return 0;
+}
 }

@@ -28,6 +28,8 @@ def emul():
                              C.c_int, dp, dp, ip]
     lib.emul_image.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp, C.c_double, dp, dp,
                                C.c_double, C.c_int, dp, dp, ip, ip]
+    lib.emul_image_packed.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp, C.c_double, dp,
+                                      dp, C.c_double, C.c_int, dp, dp]
     return lib
 
 
@@ -156,6 +158,14 @@ def test_image_rows(oracle, emul, unlock_toff):
         if unlock_toff:
             J[:, Lay.col_t_offset[2]] += rows[:, 48]
         overlaps += abs(si.value - sj.value) < 4
+        # the per-timestamp pose-pack path (packed visual kernel) emits the same rows
+        rows_p, rho_p = np.zeros((2, 56)), np.zeros(1)
+        rc = emul.emul_image_packed(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, ti, tj, dptr(pi), dptr(pj),
+                                    float(w.inv_depth[I["landmark"][i]]), dptr(w.S_CtoI), dptr(w.p_CinI), 2.0,
+                                    int(unlock_toff), dptr(rows_p), dptr(rho_p))
+        assert rc == 0
+        assert np.abs(rows_p - rows).max() <= 1e-12 * max(1.0, np.abs(rows).max())
+        assert abs(rho_p[0] - rho[0]) <= 1e-13 * max(1.0, abs(rho[0]))
         scale = max(1.0, np.abs(J_o).max())
         worst = max(worst, np.abs(J - J_o).max() / scale)
         assert np.allclose(rows[:, 49], r_o, rtol=1e-10, atol=1e-9)

@@ -190,6 +190,26 @@ def test_visual_unsorted_and_fixed_knots(cuda, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("unlock_cam_toff", [False, True])
+def test_visual_per_factor_chain_path(cuda, oracle, monkeypatch, unlock_cam_toff):
+    """Camera frames share timestamps, so the visual kernel normally composes per-timestamp pose packs.  Per-feature
+    times (rolling shutter: more distinct times than packs) take the per-factor chain kernel; so does the switch."""
+    sw = S.make_window(10, n_lidar=0, n_imu=0, n_landmarks=90, obs_per_landmark=6, seed=47, time_margin_ns=3_000_000,
+                       t_offset_ns=(0.0, 0.0, 90_000.6 if unlock_cam_toff else 0.0))
+    kw = dict(unlock_cam_toff=unlock_cam_toff, pad=1_000_000, bias_factor=False)
+    H_pack, b_pack = compare_eval(cuda, oracle, sw, **kw)
+    monkeypatch.setenv("CLIC_NO_POSE_PACKS", "1")
+    H_chain, b_chain = compare_eval(cuda, oracle, sw, **kw)
+    monkeypatch.delenv("CLIC_NO_POSE_PACKS")
+    assert rel(H_pack, H_chain) < 1e-11 and rel(b_pack, b_chain) < 1e-11
+    rng = np.random.default_rng(5)
+    n = len(sw.image["t_i"])
+    sw.image["t_i"] = sw.image["t_i"] + rng.uniform(-4e-4, 4e-4, n)   # > 96 distinct times
+    sw.image["t_j"] = sw.image["t_j"] + rng.uniform(-4e-4, 4e-4, n)
+    compare_eval(cuda, oracle, sw, **kw)
+
+
+@pytest.mark.gpu
 def test_packed_lidar_input_is_identical(cuda):
     """clic_add_loam_packed (81 B/record) builds bit-identical normal equations to clic_add_loam."""
     sw = S.make_window(12, n_lidar=5000, n_imu=0, line_fraction=0.4, seed=77)
