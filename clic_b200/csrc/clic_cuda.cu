@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <utility>
 #include <mutex>
 #include <vector>
 
@@ -118,6 +119,24 @@ struct ScopedTrace {
   }
   ~ScopedTrace() { lap("end"); }
 };
+
+// Kernel launch with the programmatic-dependent-launch attribute (kernels.cuh: pdl_wait / pdl_trigger).  CLIC_NO_PDL=1
+// launches plainly (A/B switch); the device-side hooks are no-ops then.
+bool pdl_enabled() { static const bool v = getenv("CLIC_NO_PDL") == nullptr; return v; }
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // Launch geometry + record buffers of one factor stream.
 struct StreamExec {
@@ -497,9 +516,9 @@ int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* 
   const int n = pr->p->n, nb = (int)pr->p->blocks.size();
   const int D = std::max(1, E->L.D);
   size_t smem = (size_t)3 * n * sizeof(double) + (size_t)n * sizeof(int);
-  prior_kernel<<<1, 256, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
-                                            pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->H_loc(),
-                                            E->b_loc(), D, cost2, jac ? 1 : 0, ctl);
+  CU(launch_pdl(prior_kernel, 1, 256, smem, E->stream, pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
+                pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->H_loc(), E->b_loc(), D, cost2, jac ? 1 : 0,
+                ctl));
   E->launches++;
   return CLIC_OK;
 }
@@ -545,6 +564,7 @@ PassParams pass_params(const clic_estimator* E, const double* state, const int* 
   pp.marg_mode = 0;
   pp.marg_later_local = E->opt.ctrl_to_be_opt_later - E->knot_id0;
   pp.ctl = ctl;
+  pp.pdl_first = 0;
   return pp;
 }
 
@@ -562,6 +582,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   double* cost2 = E->cost_loc() + 2 * which;  // slot 0: pass at x, slot 1: pass at the LM candidate
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
+  pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamExec& ex = b->ex;
@@ -569,12 +590,14 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const size_t smem = loam_smem_bytes(E->K);
     if (jac) {
       E->prof_begin(0);
-      loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      CU(launch_pdl(loam_kernel<true, kLoamWarps, kLoamMinB>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
     } else {
       E->prof_begin(0);
-      loam_kernel<false, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
     }
@@ -586,12 +609,14 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const size_t smem = factor_smem_bytes(E->K, 4);
     if (jac) {
       E->prof_begin(1);
-      imu_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      CU(launch_pdl(imu_kernel<true, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
     } else {
       E->prof_begin(1);
-      imu_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+      CU(launch_pdl(imu_kernel<false, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
     }
@@ -611,19 +636,20 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const bool packed = b->st.n_packs > 0;
     const size_t smem_p = image_smem_bytes(E->K, b->st.n_packs);
     E->prof_begin(2);
-    if (jac && packed) image_kernel<true, true><<<ex.grid, kThreads, smem_p, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
-    else if (jac) image_kernel<true, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
-    else if (packed) image_kernel<false, true><<<ex.grid, kThreads, smem_p, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
-    else image_kernel<false, false><<<ex.grid, kThreads, smem, E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    if (jac && packed) CU(launch_pdl(image_kernel<true, true>, ex.grid, kThreads, smem_p, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
+    else if (jac) CU(launch_pdl(image_kernel<true, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
+    else if (packed) CU(launch_pdl(image_kernel<false, true>, ex.grid, kThreads, smem_p, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
+    else CU(launch_pdl(image_kernel<false, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
     E->prof_end();
     E->launches += 1;
+    pp.pdl_first = 0;
   }
   if (E->n_jobs == 0) {  // no factor stream at all (prior-only problem)
-    zero_cost_kernel<<<1, 32, 0, E->stream>>>(cost2, ctl);
+    CU(launch_pdl(zero_cost_kernel, 1, 32, 0, E->stream, cost2, ctl));
   } else {  // every stream's records -> per-key blocks, and the pass cost, in one launch (cost only without jac)
     const int part_ctas = jac ? E->n_part_ctas : 0;
     E->prof_begin(3);
-    reduce_all_kernel<<<part_ctas + 1, 256, 0, E->stream>>>(E->d_jobs.as<ReduceJob>(), E->n_jobs, part_ctas, cost2, ctl);
+    CU(launch_pdl(reduce_all_kernel, part_ctas + 1, 256, 0, E->stream, E->d_jobs.as<ReduceJob>(), E->n_jobs, part_ctas, cost2, ctl));
     E->prof_end();
   }
   E->launches += 1;
@@ -636,8 +662,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     cm.col_sub = E->d_col_sub.as<int>();
     const int n_entries = D * (D + 1) / 2 + D;
     E->prof_begin(3);
-    assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(E->H_loc(), E->b_loc(), cm,
-                                                                    E->d_descs.as<StreamDesc>(), E->n_desc, ctl);
+    CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, E->H_loc(), E->b_loc(), cm,
+                  E->d_descs.as<StreamDesc>(), E->n_desc, ctl));
     E->prof_end();
     E->launches += 1;
   }
@@ -651,8 +677,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
     d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
     d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
-    bias_factor_kernel<<<1, 32, 0, E->stream>>>(d, state, E->sl, E->H_loc(), E->b_loc(), std::max(1, D),
-                                                cost2, jac ? 1 : 0, ctl);
+    CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, E->H_loc(), E->b_loc(), std::max(1, D),
+                  cost2, jac ? 1 : 0, ctl));
     E->launches += 1;
   }
   for (auto& pr : E->priors) {

@@ -33,6 +33,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // State vector layout on the device: [knot_q 4K | knot_p 3K | bias 6nb | t_offset 3 | gravity 3 | inv_depth L]
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the
+// stream is still draining.  pdl_trigger() lets the successor's CTAs be scheduled as SMs free up; pdl_wait() blocks
+// until the predecessor grid has completed and its writes are visible.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct StateLayout {
   int K, nb, L;
   __host__ __device__ int off_q() const { return 0; }
@@ -52,7 +58,23 @@ struct PassParams {
   int marg_mode;        // 1: marginalization set semantics (gates below), every block has a column
   int marg_later_local; // ctrl_to_be_opt_later - knot_id0
   const int* ctl;       // device control word (LM loop): ctl[0] != 0 => skip this pass
+  // PDL: 1 = first factor kernel of a pass (its inputs come from the predecessor: wait before reading anything);
+  // 0 = independent of its predecessor (another factor kernel): it overlaps that kernel's tail and only waits
+  // before exiting, so that "this grid completed" still implies "every earlier grid completed".
+  int pdl_first;
 };
+__device__ __forceinline__ bool pass_prologue(const PassParams& pp) {  // true: skip this pass
+  if (pp.pdl_first) pdl_wait();
+  pdl_trigger();
+  if (pp.ctl && pp.ctl[0]) {
+    if (!pp.pdl_first) pdl_wait();
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void pass_epilogue(const PassParams& pp) {
+  if (!pp.pdl_first) pdl_wait();
+}
 
 struct LoamStream {
   int64_t n;
@@ -268,7 +290,7 @@ __device__ __forceinline__ double warp_transpose_reduce24(const double (&v)[24],
 template <bool JAC, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
-  if (pp.ctl && pp.ctl[0]) return;
+  if (pass_prologue(pp)) return;
   extern __shared__ double smem[];
   double* rest;
   WindowView W = stage_window(smem, pp, &rest);
@@ -376,6 +398,7 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+  pass_epilogue(pp);
 }
 
 // Level-1 reduction: CTA (key, part) sums the payloads whose key matches over its share of the record slots.
@@ -496,6 +519,8 @@ struct ReduceJob {
 };
 __global__ void __launch_bounds__(256)
 reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_part_ctas, double* cost2, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctl && ctl[0]) return;
   if ((int)blockIdx.x == n_part_ctas) {
     double c_tot = 0.0, f_tot = 0.0;
@@ -652,7 +677,7 @@ template <bool JAC, bool MARG>
 __global__ void __launch_bounds__(kThreads, 1)
 imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   constexpr int NT = MARG ? 5 : 4;
-  if (pp.ctl && pp.ctl[0]) return;
+  if (pass_prologue(pp)) return;
   extern __shared__ double smem[];
   double* rest;
   WindowView W = stage_window(smem, pp, &rest);
@@ -732,6 +757,7 @@ imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+  pass_epilogue(pp);
 }
 
 // ---------------- K3: ImageFeatureFactor over a stream ----------------
@@ -761,7 +787,7 @@ template <bool JAC, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 1)
 image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, ImageShared sh) {
   constexpr int NT = 7;
-  if (pp.ctl && pp.ctl[0]) return;
+  if (pass_prologue(pp)) return;
   extern __shared__ double smem[];
   double* rest;
   WindowView W = stage_window(smem, pp, &rest);
@@ -855,6 +881,7 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+  pass_epilogue(pp);
 }
 
 __global__ void prep_image_kernel(int64_t n, const double* ti_s, const double* tj_s, const double* p_i, const double* p_j,
@@ -905,6 +932,8 @@ __device__ __forceinline__ double block_entry(const double* blk, int NT, int la,
 // so the sum order never changes between runs.
 __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
                                                        int n_desc, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctl && ctl[0]) return;
   const int D = cm.D;
   const int n_upper = D * (D + 1) / 2;
@@ -995,6 +1024,8 @@ struct BiasFactorDesc {
 };
 __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, StateLayout sl, double* H, double* b, int D,
                                    double* cost2, int jac, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctl && ctl[0]) return;
   // one lane per residual row: rows touch disjoint H / b entries (row r -> offset r % 3 of the gyro or accel blocks)
   const int r = threadIdx.x;

@@ -32,6 +32,8 @@ __global__ void prior_grad_kernel(const double* J0, const double* r0, int n, dou
 __global__ void prior_kernel(const double* J0, const double* A, const double* r0, const double* x0, const int* meta,
                              int n, int n_blocks, const double* state, double* H, double* b, int D, double* cost2,
                              int jac, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctl && ctl[0]) return;
   extern __shared__ double sm[];
   double* dx = sm;
@@ -419,6 +421,8 @@ __global__ void lm_project_kernel(LmBufs B, LayoutDev L) {
 }
 
 __global__ void zero_cost_kernel(double* cost2, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctl && ctl[0]) return;
   if (threadIdx.x < 2) cost2[threadIdx.x] = 0.0;
 }
