@@ -144,7 +144,7 @@ struct StreamExec {
   int grid = 0, slabs_per_warp = 0, n_warps = 0, warps_per_cta = kWarpsPerCta;
   int NT = 4, rd = 640, n_keys = 0, P = 8;
   DevBuf payload, key, cost, part, overflow;
-  DevBuf fin, ticket;  // solve path: per-key final blocks and the last-part tickets of reduce_all_kernel
+  DevBuf fin;  // solve path: per-key final blocks of reduce_all_kernel
   // The adders upload on the estimator's copy stream; `ready` marks the batch complete there and the compute stream
   // waits for it once, right before the first kernel that reads the batch (H2D of later batches overlaps compute).
   cudaEvent_t ready = nullptr;
@@ -328,8 +328,9 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.slabs_per_warp = (int)slabs;  // = total slabs (kernel argument)
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
-  // reduction parts: ~256 record slots (8 CTAs) each, so no (key, part) CTA walks more than a handful of records
-  ex.P = (int)std::min<size_t>(pair_keys ? 8 : 64, std::max<size_t>(1, slots / 256));
+  // reduction parts: ~512 record slots (16 CTAs) each: a (key, part) CTA sums at most ~17 records of a sorted stream
+  // and all streams' (key, part) CTAs together stay within one wave of the GPU
+  ex.P = (int)std::min<size_t>(pair_keys ? 8 : 64, std::max<size_t>(1, slots / 512));
   ex.P = std::max<int>(ex.P, (int)((slots + kMaxChunk - 1) / kMaxChunk));
   CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
   CU(ex.key.ensure(slots * sizeof(int)));
@@ -337,10 +338,8 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   CU(ex.part.ensure((size_t)ex.n_keys * ex.P * ex.rd * sizeof(double)));
   CU(ex.overflow.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
   CU(ex.fin.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
-  CU(ex.ticket.ensure((size_t)ex.n_keys * sizeof(unsigned)));
-  // reduce_all_kernel folds the atomics-fallback block into fin and re-zeroes it, and re-arms the tickets
+  // reduce_all_kernel folds the atomics-fallback block into fin and re-zeroes it
   CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), g_alloc_stream));
-  CU(cudaMemsetAsync(ex.ticket.p, 0, (size_t)ex.n_keys * sizeof(unsigned), g_alloc_stream));
   ex.overflow_flag = E->d_flags.as<int>();
   return CLIC_OK;
 }
@@ -411,15 +410,13 @@ int ensure_layout(clic_estimator* E) {
     ReduceJob j{};
     j.payload = ex.payload.as<double>();
     j.key = ex.key.as<int>();
-    j.part = ex.part.as<double>();
     j.fin = ex.fin.as<double>();
     j.overflow = ex.overflow.as<double>();
     j.warp_cost = ex.cost.as<double>();
-    j.ticket = ex.ticket.as<unsigned>();
     j.n_slots = ex.n_warps * kSlotsPerWarp;
-    j.P = ex.P; j.n_keys = ex.n_keys; j.rd = ex.rd; j.n_warps = ex.n_warps;
+    j.n_keys = ex.n_keys; j.rd = ex.rd; j.n_warps = ex.n_warps;
     j.cta0 = n_part_ctas;
-    n_part_ctas += ex.n_keys * ex.P;
+    n_part_ctas += ex.n_keys;
     jobs.push_back(j);
   };
   for (auto& b : E->loam) {

@@ -436,32 +436,46 @@ template <int RD>
 __device__ __forceinline__ void reduce_part_body(const double* payload, const int* key, int r0, int r1, int k,
                                                  double* out) {
   constexpr int EPT = (RD + 255) / 256;
+  constexpr int NB = RD <= 640 ? 8 : 4;  // records in flight per thread
   __shared__ int list[kMaxChunk];
+  __shared__ unsigned hitmask[kMaxChunk / 32];
   __shared__ int n_match;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // every warp tests 32 slots per step (the key loads of the whole chunk are in flight together) ...
+  const int n_words = min(kMaxChunk / 32, (r1 - r0 + 31) / 32);
+  for (int w = warp; w < n_words; w += 8) {
+    const int r = r0 + 32 * w + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, r < r1 && key[r] == k);
+    if (lane == 0) hitmask[w] = m;
+  }
+  __syncthreads();
+  // ... and warp 0 compacts the hits into the ordered slot list (exclusive scan over the <= 32 mask words)
   if (warp == 0) {
-    int cnt = 0;
-    for (int rb = r0; rb < r1; rb += 32) {
-      const int r = rb + lane;
-      const bool hit = r < r1 && key[r] == k;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (pos < kMaxChunk) list[pos] = r;
-      }
-      cnt += __popc(m);
+    const unsigned m = lane < n_words ? hitmask[lane] : 0u;
+    int cnt = __popc(m), base = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, base, o);
+      if (lane >= o) base += v;
     }
-    if (lane == 0) n_match = min(cnt, kMaxChunk);
+    if (lane == 31) n_match = base;
+    base -= cnt;
+    unsigned mm = m;
+    while (mm) {
+      const int bit = __ffs(mm) - 1;
+      mm &= mm - 1;
+      list[base++] = r0 + 32 * lane + bit;
+    }
   }
   __syncthreads();
   const int n = n_match;
   double acc[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; i++) acc[i] = 0.0;
-  for (int j = 0; j < n; j += 4) {
-    double v[4][EPT];
+  for (int j = 0; j < n; j += NB) {
+    double v[NB][EPT];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NB; q++) {
       const bool on = j + q < n;
       const double* src = payload + (size_t)(on ? list[j + q] : 0) * RD;
 #pragma unroll
@@ -471,7 +485,7 @@ __device__ __forceinline__ void reduce_part_body(const double* payload, const in
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < NB; q++)
 #pragma unroll
       for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
   }
@@ -503,26 +517,96 @@ reduce_records_kernel(const double* payload, const int* key, int n_slots, int P,
   reduce_part_body<RD>(payload, key, r0, r1, k, out + ((size_t)k * P + part) * RD);
 }
 
-// All factor streams of a pass in ONE launch.  CTA (job, key, part) writes its ordered partial sum; the CTA that
-// finishes a key last (ticket) folds the P partials (fixed order) and the atomics-fallback block into fin[key] and
-// re-arms both.  The extra last CTA sums every job's per-warp costs.  jac == 0: only that CTA is launched.
+// All factor streams of a pass in ONE launch: CTA (job, key) walks the stream's record slots in chunks of 1024 (the
+// chunk's keys are fetched with every load in flight, the hits compacted in slot order) and sums the matching
+// payloads in that order, NB records in flight per thread; then folds the atomics-fallback block in and re-arms
+// it.  For time-sorted streams a key has ~n_CTAs / n_keys records, so this is a handful of load rounds.  The extra
+// last CTA sums every job's per-warp costs.  jac == 0: only that CTA is launched.
 struct ReduceJob {
   const double* payload;
   const int* key;
-  double* part;      // [n_keys][P][rd]
   double* fin;       // [n_keys][rd]
   double* overflow;  // [n_keys][rd], folded into fin and zeroed again
   const double* warp_cost;
-  unsigned* ticket;  // [n_keys], zero between launches
-  int n_slots, P, n_keys, rd, n_warps;
+  int n_slots, n_keys, rd, n_warps;
   int cta0;          // first CTA of the job in the flattened grid
 };
-__global__ void __launch_bounds__(256)
-reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_part_ctas, double* cost2, const int* ctl) {
+template <int RD>
+__device__ __forceinline__ void reduce_key_body(const ReduceJob& J, int k) {
+  constexpr int EPT = (RD + 255) / 256;
+  constexpr int NB = RD <= 640 ? 8 : 4;  // records in flight per thread
+  __shared__ int skey[kMaxChunk];
+  __shared__ int list[kMaxChunk];
+  __shared__ int n_match;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double acc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; i++) acc[i] = 0.0;
+  for (int r0 = 0; r0 < J.n_slots; r0 += kMaxChunk) {
+    const int r1 = min(J.n_slots, r0 + kMaxChunk);
+#pragma unroll
+    for (int i = 0; i < kMaxChunk / 256; i++) {
+      const int r = r0 + threadIdx.x + 256 * i;
+      skey[threadIdx.x + 256 * i] = r < r1 ? J.key[r] : -1;
+    }
+    __syncthreads();
+    if (warp == 0) {  // lane L owns slots 32L .. 32L+31 of the chunk: exclusive scan of the hit counts, then expand
+      unsigned m = 0;
+#pragma unroll 8
+      for (int q = 0; q < 32; q++) m |= (skey[32 * lane + q] == k ? 1u : 0u) << q;
+      int cnt = __popc(m), base = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, base, o);
+        if (lane >= o) base += v;
+      }
+      if (lane == 31) n_match = base;
+      base -= cnt;
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        list[base++] = r0 + 32 * lane + bit;
+      }
+    }
+    __syncthreads();
+    const int n = n_match;
+    for (int j = 0; j < n; j += NB) {
+      double v[NB][EPT];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const bool on = j + q < n;
+        const double* src = J.payload + (size_t)(on ? list[j + q] : 0) * RD;
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+          const int e = threadIdx.x + i * 256;
+          v[q][i] = (on && e < RD) ? src[e] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++)
+#pragma unroll
+        for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
+    }
+    __syncthreads();  // skey / list are rewritten by the next chunk
+  }
+  double* ov = J.overflow + (size_t)k * RD;
+  double* fin = J.fin + (size_t)k * RD;
+#pragma unroll
+  for (int i = 0; i < EPT; i++) {
+    const int e = threadIdx.x + i * 256;
+    if (e < RD) {
+      const double o = ov[e];
+      if (o != 0.0) ov[e] = 0.0;
+      fin[e] = acc[i] + o;
+    }
+  }
+}
+__global__ void __launch_bounds__(256, 3)
+reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_key_ctas, double* cost2, const int* ctl) {
   pdl_wait();
   pdl_trigger();
   if (ctl && ctl[0]) return;
-  if ((int)blockIdx.x == n_part_ctas) {
+  if ((int)blockIdx.x == n_key_ctas) {
     double c_tot = 0.0, f_tot = 0.0;
     for (int j = 0; j < n_jobs; j++) {
       double c, f;
@@ -539,35 +623,13 @@ reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_part_ctas, double* co
   int j = 0;
   while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].cta0) j++;
   const ReduceJob& J = jobs[j];
-  const int local = blockIdx.x - J.cta0;
-  const int k = local / J.P, part = local % J.P;
-  const int chunk = (J.n_slots + J.P - 1) / J.P;
-  const int r0 = part * chunk, r1 = min(J.n_slots, r0 + chunk);
-  double* out = J.part + ((size_t)k * J.P + part) * J.rd;
+  const int k = blockIdx.x - J.cta0;
   switch (J.rd) {
-    case 416: reduce_part_body<416>(J.payload, J.key, r0, r1, k, out); break;
-    case 640: reduce_part_body<640>(J.payload, J.key, r0, r1, k, out); break;
-    case 960: reduce_part_body<960>(J.payload, J.key, r0, r1, k, out); break;
-    default: reduce_part_body<1792>(J.payload, J.key, r0, r1, k, out); break;
+    case 416: reduce_key_body<416>(J, k); break;
+    case 640: reduce_key_body<640>(J, k); break;
+    case 960: reduce_key_body<960>(J, k); break;
+    default: reduce_key_body<1792>(J, k); break;
   }
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&J.ticket[k], 1u) == (unsigned)(J.P - 1));
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const double* parts = J.part + (size_t)k * J.P * J.rd;
-  double* ov = J.overflow + (size_t)k * J.rd;
-  double* fin = J.fin + (size_t)k * J.rd;
-  for (int e = threadIdx.x; e < J.rd; e += 256) {
-    double a = 0.0;
-    for (int p = 0; p < J.P; p++) a += __ldcg(parts + (size_t)p * J.rd + e);
-    const double o = ov[e];
-    if (o != 0.0) ov[e] = 0.0;
-    fin[e] = a + o;
-  }
-  if (threadIdx.x == 0) J.ticket[k] = 0u;
 }
 
 // Sum of per-warp costs in warp order (single CTA, deterministic tree over fixed positions).
