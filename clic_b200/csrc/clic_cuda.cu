@@ -604,6 +604,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 4);
+    b->st.toff_free = E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1 : 0;
     if (jac) {
       E->prof_begin(1);
       CU(launch_pdl(imu_kernel<true, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
@@ -873,7 +874,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     imu_kernel<true, true><<<ex.grid, kThreads, factor_smem_bytes(K, 5), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
     if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
     E->launches += 2;
-    if ((rc = mark(ex, 34))) return rc;
+    if ((rc = mark(ex, imu_phys_col<true>(34)))) return rc;
     bool used = false;
     for (int s = 0; s < ex.n_keys; s++) used = used || present[s];
     if (used) {
@@ -1239,7 +1240,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_pt.as<double>(), r_type.as<int32_t>(), r_plane.as<double>(), r_normal.as<double>(),
-      r_gpoint.as<double>(), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
+      r_gpoint.as<double>(), ldq(S_LtoI), ldv(p_LinI), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
       B->p[2].as<double>(), B->g[0].as<double>(), B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(),
       B->g[4].as<double>(), B->g[5].as<double>(), B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>(),
       E->d_flags.as<int>() + 1);
@@ -1260,6 +1261,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   B->st.sh.S_LtoI = ldq(S_LtoI);
   B->st.sh.p_LinI = ldv(p_LinI);
   B->st.sh.weight = weight;
+  B->st.sh.point_in_imu = true;  // the prep kernel stored S_LtoI p_L + p_LinI
   B->st.sh.gm_identity = S_GtoM[0] == 0.0 && S_GtoM[1] == 0.0 && S_GtoM[2] == 0.0 && S_GtoM[3] == 1.0 &&
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
@@ -1301,7 +1303,7 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   CU(B->type.ensure(n));
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
-      n, r_t.as<double>(), r_pt.as<double>(), r_type.as<uint8_t>(), r_geo.as<double>(), t_min, t_max,
+      n, r_t.as<double>(), r_pt.as<double>(), r_type.as<uint8_t>(), r_geo.as<double>(), ldq(S_LtoI), ldv(p_LinI), t_min, t_max,
       B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
       B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
       B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>());
@@ -1322,6 +1324,7 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   B->st.sh.S_LtoI = ldq(S_LtoI);
   B->st.sh.p_LinI = ldv(p_LinI);
   B->st.sh.weight = weight;
+  B->st.sh.point_in_imu = true;  // the prep kernel stored S_LtoI p_L + p_LinI
   B->st.sh.gm_identity = S_GtoM[0] == 0.0 && S_GtoM[1] == 0.0 && S_GtoM[2] == 0.0 && S_GtoM[3] == 1.0 &&
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;

@@ -89,6 +89,7 @@ CLIC_HD M3 lamJr(const PairData& P, double lam, double ca, double cb, double sig
 struct LoamShared {  // arguments of AddLoamMeasurementAnalytic shared by a batch (trajectory_estimator.cpp:712-716)
   Q4 S_GtoM; V3 p_GinM; Q4 S_LtoI; V3 p_LinI; double weight;
   bool gm_identity;  // S_GtoM = I, p_GinM = 0: every production call (trajectory_manager.cpp:676-680) -> skip two rotations
+  bool point_in_imu; // the stream already holds p_I = S_LtoI p_L + p_LinI (rotated once at add time by the prep kernel)
 };
 
 // LoamFeatureFactor::Evaluate.  geo = plane (n.x n.y n.z d) or line (point xyz, direction xyz).
@@ -115,7 +116,7 @@ CLIC_HD void loam_eval_to(const WindowView& W, int s, double u, V3 pL, bool is_p
     A[i] = acc;
   }
   Q4 R = qmul(ldq(W.kq + 4 * s), qconj(acc));  // Ri * A_accum_inv.inverse()
-  V3 p_I = qrot(sh.S_LtoI, pL) + sh.p_LinI;
+  V3 p_I = sh.point_in_imu ? pL : qrot(sh.S_LtoI, pL) + sh.p_LinI;
   V3 pos = mk(0, 0, 0);
 #pragma unroll
   for (int i = 0; i < 4; i++) pos = fma3(c[i], ldv(W.kp + 3 * (s + i)), pos);

@@ -677,6 +677,7 @@ struct ImuStream {
   int bias_slot;
   int extras_free;  // a bias / time-offset block of these factors is a free parameter (options, known at add time)
   int marg_always;  // marg mode: a non-knot block of these factors is dropped, so they all enter the prior
+  int toff_free;    // the IMU time offset has a column in H (set per pass from the layout)
 };
 
 template <int NT>
@@ -694,8 +695,9 @@ struct SmemRowSink {
 };
 
 // IMU rows are stored in a PHYSICAL column order that packs the columns the gyro rows touch into the first three
-// tiles:  [dtheta x12 | bg | t_off | r | ba | (gravity) | dp x12 | pad].  Gyro rows (0..2) have zero dp / ba /
-// gravity blocks, so their last tile(s) are skipped: 6 instead of 10 (15 in marg mode) tile products.
+// tiles:  [dtheta x12 | bg | r | t_off | ba | (gravity) | dp x12 | pad].  Gyro rows (0..2) have zero dp / ba /
+// gravity blocks, so their last tile(s) are skipped: 6 instead of 10 (15 in marg mode) tile products — and only 3
+// (two column tiles) when the IMU time offset is a constant (every shipped LIO call): its column is never assembled.
 // Logical order (what factor_eval emits, what the assembly addresses): [knot k: dtheta dp] x4 | bg | ba | (g) | t_off | r.
 template <bool MARG>
 __host__ __device__ constexpr int imu_phys_col(int l) {
@@ -704,11 +706,11 @@ __host__ __device__ constexpr int imu_phys_col(int l) {
   if (l < 30) return 17 + (l - 27);                       // ba
   if (MARG) {
     if (l < 33) return 20 + (l - 30);                     // gravity
-    if (l == 33) return 15;                               // t_off
-    if (l == 34) return 16;                               // r
+    if (l == 33) return 16;                               // t_off
+    if (l == 34) return 15;                               // r
     return l;                                             // pad 35..39
   }
-  return l == 30 ? 15 : 16;                               // t_off, r
+  return l == 30 ? 16 : 15;                               // t_off, r
 }
 template <bool MARG>
 struct ImuRowSink {
@@ -716,6 +718,7 @@ struct ImuRowSink {
   double* Jt;
   int lane;
   bool on;
+  bool gyro2;  // t_off is constant: gyro rows only need the first two column tiles
   WarpAcc<NT>* acc;
   __device__ __forceinline__ void put(int row, int col, double v) {
     const int pc = imu_phys_col<MARG>(col);
@@ -724,7 +727,11 @@ struct ImuRowSink {
   }
   __device__ __forceinline__ void row_done(int row) {
     __syncwarp();
-    if (row < 3) acc->template accumulate<3>(Jt, lane); else acc->template accumulate<NT>(Jt, lane);
+    if (row < 3) {
+      if (gyro2) acc->template accumulate<2>(Jt, lane); else acc->template accumulate<3>(Jt, lane);
+    } else {
+      acc->template accumulate<NT>(Jt, lane);
+    }
     __syncwarp();
   }
 };
@@ -794,6 +801,7 @@ imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
         }
         ImuRowSink<MARG> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
+        sink.gyro2 = !MARG && !st.toff_free;
         double rho = imu_eval<MARG>(W, mine ? s : kmin, mine ? u : 0.0, gy, ac, sh, true, sink);
         if (mine) { if (s + 3 >= pp.kf || st.extras_free || MARG) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       } else {
@@ -1128,7 +1136,7 @@ __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, State
 // (trajectory_estimator.cpp:272-292); AoS(3n) -> planar.
 __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* point, const int32_t* geo_type,
                                  const double* geo_plane, const double* geo_normal, const double* geo_point,
-                                 int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0, double* p1, double* p2,
+                                 Q4 S_LtoI, V3 p_LinI, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0, double* p1, double* p2,
                                  double* g0, double* g1, double* g2, double* g3, double* g4, double* g5, uint8_t* type,
                                  unsigned long long* n_dropped, int* bad_input) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1137,7 +1145,8 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
   bool ok = !(t < t_lo || t >= t_hi);
   t_ns[i] = ok ? t : kDropped;
   if (!ok) atomicAdd(n_dropped, 1ULL);
-  p0[i] = point[3 * i]; p1[i] = point[3 * i + 1]; p2[i] = point[3 * i + 2];
+  const V3 pI = qrot(S_LtoI, mk(point[3 * i], point[3 * i + 1], point[3 * i + 2])) + p_LinI;  // LoamShared::point_in_imu
+  p0[i] = pI.x; p1[i] = pI.y; p2[i] = pI.z;
   const bool plane = geo_type[i] == 1;
   type[i] = plane ? 1 : 0;
   if ((plane && !geo_plane) || (!plane && (!geo_normal || !geo_point))) {  // record type present, its array missing
@@ -1156,7 +1165,7 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
 }
 
 __global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const double* point, const uint8_t* geo_type,
-                                        const double* geo, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
+                                        const double* geo, Q4 S_LtoI, V3 p_LinI, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
                                         double* p1, double* p2, double* g0, double* g1, double* g2, double* g3,
                                         double* g4, double* g5, uint8_t* type, unsigned long long* n_dropped) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1165,7 +1174,8 @@ __global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const doub
   bool ok = !(t < t_lo || t >= t_hi);
   t_ns[i] = ok ? t : kDropped;
   if (!ok) atomicAdd(n_dropped, 1ULL);
-  p0[i] = point[3 * i]; p1[i] = point[3 * i + 1]; p2[i] = point[3 * i + 2];
+  const V3 pI = qrot(S_LtoI, mk(point[3 * i], point[3 * i + 1], point[3 * i + 2])) + p_LinI;  // LoamShared::point_in_imu
+  p0[i] = pI.x; p1[i] = pI.y; p2[i] = pI.z;
   type[i] = geo_type[i] == 1 ? 1 : 0;
   g0[i] = geo[6 * i]; g1[i] = geo[6 * i + 1]; g2[i] = geo[6 * i + 2];
   g3[i] = geo[6 * i + 3]; g4[i] = geo[6 * i + 4]; g5[i] = geo[6 * i + 5];

@@ -791,7 +791,7 @@ __global__ void key_presence_kernel(const double* part, const double* overflow, 
   for (int p = 0; p <= P && !any; p++) {
     const double* blk = p < P ? part + ((size_t)s * P + p) * rd : overflow + (size_t)s * rd;
     for (int l = 0; l < 24 && !any; l++) any = block_entry(blk, NT, l, l) != 0.0;
-    any = any || block_entry(blk, NT, r_col, r_col) != 0.0;
+    if (r_col >= 0) any = any || block_entry(blk, NT, r_col, r_col) != 0.0;  // physical column of r~
   }
   present[s] = any ? 1 : 0;
 }

@@ -40,6 +40,7 @@ __attribute__((visibility("default"))) int emul_loam(int K, const double* kq, co
   LoamShared sh;
   sh.S_GtoM = ldq(S_GtoM); sh.p_GinM = ldv(p_GinM); sh.S_LtoI = ldq(S_LtoI); sh.p_LinI = ldv(p_LinI); sh.weight = weight;
   sh.gm_identity = false;
+  sh.point_in_imu = false;
   loam_eval(W.view, s, u, ldv(pL), is_plane != 0, geo, sh, true, r, J, weight);
   *s_out = s;
   *u_out = u;
