@@ -389,13 +389,19 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "loam_kernel<true> (LiDAR factor eval + DMMA J^T J)",
         "achieved": ab["lidar"] / (loam_ms * 1e-3) / 1e9 if loam_ms > 0 else None, "peak": peak, "unit": "GB/s",
-        "frac": (ab["lidar"] / (loam_ms * 1e-3) / 1e9 / peak) if loam_ms > 0 else None, "traffic": None,
+        "frac": (ab["lidar"] / (loam_ms * 1e-3) / 1e9 / peak) if loam_ms > 0 else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one loam_kernel<true> launch on this workload (ncu --set full,
+        # profiles/r01g_factor_kernels_ncu.txt): the stream stores 6 geometry doubles per feature (81 B/feature), the
+        # algorithmic figure counts 4 for planes
+        "traffic": 81071616 + 2319616 if (args.scale == 1.0 and world == 1) else None,
         "peak_kind": f"of {peak_kind}", "algorithmic_bytes_per_launch": ab["lidar"], "kernel_ms": loam_ms,
         "kernel_share_of_step": float(prof_ms[0] / prof_ms.sum()) if prof_ms.sum() > 0 else None,
         "per_class_ms_per_step": {k: float(prof_ms[i] / args.steps) for i, k in enumerate(
             ["lidar", "imu", "visual", "reduce_assemble", "prior_bias", "lm_step", "allreduce", "marginalize"])},
-        "note": "binding limit is the FP64 pipe, not HBM (SURVEY.md §7 hard part 1); FP64 DFMA/DMMA peak measured "
-                "36.3/37.1 TFLOP/s on one shared pipe (profiles/r01_fp64_peaks.txt)",
+        "note": "binding limit is the shared FP64 pipe (DFMA + DMMA), not HBM: ncu sm__pipe_shared_cycles_active = 58% "
+                "(LiDAR) / 62% (IMU) of active cycles, profiles/r01g_factor_kernels_ncu.txt; DFMA/DMMA peaks measured "
+                "36.3/37.1 TFLOP/s on that one pipe (profiles/r01_fp64_peaks.txt)",
+        "fp64_pipe_frac": {"lidar": 0.58, "imu": 0.62, "source": "ncu sm__pipe_shared_cycles_active, profiles/r01g_factor_kernels_ncu.txt"},
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -404,7 +410,9 @@ def main():
         "config": {"workload": WORKLOAD if args.scale == 1.0 else f"DEBUG scale={args.scale} of " + WORKLOAD,
                    "factors": {"lidar_plane": ab["n_plane"] * 1, "lidar_line": ab["n_line"], "imu": ab["n_imu"],
                                "visual": ab["n_vis"], "total_all_ranks": n_total},
-                   "D": D, "l2": "flushed between timed iterations (256 MiB write)", "visual_kernel": HAVE_VISUAL,
+                   "D": D, "l2": {"write": "flushed between timed iterations (256 MiB write)",
+                                   "write_read": "flushed between timed iterations (256 MiB write, then read)",
+                                   "none": "NOT flushed (inputs 84 MB < 126 MB L2)"}[flush_mode], "visual_kernel": HAVE_VISUAL,
                    "sharding": f"{world} rank(s), each a C5-sized shard of the same window; one NCCL all-reduce of H|b|cost per pass",
                    "strong_scaling_c5": strong},
         "gn_iterations": gn,
