@@ -941,7 +941,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     knot_col[k] = c;
     if (c >= 0) for (int a = 0; a < 6; a++) { col_knot[c + a] = k; col_sub[c + a] = a; }
   }
-  DevBuf d_kc, d_ck, d_cs, d_desc, d_A, d_b, d_J0, d_r0, d_status, d_cost;
+  DevBuf d_kc, d_ck, d_cs, d_desc, d_A, d_b, d_J0, d_r0, d_status, d_cost, d_perm, d_dscr;
   if ((rc = to_device(E, d_kc, knot_col.data(), K)) || (rc = to_device(E, d_ck, col_knot.data(), pos)) ||
       (rc = to_device(E, d_cs, col_sub.data(), pos)))
     return rc;
@@ -977,7 +977,9 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   CU(d_b.ensure((size_t)pos * sizeof(double)));
   CU(d_J0.ensure((size_t)n * n * sizeof(double)));
   CU(d_r0.ensure((size_t)n * sizeof(double)));
-  CU(d_status.ensure(sizeof(int)));
+  CU(d_status.ensure(4 * sizeof(int)));
+  CU(d_perm.ensure((size_t)pos * sizeof(int)));
+  CU(d_dscr.ensure((size_t)2 * pos * sizeof(double)));
   CU(d_cost.ensure(2 * sizeof(double)));
   CU(cudaMemsetAsync(d_cost.p, 0, 2 * sizeof(double), E->stream));
   ColMaps cm;
@@ -1016,10 +1018,11 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     E->launches++;
     CU(cudaStreamSynchronize(E->stream));  // h_meta is reused by the solve path
   }
-  int status = -1;
-  CU(cudaMemsetAsync(d_status.p, 0xff, sizeof(int), E->stream));
+  int status4[4] = {-1, -1, -1, -1};
+  int& status = status4[0];
+  CU(cudaMemsetAsync(d_status.p, 0xff, 4 * sizeof(int), E->stream));
   schur_kernel<<<1, 512, 0, E->stream>>>(d_A.as<double>(), d_b.as<double>(), m, n, d_J0.as<double>(), d_r0.as<double>(),
-                                         d_status.as<int>());
+                                         d_perm.as<int>(), d_dscr.as<double>(), d_status.as<int>());
   E->launches++;
   E->prof_end();
   std::unique_ptr<clic_prior> P(new clic_prior);
@@ -1028,16 +1031,15 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   P->J0.resize((size_t)n * n);
   P->r0.resize(n);
   std::vector<double> h(E->sl.size());
-  CU(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(status4, d_status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaMemcpyAsync(P->J0.data(), d_J0.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaMemcpyAsync(P->r0.data(), d_r0.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaMemcpyAsync(h.data(), E->d_state.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
-  if (status == 6)
-    return fail(CLIC_ERR_NOT_POSITIVE_DEFINITE,
-                "marginalization: A_mm or the Schur complement is not positive definite (rank-deficient blocks need the "
-                "eigen-decomposition path of marginalization_factor.cpp:208-264, not built on the GPU yet)");
+  if (ScopedTrace::on())
+    fprintf(stderr, "[clic trace] schur: m %d n %d status %d rank deficiency A_mm %d, Schur complement %d\n", m, n, status4[0],
+            status4[1], status4[2]);
   if (status != 0) return fail(CLIC_ERR_CUDA, "schur kernel did not complete");
   for (auto& b : blocks) {
     if (b.drop) continue;

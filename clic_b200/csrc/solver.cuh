@@ -107,7 +107,8 @@ constexpr int kNB = 8;
 // Warp 0, lane l < nb holds row l of the kNB x kNB diagonal block in registers; columns are eliminated with warp
 // shuffles (no shared-memory round trips on the serial critical path).  Writes L back and, if Li != nullptr, the
 // inverse of the block (row-major kNB x kNB, zero padded) used by the panel and triangular solves.
-__device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* Li, int* ok, int lane) {
+__device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* Li, int* ok, int lane,
+                                                const double* dtol = nullptr) {
   const unsigned full = 0xffffffffu;
   double a[kNB];
 #pragma unroll
@@ -116,7 +117,7 @@ __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int n
   for (int j = 0; j < kNB; j++) {
     double d = __shfl_sync(full, a[j], j);
     if (j < nb) {
-      if (!(d > 0.0) || !isfinite(d)) {
+      if (!(d > (dtol ? dtol[kb + j] : 0.0)) || !isfinite(d)) {
         if (lane == 0) *ok = 0;
         d = 1.0;
       }
@@ -156,12 +157,15 @@ __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int n
 }
 
 // Linv: nullptr (panel by substitution) or ceil(n/kNB) * 64 doubles receiving the inverses of the diagonal blocks.
-__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* Linv = nullptr) {
+// dtol[j]: pivot j <= dtol[j] counts as "not positive definite" (nullptr = 0 for the damped LM system; in K8
+// n * eps * the column's original diagonal, i.e. the column is numerically dependent on the previous ones).
+__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* Linv = nullptr,
+                                             const double* dtol = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int kb = 0; kb < n; kb += kNB) {
     const int nb = min(kNB, n - kb);
     double* Li = Linv ? Linv + (size_t)(kb / kNB) * kNB * kNB : nullptr;
-    if (tid < 32) warp_diag_block(A, ld, kb, nb, Li, ok, tid);
+    if (tid < 32) warp_diag_block(A, ld, kb, nb, Li, ok, tid, dtol);
     __syncthreads();
     if (!*ok) return;
     for (int i = kb + nb + tid; i < n; i += nt) {
@@ -705,17 +709,137 @@ __global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
 namespace clic {
 
 // ---------------- K8: marginalization (MarginalizationInfo::marginalize, marginalization_factor.cpp:150-276) ----------------
+// Rank-revealing Cholesky with diagonal pivoting (the dpstrf scheme), one CTA, unblocked, on a FULL symmetric n x n
+// block (both triangles valid, leading dimension ld):  P^T A P = L L^T with L n x r, r = numerical rank (stop when the
+// largest remaining diagonal <= n * eps * largest initial diagonal).  perm[i] = original index at position i.  On
+// return the lower triangle holds L in pivoted position order (columns >= r are to be ignored).
+__device__ __forceinline__ void cta_pivoted_cholesky(double* A, int ld, int n, int* perm, int* rank_out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double s_val[512];
+  __shared__ int s_idx[512];
+  __shared__ double s_tol;
+  __shared__ int s_stop;
+  for (int i = tid; i < n; i += nt) perm[i] = i;
+  if (tid == 0) s_stop = 0;
+  __syncthreads();
+  int rank = n;
+  for (int k = 0; k < n; k++) {
+    // pivot = largest remaining diagonal (ties -> lowest index, fixed order)
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += nt) {
+      const double d = A[(size_t)i * ld + i];
+      if (d > best) { best = d; bi = i; }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int o = nt / 2; o > 0; o >>= 1) {
+      if (tid < o) {
+        const double v = s_val[tid + o];
+        const int j = s_idx[tid + o];
+        if (v > s_val[tid] || (v == s_val[tid] && j < s_idx[tid])) { s_val[tid] = v; s_idx[tid] = j; }
+      }
+      __syncthreads();
+    }
+    const int piv = s_idx[0];
+    const double d = s_val[0];
+    if (tid == 0) {
+      if (k == 0) s_tol = (double)n * 2.220446049250313e-16 * d;
+      if (!(d > s_tol) || !isfinite(d)) s_stop = 1;
+    }
+    __syncthreads();
+    if (s_stop) { rank = k; break; }
+    if (piv != k) {  // symmetric swap of rows / columns k <-> piv over the full block
+      for (int j = tid; j < n; j += nt) {
+        const double t = A[(size_t)k * ld + j];
+        A[(size_t)k * ld + j] = A[(size_t)piv * ld + j];
+        A[(size_t)piv * ld + j] = t;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        const double t = A[(size_t)i * ld + k];
+        A[(size_t)i * ld + k] = A[(size_t)i * ld + piv];
+        A[(size_t)i * ld + piv] = t;
+      }
+      if (tid == 0) { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+      __syncthreads();
+    }
+    const double lkk = sqrt(d), inv = 1.0 / lkk;
+    for (int i = k + 1 + tid; i < n; i += nt) A[(size_t)i * ld + k] *= inv;  // column k of L (row k keeps A's values)
+    __syncthreads();
+    if (tid == 0) A[(size_t)k * ld + k] = lkk;
+    // trailing block, both triangles: A[i][j] -= L[i][k] L[j][k]
+    const int t = n - k - 1;
+    for (int e = tid; e < t * t; e += nt) {
+      const int i = k + 1 + e / t, j = k + 1 + e % t;
+      A[(size_t)i * ld + j] -= A[(size_t)i * ld + k] * A[(size_t)j * ld + k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *rank_out = rank;
+  __syncthreads();
+}
+
+// Factor a full symmetric n x n block: plain blocked Cholesky first; if a pivot is <= n*eps*(its original diagonal)
+// — a column numerically dependent on the previous ones — the block is restored, Jacobi-scaled (S A S, unit diagonal:
+// the test is then independent of the units of the parameters, e.g. time offsets in ns next to metres) and factored
+// with pivoting, and L is unscaled in place.  Returns the rank (every thread); perm = identity on the plain path.
+// d0: n doubles of scratch (original diagonal), dtol: n doubles of scratch.
+__device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* perm, double* d0, double* dtol, int* ok,
+                                                int* rank_sh) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < n; i += nt) {
+    d0[i] = A[(size_t)i * ld + i];
+    dtol[i] = (double)n * 2.220446049250313e-16 * fabs(d0[i]);
+    perm[i] = i;
+  }
+  if (tid == 0) *ok = 1;
+  __syncthreads();
+  cta_cholesky(A, ld, n, ok, nullptr, dtol);
+  __syncthreads();
+  if (*ok) return n;
+  // restore (the failed attempt touched the lower triangle and the diagonal only) and scale
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, j = e % n;
+    const double si = d0[i] > 0.0 ? rsqrt(d0[i]) : 0.0, sj = d0[j] > 0.0 ? rsqrt(d0[j]) : 0.0;
+    const double v = i == j ? d0[i] : (j < i ? A[(size_t)j * ld + i] : A[(size_t)i * ld + j]);
+    if (j <= i) {
+      A[(size_t)i * ld + j] = v * si * sj;
+      A[(size_t)j * ld + i] = v * si * sj;
+    }
+  }
+  __syncthreads();
+  cta_pivoted_cholesky(A, ld, n, perm, rank_sh);
+  const int r = *rank_sh;
+  for (int e = tid; e < n * r; e += nt) {  // L = S^-1 L_s: row i (position order) belongs to original column perm[i]
+    const int i = e / r, k = e % r;
+    if (k <= i) A[(size_t)i * ld + k] *= sqrt(fmax(d0[perm[i]], 0.0));
+  }
+  __syncthreads();
+  if (tid == 0) *ok = 1;
+  __syncthreads();
+  return r;
+}
+
 // Schur complement of the first m (dropped) tangent dimensions of the pos x pos system (A, b), then the prior's
 // square-root form.  The reference inverts A_mm and factors the result by symmetric eigendecompositions with an
-// eigenvalue cut of 1e-15 (":208-264"); for the positive-definite systems of a well-constrained window the Cholesky
-// route below gives the same A' = A_rr - A_rm A_mm^-1 A_mr, b' and the same prior energy with
-// J0 = L'^T, r0 = L'^-1 b' (J0^T J0 = A', J0^T r0 = b').  A rank-deficient block reports status 6.
-//   A: pos x pos row-major, symmetric (both triangles valid); overwritten.   J0: n x n, r0: n.   status[0] = 0 ok.
-__global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m, int n, double* J0, double* r0, int* status) {
+// eigenvalue cut of 1e-15 (":208-264").  Here: plain Cholesky first — for the positive-definite systems of a
+// well-constrained window it gives the same A' = A_rr - A_rm A_mm^-1 A_mr, b' and the same prior energy with
+// J0 = L'^T, r0 = L'^-1 b' (J0^T J0 = A', J0^T r0 = b').  If a block is not positive definite, the rank-revealing
+// pivoted factorization above takes over: for a positive semi-definite system the generalized Schur complement does not
+// depend on which generalized inverse of A_mm is used, so G = P [L_r^-T L_r^-1, 0; 0, 0] P^T gives what the truncated
+// eigen pseudo-inverse gives, and J0 = [L_r^T P^T; 0], r0 = [L_r^-1 (P^T b')_r; 0] reproduces J0^T J0 = A' and
+// J0^T r0 = proj_range(A') b' = V V^T b'.   (Differs from the reference only where it inverts noise-level eigenvalues
+// between 1e-15 and n*eps*max|diag|.)
+//   A: pos x pos row-major, symmetric (both triangles valid); overwritten.   J0: n x n, r0: n.   perm: pos ints.
+//   status[0] = 0 ok;  status[1] = rank deficiency of A_mm;  status[2] = rank deficiency of the Schur complement.
+__global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m, int n, double* J0, double* r0,
+                                                    int* perm, double* dscr, int* status) {
   const int pos = m + n;
   const int tid = threadIdx.x, nt = blockDim.x;
-  __shared__ int ok;
-  if (tid == 0) ok = 1;
+  __shared__ int ok, rank;
+  if (tid == 0) { ok = 1; status[1] = 0; status[2] = 0; }
   __syncthreads();
   if (m > 0) {
     // Amm = 0.5 (A_mm + A_mm^T)  (":208")
@@ -724,22 +848,20 @@ __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m,
       if (j < i) {
         const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
         A[(size_t)i * pos + j] = v;
+        A[(size_t)j * pos + i] = v;
       }
     }
     __syncthreads();
-    cta_cholesky(A, pos, m, &ok);
-    __syncthreads();
-    if (!ok) {
-      if (tid == 0) status[0] = 6;
-      return;
-    }
-    // X = L^-1 A_mr (m x n) in place, one column per thread; y = L^-1 b_m
+    const int rm = cta_factor_block(A, pos, m, perm, dscr, dscr + pos, &ok, &rank);
+    if (tid == 0) status[1] = m - rm;
+    // X = L_r^-1 (P^T A_mr) (rm x n) in place at rows perm[i], one column per thread; y = L_r^-1 (P^T b_m)
     for (int c = tid; c < n + 1; c += nt) {
-      for (int i = 0; i < m; i++) {
-        double v = c < n ? A[(size_t)i * pos + m + c] : b[i];
-        for (int k = 0; k < i; k++) v -= A[(size_t)i * pos + k] * (c < n ? A[(size_t)k * pos + m + c] : b[k]);
+      for (int i = 0; i < rm; i++) {
+        const int ri = perm[i];
+        double v = c < n ? A[(size_t)ri * pos + m + c] : b[ri];
+        for (int k = 0; k < i; k++) v -= A[(size_t)i * pos + k] * (c < n ? A[(size_t)perm[k] * pos + m + c] : b[perm[k]]);
         v /= A[(size_t)i * pos + i];
-        if (c < n) A[(size_t)i * pos + m + c] = v; else b[i] = v;
+        if (c < n) A[(size_t)ri * pos + m + c] = v; else b[ri] = v;
       }
     }
     __syncthreads();
@@ -748,34 +870,44 @@ __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m,
       const int i = e / n, j = e % n;
       if (j <= i) {
         double acc = 0.0;
-        for (int k = 0; k < m; k++) acc += A[(size_t)k * pos + m + i] * A[(size_t)k * pos + m + j];
+        for (int k = 0; k < rm; k++) acc += A[(size_t)perm[k] * pos + m + i] * A[(size_t)perm[k] * pos + m + j];
         A[(size_t)(m + i) * pos + m + j] -= acc;
       }
     }
     for (int i = tid; i < n; i += nt) {
       double acc = 0.0;
-      for (int k = 0; k < m; k++) acc += A[(size_t)k * pos + m + i] * b[k];
+      for (int k = 0; k < rm; k++) acc += A[(size_t)perm[k] * pos + m + i] * b[perm[k]];
       b[m + i] -= acc;
     }
     __syncthreads();
   }
-  // A' = L' L'^T on the kept block; J0 = L'^T, r0 = L'^-1 b'
+  // A' = L' L'^T on the kept block; J0 = L'^T, r0 = L'^-1 b'.  The updated values live in the lower triangle: mirror
+  // them first (cta_factor_block wants both triangles).
   double* Ar = A + (size_t)m * pos + m;
-  cta_cholesky(Ar, pos, n, &ok);
-  __syncthreads();
-  if (!ok) {
-    if (tid == 0) status[0] = 6;
-    return;
-  }
   for (int e = tid; e < n * n; e += nt) {
     const int i = e / n, j = e % n;
-    J0[e] = j >= i ? Ar[(size_t)j * pos + i] : 0.0;  // J0[i][j] = L'[j][i]
+    if (j < i) Ar[(size_t)j * pos + i] = Ar[(size_t)i * pos + j];
+  }
+  __syncthreads();
+  int* permr = perm + m;
+  const int rn = cta_factor_block(Ar, pos, n, permr, dscr, dscr + pos, &ok, &rank);
+  if (tid == 0) status[2] = n - rn;
+  // J0[k][perm[a]] = L'[a][k] for k < rn (a >= k), zero rows below
+  for (int e = tid; e < n * n; e += nt) J0[e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < n * n; e += nt) {
+    const int k = e / n, a = e % n;
+    if (k < rn && a >= k) J0[(size_t)k * n + permr[a]] = Ar[(size_t)a * pos + k];
   }
   if (tid == 0) {
     for (int i = 0; i < n; i++) {
-      double v = b[m + i];
-      for (int k = 0; k < i; k++) v -= Ar[(size_t)i * pos + k] * r0[k];
-      r0[i] = v / Ar[(size_t)i * pos + i];
+      if (i < rn) {
+        double v = b[m + permr[i]];
+        for (int k = 0; k < i; k++) v -= Ar[(size_t)i * pos + k] * r0[k];
+        r0[i] = v / Ar[(size_t)i * pos + i];
+      } else {
+        r0[i] = 0.0;
+      }
     }
     status[0] = 0;
   }

@@ -10,6 +10,7 @@ from clic_b200 import synthetic as S
 from clic_b200._abi import BLOCK_BIAS_ACCEL, BLOCK_BIAS_GYRO, BLOCK_KNOT_POS, BLOCK_KNOT_ROT
 from test_gpu_parity import rel, rel_scaled
 from test_gpu_solve import rot_err
+import oracle_lib
 
 pytestmark = pytest.mark.gpu
 
@@ -116,3 +117,80 @@ def test_nothing_to_keep(cuda, oracle):
                                        L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"],
                                        True)
         assert est.SaveMarginalizationInfo() is None
+
+
+def _marg_lidar_only(lib, sw, later, weight):
+    opt = E.default_options(lib)
+    opt.is_marg_state = 1
+    opt.ctrl_to_be_opt_now = 0
+    opt.ctrl_to_be_opt_later = later
+    est = E.TrajectoryEstimator(sw.window, opt, lib)
+    L = sw.lidar
+    est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                   L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], weight, True)
+    pr = est.SaveMarginalizationInfo()
+    assert pr is not None
+    return pr.dims(), pr.read(), pr.normal()
+
+
+def test_degenerate_geometry_zero_columns(cuda, oracle):
+    """LiDAR degeneracy: every plane normal lies in the x-z plane, so no factor constrains the y position of any knot:
+    those columns of A_mm and of the Schur complement are exactly zero.  The reference zeroes the eigenvalues <= 1e-15
+    (marginalization_factor.cpp:209-213, 253-258); the GPU's Cholesky meets a zero pivot and switches to the
+    rank-revealing pivoted factorization.  Same prior: A = J0^T J0, g = J0^T r0."""
+    sw = S.make_window(12, n_lidar=600, n_imu=0, seed=813, init_noise=(1e-3, 2e-3), line_fraction=0.0)
+    L = sw.lidar
+    gt = S.SplineNP(sw.window.t0_ns, sw.window.dt_ns, sw.gt_knot_q, sw.gt_knot_p)
+    t_eff = (L["t_point"] * 1e9).astype(np.int64)
+    p_G = S.qrot(gt.rotation(t_eff), S.qrot(L["S_LtoI"], L["point"]) + L["p_LinI"]) + gt.position(t_eff)
+    nrm = L["geo_plane"][:, :3].copy()
+    nrm[:, 1] = 0.0
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d = -np.sum(nrm * p_G, axis=1) + np.random.default_rng(3).normal(0, 0.01, len(nrm))
+    L["geo_plane"] = np.concatenate([nrm, d[:, None]], axis=1)
+    (dg, rg, (Ag, gg)), (do, ro, (Ao, go)) = (_marg_lidar_only(lib, sw, 5, 50.0) for lib in (cuda, oracle))
+    assert dg == do, (dg, do)
+    n = do[0]
+    for k in ("kind", "id", "offset"):
+        assert np.array_equal(rg[k], ro[k]), k
+    zero = np.abs(np.diag(Ao)) < 1e-9 * np.abs(Ao).max()
+    assert zero.sum() >= 2 and zero.sum() < n                      # the y-position columns of the kept knots
+    assert np.abs(Ag[zero]).max() <= 1e-9 * np.abs(Ao).max()
+    assert rel(Ag, Ao) < 1e-7, rel(Ag, Ao)
+    assert np.abs(gg - go).max() / np.abs(go).max() < 1e-7
+
+
+def test_fewer_factors_than_dropped_dimensions(cuda, oracle):
+    """8 LiDAR factors on 30 dropped dimensions: A_mm has rank 8, and since every factor of a prior touches a dropped
+    block the exact Schur complement is ZERO (rank A = rank A_mm).  The reference formula is not usable as the
+    yardstick here: it inverts the round-off eigenvalues of A_mm that happen to be positive (cut 1e-15) and forms
+    A_mm^+ explicitly, which buries the real part (1e-8) under the round-off part (1e+9) — the oracle, restating it as
+    written, returns A_rr unreduced.  The GPU is checked against the definition (numpy pinv of the system assembled
+    from the oracle's per-factor Jacobians)."""
+    sw = S.make_window(12, n_lidar=14, n_imu=0, seed=811, init_noise=(1e-3, 2e-3), line_fraction=0.3)
+    w = 1.0e4
+    dg, rg, (Ag, gg) = _marg_lidar_only(cuda, sw, 5, w)
+    # the prior's system from per-factor rows: solve-mode estimator, all knots free, same gates as the marg set
+    L = sw.lidar
+    est = E.TrajectoryEstimator(sw.window, E.default_options(oracle), oracle)
+    est.SetFixedIndex(-1)
+    est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                   L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], w)
+    s_idx, _ = est.indices(0)
+    rows, res = [], []
+    for i in range(len(s_idx)):
+        r, J = oracle_lib.block_jacobian(oracle, est, i)
+        if s_idx[i] < 5 and abs(r[0] / w) < 0.05:
+            rows.append(J[0])
+            res.append(r[0])
+    J, r = np.array(rows), np.array(res)
+    J = J[:, np.abs(J).sum(0) > 0]
+    A, b = J.T @ J, J.T @ r
+    n, _, m = dg
+    assert A.shape[0] == m + n and np.linalg.matrix_rank(A[:m, :m]) < m
+    Ainv = np.linalg.pinv(A[:m, :m], rcond=1e-12, hermitian=True)
+    S_true = A[m:, m:] - A[m:, :m] @ Ainv @ A[:m, m:]
+    scale = np.abs(A[m:, m:]).max()
+    assert np.abs(S_true).max() < 1e-9 * scale                     # zero by the rank argument
+    assert np.abs(Ag).max() < 1e-9 * scale, np.abs(Ag).max() / scale
+    assert np.abs(gg).max() < 1e-7 * np.abs(b[m:]).max()
