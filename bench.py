@@ -378,6 +378,24 @@ def main():
     e2e_value = n_total * e2e_steps / e2e_s
     d2h = 8 * (D * D + D + 2)
 
+    # ---- the step before the path: undistort 1 M raw LiDAR points into G through the ABI ----
+    undistort = None
+    if rank == 0:
+        n_pts = int(1_000_000 * args.scale)
+        rng = np.random.default_rng(77)
+        w_ = sw.window
+        t_pts = np.sort(rng.uniform(w_.t0_ns * 1e-9 + 1e-6, (w_.t0_ns + (w_.n_knots - 3) * w_.dt_ns) * 1e-9 - 1e-6, n_pts))
+        xyz, keep_t = pinned(rng.normal(0, 20, (n_pts, 3)).astype(np.float32))
+        t_pts, keep_t2 = pinned(t_pts)
+        Lx = sw.lidar
+        for _ in range(3):
+            out, bad = est.UndistortScan(t_pts, xyz, Lx["S_LtoI"], Lx["p_LinI"])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            out, bad = est.UndistortScan(t_pts, xyz, Lx["S_LtoI"], Lx["p_LinI"])
+        dt_u = (time.perf_counter() - t0) / 5
+        undistort = {"points": n_pts, "points_per_s_through_abi": n_pts / dt_u, "ms": dt_u * 1e3, "invalid": int(bad),
+                     "bytes_h2d_d2h": int(n_pts * 32), "note": "UndistortScanInG, host buffers in / out (PCIe-bound)"}
     est.close()
     if world > 1:
         dist.barrier()
@@ -418,7 +436,7 @@ def main():
         "gn_iterations": gn,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_each": [round(x, 2) for x in e2e_each]},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "undistort_scan": undistort,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

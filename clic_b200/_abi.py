@@ -127,6 +127,10 @@ PROTOTYPES = {
     "clic_solve": (C.c_int, [H, C.c_int32, C.POINTER(Summary)]),
     "clic_read_state": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "clic_write_state": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "clic_query_poses": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p,
+                                   c_int64_p]),
+    "clic_undistort_scan": (C.c_int, [H, C.c_int64, c_double_p, C.POINTER(C.c_float), c_double_p, c_double_p, C.c_double,
+                                      C.c_int32, C.c_double, C.POINTER(C.c_float), c_int64_p]),
     "clic_marginalize": (C.c_int, [H, C.POINTER(H)]),
     "clic_prior_create": (C.c_int, [C.c_int32, c_double_p, c_double_p, C.c_int32, c_int32_p, c_int32_p, c_double_p,
                                     C.POINTER(H)]),

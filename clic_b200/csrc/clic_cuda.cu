@@ -1773,6 +1773,97 @@ CLIC_API int clic_write_state(clic_estimator* E, const double* knot_q, const dou
   return CLIC_OK;
 }
 
+namespace {
+PoseQuery make_pose_query(const clic_estimator* E, int64_t n, const double* d_t, const double S[4], const double p[3],
+                          double t_offset_ns) {
+  PoseQuery q;
+  q.n = n;
+  q.t_s = d_t;
+  q.S_StoI = ldq(S);
+  q.p_SinI = ldv(p);
+  q.t_offset_ns = t_offset_ns;
+  q.t_min_ns = (double)E->minTimeNs();
+  q.t_max_ns = (double)E->maxTimeNs();
+  return q;
+}
+int query_grid(const clic_estimator* E, int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)E->n_sm * 8, (n + 255) / 256));
+}
+}  // namespace
+
+CLIC_API int clic_query_poses(clic_estimator* E, int64_t n, const double* t_s, const double S_StoI[4],
+                              const double p_SinI[3], double t_offset_ns, double* q_out, double* p_out,
+                              int64_t* n_invalid) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n_invalid) *n_invalid = 0;
+  if (n <= 0) return CLIC_OK;
+  if (!t_s || !S_StoI || !p_SinI || !q_out || !p_out) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  DevBuf d_t, d_q, d_p;
+  int rc;
+  if ((rc = to_device(E, d_t, t_s, n))) return rc;
+  CU(d_q.ensure((size_t)4 * n * sizeof(double)));
+  CU(d_p.ensure((size_t)3 * n * sizeof(double)));
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
+  const PoseQuery q = make_pose_query(E, n, d_t.as<double>(), S_StoI, p_SinI, t_offset_ns);
+  pose_query_kernel<<<query_grid(E, n), 256, window_smem_doubles(E->K) * sizeof(double), E->stream>>>(
+      pp, q, d_q.as<double>(), d_p.as<double>(), E->d_counter.as<unsigned long long>());
+  E->launches++;
+  unsigned long long bad = 0;
+  CU(cudaMemcpyAsync(q_out, d_q.p, (size_t)4 * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(p_out, d_p.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  CU(cudaGetLastError());
+  if (n_invalid) *n_invalid = (int64_t)bad;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_undistort_scan(clic_estimator* E, int64_t n, const double* t_s, const float* xyz_in,
+                                 const double S_LtoI[4], const double p_LinI[3], double t_offset_ns, int32_t in_global,
+                                 double target_t_s, float* xyz_out, int64_t* n_invalid) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n_invalid) *n_invalid = 0;
+  if (n <= 0) return CLIC_OK;
+  if (!t_s || !xyz_in || !S_LtoI || !p_LinI || !xyz_out) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  DevBuf d_t, d_in, d_out, d_target, d_tt;
+  int rc;
+  if ((rc = to_device(E, d_t, t_s, n)) || (rc = to_device(E, d_in, xyz_in, (size_t)3 * n))) return rc;
+  CU(d_out.ensure((size_t)3 * n * sizeof(float)));
+  PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
+  const size_t smem = window_smem_doubles(E->K) * sizeof(double);
+  const double* target = nullptr;
+  unsigned long long bad = 0;
+  if (!in_global) {  // GetLidarPose(target_timestamp) on the device, then its inverse inside the kernel
+    if ((rc = to_device(E, d_tt, &target_t_s, 1))) return rc;
+    CU(d_target.ensure(7 * sizeof(double)));
+    CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+    const PoseQuery qt = make_pose_query(E, 1, d_tt.as<double>(), S_LtoI, p_LinI, t_offset_ns);
+    pose_query_kernel<<<1, 256, smem, E->stream>>>(pp, qt, d_target.as<double>(), d_target.as<double>() + 4,
+                                                   E->d_counter.as<unsigned long long>());
+    E->launches++;
+    CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    if (bad) return fail(CLIC_ERR_BAD_ARGUMENT, "target time outside the trajectory");
+    target = d_target.as<double>();
+  }
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  const PoseQuery q = make_pose_query(E, n, d_t.as<double>(), S_LtoI, p_LinI, t_offset_ns);
+  undistort_kernel<<<query_grid(E, n), 256, smem, E->stream>>>(pp, q, d_in.as<float>(), target, d_out.as<float>(),
+                                                              E->d_counter.as<unsigned long long>());
+  E->launches++;
+  CU(cudaMemcpyAsync(xyz_out, d_out.p, (size_t)3 * n * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  CU(cudaGetLastError());
+  if (n_invalid) *n_invalid = (int64_t)bad;
+  return CLIC_OK;
+}
+
 CLIC_API int clic_marginalize(clic_estimator* E, clic_prior** out) {
   if (!ok_handle(E) || !out) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaSetDevice(E->device));

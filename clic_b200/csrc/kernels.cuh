@@ -954,6 +954,89 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
   pass_epilogue(pp);
 }
 
+// ---------------- forward-only spline evaluation (the step before the path) ----------------
+// Trajectory::GetSensorPose (trajectory.cpp:100-115) for a batch of timestamps: one query per thread, grid-stride;
+// the knot-only part of So3Spline::evaluate (delta_i = log(R_i^-1 R_i+1), so3_spline.h:240-244) comes from the
+// per-CTA PairData like everywhere else.  HBM traffic: 8 B in, 56 B out per pose (32 B in+out per undistorted point).
+struct PoseQuery {
+  int64_t n;
+  const double* t_s;
+  Q4 S_StoI;
+  V3 p_SinI;
+  double t_offset_ns, t_min_ns, t_max_ns;  // minTimeNs / maxTimeNs as doubles (the reference compares in double)
+};
+__device__ __forceinline__ bool sensor_pose(const WindowView& W, const PassParams& pp, const PoseQuery& q, double t_s,
+                                            Q4* R_out, V3* p_out) {
+  const double tn = t_s * 1e9 + q.t_offset_ns;
+  if (!(tn >= q.t_min_ns && tn < q.t_max_ns)) return false;
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns((int64_t)tn, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u)) return false;
+  So3Chain C;
+  Q4 P[4];
+  so3_chain_rtp(W, s, u, &C, P);  // forward accumulation R_s * prod exp(lambda_i+1 delta_i)
+  double c[4];
+  blend_plain(u, c);
+  V3 pos = mk(0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; k++) pos = fma3(c[k], ldv(W.kp + 3 * (s + k)), pos);
+  *R_out = qmul(C.R, q.S_StoI);              // pose_I_to_G * EP_StoI.se3
+  *p_out = qrot(C.R, q.p_SinI) + pos;
+  return true;
+}
+__global__ void __launch_bounds__(256) pose_query_kernel(PassParams pp, PoseQuery q, double* q_out, double* p_out,
+                                                         unsigned long long* n_invalid) {
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  unsigned long long bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += (int64_t)gridDim.x * blockDim.x) {
+    Q4 R; R.x = R.y = R.z = 0.0; R.w = 1.0;
+    V3 p = mk(0, 0, 0);
+    if (!sensor_pose(W, pp, q, q.t_s[i], &R, &p)) { bad++; R.x = R.y = R.z = 0.0; R.w = 1.0; p = mk(0, 0, 0); }
+    q_out[4 * i] = R.x; q_out[4 * i + 1] = R.y; q_out[4 * i + 2] = R.z; q_out[4 * i + 3] = R.w;
+    p_out[3 * i] = p.x; p_out[3 * i + 1] = p.y; p_out[3 * i + 2] = p.z;
+  }
+  if (bad && n_invalid) atomicAdd(n_invalid, bad);
+}
+// target: 7 doubles (q xyzw, p) of GetLidarPose(target) written by pose_query_kernel, or nullptr for the G frame.
+__global__ void __launch_bounds__(256) undistort_kernel(PassParams pp, PoseQuery q, const float* xyz_in,
+                                                        const double* target, float* xyz_out,
+                                                        unsigned long long* n_invalid) {
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  Q4 Rt; Rt.x = Rt.y = Rt.z = 0.0; Rt.w = 1.0;
+  V3 pt = mk(0, 0, 0);
+  if (target) {  // pose_G_to_target = pose.inverse()
+    Rt = qconj(ldq(target));
+    pt = -1.0 * qrot(Rt, ldv(target + 4));
+  }
+  unsigned long long bad = 0;
+  const float nan_f = __int_as_float(0x7fc00000);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = xyz_in[3 * i], y = xyz_in[3 * i + 1], z = xyz_in[3 * i + 2];
+    Q4 R;
+    V3 p;
+    if (isnan(x) || !sensor_pose(W, pp, q, q.t_s[i], &R, &p)) {
+      bad++;
+      xyz_out[3 * i] = xyz_out[3 * i + 1] = xyz_out[3 * i + 2] = nan_f;
+      continue;
+    }
+    const V3 pl = mk((double)x, (double)y, (double)z);
+    V3 o;
+    if (!target) {
+      o = qrot(R, pl) + p;
+    } else {  // (pose_G_to_target * pose_Lk_to_G) * p_Lk: poses composed first, as the reference does
+      const Q4 Rc = qmul(Rt, R);
+      const V3 pc = qrot(Rt, p) + pt;
+      o = qrot(Rc, pl) + pc;
+    }
+    xyz_out[3 * i] = (float)o.x; xyz_out[3 * i + 1] = (float)o.y; xyz_out[3 * i + 2] = (float)o.z;
+  }
+  if (bad && n_invalid) atomicAdd(n_invalid, bad);
+}
+
 __global__ void prep_image_kernel(int64_t n, const double* ti_s, const double* tj_s, const double* p_i, const double* p_j,
                                   int64_t t_lo, int64_t t_hi, int64_t pad, int64_t* ti_ns, int64_t* tj_ns, double* pi0,
                                   double* pi1, double* pi2, double* pj0, double* pj1, unsigned long long* n_dropped) {

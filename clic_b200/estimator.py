@@ -279,6 +279,30 @@ class TrajectoryEstimator:
     def profile_enable(self, on=True):
         _check(self.lib, self.lib.clic_profile_enable(self.h, int(on)))
 
+    # ---- Trajectory::GetSensorPose / UndistortScan(InG) batched (src/spline/trajectory.cpp:35-115) ----
+    def GetSensorPoses(self, t_s, S_StoI, p_SinI, t_offset_ns=0.0):
+        """pose_S_to_G at every timestamp (seconds): returns q (n,4 xyzw), p (n,3), number of out-of-range times."""
+        t_s, S_StoI, p_SinI = f64(t_s), f64(S_StoI), f64(p_SinI)
+        n = len(t_s)
+        q, p, bad = np.zeros((n, 4)), np.zeros((n, 3)), C.c_int64(0)
+        _check(self.lib, self.lib.clic_query_poses(self.h, n, dptr(t_s), dptr(S_StoI), dptr(p_SinI), float(t_offset_ns),
+                                                   dptr(q), dptr(p), C.byref(bad)))
+        return q, p, bad.value
+
+    def UndistortScan(self, t_s, xyz, S_LtoI, p_LinI, t_offset_ns=0.0, target_t_s=None):
+        """Raw LiDAR points (float32 xyz, double timestamps) into G (target_t_s None: UndistortScanInG) or into the
+        LiDAR frame at target_t_s (UndistortScan)."""
+        t_s, S_LtoI, p_LinI = f64(t_s), f64(S_LtoI), f64(p_LinI)
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        n = len(t_s)
+        out, bad = np.zeros((n, 3), np.float32), C.c_int64(0)
+        fp = C.POINTER(C.c_float)
+        _check(self.lib, self.lib.clic_undistort_scan(
+            self.h, n, dptr(t_s), xyz.ctypes.data_as(fp), dptr(S_LtoI), dptr(p_LinI), float(t_offset_ns),
+            1 if target_t_s is None else 0, 0.0 if target_t_s is None else float(target_t_s), out.ctypes.data_as(fp),
+            C.byref(bad)))
+        return out, bad.value
+
     def profile_read(self):
         ms, cnt = np.zeros(8), np.zeros(8, np.int64)
         _check(self.lib, self.lib.clic_profile_read(self.h, dptr(ms), cnt.ctypes.data_as(_abi.c_int64_p)))

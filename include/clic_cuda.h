@@ -230,6 +230,24 @@ CLIC_API int clic_read_state(clic_estimator* h, double* knot_q, double* knot_p, 
 CLIC_API int clic_write_state(clic_estimator* h, const double* knot_q, const double* knot_p, const double* bias,
                               const double* t_offset_ns /*3*/, const double* inv_depth);
 
+/* ---- the step before the path: forward-only spline evaluation at the current state ----
+ * Trajectory::GetSensorPose (src/spline/trajectory.cpp:100-115) batched: pose_S_to_G = poseNs(t) * EP_StoI for every
+ * timestamp, with the reference's time arithmetic (double time_ns = t * 1e9 + t_offset_ns, range test in double, then
+ * the implicit truncation to int64 of poseNs(int64_t)).  Se3Spline::poseNs = So3Spline::evaluate (so3_spline.h:220-262)
+ * and RdSpline::evaluate (rd_spline.h:218-244).  q_out: 4n (x,y,z,w), p_out: 3n.  A time outside
+ * [minTimeNs, maxTimeNs) — where the reference asserts — yields the identity pose and counts in n_invalid. */
+CLIC_API int clic_query_poses(clic_estimator* h, int64_t n, const double* t_s, const double S_StoI[4],
+                              const double p_SinI[3], double t_offset_ns, double* q_out, double* p_out,
+                              int64_t* n_invalid);
+/* Trajectory::UndistortScanInG (trajectory.cpp:69-97; in_global != 0): p_G = pose_Lk_to_G(t_k) * p_Lk, and
+ * Trajectory::UndistortScan (trajectory.cpp:35-67; in_global == 0): p = pose_G_to_target * pose_Lk_to_G(t_k) * p_Lk
+ * with pose_G_to_target = GetLidarPose(target_t_s).inverse().  Points are PosPoint x,y,z floats + double timestamp
+ * (the cloud type's fields); arithmetic in double, stored back as float.  NaN input points (pcl_isnan(x), skipped
+ * by the reference) and out-of-range times give NaN output and count in n_invalid. */
+CLIC_API int clic_undistort_scan(clic_estimator* h, int64_t n, const double* t_s, const float* xyz_in /*3n*/,
+                                 const double S_LtoI[4], const double p_LinI[3], double t_offset_ns, int32_t in_global,
+                                 double target_t_s, float* xyz_out /*3n*/, int64_t* n_invalid);
+
 /* SaveMarginalizationInfo (trajectory_estimator.cpp:234-249) = preMarginalize + marginalize
  * (marginalization_factor.cpp:94-116,150-276) over the factors added with marg_* = 1. */
 CLIC_API int clic_marginalize(clic_estimator* h, clic_prior** out);

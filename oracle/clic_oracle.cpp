@@ -1354,6 +1354,105 @@ CLIC_API int clic_solve(clic_estimator* E, int32_t max_iterations, clic_summary*
   return rc;
 }
 
+// ---- forward-only spline evaluation ----
+namespace {
+// Se3Spline::poseNs(int64_t) = So3Spline::evaluate (so3_spline.h:220-262) + RdSpline::evaluate<0> (rd_spline.h:218-244)
+void pose_ns(const clic_estimator* E, int64_t time_ns, Quat* R_out, Vec3* p_out) {
+  const int64_t st_ns = time_ns - E->t0_ns;  // computeTIndexNs, rd_spline.h:119-121
+  const size_t s = (size_t)(st_ns / E->dt_ns);
+  const double u = double(st_ns % E->dt_ns) / double(E->dt_ns);
+  double p[N], coeff[N];
+  base_coeffs_with_time(0, p, u);
+  matvec4(blend_cumulative(), p, coeff);
+  Quat res = load_q(&E->x.knot_q[4 * s]);
+  for (int i = 0; i < N - 1; i++) {
+    const Quat p0 = load_q(&E->x.knot_q[4 * (s + i)]), p1 = load_q(&E->x.knot_q[4 * (s + i + 1)]);
+    const Quat r01 = so3_mul(qconj(p0), p1);
+    const Vec3 delta = so3_log(r01);
+    const Vec3 kdelta = delta * coeff[i + 1];
+    res = so3_mul(res, so3_exp(kdelta));
+  }
+  double c[N];
+  matvec4(blend_plain(), p, c);  // pow_inv_dt_[0] = 1
+  Vec3 pos = v3(0, 0, 0);
+  for (int i = 0; i < N; i++) pos = pos + c[i] * load_v(&E->x.knot_p[3 * (s + i)]);
+  *R_out = res;
+  *p_out = pos;
+}
+// Trajectory::GetSensorPose, trajectory.cpp:100-115 (the assert becomes a bool)
+bool sensor_pose(const clic_estimator* E, double timestamp, const Quat& S_StoI, const Vec3& p_SinI, double t_offset_ns,
+                 Quat* R_out, Vec3* p_out) {
+  const double time_ns = timestamp * S_TO_NS + t_offset_ns;
+  if (!(time_ns >= (double)E->minTimeNs() && time_ns < (double)E->maxTimeNs())) return false;
+  Quat R;
+  Vec3 p;
+  pose_ns(E, (int64_t)time_ns, &R, &p);
+  *R_out = so3_mul(R, S_StoI);  // pose_I_to_G * EP_StoI.se3
+  *p_out = so3_rotate(R, p_SinI) + p;
+  return true;
+}
+}  // namespace
+
+CLIC_API int clic_query_poses(clic_estimator* E, int64_t n, const double* t_s, const double S_StoI[4],
+                              const double p_SinI[3], double t_offset_ns, double* q_out, double* p_out,
+                              int64_t* n_invalid) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n > 0 && (!t_s || !S_StoI || !p_SinI || !q_out || !p_out)) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  int64_t bad = 0;
+  const Quat S = load_q(S_StoI);
+  const Vec3 ps = load_v(p_SinI);
+  for (int64_t i = 0; i < n; i++) {
+    Quat R{0, 0, 0, 1};
+    Vec3 p = v3(0, 0, 0);
+    if (!sensor_pose(E, t_s[i], S, ps, t_offset_ns, &R, &p)) { bad++; R = Quat{0, 0, 0, 1}; p = v3(0, 0, 0); }
+    q_out[4 * i] = R.x; q_out[4 * i + 1] = R.y; q_out[4 * i + 2] = R.z; q_out[4 * i + 3] = R.w;
+    p_out[3 * i] = p[0]; p_out[3 * i + 1] = p[1]; p_out[3 * i + 2] = p[2];
+  }
+  if (n_invalid) *n_invalid = bad;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_undistort_scan(clic_estimator* E, int64_t n, const double* t_s, const float* xyz_in,
+                                 const double S_LtoI[4], const double p_LinI[3], double t_offset_ns, int32_t in_global,
+                                 double target_t_s, float* xyz_out, int64_t* n_invalid) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (n > 0 && (!t_s || !xyz_in || !S_LtoI || !p_LinI || !xyz_out)) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  const Quat S = load_q(S_LtoI);
+  const Vec3 ps = load_v(p_LinI);
+  Quat Rt{0, 0, 0, 1};
+  Vec3 pt = v3(0, 0, 0);
+  if (!in_global) {  // pose_G_to_target = GetLidarPose(target_timestamp).inverse(), trajectory.cpp:42
+    Quat R;
+    Vec3 p;
+    if (!sensor_pose(E, target_t_s, S, ps, t_offset_ns, &R, &p)) return fail(CLIC_ERR_BAD_ARGUMENT, "target time outside the trajectory");
+    Rt = qconj(R);
+    pt = -so3_rotate(Rt, p);
+  }
+  const float nanf_ = std::numeric_limits<float>::quiet_NaN();
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    Quat R;
+    Vec3 p;
+    if (std::isnan(xyz_in[3 * i]) || !sensor_pose(E, t_s[i], S, ps, t_offset_ns, &R, &p)) {
+      bad++;
+      xyz_out[3 * i] = xyz_out[3 * i + 1] = xyz_out[3 * i + 2] = nanf_;
+      continue;
+    }
+    const Vec3 p_Lk = v3(xyz_in[3 * i], xyz_in[3 * i + 1], xyz_in[3 * i + 2]);
+    Vec3 out;
+    if (in_global) {
+      out = so3_rotate(R, p_Lk) + p;  // pose_Lk_to_G * p_Lk
+    } else {                          // (pose_G_to_target * pose_Lk_to_G) * p_Lk: the poses are composed first
+      const Quat Rc = so3_mul(Rt, R);
+      const Vec3 pc = so3_rotate(Rt, p) + pt;
+      out = so3_rotate(Rc, p_Lk) + pc;
+    }
+    xyz_out[3 * i] = (float)out[0]; xyz_out[3 * i + 1] = (float)out[1]; xyz_out[3 * i + 2] = (float)out[2];
+  }
+  if (n_invalid) *n_invalid = bad;
+  return CLIC_OK;
+}
+
 CLIC_API int clic_read_state(clic_estimator* E, double* knot_q, double* knot_p, double* bias, double* t_offset_ns,
                              double* inv_depth) {
   if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
