@@ -223,6 +223,7 @@ struct clic_estimator {
   // normal equations: [H D*D | b D | cost_x 2 | cost_cand 2]; `loc` is what this rank's kernels write, `glb` the
   // all-reduced copy every consumer reads (the same buffer when there is one rank)
   DevBuf d_nrm_loc, d_nrm_glb;
+  DevBuf d_nrm_loc2, d_nrm_glb2;  // same layout: the speculative Jacobian pass at the LM candidate (set 1)
   bool use_comm = false;
   double* H_loc() const { return d_nrm_loc.as<double>(); }
   double* b_loc() const { return d_nrm_loc.as<double>() + (size_t)std::max(1, L.D) * std::max(1, L.D); }
@@ -231,6 +232,13 @@ struct clic_estimator {
   double* H_glb() const { return nrm_glb(); }
   double* b_glb() const { return nrm_glb() + (size_t)std::max(1, L.D) * std::max(1, L.D); }
   double* cost_glb() const { return b_glb() + std::max(1, L.D); }
+  // set 0: the system at x;  set 1: the system at the LM candidate (lm_solve, speculative evaluation)
+  double* nrm_loc_set(int set) const { return set ? d_nrm_loc2.as<double>() : d_nrm_loc.as<double>(); }
+  double* nrm_glb_set(int set) const {
+    return use_comm ? (set ? d_nrm_glb2.as<double>() : d_nrm_glb.as<double>()) : nrm_loc_set(set);
+  }
+  size_t off_b() const { return (size_t)std::max(1, L.D) * std::max(1, L.D); }
+  size_t off_cost() const { return off_b() + std::max(1, L.D); }
   DevBuf d_knot_col, d_col_knot, d_col_sub, d_descs;
   DevBuf d_lm;  // LM workspace (solver.cuh)
   std::vector<std::unique_ptr<LoamBatch>> loam;
@@ -483,7 +491,11 @@ int ensure_layout(clic_estimator* E) {
   if (!jobs.empty())
     CU(cudaMemcpyAsync(E->d_jobs.p, jobs.data(), jobs.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice, E->stream));
   CU(E->d_nrm_loc.ensure(((size_t)D * D + D + 8) * sizeof(double)));
-  if (E->use_comm) CU(E->d_nrm_glb.ensure(((size_t)D * D + D + 8) * sizeof(double)));
+  CU(E->d_nrm_loc2.ensure(((size_t)D * D + D + 8) * sizeof(double)));
+  if (E->use_comm) {
+    CU(E->d_nrm_glb.ensure(((size_t)D * D + D + 8) * sizeof(double)));
+    CU(E->d_nrm_glb2.ensure(((size_t)D * D + D + 8) * sizeof(double)));
+  }
   CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
   E->layout_dirty = false;
   return CLIC_OK;
@@ -509,12 +521,12 @@ int launch_reduce(clic_estimator* E, const StreamExec& ex, double* cost2, bool f
 }
 
 int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* state, double* cost2, bool jac,
-                 const int* ctl) {
+                 const int* ctl, double* Hp, double* bp) {
   const int n = pr->p->n, nb = (int)pr->p->blocks.size();
   const int D = std::max(1, E->L.D);
   size_t smem = (size_t)3 * n * sizeof(double) + (size_t)n * sizeof(int);
   CU(launch_pdl(prior_kernel, 1, 256, smem, E->stream, pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
-                pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, E->H_loc(), E->b_loc(), D, cost2, jac ? 1 : 0,
+                pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, Hp, bp, D, cost2, jac ? 1 : 0,
                 ctl));
   E->launches++;
   return CLIC_OK;
@@ -573,10 +585,14 @@ int set_smem(KernelT k, size_t bytes) {
 
 // One fused residual (+ Jacobian + normal-equation) pass over the solve problem at `state`.
 // jac = true: H, b, cost2 are produced; false: cost2 only.  ctl: optional device skip word.
-int run_pass(clic_estimator* E, const double* state, bool jac, int which, const int* ctl) {
+// set = 1 (with jac): the whole system goes to the second buffer set (H_c | b_c | cost_c), cost in its slot 0.
+int run_pass(clic_estimator* E, const double* state, bool jac, int which, const int* ctl, int set = 0) {
   int rc = ensure_layout(E);
   if (rc) return rc;
-  double* cost2 = E->cost_loc() + 2 * which;  // slot 0: pass at x, slot 1: pass at the LM candidate
+  double* Hp = E->nrm_loc_set(set);
+  double* bp = Hp + E->off_b();
+  // slot 0: pass at x, slot 1: pass at the LM candidate (set 0);  set 1 keeps its cost in its own slot 0
+  double* cost2 = Hp + E->off_cost() + (set ? 0 : 2 * which);
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
   pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
@@ -660,7 +676,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     cm.col_sub = E->d_col_sub.as<int>();
     const int n_entries = D * (D + 1) / 2 + D;
     E->prof_begin(3);
-    CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, E->H_loc(), E->b_loc(), cm,
+    CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, Hp, bp, cm,
                   E->d_descs.as<StreamDesc>(), E->n_desc, ctl));
     E->prof_end();
     E->launches += 1;
@@ -675,13 +691,13 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
     d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
     d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
-    CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, E->H_loc(), E->b_loc(), std::max(1, D),
+    CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, Hp, bp, std::max(1, D),
                   cost2, jac ? 1 : 0, ctl));
     E->launches += 1;
   }
   for (auto& pr : E->priors) {
     if (E->opt.is_marg_state) continue;
-    if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl))) return rc;
+    if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl, Hp, bp))) return rc;
   }
   CU(cudaGetLastError());
   if (E->use_comm) {
@@ -692,9 +708,9 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const size_t DD = (size_t)std::max(1, D) * std::max(1, D) + std::max(1, D);
     int e;
     if (jac)
-      e = nc.AllReduce(E->d_nrm_loc.p, E->d_nrm_glb.p, DD + 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+      e = nc.AllReduce(Hp, E->nrm_glb_set(set), DD + 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
     else
-      e = nc.AllReduce(E->cost_loc() + 2 * which, E->cost_glb() + 2 * which, 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+      e = nc.AllReduce(cost2, E->nrm_glb_set(set) + (cost2 - Hp), 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
     E->prof_end();
     if (e != 0) return fail(CLIC_ERR_NCCL, std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "?"));
   }
@@ -731,6 +747,11 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   B.b = E->b_glb();
   B.cost_x = E->cost_glb();
   B.cost_c = E->cost_glb() + 2;
+  // Unconstrained problems evaluate the candidate WITH its Jacobians (second buffer set): an accepted step — the
+  // common case — then needs no further pass; lm_accept_kernel adopts H_c, b_c, cost_c.  CLIC_LM_NO_SPECULATE=1 or a
+  // bounded problem (line search on residual-only passes) keeps the residual pass + conditional Jacobian pass.
+  B.Hc = nullptr;
+  B.bc = nullptr;
   B.scale = (double*)(base + o_scale);
   B.diagonal = (double*)(base + o_diag);
   B.step = (double*)(base + o_step);
@@ -753,6 +774,13 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     if (L.col_toff[s] >= 0 && E->bounds_toff[s]) constrained = true;
   }
   L.sl = E->sl;
+  const bool speculate = !constrained && !getenv("CLIC_LM_NO_SPECULATE");
+  if (speculate) {
+    double* g2 = E->nrm_glb_set(1);
+    B.Hc = g2;
+    B.bc = g2 + E->off_b();
+    B.cost_c = g2 + E->off_cost();
+  }
   LmConst C;
   const int* ctl_res = &B.st->skip_res;
   const int* ctl_jac = &B.st->skip_jac;
@@ -781,7 +809,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     E->prof_end();
     E->launches++;
     if (it == max_iterations) break;  // the last launch only records the max-iterations termination
-    if ((rc = run_pass(E, B.cand, false, 1, ctl_res))) return rc;
+    if ((rc = run_pass(E, B.cand, speculate, 1, ctl_res, speculate ? 1 : 0))) return rc;
     if (constrained) {
       for (int ls = 0; ls < max_ls + 1; ls++) {
         lm_linesearch_kernel<<<1, 256, 0, E->stream>>>(B, L, max_ls);
@@ -797,7 +825,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     lm_accept_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C);
     E->prof_end();
     E->launches++;
-    if ((rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
+    if (!speculate && (rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
     E->prof_begin(5);
     lm_post_kernel<<<1, 256, sm_small, E->stream>>>(B, L);
     E->prof_end();

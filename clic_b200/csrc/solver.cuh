@@ -388,7 +388,9 @@ struct LmBufs {
   double* H;       // D*D unscaled normal matrix (from the pass)
   double* b;       // D   unscaled gradient
   double* cost_x;  // [2] cost, fixed_cost of the pass at x
-  double* cost_c;  // [2] of the residual-only pass at the candidate
+  double* cost_c;  // [2] of the pass at the candidate
+  double* Hc;      // speculative evaluation: the system at the candidate (nullptr: residual-only candidate passes)
+  double* bc;
   double* scale;   // D
   double* diagonal;  // D
   double* step;    // D
@@ -691,6 +693,12 @@ __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
   if (accept) {
     const int n_state = L.sl.size();
     for (int i = threadIdx.x; i < n_state; i += blockDim.x) B.x[i] = B.cand[i];
+    if (B.Hc) {  // the candidate was evaluated with its Jacobians: adopt its system, no further pass needed
+      const int D = L.D;
+      for (int i = threadIdx.x; i < D * D; i += blockDim.x) B.H[i] = B.Hc[i];
+      for (int i = threadIdx.x; i < D; i += blockDim.x) B.b[i] = B.bc[i];
+      if (threadIdx.x < 2) B.cost_x[threadIdx.x] = B.cost_c[threadIdx.x];
+    }
   }
 }
 
