@@ -258,7 +258,9 @@ struct clic_estimator {
   int n_desc = 0;
   DevBuf d_jobs;
   bool packs_fit = true;  // the packed visual kernel's shared memory fits this window
-  int n_jobs = 0, n_part_ctas = 0;
+  int n_jobs = 0, n_part_ctas = 0, max_slots = 0;
+  DevBuf d_bias_descs;
+  bool bias_desc_dirty = true;
   int64_t launches = 0;
   bool bounds_toff[3] = {false, false, false};
   double toff_lo[3], toff_hi[3];
@@ -486,6 +488,10 @@ int ensure_layout(clic_estimator* E) {
   if (!descs.empty())
     CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
   E->n_jobs = (int)jobs.size();
+  E->max_slots = 1;
+  for (auto& j : jobs) E->max_slots = std::max(E->max_slots, j.n_slots);
+  if ((size_t)2 * E->max_slots * sizeof(int) > 48 * 1024)
+    CU(cudaFuncSetAttribute(reduce_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * E->max_slots * sizeof(int))));
   E->n_part_ctas = n_part_ctas;
   CU(E->d_jobs.ensure(std::max<size_t>(1, jobs.size()) * sizeof(ReduceJob)));
   if (!jobs.empty())
@@ -498,6 +504,7 @@ int ensure_layout(clic_estimator* E) {
   }
   CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
   E->layout_dirty = false;
+  E->bias_desc_dirty = true;
   return CLIC_OK;
 }
 
@@ -663,24 +670,12 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   } else {  // every stream's records -> per-key blocks, and the pass cost, in one launch (cost only without jac)
     const int part_ctas = jac ? E->n_part_ctas : 0;
     E->prof_begin(3);
-    CU(launch_pdl(reduce_all_kernel, part_ctas + 1, 256, 0, E->stream, E->d_jobs.as<ReduceJob>(), E->n_jobs, part_ctas, cost2, ctl));
+    CU(launch_pdl(reduce_all_kernel, part_ctas + 1, 256, (size_t)2 * E->max_slots * sizeof(int), E->stream,
+                  E->d_jobs.as<ReduceJob>(), E->n_jobs, part_ctas, E->max_slots, cost2, ctl));
     E->prof_end();
   }
   E->launches += 1;
-  if (jac && D > 0) {
-    ColMaps cm;
-    cm.D = D;
-    cm.K = E->K;
-    cm.knot_col = E->d_knot_col.as<int>();
-    cm.col_knot = E->d_col_knot.as<int>();
-    cm.col_sub = E->d_col_sub.as<int>();
-    const int n_entries = D * (D + 1) / 2 + D;
-    E->prof_begin(3);
-    CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, Hp, bp, cm,
-                  E->d_descs.as<StreamDesc>(), E->n_desc, ctl));
-    E->prof_end();
-    E->launches += 1;
-  }
+  std::vector<BiasFactorDesc> bias_descs;
   for (auto& bf : E->bias_f) {
     if (bf.marg) continue;
     BiasFactorDesc d;
@@ -691,10 +686,41 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
     d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
     d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
-    CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, Hp, bp, std::max(1, D),
-                  cost2, jac ? 1 : 0, ctl));
+    bias_descs.push_back(d);
+  }
+  const bool bias_in_assemble = jac && D > 0 && !bias_descs.empty() && bias_descs.size() <= 4;
+  if (jac && D > 0) {
+    ColMaps cm;
+    cm.D = D;
+    cm.K = E->K;
+    cm.knot_col = E->d_knot_col.as<int>();
+    cm.col_knot = E->d_col_knot.as<int>();
+    cm.col_sub = E->d_col_sub.as<int>();
+    const int n_entries = D * (D + 1) / 2 + D;
+    const BiasFactorDesc* d_bias = nullptr;
+    if (bias_in_assemble) {  // the descriptors only depend on the layout: uploaded once per layout
+      if (E->bias_desc_dirty) {
+        CU(E->d_bias_descs.ensure(bias_descs.size() * sizeof(BiasFactorDesc)));
+        CU(cudaMemcpyAsync(E->d_bias_descs.p, bias_descs.data(), bias_descs.size() * sizeof(BiasFactorDesc),
+                           cudaMemcpyHostToDevice, E->stream));
+        CU(cudaStreamSynchronize(E->stream));
+        E->bias_desc_dirty = false;
+      }
+      d_bias = E->d_bias_descs.as<BiasFactorDesc>();
+    }
+    E->prof_begin(3);
+    CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, Hp, bp, cm, E->d_descs.as<StreamDesc>(),
+                  E->n_desc, ctl, d_bias, bias_in_assemble ? (int)bias_descs.size() : 0, state, E->sl.off_bias(),
+                  cost2));
+    E->prof_end();
     E->launches += 1;
   }
+  if (!bias_in_assemble)
+    for (auto& d : bias_descs) {
+      CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, Hp, bp, std::max(1, D), cost2,
+                    jac ? 1 : 0, ctl));
+      E->launches += 1;
+    }
   for (auto& pr : E->priors) {
     if (E->opt.is_marg_state) continue;
     if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl, Hp, bp))) return rc;
@@ -1439,6 +1465,7 @@ CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, do
   f.marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   f.marg_all = marg_all_bias;
   E->bias_f.push_back(f);
+  E->bias_desc_dirty = true;
   return CLIC_OK;
 }
 

@@ -517,10 +517,9 @@ reduce_records_kernel(const double* payload, const int* key, int n_slots, int P,
   reduce_part_body<RD>(payload, key, r0, r1, k, out + ((size_t)k * P + part) * RD);
 }
 
-// All factor streams of a pass in ONE launch: CTA (job, key) walks the stream's record slots in chunks of 1024 (the
-// chunk's keys are fetched with every load in flight, the hits compacted in slot order) and sums the matching
-// payloads in that order, NB records in flight per thread; then folds the atomics-fallback block in and re-arms
-// it.  For time-sorted streams a key has ~n_CTAs / n_keys records, so this is a handful of load rounds.  The extra
+// All factor streams of a pass in ONE launch: CTA (job, key) fetches every slot key of the stream with all loads
+// in flight, compacts the hits in slot order (256 threads, two-level scan) and sums the matching payloads in that
+// order, NB records in flight per thread; then folds the atomics-fallback block in and re-arms it.  For time-sorted streams a key has ~n_CTAs / n_keys records, so this is a handful of load rounds.  The extra
 // last CTA sums every job's per-warp costs.  jac == 0: only that CTA is launched.
 struct ReduceJob {
   const double* payload;
@@ -532,62 +531,57 @@ struct ReduceJob {
   int cta0;          // first CTA of the job in the flattened grid
 };
 template <int RD>
-__device__ __forceinline__ void reduce_key_body(const ReduceJob& J, int k) {
+__device__ __forceinline__ void reduce_key_body(const ReduceJob& J, int k, int* skey, int* list) {
   constexpr int EPT = (RD + 255) / 256;
   constexpr int NB = RD <= 640 ? 8 : 4;  // records in flight per thread
-  __shared__ int skey[kMaxChunk];
-  __shared__ int list[kMaxChunk];
-  __shared__ int n_match;
+  __shared__ int warp_cnt[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slots = J.n_slots;
+  // every slot key of the stream, all loads in flight
+  for (int r = threadIdx.x; r < n_slots; r += 256) skey[r] = J.key[r];
+  __syncthreads();
+  // ordered compaction: thread t owns the contiguous slots [t * per, (t + 1) * per); counts are scanned within the
+  // warp (shuffles) and across the 8 warps (shared), then every thread writes its hits at its offset
+  const int per = (n_slots + 255) / 256;
+  const int s0 = min(n_slots, (int)threadIdx.x * per), s1 = min(n_slots, s0 + per);
+  int cnt = 0;
+  for (int r = s0; r < s1; r++) cnt += skey[r] == k ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_cnt[warp] = incl;
+  __syncthreads();
+  int base = incl - cnt, n = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    if (w < warp) base += warp_cnt[w];
+    n += warp_cnt[w];
+  }
+  for (int r = s0; r < s1; r++)
+    if (skey[r] == k) list[base++] = r;
+  __syncthreads();
   double acc[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; i++) acc[i] = 0.0;
-  for (int r0 = 0; r0 < J.n_slots; r0 += kMaxChunk) {
-    const int r1 = min(J.n_slots, r0 + kMaxChunk);
+  for (int j = 0; j < n; j += NB) {
+    double v[NB][EPT];
 #pragma unroll
-    for (int i = 0; i < kMaxChunk / 256; i++) {
-      const int r = r0 + threadIdx.x + 256 * i;
-      skey[threadIdx.x + 256 * i] = r < r1 ? J.key[r] : -1;
-    }
-    __syncthreads();
-    if (warp == 0) {  // lane L owns slots 32L .. 32L+31 of the chunk: exclusive scan of the hit counts, then expand
-      unsigned m = 0;
-#pragma unroll 8
-      for (int q = 0; q < 32; q++) m |= (skey[32 * lane + q] == k ? 1u : 0u) << q;
-      int cnt = __popc(m), base = cnt;
+    for (int q = 0; q < NB; q++) {
+      const bool on = j + q < n;
+      const double* src = J.payload + (size_t)(on ? list[j + q] : 0) * RD;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, base, o);
-        if (lane >= o) base += v;
-      }
-      if (lane == 31) n_match = base;
-      base -= cnt;
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        list[base++] = r0 + 32 * lane + bit;
+      for (int i = 0; i < EPT; i++) {
+        const int e = threadIdx.x + i * 256;
+        v[q][i] = (on && e < RD) ? src[e] : 0.0;
       }
     }
-    __syncthreads();
-    const int n = n_match;
-    for (int j = 0; j < n; j += NB) {
-      double v[NB][EPT];
 #pragma unroll
-      for (int q = 0; q < NB; q++) {
-        const bool on = j + q < n;
-        const double* src = J.payload + (size_t)(on ? list[j + q] : 0) * RD;
+    for (int q = 0; q < NB; q++)
 #pragma unroll
-        for (int i = 0; i < EPT; i++) {
-          const int e = threadIdx.x + i * 256;
-          v[q][i] = (on && e < RD) ? src[e] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < NB; q++)
-#pragma unroll
-        for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
-    }
-    __syncthreads();  // skey / list are rewritten by the next chunk
+      for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
   }
   double* ov = J.overflow + (size_t)k * RD;
   double* fin = J.fin + (size_t)k * RD;
@@ -602,7 +596,7 @@ __device__ __forceinline__ void reduce_key_body(const ReduceJob& J, int k) {
   }
 }
 __global__ void __launch_bounds__(256, 3)
-reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_key_ctas, double* cost2, const int* ctl) {
+reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_key_ctas, int max_slots, double* cost2, const int* ctl) {
   pdl_wait();
   pdl_trigger();
   if (ctl && ctl[0]) return;
@@ -624,11 +618,14 @@ reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_key_ctas, double* cos
   while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].cta0) j++;
   const ReduceJob& J = jobs[j];
   const int k = blockIdx.x - J.cta0;
+  extern __shared__ int red_smem[];  // [max n_slots] keys + [max n_slots] ordered hit list
+  int* skey = red_smem;
+  int* list = red_smem + max_slots;
   switch (J.rd) {
-    case 416: reduce_key_body<416>(J, k); break;
-    case 640: reduce_key_body<640>(J, k); break;
-    case 960: reduce_key_body<960>(J, k); break;
-    default: reduce_key_body<1792>(J, k); break;
+    case 416: reduce_key_body<416>(J, k, skey, list); break;
+    case 640: reduce_key_body<640>(J, k, skey, list); break;
+    case 960: reduce_key_body<960>(J, k, skey, list); break;
+    default: reduce_key_body<1792>(J, k, skey, list); break;
   }
 }
 
@@ -1080,11 +1077,21 @@ __device__ __forceinline__ double block_entry(const double* blk, int NT, int la,
   return blk[tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7)];
 }
 
+// BiasFactor (trajectory_value_factor.h:65-126) added to H, b, cost by one thread (6 residuals, +-I Jacobians).
+struct BiasFactorDesc {
+  int slot_i, slot_j;
+  double sqrt_info[6];   // info / sqrt(dt)
+  int col_gi, col_gj, col_ai, col_aj;  // columns (-1 constant)
+};
 // H[gi][gj] (upper, mirrored) and b[gi]: owner-computes gather over the per-key blocks.  One WARP per entry: the
 // lanes stride the (block, partial) contribution list in a fixed assignment and are combined by a fixed butterfly,
 // so the sum order never changes between runs.
+// bias (n_bias > 0, solve path): the BiasFactor terms (+-I Jacobians) are added by the owner of each entry, and the
+// first warp adds their cost — one launch less per pass than bias_factor_kernel.
 __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
-                                                       int n_desc, const int* ctl) {
+                                                       int n_desc, const int* ctl, const BiasFactorDesc* bias = nullptr,
+                                                       int n_bias = 0, const double* state = nullptr,
+                                                       int off_bias = 0, double* cost2 = nullptr) {
   pdl_wait();
   pdl_trigger();
   if (ctl && ctl[0]) return;
@@ -1160,6 +1167,31 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
+    double bias_cost = 0.0;
+    bool bias_free = false;
+    for (int f = 0; f < n_bias; f++) {
+      const BiasFactorDesc& bf = bias[f];
+      const double* bi = state + off_bias + 6 * bf.slot_i;
+      const double* bj = state + off_bias + 6 * bf.slot_j;
+      bias_free = bias_free || bf.col_gi >= 0 || bf.col_gj >= 0 || bf.col_ai >= 0 || bf.col_aj >= 0;
+      double tot = 0.0;
+      for (int r = 0; r < 6; r++) {
+        const double w = bf.sqrt_info[r], res = w * (bj[r] - bi[r]);
+        tot += res * res;
+        const int base_i = r < 3 ? bf.col_gi : bf.col_ai, base_j = r < 3 ? bf.col_gj : bf.col_aj;
+        const int ci = base_i >= 0 ? base_i + r % 3 : -1, cj = base_j >= 0 ? base_j + r % 3 : -1;
+        if (is_b) {
+          if (ci >= 0 && gi == ci) acc += -w * res;
+          if (cj >= 0 && gi == cj) acc += w * res;
+        } else {
+          if (ci >= 0 && gi == ci && gj == ci) acc += w * w;
+          if (cj >= 0 && gi == cj && gj == cj) acc += w * w;
+          if (ci >= 0 && cj >= 0 && gi == min(ci, cj) && gj == max(ci, cj)) acc += -w * w;
+        }
+      }
+      bias_cost += 0.5 * tot;
+    }
+    if (wid == 0 && n_bias > 0) cost2[bias_free ? 0 : 1] += bias_cost;
     if (is_b) {
       b[gi] = acc;
     } else {
@@ -1169,12 +1201,6 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
   }
 }
 
-// BiasFactor (trajectory_value_factor.h:65-126) added to H, b, cost by one thread (6 residuals, +-I Jacobians).
-struct BiasFactorDesc {
-  int slot_i, slot_j;
-  double sqrt_info[6];   // info / sqrt(dt)
-  int col_gi, col_gj, col_ai, col_aj;  // columns (-1 constant)
-};
 __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, StateLayout sl, double* H, double* b, int D,
                                    double* cost2, int jac, const int* ctl) {
   pdl_wait();
