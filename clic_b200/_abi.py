@@ -115,6 +115,10 @@ PROTOTYPES = {
                                 c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32, c_int64_p]),
     "clic_add_loam_packed": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, C.POINTER(C.c_uint8), c_double_p, c_double_p,
                                        c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32, c_int64_p]),
+    "clic_add_loam_planes": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, C.c_double, C.c_int32, c_int64_p]),
+    "clic_add_loam_lines": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                      c_double_p, C.c_double, C.c_int32, c_int64_p]),
     "clic_add_imu": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                c_int64_p]),
     "clic_add_bias": (C.c_int, [H, C.c_int32, C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int32]),

@@ -610,13 +610,17 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const size_t smem = loam_smem_bytes(E->K);
     if (jac) {
       E->prof_begin(0);
-      CU(launch_pdl(loam_kernel<true, kLoamWarps, kLoamMinB>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      if (b->st.geo_kind == 1) CU(launch_pdl(loam_kernel<true, kLoamWarps, kLoamMinB, 1>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      else if (b->st.geo_kind == 2) CU(launch_pdl(loam_kernel<true, kLoamWarps, kLoamMinB, 2>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      else CU(launch_pdl(loam_kernel<true, kLoamWarps, kLoamMinB, 0>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
       pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
     } else {
       E->prof_begin(0);
-      CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      if (b->st.geo_kind == 1) CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 1>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      else if (b->st.geo_kind == 2) CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 2>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
+      else CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 0>, ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb()));
       pp.pdl_first = 0;
       E->prof_end();
       E->launches += 1;
@@ -916,7 +920,9 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     if (!b->marg) continue;
     StreamExec& ex = b->ex;
     CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
-    loam_kernel<true, kLoamWarps, kLoamMinB><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    if (b->st.geo_kind == 1) loam_kernel<true, kLoamWarps, kLoamMinB, 1><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    else if (b->st.geo_kind == 2) loam_kernel<true, kLoamWarps, kLoamMinB, 2><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
+    else loam_kernel<true, kLoamWarps, kLoamMinB, 0><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
     if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
     E->launches += 2;
     if ((rc = mark(ex, -1))) return rc;
@@ -1213,8 +1219,12 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
   static int attr_K = -1, attr_dev = -1;  // the opt-in is per function and device; only grows with K
   if (attr_dev != E->device || E->K > attr_K) {
-  if ((rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
-      (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB>, loam_smem_bytes(E->K))) ||
+  if ((rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB, 0>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB, 0>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB, 1>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB, 1>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB, 2>, loam_smem_bytes(E->K))) ||
+      (rc = set_smem(loam_kernel<false, kLoamWarps, kLoamMinB, 2>, loam_smem_bytes(E->K))) ||
       (rc = set_smem(imu_kernel<true, false>, smem4)) || (rc = set_smem(imu_kernel<false, false>, smem4)) ||
       (rc = set_smem(imu_kernel<true, true>, smem5)) ||
       (rc = set_smem(image_kernel<true, false>, factor_smem_bytes(E->K, 7))) ||
@@ -1312,6 +1322,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   for (int k = 0; k < 3; k++) B->st.p[k] = B->p[k].as<double>();
   for (int k = 0; k < 6; k++) B->st.g[k] = B->g[k].as<double>();
   B->st.type = B->type.as<uint8_t>();
+  B->st.geo_kind = 0;
   B->st.sh.S_GtoM = ldq(S_GtoM);
   B->st.sh.p_GinM = ldv(p_GinM);
   B->st.sh.S_LtoI = ldq(S_LtoI);
@@ -1328,15 +1339,19 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
   return CLIC_OK;
 }
 
-CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_point, const double* point,
-                                  const uint8_t* geo_type, const double* geo, const double S_GtoM[4],
-                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
-                                  int32_t marg_this_factor, int64_t* n_dropped) {
-  ScopedTrace trace("clic_add_loam_packed");
+namespace {
+// geo_kind 0: mixed (geo_type per feature, 6 geometry doubles each); 1: planes (4 doubles); 2: lines (6 doubles)
+int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t_point, const double* point,
+                     const uint8_t* geo_type, const double* geo, const double S_GtoM[4], const double p_GinM[3],
+                     const double S_LtoI[4], const double p_LinI[3], double weight, int32_t marg_this_factor,
+                     int64_t* n_dropped) {
+  ScopedTrace trace("clic_add_loam_records");
+  const int gstride = geo_kind == 1 ? 4 : 6;
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
-  if (!t_point || !point || !geo_type || !geo) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_packed: null array");
+  if (!t_point || !point || (geo_kind == 0 && !geo_type) || !geo)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_*: null array");
   CU(cudaSetDevice(E->device));
   cudaStream_t cs = E->copy_stream;
   AllocScope alloc_scope(cs);
@@ -1351,18 +1366,19 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   DevBuf &r_t = B->raw[0], &r_pt = B->raw[1], &r_type = B->raw[2], &r_geo = B->raw[3];
   int rc;
   if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
-      (rc = to_device(E, r_type, geo_type, n)) || (rc = to_device(E, r_geo, geo, 6 * n)))
+      (geo_kind == 0 && (rc = to_device(E, r_type, geo_type, n))) || (rc = to_device(E, r_geo, geo, gstride * n)))
     return rc;
   CU(B->t_ns.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
-  for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
-  CU(B->type.ensure(n));
+  for (int k = 0; k < gstride; k++) CU(B->g[k].ensure(n * sizeof(double)));
+  if (geo_kind == 0) CU(B->type.ensure(n));
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
-      n, r_t.as<double>(), r_pt.as<double>(), r_type.as<uint8_t>(), r_geo.as<double>(), ldq(S_LtoI), ldv(p_LinI), t_min, t_max,
+      n, r_t.as<double>(), r_pt.as<double>(), geo_kind == 0 ? r_type.as<uint8_t>() : nullptr, r_geo.as<double>(), gstride,
+      geo_kind == 1 ? 1 : 0, ldq(S_LtoI), ldv(p_LinI), t_min, t_max,
       B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
       B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
-      B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>());
+      geo_kind == 0 ? B->type.as<uint8_t>() : nullptr, E->d_counter.as<unsigned long long>());
   E->launches++;
   if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
     unsigned long long dropped = 0;
@@ -1375,6 +1391,7 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   for (int k = 0; k < 3; k++) B->st.p[k] = B->p[k].as<double>();
   for (int k = 0; k < 6; k++) B->st.g[k] = B->g[k].as<double>();
   B->st.type = B->type.as<uint8_t>();
+  B->st.geo_kind = geo_kind;
   B->st.sh.S_GtoM = ldq(S_GtoM);
   B->st.sh.p_GinM = ldv(p_GinM);
   B->st.sh.S_LtoI = ldq(S_LtoI);
@@ -1389,6 +1406,29 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
+}
+}  // namespace
+
+CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                  const uint8_t* geo_type, const double* geo, const double S_GtoM[4],
+                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped) {
+  return add_loam_records(E, 0, n, t_point, point, geo_type, geo, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                          marg_this_factor, n_dropped);
+}
+CLIC_API int clic_add_loam_planes(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                  const double* plane, const double S_GtoM[4], const double p_GinM[3],
+                                  const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped) {
+  return add_loam_records(E, 1, n, t_point, point, nullptr, plane, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                          marg_this_factor, n_dropped);
+}
+CLIC_API int clic_add_loam_lines(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                 const double* line, const double S_GtoM[4], const double p_GinM[3],
+                                 const double S_LtoI[4], const double p_LinI[3], double weight,
+                                 int32_t marg_this_factor, int64_t* n_dropped) {
+  return add_loam_records(E, 2, n, t_point, point, nullptr, line, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                          marg_this_factor, n_dropped);
 }
 
 CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp, const double* gyro,

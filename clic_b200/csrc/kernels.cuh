@@ -81,7 +81,8 @@ struct LoamStream {
   const int64_t* t_ns;
   const double* p[3];
   const double* g[6];
-  const uint8_t* type;  // 1 plane, 0 line
+  const uint8_t* type;  // 1 plane, 0 line (mixed streams only)
+  int geo_kind;         // 0 mixed, 1 planes only, 2 lines only (loam_kernel's GEO)
   LoamShared sh;
 };
 
@@ -287,7 +288,9 @@ __device__ __forceinline__ double warp_transpose_reduce24(const double (&v)[24],
 // warp transpose-reduce (FP64 DMMA and DFMA share one pipe on B200, so the 4th tile column would cost 3x more pipe
 // time than the 24 multiplies + 31 adds); sum r~^2 is the cost.  Evaluation is divergence-free: every lane evaluates,
 // masked lanes with a zero scale.  The loads of the next slab are issued before the DMMA phase of the current one.
-template <bool JAC, int WARPS, int MINB>
+// GEO: 0 = planes and lines mixed in one stream (type byte per feature), 1 = planes only (4 geometry doubles, the
+// line code is compiled out), 2 = lines only (no type byte; no intra-warp divergence between the two residuals).
+template <bool JAC, int WARPS, int MINB, int GEO = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   if (pass_prologue(pp)) return;
@@ -315,8 +318,9 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
       n_t = st.t_ns[idx];
       n_p0 = st.p[0][idx]; n_p1 = st.p[1][idx]; n_p2 = st.p[2][idx];
       n_g0 = st.g[0][idx]; n_g1 = st.g[1][idx]; n_g2 = st.g[2][idx];
-      n_g3 = st.g[3][idx]; n_g4 = st.g[4][idx]; n_g5 = st.g[5][idx];
-      n_ty = st.type[idx];
+      n_g3 = st.g[3][idx];
+      if (GEO != 1) { n_g4 = st.g[4][idx]; n_g5 = st.g[5][idx]; }
+      if (GEO == 0) n_ty = st.type[idx];
     }
   };
 #ifndef CLIC_LOAM_PREFETCH
@@ -336,7 +340,7 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
     double geo[6];
     geo[0] = valid ? n_g0 : 0.0; geo[1] = valid ? n_g1 : 0.0; geo[2] = valid ? n_g2 : 0.0;
     geo[3] = valid ? n_g3 : 0.0; geo[4] = valid ? n_g4 : 0.0; geo[5] = valid ? n_g5 : 0.0;
-    const bool is_plane = valid ? (n_ty != 0) : true;
+    const bool is_plane = GEO == 1 ? true : (valid ? (GEO == 2 ? false : (n_ty != 0)) : true);
     if (!valid) { s = 0; u = 0.0; }
     if (pp.marg_mode && valid && s >= pp.marg_later_local) valid = false;  // empty drop set: not part of the prior
     const int key = valid ? s : -1;
@@ -1273,8 +1277,10 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
   }
 }
 
+// geo_type == nullptr: a type-uniform batch (fixed_plane) whose geometry records are gstride (4 | 6) doubles long.
 __global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const double* point, const uint8_t* geo_type,
-                                        const double* geo, Q4 S_LtoI, V3 p_LinI, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
+                                        const double* geo, int gstride, int fixed_plane, Q4 S_LtoI, V3 p_LinI,
+                                        int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
                                         double* p1, double* p2, double* g0, double* g1, double* g2, double* g3,
                                         double* g4, double* g5, uint8_t* type, unsigned long long* n_dropped) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1285,9 +1291,10 @@ __global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const doub
   if (!ok) atomicAdd(n_dropped, 1ULL);
   const V3 pI = qrot(S_LtoI, mk(point[3 * i], point[3 * i + 1], point[3 * i + 2])) + p_LinI;  // LoamShared::point_in_imu
   p0[i] = pI.x; p1[i] = pI.y; p2[i] = pI.z;
-  type[i] = geo_type[i] == 1 ? 1 : 0;
-  g0[i] = geo[6 * i]; g1[i] = geo[6 * i + 1]; g2[i] = geo[6 * i + 2];
-  g3[i] = geo[6 * i + 3]; g4[i] = geo[6 * i + 4]; g5[i] = geo[6 * i + 5];
+  if (type) type[i] = geo_type ? (geo_type[i] == 1 ? 1 : 0) : (unsigned char)fixed_plane;
+  const double* gi = geo + (size_t)gstride * i;
+  g0[i] = gi[0]; g1[i] = gi[1]; g2[i] = gi[2]; g3[i] = gi[3];
+  if (gstride > 4) { g4[i] = gi[4]; g5[i] = gi[5]; }
 }
 
 __global__ void prep_imu_kernel(int64_t n, const double* t_s, const double* gyro, const double* accel, int64_t t_lo,

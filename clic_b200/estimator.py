@@ -176,6 +176,27 @@ class TrajectoryEstimator:
             int(bool(marg_this_factor)), C.byref(dropped) if count_dropped else None))
         return dropped.value
 
+    def _add_loam_typed(self, fn, t_point, point, geo, S_GtoM, p_GinM, S_LtoI, p_LinI, weight, marg, count_dropped):
+        t_point, point, geo = f64(t_point), f64(point), f64(geo)
+        S_GtoM, p_GinM, S_LtoI, p_LinI = f64(S_GtoM), f64(p_GinM), f64(S_LtoI), f64(p_LinI)
+        dropped = C.c_int64(0)
+        _check(self.lib, fn(self.h, len(t_point), dptr(t_point), dptr(point), dptr(geo), dptr(S_GtoM), dptr(p_GinM),
+                            dptr(S_LtoI), dptr(p_LinI), float(weight), int(bool(marg)),
+                            C.byref(dropped) if count_dropped else None))
+        return dropped.value
+
+    def AddLoamPlanes(self, t_point, point, plane4, S_GtoM, p_GinM, S_LtoI, p_LinI, weight, marg_this_factor=False,
+                      count_dropped=True):
+        """A time-sorted batch of plane features: plane4 = (n.x, n.y, n.z, d) per feature."""
+        return self._add_loam_typed(self.lib.clic_add_loam_planes, t_point, point, plane4, S_GtoM, p_GinM, S_LtoI, p_LinI,
+                                    weight, marg_this_factor, count_dropped)
+
+    def AddLoamLines(self, t_point, point, line6, S_GtoM, p_GinM, S_LtoI, p_LinI, weight, marg_this_factor=False,
+                     count_dropped=True):
+        """A time-sorted batch of line features: line6 = (geo_point xyz, geo_normal xyz) per feature."""
+        return self._add_loam_typed(self.lib.clic_add_loam_lines, t_point, point, line6, S_GtoM, p_GinM, S_LtoI, p_LinI,
+                                    weight, marg_this_factor, count_dropped)
+
     # ---- trajectory_estimator.h:153-156 (batched; gravity is the window's) ----
     def AddIMUMeasurementAnalytic(self, timestamp, gyro, accel, bias_slot, info_vec, marg_this_factor=False,
                                   count_dropped=True):

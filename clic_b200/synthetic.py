@@ -284,11 +284,28 @@ def pack_lidar(L):
                 geo6=np.ascontiguousarray(geo6))
 
 
+def split_lidar(L):
+    """PointCorrespondence field arrays -> a plane batch and a line batch (what the C++ shim stages), each time-sorted."""
+    plane = L["geo_type"] == GEO_PLANE
+    line = ~plane
+    return dict(pl_t=np.ascontiguousarray(L["t_point"][plane]), pl_point=np.ascontiguousarray(L["point"][plane]),
+                pl_geo=np.ascontiguousarray(L["geo_plane"][plane]),
+                ln_t=np.ascontiguousarray(L["t_point"][line]), ln_point=np.ascontiguousarray(L["point"][line]),
+                ln_geo=np.ascontiguousarray(np.concatenate([L["geo_point"][line], L["geo_normal"][line]], axis=1)))
+
+
 def add_all_factors(est, sw, marg=False, fixed_depth=True, bias_factor=True, count_dropped=True):
     """Feed a synthetic window to an estimator in the reference's call order
     (trajectory_manager.cpp:682-750: LiDAR, image, IMU, bias)."""
     dropped = 0
-    if len(sw.lidar.get("t_point", ())) and "geo6" in sw.lidar:
+    if "pl_t" in sw.lidar:
+        L = sw.lidar
+        ext = (L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
+        if len(L["pl_t"]):
+            dropped += est.AddLoamPlanes(L["pl_t"], L["pl_point"], L["pl_geo"], *ext)
+        if len(L["ln_t"]):
+            dropped += est.AddLoamLines(L["ln_t"], L["ln_point"], L["ln_geo"], *ext)
+    elif len(sw.lidar.get("t_point", ())) and "geo6" in sw.lidar:
         L = sw.lidar
         dropped += est.AddLoamMeasurementPacked(L["t_point"], L["point"], L["geo_type_u8"], L["geo6"], L["S_GtoM"],
                                                 L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)

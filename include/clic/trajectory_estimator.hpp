@@ -170,18 +170,17 @@ class TrajectoryEstimator {
       b.marg = marg_this_factor;
       loam_.push_back(b);
     }
+    // type-uniform staging (clic_add_loam_planes / clic_add_loam_lines): 64 B per plane, 80 B per line feature
     LoamBatch& b = loam_.back();
-    b.t.push_back(pc.t_point);
-    b.point.insert(b.point.end(), pc.point.begin(), pc.point.end());
-    b.type.push_back((uint8_t)pc.geo_type);
-    // packed geometry record of clic_add_loam_packed: plane (n, d, 0, 0) | line (point, direction)
     if (pc.geo_type == Plane) {
-      b.geo.insert(b.geo.end(), pc.geo_plane.begin(), pc.geo_plane.end());
-      b.geo.push_back(0.0);
-      b.geo.push_back(0.0);
+      b.pl_t.push_back(pc.t_point);
+      b.pl_point.insert(b.pl_point.end(), pc.point.begin(), pc.point.end());
+      b.pl_geo.insert(b.pl_geo.end(), pc.geo_plane.begin(), pc.geo_plane.end());
     } else {
-      b.geo.insert(b.geo.end(), pc.geo_point.begin(), pc.geo_point.end());
-      b.geo.insert(b.geo.end(), pc.geo_normal.begin(), pc.geo_normal.end());
+      b.ln_t.push_back(pc.t_point);
+      b.ln_point.insert(b.ln_point.end(), pc.point.begin(), pc.point.end());
+      b.ln_geo.insert(b.ln_geo.end(), pc.geo_point.begin(), pc.geo_point.end());
+      b.ln_geo.insert(b.ln_geo.end(), pc.geo_normal.begin(), pc.geo_normal.end());
     }
   }
 
@@ -266,8 +265,7 @@ class TrajectoryEstimator {
 
  private:
   struct LoamBatch {
-    std::vector<double> t, point, geo;
-    std::vector<uint8_t> type;
+    std::vector<double> pl_t, pl_point, pl_geo, ln_t, ln_point, ln_geo;
     SO3d S_GtoM, S_LtoI;
     Vec3d p_GinM{}, p_LinI{};
     double weight = 1;
@@ -370,10 +368,16 @@ class TrajectoryEstimator {
     // the reference's call order: prior, LiDAR, image, IMU, bias (trajectory_manager.cpp:659-750)
     for (auto& p : priors_)
       check(clic_add_prior(h_, p.info->prior, (int32_t)p.drop.size(), p.drop.empty() ? nullptr : p.drop.data()));
-    for (auto& b : loam_)
-      check(clic_add_loam_packed(h_, (int64_t)b.t.size(), b.t.data(), b.point.data(), b.type.data(), b.geo.data(),
-                                 b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
-                                 nullptr));
+    for (auto& b : loam_) {
+      if (!b.pl_t.empty())
+        check(clic_add_loam_planes(h_, (int64_t)b.pl_t.size(), b.pl_t.data(), b.pl_point.data(), b.pl_geo.data(),
+                                   b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
+                                   nullptr));
+      if (!b.ln_t.empty())
+        check(clic_add_loam_lines(h_, (int64_t)b.ln_t.size(), b.ln_t.data(), b.ln_point.data(), b.ln_geo.data(),
+                                  b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
+                                  nullptr));
+    }
     for (auto& b : image_)
       check(clic_add_image(h_, (int64_t)b.ti.size(), b.ti.data(), b.pi.data(), b.tj.data(), b.pj.data(), b.lm.data(),
                            b.fixed, b.marg, nullptr));

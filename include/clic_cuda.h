@@ -184,6 +184,20 @@ CLIC_API int clic_add_loam_packed(clic_estimator* h, int64_t n, const double* t_
                                   const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
                                   int32_t marg_this_factor, int64_t* n_dropped);
 
+/* Type-uniform batches of the same factors — what include/clic/trajectory_estimator.hpp stages: the shim routes each
+ * AddLoamMeasurementAnalytic call to a plane batch or a line batch by pc.geo_type.  64 B per plane feature
+ * (t 8 + point 24 + geo_plane 32) and 80 B per line feature (t 8 + point 24 + geo_point 24 + geo_normal 24): exactly
+ * the information the factor reads, over PCIe and in HBM; and a type-uniform kernel (no intra-warp
+ * divergence between the plane and the line residual).  Each batch must be time-sorted for full speed. */
+CLIC_API int clic_add_loam_planes(clic_estimator* h, int64_t n, const double* t_point, const double* point /*3n*/,
+                                  const double* plane /*4n: n.x n.y n.z d*/, const double S_GtoM[4],
+                                  const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped);
+CLIC_API int clic_add_loam_lines(clic_estimator* h, int64_t n, const double* t_point, const double* point /*3n*/,
+                                 const double* line /*6n: geo_point xyz, geo_normal xyz*/, const double S_GtoM[4],
+                                 const double p_GinM[3], const double S_LtoI[4], const double p_LinI[3], double weight,
+                                 int32_t marg_this_factor, int64_t* n_dropped);
+
 /* AddIMUMeasurementAnalytic (trajectory_estimator.cpp:369-455), batched over IMUData
  * (parameter_struct.h:52-58).  All samples of one call share a bias slot, like the reference's
  * call sites (trajectory_manager.cpp:731-735).  Loss CauchyLoss(marg ? 3 : 10) (":426-430"). */

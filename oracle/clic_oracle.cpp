@@ -1128,6 +1128,30 @@ CLIC_API int clic_add_loam_packed(clic_estimator* E, int64_t n, const double* t_
                        S_LtoI, p_LinI, weight, marg_this_factor, n_dropped);
 }
 
+CLIC_API int clic_add_loam_planes(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                  const double* plane, const double S_GtoM[4], const double p_GinM[3],
+                                  const double S_LtoI[4], const double p_LinI[3], double weight,
+                                  int32_t marg_this_factor, int64_t* n_dropped) {
+  std::vector<int32_t> type((size_t)std::max<int64_t>(n, 0), 1);  // GeometryType::Plane
+  return clic_add_loam(E, n, t_point, point, type.data(), plane, nullptr, nullptr, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                       marg_this_factor, n_dropped);
+}
+CLIC_API int clic_add_loam_lines(clic_estimator* E, int64_t n, const double* t_point, const double* point,
+                                 const double* line, const double S_GtoM[4], const double p_GinM[3],
+                                 const double S_LtoI[4], const double p_LinI[3], double weight,
+                                 int32_t marg_this_factor, int64_t* n_dropped) {
+  const size_t m = (size_t)std::max<int64_t>(n, 0);
+  std::vector<int32_t> type(m, 0);  // GeometryType::Line
+  std::vector<double> gpoint(3 * m), normal(3 * m);
+  for (size_t i = 0; i < m; i++)
+    for (int k = 0; k < 3; k++) {
+      gpoint[3 * i + k] = line[6 * i + k];
+      normal[3 * i + k] = line[6 * i + 3 + k];
+    }
+  return clic_add_loam(E, n, t_point, point, type.data(), nullptr, normal.data(), gpoint.data(), S_GtoM, p_GinM, S_LtoI,
+                       p_LinI, weight, marg_this_factor, n_dropped);
+}
+
 CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp, const double* gyro,
                           const double* accel, int32_t bias_slot, const double info_vec[6],
                           int32_t marg_this_factor, int64_t* n_dropped) {

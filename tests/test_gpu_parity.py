@@ -231,3 +231,31 @@ def test_packed_lidar_input_is_identical(cuda):
     assert out[0][0] == out[1][0]
     for a, b in zip(out[0][1:], out[1][1:]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.gpu
+def test_type_uniform_lidar_batches(cuda, oracle):
+    """clic_add_loam_planes + clic_add_loam_lines (what the C++ shim stages; type-uniform kernels) against the mixed
+    stream and against the oracle fed the same two batches: same drops, same H, b, cost."""
+    sw = S.make_window(12, n_lidar=6000, n_imu=0, line_fraction=0.35, seed=78)
+    L = sw.lidar
+    L["t_point"][5] = -1.0          # one dropped plane / line each
+    L["t_point"][11] = 1e3
+    sp = S.split_lidar(L)
+    ext = (L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"])
+    out = {}
+    for name, lib, split in (("mixed", cuda, False), ("split", cuda, True), ("oracle", oracle, True)):
+        est = E.TrajectoryEstimator(sw.window, E.default_options(lib), lib)
+        est.SetFixedIndex(1)
+        if split:
+            nd = est.AddLoamPlanes(sp["pl_t"], sp["pl_point"], sp["pl_geo"], *ext)
+            nd += est.AddLoamLines(sp["ln_t"], sp["ln_point"], sp["ln_geo"], *ext)
+        else:
+            nd = est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                                L["geo_point"], *ext)
+        out[name] = (nd,) + tuple(est.Evaluate())
+        est.close()
+    assert out["mixed"][0] == out["split"][0] == out["oracle"][0] == 2
+    for ref in ("mixed", "oracle"):
+        assert rel(out["split"][1], out[ref][1]) < REL and rel(out["split"][2], out[ref][2]) < REL
+        assert abs(out["split"][3] - out[ref][3]) <= REL * abs(out[ref][3])
