@@ -239,7 +239,8 @@ def main():
         opt.stream = C.c_void_p(stream.cuda_stream)
         est = E.TrajectoryEstimator(sw.window, opt, lib)
         est.SetFixedIndex(-1)
-        S.add_all_factors(est, srcs or sw_split, bias_factor=(rank == 0), count_dropped=(srcs is None))
+        S.add_all_factors(est, srcs or sw_split, bias_factor=(rank == 0), count_dropped=(srcs is None),
+                          small_first=(srcs is not None and os.environ.get("CLIC_BENCH_E2E_ORDER", "small") == "small"))
         return est
 
     est = new_estimator()

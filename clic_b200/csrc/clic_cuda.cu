@@ -149,6 +149,7 @@ struct StreamExec {
   // waits for it once, right before the first kernel that reads the batch (H2D of later batches overlaps compute).
   cudaEvent_t ready = nullptr;
   bool ready_waited = true;
+  long seq = 0;  // upload order (mark_ready)
   StreamExec() = default;
   StreamExec(const StreamExec&) = delete;
   StreamExec& operator=(const StreamExec&) = delete;
@@ -257,6 +258,7 @@ struct clic_estimator {
   clic_layout L;
   int n_desc = 0;
   DevBuf d_jobs;
+  long add_seq = 0;
   bool packs_fit = true;  // the packed visual kernel's shared memory fits this window
   int n_jobs = 0, n_part_ctas = 0, max_slots = 0;
   DevBuf d_bias_descs;
@@ -376,6 +378,7 @@ int mark_ready(clic_estimator* E, StreamExec& ex) {
   if (!ex.ready) CU(cudaEventCreateWithFlags(&ex.ready, cudaEventDisableTiming));
   CU(cudaEventRecord(ex.ready, E->copy_stream));
   ex.ready_waited = false;
+  ex.seq = ++E->add_seq;
   return CLIC_OK;
 }
 int wait_ready(clic_estimator* E, StreamExec& ex) {
@@ -603,8 +606,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
   pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
-  for (auto& b : E->loam) {
-    if (b->marg) continue;
+  auto launch_loam = [&](LoamBatch* b) -> int {
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = loam_smem_bytes(E->K);
@@ -625,9 +627,9 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_end();
       E->launches += 1;
     }
-  }
-  for (auto& b : E->imu) {
-    if (b->marg) continue;
+    return CLIC_OK;
+  };
+  auto launch_imu = [&](ImuBatch* b) -> int {
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 4);
@@ -645,9 +647,9 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
       E->prof_end();
       E->launches += 1;
     }
-  }
-  for (auto& b : E->image) {
-    if (b->marg) continue;
+    return CLIC_OK;
+  };
+  auto launch_image = [&](ImageBatch* b) -> int {
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 7);
@@ -668,6 +670,21 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     E->prof_end();
     E->launches += 1;
     pp.pdl_first = 0;
+    return CLIC_OK;
+  };
+  // Factor kernels are independent of each other: launch them in the order their batches were uploaded, so that a
+  // kernel whose data has arrived runs under the uploads still in flight (per-batch ready events on the copy stream).
+  struct Item { long seq; int kind; void* p; };
+  std::vector<Item> order;
+  for (auto& b : E->loam) if (!b->marg) order.push_back({b->ex.seq, 0, b.get()});
+  for (auto& b : E->imu) if (!b->marg) order.push_back({b->ex.seq, 1, b.get()});
+  for (auto& b : E->image) if (!b->marg) order.push_back({b->ex.seq, 2, b.get()});
+  std::sort(order.begin(), order.end(), [](const Item& x, const Item& y) { return x.seq < y.seq; });
+  for (auto& it : order) {
+    if (it.kind == 0) rc = launch_loam(static_cast<LoamBatch*>(it.p));
+    else if (it.kind == 1) rc = launch_imu(static_cast<ImuBatch*>(it.p));
+    else rc = launch_image(static_cast<ImageBatch*>(it.p));
+    if (rc) return rc;
   }
   if (E->n_jobs == 0) {  // no factor stream at all (prior-only problem)
     CU(launch_pdl(zero_cost_kernel, 1, 32, 0, E->stream, cost2, ctl));

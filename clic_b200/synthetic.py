@@ -294,34 +294,50 @@ def split_lidar(L):
                 ln_geo=np.ascontiguousarray(np.concatenate([L["geo_point"][line], L["geo_normal"][line]], axis=1)))
 
 
-def add_all_factors(est, sw, marg=False, fixed_depth=True, bias_factor=True, count_dropped=True):
-    """Feed a synthetic window to an estimator in the reference's call order
-    (trajectory_manager.cpp:682-750: LiDAR, image, IMU, bias)."""
-    dropped = 0
-    if "pl_t" in sw.lidar:
+def add_all_factors(est, sw, marg=False, fixed_depth=True, bias_factor=True, count_dropped=True, small_first=False):
+    """Feed a synthetic window to an estimator in the reference's call order (trajectory_manager.cpp:682-750: LiDAR,
+    image, IMU, bias) or, small_first, in the upload order of the C++ shim: plane batch (the big asynchronous copy
+    goes first, the host-side staging of the visual batch runs under it), image, IMU, line batch (the kernel left
+    exposed after the last byte arrives is the smallest one).  The normal equations do not depend on the order."""
+    def lidar(part="all"):
         L = sw.lidar
-        ext = (L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
-        if len(L["pl_t"]):
-            dropped += est.AddLoamPlanes(L["pl_t"], L["pl_point"], L["pl_geo"], *ext)
-        if len(L["ln_t"]):
-            dropped += est.AddLoamLines(L["ln_t"], L["ln_point"], L["ln_geo"], *ext)
-    elif len(sw.lidar.get("t_point", ())) and "geo6" in sw.lidar:
-        L = sw.lidar
-        dropped += est.AddLoamMeasurementPacked(L["t_point"], L["point"], L["geo_type_u8"], L["geo6"], L["S_GtoM"],
+        if "pl_t" in L:
+            ext = (L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
+            n = 0
+            if part in ("all", "planes") and len(L["pl_t"]):
+                n += est.AddLoamPlanes(L["pl_t"], L["pl_point"], L["pl_geo"], *ext)
+            if part in ("all", "lines") and len(L["ln_t"]):
+                n += est.AddLoamLines(L["ln_t"], L["ln_point"], L["ln_geo"], *ext)
+            return n
+        if part == "lines":
+            return 0
+        if len(L.get("t_point", ())) and "geo6" in L:
+            return est.AddLoamMeasurementPacked(L["t_point"], L["point"], L["geo_type_u8"], L["geo6"], L["S_GtoM"],
                                                 L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
-    elif len(sw.lidar.get("t_point", ())):
-        L = sw.lidar
-        dropped += est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"],
+        if len(L.get("t_point", ())):
+            return est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"],
                                                   L["geo_normal"], L["geo_point"], L["S_GtoM"], L["p_GinM"],
                                                   L["S_LtoI"], L["p_LinI"], L["weight"], marg, count_dropped)
-    if len(sw.image.get("t_i", ())):
+        return 0
+
+    def image():
         I = sw.image
-        dropped += est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], fixed_depth, marg,
-                                               count_dropped)
-    if len(sw.imu.get("timestamp", ())):
+        if not len(I.get("t_i", ())):
+            return 0
+        return est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], fixed_depth, marg,
+                                           count_dropped)
+
+    def imu():
         M = sw.imu
-        dropped += est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], M["bias_slot"],
-                                                 M["info_vec"], marg, count_dropped)
+        if not len(M.get("timestamp", ())):
+            return 0
+        return est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], M["bias_slot"], M["info_vec"], marg,
+                                             count_dropped)
+
+    if small_first:
+        dropped = lidar("planes") + image() + imu() + lidar("lines")
+    else:
+        dropped = lidar() + image() + imu()
     nb = sw.window.bias.shape[0]
     if bias_factor and nb >= 2:
         # trajectory_manager.cpp:738-750: cov = delta_time/dt * dt^2, sqrt_info = bias_info_vec / sqrt(cov), dt arg = 1

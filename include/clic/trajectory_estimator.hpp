@@ -365,25 +365,27 @@ class TrajectoryEstimator {
     o.stream = options.stream;
     check(clic_create(&w, &o, &h_));
     check(clic_set_fixed_index(h_, fixed_control_point_index_));
-    // the reference's call order: prior, LiDAR, image, IMU, bias (trajectory_manager.cpp:659-750)
+    // the reference's call order is prior, LiDAR, image, IMU, bias (trajectory_manager.cpp:659-750).  Upload order here:
+    // plane batch first (big asynchronous copy; the visual batch's host-side staging runs under it), image, IMU, line
+    // batch last (the kernel left exposed after the last byte arrives is the smallest).  H, b do not depend on it.
     for (auto& p : priors_)
       check(clic_add_prior(h_, p.info->prior, (int32_t)p.drop.size(), p.drop.empty() ? nullptr : p.drop.data()));
-    for (auto& b : loam_) {
+    for (auto& b : loam_)
       if (!b.pl_t.empty())
         check(clic_add_loam_planes(h_, (int64_t)b.pl_t.size(), b.pl_t.data(), b.pl_point.data(), b.pl_geo.data(),
                                    b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
                                    nullptr));
-      if (!b.ln_t.empty())
-        check(clic_add_loam_lines(h_, (int64_t)b.ln_t.size(), b.ln_t.data(), b.ln_point.data(), b.ln_geo.data(),
-                                  b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
-                                  nullptr));
-    }
     for (auto& b : image_)
       check(clic_add_image(h_, (int64_t)b.ti.size(), b.ti.data(), b.pi.data(), b.tj.data(), b.pj.data(), b.lm.data(),
                            b.fixed, b.marg, nullptr));
     for (auto& b : imu_)
       check(clic_add_imu(h_, (int64_t)b.t.size(), b.t.data(), b.gyro.data(), b.accel.data(), b.slot, b.info.data(),
                          b.marg, nullptr));
+    for (auto& b : loam_)
+      if (!b.ln_t.empty())
+        check(clic_add_loam_lines(h_, (int64_t)b.ln_t.size(), b.ln_t.data(), b.ln_point.data(), b.ln_geo.data(),
+                                  b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
+                                  nullptr));
     for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
   }
 
