@@ -841,25 +841,25 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_step));
   int rc;
   if (constrained) {
-    lm_project_kernel<<<1, 256, 0, E->stream>>>(B, L);
+    CU(launch_pdl(lm_project_kernel, 1, 256, 0, E->stream, B, L));
     E->launches++;
   }
   if ((rc = run_pass(E, B.x, true, 0, nullptr))) return rc;
   E->prof_begin(5);
-  lm_init_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C, max_iterations, constrained ? 1 : 0);
+  CU(launch_pdl(lm_init_kernel, 1, 256, sm_small, E->stream, B, L, C, max_iterations, constrained ? 1 : 0));
   E->prof_end();
   E->launches++;
   const int max_ls = 20;  // Ceres default max_num_line_search_step_size_iterations
   for (int it = 0; it <= max_iterations; it++) {
     E->prof_begin(5);
-    lm_step_kernel<<<1, 512, sm_step, E->stream>>>(B, L, C, a_in_smem, constrained ? 1 : 0);
+    CU(launch_pdl(lm_step_kernel, 1, 512, sm_step, E->stream, B, L, C, a_in_smem, constrained ? 1 : 0));
     E->prof_end();
     E->launches++;
     if (it == max_iterations) break;  // the last launch only records the max-iterations termination
     if ((rc = run_pass(E, B.cand, speculate, 1, ctl_res, speculate ? 1 : 0))) return rc;
     if (constrained) {
       for (int ls = 0; ls < max_ls + 1; ls++) {
-        lm_linesearch_kernel<<<1, 256, 0, E->stream>>>(B, L, max_ls);
+        CU(launch_pdl(lm_linesearch_kernel, 1, 256, 0, E->stream, B, L, max_ls));
         E->launches++;
         if ((rc = run_pass(E, B.cand, false, 1, ctl_res))) return rc;
         int active = 0;
@@ -869,12 +869,12 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
       }
     }
     E->prof_begin(5);
-    lm_accept_kernel<<<1, 256, sm_small, E->stream>>>(B, L, C);
+    CU(launch_pdl(lm_accept_kernel, 1, 256, sm_small, E->stream, B, L, C));
     E->prof_end();
     E->launches++;
     if (!speculate && (rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
     E->prof_begin(5);
-    lm_post_kernel<<<1, 256, sm_small, E->stream>>>(B, L);
+    CU(launch_pdl(lm_post_kernel, 1, 256, sm_small, E->stream, B, L));
     E->prof_end();
     E->launches++;
   }

@@ -419,6 +419,8 @@ __device__ __forceinline__ void gradient_norms(const LmBufs& B, const LayoutDev&
 
 // IterationZero of a bounded problem: x <- Plus(x, 0) projects the start point onto the feasible set.
 __global__ void lm_project_kernel(LmBufs B, LayoutDev L) {
+  pdl_wait();
+  pdl_trigger();
   for (int i = threadIdx.x; i < L.D; i += blockDim.x) B.step[i] = 0.0;
   __syncthreads();
   plus_state(B.x, B.step, 1.0, B.tmp, L);
@@ -435,6 +437,8 @@ __global__ void zero_cost_kernel(double* cost2, const int* ctl) {
 
 // After the iteration-0 Jacobian pass: Jacobi scaling, active mask, norms, LM state.
 __global__ void lm_init_kernel(LmBufs B, LayoutDev L, LmConst C, int max_iterations, int is_constrained) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sh[];
   const int D = L.D;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -474,6 +478,8 @@ __global__ void lm_init_kernel(LmBufs B, LayoutDev L, LmConst C, int max_iterati
 // One LM iteration, first half: termination tests, damping, Cholesky, step, model decrease, candidate = x (+) delta.
 // A lives in shared memory when it fits (a_in_smem), else in global scratch.
 __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmConst C, int a_in_smem, int is_constrained) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sh[];
   LmState* s = B.st;
   const int D = L.D;
@@ -600,6 +606,8 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
 // after each residual pass at cand = x (+) cur*delta while s->ls_active: decides accept / contract (oracle: quadratic
 // interpolation with Ceres' contraction clamps), and writes the next candidate.
 __global__ void lm_linesearch_kernel(LmBufs B, LayoutDev L, int max_ls_iterations) {
+  pdl_wait();
+  pdl_trigger();
   LmState* s = B.st;
   if (s->done || !s->step_valid || !s->ls_active) return;
   __shared__ int next;
@@ -647,6 +655,8 @@ __global__ void lm_linesearch_kernel(LmBufs B, LayoutDev L, int max_ls_iteration
 
 // Second half of the iteration, after the residual-only pass at the candidate.
 __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sh[];
   LmState* s = B.st;
   __shared__ int go;
@@ -695,6 +705,7 @@ __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
     for (int i = threadIdx.x; i < n_state; i += blockDim.x) B.x[i] = B.cand[i];
     if (B.Hc) {  // the candidate was evaluated with its Jacobians: adopt its system, no further pass needed
       const int D = L.D;
+#pragma unroll 8
       for (int i = threadIdx.x; i < D * D; i += blockDim.x) B.H[i] = B.Hc[i];
       for (int i = threadIdx.x; i < D; i += blockDim.x) B.b[i] = B.bc[i];
       if (threadIdx.x < 2) B.cost_x[threadIdx.x] = B.cost_c[threadIdx.x];
@@ -704,6 +715,8 @@ __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
 
 // After the (conditional) Jacobian pass at the accepted point.
 __global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sh[];
   LmState* s = B.st;
   if (s->done || s->skip_jac) return;
