@@ -226,20 +226,23 @@ def main():
     ab = algorithmic_bytes(sw)
 
     # the LiDAR stream as the C++ shim hands it over: a plane batch and a line batch (clic_add_loam_planes / _lines)
-    sw_split = type(sw)(window=sw.window, gt_knot_q=sw.gt_knot_q, gt_knot_p=sw.gt_knot_p, name=sw.name)
-    sw_split.imu, sw_split.image = sw.imu, sw.image
-    sw_split.lidar = {k: v for k, v in sw.lidar.items()
-                      if k not in ("t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point")}
-    sw_split.lidar.update(S.split_lidar(sw.lidar))
+    def as_shim_batches(w):
+        out = type(w)(window=w.window, gt_knot_q=w.gt_knot_q, gt_knot_p=w.gt_knot_p, name=w.name)
+        out.imu, out.image = w.imu, w.image
+        out.lidar = {k: v for k, v in w.lidar.items()
+                     if k not in ("t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point")}
+        out.lidar.update(S.split_lidar(w.lidar))
+        return out
+    sw_split = as_shim_batches(sw)
 
-    def new_estimator(srcs=None):
+    def new_estimator(srcs=None, dropped=False):
         opt = E.default_options(lib)
         opt.lock_ab = opt.lock_wb = 0
         opt.device = local_rank
         opt.stream = C.c_void_p(stream.cuda_stream)
         est = E.TrajectoryEstimator(sw.window, opt, lib)
         est.SetFixedIndex(-1)
-        S.add_all_factors(est, srcs or sw_split, bias_factor=(rank == 0), count_dropped=(srcs is None),
+        S.add_all_factors(est, srcs or sw_split, bias_factor=(rank == 0), count_dropped=(srcs is None or dropped),
                           small_first=(srcs is not None and os.environ.get("CLIC_BENCH_E2E_ORDER", "small") == "small"))
         return est
 
@@ -316,9 +319,7 @@ def main():
     if world > 1:
         sw_c5 = shard(make_workload(args.scale, with_visual=HAVE_VISUAL), rank, world)
         n_c5 = FULL["n_lidar"] + FULL["n_imu"]
-        keep_sw, sw = sw, sw_c5
-        es = new_estimator()
-        sw = keep_sw
+        es = new_estimator(as_shim_batches(sw_c5), dropped=True)
         es.comm_init_torch(dist, rank, world)
         with torch.cuda.stream(stream):
             for _ in range(3):
