@@ -144,6 +144,10 @@ PROTOTYPES = {
     "clic_prior_release": (C.c_int, [H]),
     "clic_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "clic_comm_init": (C.c_int, [H, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "clic_comm_p2p_export": (C.c_int, [H, C.POINTER(C.c_uint8)]),
+    "clic_comm_p2p_import": (C.c_int, [H, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "clic_comm_p2p_ready": (C.c_int, []),
+    "clic_comm_p2p_disable": (C.c_int, []),
     "clic_linearize_async": (C.c_int, [H, C.c_int32]),
     "clic_synchronize": (C.c_int, [H]),
     "clic_num_kernel_launches": (C.c_int, [H, c_int64_p]),

@@ -79,6 +79,16 @@ struct ProcessComm {
 } g_comm;
 constexpr int kNcclDouble = 8, kNcclSum = 0;
 
+// Peer-memory exchange areas for the one-shot all-reduce (kernels.cuh), one per process, mapped into every peer with
+// CUDA IPC.  Optional: without it (single rank, IPC unavailable, D too large) the all-reduce is ncclAllReduce.
+struct ProcessP2P {
+  bool ready = false;
+  void* local = nullptr;
+  clic::P2PView view{};
+  unsigned long long seq = 0;  // all-reduce sequence number; every rank issues the same sequence of all-reduces
+  int* d_err = nullptr;
+} g_p2p;
+
 // Device buffer from the stream-ordered memory pool (cudaMallocAsync): an estimator is built per solve like the
 // reference's (trajectory_manager.cpp:637), so allocations must be cheap; the pool keeps freed blocks cached.
 thread_local cudaStream_t g_alloc_stream = nullptr;
@@ -392,6 +402,15 @@ int join_adds(clic_estimator* E) {
   for (auto& b : E->loam) if ((rc = wait_ready(E, b->ex))) return rc;
   for (auto& b : E->imu) if ((rc = wait_ready(E, b->ex))) return rc;
   for (auto& b : E->image) if ((rc = wait_ready(E, b->ex))) return rc;
+  return CLIC_OK;
+}
+
+// After a synchronisation: did a one-shot all-reduce give up waiting for a peer?
+int check_p2p(clic_estimator* E) {
+  if (!E->use_comm || !g_p2p.ready) return CLIC_OK;
+  int err = 0;
+  CU(cudaMemcpy(&err, g_p2p.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail(CLIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank");
   return CLIC_OK;
 }
 
@@ -753,11 +772,17 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     E->prof_begin(6);
     NcclApi& nc = nccl_api();
     const size_t DD = (size_t)std::max(1, D) * std::max(1, D) + std::max(1, D);
-    int e;
-    if (jac)
-      e = nc.AllReduce(Hp, E->nrm_glb_set(set), DD + 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
-    else
-      e = nc.AllReduce(cost2, E->nrm_glb_set(set) + (cost2 - Hp), 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+    int e = 0;
+    const double* ar_src = jac ? Hp : cost2;
+    double* ar_dst = jac ? E->nrm_glb_set(set) : E->nrm_glb_set(set) + (cost2 - Hp);
+    const size_t ar_count = jac ? DD + 2 : 2;
+    if (g_p2p.ready && ar_count <= kP2PMaxDoubles) {
+      CU(launch_pdl(p2p_allreduce_kernel, 1, 1024, 0, E->stream, ar_src, ar_dst, (int)ar_count, g_p2p.view, ++g_p2p.seq,
+                    g_p2p.d_err));
+      E->launches++;
+    } else {
+      e = nc.AllReduce(ar_src, ar_dst, ar_count, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+    }
     E->prof_end();
     if (e != 0) return fail(CLIC_ERR_NCCL, std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "?"));
   }
@@ -885,6 +910,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
   if (in_flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
+  if (int prc = check_p2p(E)) return prc;
   if (summary) {
     std::memset(summary, 0, sizeof(*summary));
     summary->iterations = st.iteration;
@@ -1783,6 +1809,7 @@ CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost
   CU(cudaMemcpyAsync(flags, E->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   if (flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
+  if (int prc = check_p2p(E)) return prc;
   if (cost) *cost = c2[0];
   if (fixed_cost) *fixed_cost = c2[1];
   return CLIC_OK;
@@ -2091,6 +2118,50 @@ CLIC_API int clic_comm_init(clic_estimator* E, int32_t n_ranks, int32_t rank, co
   E->layout_dirty = true;
   return CLIC_OK;
 }
+
+CLIC_API int clic_comm_p2p_export(clic_estimator* E, uint8_t handle[64]) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(E->device));
+  if (!g_p2p.local) {
+    CU(cudaMalloc(&g_p2p.local, p2p_area_bytes()));
+    CU(cudaMemset(g_p2p.local, 0, p2p_area_bytes()));
+    CU(cudaMalloc(&g_p2p.d_err, sizeof(int)));
+    CU(cudaMemset(g_p2p.d_err, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, g_p2p.local));
+  std::memcpy(handle, &h, 64);
+  return CLIC_OK;
+}
+
+CLIC_API int clic_comm_p2p_import(clic_estimator* E, int32_t n_ranks, int32_t rank, const uint8_t* handles) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (g_p2p.ready) return CLIC_OK;
+  if (n_ranks < 2 || n_ranks > kP2PMaxRanks || rank < 0 || rank >= n_ranks || !handles || !g_p2p.local)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "clic_comm_p2p_import: export first; 2..16 ranks");
+  CU(cudaSetDevice(E->device));
+  g_p2p.view.n = n_ranks;
+  g_p2p.view.rank = rank;
+  for (int r = 0; r < n_ranks; r++) {
+    if (r == rank) { g_p2p.view.peer[r] = static_cast<char*>(g_p2p.local); continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * r, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(CLIC_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    g_p2p.view.peer[r] = static_cast<char*>(p);
+  }
+  g_p2p.ready = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_comm_p2p_ready(void) { return g_p2p.ready ? 1 : 0; }
+CLIC_API int clic_comm_p2p_disable(void) { g_p2p.ready = false; return CLIC_OK; }
 
 CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");

@@ -955,6 +955,60 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
   pass_epilogue(pp);
 }
 
+// ---------------- one-shot all-reduce over NVLink peer memory ----------------
+// The exchange step of the path is tiny (H | b | cost: D^2 + D + 2 doubles, 42 KB at C5) and latency-bound, so instead
+// of a ring / tree collective every rank PUSHES its vector into a per-source slot of every peer's exchange area
+// (posted NVLink stores), publishes the sequence number with a system-scope release store, waits for the n_ranks
+// flags of its own area with acquire loads, and sums the n_ranks slots in rank order from LOCAL memory: one launch,
+// one NVLink hop, and the same summation order on every rank (bit-identical results).  Slots are double-buffered by
+// the parity of the sequence number: a rank can only be one all-reduce ahead of its slowest peer, so a slot is never
+// overwritten while it is still being read.  The wait is bounded (~1 s): a missing peer sets *err instead of hanging.
+constexpr int kP2PMaxRanks = 16;
+constexpr size_t kP2PMaxDoubles = 128 * 1024;  // per slot: D <= ~360
+constexpr size_t kP2PFlagBytes = 256;
+struct P2PView {
+  char* peer[kP2PMaxRanks];  // exchange areas: [flags: kP2PMaxRanks x u64][slots: 2 x kP2PMaxRanks x kP2PMaxDoubles doubles]
+  int n, rank;
+};
+__host__ __device__ inline size_t p2p_area_bytes() {
+  return kP2PFlagBytes + (size_t)2 * kP2PMaxRanks * kP2PMaxDoubles * sizeof(double);
+}
+__device__ __forceinline__ double* p2p_slot(char* area, int parity, int src_rank) {
+  return reinterpret_cast<double*>(area + kP2PFlagBytes) + ((size_t)parity * kP2PMaxRanks + src_rank) * kP2PMaxDoubles;
+}
+__global__ void __launch_bounds__(1024) p2p_allreduce_kernel(const double* src, double* dst, int count, P2PView v,
+                                                             unsigned long long seq, int* err) {
+  pdl_wait();
+  pdl_trigger();
+  const int tid = threadIdx.x, parity = (int)(seq & 1ull);
+  for (int i = tid; i < count; i += blockDim.x) {
+    const double x = src[i];
+    for (int r = 0; r < v.n; r++) p2p_slot(v.peer[r], parity, v.rank)[i] = x;
+  }
+  __syncthreads();
+  if (tid < v.n) {
+    __threadfence_system();  // cumulative over the CTA's stores ordered before the barrier
+    unsigned long long* remote = reinterpret_cast<unsigned long long*>(v.peer[tid]) + v.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(seq) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(v.peer[v.rank]) + tid;
+    const long long t0 = clock64();
+    unsigned long long got = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+      if (got >= seq) break;
+      if (clock64() - t0 > (1ll << 31)) { *err = 1; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  char* local = v.peer[v.rank];
+  for (int i = tid; i < count; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < v.n; r++) acc += __ldcv(p2p_slot(local, parity, r) + i);
+    dst[i] = acc;
+  }
+}
+
 // ---------------- forward-only spline evaluation (the step before the path) ----------------
 // Trajectory::GetSensorPose (trajectory.cpp:100-115) for a batch of timestamps: one query per thread, grid-stride;
 // the knot-only part of So3Spline::evaluate (delta_i = log(R_i^-1 R_i+1), so3_spline.h:240-244) comes from the

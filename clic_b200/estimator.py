@@ -289,6 +289,21 @@ class TrajectoryEstimator:
         dist.broadcast(t, src=0)
         ident = (C.c_uint8 * 128)(*t.cpu().tolist())
         _check(self.lib, self.lib.clic_comm_init(self.h, int(world), int(rank), ident))
+        # one-shot all-reduce over NVLink peer memory (CUDA IPC between the ranks of one node); NCCL stays the fallback
+        import os
+        if (world > 1 and dist.get_backend() == "nccl" and not os.environ.get("CLIC_NO_P2P")
+                and not self.lib.clic_comm_p2p_ready()):
+            mine = (C.c_uint8 * 64)()
+            _check(self.lib, self.lib.clic_comm_p2p_export(self.h, mine))
+            local = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+            gathered = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(gathered, local)
+            flat = (C.c_uint8 * (64 * world))(*torch.cat(gathered).cpu().tolist())
+            rc = self.lib.clic_comm_p2p_import(self.h, int(world), int(rank), flat)
+            ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # every rank must take the same path
+            if int(ok.item()) == 0:  # e.g. no CUDA IPC between the processes: keep ncclAllReduce on every rank
+                self.lib.clic_comm_p2p_disable()
 
     # ---- measurement hooks ----
     def linearize_async(self, reps=1):

@@ -285,6 +285,16 @@ CLIC_API int clic_comm_init(clic_estimator* h, int32_t n_ranks, int32_t rank, co
 
 /* Measurement hooks used by bench.py: repeat the fused pass `reps` times on the handle's stream without
  * host synchronisation in between (CUDA events are recorded by the caller on that stream). */
+/* Optional, after clic_comm_init on every rank of ONE node: map every rank's exchange area into every peer (CUDA IPC)
+ * so that the per-pass all-reduce of H | b | cost becomes a single one-shot kernel over NVLink peer memory (pushed
+ * slots + flags, summed in rank order: same bits on every rank) instead of ncclAllReduce.  export -> all-gather the
+ * 64-byte handles by any means (bench.py: torch.distributed) -> import on every rank.  Process-wide like the
+ * communicator.  If the import fails (no IPC between the processes) the NCCL path stays in use. */
+CLIC_API int clic_comm_p2p_export(clic_estimator* h, uint8_t handle[64]);
+CLIC_API int clic_comm_p2p_import(clic_estimator* h, int32_t n_ranks, int32_t rank, const uint8_t* handles /*64*n*/);
+CLIC_API int clic_comm_p2p_ready(void);
+CLIC_API int clic_comm_p2p_disable(void); /* back to ncclAllReduce (must be called on every rank) */
+
 CLIC_API int clic_linearize_async(clic_estimator* h, int32_t reps);
 CLIC_API int clic_synchronize(clic_estimator* h);
 CLIC_API int clic_num_kernel_launches(clic_estimator* h, int64_t* launches);

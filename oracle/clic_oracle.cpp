@@ -1584,6 +1584,11 @@ CLIC_API int clic_comm_unique_id(uint8_t*) { return fail(CLIC_ERR_UNSUPPORTED, "
 CLIC_API int clic_comm_init(clic_estimator*, int32_t, int32_t, const uint8_t*) {
   return fail(CLIC_ERR_UNSUPPORTED, "oracle is single-process");
 }
+CLIC_API int clic_comm_p2p_export(clic_estimator*, uint8_t handle[64]) { std::memset(handle, 0, 64); return CLIC_OK; }
+CLIC_API int clic_comm_p2p_import(clic_estimator*, int32_t, int32_t, const uint8_t*) { return CLIC_OK; }
+CLIC_API int clic_comm_p2p_ready(void) { return 0; }
+CLIC_API int clic_comm_p2p_disable(void) { return CLIC_OK; }
+
 CLIC_API int clic_linearize_async(clic_estimator* E, int32_t reps) {
   if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   EvalOut ev;
