@@ -369,7 +369,7 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
 size_t factor_smem_bytes(int K, int NT) {
   // NT column tiles of the transposed Jacobian tile per warp; the end-of-kernel merge scratch aliases it
   size_t jt = (size_t)kWarpsPerCta * 8 * NT * kJtStride;
-  jt = std::max<size_t>(jt, (size_t)rec_doubles(NT, 1));
+  jt = std::max<size_t>(jt, (size_t)kWarpsPerCta * rec_doubles(NT, 1));  // every warp parks its accumulator there
   return (window_smem_doubles(K) + jt) * sizeof(double);
 }
 
@@ -379,7 +379,7 @@ size_t image_smem_bytes(int K, int n_packs) {
 
 size_t loam_smem_bytes(int K) {
   size_t jt = (size_t)kLoamWarps * 24 * kJtStride;
-  jt = std::max<size_t>(jt, (size_t)rec_doubles(3, 1));
+  jt = std::max<size_t>(jt, (size_t)kLoamWarps * rec_doubles(3, 1));
   return (window_smem_doubles(K) + jt) * sizeof(double);
 }
 
