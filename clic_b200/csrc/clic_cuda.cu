@@ -152,8 +152,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 struct StreamExec {
   int64_t n = 0;
   int grid = 0, slabs_per_warp = 0, n_warps = 0, warps_per_cta = kWarpsPerCta;
-  int NT = 4, rd = 640, n_keys = 0, P = 8;
-  DevBuf payload, key, cost, part, overflow;
+  int NT = 4, rd = 640, n_keys = 0;
+  DevBuf payload, key, cost, overflow;
   DevBuf fin;  // solve path: per-key final blocks of reduce_all_kernel
   // The adders upload on the estimator's copy stream; `ready` marks the batch complete there and the compute stream
   // waits for it once, right before the first kernel that reads the batch (H2D of later batches overlaps compute).
@@ -350,14 +350,9 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.slabs_per_warp = (int)slabs;  // = total slabs (kernel argument)
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
-  // reduction parts: ~512 record slots (16 CTAs) each: a (key, part) CTA sums at most ~17 records of a sorted stream
-  // and all streams' (key, part) CTAs together stay within one wave of the GPU
-  ex.P = (int)std::min<size_t>(pair_keys ? 8 : 64, std::max<size_t>(1, slots / 512));
-  ex.P = std::max<int>(ex.P, (int)((slots + kMaxChunk - 1) / kMaxChunk));
   CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
   CU(ex.key.ensure(slots * sizeof(int)));
   CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
-  CU(ex.part.ensure((size_t)ex.n_keys * ex.P * ex.rd * sizeof(double)));
   CU(ex.overflow.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
   CU(ex.fin.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
   // reduce_all_kernel folds the atomics-fallback block into fin and re-zeroes it
@@ -530,24 +525,6 @@ int ensure_layout(clic_estimator* E) {
   return CLIC_OK;
 }
 
-
-int launch_reduce(clic_estimator* E, const StreamExec& ex, double* cost2, bool first_stream, const int* ctl) {
-  dim3 g(ex.n_keys + 1, ex.P);  // + 1: the cost-reduction CTA
-  const int n_slots = ex.n_warps * kSlotsPerWarp;
-#define CLIC_RR(RD)                                                                                             \
-  reduce_records_kernel<RD><<<g, 256, 0, E->stream>>>(ex.payload.as<double>(), ex.key.as<int>(), n_slots, ex.P,  \
-                                                      ex.part.as<double>(), ex.cost.as<double>(), ex.n_warps, cost2, \
-                                                      first_stream ? 1 : 0, ctl)
-  switch (ex.NT) {
-    case 3: CLIC_RR(416); break;
-    case 4: CLIC_RR(640); break;
-    case 5: CLIC_RR(960); break;
-    case 7: CLIC_RR(1792); break;
-    default: return 1;
-  }
-#undef CLIC_RR
-  return 0;
-}
 
 int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* state, double* cost2, bool jac,
                  const int* ctl, double* Hp, double* bp) {
@@ -944,9 +921,30 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   CU(d_present.ensure((size_t)(K - 3) * sizeof(int)));
   std::vector<char> knot_used(K, 0);
   std::vector<int> present(K - 3);
+  DevBuf d_job;
+  CU(d_job.ensure(sizeof(ReduceJob)));
+  // records of one marg stream -> per-key blocks ex.fin (the same reduction kernel as the solve path, one job)
+  auto reduce_stream = [&](StreamExec& ex) -> int {
+    ReduceJob j{};
+    j.payload = ex.payload.as<double>();
+    j.key = ex.key.as<int>();
+    j.fin = ex.fin.as<double>();
+    j.overflow = ex.overflow.as<double>();
+    j.warp_cost = ex.cost.as<double>();
+    j.n_slots = ex.n_warps * kSlotsPerWarp;
+    j.n_keys = ex.n_keys; j.rd = ex.rd; j.n_warps = ex.n_warps;
+    j.cta0 = 0;
+    CU(cudaMemcpyAsync(d_job.p, &j, sizeof(j), cudaMemcpyHostToDevice, E->stream));
+    const size_t sm = (size_t)2 * j.n_slots * sizeof(int);
+    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(reduce_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    reduce_all_kernel<<<ex.n_keys + 1, 256, sm, E->stream>>>(d_job.as<ReduceJob>(), 1, ex.n_keys, j.n_slots,
+                                                             E->cost_loc() + 4, nullptr);
+    CU(cudaStreamSynchronize(E->stream));  // `j` is a local
+    E->launches++;
+    return CLIC_OK;
+  };
   auto mark = [&](const StreamExec& ex, int r_col) -> int {
-    key_presence_kernel<<<(ex.n_keys + 63) / 64, 64, 0, E->stream>>>(ex.part.as<double>(), ex.overflow.as<double>(),
-                                                                    ex.n_keys, ex.P, ex.rd, ex.NT, r_col,
+    key_presence_kernel<<<(ex.n_keys + 63) / 64, 64, 0, E->stream>>>(ex.fin.as<double>(), ex.n_keys, ex.rd, ex.NT, r_col,
                                                                     d_present.as<int>());
     E->launches++;
     CU(cudaMemcpyAsync(present.data(), d_present.p, ex.n_keys * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
@@ -962,22 +960,18 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   for (auto& b : E->loam) {
     if (!b->marg) continue;
     StreamExec& ex = b->ex;
-    CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
     if (b->st.geo_kind == 1) loam_kernel<true, kLoamWarps, kLoamMinB, 1><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
     else if (b->st.geo_kind == 2) loam_kernel<true, kLoamWarps, kLoamMinB, 2><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
     else loam_kernel<true, kLoamWarps, kLoamMinB, 0><<<ex.grid, kLoamWarps * 32, loam_smem_bytes(K), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
-    if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
-    E->launches += 2;
-    if ((rc = mark(ex, -1))) return rc;
+    E->launches += 1;
+    if ((rc = reduce_stream(ex)) || (rc = mark(ex, -1))) return rc;
   }
   for (auto& b : E->imu) {
     if (!b->marg) continue;
     StreamExec& ex = b->ex;
-    CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), E->stream));
     imu_kernel<true, true><<<ex.grid, kThreads, factor_smem_bytes(K, 5), E->stream>>>(b->st, pp, ex.slabs_per_warp, ex.rb());
-    if (launch_reduce(E, ex, E->cost_loc() + 4, true, nullptr)) return fail(CLIC_ERR_CUDA, "reduce launch");
-    E->launches += 2;
-    if ((rc = mark(ex, imu_phys_col<true>(34)))) return rc;
+    E->launches += 1;
+    if ((rc = reduce_stream(ex)) || (rc = mark(ex, imu_phys_col<true>(34)))) return rc;
     bool used = false;
     for (int s = 0; s < ex.n_keys; s++) used = used || present[s];
     if (used) {
@@ -1052,8 +1046,8 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   for (auto& b : E->loam) {
     if (!b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
-    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.part = b->ex.fin.as<double>(); d.overflow = nullptr;
+    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = -1; d.b_off = 384; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
     descs.push_back(d);
@@ -1061,8 +1055,8 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   for (auto& b : E->imu) {
     if (!b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.part.as<double>(); d.overflow = b->ex.overflow.as<double>();
-    d.n_keys = b->ex.n_keys; d.P = b->ex.P; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.part = b->ex.fin.as<double>(); d.overflow = nullptr;
+    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 34; d.b_off = -1; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)(l < 40 ? imu_phys_col<true>(l) : l);
     const int cg = find(CLIC_BLOCK_BIAS_GYRO, b->st.bias_slot), ca = find(CLIC_BLOCK_BIAS_ACCEL, b->st.bias_slot),

@@ -396,13 +396,6 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   pass_epilogue(pp);
 }
 
-// Level-1 reduction: CTA (key, part) sums the payloads whose key matches over its share of the record slots.
-// Warp 0 first builds the ordered list of matching slots; then every thread owns RD/256 payload elements and walks
-// the list in order, issuing the loads of four records before their adds (memory-level parallelism without
-// changing the summation order => deterministic).  out[(key * P + part) * RD + e].
-constexpr int kMaxChunk = 1024;
-// The extra CTA (blockIdx.x == gridDim.x - 1, part 0) sums the per-warp costs in a fixed tree and adds (or, for the
-// first stream of a pass, stores) them into cost2 — one launch less per stream than a separate cost kernel.
 // Fixed-tree sum of the per-warp (cost, fixed_cost) pairs by one 256-thread CTA; valid in thread 0.
 __device__ __forceinline__ void cta_cost_sum(const double* warp_cost, int n_warps, double* c_out, double* f_out) {
   __shared__ double sh[2][256];
@@ -424,92 +417,6 @@ __device__ __forceinline__ void cta_cost_sum(const double* warp_cost, int n_warp
   }
   *c_out = sh[0][0];
   *f_out = sh[1][0];
-}
-
-// CTA (key k, part): ordered sum of the record payloads with key k among slots [r0, r1) -> out[e], e < RD.
-template <int RD>
-__device__ __forceinline__ void reduce_part_body(const double* payload, const int* key, int r0, int r1, int k,
-                                                 double* out) {
-  constexpr int EPT = (RD + 255) / 256;
-  constexpr int NB = RD <= 640 ? 8 : 4;  // records in flight per thread
-  __shared__ int list[kMaxChunk];
-  __shared__ unsigned hitmask[kMaxChunk / 32];
-  __shared__ int n_match;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // every warp tests 32 slots per step (the key loads of the whole chunk are in flight together) ...
-  const int n_words = min(kMaxChunk / 32, (r1 - r0 + 31) / 32);
-  for (int w = warp; w < n_words; w += 8) {
-    const int r = r0 + 32 * w + lane;
-    const unsigned m = __ballot_sync(0xffffffffu, r < r1 && key[r] == k);
-    if (lane == 0) hitmask[w] = m;
-  }
-  __syncthreads();
-  // ... and warp 0 compacts the hits into the ordered slot list (exclusive scan over the <= 32 mask words)
-  if (warp == 0) {
-    const unsigned m = lane < n_words ? hitmask[lane] : 0u;
-    int cnt = __popc(m), base = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, base, o);
-      if (lane >= o) base += v;
-    }
-    if (lane == 31) n_match = base;
-    base -= cnt;
-    unsigned mm = m;
-    while (mm) {
-      const int bit = __ffs(mm) - 1;
-      mm &= mm - 1;
-      list[base++] = r0 + 32 * lane + bit;
-    }
-  }
-  __syncthreads();
-  const int n = n_match;
-  double acc[EPT];
-#pragma unroll
-  for (int i = 0; i < EPT; i++) acc[i] = 0.0;
-  for (int j = 0; j < n; j += NB) {
-    double v[NB][EPT];
-#pragma unroll
-    for (int q = 0; q < NB; q++) {
-      const bool on = j + q < n;
-      const double* src = payload + (size_t)(on ? list[j + q] : 0) * RD;
-#pragma unroll
-      for (int i = 0; i < EPT; i++) {
-        const int e = threadIdx.x + i * 256;
-        v[q][i] = (on && e < RD) ? src[e] : 0.0;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < NB; q++)
-#pragma unroll
-      for (int i = 0; i < EPT; i++) acc[i] += v[q][i];
-  }
-#pragma unroll
-  for (int i = 0; i < EPT; i++) {
-    const int e = threadIdx.x + i * 256;
-    if (e < RD) out[e] = acc[i];
-  }
-}
-
-template <int RD>
-__global__ void __launch_bounds__(256)
-reduce_records_kernel(const double* payload, const int* key, int n_slots, int P, double* out, const double* warp_cost,
-                      int n_warps, double* cost2, int first_stream, const int* ctl) {
-  if (ctl && ctl[0]) return;
-  if (blockIdx.x == gridDim.x - 1) {
-    if (blockIdx.y != 0) return;
-    double c, f;
-    cta_cost_sum(warp_cost, n_warps, &c, &f);
-    if (threadIdx.x == 0) {
-      cost2[0] = (first_stream ? 0.0 : cost2[0]) + c;
-      cost2[1] = (first_stream ? 0.0 : cost2[1]) + f;
-    }
-    return;
-  }
-  const int k = blockIdx.x, part = blockIdx.y;
-  const int chunk = (n_slots + P - 1) / P;
-  const int r0 = part * chunk, r1 = min(n_slots, r0 + chunk);
-  reduce_part_body<RD>(payload, key, r0, r1, k, out + ((size_t)k * P + part) * RD);
 }
 
 // All factor streams of a pass in ONE launch: CTA (job, key) fetches every slot key of the stream with all loads
@@ -621,36 +528,6 @@ reduce_all_kernel(const ReduceJob* jobs, int n_jobs, int n_key_ctas, int max_slo
     case 640: reduce_key_body<640>(J, k, skey, list); break;
     case 960: reduce_key_body<960>(J, k, skey, list); break;
     default: reduce_key_body<1792>(J, k, skey, list); break;
-  }
-}
-
-// Sum of per-warp costs in warp order (single CTA, deterministic tree over fixed positions).
-__global__ void reduce_cost_kernel(const double* warp_cost, int n_warps, double* out2, int accumulate, const int* ctl) {
-  if (ctl && ctl[0]) return;
-  __shared__ double sh[2][256];
-  double c = 0, f = 0;
-  for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
-    c += warp_cost[2 * i];
-    f += warp_cost[2 * i + 1];
-  }
-  sh[0][threadIdx.x] = c;
-  sh[1][threadIdx.x] = f;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (accumulate) {
-      out2[0] += sh[0][0];
-      out2[1] += sh[1][0];
-    } else {
-      out2[0] = sh[0][0];
-      out2[1] = sh[1][0];
-    }
   }
 }
 

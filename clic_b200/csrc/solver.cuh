@@ -935,17 +935,14 @@ __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m,
 }
 
 // which interval keys received contributions: present[s] = (block diagonal of key s is non-zero)
-__global__ void key_presence_kernel(const double* part, const double* overflow, int n_keys, int P, int rd, int NT,
-                                    int r_col, int* present) {
+__global__ void key_presence_kernel(const double* fin, int n_keys, int rd, int NT, int r_col, int* present) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_keys) return;
+  // the diagonal of the knot columns and the r~ column are enough: a contributing factor has r != 0 or J != 0
+  const double* blk = fin + (size_t)s * rd;
   bool any = false;
-  // the (0,0) .. diagonal entries of tile (0,0) and the r~ column are enough: a contributing factor has r != 0 or J != 0
-  for (int p = 0; p <= P && !any; p++) {
-    const double* blk = p < P ? part + ((size_t)s * P + p) * rd : overflow + (size_t)s * rd;
-    for (int l = 0; l < 24 && !any; l++) any = block_entry(blk, NT, l, l) != 0.0;
-    if (r_col >= 0) any = any || block_entry(blk, NT, r_col, r_col) != 0.0;  // physical column of r~
-  }
+  for (int l = 0; l < 24 && !any; l++) any = block_entry(blk, NT, l, l) != 0.0;
+  if (r_col >= 0) any = any || block_entry(blk, NT, r_col, r_col) != 0.0;  // physical column of r~
   present[s] = any ? 1 : 0;
 }
 
