@@ -449,9 +449,8 @@ int ensure_layout(clic_estimator* E) {
   for (auto& b : E->loam) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
-    d.overflow = nullptr;
-    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
     add_job(b->ex);
     d.r_col = -1;
     d.b_off = 384;
@@ -465,9 +464,8 @@ int ensure_layout(clic_estimator* E) {
   for (auto& b : E->imu) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
-    d.overflow = nullptr;
-    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
     add_job(b->ex);
     d.r_col = 31;
     d.b_off = -1;
@@ -486,9 +484,8 @@ int ensure_layout(clic_estimator* E) {
   for (auto& b : E->image) {
     if (b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.fin.as<double>();  // per-key final blocks of reduce_all_kernel (overflow already folded in)
-    d.overflow = nullptr;
-    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
     add_job(b->ex);
     d.r_col = 49;
     d.b_off = -1;
@@ -1046,8 +1043,8 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   for (auto& b : E->loam) {
     if (!b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.fin.as<double>(); d.overflow = nullptr;
-    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = -1; d.b_off = 384; d.n_extra = 0; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
     descs.push_back(d);
@@ -1055,8 +1052,8 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   for (auto& b : E->imu) {
     if (!b->marg) continue;
     StreamDesc d{};
-    d.part = b->ex.fin.as<double>(); d.overflow = nullptr;
-    d.n_keys = b->ex.n_keys; d.P = 1; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
     d.r_col = 34; d.b_off = -1; d.n_extra = 10; d.extra_base = 24; d.kind = 0; d.kdim = K - 3;
     for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)(l < 40 ? imu_phys_col<true>(l) : l);
     const int cg = find(CLIC_BLOCK_BIAS_GYRO, b->st.bias_slot), ca = find(CLIC_BLOCK_BIAS_ACCEL, b->st.bias_slot),

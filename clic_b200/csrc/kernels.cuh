@@ -977,9 +977,8 @@ __global__ void prep_image_kernel(int64_t n, const double* ti_s, const double* t
 // ---------------- assembly of the dense normal equations ----------------
 // One descriptor per factor stream whose records were reduced to per-key blocks.
 struct StreamDesc {
-  const double* part;    // [n_keys][P][rd]
-  const double* overflow;  // [n_keys][rd] atomics fallback accumulators (all zero for time-sorted input)
-  int n_keys, P, NT, rd;
+  const double* fin;     // [n_keys][rd] per-key blocks of reduce_all_kernel (atomics-fallback block folded in)
+  int n_keys, NT, rd;
   int r_col;             // local column holding r~ (when b lives in the tiles)
   int b_off;             // >= 0: b = J~^T r~ is stored as a plain vector at this offset of the record (LiDAR)
   int n_extra;           // local columns extra_base .. extra_base+n_extra-1 map to extra_global[] (-1: constant)
@@ -1010,7 +1009,7 @@ struct BiasFactorDesc {
   int col_gi, col_gj, col_ai, col_aj;  // columns (-1 constant)
 };
 // H[gi][gj] (upper, mirrored) and b[gi]: owner-computes gather over the per-key blocks.  One WARP per entry: the
-// lanes stride the (block, partial) contribution list in a fixed assignment and are combined by a fixed butterfly,
+// lanes stride the block list in a fixed assignment and are combined by a fixed butterfly,
 // so the sum order never changes between runs.
 // bias (n_bias > 0, solve path): the BiasFactor terms (+-I Jacobians) are added by the owner of each entry, and the
 // first warp adds their cost — one launch less per pass than bias_factor_kernel.
@@ -1048,25 +1047,24 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
     }
     if (ki < 0 && ei < 0) continue;
     if (!is_b && kj < 0 && ej < 0) continue;
-    const int PP = sd.P + (sd.overflow ? 1 : 0);  // partials (+ the overflow block when it was not folded in)
     if (sd.kind == 0) {
       int s_lo = 0, s_hi = sd.n_keys - 1;
       if (ki >= 0) { s_lo = max(s_lo, ki - 3); s_hi = min(s_hi, ki); }
       if (!is_b && kj >= 0) { s_lo = max(s_lo, kj - 3); s_hi = min(s_hi, kj); }
-      const int n_items = max(0, s_hi - s_lo + 1) * PP;
+      const int n_items = max(0, s_hi - s_lo + 1);
       for (int it = lane; it < n_items; it += 32) {
-        const int s = s_lo + it / PP, p = it % PP;
+        const int s = s_lo + it;
         const int la = ki >= 0 ? 6 * (ki - s) + ci : ei;
         const int lb = is_b ? sd.r_col : (kj >= 0 ? 6 * (kj - s) + cj : ej);
-        const double* blk = p < sd.P ? sd.part + ((size_t)s * sd.P + p) * sd.rd : sd.overflow + (size_t)s * sd.rd;
+        const double* blk = sd.fin + (size_t)s * sd.rd;
         acc += (is_b && sd.b_off >= 0) ? blk[sd.b_off + la] : block_entry(blk, sd.NT, sd.perm[la], sd.perm[lb]);
       }
     } else {
       // two knot windows: a global knot column may appear in window i, window j or both (overlap): J_g = sum of locals
       const int nk = sd.kdim;
-      const int n_items = nk * nk * PP;
+      const int n_items = nk * nk;
       for (int it = lane; it < n_items; it += 32) {
-        const int key = it / PP, p = it % PP;
+        const int key = it;
         const int si = key / nk, sj = key % nk;
         int la[2], lb[2], na = 0, nb = 0;
         if (ki >= 0) {
@@ -1084,7 +1082,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
           lb[nb++] = ej;
         }
         if (na == 0 || nb == 0) continue;
-        const double* blk = p < sd.P ? sd.part + ((size_t)key * sd.P + p) * sd.rd : sd.overflow + (size_t)key * sd.rd;
+        const double* blk = sd.fin + (size_t)key * sd.rd;
         for (int x = 0; x < na; x++)
           for (int y = 0; y < nb; y++) acc += block_entry(blk, sd.NT, sd.perm[la[x]], sd.perm[lb[y]]);
       }
