@@ -504,7 +504,7 @@ int ensure_layout(clic_estimator* E) {
   E->n_jobs = (int)jobs.size();
   E->max_slots = 1;
   for (auto& j : jobs) E->max_slots = std::max(E->max_slots, j.n_slots);
-  if ((size_t)2 * E->max_slots * sizeof(int) > 48 * 1024)
+  if ((size_t)2 * E->max_slots * sizeof(int) > 32 * 1024)  // static shared memory comes on top of it
     CU(cudaFuncSetAttribute(reduce_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * E->max_slots * sizeof(int))));
   E->n_part_ctas = n_part_ctas;
   CU(E->d_jobs.ensure(std::max<size_t>(1, jobs.size()) * sizeof(ReduceJob)));
@@ -933,7 +933,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     j.cta0 = 0;
     CU(cudaMemcpyAsync(d_job.p, &j, sizeof(j), cudaMemcpyHostToDevice, E->stream));
     const size_t sm = (size_t)2 * j.n_slots * sizeof(int);
-    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(reduce_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    if (sm > 32 * 1024) CU(cudaFuncSetAttribute(reduce_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     reduce_all_kernel<<<ex.n_keys + 1, 256, sm, E->stream>>>(d_job.as<ReduceJob>(), 1, ex.n_keys, j.n_slots,
                                                              E->cost_loc() + 4, nullptr);
     CU(cudaStreamSynchronize(E->stream));  // `j` is a local
