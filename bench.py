@@ -87,7 +87,8 @@ def algorithmic_bytes(sw):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML in-process when the
+    binding is there (a sample every 2 ms: the timed region of the default run is ~15 ms long), else nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -95,14 +96,47 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # LOCAL_RANK indexes the visible devices; NVML enumerates all of them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            N = self.nvml
+            bits = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            while not self._halt.is_set():
+                try:
+                    sm = float(N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM))
+                    try:
+                        mask = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.rows.append((sm, self.max_sm, [n for n, b in bits.items() if mask & b]))
+                except Exception:
+                    pass
+                self._halt.wait(0.002)
+            return
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    r = [x.strip() for x in out.split(",")]
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    self.rows.append((float(r[0]), float(r[1]),
+                                      [n for n, v in zip(names, r[4:8]) if v.lower().startswith("active")]))
             except Exception:
                 pass
             self._halt.wait(0.05)
@@ -110,12 +144,11 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def pinned(a):
