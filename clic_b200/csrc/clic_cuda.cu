@@ -831,11 +831,11 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   const int* ctl_res = &B.st->skip_res;
   const int* ctl_jac = &B.st->skip_jac;
   const size_t sm_small = 1024 * sizeof(double);
-  size_t sm_step = (size_t)(512 + 2 * D + ((D + 7) / 8) * 64) * sizeof(double);
+  size_t sm_step = (size_t)(512 + 3 * D + ((D + 7) / 8) * 64) * sizeof(double);
   int a_in_smem = 0;
-  if (sm_step + (size_t)D * D * sizeof(double) <= 200 * 1024) {
+  if (sm_step + (size_t)D * (D | 1) * sizeof(double) <= 200 * 1024) {
     a_in_smem = 1;
-    sm_step += (size_t)D * D * sizeof(double);
+    sm_step += (size_t)D * (D | 1) * sizeof(double);
   }
   CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_step));
   int rc;
@@ -1073,7 +1073,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   CU(d_r0.ensure((size_t)n * sizeof(double)));
   CU(d_status.ensure(4 * sizeof(int)));
   CU(d_perm.ensure((size_t)pos * sizeof(int)));
-  CU(d_dscr.ensure((size_t)2 * pos * sizeof(double)));
+  CU(d_dscr.ensure((size_t)3 * pos * sizeof(double)));
   CU(d_cost.ensure(2 * sizeof(double)));
   CU(cudaMemsetAsync(d_cost.p, 0, 2 * sizeof(double), E->stream));
   ColMaps cm;

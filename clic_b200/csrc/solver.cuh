@@ -107,7 +107,7 @@ constexpr int kNB = 8;
 // Warp 0, lane l < nb holds row l of the kNB x kNB diagonal block in registers; columns are eliminated with warp
 // shuffles (no shared-memory round trips on the serial critical path).  Writes L back and, if Li != nullptr, the
 // inverse of the block (row-major kNB x kNB, zero padded) used by the panel and triangular solves.
-__device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* Li, int* ok, int lane,
+__device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* dinv, int* ok, int lane,
                                                 const double* dtol = nullptr) {
   const unsigned full = 0xffffffffu;
   double a[kNB];
@@ -124,8 +124,13 @@ __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int n
     } else {
       d = 1.0;
     }
-    const double piv = sqrt(d), inv = 1.0 / piv;
+    // 1/sqrt(d) refined by one Newton step to full precision, pivot = d * (1/sqrt(d)): ~1/4 of the dependent
+    // latency of sqrt() followed by a division, on the serial critical path of the factorization
+    double inv = rsqrt(d);
+    inv = inv * (1.5 - 0.5 * d * inv * inv);
+    const double piv = d * inv;
     if (lane == j) a[j] = piv; else if (lane > j) a[j] = a[j] * inv;
+    if (lane == 0 && j < nb) dinv[kb + j] = inv;
     const double lij = a[j];
 #pragma unroll
     for (int c = j + 1; c < kNB; c++) {
@@ -136,62 +141,50 @@ __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int n
 #pragma unroll
   for (int c = 0; c < kNB; c++)
     if (lane < nb && c <= lane) A[(size_t)(kb + lane) * ld + kb + c] = a[c];
-  if (Li) {
-    // lane l computes column l of L^-1 by forward substitution on e_l
-    double x[kNB];
-#pragma unroll
-    for (int i = 0; i < kNB; i++) {
-      const double lii = __shfl_sync(full, a[i], i);
-      double acc = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < i; k++) {
-        const double lik = __shfl_sync(full, a[k], i);
-        if (k >= lane) acc -= lik * x[k];
-      }
-      x[i] = (i >= lane && i < nb) ? acc / lii : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < kNB; i++)
-      if (lane < kNB) Li[i * kNB + lane] = (lane < nb) ? x[i] : 0.0;
-  }
 }
 
-// Linv: nullptr (panel by substitution) or ceil(n/kNB) * 64 doubles receiving the inverses of the diagonal blocks.
+// Inverse of the kNB x kNB diagonal block kb of L (row-major kNB x kNB, zero padded), by one warp.
+__device__ __forceinline__ void warp_block_inverse(const double* A, int ld, int kb, int nb, const double* dinv, double* Li,
+                                                   int lane) {
+  // lane l computes column l of L^-1 by forward substitution on e_l
+  double x[kNB];
+#pragma unroll
+  for (int i = 0; i < kNB; i++) {
+    double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; k++)
+      if (k >= lane && i < nb) acc -= A[(size_t)(kb + i) * ld + kb + k] * x[k];
+    x[i] = (i >= lane && i < nb && lane < nb) ? acc * dinv[kb + i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < kNB; i++)
+    if (lane < kNB) Li[i * kNB + lane] = x[i];
+}
+
+// dinv: n doubles receiving 1 / L[j][j].  Linv: nullptr or ceil(n/kNB) * 64 doubles receiving the inverses of the
+// diagonal blocks (computed after the factorization, one warp per block, off the serial path).
 // dtol[j]: pivot j <= dtol[j] counts as "not positive definite" (nullptr = 0 for the damped LM system; in K8
 // n * eps * the column's original diagonal, i.e. the column is numerically dependent on the previous ones).
-__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* Linv = nullptr,
+__device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* dinv, double* Linv = nullptr,
                                              const double* dtol = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, n_warps = nt >> 5;
   for (int kb = 0; kb < n; kb += kNB) {
     const int nb = min(kNB, n - kb);
-    double* Li = Linv ? Linv + (size_t)(kb / kNB) * kNB * kNB : nullptr;
-    if (tid < 32) warp_diag_block(A, ld, kb, nb, Li, ok, tid, dtol);
+    if (tid < 32) warp_diag_block(A, ld, kb, nb, dinv, ok, tid, dtol);
     __syncthreads();
     if (!*ok) return;
+    // panel: L[i, panel] = A[i, panel] * Lkk^-T by forward substitution along the row (multiplies by 1 / Lcc)
     for (int i = kb + nb + tid; i < n; i += nt) {
       double x[kNB];
-      if (Li) {  // L[i, panel] = A[i, panel] * Lkk^-T : x[c] = sum_{k <= c} A[i][kb+k] * Linv[c][k]
-        double ai[kNB];
 #pragma unroll
-        for (int k = 0; k < kNB; k++) ai[k] = k < nb ? A[(size_t)i * ld + kb + k] : 0.0;
-#pragma unroll
-        for (int c = 0; c < kNB; c++) {
-          double v = 0.0;
+      for (int c = 0; c < kNB; c++) {
+        if (c < nb) {
+          double v = A[(size_t)i * ld + kb + c];
 #pragma unroll
           for (int k = 0; k < kNB; k++)
-            if (k <= c) v += ai[k] * Li[c * kNB + k];
-          x[c] = v;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < kNB; c++) {
-          if (c < nb) {
-            double v = A[(size_t)i * ld + kb + c];
-#pragma unroll
-            for (int k = 0; k < kNB; k++)
-              if (k < c) v -= x[k] * A[(size_t)(kb + c) * ld + kb + k];
-            x[c] = v / A[(size_t)(kb + c) * ld + kb + c];
-          }
+            if (k < c) v -= x[k] * A[(size_t)(kb + c) * ld + kb + k];
+          x[c] = v * dinv[kb + c];
         }
       }
 #pragma unroll
@@ -199,17 +192,62 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
         if (c < nb) A[(size_t)i * ld + kb + c] = x[c];
     }
     __syncthreads();
-    const int m = n - kb - nb;
-    for (int e = tid; e < m * m; e += nt) {
-      const int i = kb + nb + e / m, j = kb + nb + e % m;
-      if (j <= i) {
+    // trailing lower triangle: warps stride the rows, lanes the columns (no integer division)
+    const int r0 = kb + nb;
+    for (int i = r0 + warp; i < n; i += n_warps) {
+      double li[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; c++) li[c] = c < nb ? A[(size_t)i * ld + kb + c] : 0.0;
+      for (int j = r0 + lane; j <= i; j += 32) {
         double acc = 0.0;
-        for (int c = 0; c < nb; c++) acc += A[(size_t)i * ld + kb + c] * A[(size_t)j * ld + kb + c];
+#pragma unroll
+        for (int c = 0; c < kNB; c++)
+          if (c < nb) acc += li[c] * A[(size_t)j * ld + kb + c];
         A[(size_t)i * ld + j] -= acc;
       }
     }
     __syncthreads();
   }
+  if (Linv) {
+    for (int blk = warp; blk * kNB < n; blk += n_warps)
+      warp_block_inverse(A, ld, blk * kNB, min(kNB, n - blk * kNB), dinv, Linv + (size_t)blk * kNB * kNB, lane);
+    __syncthreads();
+  }
+}
+
+// Both triangular solves by ONE warp (n <= 96: three unknowns per lane), no block barriers: y <- L^-1 y, y <- L^-T y.
+// Lane l owns y[l], y[l + 32], y[l + 64].  With an odd leading dimension the column reads of the forward sweep are
+// conflict-free.
+__device__ __forceinline__ void warp_cholesky_solve(const double* A, int ld, int n, double* y, const double* dinv, int lane) {
+  const unsigned full = 0xffffffffu;
+  double v[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) v[q] = lane + 32 * q < n ? y[lane + 32 * q] : 0.0;
+  for (int i = 0; i < n; i++) {  // forward: y_i /= L_ii; y_r -= L_ri y_i for r > i
+    const int q = i >> 5;
+    double yi = (q == 0 ? v[0] : q == 1 ? v[1] : v[2]);
+    yi = __shfl_sync(full, yi, i & 31) * dinv[i];
+    if (lane == (i & 31)) { if (q == 0) v[0] = yi; else if (q == 1) v[1] = yi; else v[2] = yi; }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const int r = lane + 32 * p;
+      if (r > i && r < n) v[p] -= A[(size_t)r * ld + i] * yi;
+    }
+  }
+  for (int i = n - 1; i >= 0; i--) {  // backward: y_i /= L_ii; y_r -= L_ir y_i for r < i
+    const int q = i >> 5;
+    double yi = (q == 0 ? v[0] : q == 1 ? v[1] : v[2]);
+    yi = __shfl_sync(full, yi, i & 31) * dinv[i];
+    if (lane == (i & 31)) { if (q == 0) v[0] = yi; else if (q == 1) v[1] = yi; else v[2] = yi; }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const int r = lane + 32 * p;
+      if (r < i) v[p] -= A[(size_t)i * ld + r] * yi;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+    if (lane + 32 * q < n) y[lane + 32 * q] = v[q];
 }
 
 // y <- L^-1 y then y <- L^-T y (L from cta_cholesky with Linv), blocked by kNB: the diagonal step is an 8-lane
@@ -327,28 +365,26 @@ __device__ __forceinline__ void plus_state(const double* x, const double* delta,
   __syncthreads();
 }
 
-// block-wide sums / max (blockDim.x <= 1024), fixed tree => deterministic
+// Block-wide sum / max in a fixed order: butterfly inside every warp, then the warp results in warp order.
 __device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
-  sh[threadIdx.x] = v;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  double r = sh[0];
+  double r = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
   __syncthreads();
   return r;
 }
 __device__ __forceinline__ double block_max(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   __syncthreads();
-  sh[threadIdx.x] = v;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
-    __syncthreads();
-  }
   double r = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, sh[w]);
   __syncthreads();
   return r;
 }
@@ -506,8 +542,11 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   double* red = sh;               // 512 doubles of reduction scratch
   double* gs = sh + 512;          // D scaled gradient
   double* y = gs + D;             // D
-  double* Linv = y + D;                 // ceil(D / 8) * 64 doubles: inverses of the diagonal blocks
+  double* dinv = y + D;           // D: 1 / L_jj
+  double* Linv = dinv + D;        // ceil(D / 8) * 64 doubles: inverses of the diagonal blocks (block solves, D > 96)
   double* A = a_in_smem ? (Linv + ((D + kNB - 1) / kNB) * kNB * kNB) : B.A;
+  const int ld = a_in_smem ? (D | 1) : D;  // odd leading dimension in shared memory: conflict-free column reads
+  const bool warp_solve = D <= 96;
   const double radius = s->radius;
   const int reuse = s->reuse_diagonal;
   // LevenbergMarquardtStrategy::ComputeStep: diagonal = clamp(diag(J~^T J~)), A = H~ + diag(diagonal / radius)
@@ -520,28 +559,35 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     }
   }
   __syncthreads();
-  for (int e = tid; e < D * D; e += nt) {
-    const int i = e / D, j = e % D;
-    double v = B.H[e] * B.scale[i] * B.scale[j];
-    if (i == j) {
-      double lm = sqrt(B.diagonal[i] / radius);
-      v += lm * lm;
+  for (int i = tid >> 5; i < D; i += nt >> 5) {  // warps stride the rows, lanes the columns
+    const double si = B.scale[i];
+    for (int j = tid & 31; j < D; j += 32) {
+      double v = B.H[(size_t)i * D + j] * si * B.scale[j];
+      if (i == j) {
+        double lm = sqrt(B.diagonal[i] / radius);
+        v += lm * lm;
+      }
+      A[(size_t)i * ld + j] = v;
     }
-    A[e] = v;
   }
   __syncthreads();
   // dense Cholesky A = L L^T (lower, in place), blocked right-looking (cta_cholesky)
   __shared__ int ok;
   if (tid == 0) ok = 1;
   __syncthreads();
-  cta_cholesky(A, D, D, &ok, Linv);
+  cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv);
   __syncthreads();
   int valid = ok;
   // forward / backward substitution: (L L^T) z = g~, step = -z
   if (valid) {
     for (int i = tid; i < D; i += nt) y[i] = gs[i];
     __syncthreads();
-    cta_cholesky_solve(A, D, D, y, Linv);
+    if (warp_solve) {
+      if (tid < 32) warp_cholesky_solve(A, ld, D, y, dinv, tid);
+      __syncthreads();
+    } else {
+      cta_cholesky_solve(A, ld, D, y, Linv);
+    }
     double bad = 0.0;
     for (int i = tid; i < D; i += nt) {
       double v = -y[i];
@@ -555,11 +601,13 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   if (valid) {
     // model_cost_change = -(g~^T s + 1/2 s^T H~ s)
     double part = 0.0;
-    for (int i = tid; i < D; i += nt) {
+    for (int i = tid >> 5; i < D; i += nt >> 5) {  // one warp per row of H~ (coalesced), butterfly over the lanes
       double row = 0.0;
       const double si = B.scale[i];
-      for (int j = 0; j < D; j++) row += (B.H[(size_t)i * D + j] * si * B.scale[j]) * B.step[j];
-      part += gs[i] * B.step[i] + 0.5 * B.step[i] * row;
+      for (int j = tid & 31; j < D; j += 32) row += (B.H[(size_t)i * D + j] * si * B.scale[j]) * B.step[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) row += __shfl_xor_sync(0xffffffffu, row, o);
+      if ((tid & 31) == 0) part += gs[i] * B.step[i] + 0.5 * B.step[i] * row;
     }
     mcc = -block_sum(part, red);
     if (!(mcc > 0.0)) valid = 0;
@@ -806,7 +854,7 @@ __device__ __forceinline__ void cta_pivoted_cholesky(double* A, int ld, int n, i
 // — a column numerically dependent on the previous ones — the block is restored, Jacobi-scaled (S A S, unit diagonal:
 // the test is then independent of the units of the parameters, e.g. time offsets in ns next to metres) and factored
 // with pivoting, and L is unscaled in place.  Returns the rank (every thread); perm = identity on the plain path.
-// d0: n doubles of scratch (original diagonal), dtol: n doubles of scratch.
+// d0: n doubles of scratch (original diagonal), dtol: 2 n doubles of scratch (tolerances, inverse diagonal).
 __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* perm, double* d0, double* dtol, int* ok,
                                                 int* rank_sh) {
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -817,7 +865,7 @@ __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* p
   }
   if (tid == 0) *ok = 1;
   __syncthreads();
-  cta_cholesky(A, ld, n, ok, nullptr, dtol);
+  cta_cholesky(A, ld, n, ok, dtol + n, nullptr, dtol);  // dinv scratch right behind dtol
   __syncthreads();
   if (*ok) return n;
   // restore (the failed attempt touched the lower triangle and the diagonal only) and scale
