@@ -836,6 +836,8 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   if (sm_step + (size_t)D * (D | 1) * sizeof(double) <= 200 * 1024) {
     a_in_smem = 1;
     sm_step += (size_t)D * (D | 1) * sizeof(double);
+  } else {
+    sm_step += (size_t)(D + kNB) * kPanStride * sizeof(double);  // staged panel (A stays in L2-resident global memory)
   }
   CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_step));
   int rc;

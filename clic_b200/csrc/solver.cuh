@@ -165,8 +165,11 @@ __device__ __forceinline__ void warp_block_inverse(const double* A, int ld, int 
 // diagonal blocks (computed after the factorization, one warp per block, off the serial path).
 // dtol[j]: pivot j <= dtol[j] counts as "not positive definite" (nullptr = 0 for the damped LM system; in K8
 // n * eps * the column's original diagonal, i.e. the column is numerically dependent on the previous ones).
+// pan: nullptr, or (n + kNB) * kPanStride doubles of SHARED scratch used when A itself lives in global memory: the
+// factored diagonal block and the panel are staged there, so the trailing update reads global memory once per entry.
+constexpr int kPanStride = kNB + 1;  // odd: conflict-free when lanes stride the rows
 __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* dinv, double* Linv = nullptr,
-                                             const double* dtol = nullptr) {
+                                             const double* dtol = nullptr, double* pan = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, n_warps = nt >> 5;
   for (int kb = 0; kb < n; kb += kNB) {
@@ -174,8 +177,18 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
     if (tid < 32) warp_diag_block(A, ld, kb, nb, dinv, ok, tid, dtol);
     __syncthreads();
     if (!*ok) return;
+    const int r0 = kb + nb;
+    double* pdiag = pan;                                   // [kNB][kPanStride]: the factored diagonal block
+    double* prow = pan ? pan + kNB * kPanStride : nullptr;  // [n - r0][kPanStride]: the panel rows
+    if (pan) {
+      if (tid < kNB * kNB) {
+        const int c = tid / kNB, k = tid % kNB;
+        pdiag[c * kPanStride + k] = (c < nb && k <= c) ? A[(size_t)(kb + c) * ld + kb + k] : 0.0;
+      }
+      __syncthreads();
+    }
     // panel: L[i, panel] = A[i, panel] * Lkk^-T by forward substitution along the row (multiplies by 1 / Lcc)
-    for (int i = kb + nb + tid; i < n; i += nt) {
+    for (int i = r0 + tid; i < n; i += nt) {
       double x[kNB];
 #pragma unroll
       for (int c = 0; c < kNB; c++) {
@@ -183,26 +196,30 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
           double v = A[(size_t)i * ld + kb + c];
 #pragma unroll
           for (int k = 0; k < kNB; k++)
-            if (k < c) v -= x[k] * A[(size_t)(kb + c) * ld + kb + k];
+            if (k < c) v -= x[k] * (pan ? pdiag[c * kPanStride + k] : A[(size_t)(kb + c) * ld + kb + k]);
           x[c] = v * dinv[kb + c];
+        } else {
+          x[c] = 0.0;
         }
       }
 #pragma unroll
-      for (int c = 0; c < kNB; c++)
+      for (int c = 0; c < kNB; c++) {
         if (c < nb) A[(size_t)i * ld + kb + c] = x[c];
+        if (pan) prow[(size_t)(i - r0) * kPanStride + c] = x[c];
+      }
     }
     __syncthreads();
     // trailing lower triangle: warps stride the rows, lanes the columns (no integer division)
-    const int r0 = kb + nb;
     for (int i = r0 + warp; i < n; i += n_warps) {
       double li[kNB];
 #pragma unroll
-      for (int c = 0; c < kNB; c++) li[c] = c < nb ? A[(size_t)i * ld + kb + c] : 0.0;
+      for (int c = 0; c < kNB; c++)
+        li[c] = c < nb ? (pan ? prow[(size_t)(i - r0) * kPanStride + c] : A[(size_t)i * ld + kb + c]) : 0.0;
       for (int j = r0 + lane; j <= i; j += 32) {
         double acc = 0.0;
 #pragma unroll
         for (int c = 0; c < kNB; c++)
-          if (c < nb) acc += li[c] * A[(size_t)j * ld + kb + c];
+          if (c < nb) acc += li[c] * (pan ? prow[(size_t)(j - r0) * kPanStride + c] : A[(size_t)j * ld + kb + c]);
         A[(size_t)i * ld + j] -= acc;
       }
     }
@@ -544,7 +561,9 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   double* y = gs + D;             // D
   double* dinv = y + D;           // D: 1 / L_jj
   double* Linv = dinv + D;        // ceil(D / 8) * 64 doubles: inverses of the diagonal blocks (block solves, D > 96)
-  double* A = a_in_smem ? (Linv + ((D + kNB - 1) / kNB) * kNB * kNB) : B.A;
+  double* after_linv = Linv + ((D + kNB - 1) / kNB) * kNB * kNB;
+  double* A = a_in_smem ? after_linv : B.A;
+  double* pan = a_in_smem ? nullptr : after_linv;  // (D + kNB) * kPanStride doubles: staged panel of the global path
   const int ld = a_in_smem ? (D | 1) : D;  // odd leading dimension in shared memory: conflict-free column reads
   const bool warp_solve = D <= 96;
   const double radius = s->radius;
@@ -575,7 +594,7 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   __shared__ int ok;
   if (tid == 0) ok = 1;
   __syncthreads();
-  cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv);
+  cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv, nullptr, pan);
   __syncthreads();
   int valid = ok;
   // forward / backward substitution: (L L^T) z = g~, step = -z
@@ -865,7 +884,8 @@ __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* p
   }
   if (tid == 0) *ok = 1;
   __syncthreads();
-  cta_cholesky(A, ld, n, ok, dtol + n, nullptr, dtol);  // dinv scratch right behind dtol
+  __shared__ double s_pan[(320 + kNB) * kPanStride];  // staged panel for blocks up to 320 wide (A is in global memory)
+  cta_cholesky(A, ld, n, ok, dtol + n, nullptr, dtol, n <= 320 ? s_pan : nullptr);  // dinv scratch right behind dtol
   __syncthreads();
   if (*ok) return n;
   // restore (the failed attempt touched the lower triangle and the diagonal only) and scale
