@@ -9,7 +9,7 @@
 //     upper-triangular 8x8 tile products; the accumulators stay in registers across all slabs of the warp;
 //   * a warp flushes its accumulators into a private record slot when the knot interval (the "key") of its
 //     factors changes or at the end: no atomics, fixed order => bitwise run-to-run determinism;
-//   * reduce_records + assemble kernels turn records into the dense H, b (owner-computes, no atomics).
+//   * reduce_all_kernel + assemble_kernel turn records into the dense H, b (owner-computes, no atomics).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
