@@ -907,6 +907,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
 
 // clic_marginalize: preMarginalize + marginalize (marginalization_factor.cpp:94-116, 150-276) on the device.
 int marginalize_impl(clic_estimator* E, clic_prior** out) {
+  ScopedTrace trace("marginalize");
   const int K = E->K;
   const int later_local = E->opt.ctrl_to_be_opt_later - E->knot_id0;
   const bool drop_knots = E->opt.ctrl_to_be_opt_later > E->opt.ctrl_to_be_opt_now;  // trajectory_estimator.cpp:214
@@ -987,6 +988,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
       if (bf.marg_all) bias_drop[bf.slot_j] = bias_drop[E->n_bias + bf.slot_j] = 1;
     }
   }
+  trace.lap("factor kernels + presence");
   // ---- blocks in canonical order, dropped first (marginalization_factor.cpp:154-166) ----
   struct Blk { int kind, id, size, used, drop, idx; };
   std::vector<Blk> blocks;
@@ -1037,7 +1039,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     knot_col[k] = c;
     if (c >= 0) for (int a = 0; a < 6; a++) { col_knot[c + a] = k; col_sub[c + a] = a; }
   }
-  DevBuf d_kc, d_ck, d_cs, d_desc, d_A, d_b, d_J0, d_r0, d_status, d_cost, d_perm, d_dscr;
+  DevBuf d_kc, d_ck, d_cs, d_desc, d_A, d_b, d_J0, d_r0, d_status, d_cost, d_perm, d_dscr, d_aug;
   if ((rc = to_device(E, d_kc, knot_col.data(), K)) || (rc = to_device(E, d_ck, col_knot.data(), pos)) ||
       (rc = to_device(E, d_cs, col_sub.data(), pos)))
     return rc;
@@ -1076,6 +1078,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   CU(d_status.ensure(4 * sizeof(int)));
   CU(d_perm.ensure((size_t)pos * sizeof(int)));
   CU(d_dscr.ensure((size_t)3 * pos * sizeof(double)));
+  CU(d_aug.ensure((size_t)(pos + 1) * (pos + 1) * sizeof(double)));
   CU(d_cost.ensure(2 * sizeof(double)));
   CU(cudaMemsetAsync(d_cost.p, 0, 2 * sizeof(double), E->stream));
   ColMaps cm;
@@ -1114,11 +1117,14 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     E->launches++;
     CU(cudaStreamSynchronize(E->stream));  // h_meta is reused by the solve path
   }
+  if (ScopedTrace::on()) cudaStreamSynchronize(E->stream);
+  trace.lap("assemble + bias + prior");
   int status4[4] = {-1, -1, -1, -1};
   int& status = status4[0];
   CU(cudaMemsetAsync(d_status.p, 0xff, 4 * sizeof(int), E->stream));
   schur_kernel<<<1, 512, 0, E->stream>>>(d_A.as<double>(), d_b.as<double>(), m, n, d_J0.as<double>(), d_r0.as<double>(),
-                                         d_perm.as<int>(), d_dscr.as<double>(), d_status.as<int>());
+                                         d_perm.as<int>(), d_dscr.as<double>(),
+                                         getenv("CLIC_SCHUR_TWO_STAGE") ? nullptr : d_aug.as<double>(), d_status.as<int>());
   E->launches++;
   E->prof_end();
   std::unique_ptr<clic_prior> P(new clic_prior);
@@ -1133,6 +1139,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   CU(cudaMemcpyAsync(h.data(), E->d_state.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
+  trace.lap("schur + read back");
   if (ScopedTrace::on())
     fprintf(stderr, "[clic trace] schur: m %d n %d status %d rank deficiency A_mm %d, Schur complement %d\n", m, n, status4[0],
             status4[1], status4[2]);

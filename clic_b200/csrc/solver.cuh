@@ -168,8 +168,11 @@ __device__ __forceinline__ void warp_block_inverse(const double* A, int ld, int 
 // pan: nullptr, or (n + kNB) * kPanStride doubles of SHARED scratch used when A itself lives in global memory: the
 // factored diagonal block and the panel are staged there, so the trailing update reads global memory once per entry.
 constexpr int kPanStride = kNB + 1;  // odd: conflict-free when lanes stride the rows
+// n_rows >= n (0 = n): rows n .. n_rows-1 are carried along as extra panel rows (L[i][0..n) = A[i][0..n) L^-T) and
+// their trailing entries A[i][j], j < n, are updated — a right-hand side appended as row n becomes L^-1 rhs.
 __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, double* dinv, double* Linv = nullptr,
-                                             const double* dtol = nullptr, double* pan = nullptr) {
+                                             const double* dtol = nullptr, double* pan = nullptr, int n_rows = 0) {
+  if (n_rows < n) n_rows = n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, n_warps = nt >> 5;
   for (int kb = 0; kb < n; kb += kNB) {
@@ -188,7 +191,7 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
       __syncthreads();
     }
     // panel: L[i, panel] = A[i, panel] * Lkk^-T by forward substitution along the row (multiplies by 1 / Lcc)
-    for (int i = r0 + tid; i < n; i += nt) {
+    for (int i = r0 + tid; i < n_rows; i += nt) {
       double x[kNB];
 #pragma unroll
       for (int c = 0; c < kNB; c++) {
@@ -210,12 +213,12 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
     }
     __syncthreads();
     // trailing lower triangle: warps stride the rows, lanes the columns (no integer division)
-    for (int i = r0 + warp; i < n; i += n_warps) {
+    for (int i = r0 + warp; i < n_rows; i += n_warps) {
       double li[kNB];
 #pragma unroll
       for (int c = 0; c < kNB; c++)
         li[c] = c < nb ? (pan ? prow[(size_t)(i - r0) * kPanStride + c] : A[(size_t)i * ld + kb + c]) : 0.0;
-      for (int j = r0 + lane; j <= i; j += 32) {
+      for (int j = r0 + lane; j <= i && j < n; j += 32) {
         double acc = 0.0;
 #pragma unroll
         for (int c = 0; c < kNB; c++)
@@ -874,8 +877,9 @@ __device__ __forceinline__ void cta_pivoted_cholesky(double* A, int ld, int n, i
 // the test is then independent of the units of the parameters, e.g. time offsets in ns next to metres) and factored
 // with pivoting, and L is unscaled in place.  Returns the rank (every thread); perm = identity on the plain path.
 // d0: n doubles of scratch (original diagonal), dtol: 2 n doubles of scratch (tolerances, inverse diagonal).
+// pan: (320 + kNB) * kPanStride doubles of shared scratch (staged panel; A is in global memory).
 __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* perm, double* d0, double* dtol, int* ok,
-                                                int* rank_sh) {
+                                                int* rank_sh, double* pan) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < n; i += nt) {
     d0[i] = A[(size_t)i * ld + i];
@@ -884,8 +888,7 @@ __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* p
   }
   if (tid == 0) *ok = 1;
   __syncthreads();
-  __shared__ double s_pan[(320 + kNB) * kPanStride];  // staged panel for blocks up to 320 wide (A is in global memory)
-  cta_cholesky(A, ld, n, ok, dtol + n, nullptr, dtol, n <= 320 ? s_pan : nullptr);  // dinv scratch right behind dtol
+  cta_cholesky(A, ld, n, ok, dtol + n, nullptr, dtol, n <= 320 ? pan : nullptr);  // dinv scratch right behind dtol
   __syncthreads();
   if (*ok) return n;
   // restore (the failed attempt touched the lower triangle and the diagonal only) and scale
@@ -924,12 +927,44 @@ __device__ __forceinline__ int cta_factor_block(double* A, int ld, int n, int* p
 //   A: pos x pos row-major, symmetric (both triangles valid); overwritten.   J0: n x n, r0: n.   perm: pos ints.
 //   status[0] = 0 ok;  status[1] = rank deficiency of A_mm;  status[2] = rank deficiency of the Schur complement.
 __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m, int n, double* J0, double* r0,
-                                                    int* perm, double* dscr, int* status) {
+                                                    int* perm, double* dscr, double* Aug, int* status) {
   const int pos = m + n;
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ int ok, rank;
   if (tid == 0) { ok = 1; status[1] = 0; status[2] = 0; }
   __syncthreads();
+  // ---- fast path: ONE blocked Cholesky of the augmented matrix [A b; b^T .] over its first pos columns.  After the
+  // first m columns the trailing block is the Schur complement A' and the appended row is b'; after all pos columns
+  // the kept block holds L' (J0 = L'^T) and the appended row holds r0 = L'^-1 b'.  Works on a copy: if a pivot
+  // fails the rank test the two-stage route below starts from the untouched A, b.
+  __shared__ double s_pan[(320 + kNB) * kPanStride];
+  if (Aug && pos + kNB <= 320) {
+    const int ld = pos + 1;
+    for (int e = tid; e < (pos + 1) * (pos + 1); e += nt) {
+      const int i = e / ld, j = e % ld;
+      double v = 0.0;
+      if (i < pos && j < pos) v = (i < m && j < m) ? 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]) : A[(size_t)i * pos + j];
+      else if (i == pos && j < pos) v = b[j];
+      else if (j == pos && i < pos) v = b[i];
+      Aug[e] = v;
+    }
+    for (int j = tid; j < pos; j += nt) dscr[pos + j] = (double)(j < m ? m : n) * 2.220446049250313e-16 * fabs(A[(size_t)j * pos + j]);
+    __syncthreads();
+    cta_cholesky(Aug, ld, pos, &ok, dscr + 2 * pos, nullptr, dscr + pos, s_pan, pos + 1);
+    __syncthreads();
+    if (ok) {
+      for (int e = tid; e < n * n; e += nt) {
+        const int k = e / n, a = e % n;  // J0[k][a] = L'[a][k]
+        J0[e] = a >= k ? Aug[(size_t)(m + a) * ld + m + k] : 0.0;
+      }
+      for (int k = tid; k < n; k += nt) r0[k] = Aug[(size_t)pos * ld + m + k];
+      if (tid == 0) status[0] = 0;
+      return;
+    }
+    __syncthreads();
+    if (tid == 0) ok = 1;
+    __syncthreads();
+  }
   if (m > 0) {
     // Amm = 0.5 (A_mm + A_mm^T)  (":208")
     for (int e = tid; e < m * m; e += nt) {
@@ -941,7 +976,7 @@ __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m,
       }
     }
     __syncthreads();
-    const int rm = cta_factor_block(A, pos, m, perm, dscr, dscr + pos, &ok, &rank);
+    const int rm = cta_factor_block(A, pos, m, perm, dscr, dscr + pos, &ok, &rank, s_pan);
     if (tid == 0) status[1] = m - rm;
     // X = L_r^-1 (P^T A_mr) (rm x n) in place at rows perm[i], one column per thread; y = L_r^-1 (P^T b_m)
     for (int c = tid; c < n + 1; c += nt) {
@@ -979,7 +1014,7 @@ __global__ void __launch_bounds__(512) schur_kernel(double* A, double* b, int m,
   }
   __syncthreads();
   int* permr = perm + m;
-  const int rn = cta_factor_block(Ar, pos, n, permr, dscr, dscr + pos, &ok, &rank);
+  const int rn = cta_factor_block(Ar, pos, n, permr, dscr, dscr + pos, &ok, &rank, s_pan);
   if (tid == 0) status[2] = n - rn;
   // J0[k][perm[a]] = L'[a][k] for k < rn (a >= k), zero rows below
   for (int e = tid; e < n * n; e += nt) J0[e] = 0.0;
