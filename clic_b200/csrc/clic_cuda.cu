@@ -272,6 +272,7 @@ struct clic_estimator {
   bool packs_fit = true;  // the packed visual kernel's shared memory fits this window
   int n_jobs = 0, n_part_ctas = 0, max_slots = 0;
   DevBuf d_bias_descs;
+  DevBuf d_lm_col, d_rho_side;  // free inverse depths: landmark -> column, per-landmark side rows of H | b
   bool bias_desc_dirty = true;
   int64_t launches = 0;
   bool bounds_toff[3] = {false, false, false};
@@ -501,6 +502,16 @@ int ensure_layout(clic_estimator* E) {
   CU(E->d_descs.ensure(std::max<size_t>(1, descs.size()) * sizeof(StreamDesc)));
   if (!descs.empty())
     CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
+  if (L.n_free_landmarks > 0) {
+    std::vector<int32_t> lm_col(E->n_lm, -1);
+    int rank = 0;
+    for (int i = 0; i < E->n_lm; i++)
+      if (E->lm_free[i]) lm_col[i] = L.col_inv_depth + rank++;
+    CU(E->d_lm_col.ensure((size_t)E->n_lm * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(E->d_lm_col.p, lm_col.data(), lm_col.size() * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CU(E->d_rho_side.ensure((size_t)L.n_free_landmarks * (L.col_inv_depth + 2) * sizeof(double)));
+    CU(cudaStreamSynchronize(E->stream));  // lm_col is a local
+  }
   E->n_jobs = (int)jobs.size();
   E->max_slots = 1;
   for (auto& j : jobs) E->max_slots = std::max(E->max_slots, j.n_slots);
@@ -598,6 +609,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   double* cost2 = Hp + E->off_cost() + (set ? 0 : 2 * which);
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
+  if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: accumulated by the visual kernels
+    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.col_inv_depth + 2) * sizeof(double), E->stream));
   pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
   auto launch_loam = [&](LoamBatch* b) -> int {
     StreamExec& ex = b->ex;
@@ -655,6 +668,12 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
     const bool packed = b->st.n_packs > 0;
     const size_t smem_p = image_smem_bytes(E->K, b->st.n_packs);
+    const bool free_rho = E->L.n_free_landmarks > 0;
+    b->st.rho_side = (jac && free_rho) ? E->d_rho_side.as<double>() : nullptr;
+    b->st.lm_col = free_rho ? E->d_lm_col.as<int32_t>() : nullptr;
+    b->st.knot_col = E->d_knot_col.as<int>();
+    b->st.D0 = E->L.col_inv_depth;
+    b->st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
     E->prof_begin(2);
     if (jac && packed) CU(launch_pdl(image_kernel<true, true>, ex.grid, kThreads, smem_p, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
     else if (jac) CU(launch_pdl(image_kernel<true, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
@@ -725,7 +744,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     E->prof_begin(3);
     CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, Hp, bp, cm, E->d_descs.as<StreamDesc>(),
                   E->n_desc, ctl, d_bias, bias_in_assemble ? (int)bias_descs.size() : 0, state, E->sl.off_bias(),
-                  cost2));
+                  cost2, E->L.n_free_landmarks > 0 ? (const double*)E->d_rho_side.as<double>() : (const double*)nullptr,
+                  E->L.col_inv_depth));
     E->prof_end();
     E->launches += 1;
   }
@@ -810,6 +830,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   B.st = (LmState*)(base + o_st);
   LayoutDev L;
   L.D = D; L.K = E->K; L.kf = Lh.first_free_knot; L.nb = E->n_bias; L.L = E->n_lm;
+  L.lm_col = Lh.n_free_landmarks > 0 ? E->d_lm_col.as<int32_t>() : nullptr;
   L.col_bias_gyro = Lh.col_bias_gyro; L.col_bias_accel = Lh.col_bias_accel;
   bool constrained = false;
   for (int s = 0; s < 3; s++) {
@@ -1559,14 +1580,13 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (n_dropped) *n_dropped = 0;
   if (n <= 0) return CLIC_OK;
-  if (!fixed_depth)
-    return fail(CLIC_ERR_UNSUPPORTED,
-                "fixed_depth = false (free inverse depths) is not built on the GPU yet; the shipped pipeline always "
-                "fixes them (trajectory_manager.cpp:709)");
+  if (!fixed_depth && E->opt.is_marg_state)
+    return fail(CLIC_ERR_UNSUPPORTED, "free inverse depths in a marginalization estimator are not built on the GPU");
   if (E->opt.is_marg_state && marg_this_feature)
     return fail(CLIC_ERR_UNSUPPORTED, "marginalising visual factors (UpdateVisualOffsetPrior) is not built yet");
   for (int64_t i = 0; i < n; i++)
     if (landmark[i] < 0 || landmark[i] >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
+
   CU(cudaSetDevice(E->device));
   cudaStream_t cs = E->copy_stream;
   AllocScope alloc_scope(cs);
@@ -1574,6 +1594,11 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   const int S = CLIC_SENSOR_CAMERA;
   const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
   const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
+  if (!fixed_depth)  // trajectory_estimator.cpp:789-793: the block of a KEPT factor stays variable unless fixed_depth
+    for (int64_t i = 0; i < n; i++) {  // same window test as prep_image_kernel (a dropped factor adds no block)
+      const int64_t a = (int64_t)(t_i[i] * 1e9), b = (int64_t)(t_j[i] * 1e9);
+      if (!(a - pad < t_min || a + pad >= t_max) && !(b - pad < t_min || b + pad >= t_max)) E->lm_free[landmark[i]] = 1;
+    }
   // Order by the (s_i, s_j) knot-interval key (stable counting sort, O(n)): consecutive factors then share their key
   // and a warp's accumulators are flushed rarely.  The key here only orders the inputs (host arithmetic at the
   // current offset); the kernels recompute the exact indices.

@@ -510,9 +510,11 @@ struct ImagePackPoses {
 //   [window of t_i: 0..23 | window of t_j: 24..47 | camera t_offset 48 | r 49 | pad]
 // `row_sel` (0 | 1) selects which of the two residual rows this call emits: the kernel gives row 0 to lanes 0-15 and
 // row 1 to lanes 16-31 of the same 16 factors (data-dependent only, no divergent code), the host test calls it twice.
+// free_depth: the landmark's inverse depth is a parameter; its Jacobian (image_feature_factor.h:238-247) goes to
+// local column 50 (0 otherwise).
 template <class Poses, class Sink>
 CLIC_HD double image_eval_with(const Poses& PS, V3 p_i, V3 p_j, double d_inv, const ImageShared& sh, bool want_jac,
-                               Sink& sink, int row_sel) {
+                               Sink& sink, int row_sel, bool free_depth = false) {
   V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
   V3 p_Ii = qrot(sh.S_CtoI, x_ci) + sh.p_CinI;
   const Q4 Ri = PS.Ri(), Rj = PS.Rj();
@@ -573,25 +575,31 @@ CLIC_HD double image_eval_with(const Poses& PS, V3 p_i, V3 p_j, double d_inv, co
     }
     sink.put(row, 48, sh.want_toff ? (1e-9 * sI) * dot(Jvr, jt) : 0.0);
     sink.put(row, 49, sc * (r0 ? res[0] : res[1]));
+    double j_rho = 0.0;
+    if (free_depth) {  // J_Xm_d = -(S_GtoCj R_i S_CtoI x_ci) / rho;  S_CtoI x_ci = p_Ii - p_CinI
+      const V3 jx = (-1.0 / d_inv) * qrot(S_GtoCj, qrot(Ri, p_Ii - sh.p_CinI));
+      j_rho = sI * dot(Jvr, jx);
+    }
+    sink.put(row, 50, j_rho);
 #pragma unroll
-    for (int cc = 50; cc < 56; cc++) sink.put(row, cc, 0.0);
+    for (int cc = 51; cc < 56; cc++) sink.put(row, cc, 0.0);
     sink.row_done(row);
   }
   return rho;
 }
 template <class Sink>
 CLIC_HD double image_eval(const WindowView& W, int si, double ui, int sj, double uj, V3 p_i, V3 p_j, double d_inv,
-                          const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
+                          const ImageShared& sh, bool want_jac, Sink& sink, int row_sel, bool free_depth = false) {
   const ImageChainPoses PS(W, si, ui, sj, uj, sh.inv_dt);
-  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel);
+  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel, free_depth);
 }
 template <class Sink>
 CLIC_HD double image_eval_packed(const double* pack_i, const double* pack_j, V3 p_i, V3 p_j, double d_inv,
-                                 const ImageShared& sh, bool want_jac, Sink& sink, int row_sel) {
+                                 const ImageShared& sh, bool want_jac, Sink& sink, int row_sel, bool free_depth = false) {
   ImagePackPoses PS;
   PS.A = pack_i;
   PS.B = pack_j;
-  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel);
+  return image_eval_with(PS, p_i, p_j, d_inv, sh, want_jac, sink, row_sel, free_depth);
 }
 
 }  // namespace clic

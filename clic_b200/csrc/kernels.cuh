@@ -710,6 +710,13 @@ struct ImageStream {
   double loss_a;
   // Pose packs (n_packs > 0): every feature of a camera frame shares its timestamp, so the spline poses and their
   // Jacobian maps are evaluated once per distinct (timestamp, role) by each CTA and the factors only compose them.
+  // Free inverse depths (fixed_depth = false; rho_side != nullptr): the terms that involve a landmark's column are
+  // scattered per factor with atomics into rho_side[rank][0 .. D0) = H[rho, col], [D0] = H[rho, rho], [D0 + 1] = b[rho]
+  // (two factors of one interval key see different landmarks, so these cannot ride in the per-key tiles).
+  const int32_t* lm_col;     // per landmark: its column of H, or -1 (constant)
+  const int* knot_col;       // per knot: column of its d(theta), -1 if constant
+  double* rho_side;
+  int D0, col_toff_cam;      // D0 = first inverse-depth column = number of other columns
   const int32_t* id_i;       // per factor: pack of t_i (0 .. n_pack_i-1)
   const int32_t* id_j;       // per factor: pack of t_j (n_pack_i .. n_packs-1)
   const int64_t* pack_t_ns;  // [n_packs] distinct times (ns, without offset)
@@ -768,11 +775,12 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
                  index_ns(tj + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &sj, &uj);
     V3 p_i = mk(0, 0, 1), p_j = mk(0, 0, 1);
     double rho_inv = 1.0;
-    int pack_i = 0, pack_j = 0;
+    int pack_i = 0, pack_j = 0, rho_col = -1;
     if (valid) {
       p_i = mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]);
       p_j = mk(st.pj[0][idx], st.pj[1][idx], 1.0);
       rho_inv = invd[st.landmark[idx]];
+      if (st.rho_side) rho_col = st.lm_col[st.landmark[idx]];
       if (PACKED) { pack_i = st.id_i[idx]; pack_j = st.id_j[idx]; }
     } else {
       si = sj = 0; ui = uj = 0.0;
@@ -783,7 +791,7 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
       int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
       bool mine = (key == kmin) && ((pending >> lane) & 1);
       // a visual factor touches knots of both windows: it has a free parameter unless both windows are all constant
-      const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff;
+      const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff || rho_col >= 0;
       const bool counts = mine && row_sel == 0;  // the factor's cost is counted once
       if (JAC) {
         if (kmin != acc_key) {
@@ -794,9 +802,25 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
         SmemRowSink<NT> sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
         double rho = PACKED ? image_eval_packed(packs + (size_t)pack_i * kPackDoubles, packs + (size_t)pack_j * kPackDoubles,
-                                                p_i, p_j, rho_inv, sh, true, sink, row_sel)
-                            : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel);
+                                                p_i, p_j, rho_inv, sh, true, sink, row_sel, rho_col >= 0)
+                            : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel, rho_col >= 0);
         if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
+        if (st.rho_side && mine && rho_col >= 0) {  // this lane's row is still in the tile: columns of the landmark
+          double* side = st.rho_side + (size_t)(rho_col - st.D0) * (st.D0 + 2);
+          const double jr = Jt[50 * kJtStride + lane];
+          for (int c = 0; c < 49; c++) {
+            const double v = Jt[c * kJtStride + lane];
+            if (v == 0.0) continue;
+            int g;
+            if (c < 24) { const int kc = st.knot_col[si + c / 6]; g = kc < 0 ? -1 : kc + c % 6; }
+            else if (c < 48) { const int kc = st.knot_col[sj + (c - 24) / 6]; g = kc < 0 ? -1 : kc + (c - 24) % 6; }
+            else g = st.col_toff_cam;
+            if (g >= 0) atomicAdd(side + g, jr * v);
+          }
+          atomicAdd(side + st.D0, jr * jr);
+          atomicAdd(side + st.D0 + 1, jr * Jt[49 * kJtStride + lane]);
+        }
+        __syncwarp();
       } else {
         NullSink sink;
         double rho = PACKED ? image_eval_packed(packs + (size_t)pack_i * kPackDoubles, packs + (size_t)pack_j * kPackDoubles,
@@ -1016,7 +1040,8 @@ struct BiasFactorDesc {
 __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
                                                        int n_desc, const int* ctl, const BiasFactorDesc* bias = nullptr,
                                                        int n_bias = 0, const double* state = nullptr,
-                                                       int off_bias = 0, double* cost2 = nullptr) {
+                                                       int off_bias = 0, double* cost2 = nullptr,
+                                                       const double* rho_side = nullptr, int D0 = 0) {
   pdl_wait();
   pdl_trigger();
   if (ctl && ctl[0]) return;
@@ -1091,6 +1116,14 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
+    if (rho_side) {  // entries of the inverse-depth columns (visual factors with a free landmark)
+      if (is_b) {
+        if (gi >= D0) acc += rho_side[(size_t)(gi - D0) * (D0 + 2) + D0 + 1];
+      } else if (gj >= D0) {
+        if (gi < D0) acc += rho_side[(size_t)(gj - D0) * (D0 + 2) + gi];
+        else if (gi == gj) acc += rho_side[(size_t)(gj - D0) * (D0 + 2) + D0];
+      }
+    }
     double bias_cost = 0.0;
     bool bias_free = false;
     for (int f = 0; f < n_bias; f++) {

@@ -339,6 +339,7 @@ struct LmState {
 };
 
 struct LayoutDev {
+  const int* lm_col;  // per landmark: column of its inverse depth, -1 if constant (nullptr: none is free)
   int D, K, kf, nb, L;
   int col_bias_gyro, col_bias_accel, col_toff[3];
   int has_bounds[3];
@@ -371,6 +372,9 @@ __device__ __forceinline__ void plus_state(const double* x, const double* delta,
     if (L.col_bias_accel >= 0)
       for (int a = 0; a < 3; a++) ob[3 + a] = xb[3 + a] + alpha * delta[L.col_bias_accel + 3 * j + a];
   }
+  if (L.lm_col)
+    for (int l = threadIdx.x; l < L.L; l += blockDim.x)
+      if (L.lm_col[l] >= 0) out[L.sl.off_invd() + l] = x[L.sl.off_invd() + l] + alpha * delta[L.lm_col[l]];
   if (threadIdx.x < 3) {
     const int s = threadIdx.x;
     if (L.col_toff[s] >= 0) {
@@ -434,6 +438,9 @@ __device__ __forceinline__ void ambient_diff(const double* x, const double* y, c
   }
   if (threadIdx.x < 3 && L.col_toff[threadIdx.x] >= 0 && active[L.col_toff[threadIdx.x]])
     acc(x + L.sl.off_toff() + threadIdx.x, y + L.sl.off_toff() + threadIdx.x, 1);
+  if (L.lm_col)
+    for (int l = threadIdx.x; l < L.L; l += blockDim.x)
+      if (L.lm_col[l] >= 0 && active[L.lm_col[l]]) acc(x + L.sl.off_invd() + l, y + L.sl.off_invd() + l, 1);
   double a = block_sum(xs, sh), b = block_sum(ds, sh), c = block_max(dm, sh);
   if (xs_out) *xs_out = a;
   if (ds_out) *ds_out = b;

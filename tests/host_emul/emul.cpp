@@ -83,8 +83,9 @@ __attribute__((visibility("default"))) int emul_image(int K, const double* kq, c
   sh.S_CtoI = ldq(S_CtoI); sh.p_CinI = ldv(p_CinI); sh.sqrt_info = 450.0 / 1.5; sh.loss_a = loss_a;
   sh.inv_dt = 1e9 / double(dt_ns); sh.want_toff = want_toff != 0;
   ArraySink sink{rows, 56};
-  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0);
-  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1);
+  // local column 50 = d r / d(inverse depth) (free_depth = true); callers with a fixed depth ignore it
+  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0, true);
+  *rho = image_eval(W.view, si, ui, sj, uj, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1, true);
   *si_out = si;
   *sj_out = sj;
   return 0;
@@ -109,8 +110,8 @@ __attribute__((visibility("default"))) int emul_image_packed(int K, const double
     compute_pose_pack(W.view, sj, uj, 1, sh.inv_dt, c, pb);
   }
   ArraySink sink{rows, 56};
-  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0);
-  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1);
+  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 0, true);
+  *rho = image_eval_packed(pa, pb, ldv(p_i), ldv(p_j), d_inv, sh, true, sink, 1, true);
   return 0;
 }
 }

@@ -124,8 +124,9 @@ def test_imu_rows(oracle, emul, name, sw, marg):
     assert worst < 1e-11, worst
 
 
+@pytest.mark.parametrize("free_depth", [False, True])
 @pytest.mark.parametrize("unlock_toff", [False, True])
-def test_image_rows(oracle, emul, unlock_toff):
+def test_image_rows(oracle, emul, unlock_toff, free_depth):
     sw = S.make_window(10, n_lidar=0, n_imu=0, n_landmarks=12, obs_per_landmark=6, seed=31, time_margin_ns=3_000_000)
     w = sw.window
     if unlock_toff:
@@ -136,7 +137,7 @@ def test_image_rows(oracle, emul, unlock_toff):
         opt.t_offset_padding_ns = 1_000_000
     est = E.TrajectoryEstimator(w, opt, oracle)
     I = sw.image
-    assert est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], True) == 0
+    assert est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], not free_depth) == 0
     Lay = est.layout()
     kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
     worst = 0.0
@@ -157,6 +158,8 @@ def test_image_rows(oracle, emul, unlock_toff):
         J[:, 6 * sj.value:6 * sj.value + 24] += rows[:, 24:48]   # overlapping windows add up
         if unlock_toff:
             J[:, Lay.col_t_offset[2]] += rows[:, 48]
+        if free_depth:   # every landmark of this window is observed, so its rank among the free ones is its index
+            J[:, Lay.col_inv_depth + int(I["landmark"][i])] += rows[:, 50]
         overlaps += abs(si.value - sj.value) < 4
         # the per-timestamp pose-pack path (packed visual kernel) emits the same rows
         rows_p, rho_p = np.zeros((2, 56)), np.zeros(1)

@@ -22,7 +22,7 @@ def rel_scaled(Hg, Ho):
 
 
 def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000,
-          unlock_cam_toff=False):
+          unlock_cam_toff=False, fixed_depth=True):
     opt = E.default_options(lib)
     if unlock_bias:
         opt.lock_ab = opt.lock_wb = 0
@@ -34,7 +34,7 @@ def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=T
         opt.t_offset_padding_ns = pad
     est = E.TrajectoryEstimator(sw.window, opt, lib)
     est.SetFixedIndex(fixed)
-    dropped = S.add_all_factors(est, sw, bias_factor=bias_factor)
+    dropped = S.add_all_factors(est, sw, bias_factor=bias_factor, fixed_depth=fixed_depth)
     return est, dropped
 
 
@@ -259,3 +259,26 @@ def test_type_uniform_lidar_batches(cuda, oracle):
     for ref in ("mixed", "oracle"):
         assert rel(out["split"][1], out[ref][1]) < REL and rel(out["split"][2], out[ref][2]) < REL
         assert abs(out["split"][3] - out[ref][3]) <= REL * abs(out[ref][3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unlock_cam_toff", [False, True])
+def test_c3_free_inverse_depths(cuda, oracle, unlock_cam_toff):
+    """BASELINE config 3, fixed_depth = false variant: every landmark's inverse depth is a parameter (+200 columns;
+    image_feature_factor.h:238-247).  The landmark columns are accumulated per factor (atomics into per-landmark side
+    rows), everything else through the per-key tiles."""
+    sw = S.config(3, 0.1)
+    if unlock_cam_toff:
+        sw.window.t_offset_ns = np.array([0.0, 0.0, 80_000.3])
+    eg, _ = build(cuda, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=unlock_cam_toff, pad=1_000_000)
+    Lg = eg.layout()
+    # a landmark whose observations were all dropped (time-offset padding at the window edge) adds no block
+    assert 0 < Lg.n_free_landmarks <= len(sw.window.inv_depth) and Lg.D == Lg.col_inv_depth + Lg.n_free_landmarks
+    compare_eval(cuda, oracle, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=unlock_cam_toff, pad=1_000_000)
+    # per-timestamp pose packs off: the per-factor chain kernel scatters the same landmark terms
+    import os
+    os.environ["CLIC_NO_POSE_PACKS"] = "1"
+    try:
+        compare_eval(cuda, oracle, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=unlock_cam_toff, pad=1_000_000)
+    finally:
+        del os.environ["CLIC_NO_POSE_PACKS"]

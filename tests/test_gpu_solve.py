@@ -72,3 +72,22 @@ def test_40_knot_solve(cuda, oracle):
 def test_c3_solve(cuda, oracle):
     """BASELINE config 3 at 1/10 size: LiDAR-inertial-camera solve."""
     solve_both(cuda, oracle, S.config(3, 0.1), 8, unlock_bias=True)
+
+
+def test_c3_solve_free_inverse_depths(cuda, oracle):
+    """Config 3 with the landmarks' inverse depths optimised together with the trajectory (D = 72 + 20)."""
+    sw = S.config(3, 0.1)
+    rng = np.random.default_rng(12)
+    sw.window.inv_depth = sw.window.inv_depth * (1.0 + rng.normal(0, 0.05, len(sw.window.inv_depth)))
+    out = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        est, _ = build(lib, sw, unlock_bias=True, fixed_depth=False)
+        out[name] = (est.Solve(8), est.read_state())
+    (sg, xg), (so, xo) = out["g"], out["o"]
+    for k in ("iterations", "num_successful_steps", "num_unsuccessful_steps", "termination", "termination_reason"):
+        assert sg[k] == so[k], (k, sg, so)
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-7 * abs(so["final_cost"])
+    assert np.abs(xg["knot_p"] - xo["knot_p"]).max() < POS_TOL
+    assert rot_err(xg["knot_q"], xo["knot_q"]).max() < ROT_TOL
+    assert np.abs(xg["inv_depth"] - xo["inv_depth"]).max() < 1e-7
+    assert np.abs(xg["inv_depth"] - sw.window.inv_depth).max() > 1e-6       # they did move
