@@ -404,6 +404,7 @@ class TrajectoryEstimator {
       std::memcpy(bias_ptr_[i].second, &bias[6 * i + 3], 3 * sizeof(double));
     }
     for (int s = 0; s < 3; s++) trajectory_->EP_StoI[(SensorType)s].t_offset_ns = toff[s];
+    for (size_t i = 0; i < landmark_ptr_.size(); i++) *landmark_ptr_[i] = invd[i];  // free inverse depths (fixed_depth = false)
   }
 
   Trajectory::Ptr trajectory_;
