@@ -452,18 +452,18 @@ def main():
         "achieved": ab["lidar"] / (loam_ms * 1e-3) / 1e9 if loam_ms > 0 else None, "peak": peak, "unit": "GB/s",
         "frac": (ab["lidar"] / (loam_ms * 1e-3) / 1e9 / peak) if loam_ms > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the two loam_kernel<true> launches of a pass on this workload
-        # (ncu --set full, profiles/r01j_pass_kernels_ncu.txt): plane batch 44.89 MB + line batch 24.03 MB — the
+        # (ncu --set full, profiles/r01k_pass_kernels_ncu.txt): plane batch 44.88 MB + line batch 24.03 MB — the
         # type-uniform streams store exactly the 64 / 80 algorithmic bytes per feature
-        "traffic": 44890368 + 24032512 + 512 if (args.scale == 1.0 and world == 1) else None,
+        "traffic": 44882176 + 24025600 if (args.scale == 1.0 and world == 1) else None,
         "peak_kind": f"of {peak_kind}", "algorithmic_bytes_per_launch": ab["lidar"], "kernel_ms": loam_ms,
         "kernel_share_of_step": float(prof_ms[0] / prof_ms.sum()) if prof_ms.sum() > 0 else None,
         "per_class_ms_per_step": {k: float(prof_ms[i] / args.steps) for i, k in enumerate(
             ["lidar", "imu", "visual", "reduce_assemble", "prior_bias", "lm_step", "allreduce", "marginalize"])},
-        "note": "binding limit is the shared FP64 pipe (DFMA + DMMA), not HBM: ncu sm__pipe_shared_cycles_active = 55% "
-                "(LiDAR planes) / 49% (LiDAR lines) / 59% (IMU) of active cycles, profiles/r01j_pass_kernels_ncu.txt; "
+        "note": "binding limit is the shared FP64 pipe (DFMA + DMMA), not HBM: ncu sm__pipe_shared_cycles_active = 57% "
+                "(LiDAR planes) / 52% (LiDAR lines) / 60% (IMU) of active cycles, profiles/r01k_pass_kernels_ncu.txt; "
                 "DFMA/DMMA peaks measured 36.3/37.1 TFLOP/s on that one pipe (profiles/r01_fp64_peaks.txt)",
-        "fp64_pipe_frac": {"lidar_planes": 0.55, "lidar_lines": 0.49, "imu": 0.59,
-                           "source": "ncu sm__pipe_shared_cycles_active, profiles/r01j_pass_kernels_ncu.txt"},
+        "fp64_pipe_frac": {"lidar_planes": 0.57, "lidar_lines": 0.52, "imu": 0.60,
+                           "source": "ncu sm__pipe_shared_cycles_active, profiles/r01k_pass_kernels_ncu.txt"},
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
