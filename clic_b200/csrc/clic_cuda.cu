@@ -196,6 +196,7 @@ struct ImageBatch {
   DevBuf raw[4];
   DevBuf id_i, id_j, pack_t;  // pose packs (st.n_packs > 0)
   std::vector<int64_t> perm;  // sorted position -> add order
+  std::vector<char> lm_used;  // landmarks referenced by a kept factor (marg batches: their inverse depths are dropped blocks)
   int marg = 0;
   StreamExec ex;
 };
@@ -509,7 +510,7 @@ int ensure_layout(clic_estimator* E) {
       if (E->lm_free[i]) lm_col[i] = L.col_inv_depth + rank++;
     CU(E->d_lm_col.ensure((size_t)E->n_lm * sizeof(int32_t)));
     CU(cudaMemcpyAsync(E->d_lm_col.p, lm_col.data(), lm_col.size() * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
-    CU(E->d_rho_side.ensure((size_t)L.n_free_landmarks * (L.col_inv_depth + 2) * sizeof(double)));
+    CU(E->d_rho_side.ensure((size_t)L.n_free_landmarks * (L.D + 2) * sizeof(double)));
     CU(cudaStreamSynchronize(E->stream));  // lm_col is a local
   }
   E->n_jobs = (int)jobs.size();
@@ -610,7 +611,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
   if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: accumulated by the visual kernels
-    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.col_inv_depth + 2) * sizeof(double), E->stream));
+    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.D + 2) * sizeof(double), E->stream));
   pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
   auto launch_loam = [&](LoamBatch* b) -> int {
     StreamExec& ex = b->ex;
@@ -672,7 +673,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     b->st.rho_side = (jac && free_rho) ? E->d_rho_side.as<double>() : nullptr;
     b->st.lm_col = free_rho ? E->d_lm_col.as<int32_t>() : nullptr;
     b->st.knot_col = E->d_knot_col.as<int>();
-    b->st.D0 = E->L.col_inv_depth;
+    b->st.Dtot = E->L.D;
+    b->st.rho0 = E->L.col_inv_depth;
     b->st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
     E->prof_begin(2);
     if (jac && packed) CU(launch_pdl(image_kernel<true, true>, ex.grid, kThreads, smem_p, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
@@ -745,7 +747,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     CU(launch_pdl(assemble_kernel, (n_entries + 7) / 8, 256, 0, E->stream, Hp, bp, cm, E->d_descs.as<StreamDesc>(),
                   E->n_desc, ctl, d_bias, bias_in_assemble ? (int)bias_descs.size() : 0, state, E->sl.off_bias(),
                   cost2, E->L.n_free_landmarks > 0 ? (const double*)E->d_rho_side.as<double>() : (const double*)nullptr,
-                  E->L.col_inv_depth));
+                  E->L.col_inv_depth, E->L.n_free_landmarks));
     E->prof_end();
     E->launches += 1;
   }
@@ -1001,6 +1003,53 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
       if (E->opt.marg_bias_param) bias_drop[b->st.bias_slot] = bias_drop[E->n_bias + b->st.bias_slot] = 1;
     }
   }
+  // visual factors (UpdateVisualOffsetPrior, trajectory_manager.cpp:466-553): every marginalised feature drops its
+  // inverse depth, so every such factor is in the set; first run = records only (which knots are touched decides the
+  // column layout), the landmark side rows are scattered in a second run once the columns are known.
+  std::vector<char> lm_used(std::max(1, E->n_lm), 0);
+  bool any_image = false;
+  auto image_shared = [&](const ImageBatch& b) {
+    ImageShared ish;
+    ish.S_CtoI = ldq(E->S_CtoI);
+    ish.p_CinI = ldv(E->p_CinI);
+    ish.sqrt_info = 450.0 / 1.5;
+    ish.loss_a = b.st.loss_a;
+    ish.inv_dt = 1e9 / double(E->dt_ns);
+    ish.want_toff = true;  // the marginalization evaluates every Jacobian block
+    return ish;
+  };
+  auto launch_image_marg = [&](ImageBatch& b) -> int {
+    StreamExec& ex = b.ex;
+    const ImageShared ish = image_shared(b);
+    if (b.st.n_packs > 0)
+      image_kernel<true, true><<<ex.grid, kThreads, image_smem_bytes(K, b.st.n_packs), E->stream>>>(b.st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    else
+      image_kernel<true, false><<<ex.grid, kThreads, factor_smem_bytes(K, 7), E->stream>>>(b.st, pp, ex.slabs_per_warp, ex.rb(), ish);
+    E->launches += 1;
+    return reduce_stream(ex);
+  };
+  std::vector<int> present2((size_t)(K - 3) * (K - 3));
+  DevBuf d_present2;
+  for (auto& b : E->image) {
+    if (!b->marg) continue;
+    StreamExec& ex = b->ex;
+    b->st.rho_side = nullptr;
+    b->st.lm_col = nullptr;
+    if ((rc = launch_image_marg(*b))) return rc;
+    CU(d_present2.ensure(present2.size() * sizeof(int)));
+    key_presence_kernel<<<(ex.n_keys + 63) / 64, 64, 0, E->stream>>>(ex.fin.as<double>(), ex.n_keys, ex.rd, ex.NT, 49,
+                                                                    d_present2.as<int>());
+    E->launches++;
+    CU(cudaMemcpyAsync(present2.data(), d_present2.p, ex.n_keys * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    const int nk = K - 3;
+    for (int key = 0; key < ex.n_keys; key++)
+      if (present2[key]) {
+        any_image = true;
+        for (int k = 0; k < 4; k++) knot_used[key / nk + k] = knot_used[key % nk + k] = 1;
+      }
+    for (int l = 0; l < E->n_lm; l++) lm_used[l] = lm_used[l] || b->lm_used[l];
+  }
   for (auto& bf : E->bias_f) {
     if (!bf.marg) continue;
     for (int sl : {bf.slot_i, bf.slot_j}) bias_used[sl] = bias_used[E->n_bias + sl] = 1;
@@ -1015,7 +1064,8 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   std::vector<Blk> blocks;
   std::vector<char> knot_drop(K, 0);
   bool grav_used = any_imu, grav_drop = any_imu && E->opt.marg_gravity_param;
-  bool toff_used[3] = {any_imu, false, false}, toff_drop[3] = {any_imu && E->opt.marg_t_offset_param != 0, false, false};
+  bool toff_used[3] = {any_imu, false, any_image};
+  bool toff_drop[3] = {any_imu && E->opt.marg_t_offset_param != 0, false, any_image && E->opt.marg_t_offset_param != 0};
   for (auto& pr : E->priors) {
     std::vector<char> dropped(pr->p->blocks.size(), 0);
     for (int d : pr->drop) if (d >= 0 && d < (int)dropped.size()) dropped[d] = 1;
@@ -1043,6 +1093,10 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     if (bias_used[E->n_bias + j]) blocks.push_back({CLIC_BLOCK_BIAS_ACCEL, j, 3, 1, bias_drop[E->n_bias + j], -1});
   if (grav_used) blocks.push_back({CLIC_BLOCK_GRAVITY, 0, 3, 1, grav_drop ? 1 : 0, -1});
   for (int sn = 0; sn < 3; sn++) if (toff_used[sn]) blocks.push_back({CLIC_BLOCK_T_OFFSET, sn, 1, 1, toff_drop[sn] ? 1 : 0, -1});
+  int n_rho = 0;
+  if (any_image)  // the inverse depth of a marginalised feature is always dropped (trajectory_estimator.cpp:813-818)
+    for (int l = 0; l < E->n_lm; l++)
+      if (lm_used[l]) { blocks.push_back({CLIC_BLOCK_INV_DEPTH, l, 1, 1, 1, -1}); n_rho++; }
   int pos = 0;
   for (auto& b : blocks) if (b.drop) { b.idx = pos; pos += b.size == 4 ? 3 : b.size; }
   const int m = pos;
@@ -1091,6 +1145,39 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     d.extra_global[9] = ct;
     descs.push_back(d);
   }
+  DevBuf d_lm_col, d_side;
+  int rho0 = 0;
+  if (n_rho > 0) {
+    std::vector<int32_t> lm_col(E->n_lm, -1);
+    rho0 = pos;
+    for (int l = 0; l < E->n_lm; l++)
+      if (lm_used[l]) { lm_col[l] = find(CLIC_BLOCK_INV_DEPTH, l); rho0 = std::min(rho0, (int)lm_col[l]); }
+    if ((rc = to_device(E, d_lm_col, lm_col.data(), lm_col.size()))) return rc;
+    CU(d_side.ensure((size_t)n_rho * (pos + 2) * sizeof(double)));
+    CU(cudaMemsetAsync(d_side.p, 0, (size_t)n_rho * (pos + 2) * sizeof(double), E->stream));
+    CU(cudaStreamSynchronize(E->stream));  // lm_col is a local
+  }
+  for (auto& b : E->image) {
+    if (!b->marg) continue;
+    if (n_rho > 0) {  // second run: same records, plus the landmark side rows under the final column layout
+      b->st.rho_side = d_side.as<double>();
+      b->st.lm_col = d_lm_col.as<int32_t>();
+      b->st.knot_col = d_kc.as<int>();
+      b->st.Dtot = pos;
+      b->st.rho0 = rho0;
+      b->st.col_toff_cam = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_CAMERA);
+      if ((rc = launch_image_marg(*b))) return rc;
+      b->st.rho_side = nullptr;
+      b->st.lm_col = nullptr;
+    }
+    StreamDesc d{};
+    d.fin = b->ex.fin.as<double>();
+    d.n_keys = b->ex.n_keys; d.NT = b->ex.NT; d.rd = b->ex.rd;
+    d.r_col = 49; d.b_off = -1; d.n_extra = 1; d.extra_base = 48; d.kind = 1; d.kdim = K - 3;
+    for (int l = 0; l < 64; l++) d.perm[l] = (unsigned char)l;
+    d.extra_global[0] = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_CAMERA);
+    descs.push_back(d);
+  }
   if ((rc = to_device(E, d_desc, descs.data(), descs.size()))) return rc;
   CU(d_A.ensure((size_t)pos * pos * sizeof(double)));
   CU(d_b.ensure((size_t)pos * sizeof(double)));
@@ -1106,8 +1193,9 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   cm.D = pos; cm.K = K;
   cm.knot_col = d_kc.as<int>(); cm.col_knot = d_ck.as<int>(); cm.col_sub = d_cs.as<int>();
   const int n_entries = pos * (pos + 1) / 2 + pos;
-  assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(d_A.as<double>(), d_b.as<double>(), cm,
-                                                              d_desc.as<StreamDesc>(), (int)descs.size(), nullptr);
+  assemble_kernel<<<(n_entries + 7) / 8, 256, 0, E->stream>>>(
+      d_A.as<double>(), d_b.as<double>(), cm, d_desc.as<StreamDesc>(), (int)descs.size(), nullptr, nullptr, 0, nullptr, 0,
+      nullptr, n_rho > 0 ? (const double*)d_side.as<double>() : (const double*)nullptr, rho0, n_rho);
   E->launches++;
   for (auto& bf : E->bias_f) {
     if (!bf.marg) continue;
@@ -1582,8 +1670,6 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   if (n <= 0) return CLIC_OK;
   if (!fixed_depth && E->opt.is_marg_state)
     return fail(CLIC_ERR_UNSUPPORTED, "free inverse depths in a marginalization estimator are not built on the GPU");
-  if (E->opt.is_marg_state && marg_this_feature)
-    return fail(CLIC_ERR_UNSUPPORTED, "marginalising visual factors (UpdateVisualOffsetPrior) is not built yet");
   for (int64_t i = 0; i < n; i++)
     if (landmark[i] < 0 || landmark[i] >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
 
@@ -1729,7 +1815,12 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   B->st.n_pack_i = use_packs ? n_pack_i : 0;
   B->st.n_packs = use_packs ? n_pack_i + n_pack_j : 0;
   B->st.loss_a = marg_this_feature ? 1.0 : 2.0;  // trajectory_estimator.cpp:806-810
-  B->marg = 0;
+  B->marg = (E->opt.is_marg_state && marg_this_feature) ? 1 : 0;
+  B->lm_used.assign(std::max(0, E->n_lm), 0);
+  for (int64_t i = 0; i < n; i++) {  // same window test as prep_image_kernel
+    const int64_t a = (int64_t)(t_i[i] * 1e9), b = (int64_t)(t_j[i] * 1e9);
+    if (!(a - pad < t_min || a + pad >= t_max) && !(b - pad < t_min || b + pad >= t_max)) B->lm_used[landmark[i]] = 1;
+  }
   if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:795-800
     E->bounds_toff[S] = true;
     E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;

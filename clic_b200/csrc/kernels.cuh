@@ -711,12 +711,14 @@ struct ImageStream {
   // Pose packs (n_packs > 0): every feature of a camera frame shares its timestamp, so the spline poses and their
   // Jacobian maps are evaluated once per distinct (timestamp, role) by each CTA and the factors only compose them.
   // Free inverse depths (fixed_depth = false; rho_side != nullptr): the terms that involve a landmark's column are
-  // scattered per factor with atomics into rho_side[rank][0 .. D0) = H[rho, col], [D0] = H[rho, rho], [D0 + 1] = b[rho]
-  // (two factors of one interval key see different landmarks, so these cannot ride in the per-key tiles).
+  // scattered per factor with atomics into rho_side[rank][col] = H[rho, col] (col < Dtot, any non-rho column),
+  // [Dtot] = H[rho, rho], [Dtot + 1] = b[rho]  (two factors of one interval key see different landmarks, so these
+  // cannot ride in the per-key tiles).  The rho columns are rho0 .. rho0 + n_rho - 1 (last in a solve, among the
+  // dropped ones in a marginalization).
   const int32_t* lm_col;     // per landmark: its column of H, or -1 (constant)
   const int* knot_col;       // per knot: column of its d(theta), -1 if constant
   double* rho_side;
-  int D0, col_toff_cam;      // D0 = first inverse-depth column = number of other columns
+  int Dtot, rho0, col_toff_cam;  // Dtot = number of columns of the system, rho0 = first inverse-depth column
   const int32_t* id_i;       // per factor: pack of t_i (0 .. n_pack_i-1)
   const int32_t* id_j;       // per factor: pack of t_j (n_pack_i .. n_packs-1)
   const int64_t* pack_t_ns;  // [n_packs] distinct times (ns, without offset)
@@ -791,7 +793,7 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
       int kmin = __reduce_min_sync(0xffffffffu, (key >= 0 && ((pending >> lane) & 1)) ? key : 0x7fffffff);
       bool mine = (key == kmin) && ((pending >> lane) & 1);
       // a visual factor touches knots of both windows: it has a free parameter unless both windows are all constant
-      const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff || rho_col >= 0;
+      const bool any_free = (max(si, sj) + 3 >= pp.kf) || sh.want_toff || rho_col >= 0 || pp.marg_mode;
       const bool counts = mine && row_sel == 0;  // the factor's cost is counted once
       if (JAC) {
         if (kmin != acc_key) {
@@ -806,7 +808,7 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
                             : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel, rho_col >= 0);
         if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
         if (st.rho_side && mine && rho_col >= 0) {  // this lane's row is still in the tile: columns of the landmark
-          double* side = st.rho_side + (size_t)(rho_col - st.D0) * (st.D0 + 2);
+          double* side = st.rho_side + (size_t)(rho_col - st.rho0) * (st.Dtot + 2);
           const double jr = Jt[50 * kJtStride + lane];
           for (int c = 0; c < 49; c++) {
             const double v = Jt[c * kJtStride + lane];
@@ -817,8 +819,8 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
             else g = st.col_toff_cam;
             if (g >= 0) atomicAdd(side + g, jr * v);
           }
-          atomicAdd(side + st.D0, jr * jr);
-          atomicAdd(side + st.D0 + 1, jr * Jt[49 * kJtStride + lane]);
+          atomicAdd(side + st.Dtot, jr * jr);
+          atomicAdd(side + st.Dtot + 1, jr * Jt[49 * kJtStride + lane]);
         }
         __syncwarp();
       } else {
@@ -1041,7 +1043,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
                                                        int n_desc, const int* ctl, const BiasFactorDesc* bias = nullptr,
                                                        int n_bias = 0, const double* state = nullptr,
                                                        int off_bias = 0, double* cost2 = nullptr,
-                                                       const double* rho_side = nullptr, int D0 = 0) {
+                                                       const double* rho_side = nullptr, int rho0 = 0, int n_rho = 0) {
   pdl_wait();
   pdl_trigger();
   if (ctl && ctl[0]) return;
@@ -1116,12 +1118,17 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
-    if (rho_side) {  // entries of the inverse-depth columns (visual factors with a free landmark)
+    if (rho_side) {  // entries of the inverse-depth columns (visual factors with a free / marginalised landmark)
+      const bool ri = gi >= rho0 && gi < rho0 + n_rho, rj = !is_b && gj >= rho0 && gj < rho0 + n_rho;
+      const size_t ld = (size_t)D + 2;
       if (is_b) {
-        if (gi >= D0) acc += rho_side[(size_t)(gi - D0) * (D0 + 2) + D0 + 1];
-      } else if (gj >= D0) {
-        if (gi < D0) acc += rho_side[(size_t)(gj - D0) * (D0 + 2) + gi];
-        else if (gi == gj) acc += rho_side[(size_t)(gj - D0) * (D0 + 2) + D0];
+        if (ri) acc += rho_side[(size_t)(gi - rho0) * ld + D + 1];
+      } else if (ri && rj) {
+        if (gi == gj) acc += rho_side[(size_t)(gi - rho0) * ld + D];
+      } else if (rj) {
+        acc += rho_side[(size_t)(gj - rho0) * ld + gi];
+      } else if (ri) {
+        acc += rho_side[(size_t)(gi - rho0) * ld + gj];
       }
     }
     double bias_cost = 0.0;

@@ -194,3 +194,36 @@ def test_fewer_factors_than_dropped_dimensions(cuda, oracle):
     assert np.abs(S_true).max() < 1e-9 * scale                     # zero by the rank argument
     assert np.abs(Ag).max() < 1e-9 * scale, np.abs(Ag).max() / scale
     assert np.abs(gg).max() < 1e-7 * np.abs(b[m:]).max()
+
+
+@pytest.mark.parametrize("marg_toff", [0, 1])
+def test_visual_offset_prior(cuda, oracle, marg_toff):
+    """TrajectoryManager::UpdateVisualOffsetPrior (trajectory_manager.cpp:466-553): visual factors of the oldest frames
+    are marginalised — knots older than ctrl_to_be_opt_later and every feature's inverse depth are dropped, the camera
+    time offset is kept (marg_t_offset_param = false) or dropped — on top of LiDAR factors of the same window."""
+    sw = S.make_window(14, n_lidar=1500, n_imu=0, n_landmarks=40, obs_per_landmark=6, seed=97, init_noise=(1e-3, 2e-3),
+                       line_fraction=0.2, time_margin_ns=3_000_000)
+    out = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        opt = E.default_options(lib)
+        opt.is_marg_state = 1
+        opt.marg_t_offset_param = marg_toff
+        opt.ctrl_to_be_opt_now = 0
+        opt.ctrl_to_be_opt_later = 6
+        est = E.TrajectoryEstimator(sw.window, opt, lib)
+        L, I = sw.lidar, sw.image
+        est.AddLoamMeasurementAnalytic(L["t_point"], L["point"], L["geo_type"], L["geo_plane"], L["geo_normal"],
+                                       L["geo_point"], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], L["weight"], True)
+        est.AddImageFeatureAnalytic(I["t_i"], I["p_i"], I["t_j"], I["p_j"], I["landmark"], True, True)
+        pr = est.SaveMarginalizationInfo()
+        assert pr is not None
+        out[name] = (pr.dims(), pr.read(), pr.normal())
+    (dg, rg, (Ag, gg)), (do, ro, (Ao, go)) = out["g"], out["o"]
+    assert dg == do, (dg, do)
+    n, nb, m = do
+    assert m >= 6 * 6 + 30        # dropped knots + the inverse depths of the observed landmarks
+    for k in ("kind", "id", "offset"):
+        assert np.array_equal(rg[k], ro[k]), k
+    assert (2 in list(ro["id"][ro["kind"] == 5])) == (marg_toff == 0)      # camera time offset kept iff not marginalised
+    assert rel_scaled(Ag, Ao) < 1e-7, rel_scaled(Ag, Ao)
+    assert np.abs(gg - go).max() / np.abs(go).max() < 1e-7
