@@ -11,6 +11,7 @@ import numpy as np
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
+c_float_p = C.POINTER(C.c_float)
 
 
 class WindowDesc(C.Structure):
@@ -135,6 +136,15 @@ PROTOTYPES = {
                                    c_int64_p]),
     "clic_undistort_scan": (C.c_int, [H, C.c_int64, c_double_p, C.POINTER(C.c_float), c_double_p, c_double_p, C.c_double,
                                       C.c_int32, C.c_double, C.POINTER(C.c_float), c_int64_p]),
+    "clic_feature_map_create": (C.c_int, [c_float_p, C.c_int64, c_float_p, C.c_int64, C.POINTER(H)]),
+    "clic_feature_map_destroy": (None, [H]),
+    "clic_correspondence_capacity": (C.c_int64, [C.c_int64]),
+    "clic_find_correspondence": (C.c_int, [H, C.c_int64, c_float_p, c_double_p, c_float_p,
+                                           C.c_int64, c_float_p, c_double_p, c_float_p,
+                                           c_int64_p, c_double_p, c_double_p, c_double_p, c_int64_p,
+                                           c_int64_p, c_double_p, c_double_p, c_double_p, c_int64_p]),
+    "clic_correspondence_neighbours": (C.c_int, [H, C.c_int32, C.c_int64, c_int32_p, c_int64_p]),
+    "clic_feature_map_launches": (C.c_int, [H, c_int64_p, c_double_p]),
     "clic_marginalize": (C.c_int, [H, C.POINTER(H)]),
     "clic_prior_create": (C.c_int, [C.c_int32, c_double_p, c_double_p, C.c_int32, c_int32_p, c_int32_p, c_double_p,
                                     C.POINTER(H)]),

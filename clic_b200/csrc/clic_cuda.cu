@@ -18,6 +18,7 @@
 #include "../../include/clic_cuda.h"
 #include "kernels.cuh"
 #include "solver.cuh"
+#include "assoc.cuh"
 
 using namespace clic;
 
@@ -2324,6 +2325,251 @@ CLIC_API int clic_profile_read(clic_estimator* E, double ms[8], int64_t launches
 CLIC_API int clic_num_kernel_launches(clic_estimator* E, int64_t* l) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   if (l) *l = E->launches;
+  return CLIC_OK;
+}
+
+// ---- LiDAR data association (kernels in assoc.cuh) ----
+namespace {
+struct AssocSide {  // device layout of one feature type inside the scratch buffer
+  int64_t n_feat = 0, step = 1, n_q = 0;
+  int geo_w = 4, n_slices = 1, slice_len = 1;
+  size_t o_xyzM = 0, o_xyzL = 0, o_t = 0, o_part_d = 0, o_part_i = 0, o_valid = 0, o_geo = 0, o_nn = 0, o_out_t = 0,
+         o_out_pt = 0, o_out_geo = 0, o_out_src = 0;
+};
+size_t assoc_plan(AssocSide& s, size_t off) {
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  s.o_xyzM = take((size_t)3 * s.n_feat * sizeof(float));
+  s.o_xyzL = take((size_t)3 * s.n_feat * sizeof(float));
+  s.o_t = take((size_t)s.n_feat * sizeof(double));
+  s.o_part_d = take((size_t)5 * s.n_slices * s.n_q * sizeof(float));
+  s.o_part_i = take((size_t)5 * s.n_slices * s.n_q * sizeof(int));
+  s.o_valid = take((size_t)s.n_q);
+  s.o_geo = take((size_t)6 * s.n_q * sizeof(double));
+  s.o_nn = take((size_t)5 * s.n_q * sizeof(int));
+  s.o_out_t = take((size_t)s.n_q * sizeof(double));
+  s.o_out_pt = take((size_t)3 * s.n_q * sizeof(double));
+  s.o_out_geo = take((size_t)s.geo_w * s.n_q * sizeof(double));
+  s.o_out_src = take((size_t)s.n_q * sizeof(long long));
+  return off;
+}
+}  // namespace
+
+struct clic_feature_map {
+  uint32_t magic = 0x4d41504cu;
+  int device = 0, n_sm = 148;
+  cudaStream_t stream = nullptr;
+  float* d_map[2] = {nullptr, nullptr};  // corner, surface: structure of arrays x[n] y[n] z[n]
+  int64_t n_map[2] = {0, 0};
+  void* d_scratch = nullptr;  // per-call inputs, per-feature results and the compacted outputs
+  size_t scratch_bytes = 0;
+  int64_t launches = 0;
+  AssocSide last[2];  // layout of the last call (clic_correspondence_neighbours)
+  cudaEvent_t ev[2] = {nullptr, nullptr};  // around the kernels of the last call
+};
+
+CLIC_API int clic_feature_map_create(const float* surf_xyz, int64_t n_surf, const float* corner_xyz, int64_t n_corner,
+                                     clic_feature_map** out) {
+  if (!out || n_surf < 0 || n_corner < 0 || (n_surf > 0 && !surf_xyz) || (n_corner > 0 && !corner_xyz))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bad feature map");
+  if (n_surf > INT32_MAX / 4 || n_corner > INT32_MAX / 4) return fail(CLIC_ERR_BAD_ARGUMENT, "feature map too large");
+  if (!have_device()) return fail(CLIC_ERR_NO_DEVICE, "no CUDA device: libclic_cuda has no CPU fallback");
+  std::unique_ptr<clic_feature_map> m(new clic_feature_map);
+  CU(cudaGetDevice(&m->device));
+  CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device));
+  CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&m->ev[0]));
+  CU(cudaEventCreate(&m->ev[1]));
+  const float* src[2] = {corner_xyz, surf_xyz};
+  m->n_map[0] = n_corner;
+  m->n_map[1] = n_surf;
+  float* d_tmp = nullptr;
+  const size_t nmax = (size_t)std::max(n_corner, n_surf);
+  if (nmax > 0) CU(cudaMalloc(&d_tmp, 3 * nmax * sizeof(float)));
+  for (int s = 0; s < 2; s++) {
+    const size_t n = (size_t)m->n_map[s];
+    if (n == 0) continue;
+    CU(cudaMalloc(&m->d_map[s], 3 * n * sizeof(float)));
+    CU(cudaMemcpyAsync(d_tmp, src[s], 3 * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    assoc_dev::soa_kernel<<<(int)std::min<size_t>((n + 255) / 256, 1184), 256, 0, m->stream>>>(
+        d_tmp, (int)n, m->d_map[s], m->d_map[s] + n, m->d_map[s] + 2 * n);
+    m->launches++;
+  }
+  CU(cudaStreamSynchronize(m->stream));
+  cudaFree(d_tmp);
+  CU(cudaGetLastError());
+  *out = m.release();
+  return CLIC_OK;
+}
+
+CLIC_API void clic_feature_map_destroy(clic_feature_map* m) {
+  if (!m || m->magic != 0x4d41504cu) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->d_map[0]);
+  cudaFree(m->d_map[1]);
+  cudaFree(m->d_scratch);
+  for (auto e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  m->magic = 0;
+  delete m;
+}
+
+CLIC_API int64_t clic_correspondence_capacity(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t step = n / 1500 + 1;  // lidar_odometry.cpp:501, 575
+  return (n + step - 1) / step;
+}
+
+CLIC_API int clic_feature_map_launches(clic_feature_map* m, int64_t* launches, double* last_kernel_ms) {
+  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
+  if (launches) *launches = m->launches;
+  if (last_kernel_ms) {
+    *last_kernel_ms = 0;
+    if (m->last[0].n_q + m->last[1].n_q > 0) {
+      float ms = 0;
+      CU(cudaSetDevice(m->device));
+      CU(cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]));
+      *last_kernel_ms = ms;
+    }
+  }
+  return CLIC_OK;
+}
+
+CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, const float* corner_xyz_L,
+                                      const double* corner_t, const float* corner_xyz_M, int64_t n_surf,
+                                      const float* surf_xyz_L, const double* surf_t, const float* surf_xyz_M,
+                                      int64_t* n_lines, double* line_t, double* line_point, double* line_geo,
+                                      int64_t* line_src, int64_t* n_planes, double* plane_t, double* plane_point,
+                                      double* plane_geo, int64_t* plane_src) {
+  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
+  if (!n_lines || !n_planes) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  *n_lines = *n_planes = 0;
+  if ((n_corner > 0 && (!corner_xyz_L || !corner_t || !corner_xyz_M || !line_t || !line_point || !line_geo)) ||
+      (n_surf > 0 && (!surf_xyz_L || !surf_t || !surf_xyz_M || !plane_t || !plane_point || !plane_geo)))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  CU(cudaSetDevice(m->device));
+  AssocSide side[2];
+  side[0].n_feat = (n_corner > 0 && m->n_map[0] > 10 /* ":502" */) ? n_corner : 0;
+  side[0].geo_w = 6;
+  side[1].n_feat = (n_surf > 0 && m->n_map[1] > 0) ? n_surf : 0;
+  side[1].geo_w = 4;
+  size_t total = 256;  // two counters in front
+  int max_groups = 0, max_slices = 0, max_q = 0;
+  for (int s = 0; s < 2; s++) {
+    AssocSide& S = side[s];
+    S.step = S.n_feat / 1500 + 1;
+    S.n_q = (S.n_feat + S.step - 1) / S.step;
+    if (S.n_q > INT32_MAX / 8) return fail(CLIC_ERR_BAD_ARGUMENT, "too many features");
+    if (S.n_q > 0) {
+      // cut the map so that the grid holds about 4 CTAs per SM; a slice is at least one shared-memory tile
+      const int groups = (int)((S.n_q + assoc_dev::kQPC - 1) / assoc_dev::kQPC);
+      const int tiles = (int)((m->n_map[s] + assoc_dev::kTile - 1) / assoc_dev::kTile);
+      S.n_slices = std::max(1, std::min(tiles, (4 * m->n_sm + groups - 1) / groups));
+      const int tiles_per_slice = (tiles + S.n_slices - 1) / S.n_slices;
+      S.slice_len = tiles_per_slice * assoc_dev::kTile;
+      S.n_slices = (int)((m->n_map[s] + S.slice_len - 1) / S.slice_len);
+      max_groups = std::max(max_groups, groups);
+      max_slices = std::max(max_slices, S.n_slices);
+      max_q = std::max(max_q, (int)S.n_q);
+    }
+    total = assoc_plan(S, total);
+  }
+  if (total > m->scratch_bytes) {
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(m->d_scratch);
+    m->d_scratch = nullptr;
+    m->scratch_bytes = 0;
+    CU(cudaMalloc(&m->d_scratch, total + total / 4));
+    m->scratch_bytes = total + total / 4;
+  }
+  char* base = (char*)m->d_scratch;
+  long long* d_count = (long long*)base;
+  CU(cudaMemsetAsync(d_count, 0, 2 * sizeof(long long), m->stream));
+  const float* in_M[2] = {corner_xyz_M, surf_xyz_M};
+  const float* in_L[2] = {corner_xyz_L, surf_xyz_L};
+  const double* in_t[2] = {corner_t, surf_t};
+  assoc_dev::AssocJobs jobs;
+  for (int s = 0; s < 2; s++) {
+    const AssocSide& S = side[s];
+    assoc_dev::AssocJob& J = jobs.j[s];
+    const size_t nm = (size_t)m->n_map[s];
+    J.mx = m->d_map[s];
+    J.my = m->d_map[s] + nm;
+    J.mz = m->d_map[s] + 2 * nm;
+    J.n_map = (int)nm;
+    J.xyz_M = (const float*)(base + S.o_xyzM);
+    J.xyz_L = (const float*)(base + S.o_xyzL);
+    J.t = (const double*)(base + S.o_t);
+    J.step = S.step;
+    J.n_q = (int)S.n_q;
+    J.is_surface = s;
+    J.n_slices = S.n_slices;
+    J.slice_len = S.slice_len;
+    J.part_d = (float*)(base + S.o_part_d);
+    J.part_i = (int*)(base + S.o_part_i);
+    J.valid = (unsigned char*)(base + S.o_valid);
+    J.geo = (double*)(base + S.o_geo);
+    J.nn_idx = (int*)(base + S.o_nn);
+    J.geo_w = S.geo_w;
+    J.out_t = (double*)(base + S.o_out_t);
+    J.out_point = (double*)(base + S.o_out_pt);
+    J.out_geo = (double*)(base + S.o_out_geo);
+    J.out_src = (long long*)(base + S.o_out_src);
+    J.count = d_count + s;
+    if (S.n_q == 0) continue;
+    CU(cudaMemcpyAsync(base + S.o_xyzM, in_M[s], (size_t)3 * S.n_feat * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(base + S.o_xyzL, in_L[s], (size_t)3 * S.n_feat * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(base + S.o_t, in_t[s], (size_t)S.n_feat * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  }
+  m->last[0] = side[0];
+  m->last[1] = side[1];
+  if (max_q == 0) return CLIC_OK;
+  CU(cudaEventRecord(m->ev[0], m->stream));
+  assoc_dev::knn5_partial_kernel<<<dim3(max_groups, max_slices, 2), assoc_dev::kWarps * 32, 0, m->stream>>>(jobs);
+  assoc_dev::merge_fit_kernel<<<dim3((max_q + assoc_dev::kWarps - 1) / assoc_dev::kWarps, 1, 2), assoc_dev::kWarps * 32, 0,
+                                m->stream>>>(jobs);
+  assoc_dev::compact_kernel<<<dim3(1, 1, 2), 1024, 0, m->stream>>>(jobs);
+  m->launches += 3;
+  CU(cudaEventRecord(m->ev[1], m->stream));
+  long long h_count[2] = {0, 0};
+  CU(cudaMemcpyAsync(h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaGetLastError());
+  double* out_t[2] = {line_t, plane_t};
+  double* out_pt[2] = {line_point, plane_point};
+  double* out_geo[2] = {line_geo, plane_geo};
+  int64_t* out_src[2] = {line_src, plane_src};
+  for (int s = 0; s < 2; s++) {
+    const AssocSide& S = side[s];
+    const size_t c = (size_t)h_count[s];
+    if (c == 0) continue;
+    CU(cudaMemcpyAsync(out_t[s], base + S.o_out_t, c * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaMemcpyAsync(out_pt[s], base + S.o_out_pt, 3 * c * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaMemcpyAsync(out_geo[s], base + S.o_out_geo, S.geo_w * c * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    if (out_src[s])
+      CU(cudaMemcpyAsync(out_src[s], base + S.o_out_src, c * sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
+  }
+  CU(cudaStreamSynchronize(m->stream));
+  *n_lines = h_count[0];
+  *n_planes = h_count[1];
+  return CLIC_OK;
+}
+
+CLIC_API int clic_correspondence_neighbours(clic_feature_map* m, int32_t type, int64_t capacity, int32_t* idx /*5n*/,
+                                            int64_t* n_out) {
+  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
+  if (type < 0 || type > 1 || !n_out) return fail(CLIC_ERR_BAD_ARGUMENT, "bad argument");
+  const AssocSide& S = m->last[type];
+  *n_out = S.n_q;
+  if (S.n_q == 0 || !idx) return CLIC_OK;
+  if (capacity < S.n_q) return fail(CLIC_ERR_BAD_ARGUMENT, "capacity too small");
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(idx, (char*)m->d_scratch + S.o_nn, (size_t)5 * S.n_q * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
   return CLIC_OK;
 }
 

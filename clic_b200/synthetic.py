@@ -365,3 +365,80 @@ def config(c, scale=1.0, seed=None):
         return make_window(10, n(1_000_000), n(200_000), n_landmarks=n(2000), obs_per_landmark=10,
                            line_fraction=0.3, seed=seed, name="C5")
     raise ValueError(c)
+
+
+# ---- LiDAR association scenes: a box room with poles, sampled as a feature map and as a scan ----
+@dataclass
+class FeatureScene:
+    map_surf: np.ndarray      # (Ms, 3) float32, map frame
+    map_corner: np.ndarray    # (Mc, 3) float32
+    surf_L: np.ndarray        # (Ns, 3) float32, scan surface features in the LiDAR frame
+    surf_M: np.ndarray        # the same features in the map frame (lf_cur_in_M)
+    surf_t: np.ndarray        # (Ns,) double timestamps
+    corner_L: np.ndarray
+    corner_M: np.ndarray
+    corner_t: np.ndarray
+
+
+def _room_surface(rng, n, size, noise):
+    """Points on the six faces of an axis-aligned box [0,size] with Gaussian noise along the face normal."""
+    sx, sy, sz = size
+    areas = np.array([sy * sz, sy * sz, sx * sz, sx * sz, sx * sy, sx * sy])
+    face = rng.choice(6, n, p=areas / areas.sum())
+    p = rng.uniform(0, 1, (n, 3)) * np.array(size)
+    axis = face // 2
+    side = face % 2
+    p[np.arange(n), axis] = side * np.array(size)[axis] + rng.normal(0, noise, n)
+    return p
+
+
+def _room_edges(rng, n, size, noise, n_poles=6):
+    """Points on the 12 box edges and on a few vertical poles inside the room."""
+    sx, sy, sz = size
+    segs = []
+    for a in (0, sx):
+        for b in (0, sy):
+            segs.append(((a, b, 0), (a, b, sz)))
+    for a in (0, sx):
+        for c in (0, sz):
+            segs.append(((a, 0, c), (a, sy, c)))
+    for b in (0, sy):
+        for c in (0, sz):
+            segs.append(((0, b, c), (sx, b, c)))
+    prng = np.random.default_rng(77)
+    for _ in range(n_poles):
+        x, y = prng.uniform(2, sx - 2), prng.uniform(2, sy - 2)
+        segs.append(((x, y, 0), (x, y, sz)))
+    segs = np.array(segs, dtype=np.float64)
+    length = np.linalg.norm(segs[:, 1] - segs[:, 0], axis=1)
+    which = rng.choice(len(segs), n, p=length / length.sum())
+    u = rng.uniform(0, 1, (n, 1))
+    return segs[which, 0] * (1 - u) + segs[which, 1] * u + rng.normal(0, noise, (n, 3))
+
+
+def make_feature_scene(n_map_surf=20000, n_map_corner=3000, n_surf=1200, n_corner=400, seed=0, size=(20.0, 16.0, 6.0),
+                       noise=0.01, outlier_fraction=0.05, negative_time_fraction=0.02):
+    """A feature map and one scan of the same room.  The scan's map-frame copy carries a small pose error (what the
+    association sees between the two inner iterations); a few features are far from the map, a few carry the
+    negative timestamp the reference skips."""
+    rng = np.random.default_rng(20230215 + seed)
+    map_surf = _room_surface(rng, n_map_surf, size, noise).astype(np.float32)
+    map_corner = _room_edges(rng, n_map_corner, size, noise).astype(np.float32)
+    q_err = so3_exp(np.array([0.002, -0.001, 0.003]))
+    p_err = np.array([0.02, -0.015, 0.01])
+    q_LtoM = so3_exp(np.array([0.1, -0.05, 0.7]))
+    p_LinM = np.array([9.0, 7.5, 1.5])
+
+    def scan(pts):
+        n = len(pts)
+        out = rng.uniform(0, 1, n) < outlier_fraction
+        pts = pts + out[:, None] * rng.normal(0, 3.0, (n, 3))
+        in_M = qrot(np.broadcast_to(q_err, (n, 4)), pts) + p_err
+        in_L = qrot(np.broadcast_to(qconj(q_LtoM), (n, 4)), pts - p_LinM)
+        t = np.sort(rng.uniform(0.0, 0.1, n))
+        t[rng.uniform(0, 1, n) < negative_time_fraction] = -1.0
+        return in_L.astype(np.float32), in_M.astype(np.float32), t
+
+    sL, sM, st = scan(_room_surface(rng, n_surf, size, noise))
+    cL, cM, ct = scan(_room_edges(rng, n_corner, size, noise))
+    return FeatureScene(map_surf, map_corner, sL, sM, st, cL, cM, ct)

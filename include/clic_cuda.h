@@ -262,6 +262,49 @@ CLIC_API int clic_undistort_scan(clic_estimator* h, int64_t n, const double* t_s
                                  const double S_LtoI[4], const double p_LinI[3], double t_offset_ns, int32_t in_global,
                                  double target_t_s, float* xyz_out /*3n*/, int64_t* n_invalid);
 
+/* ---- the producer of the path's input: LiDAR data association ----
+ * LidarOdometry::SetTargetMap (src/lidar_odometry/lidar_odometry.cpp:472-481): the down-sampled feature map the scan is
+ * matched against.  Points are PosPoint x,y,z floats.  corner_xyz may be NULL / n_corner 0 (use_corner_feature false). */
+typedef struct clic_feature_map clic_feature_map;
+CLIC_API int clic_feature_map_create(const float* surf_xyz /*3n*/, int64_t n_surf, const float* corner_xyz /*3n*/,
+                                     int64_t n_corner, clic_feature_map** out);
+CLIC_API void clic_feature_map_destroy(clic_feature_map* m);
+
+/* LidarOdometry::FindCorrespondence (lidar_odometry.cpp:483-657).  For every step-th feature of the current scan
+ * (step = n / 1500 + 1, ":501, :575"): exact 5 nearest map points of the feature expressed in the map frame (xyz_M, the
+ * output of clic_undistort_scan) by squared float distance (pcl::KdTreeFLANN::nearestKSearch, exact search); the
+ * feature is skipped when the 5th is farther than 1 m^2 (":508, :584").
+ *  corner: centroid (double) and float covariance of the 5 points, float symmetric eigen-decomposition
+ *          (cv::eigen, ":511-563"); kept when lambda_0 > 3 lambda_1 as a Line record: geo_point = centroid,
+ *          geo_normal = principal direction.  Only when the corner map holds more than 10 points (":502").
+ *  surface: skipped when its timestamp < 0 (":577"); float least squares A x = -1 over the 5 points by Householder QR
+ *          with column pivoting (":586-603"), plane (x, 1) / |x|; kept when all 5 points lie within 0.2 m of it
+ *          (":616-625") as a Plane record geo_plane = (n, d).
+ * Outputs are the type-uniform batches clic_add_loam_lines / clic_add_loam_planes take, in the reference's order
+ * (corner features first, each in scan order): t_point, point (the feature in the LiDAR frame, xyz_L, as double),
+ * geometry, and the index of the source feature.  Each output array must hold ceil(n / step) records
+ * (clic_correspondence_capacity).  Arithmetic: float / double exactly where the reference uses each. */
+CLIC_API int64_t clic_correspondence_capacity(int64_t n_features);
+CLIC_API int clic_find_correspondence(clic_feature_map* m,
+                                      int64_t n_corner, const float* corner_xyz_L, const double* corner_t,
+                                      const float* corner_xyz_M,
+                                      int64_t n_surf, const float* surf_xyz_L, const double* surf_t,
+                                      const float* surf_xyz_M,
+                                      int64_t* n_lines, double* line_t, double* line_point /*3n*/,
+                                      double* line_geo /*6n: geo_point, geo_normal*/, int64_t* line_src,
+                                      int64_t* n_planes, double* plane_t, double* plane_point /*3n*/,
+                                      double* plane_geo /*4n: n.x n.y n.z d*/, int64_t* plane_src);
+
+/* Parity probe: the 5 neighbour indices (nearest first; ties by smaller index) of every selected feature of the last
+ * clic_find_correspondence call on this map; type 0 corner, 1 surface; -1 rows for features gated out before the
+ * search; INT32_MAX for a neighbour outside the 1 m^2 gate (it cannot change the outcome, and is not searched for).
+ * idx holds 5 * ceil(n / step) entries. */
+CLIC_API int clic_correspondence_neighbours(clic_feature_map* m, int32_t type, int64_t capacity, int32_t* idx,
+                                            int64_t* n_out);
+/* Kernels launched on behalf of this map so far, and the device time (CUDA events on the map's stream) of the kernels
+ * of the last clic_find_correspondence call; either pointer may be NULL. */
+CLIC_API int clic_feature_map_launches(clic_feature_map* m, int64_t* launches, double* last_kernel_ms);
+
 /* SaveMarginalizationInfo (trajectory_estimator.cpp:234-249) = preMarginalize + marginalize
  * (marginalization_factor.cpp:94-116,150-276) over the factors added with marg_* = 1. */
 CLIC_API int clic_marginalize(clic_estimator* h, clic_prior** out);

@@ -25,6 +25,7 @@
 
 #include "../include/clic_cuda.h"
 #include "factors.hpp"
+#include "association.hpp"
 
 using namespace oracle;
 
@@ -1433,6 +1434,107 @@ CLIC_API int clic_query_poses(clic_estimator* E, int64_t n, const double* t_s, c
     p_out[3 * i] = p[0]; p_out[3 * i + 1] = p[1]; p_out[3 * i + 2] = p[2];
   }
   if (n_invalid) *n_invalid = bad;
+  return CLIC_OK;
+}
+
+// ---- LiDAR data association, see association.hpp ----
+struct clic_feature_map {
+  std::vector<float> surf, corner;
+  std::vector<int32_t> nn[2];
+};
+
+CLIC_API int clic_feature_map_create(const float* surf_xyz, int64_t n_surf, const float* corner_xyz, int64_t n_corner,
+                                     clic_feature_map** out) {
+  if (!out || n_surf < 0 || n_corner < 0 || (n_surf > 0 && !surf_xyz) || (n_corner > 0 && !corner_xyz))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bad feature map");
+  auto* m = new clic_feature_map;
+  m->surf.assign(surf_xyz, surf_xyz + 3 * n_surf);
+  if (n_corner > 0) m->corner.assign(corner_xyz, corner_xyz + 3 * n_corner);
+  *out = m;
+  return CLIC_OK;
+}
+CLIC_API void clic_feature_map_destroy(clic_feature_map* m) { delete m; }
+
+CLIC_API int64_t clic_correspondence_capacity(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t step = n / 1500 + 1;  // lidar_odometry.cpp:501, 575
+  return (n + step - 1) / step;
+}
+
+CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, const float* corner_xyz_L,
+                                      const double* corner_t, const float* corner_xyz_M, int64_t n_surf,
+                                      const float* surf_xyz_L, const double* surf_t, const float* surf_xyz_M,
+                                      int64_t* n_lines, double* line_t, double* line_point, double* line_geo,
+                                      int64_t* line_src, int64_t* n_planes, double* plane_t, double* plane_point,
+                                      double* plane_geo, int64_t* plane_src) {
+  if (!m || !n_lines || !n_planes) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  *n_lines = *n_planes = 0;
+  m->nn[0].clear();
+  m->nn[1].clear();
+  if ((n_corner > 0 && (!corner_xyz_L || !corner_t || !corner_xyz_M || !line_t || !line_point || !line_geo)) ||
+      (n_surf > 0 && (!surf_xyz_L || !surf_t || !surf_xyz_M || !plane_t || !plane_point || !plane_geo)))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  const int64_t n_map_c = (int64_t)m->corner.size() / 3, n_map_s = (int64_t)m->surf.size() / 3;
+  float pts[5][3];
+  auto gather = [&](const std::vector<float>& map, const assoc::Neighbours& nb) {
+    for (int j = 0; j < 5; j++)
+      for (int c = 0; c < 3; c++) pts[j][c] = map[3 * (size_t)nb.idx[j] + c];
+  };
+  if (n_corner > 0 && n_map_c > 10) {  // lidar_odometry.cpp:502
+    const int64_t step = n_corner / 1500 + 1;
+    for (int64_t i = 0; i < n_corner; i += step) {
+      const assoc::Neighbours nb = assoc::knn5(m->corner.data(), n_map_c, corner_xyz_M + 3 * i);
+      for (int k = 0; k < 5; k++) m->nn[0].push_back(nb.d2[k] <= 1.0f ? nb.idx[k] : INT32_MAX);
+      if (!(nb.d2[4] <= 1.0f)) continue;  // ":508"
+      gather(m->corner, nb);
+      double cp[3], dir[3];
+      if (!assoc::fit_line(pts, cp, dir)) continue;
+      const int64_t o = (*n_lines)++;
+      line_t[o] = corner_t[i];
+      for (int c = 0; c < 3; c++) {
+        line_point[3 * o + c] = (double)corner_xyz_L[3 * i + c];
+        line_geo[6 * o + c] = cp[c];
+        line_geo[6 * o + 3 + c] = dir[c];
+      }
+      if (line_src) line_src[o] = i;
+    }
+  }
+  if (n_surf > 0) {
+    const int64_t step = n_surf / 1500 + 1;
+    for (int64_t i = 0; i < n_surf; i += step) {
+      if (surf_t[i] < 0) {  // ":577"
+        m->nn[1].insert(m->nn[1].end(), 5, -1);
+        continue;
+      }
+      const assoc::Neighbours nb = assoc::knn5(m->surf.data(), n_map_s, surf_xyz_M + 3 * i);
+      for (int k = 0; k < 5; k++) m->nn[1].push_back(nb.d2[k] <= 1.0f ? nb.idx[k] : INT32_MAX);
+      if (!(nb.d2[4] <= 1.0f)) continue;  // ":584"; fewer than 5 map points leaves +inf here (":593")
+      gather(m->surf, nb);
+      double pl[4];
+      if (!assoc::fit_plane(pts, pl)) continue;
+      const int64_t o = (*n_planes)++;
+      plane_t[o] = surf_t[i];
+      for (int c = 0; c < 3; c++) plane_point[3 * o + c] = (double)surf_xyz_L[3 * i + c];
+      for (int c = 0; c < 4; c++) plane_geo[4 * o + c] = pl[c];
+      if (plane_src) plane_src[o] = i;
+    }
+  }
+  return CLIC_OK;
+}
+
+CLIC_API int clic_correspondence_neighbours(clic_feature_map* m, int32_t type, int64_t capacity, int32_t* idx,
+                                            int64_t* n_out) {
+  if (!m || type < 0 || type > 1 || !n_out) return fail(CLIC_ERR_BAD_ARGUMENT, "bad argument");
+  const int64_t n = (int64_t)m->nn[type].size() / 5;
+  *n_out = n;
+  if (n == 0 || !idx) return CLIC_OK;
+  if (capacity < n) return fail(CLIC_ERR_BAD_ARGUMENT, "capacity too small");
+  std::copy(m->nn[type].begin(), m->nn[type].end(), idx);
+  return CLIC_OK;
+}
+CLIC_API int clic_feature_map_launches(clic_feature_map* m, int64_t* launches, double* last_kernel_ms) {
+  if (launches) *launches = 0;
+  if (last_kernel_ms) *last_kernel_ms = 0;
   return CLIC_OK;
 }
 
