@@ -143,6 +143,9 @@ PROTOTYPES = {
                                            C.c_int64, c_float_p, c_double_p, c_float_p,
                                            c_int64_p, c_double_p, c_double_p, c_double_p, c_int64_p,
                                            c_int64_p, c_double_p, c_double_p, c_double_p, c_int64_p]),
+    "clic_add_loam_from_scan": (C.c_int, [H, H, C.c_int64, c_float_p, c_double_p, C.c_int64, c_float_p, c_double_p,
+                                          c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32,
+                                          C.c_double, C.c_int32, c_int64_p, c_int64_p, c_int64_p]),
     "clic_correspondence_neighbours": (C.c_int, [H, C.c_int32, C.c_int64, c_int32_p, c_int64_p]),
     "clic_feature_map_launches": (C.c_int, [H, c_int64_p, c_double_p]),
     "clic_marginalize": (C.c_int, [H, C.POINTER(H)]),

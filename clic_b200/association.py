@@ -72,6 +72,21 @@ class FeatureMap:
         a, b = nl.value, npl.value
         return Correspondences(lt[:a], lp[:a], lg[:a], ls[:a], pt[:b], pp[:b], pg[:b], ps[:b])
 
+    def AddLoamFromScan(self, est, corner_xyz, corner_t, surf_xyz, surf_t, S_GtoM, p_GinM, S_LtoI, p_LinI, weight,
+                        cor_downsample=1, t_offset_ns=0.0, marg_this_factor=False):
+        """GetLoamFeatureAssociation + one AddLoamMeasurementAnalytic per kept correspondence, on the device:
+        returns (n_lines, n_planes, n_dropped)."""
+        cL, sL = _f32(corner_xyz).reshape(-1, 3), _f32(surf_xyz).reshape(-1, 3)
+        ct = np.ascontiguousarray(corner_t, dtype=np.float64)
+        st = np.ascontiguousarray(surf_t, dtype=np.float64)
+        f = [np.ascontiguousarray(a, dtype=np.float64) for a in (S_GtoM, p_GinM, S_LtoI, p_LinI)]
+        nl, npl, nd = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _check(self.lib, self.lib.clic_add_loam_from_scan(
+            est.h, self.h, len(ct), _fp(cL), dptr(ct), len(st), _fp(sL), dptr(st), dptr(f[0]), dptr(f[1]), dptr(f[2]),
+            dptr(f[3]), float(t_offset_ns), int(cor_downsample), float(weight), int(bool(marg_this_factor)),
+            C.byref(nl), C.byref(npl), C.byref(nd)))
+        return nl.value, npl.value, nd.value
+
     def neighbours(self, kind):
         """(n_selected, 5) neighbour indices of the last call; kind 0 corner, 1 surface."""
         n = C.c_int64(0)

@@ -459,4 +459,115 @@ __global__ void __launch_bounds__(1024) compact_kernel(AssocJobs jobs) {
   if (threadIdx.x == 0) *C.count = running;
 }
 
+// LidarOdometry::GetLoamFeatureAssociation after FindCorrespondence (lidar_odometry.cpp:170-175, 660-671): the
+// correspondences — corner records first, then surface records — are sorted by t_point, every ds-th one is kept, and the
+// kept ones are added as factors one by one.  Here: one CTA compacts the valid records of both types into shared memory,
+// sorts them by (t_point, position in the unsorted list) with a bitonic network (the reference's std::sort leaves the
+// order of equal timestamps open; this is the stable choice), keeps every ds-th and writes them out split by type, each
+// batch still time-sorted — the layout the factor kernels want.  At most 1500 records per type exist by construction.
+constexpr int kSortMax = 4096;
+struct SortedOut {
+  double* t[2];        // [0] lines, [1] planes
+  double* point[2];    // 3 per record
+  double* geo[2];      // 6 / 4 per record
+  long long* src[2];
+  long long* count;    // 2
+};
+
+__global__ void __launch_bounds__(1024) sort_downsample_kernel(AssocJobs jobs, int ds, SortedOut out) {
+  extern __shared__ double s_key[];               // kSortMax doubles
+  int* s_ord = (int*)(s_key + kSortMax);          // kSortMax ints: (type << 16) | q, i.e. the unsorted-list order
+  __shared__ int warp_tot[32];
+  __shared__ int running, kept_run[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { running = 0; kept_run[0] = kept_run[1] = 0; }
+  __syncthreads();
+  for (int type = 0; type < 2; type++) {
+    const AssocJob& J = jobs.j[type];
+    for (int base = 0; base < J.n_q; base += 1024) {
+      const int q = base + threadIdx.x;
+      const bool v = q < J.n_q && J.valid[q];
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) warp_tot[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < 32; w++) {
+        const int c = warp_tot[w];
+        if (w < warp) before += c;
+        total += c;
+      }
+      const int off = running + before + __popc(m & ((1u << lane) - 1u));
+      if (v && off < kSortMax) {
+        s_key[off] = J.t[(long long)q * J.step];
+        s_ord[off] = (type << 16) | q;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) running += total;
+      __syncthreads();
+    }
+  }
+  const int n = min(running, kSortMax);
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += blockDim.x) {
+    s_key[i] = __longlong_as_double(0x7ff0000000000000LL);
+    s_ord[i] = INT32_MAX;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const double a = s_key[i], b = s_key[p];
+          const int oa = s_ord[i], ob = s_ord[p];
+          const bool up = (i & k) == 0;
+          const bool gt = a > b || (a == b && oa > ob);
+          if (gt == up) {
+            s_key[i] = b; s_key[p] = a;
+            s_ord[i] = ob; s_ord[p] = oa;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // keep every ds-th of the sorted list; split by type with an order-preserving scan
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const bool kept = i < n && (i % ds) == 0;
+    const int ord = kept ? s_ord[i] : 0;
+    const int type = ord >> 16;
+    const unsigned m0 = __ballot_sync(0xffffffffu, kept && type == 0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, kept && type == 1);
+    if (lane == 0) warp_tot[warp] = __popc(m0) | (__popc(m1) << 8);
+    __syncthreads();
+    int before0 = 0, before1 = 0, tot0 = 0, tot1 = 0;
+#pragma unroll
+    for (int w = 0; w < 32; w++) {
+      const int c0 = warp_tot[w] & 0xff, c1 = warp_tot[w] >> 8;
+      if (w < warp) { before0 += c0; before1 += c1; }
+      tot0 += c0;
+      tot1 += c1;
+    }
+    if (kept) {
+      const AssocJob& J = jobs.j[type];
+      const int q = ord & 0xffff;
+      const unsigned below = (1u << lane) - 1u;
+      const long long o = type == 0 ? kept_run[0] + before0 + __popc(m0 & below) : kept_run[1] + before1 + __popc(m1 & below);
+      const long long feat = (long long)q * J.step;
+      out.t[type][o] = s_key[i];
+#pragma unroll
+      for (int c = 0; c < 3; c++) out.point[type][3 * o + c] = (double)J.xyz_L[3 * feat + c];
+      for (int c = 0; c < J.geo_w; c++) out.geo[type][J.geo_w * o + c] = J.geo[6 * (size_t)q + c];
+      out.src[type][o] = feat;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { kept_run[0] += tot0; kept_run[1] += tot1; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out.count[0] = kept_run[0]; out.count[1] = kept_run[1]; }
+}
+
 }  // namespace assoc_dev

@@ -382,9 +382,9 @@ size_t loam_smem_bytes(int K) {
 }
 
 // End of an adder: the batch is complete on the copy stream when `ready` fires.
-int mark_ready(clic_estimator* E, StreamExec& ex) {
+int mark_ready(clic_estimator* E, StreamExec& ex, cudaStream_t producer = nullptr) {
   if (!ex.ready) CU(cudaEventCreateWithFlags(&ex.ready, cudaEventDisableTiming));
-  CU(cudaEventRecord(ex.ready, E->copy_stream));
+  CU(cudaEventRecord(ex.ready, producer ? producer : E->copy_stream));
   ex.ready_waited = false;
   ex.seq = ++E->add_seq;
   return CLIC_OK;
@@ -1486,7 +1486,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
-  if ((rc = mark_ready(E, B->ex))) return rc;
+  if ((rc = mark_ready(E, B->ex, cs))) return rc;
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1494,10 +1494,12 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
 
 namespace {
 // geo_kind 0: mixed (geo_type per feature, 6 geometry doubles each); 1: planes (4 doubles); 2: lines (6 doubles)
+// device_inputs: t_point / point / geo_type / geo already live on the device and were produced on stream `cs`
+// (clic_add_loam_from_scan); otherwise they are host arrays and go through the copy stream.
 int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t_point, const double* point,
                      const uint8_t* geo_type, const double* geo, const double S_GtoM[4], const double p_GinM[3],
                      const double S_LtoI[4], const double p_LinI[3], double weight, int32_t marg_this_factor,
-                     int64_t* n_dropped) {
+                     int64_t* n_dropped, bool device_inputs = false, cudaStream_t dev_stream = nullptr) {
   ScopedTrace trace("clic_add_loam_records");
   const int gstride = geo_kind == 1 ? 4 : 6;
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
@@ -1506,7 +1508,7 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
   if (!t_point || !point || (geo_kind == 0 && !geo_type) || !geo)
     return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_*: null array");
   CU(cudaSetDevice(E->device));
-  cudaStream_t cs = E->copy_stream;
+  cudaStream_t cs = device_inputs ? dev_stream : E->copy_stream;
   AllocScope alloc_scope(cs);
   std::unique_ptr<LoamBatch> B(new LoamBatch);
   // MeasuredTimeToNs(LiDARSensor): host-side scalar bounds in the reference's double arithmetic
@@ -1518,16 +1520,24 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
   }
   DevBuf &r_t = B->raw[0], &r_pt = B->raw[1], &r_type = B->raw[2], &r_geo = B->raw[3];
   int rc;
-  if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
-      (geo_kind == 0 && (rc = to_device(E, r_type, geo_type, n))) || (rc = to_device(E, r_geo, geo, gstride * n)))
-    return rc;
+  const double *in_t = t_point, *in_pt = point, *in_geo = geo;
+  const uint8_t* in_type = geo_type;
+  if (!device_inputs) {
+    if ((rc = to_device(E, r_t, t_point, n)) || (rc = to_device(E, r_pt, point, 3 * n)) ||
+        (geo_kind == 0 && (rc = to_device(E, r_type, geo_type, n))) || (rc = to_device(E, r_geo, geo, gstride * n)))
+      return rc;
+    in_t = r_t.as<double>();
+    in_pt = r_pt.as<double>();
+    in_type = r_type.as<uint8_t>();
+    in_geo = r_geo.as<double>();
+  }
   CU(B->t_ns.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
   for (int k = 0; k < gstride; k++) CU(B->g[k].ensure(n * sizeof(double)));
   if (geo_kind == 0) CU(B->type.ensure(n));
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
-      n, r_t.as<double>(), r_pt.as<double>(), geo_kind == 0 ? r_type.as<uint8_t>() : nullptr, r_geo.as<double>(), gstride,
+      n, in_t, in_pt, geo_kind == 0 ? in_type : nullptr, in_geo, gstride,
       geo_kind == 1 ? 1 : 0, ldq(S_LtoI), ldv(p_LinI), t_min, t_max,
       B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
       B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
@@ -2439,62 +2449,53 @@ CLIC_API int clic_feature_map_launches(clic_feature_map* m, int64_t* launches, d
   return CLIC_OK;
 }
 
-CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, const float* corner_xyz_L,
-                                      const double* corner_t, const float* corner_xyz_M, int64_t n_surf,
-                                      const float* surf_xyz_L, const double* surf_t, const float* surf_xyz_M,
-                                      int64_t* n_lines, double* line_t, double* line_point, double* line_geo,
-                                      int64_t* line_src, int64_t* n_planes, double* plane_t, double* plane_point,
-                                      double* plane_geo, int64_t* plane_src) {
-  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
-  if (!n_lines || !n_planes) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
-  *n_lines = *n_planes = 0;
-  if ((n_corner > 0 && (!corner_xyz_L || !corner_t || !corner_xyz_M || !line_t || !line_point || !line_geo)) ||
-      (n_surf > 0 && (!surf_xyz_L || !surf_t || !surf_xyz_M || !plane_t || !plane_point || !plane_geo)))
-    return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
-  CU(cudaSetDevice(m->device));
+namespace {
+struct AssocPlan {
   AssocSide side[2];
-  side[0].n_feat = (n_corner > 0 && m->n_map[0] > 10 /* ":502" */) ? n_corner : 0;
-  side[0].geo_w = 6;
-  side[1].n_feat = (n_surf > 0 && m->n_map[1] > 0) ? n_surf : 0;
-  side[1].geo_w = 4;
   size_t total = 256;  // two counters in front
   int max_groups = 0, max_slices = 0, max_q = 0;
+};
+// Stride, grid cut and scratch layout of one call: n_feat[0] corner features, n_feat[1] surface features.
+int assoc_plan_call(clic_feature_map* m, int64_t n_corner, int64_t n_surf, AssocPlan& P) {
+  P.side[0].n_feat = (n_corner > 0 && m->n_map[0] > 10 /* ":502" */) ? n_corner : 0;
+  P.side[0].geo_w = 6;
+  P.side[1].n_feat = (n_surf > 0 && m->n_map[1] > 0) ? n_surf : 0;
+  P.side[1].geo_w = 4;
   for (int s = 0; s < 2; s++) {
-    AssocSide& S = side[s];
+    AssocSide& S = P.side[s];
     S.step = S.n_feat / 1500 + 1;
     S.n_q = (S.n_feat + S.step - 1) / S.step;
-    if (S.n_q > INT32_MAX / 8) return fail(CLIC_ERR_BAD_ARGUMENT, "too many features");
     if (S.n_q > 0) {
-      // cut the map so that the grid holds about 4 CTAs per SM; a slice is at least one shared-memory tile
+      // cut the map so that the grid holds about 4 CTAs per SM; a slice is a whole number of shared-memory tiles
       const int groups = (int)((S.n_q + assoc_dev::kQPC - 1) / assoc_dev::kQPC);
       const int tiles = (int)((m->n_map[s] + assoc_dev::kTile - 1) / assoc_dev::kTile);
       S.n_slices = std::max(1, std::min(tiles, (4 * m->n_sm + groups - 1) / groups));
       const int tiles_per_slice = (tiles + S.n_slices - 1) / S.n_slices;
       S.slice_len = tiles_per_slice * assoc_dev::kTile;
       S.n_slices = (int)((m->n_map[s] + S.slice_len - 1) / S.slice_len);
-      max_groups = std::max(max_groups, groups);
-      max_slices = std::max(max_slices, S.n_slices);
-      max_q = std::max(max_q, (int)S.n_q);
+      P.max_groups = std::max(P.max_groups, groups);
+      P.max_slices = std::max(P.max_slices, S.n_slices);
+      P.max_q = std::max(P.max_q, (int)S.n_q);
     }
-    total = assoc_plan(S, total);
+    P.total = assoc_plan(S, P.total);
   }
-  if (total > m->scratch_bytes) {
-    CU(cudaStreamSynchronize(m->stream));
+  if (P.total > m->scratch_bytes) {
+    CU(cudaDeviceSynchronize());
     cudaFree(m->d_scratch);
     m->d_scratch = nullptr;
     m->scratch_bytes = 0;
-    CU(cudaMalloc(&m->d_scratch, total + total / 4));
-    m->scratch_bytes = total + total / 4;
+    CU(cudaMalloc(&m->d_scratch, P.total + P.total / 4));
+    m->scratch_bytes = P.total + P.total / 4;
   }
+  m->last[0] = P.side[0];
+  m->last[1] = P.side[1];
+  return CLIC_OK;
+}
+assoc_dev::AssocJobs assoc_jobs(clic_feature_map* m, const AssocPlan& P) {
   char* base = (char*)m->d_scratch;
-  long long* d_count = (long long*)base;
-  CU(cudaMemsetAsync(d_count, 0, 2 * sizeof(long long), m->stream));
-  const float* in_M[2] = {corner_xyz_M, surf_xyz_M};
-  const float* in_L[2] = {corner_xyz_L, surf_xyz_L};
-  const double* in_t[2] = {corner_t, surf_t};
   assoc_dev::AssocJobs jobs;
   for (int s = 0; s < 2; s++) {
-    const AssocSide& S = side[s];
+    const AssocSide& S = P.side[s];
     assoc_dev::AssocJob& J = jobs.j[s];
     const size_t nm = (size_t)m->n_map[s];
     J.mx = m->d_map[s];
@@ -2519,24 +2520,55 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
     J.out_point = (double*)(base + S.o_out_pt);
     J.out_geo = (double*)(base + S.o_out_geo);
     J.out_src = (long long*)(base + S.o_out_src);
-    J.count = d_count + s;
+    J.count = (long long*)base + s;
+  }
+  return jobs;
+}
+// The search and the fits: valid / geo / nn_idx of every selected feature.
+void assoc_search(clic_feature_map* m, const AssocPlan& P, const assoc_dev::AssocJobs& jobs, cudaStream_t st) {
+  assoc_dev::knn5_partial_kernel<<<dim3(P.max_groups, P.max_slices, 2), assoc_dev::kWarps * 32, 0, st>>>(jobs);
+  assoc_dev::merge_fit_kernel<<<dim3((P.max_q + assoc_dev::kWarps - 1) / assoc_dev::kWarps, 1, 2), assoc_dev::kWarps * 32, 0,
+                                st>>>(jobs);
+  m->launches += 2;
+}
+}  // namespace
+
+CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, const float* corner_xyz_L,
+                                      const double* corner_t, const float* corner_xyz_M, int64_t n_surf,
+                                      const float* surf_xyz_L, const double* surf_t, const float* surf_xyz_M,
+                                      int64_t* n_lines, double* line_t, double* line_point, double* line_geo,
+                                      int64_t* line_src, int64_t* n_planes, double* plane_t, double* plane_point,
+                                      double* plane_geo, int64_t* plane_src) {
+  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
+  if (!n_lines || !n_planes) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  *n_lines = *n_planes = 0;
+  if ((n_corner > 0 && (!corner_xyz_L || !corner_t || !corner_xyz_M || !line_t || !line_point || !line_geo)) ||
+      (n_surf > 0 && (!surf_xyz_L || !surf_t || !surf_xyz_M || !plane_t || !plane_point || !plane_geo)))
+    return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  CU(cudaSetDevice(m->device));
+  AssocPlan P;
+  int rc = assoc_plan_call(m, n_corner, n_surf, P);
+  if (rc) return rc;
+  if (P.max_q == 0) return CLIC_OK;
+  char* base = (char*)m->d_scratch;
+  const float* in_M[2] = {corner_xyz_M, surf_xyz_M};
+  const float* in_L[2] = {corner_xyz_L, surf_xyz_L};
+  const double* in_t[2] = {corner_t, surf_t};
+  for (int s = 0; s < 2; s++) {
+    const AssocSide& S = P.side[s];
     if (S.n_q == 0) continue;
     CU(cudaMemcpyAsync(base + S.o_xyzM, in_M[s], (size_t)3 * S.n_feat * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     CU(cudaMemcpyAsync(base + S.o_xyzL, in_L[s], (size_t)3 * S.n_feat * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     CU(cudaMemcpyAsync(base + S.o_t, in_t[s], (size_t)S.n_feat * sizeof(double), cudaMemcpyHostToDevice, m->stream));
   }
-  m->last[0] = side[0];
-  m->last[1] = side[1];
-  if (max_q == 0) return CLIC_OK;
+  const assoc_dev::AssocJobs jobs = assoc_jobs(m, P);
   CU(cudaEventRecord(m->ev[0], m->stream));
-  assoc_dev::knn5_partial_kernel<<<dim3(max_groups, max_slices, 2), assoc_dev::kWarps * 32, 0, m->stream>>>(jobs);
-  assoc_dev::merge_fit_kernel<<<dim3((max_q + assoc_dev::kWarps - 1) / assoc_dev::kWarps, 1, 2), assoc_dev::kWarps * 32, 0,
-                                m->stream>>>(jobs);
+  assoc_search(m, P, jobs, m->stream);
   assoc_dev::compact_kernel<<<dim3(1, 1, 2), 1024, 0, m->stream>>>(jobs);
-  m->launches += 3;
+  m->launches += 1;
   CU(cudaEventRecord(m->ev[1], m->stream));
   long long h_count[2] = {0, 0};
-  CU(cudaMemcpyAsync(h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaMemcpyAsync(h_count, base, sizeof(h_count), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
   CU(cudaGetLastError());
   double* out_t[2] = {line_t, plane_t};
@@ -2544,7 +2576,7 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
   double* out_geo[2] = {line_geo, plane_geo};
   int64_t* out_src[2] = {line_src, plane_src};
   for (int s = 0; s < 2; s++) {
-    const AssocSide& S = side[s];
+    const AssocSide& S = P.side[s];
     const size_t c = (size_t)h_count[s];
     if (c == 0) continue;
     CU(cudaMemcpyAsync(out_t[s], base + S.o_out_t, c * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -2556,6 +2588,86 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
   CU(cudaStreamSynchronize(m->stream));
   *n_lines = h_count[0];
   *n_planes = h_count[1];
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int64_t n_corner, const float* corner_xyz,
+                                     const double* corner_t, int64_t n_surf, const float* surf_xyz, const double* surf_t,
+                                     const double S_GtoM[4], const double p_GinM[3], const double S_LtoI[4],
+                                     const double p_LinI[3], double t_offset_ns, int32_t cor_downsample, double weight,
+                                     int32_t marg_this_factor, int64_t* n_lines, int64_t* n_planes, int64_t* n_dropped) {
+  ScopedTrace trace("clic_add_loam_from_scan");
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!m || m->magic != 0x4d41504cu) return fail(CLIC_ERR_BAD_HANDLE, "bad feature map");
+  if (n_lines) *n_lines = 0;
+  if (n_planes) *n_planes = 0;
+  if (n_dropped) *n_dropped = 0;
+  if ((n_corner > 0 && (!corner_xyz || !corner_t)) || (n_surf > 0 && (!surf_xyz || !surf_t)) || !S_GtoM || !p_GinM ||
+      !S_LtoI || !p_LinI || cor_downsample < 1)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bad argument");
+  if (m->device != E->device) return fail(CLIC_ERR_BAD_ARGUMENT, "feature map lives on another device");
+  CU(cudaSetDevice(E->device));
+  cudaStream_t st = E->stream;
+  AllocScope alloc_scope(st);
+  AssocPlan P;
+  int rc = assoc_plan_call(m, n_corner, n_surf, P);
+  if (rc) return rc;
+  if (P.max_q == 0) return CLIC_OK;
+  char* base = (char*)m->d_scratch;
+  const float* in_L[2] = {corner_xyz, surf_xyz};
+  const double* in_t[2] = {corner_t, surf_t};
+  const PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
+  const size_t smem = window_smem_doubles(E->K) * sizeof(double);
+  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), st));
+  for (int s = 0; s < 2; s++) {
+    const AssocSide& S = P.side[s];
+    if (S.n_q == 0) continue;
+    CU(cudaMemcpyAsync(base + S.o_xyzL, in_L[s], (size_t)3 * S.n_feat * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + S.o_t, in_t[s], (size_t)S.n_feat * sizeof(double), cudaMemcpyHostToDevice, st));
+    // Trajectory::UndistortScanInG with the current state: the scan in the map frame stays on the device
+    const PoseQuery q = make_pose_query(E, S.n_feat, (const double*)(base + S.o_t), S_LtoI, p_LinI, t_offset_ns);
+    undistort_kernel<<<query_grid(E, S.n_feat), 256, smem, st>>>(pp, q, (const float*)(base + S.o_xyzL), nullptr,
+                                                                 (float*)(base + S.o_xyzM),
+                                                                 E->d_counter.as<unsigned long long>());
+    E->launches++;
+  }
+  const assoc_dev::AssocJobs jobs = assoc_jobs(m, P);
+  assoc_search(m, P, jobs, st);
+  assoc_dev::SortedOut out;
+  for (int s = 0; s < 2; s++) {
+    out.t[s] = jobs.j[s].out_t;
+    out.point[s] = jobs.j[s].out_point;
+    out.geo[s] = jobs.j[s].out_geo;
+    out.src[s] = jobs.j[s].out_src;
+  }
+  out.count = (long long*)base;
+  static const bool sort_attr = [] {
+    return cudaFuncSetAttribute(assoc_dev::sort_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                assoc_dev::kSortMax * 12) == cudaSuccess;
+  }();
+  if (!sort_attr) return fail(CLIC_ERR_CUDA, "cannot reserve shared memory for the correspondence sort");
+  assoc_dev::sort_downsample_kernel<<<1, 1024, assoc_dev::kSortMax * 12, st>>>(jobs, cor_downsample, out);
+  m->launches += 1;
+  E->launches += 3;
+  long long h_count[2] = {0, 0};
+  CU(cudaMemcpyAsync(h_count, base, sizeof(h_count), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  int64_t dropped = 0, d1 = 0;
+  // line batch first, then the plane batch — each time-sorted, read by the prep kernel straight from the scratch
+  if ((rc = add_loam_records(E, 2, h_count[0], out.t[0], out.point[0], nullptr, out.geo[0], S_GtoM, p_GinM, S_LtoI, p_LinI,
+                             weight, marg_this_factor, n_dropped ? &d1 : nullptr, true, st)))
+    return rc;
+  dropped += d1;
+  d1 = 0;
+  if ((rc = add_loam_records(E, 1, h_count[1], out.t[1], out.point[1], nullptr, out.geo[1], S_GtoM, p_GinM, S_LtoI, p_LinI,
+                             weight, marg_this_factor, n_dropped ? &d1 : nullptr, true, st)))
+    return rc;
+  dropped += d1;
+  CU(cudaStreamSynchronize(st));  // the scratch may be reused by the next call on any stream
+  if (n_lines) *n_lines = h_count[0];
+  if (n_planes) *n_planes = h_count[1];
+  if (n_dropped) *n_dropped = dropped;
   return CLIC_OK;
 }
 

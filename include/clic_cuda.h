@@ -295,6 +295,21 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m,
                                       int64_t* n_planes, double* plane_t, double* plane_point /*3n*/,
                                       double* plane_geo /*4n: n.x n.y n.z d*/, int64_t* plane_src);
 
+/* The producer of one inner iteration, device-resident (odometry_manager.cpp:321-339 calls it twice per scan):
+ * LidarOdometry::GetLoamFeatureAssociation (lidar_odometry.cpp:148-180) = Trajectory::UndistortScanInG of the scan's
+ * corner / surface features with the current state of `h`, FindCorrespondence against `m`, std::sort by t_point,
+ * DownSampleCorrespondence (every cor_downsample-th record, ":660-671") — followed by what TrajectoryManager does with
+ * the result, one AddLoamMeasurementAnalytic per kept correspondence (trajectory_manager.cpp:676-688).  The scan goes
+ * up once (16 B per feature); the undistorted scan, the neighbours, the fitted geometry and the factor records never
+ * leave the device; two integers come back.  Records with equal timestamps keep their FindCorrespondence order (the
+ * reference's std::sort leaves that open).  The factors land in a line batch and a plane batch, each time-sorted. */
+CLIC_API int clic_add_loam_from_scan(clic_estimator* h, clic_feature_map* m,
+                                     int64_t n_corner, const float* corner_xyz /*3n, LiDAR frame*/, const double* corner_t,
+                                     int64_t n_surf, const float* surf_xyz /*3n*/, const double* surf_t,
+                                     const double S_GtoM[4], const double p_GinM[3], const double S_LtoI[4],
+                                     const double p_LinI[3], double t_offset_ns, int32_t cor_downsample, double weight,
+                                     int32_t marg_this_factor, int64_t* n_lines, int64_t* n_planes, int64_t* n_dropped);
+
 /* Parity probe: the 5 neighbour indices (nearest first; ties by smaller index) of every selected feature of the last
  * clic_find_correspondence call on this map; type 0 corner, 1 surface; -1 rows for features gated out before the
  * search; INT32_MAX for a neighbour outside the 1 m^2 gate (it cannot change the outcome, and is not searched for).

@@ -1522,6 +1522,64 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
   return CLIC_OK;
 }
 
+CLIC_API int clic_undistort_scan(clic_estimator* E, int64_t n, const double* t_s, const float* xyz_in,
+                                 const double S_LtoI[4], const double p_LinI[3], double t_offset_ns, int32_t in_global,
+                                 double target_t_s, float* xyz_out, int64_t* n_invalid);
+
+// lidar_odometry.cpp:148-180 + trajectory_manager.cpp:676-688, composed from the restatements above.
+CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int64_t n_corner, const float* corner_xyz,
+                                     const double* corner_t, int64_t n_surf, const float* surf_xyz, const double* surf_t,
+                                     const double S_GtoM[4], const double p_GinM[3], const double S_LtoI[4],
+                                     const double p_LinI[3], double t_offset_ns, int32_t cor_downsample, double weight,
+                                     int32_t marg_this_factor, int64_t* n_lines, int64_t* n_planes, int64_t* n_dropped) {
+  if (!valid(E) || !m) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (cor_downsample < 1) return fail(CLIC_ERR_BAD_ARGUMENT, "bad argument");
+  if (n_lines) *n_lines = 0;
+  if (n_planes) *n_planes = 0;
+  if (n_dropped) *n_dropped = 0;
+  std::vector<float> cM(3 * (size_t)std::max<int64_t>(n_corner, 0)), sM(3 * (size_t)std::max<int64_t>(n_surf, 0));
+  int rc;
+  if ((rc = clic_undistort_scan(E, n_corner, corner_t, corner_xyz, S_LtoI, p_LinI, t_offset_ns, 1, 0.0, cM.data(), nullptr)) ||
+      (rc = clic_undistort_scan(E, n_surf, surf_t, surf_xyz, S_LtoI, p_LinI, t_offset_ns, 1, 0.0, sM.data(), nullptr)))
+    return rc;
+  const int64_t cap_c = clic_correspondence_capacity(n_corner), cap_s = clic_correspondence_capacity(n_surf);
+  std::vector<double> lt(cap_c), lp(3 * cap_c), lg(6 * cap_c), pt(cap_s), pp(3 * cap_s), pg(4 * cap_s);
+  int64_t nl = 0, np = 0;
+  if ((rc = clic_find_correspondence(m, n_corner, corner_xyz, corner_t, cM.data(), n_surf, surf_xyz, surf_t, sM.data(), &nl,
+                                     lt.data(), lp.data(), lg.data(), nullptr, &np, pt.data(), pp.data(), pg.data(),
+                                     nullptr)))
+    return rc;
+  // std::sort(by_timestamp) over [lines..., planes...] — stable here — then every cor_downsample-th record
+  std::vector<int64_t> order(nl + np);
+  for (int64_t i = 0; i < nl + np; i++) order[i] = i;
+  auto tp = [&](int64_t i) { return i < nl ? lt[i] : pt[i - nl]; };
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return tp(a) < tp(b); });
+  std::vector<double> klt, klp, klg, kpt, kpp, kpg;
+  for (size_t k = 0; k < order.size(); k += cor_downsample) {
+    const int64_t i = order[k];
+    if (i < nl) {
+      klt.push_back(lt[i]);
+      klp.insert(klp.end(), lp.begin() + 3 * i, lp.begin() + 3 * i + 3);
+      klg.insert(klg.end(), lg.begin() + 6 * i, lg.begin() + 6 * i + 6);
+    } else {
+      const int64_t j = i - nl;
+      kpt.push_back(pt[j]);
+      kpp.insert(kpp.end(), pp.begin() + 3 * j, pp.begin() + 3 * j + 3);
+      kpg.insert(kpg.end(), pg.begin() + 4 * j, pg.begin() + 4 * j + 4);
+    }
+  }
+  int64_t d0 = 0, d1 = 0;
+  if ((rc = clic_add_loam_lines(E, (int64_t)klt.size(), klt.data(), klp.data(), klg.data(), S_GtoM, p_GinM, S_LtoI, p_LinI,
+                                weight, marg_this_factor, &d0)) ||
+      (rc = clic_add_loam_planes(E, (int64_t)kpt.size(), kpt.data(), kpp.data(), kpg.data(), S_GtoM, p_GinM, S_LtoI, p_LinI,
+                                 weight, marg_this_factor, &d1)))
+    return rc;
+  if (n_lines) *n_lines = (int64_t)klt.size();
+  if (n_planes) *n_planes = (int64_t)kpt.size();
+  if (n_dropped) *n_dropped = d0 + d1;
+  return CLIC_OK;
+}
+
 CLIC_API int clic_correspondence_neighbours(clic_feature_map* m, int32_t type, int64_t capacity, int32_t* idx,
                                             int64_t* n_out) {
   if (!m || type < 0 || type > 1 || !n_out) return fail(CLIC_ERR_BAD_ARGUMENT, "bad argument");

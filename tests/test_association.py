@@ -195,3 +195,54 @@ def test_gpu_undistort_associate_linearize_chain(cuda, oracle):
     assert (np.abs(Hc - Ho) / np.outer(d, d)).max() < 1e-9
     assert (np.abs(bc - bo) / d).max() <= 1e-9 * (np.abs(bo) / d).max()
     assert abs(cc - co) <= 1e-9 * abs(co)
+
+
+def _scan_from_trajectory(est, room, S_LtoI, p_LinI, shift, hi, rng):
+    """The room's scan features as raw LiDAR points taken along the estimator's current trajectory, in scan
+    (not time) order, like the ring-ordered feature clouds the reference extracts."""
+    scan = {}
+    for kind, pts_M in (("surf", room.surf_M), ("corner", room.corner_M)):
+        n = len(pts_M)
+        t = rng.uniform(1e-6, hi - 1e-6, n)
+        q, p, bad = est.GetSensorPoses(t, S_LtoI, p_LinI, 0.0)
+        assert bad == 0
+        scan[kind] = (S.qrot(S.qconj(q), pts_M.astype(np.float64) - shift - p).astype(np.float32), t)
+    return scan
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ds", [1, 2, 3])
+def test_gpu_add_loam_from_scan(cuda, oracle, ds):
+    """clic_add_loam_from_scan: undistortion, association, time sort, down-sampling and the factor batches without
+    leaving the device, against the same chain composed from the oracle's pieces."""
+    sw = S.make_window(12, n_lidar=10, n_imu=0, seed=32)
+    w = sw.window
+    S_LtoI, p_LinI = sw.lidar["S_LtoI"], sw.lidar["p_LinI"]
+    hi = (w.n_knots - 3) * w.dt_ns * 1e-9
+    room = S.make_feature_scene(n_map_surf=30000, n_map_corner=4000, n_surf=1700, n_corner=600, seed=5 + ds)
+    shift = np.array([9.0, 7.5, 1.5])
+    I4 = np.array([0, 0, 0, 1.0])
+    out = {}
+    scan = None
+    for name, lib in (("cuda", cuda), ("oracle", oracle)):
+        est = E.TrajectoryEstimator(w, E.default_options(lib), lib)
+        est.SetFixedIndex(2)
+        if scan is None:
+            scan = _scan_from_trajectory(est, room, S_LtoI, p_LinI, shift, hi, np.random.default_rng(11))
+        # the map frame is G + shift: give the map in G instead, so that the undistorted scan (in G) meets it
+        fm = A.FeatureMap((room.map_surf.astype(np.float64) - shift).astype(np.float32),
+                          (room.map_corner.astype(np.float64) - shift).astype(np.float32), lib)
+        counts = fm.AddLoamFromScan(est, scan["corner"][0], scan["corner"][1], scan["surf"][0], scan["surf"][1],
+                                    I4, np.zeros(3), S_LtoI, p_LinI, 50.0, cor_downsample=ds)
+        out[name] = (counts, est.Evaluate())
+        fm.close()
+        est.close()
+    assert out["cuda"][0] == out["oracle"][0]
+    nl, npl, nd = out["cuda"][0]
+    assert nd == 0 and nl > 150 // ds and npl > 600 // ds
+    Hc, bc, cc, _ = out["cuda"][1]
+    Ho, bo, co, _ = out["oracle"][1]
+    d = np.sqrt(np.maximum(np.diag(Ho), 1e-300))
+    assert (np.abs(Hc - Ho) / np.outer(d, d)).max() < 1e-9
+    assert (np.abs(bc - bo) / d).max() <= 1e-9 * (np.abs(bo) / d).max()
+    assert abs(cc - co) <= 1e-9 * abs(co)
