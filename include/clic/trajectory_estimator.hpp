@@ -104,6 +104,37 @@ struct Summary {
   }
 };
 
+struct PosPoint {  // my_pcl::PointXYZT, src/utils/mypcl_cloud_type.h:46-51 (x, y, z floats + laser timestamp)
+  float x = 0, y = 0, z = 0;
+  double timestamp = 0;
+};
+typedef std::vector<PosPoint> PosCloud;
+
+// The target of LidarOdometry::SetTargetMap (lidar_odometry.cpp:472-481): the down-sampled surface / corner feature
+// map, resident on the device (clic_feature_map).  An empty corner cloud = use_corner_feature false.
+class LidarFeatureMap {
+ public:
+  typedef std::shared_ptr<LidarFeatureMap> Ptr;
+  LidarFeatureMap(const PosCloud& surface_features, const PosCloud& corner_features) {
+    std::vector<float> s = xyz(surface_features), c = xyz(corner_features);
+    int rc = clic_feature_map_create(s.data(), (int64_t)surface_features.size(), c.empty() ? nullptr : c.data(),
+                                     (int64_t)corner_features.size(), &h_);
+    if (rc != CLIC_OK) throw std::runtime_error(std::string("clic_feature_map_create: ") + clic_last_error());
+  }
+  ~LidarFeatureMap() { clic_feature_map_destroy(h_); }
+  LidarFeatureMap(const LidarFeatureMap&) = delete;
+  LidarFeatureMap& operator=(const LidarFeatureMap&) = delete;
+  clic_feature_map* handle() const { return h_; }
+  static std::vector<float> xyz(const PosCloud& c) {
+    std::vector<float> v(3 * c.size());
+    for (size_t i = 0; i < c.size(); i++) { v[3 * i] = c[i].x; v[3 * i + 1] = c[i].y; v[3 * i + 2] = c[i].z; }
+    return v;
+  }
+
+ private:
+  clic_feature_map* h_ = nullptr;
+};
+
 // MarginalizationInfo (marginalization_factor.h:100-142): owns a clic_prior; the kept parameter blocks are
 // returned to the caller as raw pointers exactly like getParameterBlocks() (marginalization_factor.cpp:301-317).
 struct MarginalizationInfo {
@@ -181,6 +212,45 @@ class TrajectoryEstimator {
       b.ln_point.insert(b.ln_point.end(), pc.point.begin(), pc.point.end());
       b.ln_geo.insert(b.ln_geo.end(), pc.geo_point.begin(), pc.geo_point.end());
       b.ln_geo.insert(b.ln_geo.end(), pc.geo_normal.begin(), pc.geo_normal.end());
+    }
+  }
+
+  // One inner iteration's LiDAR factors straight from the scan (no reference counterpart as one call):
+  // LidarOdometry::GetLoamFeatureAssociation (lidar_odometry.cpp:148-180: UndistortScanInG with the trajectory as it
+  // stands when the problem is built, FindCorrespondence against `map`, sort by t_point, DownSampleCorrespondence)
+  // + the AddLoamMeasurementAnalytic loop of trajectory_manager.cpp:682-686, all on the device.
+  void AddLoamMeasurementsFromScan(const LidarFeatureMap::Ptr& map, const PosCloud& corner_features,
+                                   const PosCloud& surface_features, const SO3d& S_GtoM, const Vec3d& p_GinM,
+                                   const SO3d& S_LtoI, const Vec3d& p_LinI, double weight, int cor_downsample = 1,
+                                   bool marg_this_factor = false) {
+    ScanBatch b;
+    b.map = map;
+    b.corner_xyz = LidarFeatureMap::xyz(corner_features);
+    b.surf_xyz = LidarFeatureMap::xyz(surface_features);
+    for (const auto& p : corner_features) b.corner_t.push_back(p.timestamp);
+    for (const auto& p : surface_features) b.surf_t.push_back(p.timestamp);
+    b.S_GtoM = S_GtoM; b.p_GinM = p_GinM; b.S_LtoI = S_LtoI; b.p_LinI = p_LinI; b.weight = weight;
+    b.cor_downsample = cor_downsample;
+    b.marg = marg_this_factor;
+    scans_.push_back(std::move(b));
+  }
+  // (lines, planes) each scan batch contributed, after the problem has been built (Solve / SaveMarginalizationInfo)
+  const std::vector<std::pair<int64_t, int64_t>>& ScanCorrespondenceCounts() const { return scan_counts_; }
+
+  // Trajectory::GetLidarPose (trajectory.h:134-136) for many timestamps at once, at the current state.  Builds the
+  // problem: call it after the Add* calls, or on an estimator made for the query.
+  void GetLidarPoses(const std::vector<double>& t_s, std::vector<SO3d>* q_LtoG, std::vector<Vec3d>* p_LinG) {
+    build();
+    const ExtrinsicParam& ep = trajectory_->EP_StoI[LiDARSensor];
+    std::vector<double> q(4 * t_s.size()), p(3 * t_s.size());
+    int64_t bad = 0;
+    check(clic_query_poses(h_, (int64_t)t_s.size(), t_s.data(), ep.so3.data(), ep.p.data(), ep.t_offset_ns, q.data(),
+                           p.data(), &bad));
+    q_LtoG->resize(t_s.size());
+    p_LinG->resize(t_s.size());
+    for (size_t i = 0; i < t_s.size(); i++) {
+      std::memcpy((*q_LtoG)[i].q.data(), &q[4 * i], 4 * sizeof(double));
+      std::memcpy((*p_LinG)[i].data(), &p[3 * i], 3 * sizeof(double));
     }
   }
 
@@ -269,6 +339,16 @@ class TrajectoryEstimator {
     SO3d S_GtoM, S_LtoI;
     Vec3d p_GinM{}, p_LinI{};
     double weight = 1;
+    bool marg = false;
+  };
+  struct ScanBatch {
+    LidarFeatureMap::Ptr map;
+    std::vector<float> corner_xyz, surf_xyz;
+    std::vector<double> corner_t, surf_t;
+    SO3d S_GtoM, S_LtoI;
+    Vec3d p_GinM{}, p_LinI{};
+    double weight = 1;
+    int cor_downsample = 1;
     bool marg = false;
   };
   struct ImuBatch {
@@ -387,6 +467,15 @@ class TrajectoryEstimator {
                                   b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
                                   nullptr));
     for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
+    for (auto& b : scans_) {
+      int64_t nl = 0, np = 0;
+      check(clic_add_loam_from_scan(h_, b.map->handle(), (int64_t)b.corner_t.size(), b.corner_xyz.data(),
+                                    b.corner_t.data(), (int64_t)b.surf_t.size(), b.surf_xyz.data(), b.surf_t.data(),
+                                    b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(),
+                                    trajectory_->EP_StoI[LiDARSensor].t_offset_ns, b.cor_downsample, b.weight, b.marg, &nl,
+                                    &np, nullptr));
+      scan_counts_.push_back({nl, np});
+    }
   }
 
   // Ceres updates the caller's parameter blocks in place; so do we
@@ -413,6 +502,8 @@ class TrajectoryEstimator {
   clic_estimator* h_ = nullptr;
   double* gravity_ = nullptr;
   std::vector<LoamBatch> loam_;
+  std::vector<ScanBatch> scans_;
+  std::vector<std::pair<int64_t, int64_t>> scan_counts_;
   std::vector<ImuBatch> imu_;
   std::vector<ImageBatch> image_;
   std::vector<BiasFac> bias_f_;

@@ -39,6 +39,56 @@ int main() {
     pc.geo_point = {N(rng), N(rng), N(rng)};
     estimator->AddLoamMeasurementAnalytic(pc, I, zero, I, zero, 5.0);
   }
+  // The same inner iteration's LiDAR factors straight from a scan: a floor, a wall and their edge as the feature map;
+  // the scan is the map's surfaces seen from the trajectory (raw points p_L = pose(t)^-1 p_G, pose from the library).
+  {
+    PosCloud map_surf, map_corner, scan_surf, scan_corner;
+    std::vector<Vec3d> surf_G, corner_G;
+    std::vector<double> ts, tc;
+    for (int i = 0; i < 6000; i++) {
+      PosPoint p;
+      if (i % 2) { p.x = 8 * U(rng) - 2; p.y = 8 * U(rng) - 2; p.z = -1.5f + 0.01 * N(rng); }   // floor z = -1.5
+      else { p.x = 5.0f + 0.01 * N(rng); p.y = 8 * U(rng) - 2; p.z = 4 * U(rng) - 1.5; }        // wall x = 5
+      map_surf.push_back(p);
+    }
+    for (int i = 0; i < 600; i++) {
+      PosPoint p;
+      p.x = 5.0f + 0.01 * N(rng); p.y = 8 * U(rng) - 2; p.z = -1.5f + 0.01 * N(rng);             // the edge
+      map_corner.push_back(p);
+    }
+    for (int i = 0; i < 300; i++) {
+      surf_G.push_back(i % 2 ? Vec3d{8 * U(rng) - 2, 8 * U(rng) - 2, -1.5} : Vec3d{5.0, 8 * U(rng) - 2, 4 * U(rng) - 1.5});
+      ts.push_back(0.001 + 0.69 * U(rng));
+    }
+    for (int i = 0; i < 80; i++) {
+      corner_G.push_back({5.0, 7 * U(rng) - 1.5, -1.5});
+      tc.push_back(0.001 + 0.69 * U(rng));
+    }
+    TrajectoryEstimator::Ptr probe(new TrajectoryEstimator(traj, option, "pose probe"));
+    auto to_scan = [&](const std::vector<Vec3d>& pg, const std::vector<double>& t, PosCloud* out) {
+      std::vector<SO3d> q;
+      std::vector<Vec3d> p;
+      probe->GetLidarPoses(t, &q, &p);
+      for (size_t i = 0; i < pg.size(); i++) {  // p_L = R^T (p_G - p), R from the unit quaternion (x, y, z, w)
+        const double* c = q[i].data();
+        const double x = c[0], y = c[1], z = c[2], w = c[3];
+        const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                                {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                                {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+        const double d[3] = {pg[i][0] - p[i][0], pg[i][1] - p[i][1], pg[i][2] - p[i][2]};
+        PosPoint o;
+        o.x = (float)(R[0][0] * d[0] + R[1][0] * d[1] + R[2][0] * d[2]);
+        o.y = (float)(R[0][1] * d[0] + R[1][1] * d[1] + R[2][1] * d[2]);
+        o.z = (float)(R[0][2] * d[0] + R[1][2] * d[1] + R[2][2] * d[2]);
+        o.timestamp = t[i];
+        out->push_back(o);
+      }
+    };
+    to_scan(surf_G, ts, &scan_surf);
+    to_scan(corner_G, tc, &scan_corner);
+    LidarFeatureMap::Ptr map(new LidarFeatureMap(map_surf, map_corner));
+    estimator->AddLoamMeasurementsFromScan(map, scan_corner, scan_surf, I, zero, I, zero, 5.0, 2);
+  }
   double bg0[3] = {0, 0, 0}, ba0[3] = {0, 0, 0}, bg1[3] = {0.01, 0, 0}, ba1[3] = {0, 0.02, 0}, g[3] = {0, 0, 9.8};
   Vec6d info = {800, 800, 800, 36, 36, 36};
   for (int i = 0; i < 60; i++) {
@@ -52,7 +102,10 @@ int main() {
   estimator->AddBiasFactor(bg0, bg1, ba0, ba1, 1, binfo);
   Summary summary = estimator->Solve(8, false);
   std::printf("%s\n", summary.BriefReport().c_str());
-  bool ok = summary.final_cost < summary.initial_cost && std::isfinite(summary.final_cost);
+  const auto& sc = estimator->ScanCorrespondenceCounts();
+  std::printf("scan correspondences: %lld lines, %lld planes\n", (long long)sc.at(0).first, (long long)sc.at(0).second);
+  bool ok = summary.final_cost < summary.initial_cost && std::isfinite(summary.final_cost) && sc.at(0).first > 10 &&
+            sc.at(0).second > 60;
   std::printf("%s %.6e %.6e %d\n", ok ? "SHIM_OK" : "SHIM_FAIL", summary.initial_cost, summary.final_cost,
               summary.num_successful_steps);
   return ok ? 0 : 1;
