@@ -438,6 +438,44 @@ def main():
         dt_u = (time.perf_counter() - t0) / 5
         undistort = {"points": n_pts, "points_per_s_through_abi": n_pts / dt_u, "ms": dt_u * 1e3, "invalid": int(bad),
                      "bytes_h2d_d2h": int(n_pts * 32), "note": "UndistortScanInG, host buffers in / out (PCIe-bound)"}
+    # ---- the producer of the path's input: one inner iteration's undistort -> associate -> sort ->
+    # downsample -> LiDAR factor batches, device-resident, at the reference's production shape ----
+    association = None
+    if rank == 0:
+        from clic_b200 import association as A
+        room = S.make_feature_scene(n_map_surf=50000, n_map_corner=8000, n_surf=1500, n_corner=1500, seed=8)
+        shift = np.array([9.0, 7.5, 1.5])
+        w_ = sw.window
+        Lx = sw.lidar
+        hi_ = (w_.n_knots - 3) * w_.dt_ns * 1e-9
+        rng = np.random.default_rng(11)
+        scan = {}
+        for kind, pts_M in (("surf", room.surf_M), ("corner", room.corner_M)):
+            tq = rng.uniform(1e-6, hi_ - 1e-6, len(pts_M))
+            q_, p_, _ = est.GetSensorPoses(tq, Lx["S_LtoI"], Lx["p_LinI"], 0.0)
+            scan[kind] = (S.qrot(S.qconj(q_), pts_M.astype(np.float64) - shift - p_).astype(np.float32), tq)
+        fm = A.FeatureMap((room.map_surf.astype(np.float64) - shift).astype(np.float32),
+                          (room.map_corner.astype(np.float64) - shift).astype(np.float32))
+        I4, z3 = np.array([0, 0, 0, 1.0]), np.zeros(3)
+        ts_a = []
+        opt_a = E.default_options(lib)
+        opt_a.device = local_rank
+        for r in range(8):
+            est_a = E.TrajectoryEstimator(sw.window, opt_a, lib)
+            est_a.SetFixedIndex(2)
+            t0 = time.perf_counter()
+            counts = fm.AddLoamFromScan(est_a, scan["corner"][0], scan["corner"][1], scan["surf"][0], scan["surf"][1],
+                                        I4, z3, Lx["S_LtoI"], Lx["p_LinI"], 50.0, cor_downsample=2)
+            ts_a.append((time.perf_counter() - t0) * 1e3)
+            est_a.close()
+        in_G = [(m_.astype(np.float64) - shift).astype(np.float32) for m_ in (room.corner_M, room.surf_M)]
+        fm.FindCorrespondence(scan["corner"][0], scan["corner"][1], in_G[0], scan["surf"][0], scan["surf"][1], in_G[1])
+        n_l, k_ms = fm.launches()
+        fm.close()
+        association = {"map_points": 58000, "scan_features": 3000, "kept_lines": counts[0], "kept_planes": counts[1],
+                       "add_loam_from_scan_ms": float(np.median(ts_a[2:])), "find_correspondence_kernels_ms": k_ms,
+                       "note": "clic_add_loam_from_scan: H2D of the scan, undistortion, exact 5-NN + fits, time sort, "
+                               "down-sampling (2) and the factor batches on the device; wall clock of the call"}
     est.close()
     if world > 1:
         dist.barrier()
@@ -480,7 +518,7 @@ def main():
         "gn_iterations": gn,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_each": [round(x, 2) for x in e2e_each]},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "undistort_scan": undistort,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "undistort_scan": undistort, "association": association,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
