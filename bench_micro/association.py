@@ -39,12 +39,19 @@ def main():
         co = fo.FindCorrespondence(*args)
         cpu_ms = (time.perf_counter() - t0) * 1e3
         fo.close()
+        oracle.clic_oracle_set_association_search(1)
+        fo = A.FeatureMap(sc.map_surf, sc.map_corner, oracle)
+        t0 = time.perf_counter()
+        fo.FindCorrespondence(*args)
+        cpu_grid_ms = (time.perf_counter() - t0) * 1e3
+        fo.close()
+        oracle.clic_oracle_set_association_search(0)
         same = all(np.array_equal(getattr(c, k), getattr(co, k)) for k in ("line_geo", "plane_geo", "line_src", "plane_src"))
         nq = A.cuda_library().clic_correspondence_capacity(ns) + A.cuda_library().clic_correspondence_capacity(nc)
         rows.append({"map_surf": ms, "map_corner": mc, "features": ns + nc, "searched": int(nq),
                      "lines": len(c.line_t), "planes": len(c.plane_t), "bit_identical_to_oracle": bool(same),
                      "gpu_kernels_ms": round(float(np.median(kern)), 4), "gpu_call_ms": round(float(np.median(call)), 4),
-                     "cpu_bruteforce_1thread_ms": round(cpu_ms, 2)})
+                     "cpu_bruteforce_1thread_ms": round(cpu_ms, 2), "cpu_grid_1thread_ms": round(cpu_grid_ms, 2)})
         print(json.dumps(rows[-1]), flush=True)
 
 
@@ -75,8 +82,11 @@ def pipeline():
                     q, p, _ = est0.GetSensorPoses(t, S_LtoI, p_LinI, 0.0)
                     scan[kind] = (S.qrot(S.qconj(q), pts_M.astype(np.float64) - shift - p).astype(np.float32), t)
             est0.close()
+            if name == "oracle":
+                oracle.clic_oracle_set_association_search(1)  # grid-accelerated exact search for the timed CPU arm
             fm = A.FeatureMap(map_s, map_c, lib)
-            reps = 12 if name == "cuda" else 2
+            oracle.clic_oracle_set_association_search(0)
+            reps = 12 if name == "cuda" else 3
             fused, split = [], []
             for r in range(reps):
                 est = E.TrajectoryEstimator(w, E.default_options(lib), lib)

@@ -1,0 +1,153 @@
+"""One LiDAR-inertial update of the reference at its production size, through the public API
+(odometry_manager.cpp:321-339 + trajectory_manager.cpp:319-465, 555-877):
+
+  two inner iterations of  [GetLoamFeatureAssociation -> UpdateTrajectoryWithLoamFeature: prior + LiDAR + IMU + bias,
+  Solve(8)]  followed by  UpdateLIOPrior  (marginalization of the oldest knots).
+
+Sizes (SURVEY.md §6 "typical real problem size"): 1500 corner + 1500 surface scan features, correspondence
+down-sampling 2, a 58 k-point feature map, 125 IMU samples, 14 knots of which 4 are marginalised.  The reference's own
+budget for this update is 0.12 s (update_every_k_knot x knot_distance).  GPU: wall clock of the host calls; CPU: the
+restatement on one thread (the reference runs Ceres with num_threads = 1), its association searching through a uniform
+grid (exact, tests/test_association.py) in place of the reference's kd-tree — the exhaustive scan that defines the
+restatement would flatter the GPU."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from clic_b200 import association as A  # noqa: E402
+from clic_b200 import estimator as E  # noqa: E402
+from clic_b200 import synthetic as S  # noqa: E402
+from clic_b200._abi import BLOCK_BIAS_ACCEL, BLOCK_BIAS_GYRO, BLOCK_KNOT_POS, BLOCK_KNOT_ROT  # noqa: E402
+
+K, LATER = 14, 4
+SHIFT = np.array([9.0, 7.5, 1.5])
+I4, Z3 = np.array([0, 0, 0, 1.0]), np.zeros(3)
+
+
+def previous_prior(lib, sw, knots, rng):
+    kinds, ids, x0 = [], [], []
+    for k in knots:
+        kinds += [BLOCK_KNOT_ROT, BLOCK_KNOT_POS]
+        ids += [k, k]
+        x0 += [S.qmul(sw.window.knot_q[k], S.so3_exp(rng.normal(0, 2e-3, 3))),
+               np.concatenate([sw.window.knot_p[k] + rng.normal(0, 2e-3, 3), [0]])]
+    kinds += [BLOCK_BIAS_GYRO, BLOCK_BIAS_ACCEL]
+    ids += [0, 0]
+    x0 += [np.concatenate([sw.window.bias[0, :3] + 1e-4, [0]]), np.concatenate([sw.window.bias[0, 3:] - 1e-4, [0]])]
+    n = 6 * len(knots) + 6
+    J0 = 40.0 * np.eye(n) + rng.normal(size=(n, n)) * 2.0
+    r0 = rng.normal(size=n) * 0.3
+    return E.Prior.create(lib, J0, r0, kinds, ids, np.array(x0)), kinds, ids
+
+
+def update(lib, sw, fm, scan, state, prior_spec):
+    """Returns (timings dict in ms, final state, new prior dims)."""
+    M, Lx = sw.imu, sw.lidar
+    t = {"associate_add": 0.0, "other_adds": 0.0, "solve": 0.0, "marginalize": 0.0}
+    win = sw.window
+    for it in range(2):
+        opt = E.default_options(lib)
+        opt.lock_ab = opt.lock_wb = 0
+        w = E.Window(win.t0_ns, win.dt_ns, state["knot_q"], state["knot_p"], bias=state["bias"],
+                     S_LtoI=win.S_LtoI, p_LinI=win.p_LinI, gravity=win.gravity)
+        t0 = time.perf_counter()
+        est = E.TrajectoryEstimator(w, opt, lib)
+        est.SetFixedIndex(-1)
+        prior, kinds, ids = prior_spec
+        est.AddMarginalizationFactor(prior, [])
+        est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], 1, M["info_vec"], count_dropped=False)
+        est.AddBiasFactor(0, 1, 1.0, S.BIAS_INFO_VEC / np.sqrt(0.1 / S.IMU_FREQ))
+        t1 = time.perf_counter()
+        fm.AddLoamFromScan(est, scan["corner"][0], scan["corner"][1], scan["surf"][0], scan["surf"][1], I4, Z3,
+                           Lx["S_LtoI"], Lx["p_LinI"], 50.0, cor_downsample=2)
+        t2 = time.perf_counter()
+        summ = est.Solve(8)
+        state = est.read_state()
+        t3 = time.perf_counter()
+        est.close()
+        t["other_adds"] += (t1 - t0) * 1e3
+        t["associate_add"] += (t2 - t1) * 1e3
+        t["solve"] += (t3 - t2) * 1e3
+    # UpdateLIOPrior
+    opt = E.default_options(lib)
+    opt.is_marg_state = 1
+    opt.marg_bias_param = 0
+    opt.marg_gravity_param = 1
+    opt.marg_t_offset_param = 1
+    opt.ctrl_to_be_opt_now = 0
+    opt.ctrl_to_be_opt_later = LATER
+    w = E.Window(win.t0_ns, win.dt_ns, state["knot_q"], state["knot_p"], bias=state["bias"],
+                 S_LtoI=win.S_LtoI, p_LinI=win.p_LinI, gravity=win.gravity)
+    t0 = time.perf_counter()
+    est = E.TrajectoryEstimator(w, opt, lib)
+    prior, kinds, ids = prior_spec
+    drop = [i for i, (kd, idv) in enumerate(zip(kinds, ids))
+            if (kd in (BLOCK_KNOT_ROT, BLOCK_KNOT_POS) and idv < LATER) or kd in (BLOCK_BIAS_GYRO, BLOCK_BIAS_ACCEL)]
+    est.AddMarginalizationFactor(prior, drop)
+    est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], 1, M["info_vec"], True, count_dropped=False)
+    t1 = time.perf_counter()
+    fm.AddLoamFromScan(est, scan["corner"][0], scan["corner"][1], scan["surf"][0], scan["surf"][1], I4, Z3,
+                       Lx["S_LtoI"], Lx["p_LinI"], 50.0, cor_downsample=2, marg_this_factor=True)
+    t2 = time.perf_counter()
+    pr = est.SaveMarginalizationInfo()
+    dims = pr.dims() if pr is not None else None
+    t["associate_add"] += (t2 - t1) * 1e3
+    t["marginalize"] = (time.perf_counter() - t0 - (t2 - t1)) * 1e3
+    est.close()
+    t["total"] = sum(t.values())
+    return t, state, dims, summ
+
+
+def main():
+    import oracle_lib  # the checker / CPU baseline, never the product
+    cuda, oracle = E.cuda_library(), oracle_lib.load()
+    oracle.clic_oracle_set_threads(1)
+    oracle.clic_oracle_set_association_search(1)  # grid-accelerated exact search for the timed CPU arm
+    sw = S.make_window(K, n_lidar=10, n_imu=125, seed=41, init_noise=(2e-3, 5e-3))
+    room = S.make_feature_scene(n_map_surf=50000, n_map_corner=8000, n_surf=1500, n_corner=1500, seed=8)
+    map_s = (room.map_surf.astype(np.float64) - SHIFT).astype(np.float32)
+    map_c = (room.map_corner.astype(np.float64) - SHIFT).astype(np.float32)
+    hi = (K - 3) * sw.window.dt_ns * 1e-9
+    # the scan: room features seen from the ground-truth trajectory (the estimate starts a few mm / mrad off)
+    gt = S.SplineNP(sw.window.t0_ns, sw.window.dt_ns, sw.gt_knot_q, sw.gt_knot_p)
+    rng = np.random.default_rng(11)
+    Lx = sw.lidar
+    scan = {}
+    for kind, pts_M in (("surf", room.surf_M), ("corner", room.corner_M)):
+        tq = rng.uniform(1e-6, hi - 1e-6, len(pts_M))
+        t_ns = (tq * 1e9).astype(np.int64)
+        R, pos = gt.rotation(t_ns), gt.position(t_ns)
+        q = S.qmul(R, np.broadcast_to(Lx["S_LtoI"], R.shape))
+        p = S.qrot(R, np.broadcast_to(Lx["p_LinI"], pos.shape)) + pos
+        scan[kind] = (S.qrot(S.qconj(q), pts_M.astype(np.float64) - SHIFT - p).astype(np.float32), tq)
+    out = {}
+    for name, lib, reps in (("gpu", cuda, 6), ("cpu_1thread", oracle, 3)):
+        fm = A.FeatureMap(map_s, map_c, lib)
+        spec = previous_prior(lib, sw, range(0, 8), np.random.default_rng(7))
+        state0 = {"knot_q": sw.window.knot_q.copy(), "knot_p": sw.window.knot_p.copy(), "bias": sw.window.bias.copy()}
+        runs = []
+        for r in range(reps):
+            tt, state, dims, summ = update(lib, sw, fm, scan, dict(state0), spec)
+            runs.append(tt)
+        fm.close()
+        best = min(runs[1:] if len(runs) > 1 else runs, key=lambda x: x["total"])
+        out[name] = {"ms": {k: round(v, 3) for k, v in best.items()}, "new_prior_dims": dims,
+                     "last_solve": {"iterations": summ["iterations"], "final_cost": summ["final_cost"]},
+                     "final_pos": state["knot_p"][-1].tolist()}
+    dp = np.abs(np.array(out["gpu"]["final_pos"]) - np.array(out["cpu_1thread"]["final_pos"])).max()
+    out["max_abs_diff_last_knot_position_m"] = float(dp)
+    out["speedup_total"] = round(out["cpu_1thread"]["ms"]["total"] / out["gpu"]["ms"]["total"], 1)
+    out["speedup_without_association"] = round(
+        (out["cpu_1thread"]["ms"]["total"] - out["cpu_1thread"]["ms"]["associate_add"]) /
+        (out["gpu"]["ms"]["total"] - out["gpu"]["ms"]["associate_add"]), 1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

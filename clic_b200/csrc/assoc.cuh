@@ -466,21 +466,31 @@ __global__ void __launch_bounds__(1024) compact_kernel(AssocJobs jobs) {
 // order of equal timestamps open; this is the stable choice), keeps every ds-th and writes them out split by type, each
 // batch still time-sorted — the layout the factor kernels want.  At most 1500 records per type exist by construction.
 constexpr int kSortMax = 4096;
+constexpr int kAlignKeys = 128;  // key-aligned output for windows of up to this many knot intervals
 struct SortedOut {
   double* t[2];        // [0] lines, [1] planes
   double* point[2];    // 3 per record
   double* geo[2];      // 6 / 4 per record
   long long* src[2];
-  long long* count;    // 2
+  long long* count;    // [0..1] stored records per type (padding included), [2..3] kept correspondences per type
+  // Key-aligned storage (n_keys > 0): every knot interval's records start on a multiple of 32, the holes hold
+  // records with a timestamp far outside any window, which the factor adder stores as dropped — each 32-factor slab
+  // of the factor kernels then belongs to one interval (see build_key_gather in clic_cuda.cu).
+  long long t0_ns, dt_ns;
+  int n_keys;
 };
+constexpr double kHoleTime = -1e9;  // seconds
 
 __global__ void __launch_bounds__(1024) sort_downsample_kernel(AssocJobs jobs, int ds, SortedOut out) {
   extern __shared__ double s_key[];               // kSortMax doubles
   int* s_ord = (int*)(s_key + kSortMax);          // kSortMax ints: (type << 16) | q, i.e. the unsorted-list order
   __shared__ int warp_tot[32];
   __shared__ int running, kept_run[2];
+  __shared__ int cnt[2][kAlignKeys], start[2][kAlignKeys + 1], cum[2][kAlignKeys + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool align = out.n_keys > 0 && out.n_keys <= kAlignKeys;
   if (threadIdx.x == 0) { running = 0; kept_run[0] = kept_run[1] = 0; }
+  for (int i = threadIdx.x; i < 2 * kAlignKeys; i += blockDim.x) cnt[i / kAlignKeys][i % kAlignKeys] = 0;
   __syncthreads();
   for (int type = 0; type < 2; type++) {
     const AssocJob& J = jobs.j[type];
@@ -533,6 +543,38 @@ __global__ void __launch_bounds__(1024) sort_downsample_kernel(AssocJobs jobs, i
       __syncthreads();
     }
   }
+  // the knot interval of a record, as the factor kernels will index it (clamped: alignment is only a layout matter)
+  auto key_of = [&](double t_s) {
+    const long long rel = (long long)(t_s * 1e9) - out.t0_ns;
+    long long k = rel < 0 ? 0 : rel / out.dt_ns;
+    return (int)(k >= out.n_keys ? out.n_keys - 1 : k);
+  };
+  if (align) {
+    for (int i = threadIdx.x * ds; i < n; i += blockDim.x * ds) atomicAdd(&cnt[s_ord[i] >> 16][key_of(s_key[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      int a = 0, c = 0;
+      for (int k = 0; k < out.n_keys; k++) {
+        start[threadIdx.x][k] = a;
+        cum[threadIdx.x][k] = c;
+        a += (cnt[threadIdx.x][k] + 31) / 32 * 32;
+        c += cnt[threadIdx.x][k];
+      }
+      start[threadIdx.x][out.n_keys] = a;
+      cum[threadIdx.x][out.n_keys] = c;
+    }
+    __syncthreads();
+    for (int type = 0; type < 2; type++) {  // holes first; the kept records overwrite their places below
+      const int gw = jobs.j[type].geo_w, tot = start[type][out.n_keys];
+      for (int o = threadIdx.x; o < tot; o += blockDim.x) {
+        out.t[type][o] = kHoleTime;
+        out.point[type][3 * o] = out.point[type][3 * o + 1] = out.point[type][3 * o + 2] = 0.0;
+        for (int c = 0; c < gw; c++) out.geo[type][gw * o + c] = 0.0;
+        out.src[type][o] = -1;
+      }
+    }
+    __syncthreads();
+  }
   // keep every ds-th of the sorted list; split by type with an order-preserving scan
   for (int base = 0; base < n; base += 1024) {
     const int i = base + threadIdx.x;
@@ -555,7 +597,11 @@ __global__ void __launch_bounds__(1024) sort_downsample_kernel(AssocJobs jobs, i
       const AssocJob& J = jobs.j[type];
       const int q = ord & 0xffff;
       const unsigned below = (1u << lane) - 1u;
-      const long long o = type == 0 ? kept_run[0] + before0 + __popc(m0 & below) : kept_run[1] + before1 + __popc(m1 & below);
+      long long o = type == 0 ? kept_run[0] + before0 + __popc(m0 & below) : kept_run[1] + before1 + __popc(m1 & below);
+      if (align) {  // o-th kept record of its type -> its interval's slab-aligned run
+        const int k = key_of(s_key[i]);
+        o = start[type][k] + (o - cum[type][k]);
+      }
       const long long feat = (long long)q * J.step;
       out.t[type][o] = s_key[i];
 #pragma unroll
@@ -567,7 +613,12 @@ __global__ void __launch_bounds__(1024) sort_downsample_kernel(AssocJobs jobs, i
     if (threadIdx.x == 0) { kept_run[0] += tot0; kept_run[1] += tot1; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { out.count[0] = kept_run[0]; out.count[1] = kept_run[1]; }
+  if (threadIdx.x == 0) {
+    out.count[2] = kept_run[0];
+    out.count[3] = kept_run[1];
+    out.count[0] = align ? start[0][out.n_keys] : kept_run[0];
+    out.count[1] = align ? start[1][out.n_keys] : kept_run[1];
+  }
 }
 
 }  // namespace assoc_dev

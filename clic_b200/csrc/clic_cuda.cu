@@ -181,6 +181,9 @@ struct LoamBatch {
   LoamStream st;
   DevBuf t_ns, p[3], g[6], type;
   DevBuf raw[6];  // the arrays as uploaded (kept until destroy, see the adders)
+  DevBuf d_gather;
+  std::vector<int32_t> gather;  // key-aligned storage (build_key_gather): stored position -> input record, -1 = padding
+  int64_t n_input = 0;          // records the caller added (st.n counts the padding too)
   int marg = 0;
   StreamExec ex;
 };
@@ -188,6 +191,9 @@ struct ImuBatch {
   ImuStream st;
   DevBuf t_ns, gy[3], ac[3];
   DevBuf raw[3];
+  DevBuf d_gather;
+  std::vector<int32_t> gather;
+  int64_t n_input = 0;
   int marg = 0;
   StreamExec ex;
 };
@@ -798,6 +804,58 @@ int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
 
 
 
+// Key-aligned storage for small batches.  A warp evaluates 32 consecutive factors at a time and accumulates them into
+// the 24-column block of ONE knot interval, so a 32-factor slab that straddles k intervals costs k evaluation rounds.
+// With 10^5-10^6 factors per window that never matters; at the reference's production size (a few hundred LiDAR and
+// ~100 IMU factors over ~10 intervals) nearly every slab straddles 2-4 intervals.  For a small, time-sorted batch the
+// host therefore starts every interval's factors on a slab boundary (padding entries are stored as dropped factors):
+// one round per slab, and the slabs of different intervals run on different warps.  Sums per interval keep their
+// order, so H, b are unchanged bit for bit.  Returns an empty map when the batch is large, unsorted, or already aligned.
+// t_s: the caller's timestamps; shift_ns: what the factor adds before indexing ((int64) time offset for the IMU).
+constexpr int64_t kKeyAlignMax = 1 << 15;
+bool key_align_enabled() { static const bool v = getenv("CLIC_NO_KEY_ALIGN") == nullptr; return v; }
+std::vector<int32_t> build_key_gather(const clic_estimator* E, const double* t_s, int64_t n, int64_t t_lo, int64_t t_hi,
+                                      int64_t pad, int64_t shift_ns) {
+  std::vector<int32_t> g;
+  if (!key_align_enabled() || n > kKeyAlignMax || n <= 1) return g;
+  std::vector<int32_t> key((size_t)n);
+  const int n_keys = E->K - 3;
+  std::vector<int32_t> count((size_t)n_keys, 0);
+  int prev = -1;
+  int64_t n_bad = 0;
+  bool straddle = false;
+  int64_t run = 0;  // valid records since the last slab boundary in the unpadded layout
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t t = (int64_t)(t_s[i] * 1e9);  // prep_*_kernel's conversion and window test
+    const bool ok = !(t - pad < t_lo || t + pad >= t_hi);
+    int k = -1;
+    if (ok) {
+      const int64_t rel = t + shift_ns - E->t0_ns;
+      k = rel < 0 ? -1 : (int)std::min<int64_t>(rel / E->dt_ns, n_keys - 1);
+    }
+    key[i] = k;
+    if (k < 0) { n_bad++; continue; }
+    if (k < prev) return g;  // not time-sorted: leave the batch as it is (the kernels cope, with more rounds)
+    if (k != prev && (run % 32) != 0) straddle = true;
+    prev = k;
+    count[k]++;
+    run++;
+  }
+  if (!straddle && n_bad == 0) return g;
+  std::vector<int64_t> start((size_t)n_keys + 1, 0);
+  for (int k = 0; k < n_keys; k++) start[k + 1] = start[k] + (count[k] + 31) / 32 * 32;
+  const int64_t total = start[n_keys] + n_bad;  // dropped records last: still counted by the prep kernel
+  if (total > INT32_MAX) return g;
+  g.assign((size_t)total, -1);
+  std::vector<int64_t> fill(start.begin(), start.end() - 1);
+  int64_t bad_at = start[n_keys];
+  for (int64_t i = 0; i < n; i++) {
+    if (key[i] >= 0) g[(size_t)fill[key[i]]++] = (int32_t)i;
+    else g[(size_t)bad_at++] = (int32_t)i;
+  }
+  return g;
+}
+
 // clic_solve: the LM loop runs on the device; the host only enqueues kernels (and, for bounded problems, polls the
 // line-search flag once per sample).
 int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
@@ -894,7 +952,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
       }
     }
     E->prof_begin(5);
-    CU(launch_pdl(lm_accept_kernel, 1, 256, sm_small, E->stream, B, L, C));
+    CU(launch_pdl(lm_accept_kernel, 1, 1024, sm_small, E->stream, B, L, C));
     E->prof_end();
     E->launches++;
     if (!speculate && (rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
@@ -1452,6 +1510,14 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
       (rc = to_device(E, r_normal, geo_normal, geo_normal ? 3 * n : 0)) ||
       (rc = to_device(E, r_gpoint, geo_point, geo_point ? 3 * n : 0)))
     return rc;
+  B->n_input = n;
+  B->gather = build_key_gather(E, t_point, n, t_min, t_max, 0, 0);
+  const int32_t* d_gather = nullptr;
+  if (!B->gather.empty()) {
+    if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;
+    d_gather = B->d_gather.as<int32_t>();
+    n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
+  }
   CU(B->t_ns.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
   for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
@@ -1462,7 +1528,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
       r_gpoint.as<double>(), ldq(S_LtoI), ldv(p_LinI), t_min, t_max, B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(),
       B->p[2].as<double>(), B->g[0].as<double>(), B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(),
       B->g[4].as<double>(), B->g[5].as<double>(), B->type.as<uint8_t>(), E->d_counter.as<unsigned long long>(),
-      E->d_flags.as<int>() + 1);
+      E->d_flags.as<int>() + 1, d_gather);
   E->launches++;
   if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
     unsigned long long dropped = 0;
@@ -1531,6 +1597,16 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
     in_type = r_type.as<uint8_t>();
     in_geo = r_geo.as<double>();
   }
+  B->n_input = n;
+  const int32_t* d_gather = nullptr;
+  if (!device_inputs) {
+    B->gather = build_key_gather(E, t_point, n, t_min, t_max, 0, 0);
+    if (!B->gather.empty()) {
+      if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;
+      d_gather = B->d_gather.as<int32_t>();
+      n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
+    }
+  }
   CU(B->t_ns.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
   for (int k = 0; k < gstride; k++) CU(B->g[k].ensure(n * sizeof(double)));
@@ -1541,7 +1617,7 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
       geo_kind == 1 ? 1 : 0, ldq(S_LtoI), ldv(p_LinI), t_min, t_max,
       B->t_ns.as<int64_t>(), B->p[0].as<double>(), B->p[1].as<double>(), B->p[2].as<double>(), B->g[0].as<double>(),
       B->g[1].as<double>(), B->g[2].as<double>(), B->g[3].as<double>(), B->g[4].as<double>(), B->g[5].as<double>(),
-      geo_kind == 0 ? B->type.as<uint8_t>() : nullptr, E->d_counter.as<unsigned long long>());
+      geo_kind == 0 ? B->type.as<uint8_t>() : nullptr, E->d_counter.as<unsigned long long>(), d_gather);
   E->launches++;
   if (n_dropped) {  // the count is only read back (one synchronisation) when the caller asks for it
     unsigned long long dropped = 0;
@@ -1565,7 +1641,7 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
                          p_GinM[0] == 0.0 && p_GinM[1] == 0.0 && p_GinM[2] == 0.0;
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   if ((rc = plan_stream(E, B->ex, n, 3, kLoamMinB, false, 1, kLoamWarps))) return rc;
-  if ((rc = mark_ready(E, B->ex))) return rc;
+  if ((rc = mark_ready(E, B->ex, cs))) return rc;
   E->loam.push_back(std::move(B));
   E->layout_dirty = true;
   return CLIC_OK;
@@ -1614,6 +1690,14 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   if ((rc = to_device(E, r_t, timestamp, n)) || (rc = to_device(E, r_g, gyro, 3 * n)) ||
       (rc = to_device(E, r_a, accel, 3 * n)))
     return rc;
+  B->n_input = n;
+  B->gather = build_key_gather(E, timestamp, n, t_min, t_max, pad, (int64_t)E->h_state[E->sl.off_toff() + S]);
+  const int32_t* d_gather = nullptr;
+  if (!B->gather.empty()) {
+    if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;
+    d_gather = B->d_gather.as<int32_t>();
+    n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
+  }
   CU(B->t_ns.ensure(n * sizeof(int64_t)));
   for (int k = 0; k < 3; k++) {
     CU(B->gy[k].ensure(n * sizeof(double)));
@@ -1623,7 +1707,7 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   prep_imu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_g.as<double>(), r_a.as<double>(), t_min, t_max, pad, B->t_ns.as<int64_t>(),
       B->gy[0].as<double>(), B->gy[1].as<double>(), B->gy[2].as<double>(), B->ac[0].as<double>(),
-      B->ac[1].as<double>(), B->ac[2].as<double>(), E->d_counter.as<unsigned long long>());
+      B->ac[1].as<double>(), B->ac[2].as<double>(), E->d_counter.as<unsigned long long>(), d_gather);
   E->launches++;
   if (n_dropped) {
     unsigned long long dropped = 0;
@@ -1949,8 +2033,8 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   CU(cudaSetDevice(E->device));
   AllocScope alloc_scope(E->stream);
   int64_t total = 0;
-  if (stream == 0) for (auto& b : E->loam) total += b->st.n;
-  if (stream == 1) for (auto& b : E->imu) total += b->st.n;
+  if (stream == 0) for (auto& b : E->loam) total += b->n_input;
+  if (stream == 1) for (auto& b : E->imu) total += b->n_input;
   if (stream >= 2) for (auto& b : E->image) total += b->st.n;
   if (n_out) *n_out = total;
   if (capacity <= 0 || total == 0) return CLIC_OK;
@@ -1961,7 +2045,28 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   CU(cudaStreamSynchronize(E->stream));
   DevBuf ds, du;
   int64_t done = 0;
-  auto run = [&](int64_t n, const int64_t* t_ns, int64_t toff) -> int {
+  // gather: the batch is stored key-aligned (stored position -> input record, -1 padding): report in add order
+  auto run = [&](int64_t n, const int64_t* t_ns, int64_t toff, const std::vector<int32_t>* gather = nullptr,
+                 int64_t n_input = 0) -> int {
+    if (gather && !gather->empty()) {
+      if (n_input > capacity - done) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_get_indices: capacity too small");
+      CU(ds.ensure(n * sizeof(int32_t)));
+      CU(du.ensure(n * sizeof(double)));
+      index_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, E->stream>>>(n, t_ns, toff, E->t0_ns, E->dt_ns, E->K,
+                                                                           ds.as<int32_t>(), du.as<double>());
+      E->launches++;
+      std::vector<int32_t> ts((size_t)n);
+      std::vector<double> tu((size_t)n);
+      CU(cudaMemcpyAsync(ts.data(), ds.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
+      CU(cudaMemcpyAsync(tu.data(), du.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+      CU(cudaStreamSynchronize(E->stream));
+      for (int64_t o = 0; o < n; o++) {
+        const int32_t i = (*gather)[(size_t)o];
+        if (i >= 0) { s_out[done + i] = ts[(size_t)o]; u_out[done + i] = tu[(size_t)o]; }
+      }
+      done += n_input;
+      return CLIC_OK;
+    }
     int64_t m = std::min(n, capacity - done);
     if (m <= 0) return CLIC_OK;
     CU(ds.ensure(m * sizeof(int32_t)));
@@ -1977,9 +2082,10 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   };
   int rc = CLIC_OK;
   if (stream == 0)
-    for (auto& b : E->loam) if ((rc = run(b->st.n, b->st.t_ns, 0))) return rc;
+    for (auto& b : E->loam) if ((rc = run(b->st.n, b->st.t_ns, 0, &b->gather, b->n_input))) return rc;
   if (stream == 1)
-    for (auto& b : E->imu) if ((rc = run(b->st.n, b->st.t_ns, (int64_t)toff_d[CLIC_SENSOR_IMU]))) return rc;
+    for (auto& b : E->imu)
+      if ((rc = run(b->st.n, b->st.t_ns, (int64_t)toff_d[CLIC_SENSOR_IMU], &b->gather, b->n_input))) return rc;
   if (stream >= 2)
     for (auto& b : E->image) {
       const int64_t base = done;
@@ -2360,10 +2466,11 @@ size_t assoc_plan(AssocSide& s, size_t off) {
   s.o_valid = take((size_t)s.n_q);
   s.o_geo = take((size_t)6 * s.n_q * sizeof(double));
   s.o_nn = take((size_t)5 * s.n_q * sizeof(int));
-  s.o_out_t = take((size_t)s.n_q * sizeof(double));
-  s.o_out_pt = take((size_t)3 * s.n_q * sizeof(double));
-  s.o_out_geo = take((size_t)s.geo_w * s.n_q * sizeof(double));
-  s.o_out_src = take((size_t)s.n_q * sizeof(long long));
+  const size_t cap = (size_t)s.n_q + 32 * assoc_dev::kAlignKeys;  // key-aligned output: up to 31 holes per knot interval
+  s.o_out_t = take(cap * sizeof(double));
+  s.o_out_pt = take(3 * cap * sizeof(double));
+  s.o_out_geo = take(s.geo_w * cap * sizeof(double));
+  s.o_out_src = take(cap * sizeof(long long));
   return off;
 }
 }  // namespace
@@ -2641,6 +2748,9 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
     out.src[s] = jobs.j[s].out_src;
   }
   out.count = (long long*)base;
+  out.t0_ns = E->t0_ns;
+  out.dt_ns = E->dt_ns;
+  out.n_keys = key_align_enabled() ? E->K - 3 : 0;
   static const bool sort_attr = [] {
     return cudaFuncSetAttribute(assoc_dev::sort_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 assoc_dev::kSortMax * 12) == cudaSuccess;
@@ -2649,7 +2759,7 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
   assoc_dev::sort_downsample_kernel<<<1, 1024, assoc_dev::kSortMax * 12, st>>>(jobs, cor_downsample, out);
   m->launches += 1;
   E->launches += 3;
-  long long h_count[2] = {0, 0};
+  long long h_count[4] = {0, 0, 0, 0};  // stored (padded) lines, planes; kept lines, planes
   CU(cudaMemcpyAsync(h_count, base, sizeof(h_count), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
@@ -2665,9 +2775,10 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
     return rc;
   dropped += d1;
   CU(cudaStreamSynchronize(st));  // the scratch may be reused by the next call on any stream
-  if (n_lines) *n_lines = h_count[0];
-  if (n_planes) *n_planes = h_count[1];
-  if (n_dropped) *n_dropped = dropped;
+  if (n_lines) *n_lines = h_count[2];
+  if (n_planes) *n_planes = h_count[3];
+  // the holes of the key-aligned layout were stored as dropped records: they are not measurements
+  if (n_dropped) *n_dropped = dropped - (h_count[0] - h_count[2]) - (h_count[1] - h_count[3]);
   return CLIC_OK;
 }
 

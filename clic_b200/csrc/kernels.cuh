@@ -1211,29 +1211,37 @@ __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* poi
                                  const double* geo_plane, const double* geo_normal, const double* geo_point,
                                  Q4 S_LtoI, V3 p_LinI, int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0, double* p1, double* p2,
                                  double* g0, double* g1, double* g2, double* g3, double* g4, double* g5, uint8_t* type,
-                                 unsigned long long* n_dropped, int* bad_input) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                 unsigned long long* n_dropped, int* bad_input, const int32_t* gather) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // stored position
+  if (o >= n) return;
+  const int64_t i = gather ? gather[o] : o;                          // input record (-1: padding of a key-aligned batch)
+  if (i < 0) {
+    t_ns[o] = kDropped;
+    p0[o] = p1[o] = p2[o] = 0.0;
+    g0[o] = g1[o] = g2[o] = g3[o] = g4[o] = g5[o] = 0.0;
+    type[o] = 1;
+    return;
+  }
   int64_t t = (int64_t)(t_s[i] * 1e9);
   bool ok = !(t < t_lo || t >= t_hi);
-  t_ns[i] = ok ? t : kDropped;
+  t_ns[o] = ok ? t : kDropped;
   if (!ok) atomicAdd(n_dropped, 1ULL);
   const V3 pI = qrot(S_LtoI, mk(point[3 * i], point[3 * i + 1], point[3 * i + 2])) + p_LinI;  // LoamShared::point_in_imu
-  p0[i] = pI.x; p1[i] = pI.y; p2[i] = pI.z;
+  p0[o] = pI.x; p1[o] = pI.y; p2[o] = pI.z;
   const bool plane = geo_type[i] == 1;
-  type[i] = plane ? 1 : 0;
+  type[o] = plane ? 1 : 0;
   if ((plane && !geo_plane) || (!plane && (!geo_normal || !geo_point))) {  // record type present, its array missing
     *bad_input = 1;
-    t_ns[i] = kDropped;
-    g0[i] = g1[i] = g2[i] = g3[i] = g4[i] = g5[i] = 0.0;
+    t_ns[o] = kDropped;
+    g0[o] = g1[o] = g2[o] = g3[o] = g4[o] = g5[o] = 0.0;
     return;
   }
   if (plane) {
-    g0[i] = geo_plane[4 * i]; g1[i] = geo_plane[4 * i + 1]; g2[i] = geo_plane[4 * i + 2]; g3[i] = geo_plane[4 * i + 3];
-    g4[i] = 0.0; g5[i] = 0.0;
+    g0[o] = geo_plane[4 * i]; g1[o] = geo_plane[4 * i + 1]; g2[o] = geo_plane[4 * i + 2]; g3[o] = geo_plane[4 * i + 3];
+    g4[o] = 0.0; g5[o] = 0.0;
   } else {
-    g0[i] = geo_point[3 * i]; g1[i] = geo_point[3 * i + 1]; g2[i] = geo_point[3 * i + 2];
-    g3[i] = geo_normal[3 * i]; g4[i] = geo_normal[3 * i + 1]; g5[i] = geo_normal[3 * i + 2];
+    g0[o] = geo_point[3 * i]; g1[o] = geo_point[3 * i + 1]; g2[o] = geo_point[3 * i + 2];
+    g3[o] = geo_normal[3 * i]; g4[o] = geo_normal[3 * i + 1]; g5[o] = geo_normal[3 * i + 2];
   }
 }
 
@@ -1242,32 +1250,49 @@ __global__ void prep_loam_packed_kernel(int64_t n, const double* t_s, const doub
                                         const double* geo, int gstride, int fixed_plane, Q4 S_LtoI, V3 p_LinI,
                                         int64_t t_lo, int64_t t_hi, int64_t* t_ns, double* p0,
                                         double* p1, double* p2, double* g0, double* g1, double* g2, double* g3,
-                                        double* g4, double* g5, uint8_t* type, unsigned long long* n_dropped) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                        double* g4, double* g5, uint8_t* type, unsigned long long* n_dropped,
+                                        const int32_t* gather) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // stored position
+  if (o >= n) return;
+  const int64_t i = gather ? gather[o] : o;                          // input record (-1: padding of a key-aligned batch)
+  if (i < 0) {
+    t_ns[o] = kDropped;
+    p0[o] = p1[o] = p2[o] = 0.0;
+    if (type) type[o] = (unsigned char)fixed_plane;
+    g0[o] = g1[o] = g2[o] = g3[o] = 0.0;
+    if (gstride > 4) { g4[o] = 0.0; g5[o] = 0.0; }
+    return;
+  }
   int64_t t = (int64_t)(t_s[i] * 1e9);
   bool ok = !(t < t_lo || t >= t_hi);
-  t_ns[i] = ok ? t : kDropped;
+  t_ns[o] = ok ? t : kDropped;
   if (!ok) atomicAdd(n_dropped, 1ULL);
   const V3 pI = qrot(S_LtoI, mk(point[3 * i], point[3 * i + 1], point[3 * i + 2])) + p_LinI;  // LoamShared::point_in_imu
-  p0[i] = pI.x; p1[i] = pI.y; p2[i] = pI.z;
-  if (type) type[i] = geo_type ? (geo_type[i] == 1 ? 1 : 0) : (unsigned char)fixed_plane;
+  p0[o] = pI.x; p1[o] = pI.y; p2[o] = pI.z;
+  if (type) type[o] = geo_type ? (geo_type[i] == 1 ? 1 : 0) : (unsigned char)fixed_plane;
   const double* gi = geo + (size_t)gstride * i;
-  g0[i] = gi[0]; g1[i] = gi[1]; g2[i] = gi[2]; g3[i] = gi[3];
-  if (gstride > 4) { g4[i] = gi[4]; g5[i] = gi[5]; }
+  g0[o] = gi[0]; g1[o] = gi[1]; g2[o] = gi[2]; g3[o] = gi[3];
+  if (gstride > 4) { g4[o] = gi[4]; g5[o] = gi[5]; }
 }
 
 __global__ void prep_imu_kernel(int64_t n, const double* t_s, const double* gyro, const double* accel, int64_t t_lo,
                                 int64_t t_hi, int64_t pad, int64_t* t_ns, double* g0, double* g1, double* g2,
-                                double* a0, double* a1, double* a2, unsigned long long* n_dropped) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                double* a0, double* a1, double* a2, unsigned long long* n_dropped,
+                                const int32_t* gather) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // stored position
+  if (o >= n) return;
+  const int64_t i = gather ? gather[o] : o;                          // input record (-1: padding of a key-aligned batch)
+  if (i < 0) {
+    t_ns[o] = kDropped;
+    g0[o] = g1[o] = g2[o] = a0[o] = a1[o] = a2[o] = 0.0;
+    return;
+  }
   int64_t t = (int64_t)(t_s[i] * 1e9);
   bool ok = !(t - pad < t_lo || t + pad >= t_hi);
-  t_ns[i] = ok ? t : kDropped;
+  t_ns[o] = ok ? t : kDropped;
   if (!ok) atomicAdd(n_dropped, 1ULL);
-  g0[i] = gyro[3 * i]; g1[i] = gyro[3 * i + 1]; g2[i] = gyro[3 * i + 2];
-  a0[i] = accel[3 * i]; a1[i] = accel[3 * i + 1]; a2[i] = accel[3 * i + 2];
+  g0[o] = gyro[3 * i]; g1[o] = gyro[3 * i + 1]; g2[o] = gyro[3 * i + 2];
+  a0[o] = accel[3 * i]; a1[o] = accel[3 * i + 1]; a2[o] = accel[3 * i + 2];
 }
 
 // Index probe (clic_get_indices): s, u per factor of a stream at the current offset.

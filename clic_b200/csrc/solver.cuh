@@ -782,8 +782,12 @@ __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
     for (int i = threadIdx.x; i < n_state; i += blockDim.x) B.x[i] = B.cand[i];
     if (B.Hc) {  // the candidate was evaluated with its Jacobians: adopt its system, no further pass needed
       const int D = L.D;
-#pragma unroll 8
-      for (int i = threadIdx.x; i < D * D; i += blockDim.x) B.H[i] = B.Hc[i];
+      const int n2 = (D * D) >> 1;  // both buffers are 256-byte aligned: copy 16 bytes per thread and step
+      const double2* src = reinterpret_cast<const double2*>(B.Hc);
+      double2* dst = reinterpret_cast<double2*>(B.H);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+      if ((D & 1) && threadIdx.x == 0) B.H[D * D - 1] = B.Hc[D * D - 1];
       for (int i = threadIdx.x; i < D; i += blockDim.x) B.b[i] = B.bc[i];
       if (threadIdx.x < 2) B.cost_x[threadIdx.x] = B.cost_c[threadIdx.x];
     }

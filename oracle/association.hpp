@@ -18,6 +18,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
+#include <unordered_map>
 #include <vector>
 
 namespace assoc {
@@ -57,6 +59,60 @@ inline Neighbours knn5(const float* map, int64_t n_map, const float* q) {
   }
   return nb;
 }
+
+// The same exact search through a uniform 1 m grid, for the timed CPU baseline only (the reference walks a kd-tree;
+// an exhaustive scan would flatter the GPU).  Only neighbours inside the 1 m^2 gate can change the outcome, and those
+// lie in the cells within reach of the query, so the kept records are identical; neighbours outside the gate come back
+// as (+inf, INT32_MAX).  tests/test_association.py checks it against knn5.
+struct Grid {
+  std::unordered_map<uint64_t, std::vector<int>> cells;
+  static uint64_t key(int64_t cx, int64_t cy, int64_t cz) {
+    return ((uint64_t)(cx & 0x1fffff) << 42) | ((uint64_t)(cy & 0x1fffff) << 21) | (uint64_t)(cz & 0x1fffff);
+  }
+  void build(const float* map, int64_t n) {
+    cells.clear();
+    for (int64_t j = 0; j < n; j++) {
+      const float* p = map + 3 * j;
+      if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+      cells[key((int64_t)std::floor(p[0]), (int64_t)std::floor(p[1]), (int64_t)std::floor(p[2]))].push_back((int)j);
+    }
+  }
+  Neighbours knn5(const float* map, const float* q) const {
+    Neighbours nb;
+    for (int k = 0; k < 5; k++) {
+      nb.idx[k] = INT32_MAX;
+      nb.d2[k] = INFINITY;
+    }
+    if (!(std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]))) return nb;
+    const float amax = std::max(std::fabs(q[0]), std::max(std::fabs(q[1]), std::fabs(q[2])));
+    const float r = 1.0001f + 4e-7f * amax;  // reach of the gate plus the rounding of a float difference
+    int64_t lo[3], hi[3];
+    for (int c = 0; c < 3; c++) {
+      lo[c] = (int64_t)std::floor(q[c] - r);
+      hi[c] = (int64_t)std::floor(q[c] + r);
+    }
+    for (int64_t cx = lo[0]; cx <= hi[0]; cx++)
+      for (int64_t cy = lo[1]; cy <= hi[1]; cy++)
+        for (int64_t cz = lo[2]; cz <= hi[2]; cz++) {
+          auto it = cells.find(key(cx, cy, cz));
+          if (it == cells.end()) continue;
+          for (int j : it->second) {
+            const float d = sq_dist(q, map + 3 * (size_t)j);
+            if (!(d <= 1.0f)) continue;
+            if (!(d < nb.d2[4] || (d == nb.d2[4] && j < nb.idx[4]))) continue;
+            int k = 4;
+            while (k > 0 && (d < nb.d2[k - 1] || (d == nb.d2[k - 1] && j < nb.idx[k - 1]))) {
+              nb.d2[k] = nb.d2[k - 1];
+              nb.idx[k] = nb.idx[k - 1];
+              k--;
+            }
+            nb.d2[k] = d;
+            nb.idx[k] = j;
+          }
+        }
+    return nb;
+  }
+};
 
 inline float hyp(float a, float b) { return (float)std::sqrt((double)a * (double)a + (double)b * (double)b); }
 

@@ -1441,7 +1441,16 @@ CLIC_API int clic_query_poses(clic_estimator* E, int64_t n, const double* t_s, c
 struct clic_feature_map {
   std::vector<float> surf, corner;
   std::vector<int32_t> nn[2];
+  assoc::Grid grid[2];  // corner, surface: built only in grid-search mode
+  bool use_grid = false;
 };
+static bool g_assoc_grid = false;
+// Oracle-only switch for the timed CPU baseline: 0 exhaustive search (the definition), 1 the same search through a
+// uniform grid.  Applies to feature maps created afterwards.
+CLIC_API int clic_oracle_set_association_search(int mode) {
+  g_assoc_grid = mode != 0;
+  return CLIC_OK;
+}
 
 CLIC_API int clic_feature_map_create(const float* surf_xyz, int64_t n_surf, const float* corner_xyz, int64_t n_corner,
                                      clic_feature_map** out) {
@@ -1450,6 +1459,11 @@ CLIC_API int clic_feature_map_create(const float* surf_xyz, int64_t n_surf, cons
   auto* m = new clic_feature_map;
   m->surf.assign(surf_xyz, surf_xyz + 3 * n_surf);
   if (n_corner > 0) m->corner.assign(corner_xyz, corner_xyz + 3 * n_corner);
+  m->use_grid = g_assoc_grid;
+  if (m->use_grid) {
+    m->grid[0].build(m->corner.data(), n_corner);
+    m->grid[1].build(m->surf.data(), n_surf);
+  }
   *out = m;
   return CLIC_OK;
 }
@@ -1483,7 +1497,8 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
   if (n_corner > 0 && n_map_c > 10) {  // lidar_odometry.cpp:502
     const int64_t step = n_corner / 1500 + 1;
     for (int64_t i = 0; i < n_corner; i += step) {
-      const assoc::Neighbours nb = assoc::knn5(m->corner.data(), n_map_c, corner_xyz_M + 3 * i);
+      const assoc::Neighbours nb = m->use_grid ? m->grid[0].knn5(m->corner.data(), corner_xyz_M + 3 * i)
+                                               : assoc::knn5(m->corner.data(), n_map_c, corner_xyz_M + 3 * i);
       for (int k = 0; k < 5; k++) m->nn[0].push_back(nb.d2[k] <= 1.0f ? nb.idx[k] : INT32_MAX);
       if (!(nb.d2[4] <= 1.0f)) continue;  // ":508"
       gather(m->corner, nb);
@@ -1506,7 +1521,8 @@ CLIC_API int clic_find_correspondence(clic_feature_map* m, int64_t n_corner, con
         m->nn[1].insert(m->nn[1].end(), 5, -1);
         continue;
       }
-      const assoc::Neighbours nb = assoc::knn5(m->surf.data(), n_map_s, surf_xyz_M + 3 * i);
+      const assoc::Neighbours nb = m->use_grid ? m->grid[1].knn5(m->surf.data(), surf_xyz_M + 3 * i)
+                                               : assoc::knn5(m->surf.data(), n_map_s, surf_xyz_M + 3 * i);
       for (int k = 0; k < 5; k++) m->nn[1].push_back(nb.d2[k] <= 1.0f ? nb.idx[k] : INT32_MAX);
       if (!(nb.d2[4] <= 1.0f)) continue;  // ":584"; fewer than 5 map points leaves +inf here (":593")
       gather(m->surf, nb);

@@ -246,3 +246,19 @@ def test_gpu_add_loam_from_scan(cuda, oracle, ds):
     assert (np.abs(Hc - Ho) / np.outer(d, d)).max() < 1e-9
     assert (np.abs(bc - bo) / d).max() <= 1e-9 * (np.abs(bo) / d).max()
     assert abs(cc - co) <= 1e-9 * abs(co)
+
+
+def test_oracle_grid_search_equals_exhaustive_search(oracle):
+    """The grid-accelerated search that only the timed CPU baseline uses returns the same records and neighbours."""
+    sc = S.make_feature_scene(n_map_surf=8000, n_map_corner=1200, n_surf=900, n_corner=400, seed=13)
+    sc.map_surf = np.concatenate([sc.map_surf, sc.map_surf[:300]])     # exact ties
+    sc.surf_M[5] = np.nan
+    ref, nn_ref = _run(oracle, sc)
+    oracle.clic_oracle_set_association_search(1)
+    try:
+        grid, nn_grid = _run(oracle, sc)
+    finally:
+        oracle.clic_oracle_set_association_search(0)
+    _assert_identical(ref, grid)
+    for a, b in zip(nn_ref, nn_grid):
+        assert np.array_equal(a, b)
