@@ -915,9 +915,9 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   const size_t sm_small = 1024 * sizeof(double);
   size_t sm_step = (size_t)(512 + 3 * D + ((D + 7) / 8) * 64) * sizeof(double);
   int a_in_smem = 0;
-  if (sm_step + (size_t)D * (D | 1) * sizeof(double) <= 200 * 1024) {
+  if (sm_step + (size_t)(D + 1) * (D | 1) * sizeof(double) <= 200 * 1024) {
     a_in_smem = 1;
-    sm_step += (size_t)D * (D | 1) * sizeof(double);
+    sm_step += (size_t)(D + 1) * (D | 1) * sizeof(double);  // + one row: the right-hand side of the D <= 96 path
   } else {
     sm_step += (size_t)(D + kNB) * kPanStride * sizeof(double);  // staged panel (A stays in L2-resident global memory)
   }

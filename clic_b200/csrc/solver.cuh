@@ -235,15 +235,87 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
   }
 }
 
+// The same factorization with one panel of look-ahead, for A in shared memory: after the panel solve the next block
+// column is updated first, then warp 0 factors the next diagonal block while the other warps update the rest of the
+// trailing matrix — the serial 8-column elimination (about half of a panel step at n ~ 100) leaves the critical path.
+// Same operations on every entry in the same order as cta_cholesky, so the factor is identical bit for bit.
+__device__ __forceinline__ void cta_cholesky_lookahead(double* A, int ld, int n, int* ok, double* dinv, int n_rows = 0) {
+  if (n_rows < n) n_rows = n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, n_warps = nt >> 5;
+  if (tid < 32) warp_diag_block(A, ld, 0, min(kNB, n), dinv, ok, tid, nullptr);
+  __syncthreads();
+  if (!*ok) return;
+  for (int kb = 0; kb < n; kb += kNB) {
+    const int nb = min(kNB, n - kb);
+    const int r0 = kb + nb;
+    // panel: L[i, panel] = A[i, panel] * Lkk^-T by forward substitution along the row
+    for (int i = r0 + tid; i < n_rows; i += nt) {
+      double x[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; c++) {
+        if (c < nb) {
+          double v = A[(size_t)i * ld + kb + c];
+#pragma unroll
+          for (int k = 0; k < kNB; k++)
+            if (k < c) v -= x[k] * A[(size_t)(kb + c) * ld + kb + k];
+          x[c] = v * dinv[kb + c];
+        } else {
+          x[c] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kNB; c++)
+        if (c < nb) A[(size_t)i * ld + kb + c] = x[c];
+    }
+    __syncthreads();
+    if (r0 >= n) break;
+    const int nb1 = min(kNB, n - r0);
+    // next block column first: entries (i, j), j in [r0, r0 + nb1), j <= i
+    for (int idx = tid; idx < (n_rows - r0) * kNB; idx += nt) {
+      const int i = r0 + (idx >> 3), j = r0 + (idx & 7);
+      if (j <= i && j < r0 + nb1) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < kNB; c++)
+          if (c < nb) acc += A[(size_t)i * ld + kb + c] * A[(size_t)j * ld + kb + c];
+        A[(size_t)i * ld + j] -= acc;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      warp_diag_block(A, ld, r0, nb1, dinv, ok, lane, nullptr);
+    } else {  // the rest of the trailing lower triangle: columns j >= r0 + nb1
+      const int c0 = r0 + nb1;
+      for (int i = c0 + warp - 1; i < n_rows; i += n_warps - 1) {
+        double li[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; c++) li[c] = c < nb ? A[(size_t)i * ld + kb + c] : 0.0;
+        for (int j = c0 + lane; j <= i && j < n; j += 32) {
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < kNB; c++)
+            if (c < nb) acc += li[c] * A[(size_t)j * ld + kb + c];
+          A[(size_t)i * ld + j] -= acc;
+        }
+      }
+    }
+    __syncthreads();
+    if (!*ok) return;
+  }
+}
+
 // Both triangular solves by ONE warp (n <= 96: three unknowns per lane), no block barriers: y <- L^-1 y, y <- L^-T y.
 // Lane l owns y[l], y[l + 32], y[l + 64].  With an odd leading dimension the column reads of the forward sweep are
 // conflict-free.
-__device__ __forceinline__ void warp_cholesky_solve(const double* A, int ld, int n, double* y, const double* dinv, int lane) {
+// forward = false: y already holds L^-1 y (the right-hand side rode along the factorization as an extra row).
+__device__ __forceinline__ void warp_cholesky_solve(const double* A, int ld, int n, double* y, const double* dinv, int lane,
+                                                    bool forward = true) {
   const unsigned full = 0xffffffffu;
   double v[3];
 #pragma unroll
   for (int q = 0; q < 3; q++) v[q] = lane + 32 * q < n ? y[lane + 32 * q] : 0.0;
-  for (int i = 0; i < n; i++) {  // forward: y_i /= L_ii; y_r -= L_ri y_i for r > i
+  for (int i = 0; forward && i < n; i++) {  // forward: y_i /= L_ii; y_r -= L_ri y_i for r > i
     const int q = i >> 5;
     double yi = (q == 0 ? v[0] : q == 1 ? v[1] : v[2]);
     yi = __shfl_sync(full, yi, i & 31) * dinv[i];
@@ -603,16 +675,21 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   // dense Cholesky A = L L^T (lower, in place), blocked right-looking (cta_cholesky)
   __shared__ int ok;
   if (tid == 0) ok = 1;
+  // D <= 96: the scaled gradient rides along the factorization as row D of A and comes out as L^-1 g~ (the forward
+  // substitution costs no extra serial sweep); the host sized A for D + 1 rows
+  if (warp_solve)
+    for (int j = tid; j < D; j += nt) A[(size_t)D * ld + j] = gs[j];
   __syncthreads();
-  cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv, nullptr, pan);
+  if (warp_solve && a_in_smem) cta_cholesky_lookahead(A, ld, D, &ok, dinv, D + 1);
+  else cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv, nullptr, pan, warp_solve ? D + 1 : 0);
   __syncthreads();
   int valid = ok;
   // forward / backward substitution: (L L^T) z = g~, step = -z
   if (valid) {
-    for (int i = tid; i < D; i += nt) y[i] = gs[i];
+    for (int i = tid; i < D; i += nt) y[i] = warp_solve ? A[(size_t)D * ld + i] : gs[i];
     __syncthreads();
     if (warp_solve) {
-      if (tid < 32) warp_cholesky_solve(A, ld, D, y, dinv, tid);
+      if (tid < 32) warp_cholesky_solve(A, ld, D, y, dinv, tid, false);
       __syncthreads();
     } else {
       cta_cholesky_solve(A, ld, D, y, Linv);
