@@ -547,7 +547,7 @@ int launch_prior(clic_estimator* E, clic_estimator::PriorRef* pr, const double* 
   const int n = pr->p->n, nb = (int)pr->p->blocks.size();
   const int D = std::max(1, E->L.D);
   size_t smem = (size_t)3 * n * sizeof(double) + (size_t)n * sizeof(int);
-  CU(launch_pdl(prior_kernel, 1, 256, smem, E->stream, pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
+  CU(launch_pdl(prior_kernel, 1, 1024, smem, E->stream, pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
                 pr->x0.as<double>(), pr->meta.as<int>(), n, nb, state, Hp, bp, D, cost2, jac ? 1 : 0,
                 ctl));
   E->launches++;
@@ -1279,7 +1279,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     CU(cudaMemcpyAsync(pr->meta.p, pr->h_meta.data(), pr->h_meta.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
     const int pn = pr->p->n;
     size_t smem = (size_t)3 * pn * sizeof(double) + (size_t)pn * sizeof(int);
-    prior_kernel<<<1, 256, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
+    prior_kernel<<<1, 1024, smem, E->stream>>>(pr->J0.as<double>(), pr->A.as<double>(), pr->r0.as<double>(),
                                               pr->x0.as<double>(), pr->meta.as<int>(), pn, nb, E->d_state.as<double>(),
                                               d_A.as<double>(), d_b.as<double>(), pos, d_cost.as<double>(), 1, nullptr);
     E->launches++;

@@ -66,28 +66,37 @@ __global__ void prior_kernel(const double* J0, const double* A, const double* r0
     if (col >= 0) any_free = 1;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int t = warp; t < n; t += n_warps) {  // one warp per row of J0: coalesced loads, fixed-order butterfly sum
     double acc = 0.0;
-    for (int c = 0; c < n; c++) acc += J0[(size_t)t * n + c] * dx[c];
-    r[t] = r0[t] + acc;
+    for (int c = lane; c < n; c += 32) acc += J0[(size_t)t * n + c] * dx[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) r[t] = r0[t] + acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     double c = 0.0;
-    for (int t = 0; t < n; t++) c += r[t] * r[t];
-    cost2[any_free ? 0 : 1] += 0.5 * c;
+    for (int t = lane; t < n; t += 32) c += r[t] * r[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cost2[any_free ? 0 : 1] += 0.5 * c;
   }
   if (!jac) return;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {  // column t of J0: coalesced across threads
     double acc = 0.0;
+#pragma unroll 8
     for (int k = 0; k < n; k++) acc += J0[(size_t)k * n + t] * r[k];
     g[t] = acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int a = e / n, c = e % n;
-    const int ca = tcol[a], cc = tcol[c];
-    if (ca >= 0 && cc >= 0) H[(size_t)ca * D + cc] += A[(size_t)a * n + c];
+  for (int a = warp; a < n; a += n_warps) {
+    const int ca = tcol[a];
+    if (ca < 0) continue;
+    for (int c = lane; c < n; c += 32) {
+      const int cc = tcol[c];
+      if (cc >= 0) H[(size_t)ca * D + cc] += A[(size_t)a * n + c];
+    }
   }
   for (int a = threadIdx.x; a < n; a += blockDim.x)
     if (tcol[a] >= 0) b[tcol[a]] += g[a];
