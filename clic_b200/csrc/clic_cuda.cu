@@ -809,8 +809,8 @@ int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
 // With 10^5-10^6 factors per window that never matters; at the reference's production size (a few hundred LiDAR and
 // ~100 IMU factors over ~10 intervals) nearly every slab straddles 2-4 intervals.  For a small, time-sorted batch the
 // host therefore starts every interval's factors on a slab boundary (padding entries are stored as dropped factors):
-// one round per slab, and the slabs of different intervals run on different warps.  Sums per interval keep their
-// order, so H, b are unchanged bit for bit.  Returns an empty map when the batch is large, unsorted, or already aligned.
+// one round per slab, and the slabs of different intervals run on different warps.  Only the grouping of the sums
+// changes (H, b move by rounding, ~1e-16).  Returns an empty map when the batch is large, unsorted, or already aligned.
 // t_s: the caller's timestamps; shift_ns: what the factor adds before indexing ((int64) time offset for the IMU).
 constexpr int64_t kKeyAlignMax = 1 << 15;
 bool key_align_enabled() { static const bool v = getenv("CLIC_NO_KEY_ALIGN") == nullptr; return v; }

@@ -282,3 +282,42 @@ def test_c3_free_inverse_depths(cuda, oracle, unlock_cam_toff):
         compare_eval(cuda, oracle, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=unlock_cam_toff, pad=1_000_000)
     finally:
         del os.environ["CLIC_NO_POSE_PACKS"]
+
+
+@pytest.mark.gpu
+def test_key_aligned_storage_is_a_layout_change_only(tmp_path):
+    """Small time-sorted batches are stored with every knot interval's factors on a 32-factor slab boundary
+    (build_key_gather).  It is a layout change only: the index probe must not move by a bit and H, b, cost only by the
+    rounding of a different summation grouping, against the plain layout (CLIC_NO_KEY_ALIGN=1, read once per process,
+    hence the two subprocesses)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from clic_b200 import estimator as E, synthetic as S
+lib = E.cuda_library()
+sw = S.make_window(14, n_lidar=700, n_imu=125, n_landmarks=12, obs_per_landmark=6, line_fraction=0.4, seed=77)
+opt = E.default_options(lib); opt.lock_ab = opt.lock_wb = 0
+est = E.TrajectoryEstimator(sw.window, opt, lib); est.SetFixedIndex(1)
+S.add_all_factors(est, sw)
+H, b, c, _ = est.Evaluate()
+s0, u0 = est.indices(0); s1, u1 = est.indices(1)
+np.savez(sys.argv[1], H=H, b=b, c=c, s0=s0, u0=u0, s1=s1, u1=u1)
+''' % root
+    out = {}
+    for name, env in (("aligned", {}), ("plain", {"CLIC_NO_KEY_ALIGN": "1"})):
+        path = str(tmp_path / (name + ".npz"))
+        r = subprocess.run([sys.executable, "-c", code, path], env={**os.environ, **env}, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = np.load(path)
+    for k in ("s0", "u0", "s1", "u1"):
+        assert np.array_equal(out["aligned"][k], out["plain"][k]), k
+    Ha, Hp = out["aligned"]["H"], out["plain"]["H"]
+    d = np.sqrt(np.maximum(np.diag(Hp), 1e-300))
+    assert (np.abs(Ha - Hp) / np.outer(d, d)).max() < 1e-13
+    assert (np.abs(out["aligned"]["b"] - out["plain"]["b"]) / d).max() <= 1e-12 * (np.abs(out["plain"]["b"]) / d).max()
+    assert abs(out["aligned"]["c"] - out["plain"]["c"]) <= 1e-13 * abs(out["plain"]["c"])
