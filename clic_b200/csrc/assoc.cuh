@@ -353,11 +353,18 @@ __global__ void __launch_bounds__(kWarps * 32) knn5_partial_kernel(AssocJobs job
 #pragma unroll 2
     for (int j = lane; j < tn; j += 32) {
       const float px = sx[j], py = sy[j], pz = sz[j];
+      float d[kQPW];
+      bool any = false;
 #pragma unroll
       for (int k = 0; k < kQPW; k++) {
         const float dx = fsub(qx[k], px), dy = fsub(qy[k], py), dz = fsub(qz[k], pz);
-        const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // flann::L2_Simple<float>
-        if (d < b[k].d[4]) best5_insert(b[k], d, base + j);
+        d[k] = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // flann::L2_Simple<float>
+        any |= d[k] < b[k].d[4];
+      }
+      if (any) {  // one rarely taken branch per point instead of one per (point, feature)
+#pragma unroll
+        for (int k = 0; k < kQPW; k++)
+          if (d[k] < b[k].d[4]) best5_insert(b[k], d[k], base + j);
       }
     }
   }
