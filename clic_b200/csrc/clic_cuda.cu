@@ -2796,4 +2796,12 @@ CLIC_API int clic_correspondence_neighbours(clic_feature_map* m, int32_t type, i
   return CLIC_OK;
 }
 
+#ifdef CLIC_LM_TIMING
+CLIC_API int clic_debug_lm_stamps(long long* out /*16*/) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out, clic::g_lm_stamps, 16 * sizeof(long long)));
+  return CLIC_OK;
+}
+#endif
+
 }  // extern "C"

@@ -119,33 +119,38 @@ constexpr int kNB = 8;
 __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* dinv, int* ok, int lane,
                                                 const double* dtol = nullptr) {
   const unsigned full = 0xffffffffu;
-  double a[kNB];
+  double a[kNB], invs[kNB];
 #pragma unroll
   for (int c = 0; c < kNB; c++) a[c] = (lane < nb && c <= lane) ? A[(size_t)(kb + lane) * ld + kb + c] : 0.0;
+  // This is the serial critical path of the whole factorization and it runs in ONE warp, so what counts is the number
+  // of dependent instructions per column.  Branch-free on purpose: lanes above the diagonal carry values nobody reads
+  // (entries with c > lane are never shuffled from nor stored), a failed pivot is replaced by 1 and reported once.
+  bool any_bad = false;
 #pragma unroll
   for (int j = 0; j < kNB; j++) {
     double d = __shfl_sync(full, a[j], j);
-    if (j < nb) {
-      if (!(d > (dtol ? dtol[kb + j] : 0.0)) || !isfinite(d)) {
-        if (lane == 0) *ok = 0;
-        d = 1.0;
-      }
-    } else {
-      d = 1.0;
-    }
-    // 1/sqrt(d) refined by one Newton step to full precision, pivot = d * (1/sqrt(d)): ~1/4 of the dependent
-    // latency of sqrt() followed by a division, on the serial critical path of the factorization
-    double inv = rsqrt(d);
-    inv = inv * (1.5 - 0.5 * d * inv * inv);
-    const double piv = d * inv;
-    if (lane == j) a[j] = piv; else if (lane > j) a[j] = a[j] * inv;
-    if (lane == 0 && j < nb) dinv[kb + j] = inv;
+    const bool bad = (j < nb) && (!(d > (dtol ? dtol[kb + j] : 0.0)) || !isfinite(d));
+    any_bad |= bad;
+    d = (bad || j >= nb) ? 1.0 : d;
+    // 1/sqrt(d): the hardware approximation (MUFU.RSQ64H, ~2^-22) refined by two Newton steps to full precision;
+    // pivot = d * (1/sqrt(d)) falls out of the same multiply as the column scaling (lane j holds d in a[j]).
+    // The library rsqrt() and sqrt() + division put several times more dependent instructions here.
+    double inv;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
+    const double hd = 0.5 * d;
+    inv = inv * (1.5 - hd * inv * inv);
+    inv = inv * (1.5 - hd * inv * inv);
+    invs[j] = inv;
+    a[j] = (lane == j ? d : a[j]) * inv;
     const double lij = a[j];
 #pragma unroll
-    for (int c = j + 1; c < kNB; c++) {
-      const double lcj = __shfl_sync(full, lij, c);
-      if (lane >= c) a[c] -= lij * lcj;
-    }
+    for (int c = j + 1; c < kNB; c++) a[c] -= lij * __shfl_sync(full, lij, c);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kNB; j++)
+      if (j < nb) dinv[kb + j] = invs[j];
+    if (any_bad) *ok = 0;
   }
 #pragma unroll
   for (int c = 0; c < kNB; c++)
@@ -244,6 +249,16 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
   }
 }
 
+#ifdef CLIC_LM_TIMING  // developer build: phase time stamps of the last lm_step_kernel launch (bench_micro/lm_timeline.py)
+__device__ long long g_lm_stamps[16];
+#define LM_STAMP(i) do { if (threadIdx.x == 0) g_lm_stamps[i] = clock64(); } while (0)
+#define LM_ACC(i, t0) do { if (threadIdx.x == 0) g_lm_stamps[i] += clock64() - (t0); } while (0)
+#define LM_NOW() clock64()
+#else
+#define LM_STAMP(i) do { } while (0)
+#define LM_ACC(i, t0) do { } while (0)
+#define LM_NOW() 0
+#endif
 // The same factorization with one panel of look-ahead, for A in shared memory: after the panel solve the next block
 // column is updated first, then warp 0 factors the next diagonal block while the other warps update the rest of the
 // trailing matrix — the serial 8-column elimination (about half of a panel step at n ~ 100) leaves the critical path.
@@ -255,9 +270,13 @@ __device__ __forceinline__ void cta_cholesky_lookahead(double* A, int ld, int n,
   if (tid < 32) warp_diag_block(A, ld, 0, min(kNB, n), dinv, ok, tid, nullptr);
   __syncthreads();
   if (!*ok) return;
+#ifdef CLIC_LM_TIMING
+  if (tid == 0) for (int i = 9; i < 16; i++) g_lm_stamps[i] = 0;
+#endif
   for (int kb = 0; kb < n; kb += kNB) {
     const int nb = min(kNB, n - kb);
     const int r0 = kb + nb;
+    long long tp0 = LM_NOW();
     // panel: L[i, panel] = A[i, panel] * Lkk^-T by forward substitution along the row
     for (int i = r0 + tid; i < n_rows; i += nt) {
       double x[kNB];
@@ -278,8 +297,10 @@ __device__ __forceinline__ void cta_cholesky_lookahead(double* A, int ld, int n,
         if (c < nb) A[(size_t)i * ld + kb + c] = x[c];
     }
     __syncthreads();
+    LM_ACC(9, tp0);
     if (r0 >= n) break;
     const int nb1 = min(kNB, n - r0);
+    tp0 = LM_NOW();
     // next block column first: entries (i, j), j in [r0, r0 + nb1), j <= i
     for (int idx = tid; idx < (n_rows - r0) * kNB; idx += nt) {
       const int i = r0 + (idx >> 3), j = r0 + (idx & 7);
@@ -292,8 +313,11 @@ __device__ __forceinline__ void cta_cholesky_lookahead(double* A, int ld, int n,
       }
     }
     __syncthreads();
+    LM_ACC(10, tp0);
+    tp0 = LM_NOW();
     if (warp == 0) {
       warp_diag_block(A, ld, r0, nb1, dinv, ok, lane, nullptr);
+      LM_ACC(11, tp0);
     } else {  // the rest of the trailing lower triangle: columns j >= r0 + nb1
       const int c0 = r0 + nb1;
       for (int i = c0 + warp - 1; i < n_rows; i += n_warps - 1) {
@@ -310,6 +334,7 @@ __device__ __forceinline__ void cta_cholesky_lookahead(double* A, int ld, int n,
       }
     }
     __syncthreads();
+    LM_ACC(12, tp0);
     if (!*ok) return;
   }
 }
@@ -335,16 +360,33 @@ __device__ __forceinline__ void warp_cholesky_solve(const double* A, int ld, int
       if (r > i && r < n) v[p] -= A[(size_t)r * ld + i] * yi;
     }
   }
-  for (int i = n - 1; i >= 0; i--) {  // backward: y_i /= L_ii; y_r -= L_ir y_i for r < i
-    const int q = i >> 5;
-    double yi = (q == 0 ? v[0] : q == 1 ? v[1] : v[2]);
-    yi = __shfl_sync(full, yi, i & 31) * dinv[i];
-    if (lane == (i & 31)) { if (q == 0) v[0] = yi; else if (q == 1) v[1] = yi; else v[2] = yi; }
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-      const int r = lane + 32 * p;
-      if (r < i) v[p] -= A[(size_t)i * ld + r] * yi;
+  // backward: y_i /= L_ii; y_r -= L_ir y_i for r < i.  One warp, n dependent steps: the row of L and 1 / L_ii of the
+  // NEXT step are loaded before the shuffle of this one, and the three 32-row segments use their registers statically,
+  // so a step is shuffle -> multiply -> FMA on the dependent chain and nothing else.
+  {
+    int i = n - 1;
+    double di = i >= 0 ? dinv[i] : 0.0;
+    double r0v = (i >= 0 && lane < i) ? A[(size_t)i * ld + lane] : 0.0;
+    double r1v = (i >= 0 && lane + 32 < i) ? A[(size_t)i * ld + lane + 32] : 0.0;
+    double r2v = (i >= 0 && lane + 64 < i) ? A[(size_t)i * ld + lane + 64] : 0.0;
+#define CLIC_BACK_STEP(VQ)                                                                   \
+    {                                                                                        \
+      const int in = i - 1;                                                                  \
+      const double dn = in >= 0 ? dinv[in] : 0.0;                                            \
+      const double n0 = (in >= 0 && lane < in) ? A[(size_t)in * ld + lane] : 0.0;            \
+      const double n1 = (in >= 0 && lane + 32 < in) ? A[(size_t)in * ld + lane + 32] : 0.0;  \
+      const double n2 = (in >= 0 && lane + 64 < in) ? A[(size_t)in * ld + lane + 64] : 0.0;  \
+      const double yi = __shfl_sync(full, VQ, i & 31) * di;                                  \
+      if (lane == (i & 31)) VQ = yi;                                                         \
+      v[0] -= r0v * yi;                                                                      \
+      v[1] -= r1v * yi;                                                                      \
+      v[2] -= r2v * yi;                                                                      \
+      di = dn; r0v = n0; r1v = n1; r2v = n2;                                                 \
     }
+    for (; i >= 64; i--) CLIC_BACK_STEP(v[2])
+    for (; i >= 32; i--) CLIC_BACK_STEP(v[1])
+    for (; i >= 0; i--) CLIC_BACK_STEP(v[0])
+#undef CLIC_BACK_STEP
   }
 #pragma unroll
   for (int q = 0; q < 3; q++)
@@ -621,6 +663,46 @@ __global__ void lm_init_kernel(LmBufs B, LayoutDev L, LmConst C, int max_iterati
 
 // One LM iteration, first half: termination tests, damping, Cholesky, step, model decrease, candidate = x (+) delta.
 // A lives in shared memory when it fits (a_in_smem), else in global scratch.
+// lm_step_kernel's middle: A = H~ + diag(diagonal / radius), Cholesky, (L L^T) y = g~.  Returns 0 if a pivot failed.
+__device__ __forceinline__ int lm_factor_solve(double* A, int ld, int D, const LmBufs& B, const double* gs, double* y,
+                                               double* dinv, double* Linv, double* pan, double radius, bool warp_solve,
+                                               bool a_in_smem, int* ok) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid >> 5; i < D; i += nt >> 5) {  // warps stride the rows, lanes the columns
+    const double si = B.scale[i];
+    for (int j = tid & 31; j < D; j += 32) {
+      double v = B.H[(size_t)i * D + j] * si * B.scale[j];
+      if (i == j) {
+        double lm = sqrt(B.diagonal[i] / radius);
+        v += lm * lm;
+      }
+      A[(size_t)i * ld + j] = v;
+    }
+  }
+  // D <= 96: the scaled gradient rides along the factorization as row D of A and comes out as L^-1 g~ (the forward
+  // substitution costs no extra serial sweep); the host sized A for D + 1 rows
+  if (warp_solve)
+    for (int j = tid; j < D; j += nt) A[(size_t)D * ld + j] = gs[j];
+  __syncthreads();
+  LM_STAMP(2);
+  // dense Cholesky A = L L^T (lower, in place), blocked right-looking
+  if (warp_solve && a_in_smem) cta_cholesky_lookahead(A, ld, D, ok, dinv, D + 1);
+  else cta_cholesky(A, ld, D, ok, dinv, warp_solve ? nullptr : Linv, nullptr, pan, warp_solve ? D + 1 : 0);
+  __syncthreads();
+  LM_STAMP(3);
+  if (!*ok) return 0;
+  // forward / backward substitution: (L L^T) z = g~
+  for (int i = tid; i < D; i += nt) y[i] = warp_solve ? A[(size_t)D * ld + i] : gs[i];
+  __syncthreads();
+  if (warp_solve) {
+    if (tid < 32) warp_cholesky_solve(A, ld, D, y, dinv, tid, false);
+    __syncthreads();
+  } else {
+    cta_cholesky_solve(A, ld, D, y, Linv);
+  }
+  return 1;
+}
+
 __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmConst C, int a_in_smem, int is_constrained) {
   pdl_wait();
   pdl_trigger();
@@ -647,13 +729,13 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
   }
   __syncthreads();
   if (!go) return;
+  LM_STAMP(0);
   double* red = sh;               // 512 doubles of reduction scratch
   double* gs = sh + 512;          // D scaled gradient
   double* y = gs + D;             // D
   double* dinv = y + D;           // D: 1 / L_jj
   double* Linv = dinv + D;        // ceil(D / 8) * 64 doubles: inverses of the diagonal blocks (block solves, D > 96)
   double* after_linv = Linv + ((D + kNB - 1) / kNB) * kNB * kNB;
-  double* A = a_in_smem ? after_linv : B.A;
   double* pan = a_in_smem ? nullptr : after_linv;  // (D + kNB) * kPanStride doubles: staged panel of the global path
   const int ld = a_in_smem ? (D | 1) : D;  // odd leading dimension in shared memory: conflict-free column reads
   const bool warp_solve = D <= 96;
@@ -669,40 +751,17 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     }
   }
   __syncthreads();
-  for (int i = tid >> 5; i < D; i += nt >> 5) {  // warps stride the rows, lanes the columns
-    const double si = B.scale[i];
-    for (int j = tid & 31; j < D; j += 32) {
-      double v = B.H[(size_t)i * D + j] * si * B.scale[j];
-      if (i == j) {
-        double lm = sqrt(B.diagonal[i] / radius);
-        v += lm * lm;
-      }
-      A[(size_t)i * ld + j] = v;
-    }
-  }
-  __syncthreads();
-  // dense Cholesky A = L L^T (lower, in place), blocked right-looking (cta_cholesky)
+  LM_STAMP(1);
+  // Build A = H~ + diag(diagonal / radius), factor it, solve.  Two inlined copies of the same code, so that the copy
+  // working in shared memory addresses it with shared-memory instructions (the run-time choice of A would make every
+  // access in the factorization a slower generic one).
   __shared__ int ok;
   if (tid == 0) ok = 1;
-  // D <= 96: the scaled gradient rides along the factorization as row D of A and comes out as L^-1 g~ (the forward
-  // substitution costs no extra serial sweep); the host sized A for D + 1 rows
-  if (warp_solve)
-    for (int j = tid; j < D; j += nt) A[(size_t)D * ld + j] = gs[j];
-  __syncthreads();
-  if (warp_solve && a_in_smem) cta_cholesky_lookahead(A, ld, D, &ok, dinv, D + 1);
-  else cta_cholesky(A, ld, D, &ok, dinv, warp_solve ? nullptr : Linv, nullptr, pan, warp_solve ? D + 1 : 0);
-  __syncthreads();
-  int valid = ok;
-  // forward / backward substitution: (L L^T) z = g~, step = -z
+  int valid;
+  if (a_in_smem) valid = lm_factor_solve(after_linv, ld, D, B, gs, y, dinv, Linv, nullptr, radius, warp_solve, true, &ok);
+  else valid = lm_factor_solve(B.A, ld, D, B, gs, y, dinv, Linv, pan, radius, warp_solve, false, &ok);
   if (valid) {
-    for (int i = tid; i < D; i += nt) y[i] = warp_solve ? A[(size_t)D * ld + i] : gs[i];
-    __syncthreads();
-    if (warp_solve) {
-      if (tid < 32) warp_cholesky_solve(A, ld, D, y, dinv, tid, false);
-      __syncthreads();
-    } else {
-      cta_cholesky_solve(A, ld, D, y, Linv);
-    }
+    LM_STAMP(4);
     double bad = 0.0;
     for (int i = tid; i < D; i += nt) {
       double v = -y[i];
@@ -712,6 +771,7 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     if (block_max(bad, red) > 0.0) valid = 0;
   }
   __syncthreads();
+  LM_STAMP(5);
   double mcc = 0.0;
   if (valid) {
     // model_cost_change = -(g~^T s + 1/2 s^T H~ s)
@@ -741,9 +801,11 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     }
     return;
   }
+  LM_STAMP(6);
   for (int i = tid; i < D; i += nt) B.delta[i] = B.step[i] * B.scale[i];
   __syncthreads();
   plus_state(B.x, B.delta, 1.0, B.cand, L);
+  LM_STAMP(7);
   double g0p = 0.0, dmx = 0.0;
   for (int i = tid; i < D; i += nt) {
     g0p += B.b[i] * B.delta[i];
@@ -763,6 +825,7 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     s->ls_success = 1;
     s->ls_active = is_constrained;
   }
+  LM_STAMP(8);
 }
 
 // Projected Armijo line search of bounded problems (TrustRegionMinimizer::DoLineSearch).  Called by the host loop
