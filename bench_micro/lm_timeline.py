@@ -21,4 +21,5 @@ for K, nb in ((14, 2), (10, 2)):
     for n, c in zip(names[:-1], d):
         print("  %-16s %7d cycles  %5.1f%%" % (n, c, 100.0 * c / (t[8] - t[0])))
     print("  inside the look-ahead Cholesky (sums over panels): panel solve %d, next block column %d, diag block (warp 0) %d, diag || trailing incl. barrier %d" % tuple(st[9:13]))
+    print("  inside warp_diag_block (sums): load %d, eliminate %d, store %d" % tuple(st[13:16]))
     est.close()

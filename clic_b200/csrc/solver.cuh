@@ -113,48 +113,74 @@ namespace clic {
 // in shared memory when it fits, else in L2-resident global scratch; only the lower triangle is referenced.
 constexpr int kNB = 8;
 
+#ifdef CLIC_LM_TIMING  // developer build: phase time stamps of the last lm_step_kernel launch (bench_micro/lm_timeline.py)
+__device__ long long g_lm_stamps[16];
+#define LM_STAMP(i) do { if (threadIdx.x == 0) g_lm_stamps[i] = clock64(); } while (0)
+#define LM_ACC(i, t0) do { if (threadIdx.x == 0) g_lm_stamps[i] += clock64() - (t0); } while (0)
+#define LM_NOW() clock64()
+#else
+#define LM_STAMP(i) do { } while (0)
+#define LM_ACC(i, t0) do { } while (0)
+#define LM_NOW() 0
+#endif
+
 // Warp 0, lane l < nb holds row l of the kNB x kNB diagonal block in registers; columns are eliminated with warp
 // shuffles (no shared-memory round trips on the serial critical path).  Writes L back and, if Li != nullptr, the
 // inverse of the block (row-major kNB x kNB, zero padded) used by the panel and triangular solves.
 __device__ __forceinline__ void warp_diag_block(double* A, int ld, int kb, int nb, double* dinv, int* ok, int lane,
                                                 const double* dtol = nullptr) {
-  const unsigned full = 0xffffffffu;
-  double a[kNB], invs[kNB];
+  // This is the serial critical path of the whole factorization.  Measured on B200 (bench_micro/lm_timeline.py): a
+  // warp-parallel elimination (one row per lane, columns exchanged with shuffles) costs ~270 cycles per column however
+  // its dependent chain is arranged — one warp alone issues an instruction every 3-4 cycles and the ~36 double
+  // shuffles + selects per block are what it spends them on.  ONE thread holding the whole 8 x 8 block in registers
+  // needs no exchange at all: ~330 instructions per block, independent updates fill the latency of the pivot chain.
+  // Chain per column: 1/d (hardware reciprocal approximation, ~2^-20, + two Newton steps of two FMAs) -> t_i = a_ij / d
+  // -> a_ic -= t_i a_cj.  Off the chain: 1/sqrt(d) for the stored column (MUFU.RSQ64H + two Newton steps; the pivot is
+  // d * (1/sqrt(d))), and the pivot test, whose failure is only reported — the block then holds garbage and every
+  // caller stops on !*ok.  The library rsqrt() / sqrt() + division put several times more dependent instructions here.
+  long long tq0 = LM_NOW();
+  if (lane != 0) return;
+  double a[kNB][kNB];
 #pragma unroll
-  for (int c = 0; c < kNB; c++) a[c] = (lane < nb && c <= lane) ? A[(size_t)(kb + lane) * ld + kb + c] : 0.0;
-  // This is the serial critical path of the whole factorization and it runs in ONE warp, so what counts is the number
-  // of dependent instructions per column.  Branch-free on purpose: lanes above the diagonal carry values nobody reads
-  // (entries with c > lane are never shuffled from nor stored), a failed pivot is replaced by 1 and reported once.
+  for (int i = 0; i < kNB; i++)
+#pragma unroll
+    for (int c = 0; c <= i; c++)  // rows / columns past a partial block are padded with the identity
+      a[i][c] = i < nb ? A[(size_t)(kb + i) * ld + kb + c] : (c == i ? 1.0 : 0.0);
+  LM_ACC(13, tq0);
+  tq0 = LM_NOW();
   bool any_bad = false;
 #pragma unroll
   for (int j = 0; j < kNB; j++) {
-    double d = __shfl_sync(full, a[j], j);
-    const bool bad = (j < nb) && (!(d > (dtol ? dtol[kb + j] : 0.0)) || !isfinite(d));
-    any_bad |= bad;
-    d = (bad || j >= nb) ? 1.0 : d;
-    // 1/sqrt(d): the hardware approximation (MUFU.RSQ64H, ~2^-22) refined by two Newton steps to full precision;
-    // pivot = d * (1/sqrt(d)) falls out of the same multiply as the column scaling (lane j holds d in a[j]).
-    // The library rsqrt() and sqrt() + division put several times more dependent instructions here.
+    const double d = a[j][j];
+    double rd;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(d));
+    rd = fma(rd, fma(-d, rd, 1.0), rd);
+    rd = fma(rd, fma(-d, rd, 1.0), rd);
+#pragma unroll
+    for (int i = j + 1; i < kNB; i++) {
+      const double t = a[i][j] * rd;
+#pragma unroll
+      for (int c = j + 1; c <= i; c++) a[i][c] = fma(-t, a[c][j], a[i][c]);
+    }
+    any_bad |= (j < nb) && (!(d > (dtol ? dtol[kb + j] : 0.0)) || !isfinite(d));
     double inv;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
     const double hd = 0.5 * d;
-    inv = inv * (1.5 - hd * inv * inv);
-    inv = inv * (1.5 - hd * inv * inv);
-    invs[j] = inv;
-    a[j] = (lane == j ? d : a[j]) * inv;
-    const double lij = a[j];
+    inv = inv * fma(-hd, inv * inv, 1.5);
+    inv = inv * fma(-hd, inv * inv, 1.5);
+    if (j < nb) dinv[kb + j] = inv;
 #pragma unroll
-    for (int c = j + 1; c < kNB; c++) a[c] -= lij * __shfl_sync(full, lij, c);
+    for (int i = j; i < kNB; i++) a[i][j] *= inv;
   }
-  if (lane == 0) {
+  LM_ACC(14, tq0);
+  tq0 = LM_NOW();
+  if (any_bad) *ok = 0;
 #pragma unroll
-    for (int j = 0; j < kNB; j++)
-      if (j < nb) dinv[kb + j] = invs[j];
-    if (any_bad) *ok = 0;
-  }
+  for (int i = 0; i < kNB; i++)
 #pragma unroll
-  for (int c = 0; c < kNB; c++)
-    if (lane < nb && c <= lane) A[(size_t)(kb + lane) * ld + kb + c] = a[c];
+    for (int c = 0; c <= i; c++)
+      if (i < nb) A[(size_t)(kb + i) * ld + kb + c] = a[i][c];
+  LM_ACC(15, tq0);
 }
 
 // Inverse of the kNB x kNB diagonal block kb of L (row-major kNB x kNB, zero padded), by one warp.
@@ -249,16 +275,6 @@ __device__ __forceinline__ void cta_cholesky(double* A, int ld, int n, int* ok, 
   }
 }
 
-#ifdef CLIC_LM_TIMING  // developer build: phase time stamps of the last lm_step_kernel launch (bench_micro/lm_timeline.py)
-__device__ long long g_lm_stamps[16];
-#define LM_STAMP(i) do { if (threadIdx.x == 0) g_lm_stamps[i] = clock64(); } while (0)
-#define LM_ACC(i, t0) do { if (threadIdx.x == 0) g_lm_stamps[i] += clock64() - (t0); } while (0)
-#define LM_NOW() clock64()
-#else
-#define LM_STAMP(i) do { } while (0)
-#define LM_ACC(i, t0) do { } while (0)
-#define LM_NOW() 0
-#endif
 // The same factorization with one panel of look-ahead, for A in shared memory: after the panel solve the next block
 // column is updated first, then warp 0 factors the next diagonal block while the other warps update the rest of the
 // trailing matrix — the serial 8-column elimination (about half of a panel step at n ~ 100) leaves the critical path.
