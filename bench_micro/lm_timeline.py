@@ -1,5 +1,7 @@
-"""Phase timeline of the last lm_step_kernel launch of a production-size Solve(8) (developer build:
-nvcc -DCLIC_LM_TIMING into another .so, selected with CLIC_CUDA_LIB)."""
+"""Phase timeline of the last lm_step_kernel launch of a production-size Solve(8).  Needs the developer build:
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --compiler-options "-fPIC -fvisibility=hidden" \
+       -shared -DCLIC_LM_TIMING -o bench_micro/_libclic_lmtiming.so clic_b200/csrc/clic_cuda.cu
+  CLIC_CUDA_LIB=$PWD/bench_micro/_libclic_lmtiming.so python bench_micro/lm_timeline.py"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "bench_micro"))

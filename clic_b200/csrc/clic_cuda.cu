@@ -2720,6 +2720,9 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
   int rc = assoc_plan_call(m, n_corner, n_surf, P);
   if (rc) return rc;
   if (P.max_q == 0) return CLIC_OK;
+  // earlier asynchronous adders may still be running their prep kernels on the copy stream; they share the dropped-
+  // record counter with the adders below
+  if ((rc = join_adds(E))) return rc;
   char* base = (char*)m->d_scratch;
   const float* in_L[2] = {corner_xyz, surf_xyz};
   const double* in_t[2] = {corner_t, surf_t};
