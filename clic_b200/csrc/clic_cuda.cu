@@ -807,10 +807,10 @@ int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
 // Key-aligned storage for small batches.  A warp evaluates 32 consecutive factors at a time and accumulates them into
 // the 24-column block of ONE knot interval, so a 32-factor slab that straddles k intervals costs k evaluation rounds.
 // With 10^5-10^6 factors per window that never matters; at the reference's production size (a few hundred LiDAR and
-// ~100 IMU factors over ~10 intervals) nearly every slab straddles 2-4 intervals.  For a small, time-sorted batch the
+// ~100 IMU factors over ~10 intervals) nearly every slab straddles 2-4 intervals.  For a small batch the
 // host therefore starts every interval's factors on a slab boundary (padding entries are stored as dropped factors):
 // one round per slab, and the slabs of different intervals run on different warps.  Only the grouping of the sums
-// changes (H, b move by rounding, ~1e-16).  Returns an empty map when the batch is large, unsorted, or already aligned.
+// changes (H, b move by rounding, ~1e-16).  Returns an empty map when the batch is large or already aligned.
 // t_s: the caller's timestamps; shift_ns: what the factor adds before indexing ((int64) time offset for the IMU).
 constexpr int64_t kKeyAlignMax = 1 << 15;
 bool key_align_enabled() { static const bool v = getenv("CLIC_NO_KEY_ALIGN") == nullptr; return v; }
@@ -835,8 +835,9 @@ std::vector<int32_t> build_key_gather(const clic_estimator* E, const double* t_s
     }
     key[i] = k;
     if (k < 0) { n_bad++; continue; }
-    if (k < prev) return g;  // not time-sorted: leave the batch as it is (the kernels cope, with more rounds)
-    if (k != prev && (run % 32) != 0) straddle = true;
+    // an unsorted batch is bucketed by interval all the same (a stable counting sort: arrival order within an
+    // interval), which also takes it off the kernels' atomics fallback for records that revisit an interval
+    if (k != prev && ((run % 32) != 0 || k < prev)) straddle = true;
     prev = k;
     count[k]++;
     run++;

@@ -101,11 +101,14 @@ def test_single_factor_and_tiny(cuda, oracle):
     compare_eval(cuda, oracle, sw)
 
 
-def test_unsorted_input(cuda, oracle):
-    """Time-unsorted factors exercise the multi-key warp loop and the atomics overflow path."""
-    sw = S.make_window(10, n_lidar=4000, n_imu=300, line_fraction=0.3, seed=8)
+@pytest.mark.parametrize("n_lidar", [4000, 40000])
+def test_unsorted_input(cuda, oracle, n_lidar):
+    """Time-unsorted factors.  Up to 32 k records per batch the adder buckets them by knot interval (key-aligned
+    storage); above that they go to the kernels as they are and exercise the multi-key warp loop and the atomics
+    overflow path."""
+    sw = S.make_window(10, n_lidar=n_lidar, n_imu=300, line_fraction=0.3, seed=8)
     rng = np.random.default_rng(0)
-    perm = rng.permutation(4000)
+    perm = rng.permutation(n_lidar)
     for k in ("t_point", "point", "geo_type", "geo_plane", "geo_normal", "geo_point"):
         sw.lidar[k] = np.ascontiguousarray(sw.lidar[k][perm])
     perm = rng.permutation(300)
