@@ -1,8 +1,9 @@
 """One LiDAR-inertial update of the reference at its production size, through the public API
 (odometry_manager.cpp:321-339 + trajectory_manager.cpp:319-465, 555-877):
 
-  two inner iterations of  [GetLoamFeatureAssociation -> UpdateTrajectoryWithLoamFeature: prior + LiDAR + IMU + bias,
-  Solve(8)]  followed by  UpdateLIOPrior  (marginalization of the oldest knots).
+  InitTrajWithPropagation  (prior + IMU + one global-velocity factor, Solve(50)),  two inner iterations of
+  [GetLoamFeatureAssociation -> UpdateTrajectoryWithLoamFeature: prior + LiDAR + IMU + bias, Solve(8)]  and
+  UpdateLIOPrior  (marginalization of the oldest knots).
 
 Sizes (SURVEY.md §6 "typical real problem size"): 1500 corner + 1500 surface scan features, correspondence
 down-sampling 2, a 58 k-point feature map, 125 IMU samples, 14 knots of which 4 are marginalised.  The reference's own
@@ -46,11 +47,27 @@ def previous_prior(lib, sw, knots, rng):
     return E.Prior.create(lib, J0, r0, kinds, ids, np.array(x0)), kinds, ids
 
 
-def update(lib, sw, fm, scan, state, prior_spec):
+def update(lib, sw, fm, scan, state, prior_spec, vel):
     """Returns (timings dict in ms, final state, new prior dims)."""
     M, Lx = sw.imu, sw.lidar
-    t = {"associate_add": 0.0, "other_adds": 0.0, "solve": 0.0, "marginalize": 0.0}
+    t = {"init_solve50": 0.0, "associate_add": 0.0, "other_adds": 0.0, "solve": 0.0, "marginalize": 0.0}
     win = sw.window
+    # InitTrajWithPropagation (trajectory_manager.cpp:233-300): biases locked, prior + IMU + global velocity, Solve(50)
+    opt = E.default_options(lib)
+    w = E.Window(win.t0_ns, win.dt_ns, state["knot_q"], state["knot_p"], bias=state["bias"],
+                 S_LtoI=win.S_LtoI, p_LinI=win.p_LinI, gravity=win.gravity)
+    t0 = time.perf_counter()
+    est = E.TrajectoryEstimator(w, opt, lib)
+    est.SetFixedIndex(-1)
+    prior, kinds, ids = prior_spec
+    est.AddMarginalizationFactor(prior, [])
+    est.AddIMUMeasurementAnalytic(M["timestamp"], M["gyro"], M["accel"], 1, M["info_vec"], count_dropped=False)
+    est.AddGlobalVelocityMeasurement(vel[0], vel[1], 25.0)
+    init_summ = est.Solve(50)
+    st_i = est.read_state()
+    state = dict(knot_q=st_i["knot_q"], knot_p=st_i["knot_p"], bias=state["bias"])
+    est.close()
+    t["init_solve50"] = (time.perf_counter() - t0) * 1e3
     for it in range(2):
         opt = E.default_options(lib)
         opt.lock_ab = opt.lock_wb = 0
@@ -101,7 +118,7 @@ def update(lib, sw, fm, scan, state, prior_spec):
     t["marginalize"] = (time.perf_counter() - t0 - (t2 - t1)) * 1e3
     est.close()
     t["total"] = sum(t.values())
-    return t, state, dims, summ
+    return t, state, dims, summ, init_summ
 
 
 def main():
@@ -126,6 +143,10 @@ def main():
         q = S.qmul(R, np.broadcast_to(Lx["S_LtoI"], R.shape))
         p = S.qrot(R, np.broadcast_to(Lx["p_LinI"], pos.shape)) + pos
         scan[kind] = (S.qrot(S.qconj(q), pts_M.astype(np.float64) - SHIFT - p).astype(np.float32), tq)
+    # the propagated IMU state's velocity at the end of the window (ground truth here)
+    v_t = hi - 0.013
+    tv = np.array([int(v_t * 1e9)], dtype=np.int64)
+    vel = (v_t, ((gt.position(tv + 1_000_000) - gt.position(tv - 1_000_000)) / 2e-3)[0])
     out = {}
     for name, lib, reps in (("gpu", cuda, 6), ("cpu_1thread", oracle, 3)):
         fm = A.FeatureMap(map_s, map_c, lib)
@@ -133,11 +154,12 @@ def main():
         state0 = {"knot_q": sw.window.knot_q.copy(), "knot_p": sw.window.knot_p.copy(), "bias": sw.window.bias.copy()}
         runs = []
         for r in range(reps):
-            tt, state, dims, summ = update(lib, sw, fm, scan, dict(state0), spec)
+            tt, state, dims, summ, init_summ = update(lib, sw, fm, scan, dict(state0), spec, vel)
             runs.append(tt)
         fm.close()
         best = min(runs[1:] if len(runs) > 1 else runs, key=lambda x: x["total"])
         out[name] = {"ms": {k: round(v, 3) for k, v in best.items()}, "new_prior_dims": dims,
+                     "init_solve": {"iterations": init_summ["iterations"]},
                      "last_solve": {"iterations": summ["iterations"], "final_cost": summ["final_cost"]},
                      "final_pos": state["knot_p"][-1].tolist()}
     dp = np.abs(np.array(out["gpu"]["final_pos"]) - np.array(out["cpu_1thread"]["final_pos"])).max()

@@ -123,6 +123,7 @@ PROTOTYPES = {
     "clic_add_imu": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                c_int64_p]),
     "clic_add_bias": (C.c_int, [H, C.c_int32, C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int32]),
+    "clic_add_global_velocity": (C.c_int, [H, C.c_double, c_double_p, C.c_double, c_int32_p]),
     "clic_add_image": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.c_int32,
                                  C.c_int32, c_int64_p]),
     "clic_add_prior": (C.c_int, [H, H, C.c_int32, c_int32_p]),

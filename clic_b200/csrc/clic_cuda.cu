@@ -262,6 +262,7 @@ struct clic_estimator {
   DevBuf d_lm;  // LM workspace (solver.cuh)
   std::vector<std::unique_ptr<LoamBatch>> loam;
   std::vector<std::unique_ptr<ImuBatch>> imu;
+  std::vector<VelFactorDesc> vel_factors;  // AddGlobalVelocityMeasurement (one per init solve in the reference)
   std::vector<std::unique_ptr<ImageBatch>> image;
   std::vector<BiasFac> bias_f;
   struct PriorRef {
@@ -767,6 +768,12 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   for (auto& pr : E->priors) {
     if (E->opt.is_marg_state) continue;
     if ((rc = launch_prior(E, pr.get(), state, cost2, jac, ctl, Hp, bp))) return rc;
+  }
+  for (auto& vf : E->vel_factors) {
+    CU(launch_pdl(velocity_factor_kernel, 1, 64, 0, E->stream, vf, state, E->sl, (long long)E->t0_ns, (long long)E->dt_ns,
+                  E->K, (const int*)E->d_knot_col.as<int>(), E->L.col_t_offset[CLIC_SENSOR_IMU], Hp, bp, std::max(1, D),
+                  cost2, jac ? 1 : 0, ctl));
+    E->launches++;
   }
   CU(cudaGetLastError());
   if (E->use_comm) {
@@ -1737,6 +1744,33 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   if ((rc = mark_ready(E, B->ex))) return rc;
   E->imu.push_back(std::move(B));
   E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_global_velocity(clic_estimator* E, double timestamp, const double global_v[3], double vel_weight,
+                                      int32_t* added) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!global_v) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  if (added) *added = 0;
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "global velocity factor in a marginalization estimator");
+  // MeasuredTimeToNs(IMUSensor), trajectory_estimator.cpp:272-292: same host arithmetic as the IMU adder's bounds
+  const int S = CLIC_SENSOR_IMU;
+  const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
+  const int64_t t = (int64_t)(timestamp * 1e9);
+  if (t - pad < t_min || t + pad >= t_max) return CLIC_OK;  // the reference returns false
+  VelFactorDesc vf;
+  vf.time_ns = t;
+  for (int k = 0; k < 3; k++) vf.v[k] = global_v[k];
+  vf.w = vel_weight;
+  E->vel_factors.push_back(vf);
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // trajectory_estimator.cpp:653-656
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
+    E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
+  }
+  E->layout_dirty = true;
+  if (added) *added = 1;
   return CLIC_OK;
 }
 

@@ -1205,6 +1205,76 @@ __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, State
   }
 }
 
+// auto_diff::IMUGlobalVelocityFactor (factor/auto_diff/trajectory_value_factor.h:436-487) with CauchyLoss(60)
+// (trajectory_estimator.cpp:642): r = w (p'(t) - v), t = double(time_ns) + t_offset_IMU (not truncated: a Jet in the
+// reference), indexed by the templated SplineSegmentMeta::computeTIndexNs (spline_segment.h:108-118: floor of a double
+// quotient).  One factor per solve (InitTrajWithPropagation): a single small CTA adds it to H, b, cost after the
+// assembly, every thread owning distinct entries.
+struct VelFactorDesc {
+  long long time_ns;
+  double v[3];
+  double w;
+};
+__global__ void velocity_factor_kernel(VelFactorDesc vf, const double* state, StateLayout sl, long long t0_ns,
+                                       long long dt_ns, int K, const int* knot_col, int col_toff, double* H, double* b,
+                                       int D, double* cost2, int jac, const int* ctl) {
+  pdl_wait();
+  pdl_trigger();
+  if (ctl && ctl[0]) return;
+  const double t_corr = (double)vf.time_ns + state[sl.off_toff() + 0];  // IMUSensor = 0
+  const double t_lo = (double)t0_ns, t_hi = (double)(t0_ns + (long long)(K - 3) * dt_ns);
+  if (t_corr < t_lo || t_corr >= t_hi) return;
+  const double st = (t_corr - (double)t0_ns) / (double)dt_ns;
+  const int s = (int)floor(st);
+  const double u = st - (double)s;
+  const double inv_dt = 1e9 * 1.0 / (double)dt_ns;
+  double c[4], ca[4];
+  blend_plain_d1(u, inv_dt, c);       // inv_dt * M p'(u)
+  blend_plain_d2(u, inv_dt, ca);      // d/du of the above
+  const double* kp = state + sl.off_p();
+  double v[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+  for (int k = 0; k < 4; k++)
+    for (int r = 0; r < 3; r++) {
+      v[r] += c[k] * kp[3 * (s + k) + r];
+      dv[r] += ca[k] * kp[3 * (s + k) + r];
+    }
+  double res[3], jt[3], sq = 0.0;
+  for (int r = 0; r < 3; r++) {
+    res[r] = vf.w * (v[r] - vf.v[r]);
+    jt[r] = vf.w * dv[r] * (1.0 / (double)dt_ns);  // d r / d t_offset: du / dt_offset = 1 / dt_ns
+    sq += res[r] * res[r];
+  }
+  double rho;
+  const double sc = cauchy_scale(sq, 60.0, &rho);
+  const double rp = sc * sc;  // rho'
+  int col[4];
+  bool any_free = col_toff >= 0;
+  for (int k = 0; k < 4; k++) {
+    col[k] = knot_col[s + k] >= 0 ? knot_col[s + k] + 3 : -1;
+    any_free |= col[k] >= 0;
+  }
+  const int t = threadIdx.x;
+  if (t == 63) cost2[any_free ? 0 : 1] += 0.5 * rho;
+  if (!jac) return;
+  if (t < 48) {  // H[p_k + r][p_l + r] += rho' w^2 c_k c_l
+    const int k = t / 12, l = (t / 3) % 4, r = t % 3;
+    if (col[k] >= 0 && col[l] >= 0) H[(size_t)(col[k] + r) * D + col[l] + r] += rp * (vf.w * c[k]) * (vf.w * c[l]);
+  } else if (t < 60) {  // cross terms with the time offset, and b on the position knots
+    const int k = (t - 48) / 3, r = (t - 48) % 3;
+    if (col[k] >= 0) {
+      b[col[k] + r] += rp * (vf.w * c[k]) * res[r];
+      if (col_toff >= 0) {
+        const double h = rp * (vf.w * c[k]) * jt[r];
+        H[(size_t)(col[k] + r) * D + col_toff] += h;
+        H[(size_t)col_toff * D + col[k] + r] += h;
+      }
+    }
+  } else if (t == 60 && col_toff >= 0) {
+    H[(size_t)col_toff * D + col_toff] += rp * (jt[0] * jt[0] + jt[1] * jt[1] + jt[2] * jt[2]);
+    b[col_toff] += rp * (jt[0] * res[0] + jt[1] * res[1] + jt[2] * res[2]);
+  }
+}
+
 // K0 at add time: double seconds -> int64 ns with the reference's truncation and window test
 // (trajectory_estimator.cpp:272-292); AoS(3n) -> planar.
 __global__ void prep_loam_kernel(int64_t n, const double* t_s, const double* point, const int32_t* geo_type,

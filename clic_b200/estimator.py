@@ -213,6 +213,15 @@ class TrajectoryEstimator:
         _check(self.lib, self.lib.clic_add_bias(self.h, int(slot_i), int(slot_j), float(dt), dptr(info_vec),
                                                 int(bool(marg_this_factor)), int(bool(marg_all_bias))))
 
+    # ---- trajectory_estimator.cpp:609-664 ----
+    def AddGlobalVelocityMeasurement(self, timestamp, global_v, vel_weight):
+        """IMUGlobalVelocityFactor at one timestamp; returns False when it falls outside the window."""
+        v = f64(global_v)
+        added = C.c_int32(0)
+        _check(self.lib, self.lib.clic_add_global_velocity(self.h, float(timestamp), dptr(v), float(vel_weight),
+                                                           C.byref(added)))
+        return bool(added.value)
+
     # ---- trajectory_estimator.h:196-199 (batched) ----
     def AddImageFeatureAnalytic(self, ti, pi, tj, pj, landmark, fixed_depth=True, marg_this_feature=False,
                                 count_dropped=True):

@@ -189,6 +189,25 @@ class TrajectoryEstimator {
     bias_f_.push_back(f);
   }
 
+  // trajectory_estimator.cpp:609-664 (IMUGlobalVelocityFactor, CauchyLoss(60)); false when the timestamp is outside
+  // the window (MeasuredTimeToNs(IMUSensor), ":272-292" — repeated by the library when the problem is built)
+  bool AddGlobalVelocityMeasurement(const double timestamp, const Vec3d& global_v, double vel_weight) {
+    const double toff_s = 1e-9 * trajectory_->EP_StoI[IMUSensor].t_offset_ns;
+    const int64_t K = (int64_t)trajectory_->numKnots();
+    const int64_t t_min = (int64_t)((1e-9 * (double)trajectory_->t0_ns - toff_s) * 1e9);
+    const int64_t t_max =  // Se3Spline::maxTimeNs = t0 + (n - N + 1) dt - 1 (rd_spline.h:142-144)
+        (int64_t)((1e-9 * (double)(trajectory_->t0_ns + (K - 3) * trajectory_->dt_ns - 1) - toff_s) * 1e9);
+    const int64_t pad = options.lock_EPs.at(IMUSensor).lock_t_offset ? 0 : options.t_offset_padding_ns;
+    const int64_t t = (int64_t)(timestamp * 1e9);
+    if (t - pad < t_min || t + pad >= t_max) return false;
+    VelFac f;
+    f.t = timestamp;
+    f.v = global_v;
+    f.w = vel_weight;
+    vel_f_.push_back(f);
+    return true;
+  }
+
   // trajectory_estimator.h:188-193
   void AddLoamMeasurementAnalytic(const PointCorrespondence& pc, const SO3d& S_GtoM, const Vec3d& p_GinM,
                                   const SO3d& S_LtoI, const Vec3d& p_LinI, double weight,
@@ -362,6 +381,10 @@ class TrajectoryEstimator {
     std::vector<int32_t> lm;
     bool fixed = true, marg = false;
   };
+  struct VelFac {
+    double t, w;
+    Vec3d v{};
+  };
   struct BiasFac {
     int i, j;
     double dt;
@@ -467,6 +490,7 @@ class TrajectoryEstimator {
                                   b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
                                   nullptr));
     for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
+    for (auto& f : vel_f_) check(clic_add_global_velocity(h_, f.t, f.v.data(), f.w, nullptr));
     for (auto& b : scans_) {
       int64_t nl = 0, np = 0;
       check(clic_add_loam_from_scan(h_, b.map->handle(), (int64_t)b.corner_t.size(), b.corner_xyz.data(),
@@ -507,6 +531,7 @@ class TrajectoryEstimator {
   std::vector<ImuBatch> imu_;
   std::vector<ImageBatch> image_;
   std::vector<BiasFac> bias_f_;
+  std::vector<VelFac> vel_f_;
   std::vector<PriorRef> priors_;
   std::vector<std::pair<double*, double*>> bias_ptr_;
   std::map<double*, int> landmark_;

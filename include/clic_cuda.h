@@ -209,6 +209,15 @@ CLIC_API int clic_add_imu(clic_estimator* h, int64_t n, const double* timestamp,
 CLIC_API int clic_add_bias(clic_estimator* h, int32_t slot_i, int32_t slot_j, double dt,
                            const double info_vec[6], int32_t marg_this_factor, int32_t marg_all_bias);
 
+/* AddGlobalVelocityMeasurement (trajectory_estimator.cpp:609-664) with auto_diff::IMUGlobalVelocityFactor
+ * (factor/auto_diff/trajectory_value_factor.h:436-487): r = vel_weight * (p'(t + t_offset_IMU) - global_v) on the
+ * position knots (+ the IMU time offset when it is free), CauchyLoss(60) (":642").  It is the one factor besides the
+ * prior and the IMU factors that TrajectoryManager::InitTrajWithPropagation adds (trajectory_manager.cpp:233-300),
+ * so with it the third solve of every update runs here too.  *added = 0 when the timestamp falls outside the window
+ * (the reference returns false).  Not supported in a marginalization estimator (the reference never adds it there). */
+CLIC_API int clic_add_global_velocity(clic_estimator* h, double timestamp, const double global_v[3], double vel_weight,
+                                      int32_t* added);
+
 /* AddImageFeatureAnalytic (trajectory_estimator.cpp:752-829), batched; landmark[i] indexes
  * clic_window_desc::inv_depth.  Loss CauchyLoss(marg ? 1 : 2) (":806-810"). */
 CLIC_API int clic_add_image(clic_estimator* h, int64_t n, const double* t_i, const double* p_i /*3n*/,

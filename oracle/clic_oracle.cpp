@@ -1211,6 +1211,41 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   return CLIC_OK;
 }
 
+// AddGlobalVelocityMeasurement — trajectory_estimator.cpp:609-664
+CLIC_API int clic_add_global_velocity(clic_estimator* E, double timestamp, const double global_v[3], double vel_weight,
+                                      int32_t* added) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!global_v) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  if (added) *added = 0;
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "global velocity factor in a marginalization estimator");
+  const int S = CLIC_SENSOR_IMU;
+  int64_t time_ns;
+  if (!E->MeasuredTimeToNs(S, timestamp, time_ns)) return CLIC_OK;  // "return false"
+  const int64_t t_corrected_ns = (int64_t)(time_ns + E->x.t_offset_ns[S]);  // ":615"
+  SplineMeta meta;
+  if (E->opt.lock_t_offset[S])
+    E->CaculateSplineMeta({{t_corrected_ns, t_corrected_ns}}, meta);
+  else
+    E->CaculateSplineMeta(
+        {{t_corrected_ns - E->opt.t_offset_padding_ns, t_corrected_ns + E->opt.t_offset_padding_ns}}, meta);
+  ResidualBlock rb;
+  rb.cost.reset(new GlobalVelocityFactor(time_ns, load_v(global_v), meta, vel_weight));
+  E->AddControlPoints(meta, rb.refs, true);  // position knots only (":645")
+  rb.refs.push_back({CLIC_BLOCK_T_OFFSET, S});
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {  // ":653-656"
+    const double t_ns = (double)E->opt.t_offset_padding_ns;
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->x.t_offset_ns[S] - t_ns;
+    E->toff_hi[S] = E->x.t_offset_ns[S] + t_ns;
+  }
+  rb.has_loss = true;
+  rb.loss_a = 60;  // CauchyLoss(60), ":642"
+  rb.rtype = 3;
+  E->blocks.push_back(std::move(rb));
+  if (added) *added = 1;
+  return CLIC_OK;
+}
+
 CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, double dt, const double info_vec[6],
                            int32_t marg_this_factor, int32_t marg_all_bias) {
   if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");

@@ -246,6 +246,77 @@ struct BiasFactor : CostFunction {
   }
 };
 
+// IMUGlobalVelocityFactor — src/estimator/factor/auto_diff/trajectory_value_factor.h:436-487 (an auto-diff functor in
+// the reference; the Jacobians here are its derivatives written out).  Parameters: the position knots of the spline
+// meta, then the IMU time offset (1).  t_corrected = double(time_ns) + time_offset (NOT truncated: the offset is a Jet
+// there), indexed through the templated SplineSegmentMeta::computeTIndexNs (spline_segment.h:108-118: floor of a double
+// quotient, u = st - floor(st)); velocity = inv_dt * sum_i (M p'(u))_i p_i (ceres_spline_helper_jet.h:201-221).
+struct GlobalVelocityFactor : CostFunction {
+  int64_t time_ns_;
+  Vec3 velocity_;
+  SplineMeta spline_meta_;
+  double vel_weight_, inv_dt_;
+  GlobalVelocityFactor(int64_t time_ns, const Vec3& v, const SplineMeta& meta, double w)
+      : time_ns_(time_ns), velocity_(v), spline_meta_(meta), vel_weight_(w) {
+    inv_dt_ = 1e9 * 1.0 / (double)spline_meta_.segments.begin()->dt_ns;
+    num_residuals = 3;
+    block_sizes.assign(spline_meta_.NumParameters(), 3);
+    block_sizes.push_back(1);
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    const size_t Knot_offset = spline_meta_.NumParameters();
+    const double t_corrected = (double)time_ns_ + parameters[Knot_offset][0];
+    // SplineMeta::ComputeSplineIndex<T> over the segments
+    size_t P_offset = 0;
+    double u = 0;
+    bool found = false;
+    for (auto const& seg : spline_meta_.segments) {
+      if (!(t_corrected < (double)seg.MinTimeNs() || t_corrected >= (double)seg.MaxTimeNs())) {
+        const double st = (t_corrected - (double)seg.t0_ns) / (double)seg.dt_ns;
+        const size_t s = (size_t)std::floor(st);
+        u = st - (double)s;
+        P_offset += s;
+        found = true;
+        break;
+      }
+      P_offset += seg.NumParameters();
+    }
+    if (!found) return false;
+    // baseCoeffsWithTime<1>: p' = [0, 1, 2u, 3u^2]; coeff = inv_dt * M p'   (plain blending matrix M)
+    const double u2 = u * u;
+    double c[4], ca[4];
+    c[0] = inv_dt_ * ((-3.0 + 6.0 * u - 3.0 * u2) / 6.0);
+    c[1] = inv_dt_ * ((-12.0 * u + 9.0 * u2) / 6.0);
+    c[2] = inv_dt_ * ((3.0 + 6.0 * u - 9.0 * u2) / 6.0);
+    c[3] = inv_dt_ * ((3.0 * u2) / 6.0);
+    // d coeff / du = inv_dt * M p'' with p'' = [0, 0, 2, 6u]
+    ca[0] = inv_dt_ * ((6.0 - 6.0 * u) / 6.0);
+    ca[1] = inv_dt_ * ((-12.0 + 18.0 * u) / 6.0);
+    ca[2] = inv_dt_ * ((6.0 - 18.0 * u) / 6.0);
+    ca[3] = inv_dt_ * ((6.0 * u) / 6.0);
+    Vec3 v = v3(0, 0, 0), dv_du = v3(0, 0, 0);
+    for (int i = 0; i < 4; i++) {
+      const Vec3 p = load_v(parameters[P_offset + i]);
+      v = v + c[i] * p;
+      dv_du = dv_du + ca[i] * p;
+    }
+    for (int r = 0; r < 3; r++) residuals[r] = vel_weight_ * (v[r] - velocity_[r]);
+    if (jacobians) {
+      for (size_t k = 0; k < Knot_offset; k++) {
+        if (!jacobians[k]) continue;
+        for (int e = 0; e < 9; e++) jacobians[k][e] = 0;
+        if (k >= P_offset && k < P_offset + 4)
+          for (int r = 0; r < 3; r++) jacobians[k][r * 3 + r] = vel_weight_ * c[k - P_offset];
+      }
+      if (jacobians[Knot_offset]) {  // du / d t_offset = 1 / dt_ns
+        const double du = 1.0 / (double)spline_meta_.segments.begin()->dt_ns;
+        for (int r = 0; r < 3; r++) jacobians[Knot_offset][r] = vel_weight_ * dv_du[r] * du;
+      }
+    }
+    return true;
+  }
+};
+
 // ImageFeatureFactor — src/estimator/factor/analytic_diff/image_feature_factor.h:31-292
 struct ImageFeatureFactor : CostFunction {
   int64_t t_i_ns_, t_j_ns_;

@@ -98,6 +98,9 @@ int main() {
     d.accel = {0.1, 0.2, 9.8};
     estimator->AddIMUMeasurementAnalytic(d, bg1, ba1, g, info);
   }
+  // InitTrajWithPropagation's extra factor (trajectory_manager.cpp:279-288)
+  bool vel_in = estimator->AddGlobalVelocityMeasurement(0.3, {1.2, 0.4, 0.1}, 10.0);
+  bool vel_out = estimator->AddGlobalVelocityMeasurement(7.0, {1.2, 0.4, 0.1}, 10.0);
   Vec6d binfo = {1e4, 1e4, 1e4, 1e3, 1e3, 1e3};
   estimator->AddBiasFactor(bg0, bg1, ba0, ba1, 1, binfo);
   Summary summary = estimator->Solve(8, false);
@@ -105,7 +108,7 @@ int main() {
   const auto& sc = estimator->ScanCorrespondenceCounts();
   std::printf("scan correspondences: %lld lines, %lld planes\n", (long long)sc.at(0).first, (long long)sc.at(0).second);
   bool ok = summary.final_cost < summary.initial_cost && std::isfinite(summary.final_cost) && sc.at(0).first > 10 &&
-            sc.at(0).second > 60;
+            sc.at(0).second > 60 && vel_in && !vel_out;
   std::printf("%s %.6e %.6e %d\n", ok ? "SHIM_OK" : "SHIM_FAIL", summary.initial_cost, summary.final_cost,
               summary.num_successful_steps);
   return ok ? 0 : 1;
