@@ -97,10 +97,18 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   cudaStream_t st = nullptr;
-  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  bool owned = true;  // false: a view into another DevBuf (carve), never freed here
+  ~DevBuf() { if (p && owned) cudaFreeAsync(p, st); }
+  void view(void* ptr, size_t n) {
+    if (p && owned) cudaFreeAsync(p, st);
+    p = ptr;
+    bytes = n;
+    owned = false;
+  }
   cudaError_t ensure(size_t n) {
     if (n <= bytes) return cudaSuccess;
-    if (p) cudaFreeAsync(p, st);
+    if (p && owned) cudaFreeAsync(p, st);
+    owned = true;
     p = nullptr;
     bytes = 0;
     st = g_alloc_stream;
@@ -110,6 +118,24 @@ struct DevBuf {
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+// One stream-ordered allocation for a group of buffers (a factor batch has ~10 arrays, its execution plan 5 more: at a
+// few microseconds per cudaMallocAsync the allocations dominated the host time of adding a production-size batch).
+struct CarveItem {
+  DevBuf* buf;
+  size_t bytes;
+};
+cudaError_t carve(DevBuf& arena, std::initializer_list<CarveItem> items) {
+  size_t total = 0;
+  for (const auto& it : items) total += (std::max<size_t>(it.bytes, 1) + 255) & ~(size_t)255;
+  cudaError_t e = arena.ensure(total);
+  if (e != cudaSuccess) return e;
+  size_t off = 0;
+  for (const auto& it : items) {
+    it.buf->view(static_cast<char*>(arena.p) + off, it.bytes);
+    off += (std::max<size_t>(it.bytes, 1) + 255) & ~(size_t)255;
+  }
+  return cudaSuccess;
+}
 struct AllocScope {  // every ABI entry point that may allocate names the estimator's stream
   cudaStream_t prev;
   explicit AllocScope(cudaStream_t s) : prev(g_alloc_stream) { g_alloc_stream = s; }
@@ -156,6 +182,7 @@ struct StreamExec {
   int NT = 4, rd = 640, n_keys = 0;
   DevBuf payload, key, cost, overflow;
   DevBuf fin;  // solve path: per-key final blocks of reduce_all_kernel
+  DevBuf arena;  // one allocation behind the five buffers above (plan_stream)
   // The adders upload on the estimator's copy stream; `ready` marks the batch complete there and the compute stream
   // waits for it once, right before the first kernel that reads the batch (H2D of later batches overlaps compute).
   cudaEvent_t ready = nullptr;
@@ -181,6 +208,7 @@ struct LoamBatch {
   LoamStream st;
   DevBuf t_ns, p[3], g[6], type;
   DevBuf raw[6];  // the arrays as uploaded (kept until destroy, see the adders)
+  DevBuf arena;   // one allocation behind t_ns / p / g / type
   DevBuf d_gather;
   std::vector<int32_t> gather;  // key-aligned storage (build_key_gather): stored position -> input record, -1 = padding
   int64_t n_input = 0;          // records the caller added (st.n counts the padding too)
@@ -191,6 +219,7 @@ struct ImuBatch {
   ImuStream st;
   DevBuf t_ns, gy[3], ac[3];
   DevBuf raw[3];
+  DevBuf arena;
   DevBuf d_gather;
   std::vector<int32_t> gather;
   int64_t n_input = 0;
@@ -360,11 +389,11 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   ex.slabs_per_warp = (int)slabs;  // = total slabs (kernel argument)
   ex.n_warps = ex.grid * kWarpsPerCta;
   const size_t slots = (size_t)ex.n_warps * kSlotsPerWarp;
-  CU(ex.payload.ensure(slots * ex.rd * sizeof(double)));
-  CU(ex.key.ensure(slots * sizeof(int)));
-  CU(ex.cost.ensure((size_t)ex.n_warps * 2 * sizeof(double)));
-  CU(ex.overflow.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
-  CU(ex.fin.ensure((size_t)ex.n_keys * ex.rd * sizeof(double)));
+  CU(carve(ex.arena, {{&ex.payload, slots * ex.rd * sizeof(double)},
+                      {&ex.key, slots * sizeof(int)},
+                      {&ex.cost, (size_t)ex.n_warps * 2 * sizeof(double)},
+                      {&ex.overflow, (size_t)ex.n_keys * ex.rd * sizeof(double)},
+                      {&ex.fin, (size_t)ex.n_keys * ex.rd * sizeof(double)}}));
   // reduce_all_kernel folds the atomics-fallback block into fin and re-zeroes it
   CU(cudaMemsetAsync(ex.overflow.p, 0, (size_t)ex.n_keys * ex.rd * sizeof(double), g_alloc_stream));
   ex.overflow_flag = E->d_flags.as<int>();
@@ -1526,10 +1555,12 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
     d_gather = B->d_gather.as<int32_t>();
     n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
   }
-  CU(B->t_ns.ensure(n * sizeof(int64_t)));
-  for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
-  for (int k = 0; k < 6; k++) CU(B->g[k].ensure(n * sizeof(double)));
-  CU(B->type.ensure(n));
+  {
+    const size_t nd = (size_t)n * sizeof(double);
+    CU(carve(B->arena, {{&B->t_ns, (size_t)n * sizeof(int64_t)}, {&B->p[0], nd}, {&B->p[1], nd}, {&B->p[2], nd},
+                        {&B->g[0], nd}, {&B->g[1], nd}, {&B->g[2], nd}, {&B->g[3], nd}, {&B->g[4], nd}, {&B->g[5], nd},
+                        {&B->type, (size_t)n}}));
+  }
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, r_t.as<double>(), r_pt.as<double>(), r_type.as<int32_t>(), r_plane.as<double>(), r_normal.as<double>(),
@@ -1615,10 +1646,14 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
       n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
     }
   }
-  CU(B->t_ns.ensure(n * sizeof(int64_t)));
-  for (int k = 0; k < 3; k++) CU(B->p[k].ensure(n * sizeof(double)));
-  for (int k = 0; k < gstride; k++) CU(B->g[k].ensure(n * sizeof(double)));
-  if (geo_kind == 0) CU(B->type.ensure(n));
+  {
+    const size_t nd = (size_t)n * sizeof(double), g45 = gstride > 4 ? nd : 0;
+    CU(carve(B->arena, {{&B->t_ns, (size_t)n * sizeof(int64_t)}, {&B->p[0], nd}, {&B->p[1], nd}, {&B->p[2], nd},
+                        {&B->g[0], nd}, {&B->g[1], nd}, {&B->g[2], nd}, {&B->g[3], nd}, {&B->g[4], g45}, {&B->g[5], g45},
+                        {&B->type, geo_kind == 0 ? (size_t)n : 0}}));
+    if (gstride <= 4) { B->g[4].view(nullptr, 0); B->g[5].view(nullptr, 0); }
+    if (geo_kind != 0) B->type.view(nullptr, 0);
+  }
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_loam_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
       n, in_t, in_pt, geo_kind == 0 ? in_type : nullptr, in_geo, gstride,
@@ -1706,10 +1741,10 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
     d_gather = B->d_gather.as<int32_t>();
     n = (int64_t)B->gather.size();  // stored length: every interval's factors start on a slab boundary
   }
-  CU(B->t_ns.ensure(n * sizeof(int64_t)));
-  for (int k = 0; k < 3; k++) {
-    CU(B->gy[k].ensure(n * sizeof(double)));
-    CU(B->ac[k].ensure(n * sizeof(double)));
+  {
+    const size_t nd = (size_t)n * sizeof(double);
+    CU(carve(B->arena, {{&B->t_ns, (size_t)n * sizeof(int64_t)}, {&B->gy[0], nd}, {&B->gy[1], nd}, {&B->gy[2], nd},
+                        {&B->ac[0], nd}, {&B->ac[1], nd}, {&B->ac[2], nd}}));
   }
   CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), cs));
   prep_imu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
