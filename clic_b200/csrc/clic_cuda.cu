@@ -997,6 +997,15 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     CU(launch_pdl(lm_post_kernel, 1, 256, sm_small, E->stream, B, L));
     E->prof_end();
     E->launches++;
+    // Long solves (Solve(50) of InitTrajWithPropagation) usually converge within a handful of iterations; every
+    // iteration enqueued after that is ~9 launches that exit at once.  One 4-byte poll every 8 iterations stops the
+    // enqueueing instead (Solve(8), the inner-iteration solve, never polls).
+    if (max_iterations > 12 && (it % 8) == 7 && it + 1 < max_iterations) {
+      int done = 0;
+      CU(cudaMemcpyAsync(&done, &B.st->done, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+      CU(cudaStreamSynchronize(E->stream));
+      if (done) break;
+    }
   }
   LmState st;
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, E->stream));
