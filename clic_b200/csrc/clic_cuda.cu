@@ -17,6 +17,7 @@
 
 #include "../../include/clic_cuda.h"
 #include "kernels.cuh"
+#include "pass_fused.cuh"
 #include "solver.cuh"
 #include "assoc.cuh"
 
@@ -175,6 +176,48 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
+// Cooperative launch (every CTA resident: pass_kernel synchronises the grid) with the PDL attribute on top when the
+// driver accepts the pair; probed on the first launch.  CLIC_FUSED_COOP=0 drops the cooperative attribute (experiments
+// only: residency is then merely likely), CLIC_FUSED_NO_PDL=1 the other one.
+template <class... KArgs, class... Args>
+cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static int pdl_ok = -1;
+  static const bool coop = !(getenv("CLIC_FUSED_COOP") && getenv("CLIC_FUSED_COOP")[0] == '0');
+  static const bool no_pdl = getenv("CLIC_FUSED_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (coop) {
+    at[n].id = cudaLaunchAttributeCooperative;
+    at[n].val.cooperative = 1;
+    n++;
+  }
+  const bool try_pdl = pdl_enabled() && !no_pdl && pdl_ok != 0;
+  if (try_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  if (try_pdl && pdl_ok < 0) {
+    if (e == cudaSuccess) {
+      pdl_ok = 1;
+    } else {  // the pair is not accepted: cooperative only from now on
+      cudaGetLastError();
+      pdl_ok = 0;
+      cfg.numAttrs = n - 1;
+      e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+    }
+  }
+  return e;
+}
+
 // Launch geometry + record buffers of one factor stream.
 struct StreamExec {
   int64_t n = 0;
@@ -231,7 +274,8 @@ struct ImageBatch {
   DevBuf ti, tj, pi[3], pj[2], lm;
   DevBuf raw[4];
   DevBuf id_i, id_j, pack_t;  // pose packs (st.n_packs > 0)
-  std::vector<int64_t> perm;  // sorted position -> add order
+  std::vector<int32_t> gather;  // stored position -> add order, -1 = padding (buckets start on slab boundaries)
+  int64_t n_input = 0;          // factors the caller added (st.n counts the padding too)
   std::vector<char> lm_used;  // landmarks referenced by a kept factor (marg batches: their inverse depths are dropped blocks)
   int marg = 0;
   StreamExec ex;
@@ -313,6 +357,19 @@ struct clic_estimator {
   DevBuf d_lm_col, d_rho_side;  // free inverse depths: landmark -> column, per-landmark side rows of H | b
   bool bias_desc_dirty = true;
   int64_t launches = 0;
+  // fused pass (pass_fused.cuh): one persistent launch per pass; built by ensure_layout when the problem qualifies
+  struct Fused {
+    bool ok = false;
+    FusedArgs fa{};
+    int grid = 0;
+    size_t smem = 0;
+    int part_ctas[kFusedKinds] = {0, 0, 0, 0, 0, 0};
+    LoamBatch* lb[3] = {nullptr, nullptr, nullptr};
+    ImuBatch* ib = nullptr;
+    ImageBatch* gb = nullptr;
+    DevBuf d_bar, d_stamps, d_addend, d_hloc, d_descs_ovf;
+    bool stamps_on = false;
+  } fused;
   bool bounds_toff[3] = {false, false, false};
   double toff_lo[3], toff_hi[3];
   // profiling (clic_profile_*)
@@ -444,7 +501,224 @@ int check_p2p(clic_estimator* E) {
   if (!E->use_comm || !g_p2p.ready) return CLIC_OK;
   int err = 0;
   CU(cudaMemcpy(&err, g_p2p.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) return fail(CLIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank");
+  if (err) {
+    CU(cudaMemset(g_p2p.d_err, 0, sizeof(int)));  // reported once; later all-reduces start clean
+    return fail(CLIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank (result zeroed)");
+  }
+  return CLIC_OK;
+}
+
+// ---- fused pass (pass_fused.cuh) ----
+// CLIC_FUSED=0: one kernel per stream + reduction + assembly (+ all-reduce) as in round 1 (A/B runs, tests compare the
+// two paths); read at every layout so that a test can flip it between two estimators.
+bool fused_enabled() { const char* e = getenv("CLIC_FUSED"); return !(e && e[0] == '0'); }
+// Static cost model of the grid partition: a stream on n CTAs takes  f + ceil(slabs / (8 n)) * w  microseconds — w per
+// 32-factor slab (16 for the visual stream) of one warp with two warps per SM sub-partition, f the stream's fixed part
+// (window staging, pose packs, first-slab latency, the dense finish) — fitted to %globaltimer stamps of the C5 window
+// and of its 1/8 shard on B200 (bench_micro/fused_probe.py; profiles/).  Only the ratios matter, and a wrong model costs
+// balance, never correctness: the partition is a pure function of the problem, so results stay bit-reproducible.
+// CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
+struct FusedModel { double w[kFusedKinds], f[kFusedKinds]; };
+const FusedModel& fused_model() {
+  static FusedModel m = {{3.7, 3.25, 3.5, 13.0, 9.0, 12.0}, {6.0, 6.0, 5.0, 26.0, 20.0, 30.0}};
+  static bool init = false;
+  if (!init) {
+    init = true;
+    double v[kFusedKinds];
+    if (const char* e = getenv("CLIC_FUSED_W"))
+      if (sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == kFusedKinds)
+        for (int i = 0; i < kFusedKinds; i++) if (v[i] > 0) m.w[i] = v[i];
+    if (const char* e = getenv("CLIC_FUSED_F"))
+      if (sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == kFusedKinds)
+        for (int i = 0; i < kFusedKinds; i++) if (v[i] >= 0) m.f[i] = v[i];
+  }
+  return m;
+}
+unsigned long long p2p_timeout_ns() {
+  static unsigned long long v = 0;
+  if (!v) {
+    double ms = 30000.0;
+    if (const char* e = getenv("CLIC_P2P_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
+    v = (unsigned long long)(ms * 1e6);
+  }
+  return v;
+}
+
+// Decides whether the pass of this layout runs as ONE pass_kernel launch and prepares its constant arguments: at most one
+// non-marginalization batch per stream kind (every shipped call pattern: a plane batch, a line batch, one IMU batch, one
+// visual batch), a device that launches cooperatively, and the grid partition from the cost model above.
+int build_fused(clic_estimator* E) {
+  auto& F = E->fused;
+  F.ok = false;
+  for (int k = 0; k < 3; k++) F.lb[k] = nullptr;
+  F.ib = nullptr;
+  F.gb = nullptr;
+  if (!fused_enabled() || E->L.D <= 0) return CLIC_OK;
+  for (auto& b : E->loam) {
+    if (b->marg) continue;
+    const int k = b->st.geo_kind;
+    if (k < 0 || k > 2 || F.lb[k]) return CLIC_OK;
+    F.lb[k] = b.get();
+  }
+  for (auto& b : E->imu) {
+    if (b->marg) continue;
+    if (F.ib) return CLIC_OK;
+    F.ib = b.get();
+  }
+  for (auto& b : E->image) {
+    if (b->marg) continue;
+    if (F.gb || b->st.n_packs <= 0) return CLIC_OK;  // the per-factor chain variant (> 96 distinct frame times) stays unfused
+    F.gb = b.get();
+  }
+  int coop = 0;
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, E->device));
+  if (!coop) return CLIC_OK;
+  struct Job { int kind; StreamExec* ex; int64_t slabs; int cap, n; double w, f; };
+  std::vector<Job> js;
+  const FusedModel& M = fused_model();
+  auto push = [&](int kind, StreamExec& ex, double scale = 1.0) {
+    Job j;
+    j.kind = kind;
+    j.ex = &ex;
+    j.slabs = std::max<int64_t>(1, ex.slabs_per_warp);  // (the field holds the stream's total slab count)
+    j.cap = (int)std::max<int64_t>(1, std::min<int64_t>(ex.grid, (j.slabs + kWarpsPerCta - 1) / kWarpsPerCta));
+    j.n = 1;
+    j.w = M.w[kind] * scale;
+    j.f = M.f[kind];
+    js.push_back(j);
+  };
+  // same order as the descriptors / reduce jobs of ensure_layout: LiDAR batches in add order, IMU, visual
+  for (auto& b : E->loam) if (!b->marg) push(b->st.geo_kind, b->ex);
+  if (F.ib) push(3, F.ib->ex, E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1.25 : 1.0);
+  if (F.gb) push(F.gb->st.n_packs > 0 ? 4 : 5, F.gb->ex);
+  if (js.empty() || (int)js.size() > E->n_sm) return CLIC_OK;
+  {
+    // exact min-max under the model: the finishing time T is one of  f_j + m w_j;  a stream needs
+    // n_j(T) = ceil(slabs_j / (8 floor((T - f_j) / w_j))) CTAs; smallest T whose CTAs fit the grid
+    auto need = [&](double T, std::vector<int>& n) -> bool {
+      int tot = 0;
+      for (size_t i = 0; i < js.size(); i++) {
+        const double room = (T - js[i].f) / js[i].w + 1e-9;
+        if (room < 1.0) return false;
+        const int64_t m = (int64_t)room;  // slabs per warp that fit
+        const int64_t c = (js[i].slabs + kWarpsPerCta * m - 1) / (kWarpsPerCta * m);
+        if (c > js[i].cap) return false;
+        n[i] = (int)std::max<int64_t>(1, c);
+        tot += n[i];
+      }
+      return tot <= E->n_sm;
+    };
+    std::vector<double> cand;
+    for (auto& j : js) {
+      const int64_t m_max = (j.slabs + kWarpsPerCta - 1) / kWarpsPerCta;
+      for (int64_t m = 1; m <= m_max; m = m < 64 ? m + 1 : m + m / 32)  // every m while small, ~3 % steps beyond
+        cand.push_back(j.f + (double)m * j.w);
+      cand.push_back(j.f + (double)m_max * j.w);
+    }
+    std::sort(cand.begin(), cand.end());
+    std::vector<int> n(js.size(), 1), best;
+    size_t lo = 0, hi = cand.size();
+    while (lo < hi) {  // feasibility is monotone in T
+      const size_t mid = (lo + hi) / 2;
+      if (need(cand[mid], n)) { best = n; hi = mid; } else { lo = mid + 1; }
+    }
+    if (!best.empty())
+      for (size_t i = 0; i < js.size(); i++) js[i].n = best[i];
+  }
+  // leftover CTAs (and the whole grid when the model found no fit): to the stream that would finish last
+  int used = 0;
+  for (auto& j : js) used += j.n;
+  while (used < E->n_sm) {
+    int best = -1;
+    double worst = 0.0;
+    for (size_t i = 0; i < js.size(); i++) {
+      if (js[i].n >= js[i].cap) continue;
+      const double t = js[i].f + js[i].w * (double)((js[i].slabs + (int64_t)kWarpsPerCta * js[i].n - 1) / ((int64_t)kWarpsPerCta * js[i].n));
+      if (best < 0 || t > worst) { best = (int)i; worst = t; }
+    }
+    if (best < 0) break;
+    js[best].n++;
+    used++;
+  }
+  if ((int)js.size() > kMaxFusedJobs || (int)js.size() != E->n_desc) return CLIC_OK;
+  FusedArgs& fa = F.fa;
+  std::memset(&fa, 0, sizeof(fa));
+  if (!F.d_bar.p) {  // one barrier word per CTA + the overflow flag (word 1024)
+    CU(F.d_bar.ensure(1025 * sizeof(unsigned)));
+    CU(cudaMemsetAsync(F.d_bar.p, 0, 1025 * sizeof(unsigned), E->stream));
+  }
+  const int D = E->L.D;
+  const int n_tot = D * (D + 1) / 2 + D + 2;
+  int cta0 = 0;
+  size_t body_smem = 0;
+  for (int k = 0; k < kFusedKinds; k++) F.part_ctas[k] = 0;
+  int jn = 0;
+  for (auto& j : js) {
+    FusedPart& P = fa.part[j.kind];
+    P.cta0 = cta0;
+    P.n_ctas = j.n;
+    P.total_slabs = j.ex->slabs_per_warp;
+    P.desc = jn;
+    P.rb = j.ex->rb();
+    P.rb.overflow_flag = reinterpret_cast<int*>(F.d_bar.as<unsigned>() + 1024);  // read back by phase A of the same pass
+    F.part_ctas[j.kind] = j.n;
+    cta0 += j.n;
+    fa.ovf_blocks[jn] = j.ex->overflow.as<double>();
+    fa.ovf_doubles[jn] = j.ex->n_keys * j.ex->rd;
+    jn++;
+    if (j.kind <= 2) body_smem = std::max(body_smem, loam_smem_bytes(E->K));
+    else if (j.kind == 3) body_smem = std::max(body_smem, factor_smem_bytes(E->K, 4));
+    else body_smem = std::max(body_smem, image_smem_bytes(E->K, F.gb->st.n_packs));
+  }
+  fa.n_jobs = jn;
+  fa.n_factor_ctas = cta0;
+  for (int k = 0; k < 3; k++) if (F.lb[k]) fa.loam[k] = F.lb[k]->st;
+  if (F.ib) fa.imu = F.ib->st;
+  if (F.gb) fa.image = F.gb->st;
+  F.grid = std::min(E->n_sm, std::max(cta0, (n_tot + 15) / 16));
+  const int epc = (n_tot + F.grid - 1) / F.grid;
+  // phase F: the stream bodies' shared memory, then the CTA's packed system and the key-column scratch;
+  // phase A: staged chunk + coordinates + the (producers x chunk) tile
+  body_smem = (body_smem + 15) & ~(size_t)15;
+  fa.hs_off = (int)(body_smem / sizeof(double));
+  size_t smem = body_smem + (size_t)((n_tot + 1) & ~1) * sizeof(double) + kKeyColsInts * sizeof(int);
+  smem = std::max(smem, (size_t)2 * epc * sizeof(double) + (size_t)cta0 * epc * sizeof(double));
+  smem = (smem + 15) & ~(size_t)15;
+  fa.persist_off = (int)(smem / sizeof(double));
+  smem += fused_persist_bytes(E->K, E->n_bias);
+  int max_optin = 0;
+  CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, E->device));
+  if (smem > (size_t)max_optin) return CLIC_OK;  // a system too wide for a per-CTA copy (C4, D = 240): per-stream kernels
+  F.smem = smem;
+  CU(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<true>, kThreads, smem));
+  if (occ < 1 || F.grid > occ * E->n_sm) return CLIC_OK;  // the grid barrier needs every CTA resident
+  CU(F.d_stamps.ensure((size_t)E->n_sm * 8 * sizeof(unsigned long long)));
+  CU(F.d_addend.ensure(((size_t)D * D + D + 2) * sizeof(double)));
+  CU(F.d_hloc.ensure((size_t)cta0 * n_tot * sizeof(double)));
+  {  // descriptors of the atomics-fallback blocks: the per-interval block layout of the per-stream path
+    std::vector<StreamDesc> dv(E->n_desc);
+    CU(cudaMemcpyAsync(dv.data(), E->d_descs.p, dv.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    for (int j = 0; j < jn; j++) dv[j].fin = fa.ovf_blocks[j];
+    CU(F.d_descs_ovf.ensure(dv.size() * sizeof(StreamDesc)));
+    CU(cudaMemcpyAsync(F.d_descs_ovf.p, dv.data(), dv.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+  }
+  fa.hloc = F.d_hloc.as<double>();
+  fa.cm.D = D;
+  fa.cm.K = E->K;
+  fa.cm.knot_col = E->d_knot_col.as<int>();
+  fa.cm.col_knot = E->d_col_knot.as<int>();
+  fa.cm.col_sub = E->d_col_sub.as<int>();
+  fa.descs = E->d_descs.as<StreamDesc>();
+  fa.descs_ovf = F.d_descs_ovf.as<StreamDesc>();
+  fa.off_bias = E->sl.off_bias();
+  fa.bar = F.d_bar.as<unsigned>();
+  fa.ovf_flag = F.d_bar.as<unsigned>() + 1024;
+  F.ok = true;
   return CLIC_OK;
 }
 
@@ -568,7 +842,7 @@ int ensure_layout(clic_estimator* E) {
   CU(cudaStreamSynchronize(E->stream));  // host vectors above go out of scope
   E->layout_dirty = false;
   E->bias_desc_dirty = true;
-  return CLIC_OK;
+  return build_fused(E);
 }
 
 
@@ -629,6 +903,144 @@ PassParams pass_params(const clic_estimator* E, const double* state, const int* 
   return pp;
 }
 
+std::vector<BiasFactorDesc> solve_bias_descs(const clic_estimator* E) {
+  std::vector<BiasFactorDesc> bias_descs;
+  for (auto& bf : E->bias_f) {
+    if (bf.marg) continue;
+    BiasFactorDesc d;
+    d.slot_i = bf.slot_i;
+    d.slot_j = bf.slot_j;
+    for (int i = 0; i < 6; i++) d.sqrt_info[i] = bf.sqrt_info[i];
+    d.col_gi = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_i : -1;
+    d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
+    d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
+    d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
+    bias_descs.push_back(d);
+  }
+  return bias_descs;
+}
+
+ImageShared image_shared(const clic_estimator* E, const ImageBatch* b) {
+  ImageShared ish;
+  ish.S_CtoI = ldq(E->S_CtoI);
+  ish.p_CinI = ldv(E->p_CinI);
+  ish.sqrt_info = 450.0 / 1.5;
+  ish.loss_a = b->st.loss_a;
+  ish.inv_dt = 1e9 / double(E->dt_ns);
+  ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
+  return ish;
+}
+void image_pass_fields(const clic_estimator* E, ImageStream& st, bool jac) {
+  const bool free_rho = E->L.n_free_landmarks > 0;
+  st.rho_side = (jac && free_rho) ? E->d_rho_side.as<double>() : nullptr;
+  st.lm_col = free_rho ? E->d_lm_col.as<int32_t>() : nullptr;
+  st.knot_col = E->d_knot_col.as<int>();
+  st.Dtot = E->L.D;
+  st.rho0 = E->L.col_inv_depth;
+  st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
+}
+
+// The pass as ONE persistent launch (pass_fused.cuh).  Terms that other kernels own (priors, the global-velocity
+// factor, more BiasFactors than the kernel takes) are evaluated first into a zeroed addend system that phase A adds
+// entry by entry, so they ride through the in-kernel exchange like everything else.
+int run_pass_fused(clic_estimator* E, const double* state, bool jac, double* Hp, double* bp, double* cost2,
+                   const int* ctl, int set) {
+  auto& F = E->fused;
+  int rc;
+  const int D = E->L.D;
+  for (int k = 0; k < 3; k++) if (F.lb[k] && (rc = wait_ready(E, F.lb[k]->ex))) return rc;
+  if (F.ib && (rc = wait_ready(E, F.ib->ex))) return rc;
+  if (F.gb && (rc = wait_ready(E, F.gb->ex))) return rc;
+  PassParams pp = pass_params(E, state, ctl);
+  pp.pdl_first = 1;
+  FusedArgs fa = F.fa;
+  if (F.ib) fa.imu.toff_free = E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1 : 0;
+  if (F.gb) {
+    image_pass_fields(E, fa.image, jac);
+    fa.ish = image_shared(E, F.gb);
+  }
+  if (jac && E->L.n_free_landmarks > 0) {
+    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.D + 2) * sizeof(double), E->stream));
+    fa.rho_side = E->d_rho_side.as<double>();
+    fa.rho0 = E->L.col_inv_depth;
+    fa.n_rho = E->L.n_free_landmarks;
+  }
+  std::vector<BiasFactorDesc> bias_descs = solve_bias_descs(E);
+  const bool bias_in_kernel = !bias_descs.empty() && (int)bias_descs.size() <= kMaxFusedBias;
+  if (bias_in_kernel) {  // the descriptors only depend on the layout: uploaded once per layout
+    if (E->bias_desc_dirty) {
+      CU(E->d_bias_descs.ensure(bias_descs.size() * sizeof(BiasFactorDesc)));
+      CU(cudaMemcpyAsync(E->d_bias_descs.p, bias_descs.data(), bias_descs.size() * sizeof(BiasFactorDesc),
+                         cudaMemcpyHostToDevice, E->stream));
+      CU(cudaStreamSynchronize(E->stream));
+      E->bias_desc_dirty = false;
+    }
+    fa.bias = E->d_bias_descs.as<BiasFactorDesc>();
+    fa.n_bias = (int)bias_descs.size();
+  }
+  const bool have_priors = !E->priors.empty() && !E->opt.is_marg_state;
+  const bool need_addend = have_priors || !E->vel_factors.empty() || (!bias_descs.empty() && !bias_in_kernel);
+  double* addend = nullptr;
+  if (need_addend) {
+    addend = F.d_addend.as<double>();
+    double* Ha = addend;
+    double* ba = addend + (size_t)D * D;
+    double* ca = ba + D;
+    CU(cudaMemsetAsync(addend, 0, ((size_t)D * D + D + 2) * sizeof(double), E->stream));
+    E->prof_begin(4);
+    if (!bias_in_kernel)
+      for (auto& d : bias_descs) {
+        CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, Ha, ba, D, ca, jac ? 1 : 0, ctl));
+        E->launches++;
+      }
+    if (have_priors)
+      for (auto& pr : E->priors)
+        if ((rc = launch_prior(E, pr.get(), state, ca, jac, ctl, Ha, ba))) return rc;
+    for (auto& vf : E->vel_factors) {
+      CU(launch_pdl(velocity_factor_kernel, 1, 64, 0, E->stream, vf, state, E->sl, (long long)E->t0_ns, (long long)E->dt_ns,
+                    E->K, (const int*)E->d_knot_col.as<int>(), E->L.col_t_offset[CLIC_SENSOR_IMU], Ha, ba, D, ca,
+                    jac ? 1 : 0, ctl));
+      E->launches++;
+    }
+    E->prof_end();
+  }
+  if (F.stamps_on) fa.stamps = F.d_stamps.as<unsigned long long>();
+  FusedOut out{};
+  out.H = Hp;
+  out.b = bp;
+  out.cost2 = cost2;
+  out.addend = addend;
+  const size_t n_tot = jac ? (size_t)D * (D + 1) / 2 + D + 2 : 2;
+  const bool exchange = E->use_comm && g_p2p.ready && n_tot <= kP2PMaxDoubles && F.grid <= kP2PMaxCtas;
+  if (exchange) {
+    double* G = E->nrm_glb_set(set);
+    out.Hg = G;
+    out.bg = G + E->off_b();
+    out.cost2g = G + (cost2 - Hp);
+    out.seq = ++g_p2p.seq;
+    out.timeout_ns = p2p_timeout_ns();
+    out.err = g_p2p.d_err;
+    out.exchange = 1;
+  }
+  E->prof_begin(0);
+  if (jac) CU(launch_coop(pass_kernel<true>, F.grid, kThreads, F.smem, E->stream, fa, pp, out, g_p2p.view));
+  else CU(launch_coop(pass_kernel<false>, F.grid, kThreads, F.smem, E->stream, fa, pp, out, g_p2p.view));
+  E->prof_end();
+  E->launches++;
+  CU(cudaGetLastError());
+  if (E->use_comm && !exchange) {  // no peer mapping (or a system too large for the slots): ncclAllReduce of the dense system
+    NcclApi& nc = nccl_api();
+    const size_t DD = (size_t)D * D + D;
+    const double* ar_src = jac ? Hp : cost2;
+    double* ar_dst = jac ? E->nrm_glb_set(set) : E->nrm_glb_set(set) + (cost2 - Hp);
+    E->prof_begin(6);
+    const int e = nc.AllReduce(ar_src, ar_dst, jac ? DD + 2 : 2, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
+    E->prof_end();
+    if (e != 0) return fail(CLIC_ERR_NCCL, std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "?"));
+  }
+  return CLIC_OK;
+}
+
 template <class KernelT>
 int set_smem(KernelT k, size_t bytes) {
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -645,6 +1057,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   double* bp = Hp + E->off_b();
   // slot 0: pass at x, slot 1: pass at the LM candidate (set 0);  set 1 keeps its cost in its own slot 0
   double* cost2 = Hp + E->off_cost() + (set ? 0 : 2 * which);
+  if (E->fused.ok) return run_pass_fused(E, state, jac, Hp, bp, cost2, ctl, set);
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
   if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: accumulated by the visual kernels
@@ -697,22 +1110,10 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
     const size_t smem = factor_smem_bytes(E->K, 7);
-    ImageShared ish;
-    ish.S_CtoI = ldq(E->S_CtoI);
-    ish.p_CinI = ldv(E->p_CinI);
-    ish.sqrt_info = 450.0 / 1.5;
-    ish.loss_a = b->st.loss_a;
-    ish.inv_dt = 1e9 / double(E->dt_ns);
-    ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
+    const ImageShared ish = image_shared(E, b);
     const bool packed = b->st.n_packs > 0;
     const size_t smem_p = image_smem_bytes(E->K, b->st.n_packs);
-    const bool free_rho = E->L.n_free_landmarks > 0;
-    b->st.rho_side = (jac && free_rho) ? E->d_rho_side.as<double>() : nullptr;
-    b->st.lm_col = free_rho ? E->d_lm_col.as<int32_t>() : nullptr;
-    b->st.knot_col = E->d_knot_col.as<int>();
-    b->st.Dtot = E->L.D;
-    b->st.rho0 = E->L.col_inv_depth;
-    b->st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
+    image_pass_fields(E, b->st, jac);
     E->prof_begin(2);
     if (jac && packed) CU(launch_pdl(image_kernel<true, true>, ex.grid, kThreads, smem_p, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
     else if (jac) CU(launch_pdl(image_kernel<true, false>, ex.grid, kThreads, smem, E->stream, b->st, pp, ex.slabs_per_warp, ex.rb(), ish));
@@ -747,19 +1148,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     E->prof_end();
   }
   E->launches += 1;
-  std::vector<BiasFactorDesc> bias_descs;
-  for (auto& bf : E->bias_f) {
-    if (bf.marg) continue;
-    BiasFactorDesc d;
-    d.slot_i = bf.slot_i;
-    d.slot_j = bf.slot_j;
-    for (int i = 0; i < 6; i++) d.sqrt_info[i] = bf.sqrt_info[i];
-    d.col_gi = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_i : -1;
-    d.col_gj = E->L.col_bias_gyro >= 0 ? E->L.col_bias_gyro + 3 * bf.slot_j : -1;
-    d.col_ai = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_i : -1;
-    d.col_aj = E->L.col_bias_accel >= 0 ? E->L.col_bias_accel + 3 * bf.slot_j : -1;
-    bias_descs.push_back(d);
-  }
+  std::vector<BiasFactorDesc> bias_descs = solve_bias_descs(E);
   const bool bias_in_assemble = jac && D > 0 && !bias_descs.empty() && bias_descs.size() <= 4;
   if (jac && D > 0) {
     ColMaps cm;
@@ -817,7 +1206,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
     const size_t ar_count = jac ? DD + 2 : 2;
     if (g_p2p.ready && ar_count <= kP2PMaxDoubles) {
       CU(launch_pdl(p2p_allreduce_kernel, 1, 1024, 0, E->stream, ar_src, ar_dst, (int)ar_count, g_p2p.view, ++g_p2p.seq,
-                    g_p2p.d_err));
+                    p2p_timeout_ns(), g_p2p.d_err));
       E->launches++;
     } else {
       e = nc.AllReduce(ar_src, ar_dst, ar_count, kNcclDouble, kNcclSum, g_comm.comm, E->stream);
@@ -1859,10 +2248,12 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
       const int64_t a = (int64_t)(t_i[i] * 1e9), b = (int64_t)(t_j[i] * 1e9);
       if (!(a - pad < t_min || a + pad >= t_max) && !(b - pad < t_min || b + pad >= t_max)) E->lm_free[landmark[i]] = 1;
     }
-  // Order by the (s_i, s_j) knot-interval key (stable counting sort, O(n)): consecutive factors then share their key
-  // and a warp's accumulators are flushed rarely.  The key here only orders the inputs (host arithmetic at the
-  // current offset); the kernels recompute the exact indices.
-  B->perm.resize(n);
+  // Order by the (s_i, s_j) knot-interval key (stable counting sort, O(n)), every key's factors starting on a slab
+  // boundary (padding = dropped factors): a 16-factor slab then holds ONE key — a slab that straddles k keys costs k
+  // evaluation rounds — and a warp's accumulators are flushed rarely.  The key here only orders the inputs (host
+  // arithmetic at the current offset); the kernels recompute the exact indices.
+  const int64_t n_in = n;
+  if (n_in > INT32_MAX / 2) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_image: batch too large");
   {
     const int nk = std::max(1, E->K - 3);
     const int64_t toff = (int64_t)E->h_state[E->sl.off_toff() + S];
@@ -1870,15 +2261,19 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
       const int64_t q = ((int64_t)(t * 1e9) + toff - E->t0_ns) / E->dt_ns;
       return (int)std::min<int64_t>(nk - 1, std::max<int64_t>(0, q));
     };
-    std::vector<int> key(n);
+    std::vector<int> key(n_in);
     std::vector<int64_t> start((size_t)nk * nk + 1, 0);
-    for (int64_t i = 0; i < n; i++) {
+    for (int64_t i = 0; i < n_in; i++) {
       key[i] = interval(t_i[i]) * nk + interval(t_j[i]);
       start[key[i] + 1]++;
     }
-    for (size_t k = 0; k < (size_t)nk * nk; k++) start[k + 1] += start[k];
-    for (int64_t i = 0; i < n; i++) B->perm[start[key[i]]++] = i;
+    for (size_t k = 0; k < (size_t)nk * nk; k++)
+      start[k + 1] = start[k] + (start[k + 1] + kImageFactorsPerSlab - 1) / kImageFactorsPerSlab * kImageFactorsPerSlab;
+    B->gather.assign((size_t)start[(size_t)nk * nk], -1);
+    for (int64_t i = 0; i < n_in; i++) B->gather[start[key[i]]++] = (int32_t)i;
   }
+  n = (int64_t)B->gather.size();  // stored factors, padding included
+  B->n_input = n_in;
   // Permuted copies go through a page-locked staging arena (process-wide, grown on demand, guarded by the event of
   // its last upload): a cudaMemcpyAsync from pageable vectors would block this thread until every earlier copy on
   // the stream (the LiDAR batch) has drained.
@@ -1906,8 +2301,16 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   int32_t* s_lm = reinterpret_cast<int32_t*>(s_pack_t + kMaxPosePacks);
   int32_t* s_idi = s_lm + n;
   int32_t* s_idj = s_idi + n;
+  constexpr double kPadTime = -1.0e9;  // seconds: far before any window, exactly representable in ns
   for (int64_t k = 0; k < n; k++) {
-    const int64_t i = B->perm[k];
+    const int64_t i = B->gather[k];
+    if (i < 0) {
+      s_ti[k] = s_tj[k] = kPadTime;
+      for (int c = 0; c < 3; c++) { s_pi[3 * k + c] = 0.0; s_pj[3 * k + c] = 0.0; }
+      s_lm[k] = 0;
+      s_idi[k] = s_idj[k] = 0;
+      continue;
+    }
     s_ti[k] = t_i[i];
     s_tj[k] = t_j[i];
     for (int c = 0; c < 3; c++) { s_pi[3 * k + c] = p_i[3 * i + c]; s_pj[3 * k + c] = p_j[3 * i + c]; }
@@ -1936,6 +2339,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
       return tab_id[r][h];
     };
     for (int64_t k = 0; k < n && use_packs; k++) {
+      if (B->gather[k] < 0) continue;
       const int a = lookup(0, (int64_t)(s_ti[k] * 1e9), n_pack_i, pack_t_i);
       const int b = a < 0 ? -1 : lookup(1, (int64_t)(s_tj[k] * 1e9), n_pack_j, pack_t_j);
       if (a < 0 || b < 0) { use_packs = false; break; }
@@ -1943,7 +2347,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
       s_idj[k] = b;
     }
     if (use_packs) {
-      for (int64_t k = 0; k < n; k++) s_idj[k] += n_pack_i;
+      for (int64_t k = 0; k < n; k++) if (B->gather[k] >= 0) s_idj[k] += n_pack_i;
       for (int q = 0; q < n_pack_i; q++) s_pack_t[q] = pack_t_i[q];
       for (int q = 0; q < n_pack_j; q++) s_pack_t[n_pack_i + q] = pack_t_j[q];
     }
@@ -1975,7 +2379,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     unsigned long long dropped = 0;
     CU(cudaMemcpyAsync(&dropped, E->d_counter.p, sizeof(dropped), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
-    *n_dropped = (int64_t)dropped;
+    *n_dropped = (int64_t)dropped - (n - n_in);  // the padding counted as dropped
   }
   B->st.n = n;
   B->st.ti_ns = B->ti.as<int64_t>();
@@ -1991,7 +2395,7 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
   B->st.loss_a = marg_this_feature ? 1.0 : 2.0;  // trajectory_estimator.cpp:806-810
   B->marg = (E->opt.is_marg_state && marg_this_feature) ? 1 : 0;
   B->lm_used.assign(std::max(0, E->n_lm), 0);
-  for (int64_t i = 0; i < n; i++) {  // same window test as prep_image_kernel
+  for (int64_t i = 0; i < n_in; i++) {  // same window test as prep_image_kernel
     const int64_t a = (int64_t)(t_i[i] * 1e9), b = (int64_t)(t_j[i] * 1e9);
     if (!(a - pad < t_min || a + pad >= t_max) && !(b - pad < t_min || b + pad >= t_max)) B->lm_used[landmark[i]] = 1;
   }
@@ -2114,7 +2518,7 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   int64_t total = 0;
   if (stream == 0) for (auto& b : E->loam) total += b->n_input;
   if (stream == 1) for (auto& b : E->imu) total += b->n_input;
-  if (stream >= 2) for (auto& b : E->image) total += b->st.n;
+  if (stream >= 2) for (auto& b : E->image) total += b->n_input;
   if (n_out) *n_out = total;
   if (capacity <= 0 || total == 0) return CLIC_OK;
   if (int jrc = join_adds(E)) return jrc;
@@ -2165,17 +2569,11 @@ CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacit
   if (stream == 1)
     for (auto& b : E->imu)
       if ((rc = run(b->st.n, b->st.t_ns, (int64_t)toff_d[CLIC_SENSOR_IMU], &b->gather, b->n_input))) return rc;
-  if (stream >= 2)
-    for (auto& b : E->image) {
-      const int64_t base = done;
-      if ((rc = run(b->st.n, stream == 2 ? b->st.ti_ns : b->st.tj_ns, (int64_t)toff_d[CLIC_SENSOR_CAMERA]))) return rc;
-      // the stream is stored sorted by (t_i, t_j): report in add order
-      const int64_t m = done - base;
-      std::vector<int32_t> ts(s_out + base, s_out + base + m);
-      std::vector<double> tu(u_out + base, u_out + base + m);
-      if (m == b->st.n)
-        for (int64_t k = 0; k < m; k++) { s_out[base + b->perm[k]] = ts[k]; u_out[base + b->perm[k]] = tu[k]; }
-    }
+  if (stream >= 2)  // the stream is stored sorted by (s_i, s_j) with padding: reported in add order through the gather map
+    for (auto& b : E->image)
+      if ((rc = run(b->st.n, stream == 2 ? b->st.ti_ns : b->st.tj_ns, (int64_t)toff_d[CLIC_SENSOR_CAMERA], &b->gather,
+                    b->n_input)))
+        return rc;
   return CLIC_OK;
 }
 
@@ -2491,7 +2889,7 @@ CLIC_API int clic_synchronize(clic_estimator* E) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
   CU(cudaStreamSynchronize(E->copy_stream));
   CU(cudaStreamSynchronize(E->stream));
-  return CLIC_OK;
+  return check_p2p(E);
 }
 
 CLIC_API int clic_profile_enable(clic_estimator* E, int32_t enable) {
@@ -2514,6 +2912,30 @@ CLIC_API int clic_profile_read(clic_estimator* E, double ms[8], int64_t launches
     CU(cudaEventElapsedTime(&t, sp.a, sp.b));
     if (sp.kind >= 0 && sp.kind < 8) { if (ms) ms[sp.kind] += t; if (launches) launches[sp.kind] += 1; }
   }
+  return CLIC_OK;
+}
+
+CLIC_API int clic_pass_info(clic_estimator* E, int32_t* fused, int32_t* grid, int32_t part_ctas[6]) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  if (fused) *fused = E->fused.ok ? 1 : 0;
+  if (grid) *grid = E->fused.ok ? E->fused.grid : 0;
+  if (part_ctas)
+    for (int k = 0; k < kFusedKinds; k++) part_ctas[k] = E->fused.ok ? E->fused.part_ctas[k] : 0;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_pass_stamps(clic_estimator* E, int32_t enable, int64_t capacity, uint64_t* stamps, int32_t* n_ctas) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  CU(cudaStreamSynchronize(E->stream));
+  if (n_ctas) *n_ctas = E->fused.ok ? E->fused.grid : 0;
+  if (stamps && E->fused.ok && E->fused.stamps_on && capacity >= (int64_t)E->fused.grid * 8)
+    CU(cudaMemcpy(stamps, E->fused.d_stamps.p, (size_t)E->fused.grid * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  E->fused.stamps_on = enable != 0;
   return CLIC_OK;
 }
 

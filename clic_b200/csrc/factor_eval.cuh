@@ -451,19 +451,24 @@ struct ImageChainPoses {
 //   q[4] | pos[3] | c[4] | G[4][3][3] | gyro[3] | vel[3]      with  rows(a)[k] = a^T G[k]  (the rows are linear in a)
 constexpr int kPackQ = 0, kPackPos = 4, kPackC = 7, kPackG = 11, kPackGyro = 47, kPackVel = 50, kPackDoubles = 54;
 // One call fills the row `c` (0..2) of every G[k]; the call with c == 0 also fills the other fields.
-CLIC_HD void compute_pose_pack(const WindowView& W, int s, double u, int role_j, double inv_dt, int c, double* pack) {
+// Rows c0 .. c1-1 of every G[k] from ONE evaluation of the chain; the call with c0 == 0 also fills the other fields.
+CLIC_HD void compute_pose_pack_rows(const WindowView& W, int s, double u, int role_j, double inv_dt, int c0, int c1,
+                                    double* pack) {
   So3Chain C;
   Q4 P[4];
   if (role_j) so3_chain_rtp(W, s, u, &C, P); else so3_chain_rp(W, s, u, &C);
-  const V3 e = mk(c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0);
-  V3 j[4];
-  if (role_j) so3_rows_rtp(W, s, C, P, e, j); else so3_rows_rp(W, s, C, e, j);
+  for (int c = c0; c < c1; c++) {
+    const V3 e = mk(c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0);
+    V3 j[4];
+    if (role_j) so3_rows_rtp(W, s, C, P, e, j); else so3_rows_rp(W, s, C, e, j);
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    pack[kPackG + 9 * k + 3 * c + 0] = j[k].x;
-    pack[kPackG + 9 * k + 3 * c + 1] = j[k].y;
-    pack[kPackG + 9 * k + 3 * c + 2] = j[k].z;
+    for (int k = 0; k < 4; k++) {
+      pack[kPackG + 9 * k + 3 * c + 0] = j[k].x;
+      pack[kPackG + 9 * k + 3 * c + 1] = j[k].y;
+      pack[kPackG + 9 * k + 3 * c + 2] = j[k].z;
+    }
   }
+  const int c = c0;
   if (c != 0) return;
   pack[kPackQ + 0] = C.R.x; pack[kPackQ + 1] = C.R.y; pack[kPackQ + 2] = C.R.z; pack[kPackQ + 3] = C.R.w;
   double cc[4];
@@ -478,6 +483,9 @@ CLIC_HD void compute_pose_pack(const WindowView& W, int s, double u, int role_j,
   const V3 g = so3_velocity_body(W, s, u, inv_dt), v = ImageChainPoses::lin_vel(W, s, u, inv_dt);
   pack[kPackGyro + 0] = g.x; pack[kPackGyro + 1] = g.y; pack[kPackGyro + 2] = g.z;
   pack[kPackVel + 0] = v.x; pack[kPackVel + 1] = v.y; pack[kPackVel + 2] = v.z;
+}
+CLIC_HD void compute_pose_pack(const WindowView& W, int s, double u, int role_j, double inv_dt, int c, double* pack) {
+  compute_pose_pack_rows(W, s, u, role_j, inv_dt, c, c + 1, pack);
 }
 struct ImagePackPoses {
   const double* A;  // pack of t_i (role i)

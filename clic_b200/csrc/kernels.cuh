@@ -187,6 +187,202 @@ __device__ __forceinline__ void flush_record(const WarpAcc<NT, EXTRA>& acc, int 
   }
 }
 
+// One descriptor per factor stream whose records were reduced to per-key blocks.
+struct StreamDesc {
+  const double* fin;     // [n_keys][rd] per-key blocks of reduce_all_kernel (atomics-fallback block folded in)
+  int n_keys, NT, rd;
+  int r_col;             // local column holding r~ (when b lives in the tiles)
+  int b_off;             // >= 0: b = J~^T r~ is stored as a plain vector at this offset of the record (LiDAR)
+  int n_extra;           // local columns extra_base .. extra_base+n_extra-1 map to extra_global[] (-1: constant)
+  int extra_base;        // 24 (one knot window) or 48 (two windows)
+  int kind;              // 0: key = interval s (LiDAR / IMU);  1: key = s_i * kdim + s_j (visual, two knot windows)
+  int kdim;
+  int extra_global[12];
+  unsigned char perm[64]; // logical local column -> physical column inside the record tiles
+};
+
+struct ColMaps {
+  int D, K;
+  const int* knot_col;   // [K] column of knot's dtheta (dp = +3), -1 if constant
+  const int* col_knot;   // [D] knot of a column (-1: not a knot column)
+  const int* col_sub;    // [D] 0..5 within the knot
+};
+
+
+__device__ __forceinline__ int block_offset(int NT, int la, int lb) {  // la, lb: PHYSICAL columns of the record tiles
+  int ta = la >> 3, tb = lb >> 3;
+  if (ta > tb) { int t = ta; ta = tb; tb = t; t = la; la = lb; lb = t; }
+  return tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7);
+}
+
+// ---- dense finish (pass_kernel, pass_fused.cuh): instead of emitting records for a later reduction, a CTA adds what it
+// accumulated straight into ITS OWN copy of the packed system [upper triangle of H row-major | b | cost, fixed cost]
+// in shared memory and writes that out contiguously; after one grid barrier the assembly is a sum over CTAs of
+// identically laid out vectors (coalesced, no keys to look up).  Everything stays deterministic: groups of warps with
+// the same interval are summed element-wise in warp order, then every target entry of the packed system is owned by
+// one thread, which pulls its <= 4 terms from the group's record in a fixed order.
+struct DenseOut {
+  double* Hs;              // shared memory: the CTA's packed system, n_ent + 2 doubles, zeroed at kernel start
+  int n_ent;               // D (D + 1) / 2 + D
+  int D;
+  const StreamDesc* sd;    // this stream's column descriptor (a shared-memory copy: it is read per target entry)
+  const int* knot_col;     // [K] column of the knot's dtheta, -1 if constant (shared-memory copy)
+  int* key_cols;           // shared memory scratch: [1 + 64 * 3] ints (see build_key_cols)
+};
+__device__ __forceinline__ int packed_row_start(int D, int gi) { return gi * D - gi * (gi - 1) / 2; }
+
+// The distinct global columns a record of interval key `key` touches, ascending, each with its (<= 2) local logical
+// columns: kc[0] = U, then U triples (global column, local candidate 0, local candidate 1 or -1).  Built by warp 0.
+__device__ __forceinline__ void build_key_cols(const StreamDesc& sd, const int* knot_col, int key, int* kc, int lane) {
+  int base = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int i = half * 32 + lane;
+    int g = -1, c0 = -1, c1 = -1;
+    if (sd.kind == 0) {
+      if (i < 24) {
+        const int kcol = knot_col[key + i / 6];
+        if (kcol >= 0) { g = kcol + i % 6; c0 = i; }
+      } else if (i < 24 + sd.n_extra) {
+        g = sd.extra_global[i - 24];
+        c0 = sd.extra_base + (i - 24);
+      }
+    } else {
+      const int si = key / sd.kdim, sj = key - si * sd.kdim;
+      const int lo = min(si, sj), hi = max(si, sj);
+      if (i < 48) {  // candidate knots lo..lo+3, then hi..hi+3 (those not among the first four): ascending, unique
+        const int m = i / 6, c = i % 6;
+        const int k = m < 4 ? lo + m : hi + (m - 4);
+        if (m < 4 || k > lo + 3) {
+          const int kcol = knot_col[k];
+          if (kcol >= 0) {
+            g = kcol + c;
+            const int di = k - si, dj = k - sj;
+            const int a = (di >= 0 && di <= 3) ? 6 * di + c : -1, b = (dj >= 0 && dj <= 3) ? 24 + 6 * dj + c : -1;
+            c0 = a >= 0 ? a : b;
+            c1 = a >= 0 ? b : -1;
+          }
+        }
+      } else if (i < 48 + sd.n_extra) {
+        g = sd.extra_global[i - 48];
+        c0 = sd.extra_base + (i - 48);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, g >= 0);
+    if (g >= 0) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      kc[1 + 3 * pos] = g;
+      kc[2 + 3 * pos] = c0;
+      kc[3 + 3 * pos] = c1;
+    }
+    base += __popc(m);
+  }
+  if (lane == 0) kc[0] = base;
+}
+
+// rec (shared or global memory): one record of this stream (tiles [+ b vector]); adds it into dn.Hs.  All threads of the
+// CTA call; two block barriers inside.
+template <int NTHREADS>
+__device__ __forceinline__ void dense_scatter_record(const DenseOut& dn, const double* rec, int key) {
+  const StreamDesc& sd = *dn.sd;
+  __syncthreads();  // key_cols of the previous record are no longer read; rec is complete
+  if (threadIdx.x < 32) build_key_cols(sd, dn.knot_col, key, dn.key_cols, threadIdx.x);
+  __syncthreads();
+  const int* kc = dn.key_cols;
+  const int U = kc[0];
+  const int n_pairs = U * (U + 1) / 2;
+  const int D = dn.D, n_upper = D * (D + 1) / 2;
+  const int NT = sd.NT;
+  for (int t = threadIdx.x; t < n_pairs + U; t += NTHREADS) {
+    double v = 0.0;
+    int dst;
+    if (t < n_pairs) {  // unrank u <= v over U (float estimate, exact integer correction)
+      const float q = 2.0f * U + 1.0f;
+      int u = (int)((q - sqrtf(q * q - 8.0f * (float)t)) * 0.5f);
+      u = max(0, min(U - 1, u));
+      while (u > 0 && u * U - u * (u - 1) / 2 > t) u--;
+      while ((u + 1) * U - (u + 1) * u / 2 <= t) u++;
+      const int w = u + (t - (u * U - u * (u - 1) / 2));
+      const int gi = kc[1 + 3 * u], gj = kc[1 + 3 * w];
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const int la = kc[2 + x + 3 * u];
+        if (la < 0) continue;
+#pragma unroll
+        for (int y = 0; y < 2; y++) {
+          const int lb = kc[2 + y + 3 * w];
+          if (lb < 0) continue;
+          v += rec[block_offset(NT, sd.perm[la], sd.perm[lb])];
+        }
+      }
+      dst = packed_row_start(D, gi) + (gj - gi);
+    } else {
+      const int u = t - n_pairs;
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const int la = kc[2 + x + 3 * u];
+        if (la < 0) continue;
+        v += sd.b_off >= 0 ? rec[sd.b_off + la] : rec[block_offset(NT, sd.perm[la], sd.perm[sd.r_col])];
+      }
+      dst = n_upper + kc[1 + 3 * u];
+    }
+    dn.Hs[dst] += v;
+  }
+}
+
+// End of a factor body in dense mode (replaces cta_merge_and_flush + the per-warp cost words).
+template <int NT, int EXTRA, int WARPS>
+__device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, int acc_key, int slot, int warp, int lane,
+                                                 int warp_global, const RecordBuf& rb, double* scratch, const DenseOut& dn,
+                                                 double cost, double fcost, bool jac) {
+  constexpr int RD = rec_doubles(NT, EXTRA);
+  __shared__ int s_keys[WARPS], s_slot[WARPS];
+  __shared__ double s_cost[WARPS][2];
+  __syncthreads();  // the Jt tiles under `scratch` are dead for every warp
+  if (jac && acc_key >= 0) acc.store(scratch + (size_t)warp * RD, lane);
+  if (lane == 0) {
+    s_keys[warp] = jac ? acc_key : -1;
+    s_slot[warp] = slot;
+    s_cost[warp][0] = cost;
+    s_cost[warp][1] = fcost;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {  // the CTA's cost words: warps in order
+    double c = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) c += s_cost[w][threadIdx.x];
+    dn.Hs[dn.n_ent + threadIdx.x] = c;  // a CTA runs one stream: plain store
+  }
+  if (!jac) return;
+  // groups of warps with the same key, in order of their first warp: element-wise sum in warp order into the first
+  // warp's slice, then one scatter per group
+  for (int w0 = 0; w0 < WARPS; w0++) {
+    const int kc = s_keys[w0];
+    if (kc < 0) continue;
+    bool first = true;
+    for (int w = 0; w < w0; w++) first = first && s_keys[w] != kc;
+    if (!first) continue;
+    bool alone = true;
+    for (int w = w0 + 1; w < WARPS; w++) alone = alone && s_keys[w] != kc;
+    if (!alone) {
+      for (int e = threadIdx.x; e < RD; e += WARPS * 32) {
+        double a = scratch[(size_t)w0 * RD + e];
+        for (int w = w0 + 1; w < WARPS; w++)
+          if (s_keys[w] == kc) a += scratch[(size_t)w * RD + e];
+        scratch[(size_t)w0 * RD + e] = a;
+      }
+    }
+    dense_scatter_record<WARPS * 32>(dn, scratch + (size_t)w0 * RD, kc);
+  }
+  // records flushed in mid-run (a warp whose interval changed): read back from this CTA's own slots, in (warp, slot) order
+  for (int w = 0; w < WARPS; w++)
+    for (int sl = 0; sl < min(s_slot[w], kSlotsPerWarp); sl++) {
+      const int r = (warp_global - warp + w) * kSlotsPerWarp + sl;
+      dense_scatter_record<WARPS * 32>(dn, rb.payload + (size_t)r * RD, rb.key[r]);
+    }
+  __syncthreads();
+}
+
 // End of a factor kernel: the live accumulators of the CTA's warps that share the key of the first live warp (all
 // of them, for time-sorted input) become ONE record; the others are flushed individually.  8x fewer records for the
 // reduction stage, no atomics, fixed order.  Every warp first parks its accumulator in its own slice of `scratch`
@@ -281,22 +477,21 @@ __device__ __forceinline__ double warp_transpose_reduce24(const double (&v)[24],
 // masked lanes with a zero scale.  The loads of the next slab are issued before the DMMA phase of the current one.
 // GEO: 0 = planes and lines mixed in one stream (type byte per feature), 1 = planes only (4 geometry doubles, the
 // line code is compiled out), 2 = lines only (no type byte; no intra-warp divergence between the two residuals).
-template <bool JAC, int WARPS, int MINB, int GEO = 0>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
-  if (pass_prologue(pp)) return;
-  extern __shared__ double smem[];
-  double* rest;
-  WindowView W = stage_window(smem, pp, &rest);
+// The body is shared by loam_kernel (one stream per launch) and pass_kernel (pass_fused.cuh: every stream of a pass in
+// one launch, this stream on CTAs cta = 0 .. n_ctas-1 of its partition).
+template <bool JAC, int WARPS, int GEO, bool DENSE = false>
+__device__ __forceinline__ void loam_body(const LoamStream& st, const PassParams& pp, int total_slabs, const RecordBuf& rb,
+                                          const WindowView& W, double* rest, int cta, int n_ctas,
+                                          const DenseOut* dn = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * WARPS + warp;
+  const int warp_global = cta * WARPS + warp;
   double* Jt = rest + (size_t)warp * 24 * kJtStride;
   WarpAcc<3, 1> acc;
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
   // balanced contiguous split of the slabs over all warps of the grid (sizes differ by at most one)
-  const int64_t n_warps_grid = (int64_t)gridDim.x * WARPS;
+  const int64_t n_warps_grid = (int64_t)n_ctas * WARPS;
   const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
   const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   // software pipeline registers (next slab)
@@ -379,20 +574,33 @@ loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
     }
     if (!prefetched) prefetch(next_idx);
   }
-  if (JAC) {
-    cta_merge_and_flush<3, 1, WARPS>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
-    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
-  }
   // deterministic butterfly
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cost += __shfl_xor_sync(0xffffffffu, cost, o);
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
+  if (DENSE) {
+    cta_finish_dense<3, 1, WARPS>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
+    return;
+  }
+  if (JAC) {
+    cta_merge_and_flush<3, 1, WARPS>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
   if (lane == 0) {
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+}
+template <bool JAC, int WARPS, int MINB, int GEO = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+loam_kernel(LoamStream st, PassParams pp, int total_slabs, RecordBuf rb) {
+  if (pass_prologue(pp)) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  loam_body<JAC, WARPS, GEO>(st, pp, total_slabs, rb, W, rest, blockIdx.x, gridDim.x);
   pass_epilogue(pp);
 }
 
@@ -611,16 +819,13 @@ struct NullSink {
 
 // Local columns (solve, NT=4): [knots 0..23 | bg 24..26 | ba 27..29 | toff 30 | r 31]
 //               (marg,  NT=5): [knots 0..23 | bg | ba | gravity 30..32 | toff 33 | r 34 | pad]
-template <bool JAC, bool MARG>
-__global__ void __launch_bounds__(kThreads, 1)
-imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
+template <bool JAC, bool MARG, bool DENSE = false>
+__device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& pp, int total_slabs, const RecordBuf& rb,
+                                         const WindowView& W, double* rest, int cta, int n_ctas,
+                                         const DenseOut* dn = nullptr) {
   constexpr int NT = MARG ? 5 : 4;
-  if (pass_prologue(pp)) return;
-  extern __shared__ double smem[];
-  double* rest;
-  WindowView W = stage_window(smem, pp, &rest);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  const int warp_global = cta * kWarpsPerCta + warp;
   double* Jt = rest + (size_t)warp * (8 * NT) * kJtStride;
   ImuShared sh;
 #pragma unroll
@@ -638,7 +843,7 @@ imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
-  const int64_t n_warps_grid = (int64_t)gridDim.x * kWarpsPerCta;
+  const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
   const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
   const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
@@ -683,19 +888,32 @@ imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
       pending &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
-  if (JAC) {
-    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
-    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
-  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cost += __shfl_xor_sync(0xffffffffu, cost, o);
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
+  if (DENSE) {
+    cta_finish_dense<NT, 0, kWarpsPerCta>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
+    return;
+  }
+  if (JAC) {
+    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
   if (lane == 0) {
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+}
+template <bool JAC, bool MARG>
+__global__ void __launch_bounds__(kThreads, 1)
+imu_kernel(ImuStream st, PassParams pp, int total_slabs, RecordBuf rb) {
+  if (pass_prologue(pp)) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  imu_body<JAC, MARG>(st, pp, total_slabs, rb, W, rest, blockIdx.x, gridDim.x);
   pass_epilogue(pp);
 }
 
@@ -731,27 +949,29 @@ constexpr int kMaxPosePacks = 96;
 // 32-row tile accumulation covers a slab and each lane builds one Jacobian row only (this stream is small and
 // latency-bound: shorter per-lane work + twice as many slabs to spread over the SMs).
 constexpr int kImageFactorsPerSlab = 16;
-template <bool JAC, bool PACKED>
-__global__ void __launch_bounds__(kThreads, 1)
-image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, ImageShared sh) {
+template <bool JAC, bool PACKED, bool DENSE = false>
+__device__ __forceinline__ void image_body(const ImageStream& st, const PassParams& pp, int total_slabs, const RecordBuf& rb,
+                                           const ImageShared& sh, const WindowView& W, double* rest, int cta, int n_ctas,
+                                           const DenseOut* dn = nullptr) {
   constexpr int NT = 7;
-  if (pass_prologue(pp)) return;
-  extern __shared__ double smem[];
-  double* rest;
-  WindowView W = stage_window(smem, pp, &rest);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+  const int warp_global = cta * kWarpsPerCta + warp;
   const int row_sel = lane >> 4;
   const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 2];  // camera offset, image_feature_factor.h:75-76
   const double* packs = rest;
   if (PACKED) {  // thread (pack, c): row c of the pack's Jacobian maps; c == 0 also the pose itself
     double* pk = rest;
-    for (int t = threadIdx.x; t < 3 * st.n_packs; t += blockDim.x) {
-      const int id = t / 3, c = t % 3;
+    // every task is one chain evaluation (~10 us of dependent FP64 latency): as many tasks per pack as fit ONE round
+    // of the CTA's threads — 3 (one row of the maps each), 2 (row 0 + pose | rows 1, 2) or 1
+    const int tpp = 3 * st.n_packs <= (int)blockDim.x ? 3 : (2 * st.n_packs <= (int)blockDim.x ? 2 : 1);
+    for (int t = threadIdx.x; t < tpp * st.n_packs; t += blockDim.x) {
+      const int id = t / tpp, q = t % tpp;
+      const int c0 = tpp == 3 ? q : (tpp == 2 ? (q == 0 ? 0 : 1) : 0);
+      const int c1 = tpp == 3 ? q + 1 : (tpp == 2 ? (q == 0 ? 1 : 3) : 3);
       int s = 0;
       double u = 0.0;
       if (!index_ns(st.pack_t_ns[id] + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &s, &u)) { s = 0; u = 0.0; }  // unused pack
-      compute_pose_pack(W, s, u, id >= st.n_pack_i ? 1 : 0, sh.inv_dt, c, pk + (size_t)id * kPackDoubles);
+      compute_pose_pack_rows(W, s, u, id >= st.n_pack_i ? 1 : 0, sh.inv_dt, c0, c1, pk + (size_t)id * kPackDoubles);
     }
     rest += (size_t)st.n_packs * kPackDoubles;  // even: what follows stays 16-byte aligned
     __syncthreads();
@@ -763,7 +983,7 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
   acc.zero();
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
-  const int64_t n_warps_grid = (int64_t)gridDim.x * kWarpsPerCta;
+  const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
   const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
   const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
@@ -833,19 +1053,32 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
       pending &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
-  if (JAC) {
-    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
-    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
-  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cost += __shfl_xor_sync(0xffffffffu, cost, o);
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
+  if (DENSE) {
+    cta_finish_dense<NT, 0, kWarpsPerCta>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
+    return;
+  }
+  if (JAC) {
+    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
+  }
   if (lane == 0) {
     rb.cost[2 * warp_global] = cost;
     rb.cost[2 * warp_global + 1] = fcost;
   }
+}
+template <bool JAC, bool PACKED>
+__global__ void __launch_bounds__(kThreads, 1)
+image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, ImageShared sh) {
+  if (pass_prologue(pp)) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  image_body<JAC, PACKED>(st, pp, total_slabs, rb, sh, W, rest, blockIdx.x, gridDim.x);
   pass_epilogue(pp);
 }
 
@@ -859,7 +1092,9 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
 // overwritten while it is still being read.  The wait is bounded (~1 s): a missing peer sets *err instead of hanging.
 constexpr int kP2PMaxRanks = 16;
 constexpr size_t kP2PMaxDoubles = 128 * 1024;  // per slot: D <= ~360
-constexpr size_t kP2PFlagBytes = 256;
+// flags: [kP2PMaxRanks] per-rank words of p2p_allreduce_kernel, then (offset 256) [kP2PMaxRanks][512] per-(rank, CTA) words
+// of the fused pass_kernel exchange (pass_fused.cuh)
+constexpr size_t kP2PFlagBytes = 128 * 1024;
 struct P2PView {
   char* peer[kP2PMaxRanks];  // exchange areas: [flags: kP2PMaxRanks x u64][slots: 2 x kP2PMaxRanks x kP2PMaxDoubles doubles]
   int n, rank;
@@ -870,8 +1105,12 @@ __host__ __device__ inline size_t p2p_area_bytes() {
 __device__ __forceinline__ double* p2p_slot(char* area, int parity, int src_rank) {
   return reinterpret_cast<double*>(area + kP2PFlagBytes) + ((size_t)parity * kP2PMaxRanks + src_rank) * kP2PMaxDoubles;
 }
+// The wait is bounded in wall-clock time (timeout_ns of %globaltimer, tens of seconds by default: a peer that is merely
+// slow — first-call module load, a large copy ahead of it — is not a missing peer).  On a timeout *err is set and dst
+// is ZEROED, never a partial sum.
 __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(const double* src, double* dst, int count, P2PView v,
-                                                             unsigned long long seq, int* err) {
+                                                             unsigned long long seq, unsigned long long timeout_ns,
+                                                             int* err) {
   pdl_wait();
   pdl_trigger();
   const int tid = threadIdx.x, parity = (int)(seq & 1ull);
@@ -880,25 +1119,30 @@ __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(const double* src, 
     for (int r = 0; r < v.n; r++) p2p_slot(v.peer[r], parity, v.rank)[i] = x;
   }
   __syncthreads();
+  bool timed_out = false;
   if (tid < v.n) {
     __threadfence_system();  // cumulative over the CTA's stores ordered before the barrier
     unsigned long long* remote = reinterpret_cast<unsigned long long*>(v.peer[tid]) + v.rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(seq) : "memory");
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(v.peer[v.rank]) + tid;
-    const long long t0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     unsigned long long got = 0;
     while (true) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
       if (got >= seq) break;
-      if (clock64() - t0 > (1ll << 31)) { *err = 1; break; }
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { timed_out = true; break; }
       __nanosleep(64);
     }
   }
-  __syncthreads();
+  const int any_timeout = __syncthreads_or(timed_out ? 1 : 0);
+  if (any_timeout && tid == 0) *err = 1;
   char* local = v.peer[v.rank];
   for (int i = tid; i < count; i += blockDim.x) {
     double acc = 0.0;
-    for (int r = 0; r < v.n; r++) acc += __ldcv(p2p_slot(local, parity, r) + i);
+    if (!any_timeout)
+      for (int r = 0; r < v.n; r++) acc += __ldcv(p2p_slot(local, parity, r) + i);
     dst[i] = acc;
   }
 }
@@ -916,7 +1160,7 @@ struct PoseQuery {
 };
 __device__ __forceinline__ bool sensor_pose(const WindowView& W, const PassParams& pp, const PoseQuery& q, double t_s,
                                             Q4* R_out, V3* p_out) {
-  const double tn = t_s * 1e9 + q.t_offset_ns;
+  const double tn = __dadd_rn(__dmul_rn(t_s, 1e9), q.t_offset_ns);  // product rounded first (trajectory.cpp:101), no FMA contraction
   if (!(tn >= q.t_min_ns && tn < q.t_max_ns)) return false;
   int s = 0;
   double u = 0.0;
@@ -1001,27 +1245,7 @@ __global__ void prep_image_kernel(int64_t n, const double* ti_s, const double* t
 }
 
 // ---------------- assembly of the dense normal equations ----------------
-// One descriptor per factor stream whose records were reduced to per-key blocks.
-struct StreamDesc {
-  const double* fin;     // [n_keys][rd] per-key blocks of reduce_all_kernel (atomics-fallback block folded in)
-  int n_keys, NT, rd;
-  int r_col;             // local column holding r~ (when b lives in the tiles)
-  int b_off;             // >= 0: b = J~^T r~ is stored as a plain vector at this offset of the record (LiDAR)
-  int n_extra;           // local columns extra_base .. extra_base+n_extra-1 map to extra_global[] (-1: constant)
-  int extra_base;        // 24 (one knot window) or 48 (two windows)
-  int kind;              // 0: key = interval s (LiDAR / IMU);  1: key = s_i * kdim + s_j (visual, two knot windows)
-  int kdim;
-  int extra_global[12];
-  unsigned char perm[64]; // logical local column -> physical column inside the record tiles
-};
-
-struct ColMaps {
-  int D, K;
-  const int* knot_col;   // [K] column of knot's dtheta (dp = +3), -1 if constant
-  const int* col_knot;   // [D] knot of a column (-1: not a knot column)
-  const int* col_sub;    // [D] 0..5 within the knot
-};
-
+// (StreamDesc / ColMaps: defined near the top of this file)
 __device__ __forceinline__ double block_entry(const double* blk, int NT, int la, int lb) {
   int ta = la >> 3, tb = lb >> 3;  // la, lb: PHYSICAL columns
   if (ta > tb) { int t = ta; ta = tb; tb = t; t = la; la = lb; lb = t; }
@@ -1039,29 +1263,30 @@ struct BiasFactorDesc {
 // so the sum order never changes between runs.
 // bias (n_bias > 0, solve path): the BiasFactor terms (+-I Jacobians) are added by the owner of each entry, and the
 // first warp adds their cost — one launch less per pass than bias_factor_kernel.
-__global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
-                                                       int n_desc, const int* ctl, const BiasFactorDesc* bias = nullptr,
-                                                       int n_bias = 0, const double* state = nullptr,
-                                                       int off_bias = 0, double* cost2 = nullptr,
-                                                       const double* rho_side = nullptr, int rho0 = 0, int n_rho = 0) {
-  pdl_wait();
-  pdl_trigger();
-  if (ctl && ctl[0]) return;
+// Entry `wid` of the packed system [upper triangle of H, row-major | b]: its value on lane 0 of the calling warp (all 32
+// lanes must call); *gi_out, *gj_out = its row / column (gj = -1 for an entry of b); *bias_cost_out = cost of the
+// BiasFactors (same on every entry).
+__device__ __forceinline__ double assemble_entry(int wid, int lane, const ColMaps& cm, const StreamDesc* descs, int n_desc,
+                                                 const BiasFactorDesc* bias, int n_bias, const double* state, int off_bias,
+                                                 const double* rho_side, int rho0, int n_rho, int* gi_out, int* gj_out,
+                                                 double* bias_cost_out, bool* bias_free_out) {
   const int D = cm.D;
   const int n_upper = D * (D + 1) / 2;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= n_upper + D) return;
   int gi, gj;
   const bool is_b = wid >= n_upper;
   if (is_b) {
     gi = wid - n_upper;
     gj = -1;
-  } else {  // unrank (gi <= gj) from the row-major upper-triangular index
-    int rem = wid;
-    gi = 0;
-    while (rem >= D - gi) { rem -= D - gi; gi++; }
-    gj = gi + rem;
+  } else {  // unrank (gi <= gj) from the row-major upper-triangular index: rows before gi hold gi*D - gi(gi-1)/2 entries
+    const double q = 2.0 * D + 1.0;
+    gi = (int)((q - sqrt(q * q - 8.0 * (double)wid)) * 0.5);
+    gi = max(0, min(D - 1, gi));
+    while (gi > 0 && gi * D - gi * (gi - 1) / 2 > wid) gi--;
+    while ((gi + 1) * D - (gi + 1) * gi / 2 <= wid) gi++;
+    gj = gi + (wid - (gi * D - gi * (gi - 1) / 2));
   }
+  *gi_out = gi;
+  *gj_out = gj;
   const int ki = cm.col_knot[gi], ci = cm.col_sub[gi];
   const int kj = is_b ? -1 : cm.col_knot[gj], cj = is_b ? 0 : cm.col_sub[gj];
   double acc = 0.0;
@@ -1155,8 +1380,31 @@ __global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, Col
       }
       bias_cost += 0.5 * tot;
     }
+    *bias_cost_out = bias_cost;
+    *bias_free_out = bias_free;
+  }
+  return acc;
+}
+__global__ void __launch_bounds__(256) assemble_kernel(double* H, double* b, ColMaps cm, const StreamDesc* descs,
+                                                       int n_desc, const int* ctl, const BiasFactorDesc* bias = nullptr,
+                                                       int n_bias = 0, const double* state = nullptr,
+                                                       int off_bias = 0, double* cost2 = nullptr,
+                                                       const double* rho_side = nullptr, int rho0 = 0, int n_rho = 0) {
+  pdl_wait();
+  pdl_trigger();
+  if (ctl && ctl[0]) return;
+  const int D = cm.D;
+  const int n_upper = D * (D + 1) / 2;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_upper + D) return;
+  int gi, gj;
+  double bias_cost = 0.0;
+  bool bias_free = false;
+  const double acc = assemble_entry(wid, lane, cm, descs, n_desc, bias, n_bias, state, off_bias, rho_side, rho0, n_rho,
+                                    &gi, &gj, &bias_cost, &bias_free);
+  if (lane == 0) {
     if (wid == 0 && n_bias > 0) cost2[bias_free ? 0 : 1] += bias_cost;
-    if (is_b) {
+    if (gj < 0) {
       b[gi] = acc;
     } else {
       H[(size_t)gi * D + gj] = acc;

@@ -353,6 +353,23 @@ class TrajectoryEstimator:
         _check(self.lib, self.lib.clic_profile_read(self.h, dptr(ms), cnt.ctypes.data_as(_abi.c_int64_p)))
         return ms, cnt
 
+    def pass_info(self):
+        """How the pass executes: dict(fused, grid, part_ctas[6]) — see clic_pass_info."""
+        fused, grid = C.c_int32(0), C.c_int32(0)
+        part = (C.c_int32 * 6)()
+        _check(self.lib, self.lib.clic_pass_info(self.h, C.byref(fused), C.byref(grid), part))
+        return dict(fused=bool(fused.value), grid=grid.value, part_ctas=list(part))
+
+    def pass_stamps(self, enable=True):
+        """Per-CTA %globaltimer stamps (ns) of the last fused pass recorded while enabled: (grid, 8) uint64 array
+        [start, end of factor phase, after the grid barrier, after key staging, end of assembly, end, -, -], or None;
+        then sets the switch."""
+        n = C.c_int32(0)
+        buf = np.zeros((1024, 8), np.uint64)
+        _check(self.lib, self.lib.clic_pass_stamps(self.h, int(bool(enable)), buf.size,
+                                                   buf.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(n)))
+        return buf[:n.value].copy() if n.value > 0 and buf[:n.value].any() else None
+
     def num_kernel_launches(self):
         n = C.c_int64(0)
         _check(self.lib, self.lib.clic_num_kernel_launches(self.h, C.byref(n)))

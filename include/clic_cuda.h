@@ -362,6 +362,18 @@ CLIC_API int clic_comm_p2p_import(clic_estimator* h, int32_t n_ranks, int32_t ra
 CLIC_API int clic_comm_p2p_ready(void);
 CLIC_API int clic_comm_p2p_disable(void); /* back to ncclAllReduce (must be called on every rank) */
 
+/* How the pass of the factors added so far executes.  *fused = 1: ONE persistent launch (clic_b200/csrc/pass_fused.cuh:
+ * every factor stream on its own partition of the grid, then the record reduction, the assembly and — on several ranks
+ * with mapped peer memory — the exchange of H | b | cost inside the same kernel); *grid = its CTAs, part_ctas[k] = CTAs
+ * of stream kind k (0 LiDAR mixed, 1 LiDAR planes, 2 LiDAR lines, 3 IMU, 4 visual with pose packs, 5 visual per-factor
+ * chain).  *fused = 0: one kernel per stream + reduction + assembly (+ all-reduce), e.g. two batches of one kind. */
+CLIC_API int clic_pass_info(clic_estimator* h, int32_t* fused, int32_t* grid, int32_t part_ctas[6]);
+/* Per-CTA %globaltimer stamps (ns) of the LAST fused pass: stamps[8*cta + {0..5}] = start, end of the factor phase,
+ * after the grid barrier, after staging the slot keys, end of the assembly, end (after the exchange).  Reads what the
+ * previous passes recorded (if enabled then), then sets the switch.
+ * Measurement aid for the partition's cost model and bench.py's per-stream times. */
+CLIC_API int clic_pass_stamps(clic_estimator* h, int32_t enable, int64_t capacity, uint64_t* stamps, int32_t* n_ctas);
+
 CLIC_API int clic_linearize_async(clic_estimator* h, int32_t reps);
 CLIC_API int clic_synchronize(clic_estimator* h);
 CLIC_API int clic_num_kernel_launches(clic_estimator* h, int64_t* launches);

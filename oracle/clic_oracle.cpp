@@ -1811,6 +1811,16 @@ CLIC_API int clic_num_kernel_launches(clic_estimator*, int64_t* l) {
   if (l) *l = 0;
   return CLIC_OK;
 }
+CLIC_API int clic_pass_info(clic_estimator*, int32_t* fused, int32_t* grid, int32_t part_ctas[6]) {
+  if (fused) *fused = 0;
+  if (grid) *grid = 0;
+  if (part_ctas) for (int k = 0; k < 6; k++) part_ctas[k] = 0;
+  return CLIC_OK;
+}
+CLIC_API int clic_pass_stamps(clic_estimator*, int32_t, int64_t, uint64_t*, int32_t* n_ctas) {
+  if (n_ctas) *n_ctas = 0;
+  return CLIC_OK;
+}
 CLIC_API int clic_profile_enable(clic_estimator*, int32_t) { return CLIC_OK; }
 CLIC_API int clic_profile_read(clic_estimator*, double* ms, int64_t* n) {
   for (int i = 0; i < 8; i++) {

@@ -1,0 +1,133 @@
+"""The fused pass (clic_b200/csrc/pass_fused.cuh: every factor stream, the record reduction, the assembly — and on
+several GPUs the exchange — in one persistent launch) against the per-stream kernels of the same library
+(CLIC_FUSED=0) and, through the other GPU test files, against the oracle (the fused pass is the default path).
+The two paths partition the factors over warps differently, so they agree to rounding, not bitwise."""
+import os
+
+import numpy as np
+import pytest
+
+from clic_b200 import estimator as E
+from clic_b200 import synthetic as S
+from test_gpu_parity import build, rel, rel_scaled
+
+pytestmark = pytest.mark.gpu
+
+
+class per_stream_kernels:
+    """Estimators whose layout is built inside this block run one kernel per stream (round-1 path)."""
+
+    def __enter__(self):
+        self.prev = os.environ.get("CLIC_FUSED")
+        os.environ["CLIC_FUSED"] = "0"
+
+    def __exit__(self, *a):
+        if self.prev is None:
+            os.environ.pop("CLIC_FUSED", None)
+        else:
+            os.environ["CLIC_FUSED"] = self.prev
+
+
+def both_paths(cuda, sw, solve_iters=None, **kw):
+    est, _ = build(cuda, sw, **kw)
+    info = est.pass_info()
+    assert info["fused"], info
+    assert sum(info["part_ctas"]) <= info["grid"] <= 148 * 2
+    out_f = est.Evaluate()
+    sol_f = (est.Solve(solve_iters), est.read_state()) if solve_iters is not None else None
+    est.close()
+    with per_stream_kernels():
+        est, _ = build(cuda, sw, **kw)
+        assert not est.pass_info()["fused"]
+        out_s = est.Evaluate()
+        sol_s = (est.Solve(solve_iters), est.read_state()) if solve_iters is not None else None
+        est.close()
+    Hf, bf, cf, ff = out_f
+    Hs, bs, cs, fs = out_s
+    assert rel(Hf, Hs) < 1e-12 and rel_scaled(Hf, Hs) < 1e-11, (rel(Hf, Hs), rel_scaled(Hf, Hs))
+    assert rel(bf, bs) < 1e-11, rel(bf, bs)
+    assert abs(cf - cs) <= 1e-12 * abs(cs) and abs(ff - fs) <= 1e-12 * max(abs(fs), 1.0)
+    assert np.array_equal(Hf, Hf.T)
+    if solve_iters is not None:
+        (sf, xf), (ss, xs) = sol_f, sol_s
+        for k in ("iterations", "num_successful_steps", "num_unsuccessful_steps", "termination", "termination_reason"):
+            assert sf[k] == ss[k], (k, sf, ss)
+        assert np.abs(xf["knot_p"] - xs["knot_p"]).max() < 1e-9
+        assert np.abs(xf["knot_q"] - xs["knot_q"]).max() < 1e-9
+    return info
+
+
+def test_c1_fused_equals_per_stream(cuda):
+    both_paths(cuda, S.config(1), solve_iters=8, bias_factor=False)
+
+
+def test_c3_all_streams_bias_and_fixed_knots(cuda):
+    info = both_paths(cuda, S.config(3, 0.1), solve_iters=6, fixed=2, unlock_bias=True)
+    p = info["part_ctas"]
+    assert p[1] > 0 or p[0] > 0  # a LiDAR partition
+    assert p[3] > 0 and p[4] > 0  # IMU and visual (pose packs) partitions
+
+
+def test_c2_time_offset_bounded_line_search(cuda):
+    """Residual-only passes (JAC = false instantiation) of the bounded problem's line search."""
+    both_paths(cuda, S.config(2, 0.1), solve_iters=6, unlock_bias=True, unlock_toff=True)
+
+
+def test_free_inverse_depths(cuda):
+    sw = S.config(3, 0.05)
+    est, _ = build(cuda, sw, unlock_bias=True, fixed_depth=False)
+    assert est.pass_info()["fused"]
+    Hf, bf, cf, _ = est.Evaluate()
+    est.close()
+    with per_stream_kernels():
+        est, _ = build(cuda, sw, unlock_bias=True, fixed_depth=False)
+        Hs, bs, cs, _ = est.Evaluate()
+        est.close()
+    assert rel_scaled(Hf, Hs) < 1e-10 and rel(bf, bs) < 1e-10 and abs(cf - cs) <= 1e-12 * abs(cs)
+
+
+def test_tiny_and_ragged_windows(cuda):
+    for n_l, n_i, seed in ((1, 0, 3), (33, 7, 4), (0, 40, 5), (700, 130, 6)):
+        sw = S.make_window(10, n_lidar=n_l, n_imu=n_i, line_fraction=0.4, seed=seed)
+        both_paths(cuda, sw, unlock_bias=n_i > 0)
+
+
+def test_fused_pass_is_deterministic(cuda):
+    sw = S.config(3, 0.1)
+    runs = []
+    for _ in range(3):
+        est, _ = build(cuda, sw, unlock_bias=True)
+        runs.append(est.Evaluate())
+        est.close()
+    for H, b, c, f in runs[1:]:
+        assert np.array_equal(H, runs[0][0]) and np.array_equal(b, runs[0][1]) and c == runs[0][2] and f == runs[0][3]
+
+
+def test_two_batches_of_one_kind_fall_back(cuda, oracle):
+    """More than one batch per stream kind is not fused; both layouts give the same system."""
+    sw = S.config(1)
+    opt = E.default_options(cuda)
+    est = E.TrajectoryEstimator(sw.window, opt, cuda)
+    est.SetFixedIndex(-1)
+    S.add_all_factors(est, sw, bias_factor=False)
+    S.add_all_factors(est, sw, bias_factor=False)  # the same measurements twice: every sum doubles
+    assert not est.pass_info()["fused"]
+    H2, b2, c2, _ = est.Evaluate()
+    est.close()
+    est, _ = build(cuda, sw, bias_factor=False)
+    H1, b1, c1, _ = est.Evaluate()
+    est.close()
+    assert rel(H2, 2 * H1) < 1e-12 and rel(b2, 2 * b1) < 1e-11 and abs(c2 - 2 * c1) < 1e-12 * abs(c1)
+
+
+def test_stamps_cover_every_partition(cuda):
+    sw = S.config(3, 0.1)
+    est, _ = build(cuda, sw, unlock_bias=True)
+    info = est.pass_info()
+    est.pass_stamps(True)
+    est.Evaluate()
+    st = est.pass_stamps(False)
+    est.close()
+    assert st is not None and st.shape == (info["grid"], 8)
+    assert (st[:, 1] >= st[:, 0]).all() and (st[:, 2] >= st[:, 1]).all() and (st[:, 5] >= st[:, 4]).all()
+    assert (st[:, 4] >= st[:, 2]).all()
