@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--shard", type=int, default=1, help="time rank 0's shard of an N-way split (no exchange)")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (code and data)")
     args = ap.parse_args()
     lib = E.cuda_library()
     stream = torch.cuda.Stream()
@@ -48,7 +49,8 @@ def main():
             torch.cuda.synchronize()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
             for a, b in ev:
-                flush.fill_(1)
+                if not args.no_flush:
+                    flush.fill_(1)
                 a.record(stream)
                 est.linearize_async(1)
                 b.record(stream)
@@ -58,7 +60,8 @@ def main():
                   f"min {ms.min():.4f} median {np.median(ms):.4f} max {ms.max():.4f}  n_factors {sw.n_factors}")
             if info["fused"]:
                 est.pass_stamps(True)
-                flush.fill_(1)
+                if not args.no_flush:
+                    flush.fill_(1)
                 est.linearize_async(1)
                 torch.cuda.synchronize()
                 st = est.pass_stamps(False).astype(np.int64)
@@ -81,6 +84,17 @@ def main():
                       "barrier wait of the last CTA %.2f us" % (
                           (us[:-1, 4] - us[:-1, 3]).mean(), (us[:-1, 4] - us[:-1, 3]).max(),
                           (us[:-1, 3] - us[:-1, 2]).mean(), us[:, 2].max() - us[:, 1].max()))
+            if not info["fused"]:
+                est.profile_enable(True)
+                for _ in range(args.steps):
+                    if not args.no_flush:
+                        flush.fill_(1)
+                    est.linearize_async(1)
+                torch.cuda.synchronize()
+                pm, pn = est.profile_read()
+                est.profile_enable(False)
+                print("  per-class event spans (us/step): lidar %.1f imu %.1f visual %.1f reduce+assemble %.1f" % tuple(
+                    1e3 * pm[i] / args.steps for i in range(4)))
         H, b, c, f = est.Evaluate()
         est.close()
         return H, b, c

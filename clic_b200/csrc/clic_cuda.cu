@@ -332,6 +332,7 @@ struct clic_estimator {
   size_t off_b() const { return (size_t)std::max(1, L.D) * std::max(1, L.D); }
   size_t off_cost() const { return off_b() + std::max(1, L.D); }
   DevBuf d_knot_col, d_col_knot, d_col_sub, d_descs;
+  std::vector<StreamDesc> h_descs;  // host copy of d_descs
   DevBuf d_lm;  // LM workspace (solver.cuh)
   std::vector<std::unique_ptr<LoamBatch>> loam;
   std::vector<std::unique_ptr<ImuBatch>> imu;
@@ -367,7 +368,8 @@ struct clic_estimator {
     LoamBatch* lb[3] = {nullptr, nullptr, nullptr};
     ImuBatch* ib = nullptr;
     ImageBatch* gb = nullptr;
-    DevBuf d_bar, d_stamps, d_addend, d_hloc, d_descs_ovf;
+    DevBuf d_bar, d_stamps, d_addend, d_hloc, d_descs_ovf, arena;
+    std::vector<StreamDesc> h_descs_ovf;
     bool stamps_on = false;
   } fused;
   bool bounds_toff[3] = {false, false, false};
@@ -520,7 +522,7 @@ bool fused_enabled() { const char* e = getenv("CLIC_FUSED"); return !(e && e[0] 
 // CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.7, 3.25, 3.5, 13.0, 9.0, 12.0}, {6.0, 6.0, 5.0, 26.0, 20.0, 30.0}};
+  static FusedModel m = {{3.7, 3.2, 3.5, 13.0, 8.4, 12.0}, {14.0, 10.8, 17.5, 31.0, 41.6, 50.0}};
   static bool init = false;
   if (!init) {
     init = true;
@@ -690,22 +692,30 @@ int build_fused(clic_estimator* E) {
   CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, E->device));
   if (smem > (size_t)max_optin) return CLIC_OK;  // a system too wide for a per-CTA copy (C4, D = 240): per-stream kernels
   F.smem = smem;
-  CU(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<true>, kThreads, smem));
-  if (occ < 1 || F.grid > occ * E->n_sm) return CLIC_OK;  // the grid barrier needs every CTA resident
-  CU(F.d_stamps.ensure((size_t)E->n_sm * 8 * sizeof(unsigned long long)));
-  CU(F.d_addend.ensure(((size_t)D * D + D + 2) * sizeof(double)));
-  CU(F.d_hloc.ensure((size_t)cta0 * n_tot * sizeof(double)));
+  {  // an estimator is built per solve: the attribute / occupancy queries are cached per device and size
+    static std::mutex mu;
+    static size_t set_smem[16] = {};
+    static int occ_of[16] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    const int dv = E->device & 15;
+    if (smem > set_smem[dv]) {
+      CU(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_smem[dv] = smem;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_of[dv], pass_kernel<true>, kThreads, smem));
+    }
+    if (occ_of[dv] < 1 || F.grid > occ_of[dv] * E->n_sm) return CLIC_OK;  // the grid barrier needs every CTA resident
+  }
+  // one allocation behind the kernel's scratch buffers
+  CU(carve(F.arena, {{&F.d_stamps, (size_t)E->n_sm * 8 * sizeof(unsigned long long)},
+                     {&F.d_addend, ((size_t)D * D + D + 2) * sizeof(double)},
+                     {&F.d_hloc, (size_t)cta0 * n_tot * sizeof(double)},
+                     {&F.d_descs_ovf, (size_t)kMaxFusedJobs * sizeof(StreamDesc)}}));
   {  // descriptors of the atomics-fallback blocks: the per-interval block layout of the per-stream path
-    std::vector<StreamDesc> dv(E->n_desc);
-    CU(cudaMemcpyAsync(dv.data(), E->d_descs.p, dv.size() * sizeof(StreamDesc), cudaMemcpyDeviceToHost, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
-    for (int j = 0; j < jn; j++) dv[j].fin = fa.ovf_blocks[j];
-    CU(F.d_descs_ovf.ensure(dv.size() * sizeof(StreamDesc)));
-    CU(cudaMemcpyAsync(F.d_descs_ovf.p, dv.data(), dv.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
+    F.h_descs_ovf = E->h_descs;  // (member: the asynchronous copy below reads it after this function returns)
+    for (int j = 0; j < jn; j++) F.h_descs_ovf[j].fin = fa.ovf_blocks[j];
+    CU(cudaMemcpyAsync(F.d_descs_ovf.p, F.h_descs_ovf.data(), F.h_descs_ovf.size() * sizeof(StreamDesc),
+                       cudaMemcpyHostToDevice, E->stream));
   }
   fa.hloc = F.d_hloc.as<double>();
   fa.cm.D = D;
@@ -811,6 +821,7 @@ int ensure_layout(clic_estimator* E) {
     descs.push_back(d);
   }
   E->n_desc = (int)descs.size();
+  E->h_descs = descs;
   CU(E->d_descs.ensure(std::max<size_t>(1, descs.size()) * sizeof(StreamDesc)));
   if (!descs.empty())
     CU(cudaMemcpyAsync(E->d_descs.p, descs.data(), descs.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, E->stream));

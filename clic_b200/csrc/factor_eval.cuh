@@ -62,7 +62,7 @@ CLIC_HD V3 ldv(const double* p) { return mk(p[0], p[1], p[2]); }
 CLIC_HD Q4 step_exp_neg(const PairData& P, double lam, double* ca, double* cb) {
   double th = lam * P.theta;
   double s, c;
-  sincos_hd(0.5 * th, &s, &c);
+  sincos_half_pi(0.5 * th, &s, &c);  // |th / 2| <= pi / 2: lam in [0, 1], theta <= pi
   *ca = (2.0 * s * s) * P.inv_theta;
   *cb = lam - (2.0 * s * c) * P.inv_theta;
   Q4 e; e.x = -s * P.nhat[0]; e.y = -s * P.nhat[1]; e.z = -s * P.nhat[2]; e.w = c;

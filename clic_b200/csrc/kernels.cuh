@@ -283,7 +283,7 @@ __device__ __forceinline__ void build_key_cols(const StreamDesc& sd, const int* 
 // rec (shared or global memory): one record of this stream (tiles [+ b vector]); adds it into dn.Hs.  All threads of the
 // CTA call; two block barriers inside.
 template <int NTHREADS>
-__device__ __forceinline__ void dense_scatter_record(const DenseOut& dn, const double* rec, int key) {
+__device__ __noinline__ void dense_scatter_record(const DenseOut& dn, const double* rec, int key) {
   const StreamDesc& sd = *dn.sd;
   __syncthreads();  // key_cols of the previous record are no longer read; rec is complete
   if (threadIdx.x < 32) build_key_cols(sd, dn.knot_col, key, dn.key_cols, threadIdx.x);
@@ -374,11 +374,28 @@ __device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, 
     }
     dense_scatter_record<WARPS * 32>(dn, scratch + (size_t)w0 * RD, kc);
   }
-  // records flushed in mid-run (a warp whose interval changed): read back from this CTA's own slots, in (warp, slot) order
+  // records flushed in mid-run (a warp whose interval changed): read back from this CTA's own slots, in (warp, slot)
+  // order, through the (now free) parking area — every load of a record in flight at once; scattering straight from
+  // global memory would pay an L2 round trip per term (in-order issue)
   for (int w = 0; w < WARPS; w++)
     for (int sl = 0; sl < min(s_slot[w], kSlotsPerWarp); sl++) {
       const int r = (warp_global - warp + w) * kSlotsPerWarp + sl;
-      dense_scatter_record<WARPS * 32>(dn, rb.payload + (size_t)r * RD, rb.key[r]);
+      const double* src = rb.payload + (size_t)r * RD;
+      constexpr int PER = (RD + WARPS * 32 - 1) / (WARPS * 32);
+      double v[PER];
+      __syncthreads();  // the previous scatter no longer reads the staging area
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const int e = q * WARPS * 32 + threadIdx.x;
+        v[q] = e < RD ? src[e] : 0.0;
+      }
+      const int key = rb.key[r];
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const int e = q * WARPS * 32 + threadIdx.x;
+        if (e < RD) scratch[e] = v[q];
+      }
+      dense_scatter_record<WARPS * 32>(dn, scratch, key);
     }
   __syncthreads();
 }

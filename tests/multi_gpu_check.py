@@ -40,6 +40,9 @@ def main():
 
     est = build(lib, mine, bias_factor=(rank == 0), device=local)   # the single bias factor lives on rank 0
     est.comm_init_torch(dist, rank, world)
+    if rank == 0:
+        print("pass: fused=%s exchange=%s" % (est.pass_info()["fused"],
+                                               "kernel" if lib.clic_comm_p2p_ready() else "nccl"))
     H, b, cost, _ = est.Evaluate()
     summary = est.Solve(8)
     x = est.read_state()
