@@ -522,7 +522,7 @@ bool fused_enabled() { const char* e = getenv("CLIC_FUSED"); return !(e && e[0] 
 // CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.7, 3.2, 3.5, 13.0, 8.4, 12.0}, {14.0, 10.8, 17.5, 31.0, 41.6, 50.0}};
+  static FusedModel m = {{3.7, 3.2, 3.5, 13.8, 9.6, 12.0}, {14.0, 10.8, 17.5, 31.0, 41.6, 50.0}};
   static bool init = false;
   if (!init) {
     init = true;
@@ -1022,7 +1022,9 @@ int run_pass_fused(clic_estimator* E, const double* state, bool jac, double* Hp,
   out.cost2 = cost2;
   out.addend = addend;
   const size_t n_tot = jac ? (size_t)D * (D + 1) / 2 + D + 2 : 2;
-  const bool exchange = E->use_comm && g_p2p.ready && n_tot <= kP2PMaxDoubles && F.grid <= kP2PMaxCtas;
+  // in-kernel exchange: two 8-byte words per double in the peer slots, one thread per value of a CTA's chunk
+  const size_t chunk = (n_tot + F.grid - 1) / F.grid;
+  const bool exchange = E->use_comm && g_p2p.ready && 2 * n_tot <= kP2PMaxDoubles && chunk <= (size_t)kThreads;
   if (exchange) {
     double* G = E->nrm_glb_set(set);
     out.Hg = G;

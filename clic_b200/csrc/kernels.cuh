@@ -816,7 +816,10 @@ struct ImuRowSink {
   WarpAcc<NT>* acc;
   __device__ __forceinline__ void put(int row, int col, double v) {
     const int pc = imu_phys_col<MARG>(col);
-    if (row < 3 && pc >= 24) return;  // never read for gyro rows
+    if (pc >= 24) {  // never read for gyro rows (row is a run-time value inside the evaluator's row loop)
+      if (row >= 3) Jt[pc * kJtStride + lane] = on ? v : 0.0;
+      return;
+    }
     Jt[pc * kJtStride + lane] = on ? v : 0.0;
   }
   __device__ __forceinline__ void row_done(int row) {

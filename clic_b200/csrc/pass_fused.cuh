@@ -384,34 +384,43 @@ pass_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ PassPa
     }
   }
   if (out.exchange && my_n > 0) {
+    // Low-latency exchange: every double travels as two 8-byte words (32 data bits | 32-bit sequence number), so the
+    // data is its own arrival flag — no system-scope fence and no separate flag round trip (an 8-byte store is
+    // single-copy atomic over NVLink).  CTA c pushes its chunk into slot `rank` of every peer, then polls slot r of its
+    // own area for every rank r's chunk c and sums in rank order: same bits on every rank.  Slots are double-buffered by
+    // the parity of the sequence number (a rank can be at most one exchange ahead of its slowest peer).
     const int parity = (int)(out.seq & 1ull);
-    // push my chunk into slot `rank` of every peer (posted NVLink stores), then release the per-CTA flag
+    const unsigned long long tag = (out.seq & 0xffffffffull) << 32;
     for (int i = threadIdx.x; i < my_n * pv.n; i += blockDim.x) {
       const int r = i / my_n, k = i - r * my_n;
-      p2p_slot(pv.peer[r], parity, pv.rank)[e0 + k] = stage[k];
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(stage[k]);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(p2p_slot(pv.peer[r], parity, pv.rank)) + 2 * (e0 + k);
+      const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+      asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
     }
-    __syncthreads();
     bool timed_out = false;
-    if ((int)threadIdx.x < pv.n) {
-      __threadfence_system();  // cumulative over the CTA's stores ordered before the barrier
-      unsigned long long* remote = p2p_cta_flag(pv.peer[threadIdx.x], pv.rank, cta);
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(out.seq) : "memory");
-      const unsigned long long* mine = p2p_cta_flag(pv.peer[pv.rank], threadIdx.x, cta);
+    double acc = 0.0;
+    if ((int)threadIdx.x < my_n) {
+      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(p2p_slot(pv.peer[pv.rank], parity, 0)) +
+                                       2 * (e0 + threadIdx.x);
       const unsigned long long t0 = globaltimer_ns();
-      unsigned long long got = 0;
-      while (true) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
-        if (got >= out.seq) break;
-        if (globaltimer_ns() - t0 > out.timeout_ns) { timed_out = true; break; }
+      for (int r = 0; r < pv.n; r++) {
+        const unsigned long long* src = base + (size_t)r * kP2PMaxDoubles;  // slot r of my own area
+        unsigned long long w0, w1;
+        while (true) {
+          asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+          if ((w0 >> 32) == (tag >> 32) && (w1 >> 32) == (tag >> 32)) break;
+          if (globaltimer_ns() - t0 > out.timeout_ns) { timed_out = true; break; }
+        }
+        if (timed_out) break;
+        acc += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
       }
     }
     const int any_timeout = __syncthreads_or(timed_out ? 1 : 0);
     if (any_timeout && threadIdx.x == 0) *out.err = 1;
-    char* local = pv.peer[pv.rank];
-    for (int i = threadIdx.x; i < my_n; i += blockDim.x) {
-      double acc = 0.0;
-      if (!any_timeout)  // a missing peer: the result is zeroed (never a partial sum) and the error word is set
-        for (int r = 0; r < pv.n; r++) acc += __ldcv(p2p_slot(local, parity, r) + e0 + i);
+    if ((int)threadIdx.x < my_n) {
+      if (any_timeout) acc = 0.0;  // a missing peer: the result is zeroed (never a partial sum) and the error word is set
+      const int i = threadIdx.x;
       const int gi = st_g[2 * i], gj = st_g[2 * i + 1];
       if (gj >= 0) {
         out.Hg[(size_t)gi * D + gj] = acc;
