@@ -54,7 +54,9 @@ class Options(C.Structure):
         ("device", C.c_int32),
         ("stream", C.c_void_p),
         ("deterministic", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("reserved0", C.c_int32),
+        ("image_sqrt_info", C.c_double),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -123,6 +125,7 @@ PROTOTYPES = {
     "clic_add_imu": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                c_int64_p]),
     "clic_add_bias": (C.c_int, [H, C.c_int32, C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int32]),
+    "clic_add_gravity": (C.c_int, [H, c_double_p, c_double_p, C.c_int32]),
     "clic_add_global_velocity": (C.c_int, [H, C.c_double, c_double_p, C.c_double, c_int32_p]),
     "clic_add_image": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.c_int32,
                                  C.c_int32, c_int64_p]),

@@ -339,6 +339,20 @@ struct clic_estimator {
   std::vector<VelFactorDesc> vel_factors;  // AddGlobalVelocityMeasurement (one per init solve in the reference)
   std::vector<std::unique_ptr<ImageBatch>> image;
   std::vector<BiasFac> bias_f;
+  struct GravFac { double g0[3], sqrt_info[3]; int marg; };
+  std::vector<GravFac> grav_f;  // AddGravityFactor
+  // GravityFactors of the solve problem: gravity is a constant block there, so their cost is a constant of the problem
+  double grav_fixed_cost() const {
+    double c = 0.0;
+    for (auto& f : grav_f) {
+      if (f.marg) continue;
+      for (int i = 0; i < 3; i++) {
+        const double r = f.sqrt_info[i] * (h_state[sl.off_grav() + i] - f.g0[i]);
+        c += 0.5 * r * r;
+      }
+    }
+    return c;
+  }
   struct PriorRef {
     const clic_prior* p;
     std::vector<int> drop;
@@ -935,7 +949,7 @@ ImageShared image_shared(const clic_estimator* E, const ImageBatch* b) {
   ImageShared ish;
   ish.S_CtoI = ldq(E->S_CtoI);
   ish.p_CinI = ldv(E->p_CinI);
-  ish.sqrt_info = 450.0 / 1.5;
+  ish.sqrt_info = E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450.0 / 1.5;
   ish.loss_a = b->st.loss_a;
   ish.inv_dt = 1e9 / double(E->dt_ns);
   ish.want_toff = E->L.col_t_offset[CLIC_SENSOR_CAMERA] >= 0;
@@ -1426,9 +1440,10 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
     summary->termination_reason = st.reason;
     summary->num_jacobian_evals = st.n_jac;
     summary->num_residual_evals = st.n_res;
-    summary->initial_cost = st.initial_cost;
-    summary->final_cost = st.x_cost + st.fixed_cost;
-    summary->fixed_cost = st.fixed_cost;
+    const double gfc = E->grav_fixed_cost();  // GravityFactors on the constant gravity block
+    summary->initial_cost = st.initial_cost + gfc;
+    summary->final_cost = st.x_cost + st.fixed_cost + gfc;
+    summary->fixed_cost = st.fixed_cost + gfc;
     summary->final_radius = st.radius;
     summary->final_gradient_max_norm = st.gmax;
   }
@@ -1519,7 +1534,7 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
     ImageShared ish;
     ish.S_CtoI = ldq(E->S_CtoI);
     ish.p_CinI = ldv(E->p_CinI);
-    ish.sqrt_info = 450.0 / 1.5;
+    ish.sqrt_info = E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450.0 / 1.5;
     ish.loss_a = b.st.loss_a;
     ish.inv_dt = 1e9 / double(E->dt_ns);
     ish.want_toff = true;  // the marginalization evaluates every Jacobian block
@@ -1570,7 +1585,11 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   struct Blk { int kind, id, size, used, drop, idx; };
   std::vector<Blk> blocks;
   std::vector<char> knot_drop(K, 0);
-  bool grav_used = any_imu, grav_drop = any_imu && E->opt.marg_gravity_param;
+  bool any_grav_f = false;
+  for (auto& gf : E->grav_f) any_grav_f = any_grav_f || gf.marg;
+  // an IMU factor or a GravityFactor of the marginalization set brings the gravity block in; dropped iff marg_gravity_param
+  // (trajectory_estimator.cpp:434-440, 515-519)
+  bool grav_used = any_imu || any_grav_f, grav_drop = (any_imu || any_grav_f) && E->opt.marg_gravity_param;
   bool toff_used[3] = {any_imu, false, any_image};
   bool toff_drop[3] = {any_imu && E->opt.marg_t_offset_param != 0, false, any_image && E->opt.marg_t_offset_param != 0};
   for (auto& pr : E->priors) {
@@ -1715,6 +1734,14 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
                                                 d_cost.as<double>(), 1, nullptr);
     E->launches++;
   }
+  for (auto& gf : E->grav_f) {
+    if (!gf.marg) continue;
+    const int col = find(CLIC_BLOCK_GRAVITY, 0);
+    gravity_factor_kernel<<<1, 32, 0, E->stream>>>(gf.g0[0], gf.g0[1], gf.g0[2], gf.sqrt_info[0], gf.sqrt_info[1],
+                                                   gf.sqrt_info[2], E->d_state.as<double>() + E->sl.off_grav(), col,
+                                                   d_A.as<double>(), d_b.as<double>(), pos, d_cost.as<double>());
+    E->launches++;
+  }
   for (auto& pr : E->priors) {
     const int nb = (int)pr->p->blocks.size();
     for (int i = 0; i < nb; i++) {
@@ -1805,6 +1832,7 @@ CLIC_API void clic_default_options(clic_options* o) {
   o->t_offset_padding_ns = (int64_t)1e7;
   o->marg_bias_param = o->marg_gravity_param = o->marg_t_offset_param = 1;
   o->deterministic = 1;
+  o->image_sqrt_info = 450.0 / 1.5;  // ImageFeatureFactor's class default (image_feature_factor.h:277-278)
 }
 
 CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, clic_estimator** out) {
@@ -1869,7 +1897,7 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   AllocScope alloc_scope(E->stream);
   CU(E->d_state.ensure(E->sl.size() * sizeof(double)));
   CU(E->d_cand.ensure(E->sl.size() * sizeof(double)));
-  CU(E->d_counter.ensure(sizeof(unsigned long long)));
+  CU(E->d_counter.ensure(2 * sizeof(unsigned long long)));  // [0]: adders (copy stream); [1]: queries / scan association (compute stream)
   CU(E->d_flags.ensure(16 * sizeof(int)));
   CU(cudaMemsetAsync(E->d_flags.p, 0, 16 * sizeof(int), E->stream));
   int rc = upload_state(E.get());
@@ -2237,6 +2265,17 @@ CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, do
   return CLIC_OK;
 }
 
+CLIC_API int clic_add_gravity(clic_estimator* E, const double gravity[3], const double info_vec[3],
+                              int32_t marg_this_factor) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!gravity || !info_vec) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_gravity: null argument");
+  clic_estimator::GravFac f;
+  for (int i = 0; i < 3; i++) { f.g0[i] = gravity[i]; f.sqrt_info[i] = info_vec[i]; }
+  f.marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
+  E->grav_f.push_back(f);
+  return CLIC_OK;
+}
+
 CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, const double* p_i, const double* t_j,
                             const double* p_j, const int32_t* landmark, int32_t fixed_depth,
                             int32_t marg_this_feature, int64_t* n_dropped) {
@@ -2518,7 +2557,7 @@ CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost
   if (flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
   if (int prc = check_p2p(E)) return prc;
   if (cost) *cost = c2[0];
-  if (fixed_cost) *fixed_cost = c2[1];
+  if (fixed_cost) *fixed_cost = c2[1] + E->grav_fixed_cost();
   return CLIC_OK;
 }
 
@@ -2667,16 +2706,16 @@ CLIC_API int clic_query_poses(clic_estimator* E, int64_t n, const double* t_s, c
   if ((rc = to_device(E, d_t, t_s, n))) return rc;
   CU(d_q.ensure((size_t)4 * n * sizeof(double)));
   CU(d_p.ensure((size_t)3 * n * sizeof(double)));
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  CU(cudaMemsetAsync(E->d_counter.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), E->stream));
   PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
   const PoseQuery q = make_pose_query(E, n, d_t.as<double>(), S_StoI, p_SinI, t_offset_ns);
   pose_query_kernel<<<query_grid(E, n), 256, window_smem_doubles(E->K) * sizeof(double), E->stream>>>(
-      pp, q, d_q.as<double>(), d_p.as<double>(), E->d_counter.as<unsigned long long>());
+      pp, q, d_q.as<double>(), d_p.as<double>(), E->d_counter.as<unsigned long long>() + 1);
   E->launches++;
   unsigned long long bad = 0;
   CU(cudaMemcpyAsync(q_out, d_q.p, (size_t)4 * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaMemcpyAsync(p_out, d_p.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(&bad, E->d_counter.as<unsigned long long>() + 1, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
   if (n_invalid) *n_invalid = (int64_t)bad;
@@ -2703,23 +2742,23 @@ CLIC_API int clic_undistort_scan(clic_estimator* E, int64_t n, const double* t_s
   if (!in_global) {  // GetLidarPose(target_timestamp) on the device, then its inverse inside the kernel
     if ((rc = to_device(E, d_tt, &target_t_s, 1))) return rc;
     CU(d_target.ensure(7 * sizeof(double)));
-    CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+    CU(cudaMemsetAsync(E->d_counter.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), E->stream));
     const PoseQuery qt = make_pose_query(E, 1, d_tt.as<double>(), S_LtoI, p_LinI, t_offset_ns);
     pose_query_kernel<<<1, 256, smem, E->stream>>>(pp, qt, d_target.as<double>(), d_target.as<double>() + 4,
-                                                   E->d_counter.as<unsigned long long>());
+                                                   E->d_counter.as<unsigned long long>() + 1);
     E->launches++;
-    CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaMemcpyAsync(&bad, E->d_counter.as<unsigned long long>() + 1, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
     CU(cudaStreamSynchronize(E->stream));
     if (bad) return fail(CLIC_ERR_BAD_ARGUMENT, "target time outside the trajectory");
     target = d_target.as<double>();
   }
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), E->stream));
+  CU(cudaMemsetAsync(E->d_counter.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), E->stream));
   const PoseQuery q = make_pose_query(E, n, d_t.as<double>(), S_LtoI, p_LinI, t_offset_ns);
   undistort_kernel<<<query_grid(E, n), 256, smem, E->stream>>>(pp, q, d_in.as<float>(), target, d_out.as<float>(),
-                                                              E->d_counter.as<unsigned long long>());
+                                                              E->d_counter.as<unsigned long long>() + 1);
   E->launches++;
   CU(cudaMemcpyAsync(xyz_out, d_out.p, (size_t)3 * n * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaMemcpyAsync(&bad, E->d_counter.p, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaMemcpyAsync(&bad, E->d_counter.as<unsigned long long>() + 1, sizeof(bad), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   CU(cudaGetLastError());
   if (n_invalid) *n_invalid = (int64_t)bad;
@@ -3242,7 +3281,7 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
   const double* in_t[2] = {corner_t, surf_t};
   const PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
   const size_t smem = window_smem_doubles(E->K) * sizeof(double);
-  CU(cudaMemsetAsync(E->d_counter.p, 0, sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(E->d_counter.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), st));
   for (int s = 0; s < 2; s++) {
     const AssocSide& S = P.side[s];
     if (S.n_q == 0) continue;
@@ -3252,10 +3291,14 @@ CLIC_API int clic_add_loam_from_scan(clic_estimator* E, clic_feature_map* m, int
     const PoseQuery q = make_pose_query(E, S.n_feat, (const double*)(base + S.o_t), S_LtoI, p_LinI, t_offset_ns);
     undistort_kernel<<<query_grid(E, S.n_feat), 256, smem, st>>>(pp, q, (const float*)(base + S.o_xyzL), nullptr,
                                                                  (float*)(base + S.o_xyzM),
-                                                                 E->d_counter.as<unsigned long long>());
+                                                                 E->d_counter.as<unsigned long long>() + 1);
     E->launches++;
   }
   const assoc_dev::AssocJobs jobs = assoc_jobs(m, P);
+  // sort_downsample_kernel packs (type << 16) | q and sorts at most kSortMax records in one CTA; the plan's stride
+  // (n / 1500 + 1) keeps n_q <= 1500 per type — refuse instead of truncating if that ever stops being true
+  if (jobs.j[0].n_q + jobs.j[1].n_q > assoc_dev::kSortMax || jobs.j[0].n_q > 65535 || jobs.j[1].n_q > 65535)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam_from_scan: more selected features than the correspondence sort holds");
   assoc_search(m, P, jobs, st);
   assoc_dev::SortedOut out;
   for (int s = 0; s < 2; s++) {

@@ -1473,6 +1473,26 @@ __global__ void bias_factor_kernel(BiasFactorDesc bf, const double* state, State
   }
 }
 
+// GravityFactor (trajectory_value_factor.h:33-62) added to the marginalization system: r = w (g - g0), J = diag(w) on the
+// three ambient gravity columns starting at `col` (-1: no column).  One lane per row.
+__global__ void gravity_factor_kernel(double g0x, double g0y, double g0z, double wx, double wy, double wz, const double* g,
+                                      int col, double* A, double* b, int D, double* cost2) {
+  const int r = threadIdx.x;
+  double c = 0.0;
+  if (r < 3) {
+    const double w = r == 0 ? wx : (r == 1 ? wy : wz), g0 = r == 0 ? g0x : (r == 1 ? g0y : g0z);
+    const double res = w * (g[r] - g0);
+    c = res * res;
+    if (col >= 0) {
+      A[(size_t)(col + r) * D + col + r] += w * w;
+      b[col + r] += w * res;
+    }
+  }
+  double tot = 0.0;
+  for (int k = 0; k < 3; k++) tot += __shfl_sync(0xffffffffu, c, k);
+  if (r == 0) cost2[0] += 0.5 * tot;
+}
+
 // auto_diff::IMUGlobalVelocityFactor (factor/auto_diff/trajectory_value_factor.h:436-487) with CauchyLoss(60)
 // (trajectory_estimator.cpp:642): r = w (p'(t) - v), t = double(time_ns) + t_offset_IMU (not truncated: a Jet in the
 // reference), indexed by the templated SplineSegmentMeta::computeTIndexNs (spline_segment.h:108-118: floor of a double

@@ -213,6 +213,11 @@ class TrajectoryEstimator:
         _check(self.lib, self.lib.clic_add_bias(self.h, int(slot_i), int(slot_j), float(dt), dptr(info_vec),
                                                 int(bool(marg_this_factor)), int(bool(marg_all_bias))))
 
+    # ---- trajectory_estimator.h:164-165 ----
+    def AddGravityFactor(self, gravity, info_vec, marg_this_factor=False):
+        g, info_vec = f64(gravity), f64(info_vec)
+        _check(self.lib, self.lib.clic_add_gravity(self.h, dptr(g), dptr(info_vec), int(bool(marg_this_factor))))
+
     # ---- trajectory_estimator.cpp:609-664 ----
     def AddGlobalVelocityMeasurement(self, timestamp, global_v, vel_weight):
         """IMUGlobalVelocityFactor at one timestamp; returns False when it falls outside the window."""

@@ -8,6 +8,7 @@
 // types replace Eigen::Vector3d / Sophus::SO3d (same memory layout: 3 doubles / 4 doubles x,y,z,w).
 // Link against libclic_cuda.so (product) — or, in tests only, the oracle library, which exports the same symbols.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -145,6 +146,51 @@ struct MarginalizationInfo {
     if (prior) clic_prior_release(prior);
   }
 };
+
+// marginalization_factor.h:31-46
+enum ResidualType {
+  RType_Pose = 0, RType_IMU, RType_Bias, RType_Gravity, RType_LiDAR, RType_LiDAR_Relative, RType_LiDAROpt,
+  RType_PreIntegration, RType_GlobalVelocity, RType_LocalVelocity, RType_Local6DoFVel, RType_Image, RType_Epipolar,
+  RType_Prior
+};
+
+// MarginalizationFactor (marginalization_factor.h:145-154): the cost function the caller wraps a prior in before
+// handing it to PrepareMarginalizationInfo(RType_Prior, ...) (trajectory_manager.cpp:370-376, 488-494).  Here it only
+// carries the prior; its Evaluate (marginalization_factor.cpp:331-372) runs on the device (prior_kernel).
+struct MarginalizationFactor {
+  explicit MarginalizationFactor(MarginalizationInfo::Ptr _marginalization_info)
+      : marginalization_info(std::move(_marginalization_info)) {}
+  MarginalizationInfo::Ptr marginalization_info;
+};
+
+// 2 x 2 matrix with just enough arithmetic for `image_feature_weight * Matrix2d::Identity()` (trajectory_manager.cpp:57-58)
+struct Matrix2d {
+  double m[4] = {1, 0, 0, 1};
+  static Matrix2d Identity() { return Matrix2d(); }
+  friend Matrix2d operator*(double s, Matrix2d a) {
+    for (double& x : a.m) x *= s;
+    return a;
+  }
+  double operator()(int r, int c) const { return m[2 * r + c]; }
+};
+
+namespace analytic_derivative {
+// The static parameters TrajectoryManager::InitFactorInfo sets on the visual factor class once per run
+// (trajectory_manager.cpp:53-61; image_feature_factor.h:270-284): camera extrinsics and sqrt_info = image_weight * I2.
+// The estimator reads them when it builds the problem (sqrt_info -> clic_options::image_sqrt_info; the camera extrinsics
+// also travel in Trajectory::EP_StoI[CameraSensor], which is what the reference's SetParam call is fed from).
+struct ImageFeatureFactor {
+  static void SetParam(const SO3d& _S_CtoI, const Vec3d& _p_CinI) {
+    S_CtoI() = _S_CtoI;
+    p_CinI() = _p_CinI;
+    param_set() = true;
+  }
+  static SO3d& S_CtoI() { static SO3d v; return v; }
+  static Vec3d& p_CinI() { static Vec3d v{}; return v; }
+  static bool& param_set() { static bool v = false; return v; }
+  static inline Matrix2d sqrt_info = (450. / 1.5) * Matrix2d::Identity();  // class default, image_feature_factor.h:277-278
+};
+}  // namespace analytic_derivative
 
 class TrajectoryEstimator {
  public:
@@ -303,6 +349,44 @@ class TrajectoryEstimator {
     priors_.push_back({last_marginalization_info, drop_blocks});
   }
 
+  // trajectory_estimator.h:228-232 with a MarginalizationFactor (RType_Prior): what UpdateLIOPrior /
+  // UpdateVisualOffsetPrior call to route the previous prior into the marginalization set, `drop_set` = indices into
+  // `parameter_blocks` (trajectory_manager.cpp:352-376, 488-494).  Takes ownership of the factor like the reference's
+  // MarginalizationInfo does (marginalization_factor.cpp:64-74).  Other residual types reach the marginalization set
+  // through their Add* call with marg_this_factor = true, exactly as in the reference.
+  void PrepareMarginalizationInfo(ResidualType r_type, MarginalizationFactor* cost_function, void* /*loss_function*/,
+                                  std::vector<double*>& parameter_blocks, std::vector<int>& drop_set) {
+    if (r_type != RType_Prior || !cost_function)
+      throw std::runtime_error("PrepareMarginalizationInfo: only RType_Prior factors are passed in by the caller");
+    std::unique_ptr<MarginalizationFactor> own(cost_function);
+    AddMarginalizationFactor(own->marginalization_info, parameter_blocks, drop_set);
+  }
+
+  // trajectory_estimator.h:144 / .cpp:303-310: makes the time-offset blocks constant when their lock flag is set.
+  // Here the lock flags travel with the options when the problem is built, so there is nothing left to do.
+  void SetTimeoffsetState() {}
+
+  // trajectory_estimator.cpp:251-270: every knot whose segment starts before max_time becomes constant.  (The reference
+  // keeps the method but its only call site is commented out, trajectory_manager.cpp:263.)
+  void SetKeyScanConstant(double max_time) {
+    const double toff_s = 1e-9 * trajectory_->EP_StoI[LiDARSensor].t_offset_ns;
+    const int64_t t_ns = (int64_t)((max_time + toff_s) * 1e9);
+    if (t_ns < trajectory_->t0_ns) return;
+    const int64_t s = (t_ns - trajectory_->t0_ns) / trajectory_->dt_ns;  // start index of the segment holding max_time
+    const int last = trajectory_->knot_id0 + (int)std::min<int64_t>(s + 3, (int64_t)trajectory_->numKnots() - 1);
+    if (last > fixed_control_point_index_) fixed_control_point_index_ = last;
+  }
+
+  // trajectory_estimator.h:164-165
+  void AddGravityFactor(double* gravity, const Vec3d& info_vec, bool marg_this_factor = false) {
+    gravity_ = gravity;
+    GravFac f;
+    f.g0 = {{gravity[0], gravity[1], gravity[2]}};
+    f.info = info_vec;
+    f.marg = marg_this_factor;
+    grav_f_.push_back(f);
+  }
+
   // trajectory_estimator.h:225-226
   Summary Solve(int max_iterations = 50, bool /*progress*/ = false, int /*num_threads*/ = -1) {
     build();
@@ -395,6 +479,10 @@ class TrajectoryEstimator {
     MarginalizationInfo::Ptr info;
     std::vector<int> drop;
   };
+  struct GravFac {
+    Vec3d g0{}, info{};
+    bool marg = false;
+  };
 
   static void check(int rc) {
     if (rc != CLIC_OK) throw std::runtime_error(std::string("clic: ") + clic_last_error());
@@ -466,6 +554,11 @@ class TrajectoryEstimator {
     o.marg_t_offset_param = options.marg_t_offset_param;
     o.device = options.device;
     o.stream = options.stream;
+    o.image_sqrt_info = analytic_derivative::ImageFeatureFactor::sqrt_info(0, 0);  // InitFactorInfo, trajectory_manager.cpp:57-61
+    if (analytic_derivative::ImageFeatureFactor::param_set()) {  // ImageFeatureFactor::SetParam wins, as in the reference
+      std::memcpy(w.S_CtoI, analytic_derivative::ImageFeatureFactor::S_CtoI().data(), sizeof(w.S_CtoI));
+      std::memcpy(w.p_CinI, analytic_derivative::ImageFeatureFactor::p_CinI().data(), sizeof(w.p_CinI));
+    }
     check(clic_create(&w, &o, &h_));
     check(clic_set_fixed_index(h_, fixed_control_point_index_));
     // the reference's call order is prior, LiDAR, image, IMU, bias (trajectory_manager.cpp:659-750).  Upload order here:
@@ -490,6 +583,7 @@ class TrajectoryEstimator {
                                   b.S_GtoM.data(), b.p_GinM.data(), b.S_LtoI.data(), b.p_LinI.data(), b.weight, b.marg,
                                   nullptr));
     for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
+    for (auto& f : grav_f_) check(clic_add_gravity(h_, f.g0.data(), f.info.data(), f.marg));
     for (auto& f : vel_f_) check(clic_add_global_velocity(h_, f.t, f.v.data(), f.w, nullptr));
     for (auto& b : scans_) {
       int64_t nl = 0, np = 0;
@@ -531,6 +625,7 @@ class TrajectoryEstimator {
   std::vector<ImuBatch> imu_;
   std::vector<ImageBatch> image_;
   std::vector<BiasFac> bias_f_;
+  std::vector<GravFac> grav_f_;
   std::vector<VelFac> vel_f_;
   std::vector<PriorRef> priors_;
   std::vector<std::pair<double*, double*>> bias_ptr_;

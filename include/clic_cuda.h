@@ -119,7 +119,13 @@ typedef struct {
   int32_t device;        /* CUDA device ordinal */
   void* stream;          /* cudaStream_t to run on; NULL = library-owned stream */
   int32_t deterministic; /* 1 (default): fixed reduction order */
-  int32_t reserved[7];
+  int32_t reserved0;
+  /* ImageFeatureFactor::sqrt_info (scalar x I2).  The class default is 450/1.5 (image_feature_factor.h:277-278), but
+   * every run overwrites it with the configured `image_weight` through TrajectoryManager::InitFactorInfo
+   * (trajectory_manager.cpp:53-61; config/ct_odometry_ntu.yaml:35 = 200, ct_odometry_lvi.yaml:35 = 450).
+   * clic_default_options sets the class default; <= 0 also means the class default. */
+  double image_sqrt_info;
+  int32_t reserved[4];
 } clic_options;
 
 /* POD replacement of ceres::Solver::Summary (trajectory_estimator.h:225-226). */
@@ -208,6 +214,14 @@ CLIC_API int clic_add_imu(clic_estimator* h, int64_t n, const double* timestamp,
 /* AddBiasFactor (trajectory_estimator.cpp:457-498). */
 CLIC_API int clic_add_bias(clic_estimator* h, int32_t slot_i, int32_t slot_j, double dt,
                            const double info_vec[6], int32_t marg_this_factor, int32_t marg_all_bias);
+
+/* AddGravityFactor (trajectory_estimator.cpp:500-523) with GravityFactor (trajectory_value_factor.h:33-62):
+ * r = diag(info_vec) (g - gravity), gravity = the value the caller passes (the reference passes the block's value at
+ * add time, so r = 0 until the block moves).  In a solve the gravity block is constant (lock_g: every shipped call), so
+ * the factor only adds its constant cost to fixed_cost; in a marginalization estimator with marg_this_factor it enters the
+ * prior (J = diag(info_vec) on the 3 ambient gravity columns), the block dropped iff marg_gravity_param. */
+CLIC_API int clic_add_gravity(clic_estimator* h, const double gravity[3], const double info_vec[3],
+                              int32_t marg_this_factor);
 
 /* AddGlobalVelocityMeasurement (trajectory_estimator.cpp:609-664) with auto_diff::IMUGlobalVelocityFactor
  * (factor/auto_diff/trajectory_value_factor.h:436-487): r = vel_weight * (p'(t + t_offset_IMU) - global_v) on the

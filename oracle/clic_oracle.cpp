@@ -970,6 +970,7 @@ CLIC_API void clic_default_options(clic_options* o) {
   o->device = 0;
   o->stream = nullptr;
   o->deterministic = 1;
+  o->image_sqrt_info = 450.0 / 1.5;  // ImageFeatureFactor's class default (image_feature_factor.h:277-278)
 }
 
 // Test-only knob: number of OpenMP threads of the evaluation loop (the reference runs Ceres with 1 thread,
@@ -1269,6 +1270,25 @@ CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, do
   return CLIC_OK;
 }
 
+// TrajectoryEstimator::AddGravityFactor — trajectory_estimator.cpp:500-523
+CLIC_API int clic_add_gravity(clic_estimator* E, const double gravity[3], const double info_vec[3],
+                              int32_t marg_this_factor) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  ResidualBlock rb;
+  rb.cost.reset(new GravityFactor(gravity, info_vec));
+  rb.refs = {{CLIC_BLOCK_GRAVITY, 0}};
+  rb.rtype = 5;
+  if (E->opt.is_marg_state && marg_this_factor) {
+    std::vector<int> drop = {0};  // ":515-519"
+    if (!E->opt.marg_gravity_param) drop.clear();
+    rb.drop_set = drop;  // non-spline PrepareMarginalizationInfo: always added (":199-206")
+    E->marg_blocks.push_back(std::move(rb));
+  } else {
+    E->blocks.push_back(std::move(rb));
+  }
+  return CLIC_OK;
+}
+
 CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, const double* p_i, const double* t_j,
                             const double* p_j, const int32_t* landmark, int32_t fixed_depth,
                             int32_t marg_this_feature, int64_t* n_dropped) {
@@ -1301,7 +1321,8 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     }
     ResidualBlock rb;
     rb.cost.reset(new ImageFeatureFactor(time_i_ns, load_v(p_i + 3 * i), time_j_ns, load_v(p_j + 3 * i), meta,
-                                         E->S_CtoI, E->p_CinI));
+                                         E->S_CtoI, E->p_CinI,
+                                         E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450. / 1.5));
     E->AddControlPoints(meta, rb.refs, false);
     E->AddControlPoints(meta, rb.refs, true);
     rb.refs.push_back({CLIC_BLOCK_INV_DEPTH, lm});

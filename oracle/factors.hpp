@@ -217,6 +217,26 @@ struct IMUFactor : CostFunction {
 };
 
 // BiasFactor — trajectory_value_factor.h:65-126
+// GravityFactor — src/estimator/factor/analytic_diff/trajectory_value_factor.h:33-62
+struct GravityFactor : CostFunction {
+  Vec3 gravity_;
+  double sqrt_info_[3];
+  GravityFactor(const double gravity[3], const double sqrt_info[3]) : gravity_(load_v(gravity)) {
+    for (int i = 0; i < 3; i++) sqrt_info_[i] = sqrt_info[i];
+    num_residuals = 3;
+    block_sizes = {3};
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    Vec3 g = load_v(parameters[0]);
+    for (int i = 0; i < 3; i++) residuals[i] = sqrt_info_[i] * (g[i] - gravity_[i]);
+    if (jacobians && jacobians[0]) {
+      for (int c = 0; c < 9; c++) jacobians[0][c] = 0;
+      for (int r = 0; r < 3; r++) jacobians[0][r * 3 + r] = sqrt_info_[r];
+    }
+    return true;
+  }
+};
+
 struct BiasFactor : CostFunction {
   double sqrt_info_[6];
   BiasFactor(double dt, const double sqrt_info[6]) {
@@ -324,11 +344,14 @@ struct ImageFeatureFactor : CostFunction {
   SplineMeta spline_meta_;
   Quat S_CtoI;
   Vec3 p_CinI;
-  double sqrt_info;  // 450/1.5 * I2 (":277-278")
+  // static Eigen::Matrix2d sqrt_info, class default 450/1.5 * I2 (":277-278"), overwritten per run with
+  // image_weight * I2 by TrajectoryManager::InitFactorInfo (trajectory_manager.cpp:53-61): a member here, set from
+  // clic_options::image_sqrt_info
+  double sqrt_info;
   ImageFeatureFactor(int64_t t_i_ns, const Vec3& p_i, int64_t t_j_ns, const Vec3& p_j, const SplineMeta& meta,
-                     const Quat& _S_CtoI, const Vec3& _p_CinI)
+                     const Quat& _S_CtoI, const Vec3& _p_CinI, double _sqrt_info = 450. / 1.5)
       : t_i_ns_(t_i_ns), t_j_ns_(t_j_ns), p_i_(p_i), p_j_(p_j), spline_meta_(meta), S_CtoI(_S_CtoI),
-        p_CinI(_p_CinI), sqrt_info(450. / 1.5) {
+        p_CinI(_p_CinI), sqrt_info(_sqrt_info) {
     num_residuals = 2;
     size_t kont_num = spline_meta_.NumParameters();
     for (size_t i = 0; i < kont_num; ++i) block_sizes.push_back(4);

@@ -227,3 +227,37 @@ def test_visual_offset_prior(cuda, oracle, marg_toff):
     assert (2 in list(ro["id"][ro["kind"] == 5])) == (marg_toff == 0)      # camera time offset kept iff not marginalised
     assert rel_scaled(Ag, Ao) < 1e-7, rel_scaled(Ag, Ao)
     assert np.abs(gg - go).max() / np.abs(go).max() < 1e-7
+
+
+def test_gravity_factor_enters_the_prior(cuda, oracle):
+    """AddGravityFactor (trajectory_estimator.cpp:500-523) in a marginalization estimator: J = diag(info) on the gravity
+    block, dropped iff marg_gravity_param; in a solve the block is constant and the factor only adds fixed cost."""
+    sw = make(0.1)
+    for marg_g in (1, 0):
+        out = {}
+        for name, lib in (("g", cuda), ("o", oracle)):
+            rng = np.random.default_rng(7)
+            p0, kinds, ids = previous_prior(lib, sw, range(0, 24), rng)
+            est = marg_estimator(lib, sw, p0, kinds, ids)
+            est.AddGravityFactor(sw.window.gravity + np.array([0.01, -0.02, 0.03]), [50.0, 60.0, 70.0], True)
+            pr = est.SaveMarginalizationInfo()
+            out[name] = (pr.dims(), pr.read(), pr.normal())
+        (dg, rg, (Ag, gg)), (do, ro, (Ao, go)) = out["g"], out["o"]
+        assert dg == do
+        for k in ("kind", "id", "offset"):
+            assert np.array_equal(rg[k], ro[k]), k
+        assert rel_scaled(Ag, Ao) < 1e-7 and np.abs(gg - go).max() / np.abs(go).max() < 1e-7
+    # solve mode: accepted, constant block -> fixed cost only
+    costs = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        opt = E.default_options(lib)
+        est = E.TrajectoryEstimator(sw.window, opt, lib)
+        est.SetFixedIndex(2)
+        S.add_all_factors(est, sw, bias_factor=False)
+        H0, b0, c0, f0 = est.Evaluate()
+        est.AddGravityFactor(sw.window.gravity + np.array([0.01, -0.02, 0.03]), [50.0, 60.0, 70.0])
+        H1, b1, c1, f1 = est.Evaluate()
+        assert np.array_equal(H0, H1) and np.array_equal(b0, b1) and c0 == c1
+        costs[name] = f1 - f0
+    expect = 0.5 * ((50 * 0.01) ** 2 + (60 * 0.02) ** 2 + (70 * 0.03) ** 2)
+    assert abs(costs["o"] - expect) < 1e-9 and abs(costs["g"] - expect) < 1e-9

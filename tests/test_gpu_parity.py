@@ -22,8 +22,10 @@ def rel_scaled(Hg, Ho):
 
 
 def build(lib, sw, fixed=-1, unlock_bias=False, unlock_toff=False, bias_factor=True, pad=10_000_000,
-          unlock_cam_toff=False, fixed_depth=True):
+          unlock_cam_toff=False, fixed_depth=True, image_weight=None):
     opt = E.default_options(lib)
+    if image_weight is not None:
+        opt.image_sqrt_info = image_weight
     if unlock_bias:
         opt.lock_ab = opt.lock_wb = 0
     if unlock_toff:
@@ -324,3 +326,14 @@ np.savez(sys.argv[1], H=H, b=b, c=c, s0=s0, u0=u0, s1=s1, u1=u1)
     assert (np.abs(Ha - Hp) / np.outer(d, d)).max() < 1e-13
     assert (np.abs(out["aligned"]["b"] - out["plain"]["b"]) / d).max() <= 1e-12 * (np.abs(out["plain"]["b"]) / d).max()
     assert abs(out["aligned"]["c"] - out["plain"]["c"]) <= 1e-13 * abs(out["plain"]["c"])
+
+
+@pytest.mark.parametrize("weight", [200.0, 450.0])
+def test_c3_image_weight_from_config(cuda, oracle, weight):
+    """The visual factor's sqrt_info as every shipped config sets it (trajectory_manager.cpp:53-61: image_weight = 200 /
+    450), not the class default; the option itself is pinned on the CPU against auto-diff
+    (tests/test_oracle_autodiff.py::test_image_feature_weight_from_config)."""
+    sw = S.config(3, 0.1)
+    Hw, bw = compare_eval(cuda, oracle, sw, unlock_bias=True, image_weight=weight)
+    Hd, bd = compare_eval(cuda, oracle, sw, unlock_bias=True)
+    assert rel_scaled(Hw, Hd) > 1e-4  # the weight does change the system

@@ -106,6 +106,33 @@ def test_image_feature_factor(oracle, seed, case):
     assert np.abs(J[:, L.col_t_offset[2]] - Jx[1][:, 0]).max() < TOL * scale
 
 
+@pytest.mark.parametrize("weight", [200.0, 450.0])
+def test_image_feature_weight_from_config(oracle, weight):
+    """ImageFeatureFactor::sqrt_info is not the class default in any shipped run: TrajectoryManager::InitFactorInfo sets
+    it to image_weight * I2 (trajectory_manager.cpp:53-61; config/ct_odometry_ntu.yaml:35 = 200, ct_odometry_lvi.yaml:35
+    = 450).  The option that carries it is pinned here against the independent auto-diff lineage, which takes the
+    weight as a plain argument (round 1 shared one literal between oracle and product, so a wrong weight was invisible)."""
+    w = reference_test_trajectory(2)
+    ti, tj = 0.13, 0.34
+    pi, pj = np.array([1, 2, 1.0]), np.array([4, 5, 1.0])
+    opt = E.default_options(oracle)
+    assert abs(opt.image_sqrt_info - 450.0 / 1.5) < 1e-12          # the class default (image_feature_factor.h:277-278)
+    opt.image_sqrt_info = weight
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    assert est.AddImageFeatureAnalytic([ti], [pi], [tj], [pj], [0], fixed_depth=True) == 0
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.image_residual(win_dict(w), int(ti * 1e9), pi, int(tj * 1e9), pj, w.S_CtoI, w.p_CinI, sqrt_info=weight)
+    r_ad, Jk, _ = AD.jac(fn, w.n_knots, [[w.inv_depth[0]], [w.t_offset_ns[2]]])
+    assert np.allclose(r, r_ad, rtol=1e-9, atol=1e-7)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * max(1.0, np.abs(Jk).max())
+    # and it is not the default: the residual scales with the weight
+    est0 = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    est0.AddImageFeatureAnalytic([ti], [pi], [tj], [pj], [0], fixed_depth=True)
+    r0, _ = oracle_lib.block_jacobian(oracle, est0, 0)
+    assert np.allclose(r / weight, r0 / (450.0 / 1.5), rtol=1e-12)
+
+
 def test_synthetic_window_factors(oracle):
     """Same property on a realistic (small-rotation-increment) window, every factor type, a few factors each."""
     sw = S.make_window(10, n_lidar=12, n_imu=6, n_landmarks=3, obs_per_landmark=3, line_fraction=0.5, seed=7)
