@@ -525,9 +525,11 @@ int check_p2p(clic_estimator* E) {
 }
 
 // ---- fused pass (pass_fused.cuh) ----
-// CLIC_FUSED=0: one kernel per stream + reduction + assembly (+ all-reduce) as in round 1 (A/B runs, tests compare the
-// two paths); read at every layout so that a test can flip it between two estimators.
-bool fused_enabled() { const char* e = getenv("CLIC_FUSED"); return !(e && e[0] == '0'); }
+// CLIC_FUSED=0: one kernel per stream + reduction + assembly (+ all-reduce) as in round 1; =1: the fused pass whenever
+// it is applicable; unset: automatic (build_fused: the fused pass for windows with enough work to amortise its fixed
+// cost — per-CTA dense system, grid barrier — and always on several ranks, where it carries the exchange).  Read at
+// every layout so that a test can flip it between two estimators.
+int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }
 // Static cost model of the grid partition: a stream on n CTAs takes  f + ceil(slabs / (8 n)) * w  microseconds — w per
 // 32-factor slab (16 for the visual stream) of one warp with two warps per SM sub-partition, f the stream's fixed part
 // (window staging, pose packs, first-slab latency, the dense finish) — fitted to %globaltimer stamps of the C5 window
@@ -569,7 +571,7 @@ int build_fused(clic_estimator* E) {
   for (int k = 0; k < 3; k++) F.lb[k] = nullptr;
   F.ib = nullptr;
   F.gb = nullptr;
-  if (!fused_enabled() || E->L.D <= 0) return CLIC_OK;
+  if (fused_mode() == 0 || E->L.D <= 0) return CLIC_OK;
   for (auto& b : E->loam) {
     if (b->marg) continue;
     const int k = b->st.geo_kind;
@@ -608,6 +610,14 @@ int build_fused(clic_estimator* E) {
   if (F.ib) push(3, F.ib->ex, E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1.25 : 1.0);
   if (F.gb) push(F.gb->st.n_packs > 0 ? 4 : 5, F.gb->ex);
   if (js.empty() || (int)js.size() > E->n_sm) return CLIC_OK;
+  if (fused_mode() < 0 && !E->use_comm) {
+    // Small windows (the reference's production size: a few hundred factors, ~30 slabs) are latency-bound and run
+    // faster as per-stream launches (measured, bench_micro/small_window.py: C1 85 vs 100 us per LM iteration); from
+    // ~C2's size on the fused pass wins (C3 45.6 vs 54.4 us per pass, C5 204 vs 244 us).  Work = modelled warp-time.
+    double work = 0.0;
+    for (auto& j : js) work += j.w * (double)j.slabs;
+    if (work < 6000.0) return CLIC_OK;
+  }
   {
     // exact min-max under the model: the finishing time T is one of  f_j + m w_j;  a stream needs
     // n_j(T) = ceil(slabs_j / (8 floor((T - f_j) / w_j))) CTAs; smallest T whose CTAs fit the grid

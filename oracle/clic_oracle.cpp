@@ -793,6 +793,12 @@ int solve(clic_estimator* E, int max_iterations, clic_summary* sum) {
 }
 
 // ---------------- marginalization (MarginalizationInfo) ----------------
+// The assembled system [dropped | kept] of the last marginalize() call, before the Schur complement (test probe:
+// tests compare the Schur routes — the reference's eigen pseudo-inverse, the product's Cholesky — with an extended-
+// precision elimination of this system).
+static std::vector<double> g_last_marg_A, g_last_marg_b;
+static int g_last_marg_pos = 0, g_last_marg_m = 0;
+
 int marginalize(clic_estimator* E, clic_prior** out) {
   // addResidualBlockInfo: sizes of all blocks, idx=0 marks dropped — marginalization_factor.cpp:76-92
   std::map<CanonKey, BlockRef> all;
@@ -856,6 +862,10 @@ int marginalize(clic_estimator* E, clic_prior** out) {
       }
     }
   }
+  g_last_marg_A = A;
+  g_last_marg_b = b;
+  g_last_marg_pos = pos;
+  g_last_marg_m = m;
   const double eps = 1e-15;  // marginalization_factor.h:142
   // Amm^+ via eigen-decomposition with eigenvalue cut — ":208-213"
   std::vector<double> Amm((size_t)m * m), Amm_inv((size_t)m * m, 0.0);
@@ -975,6 +985,14 @@ CLIC_API void clic_default_options(clic_options* o) {
 
 // Test-only knob: number of OpenMP threads of the evaluation loop (the reference runs Ceres with 1 thread,
 // trajectory_estimator.cpp:1004-1007, and marginalization with 4 pthreads, marginalization_factor.h:29).
+CLIC_API int clic_oracle_last_marg_system(double* A, double* b, int32_t* pos, int32_t* m) {
+  if (pos) *pos = g_last_marg_pos;
+  if (m) *m = g_last_marg_m;
+  if (A) std::memcpy(A, g_last_marg_A.data(), g_last_marg_A.size() * sizeof(double));
+  if (b) std::memcpy(b, g_last_marg_b.data(), g_last_marg_b.size() * sizeof(double));
+  return CLIC_OK;
+}
+
 CLIC_API int clic_oracle_set_threads(int n) {
   g_threads = n < 1 ? 1 : n;
   return CLIC_OK;

@@ -14,18 +14,32 @@ from test_gpu_parity import build, rel, rel_scaled
 pytestmark = pytest.mark.gpu
 
 
-class per_stream_kernels:
-    """Estimators whose layout is built inside this block run one kernel per stream (round-1 path)."""
+class pass_mode:
+    """Estimators whose layout is built inside this block run the chosen pass: "0" one kernel per stream (round-1
+    path), "1" the fused pass whenever applicable (by default the library picks by problem size)."""
+
+    def __init__(self, mode):
+        self.mode = mode
 
     def __enter__(self):
         self.prev = os.environ.get("CLIC_FUSED")
-        os.environ["CLIC_FUSED"] = "0"
+        os.environ["CLIC_FUSED"] = self.mode
 
     def __exit__(self, *a):
         if self.prev is None:
             os.environ.pop("CLIC_FUSED", None)
         else:
             os.environ["CLIC_FUSED"] = self.prev
+
+
+def per_stream_kernels():
+    return pass_mode("0")
+
+
+@pytest.fixture(autouse=True)
+def force_fused():
+    with pass_mode("1"):
+        yield
 
 
 def both_paths(cuda, sw, solve_iters=None, **kw):
@@ -131,3 +145,34 @@ def test_stamps_cover_every_partition(cuda):
     assert st is not None and st.shape == (info["grid"], 8)
     assert (st[:, 1] >= st[:, 0]).all() and (st[:, 2] >= st[:, 1]).all() and (st[:, 5] >= st[:, 4]).all()
     assert (st[:, 4] >= st[:, 2]).all()
+
+
+def test_automatic_choice_by_problem_size(cuda):
+    """Unset CLIC_FUSED: small (production-size) windows keep the per-stream launches, large ones take the fused pass."""
+    prev = os.environ.pop("CLIC_FUSED", None)
+    try:
+        est, _ = build(cuda, S.config(1), bias_factor=False)
+        small = est.pass_info()["fused"]
+        est.close()
+        est, _ = build(cuda, S.config(3), unlock_bias=True)
+        large = est.pass_info()["fused"]
+        est.close()
+    finally:
+        if prev is not None:
+            os.environ["CLIC_FUSED"] = prev
+    assert not small and large
+
+
+def test_fused_pass_against_the_oracle_on_small_windows(cuda, oracle):
+    """The other GPU test files reach the fused pass only at BASELINE's full sizes (the automatic choice); here it is
+    forced on the small and ragged windows too and held to the same bars against the oracle."""
+    from test_gpu_parity import compare_eval
+    from test_gpu_solve import solve_both
+    compare_eval(cuda, oracle, S.config(1), bias_factor=False)
+    compare_eval(cuda, oracle, S.config(1), fixed=3, unlock_bias=True)
+    compare_eval(cuda, oracle, S.config(2, 0.1), unlock_bias=True, unlock_toff=True)
+    compare_eval(cuda, oracle, S.config(3, 0.1), unlock_bias=True, unlock_cam_toff=True)
+    compare_eval(cuda, oracle, S.make_window(10, n_lidar=3000, n_imu=0, line_fraction=1.0, seed=5))
+    solve_both(cuda, oracle, S.config(1), 8, fixed=2, unlock_bias=True)
+    solve_both(cuda, oracle, S.config(3, 0.1), 8, unlock_bias=True)
+    solve_both(cuda, oracle, S.config(2, 0.1), 8, unlock_bias=True, unlock_toff=True)

@@ -73,13 +73,14 @@ def test_c4_schur_of_20_knots(cuda, oracle):
     for k in ("kind", "id", "offset"):
         assert np.array_equal(rg[k], ro[k]), k       # same kept blocks in the same order
     assert np.allclose(rg["x0"], ro["x0"], rtol=0, atol=0)
-    # Schur complement: conditioning-limited agreement (cancellation A_rr - A_rm A_mm^-1 A_mr)
-    assert rel_scaled(Ag, Ao) < 1e-7, rel_scaled(Ag, Ao)
-    assert rel(Ag, Ao) < 1e-8, rel(Ag, Ao)
-    assert np.abs(gg - go).max() / np.abs(go).max() < 1e-7
+    # Schur complement: the same 1e-9 bar as H, b (measured 1e-13, see test_c4_schur_against_extended_precision; round 1
+    # asserted 1e-7 here without need)
+    assert rel_scaled(Ag, Ao) < 1e-9, rel_scaled(Ag, Ao)
+    assert rel(Ag, Ao) < 1e-9, rel(Ag, Ao)
+    assert np.abs(gg - go).max() / np.abs(go).max() < 1e-9
     # prior energy at the linearisation point: 1/2 r0^T r0
     eg, eo = 0.5 * rg["r0"] @ rg["r0"], 0.5 * ro["r0"] @ ro["r0"]
-    assert abs(eg - eo) <= 1e-7 * abs(eo)
+    assert abs(eg - eo) <= 1e-9 * abs(eo)
 
 
 def test_c4_fixed_lag_step_solve_with_new_prior(cuda, oracle):
@@ -246,7 +247,7 @@ def test_gravity_factor_enters_the_prior(cuda, oracle):
         assert dg == do
         for k in ("kind", "id", "offset"):
             assert np.array_equal(rg[k], ro[k]), k
-        assert rel_scaled(Ag, Ao) < 1e-7 and np.abs(gg - go).max() / np.abs(go).max() < 1e-7
+        assert rel_scaled(Ag, Ao) < 1e-9 and np.abs(gg - go).max() / np.abs(go).max() < 1e-9
     # solve mode: accepted, constant block -> fixed cost only
     costs = {}
     for name, lib in (("g", cuda), ("o", oracle)):
@@ -261,3 +262,41 @@ def test_gravity_factor_enters_the_prior(cuda, oracle):
         costs[name] = f1 - f0
     expect = 0.5 * ((50 * 0.01) ** 2 + (60 * 0.02) ** 2 + (70 * 0.03) ** 2)
     assert abs(costs["o"] - expect) < 1e-9 and abs(costs["g"] - expect) < 1e-9
+
+
+def _c4_priors(cuda, oracle, scale):
+    sw = make(scale)
+    out = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        rng = np.random.default_rng(7)
+        p0, kinds, ids = previous_prior(lib, sw, range(0, 24), rng)
+        est = marg_estimator(lib, sw, p0, kinds, ids)
+        pr = est.SaveMarginalizationInfo()
+        out[name] = pr.normal()
+    A, b, m = oracle_lib.last_marg_system(oracle)          # the assembled system of the oracle's run, before Schur
+    At, bt = oracle_lib.schur_extended_precision(A, b, m)   # 80-bit elimination of it: the yardstick
+    return out["g"], out["o"], (At, bt), (A, m)
+
+
+@pytest.mark.parametrize("scale", [0.25, 1.0])
+def test_c4_schur_against_extended_precision(cuda, oracle, scale):
+    """BASELINE config 4 at full size (40 knots, 20 000 LiDAR + 700 IMU, previous prior over 24 knots, Schur complement
+    of the 20 oldest): both Schur routes — the reference's eigen pseudo-inverse (oracle) and the product's Cholesky —
+    against an 80-bit elimination of the same assembled system.  Round 1 accepted 1e-7 between GPU and oracle and called
+    it conditioning; measured here instead: cond(A_mm) is 1e19 raw (ns next to metres) but ~1e2 after diagonal scaling,
+    and each route must sit within 1e-10 of the yardstick."""
+    (Ag, gg), (Ao, go), (At, bt), (A, m) = _c4_priors(cuda, oracle, scale)
+    Amm = A[:m, :m]
+    d = np.sqrt(np.diag(Amm))
+    ws = np.linalg.eigvalsh(Amm / np.outer(d, d))
+    print(f"\nC4 scale {scale}: m {m} n {At.shape[0]}  cond(A_mm) scaled {ws[-1] / ws[0]:.2e}")
+    print("  oracle vs 80-bit: A %.2e (scaled %.2e) g %.2e" % (rel(Ao, At), rel_scaled(Ao, At),
+                                                              np.abs(go - bt).max() / np.abs(bt).max()))
+    print("  GPU    vs 80-bit: A %.2e (scaled %.2e) g %.2e" % (rel(Ag, At), rel_scaled(Ag, At),
+                                                              np.abs(gg - bt).max() / np.abs(bt).max()))
+    print("  GPU    vs oracle: A %.2e (scaled %.2e) g %.2e" % (rel(Ag, Ao), rel_scaled(Ag, Ao),
+                                                              np.abs(gg - go).max() / np.abs(go).max()))
+    assert ws[-1] / ws[0] < 1e4
+    assert rel(Ao, At) < 1e-10 and rel_scaled(Ao, At) < 1e-10
+    assert rel(Ag, At) < 1e-10 and rel_scaled(Ag, At) < 1e-10
+    assert np.abs(gg - bt).max() / np.abs(bt).max() < 1e-10
