@@ -126,6 +126,10 @@ PROTOTYPES = {
                                c_int64_p]),
     "clic_add_bias": (C.c_int, [H, C.c_int32, C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int32]),
     "clic_add_gravity": (C.c_int, [H, c_double_p, c_double_p, C.c_int32]),
+    "clic_add_pose": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int64_p]),
+    "clic_add_local_velocity": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, C.c_double, c_int64_p]),
+    "clic_add_relative_rotation": (C.c_int, [H, C.c_double, C.c_double, c_double_p, c_double_p, c_int32_p]),
+    "clic_add_image_depth": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32]),
     "clic_add_global_velocity": (C.c_int, [H, C.c_double, c_double_p, C.c_double, c_int32_p]),
     "clic_add_image": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.c_int32,
                                  C.c_int32, c_int64_p]),

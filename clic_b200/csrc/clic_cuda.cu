@@ -337,6 +337,9 @@ struct clic_estimator {
   std::vector<std::unique_ptr<LoamBatch>> loam;
   std::vector<std::unique_ptr<ImuBatch>> imu;
   std::vector<VelFactorDesc> vel_factors;  // AddGlobalVelocityMeasurement (one per init solve in the reference)
+  std::vector<SmallFactor> small_f;        // pose / local velocity / relative rotation / image depth factors (§8f-4)
+  DevBuf d_small;
+  bool small_dirty = true;
   std::vector<std::unique_ptr<ImageBatch>> image;
   std::vector<BiasFac> bias_f;
   struct GravFac { double g0[3], sqrt_info[3]; int marg; };
@@ -975,6 +978,29 @@ void image_pass_fields(const clic_estimator* E, ImageStream& st, bool jac) {
   st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
 }
 
+// small_factors_kernel over E->small_f into (Hp, bp, cost2): after the assembly, or into the fused pass's addend system
+int launch_small_factors(clic_estimator* E, const double* state, double* Hp, double* bp, double* cost2, bool jac,
+                         const int* ctl) {
+  if (E->small_f.empty()) return CLIC_OK;
+  if (E->small_dirty) {
+    CU(E->d_small.ensure(E->small_f.size() * sizeof(SmallFactor)));
+    CU(cudaMemcpyAsync(E->d_small.p, E->small_f.data(), E->small_f.size() * sizeof(SmallFactor), cudaMemcpyHostToDevice,
+                       E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    E->small_dirty = false;
+  }
+  PassParams pp = pass_params(E, state, ctl);
+  SmallCols sc;
+  sc.knot_col = E->d_knot_col.as<int>();
+  sc.col_toff_imu = E->L.col_t_offset[CLIC_SENSOR_IMU];
+  sc.lm_col = E->L.n_free_landmarks > 0 ? E->d_lm_col.as<int32_t>() : nullptr;
+  const size_t smem = window_smem_doubles(E->K) * sizeof(double) + sizeof(SmallOut) + 16;
+  CU(launch_pdl(small_factors_kernel, 1, 128, smem, E->stream, E->d_small.as<SmallFactor>(), (int)E->small_f.size(), pp, sc,
+                Hp, bp, std::max(1, E->L.D), cost2, jac ? 1 : 0));
+  E->launches++;
+  return CLIC_OK;
+}
+
 // The pass as ONE persistent launch (pass_fused.cuh).  Terms that other kernels own (priors, the global-velocity
 // factor, more BiasFactors than the kernel takes) are evaluated first into a zeroed addend system that phase A adds
 // entry by entry, so they ride through the in-kernel exchange like everything else.
@@ -1014,7 +1040,8 @@ int run_pass_fused(clic_estimator* E, const double* state, bool jac, double* Hp,
     fa.n_bias = (int)bias_descs.size();
   }
   const bool have_priors = !E->priors.empty() && !E->opt.is_marg_state;
-  const bool need_addend = have_priors || !E->vel_factors.empty() || (!bias_descs.empty() && !bias_in_kernel);
+  const bool need_addend =
+      have_priors || !E->vel_factors.empty() || !E->small_f.empty() || (!bias_descs.empty() && !bias_in_kernel);
   double* addend = nullptr;
   if (need_addend) {
     addend = F.d_addend.as<double>();
@@ -1037,6 +1064,7 @@ int run_pass_fused(clic_estimator* E, const double* state, bool jac, double* Hp,
                     jac ? 1 : 0, ctl));
       E->launches++;
     }
+    if ((rc = launch_small_factors(E, state, Ha, ba, ca, jac, ctl))) return rc;
     E->prof_end();
   }
   if (F.stamps_on) fa.stamps = F.d_stamps.as<unsigned long long>();
@@ -1230,6 +1258,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
                   cost2, jac ? 1 : 0, ctl));
     E->launches++;
   }
+  if ((rc = launch_small_factors(E, state, Hp, bp, cost2, jac, ctl))) return rc;
   CU(cudaGetLastError());
   if (E->use_comm) {
     // the single exchange step of the path: sum of H | b | cost over the ranks' factor shards.
@@ -2272,6 +2301,114 @@ CLIC_API int clic_add_bias(clic_estimator* E, int32_t slot_i, int32_t slot_j, do
   f.marg_all = marg_all_bias;
   E->bias_f.push_back(f);
   E->bias_desc_dirty = true;
+  return CLIC_OK;
+}
+
+namespace {
+// MeasuredTimeToNs(IMUSensor) (trajectory_estimator.cpp:272-292) with the host arithmetic of the IMU adder; false: dropped
+bool imu_time_in_window(clic_estimator* E, double timestamp, int64_t* t_ns) {
+  const int S = CLIC_SENSOR_IMU;
+  const int64_t t_min = (int64_t)(E->minTime(S) * 1e9), t_max = (int64_t)(E->maxTime(S) * 1e9);
+  const int64_t pad = E->opt.lock_t_offset[S] ? 0 : E->opt.t_offset_padding_ns;
+  const int64_t t = (int64_t)(timestamp * 1e9);
+  *t_ns = t;
+  return !(t - pad < t_min || t + pad >= t_max);
+}
+void imu_offset_bounds(clic_estimator* E) {  // trajectory_estimator.cpp:355-361, 696-702
+  const int S = CLIC_SENSOR_IMU;
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->h_state[E->sl.off_toff() + S] - (double)E->opt.t_offset_padding_ns;
+    E->toff_hi[S] = E->h_state[E->sl.off_toff() + S] + (double)E->opt.t_offset_padding_ns;
+  }
+}
+}  // namespace
+
+CLIC_API int clic_add_pose(clic_estimator* E, int64_t n, const double* timestamp, const double* position,
+                           const double* orientation, const double info_vec[6], int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "pose factor in a marginalization estimator");
+  if (n > 0 && (!timestamp || !position || !orientation || !info_vec)) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  int64_t dropped = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t t;
+    if (!imu_time_in_window(E, timestamp[i], &t)) { dropped++; continue; }
+    SmallFactor f{};
+    f.kind = kSmallPose;
+    f.t_a = t;
+    for (int k = 0; k < 3; k++) f.d[k] = position[3 * i + k];
+    for (int k = 0; k < 4; k++) f.d[3 + k] = orientation[4 * i + k];
+    for (int k = 0; k < 6; k++) f.d[7 + k] = info_vec[k];
+    E->small_f.push_back(f);
+    imu_offset_bounds(E);
+  }
+  if (n_dropped) *n_dropped = dropped;
+  E->small_dirty = true;
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_local_velocity(clic_estimator* E, int64_t n, const double* timestamp, const double* local_v,
+                                     double weight, int64_t* n_dropped) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "local velocity factor in a marginalization estimator");
+  if (n > 0 && (!timestamp || !local_v)) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  int64_t dropped = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t t;
+    if (!imu_time_in_window(E, timestamp[i], &t)) { dropped++; continue; }
+    SmallFactor f{};
+    f.kind = kSmallLocalVelocity;
+    f.t_a = t;
+    for (int k = 0; k < 3; k++) f.d[k] = local_v[3 * i + k];
+    f.d[3] = weight;
+    E->small_f.push_back(f);
+    imu_offset_bounds(E);
+  }
+  if (n_dropped) *n_dropped = dropped;
+  E->small_dirty = true;
+  E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_relative_rotation(clic_estimator* E, double ta, double tb, const double S_BtoA[4],
+                                        const double info_vec[3], int32_t* added) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "relative rotation factor in a marginalization estimator");
+  if (!S_BtoA || !info_vec) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  if (added) *added = 0;
+  int64_t t_a, t_b;
+  if (!imu_time_in_window(E, ta, &t_a) || !imu_time_in_window(E, tb, &t_b)) return CLIC_OK;
+  SmallFactor f{};
+  f.kind = kSmallRelativeRotation;
+  f.t_a = t_a;  // used as they are: the factor has no time-offset parameter (trajectory_estimator.cpp:586-607)
+  f.t_b = t_b;
+  for (int k = 0; k < 4; k++) f.d[k] = S_BtoA[k];
+  for (int k = 0; k < 3; k++) f.d[4 + k] = info_vec[k];
+  E->small_f.push_back(f);
+  E->small_dirty = true;
+  E->layout_dirty = true;
+  if (added) *added = 1;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_add_image_depth(clic_estimator* E, const double p_i[3], const double p_j[3], const double S_CitoCj[4],
+                                  const double p_CiinCj[3], int32_t landmark) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "image depth factor in a marginalization estimator");
+  if (!p_i || !p_j || !S_CitoCj || !p_CiinCj) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  if (landmark < 0 || landmark >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
+  SmallFactor f{};
+  f.kind = kSmallImageDepth;
+  f.landmark = landmark;
+  for (int k = 0; k < 3; k++) { f.d[k] = p_i[k]; f.d[3 + k] = p_j[k]; f.d[10 + k] = p_CiinCj[k]; }
+  for (int k = 0; k < 4; k++) f.d[6 + k] = S_CitoCj[k];
+  f.d[13] = E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450.0 / 1.5;  // ImageDepthFactor::sqrt_info
+  f.loss_a = 1.0;                                                                  // CauchyLoss(1.0), ":842"
+  E->small_f.push_back(f);
+  E->lm_free[landmark] = 1;  // the inverse depth is a free parameter of the solve
+  E->small_dirty = true;
+  E->layout_dirty = true;
   return CLIC_OK;
 }
 

@@ -229,6 +229,15 @@ CLIC_HD M3 right_jacobian_inv(V3 phi) {
   return J;
 }
 
+// leftJacobianInvSO3 (src/utils/sophus_utils.hpp:279-307): the same series with -hat(phi)/2
+CLIC_HD M3 left_jacobian_inv(V3 phi) {
+  M3 J = right_jacobian_inv(phi);
+  M3 K = hat(phi);
+#pragma unroll
+  for (int i = 0; i < 9; i++) J.m[i] -= K.m[i];
+  return J;
+}
+
 // ---- uniform cubic B-spline blending (src/spline/spline_common.h:72-138), coefficients in closed form ----
 // cumulative M~ = 1/6 [[6,0,0,0],[5,3,-3,1],[1,3,3,-2],[0,0,0,1]], plain M = 1/6 [[1,-3,3,-1],[4,0,-6,3],[1,3,3,-3],[0,0,0,1]]
 CLIC_HD void blend_cum(double u, double lam[4]) {  // value coefficients lambda~_0..3 (lambda~_0 = 1)

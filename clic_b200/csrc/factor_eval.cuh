@@ -180,6 +180,8 @@ struct ImuShared {  // per AddIMUMeasurementAnalytic batch
   V3 bg, ba, gravity;
   double loss_a;     // Cauchy parameter (10, or 3 when marginalised); <= 0: no loss
   double inv_dt;     // 1e9 / dt_ns
+  bool want_toff = true;  // false: the IMU time offset is a constant of this solve — its Jacobian column (body
+                          // acceleration chain + jerk, ~200 FP64 instructions per factor) is never assembled: emit zeros
 };
 
 // IMUFactor::Evaluate on SplitSpineView::Evaluate.  Emits 6 rows of NC = 32 (solve) or 40 (marg: + gravity) columns:
@@ -237,7 +239,7 @@ CLIC_HD double imu_eval(const WindowView& W, int s, double u, V3 gyro_m, V3 acce
   M3 Rinv_m = qmat(R_inv);
   // time-offset column (trajectory_value_factor.h:268-291)
   V3 jt_top = mk(0, 0, 0), jt_bot = mk(0, 0, 0);
-  {
+  if (sh.want_toff) {
     double lamWW[4];
     blend_cum_d2(u, sh.inv_dt * sh.inv_dt, lamWW);
     V3 rv = mk(0, 0, 0), ra = mk(0, 0, 0);
@@ -396,6 +398,235 @@ CLIC_HD V3 so3_velocity_body(const WindowView& W, int s, double u, double inv_dt
     w = fma3(dl[i + 1], ldv(W.pair[s + i].delta), qrot(e, w));
   }
   return w;
+}
+
+// ---- rows of the two remaining rotation views (used by the factors of SURVEY.md §8f-4) ----
+// EvaluateRotation (so3_spline_view.h:65-117): forward products P_0 = R_s, P_i+1 = P_i exp(lambda_i+1 delta_i);
+// J_helper_i = lambda_i+1 mat(P_i+1) Jr(+lambda delta_i).  Rows a * d_val_d_knot[k].
+CLIC_HD void so3_rows_rot(const WindowView& W, int s, const So3Chain& C, const Q4 P[4], V3 a, V3 j[4]) {
+  V3 w0 = qrot_inv(P[0], a);
+  V3 t0 = row_times_lamJr(qrot_inv(P[1], a), W.pair[s + 0], C.lam[1], C.ca[0], C.cb[0], +1.0);
+  V3 t1 = row_times_lamJr(qrot_inv(P[2], a), W.pair[s + 1], C.lam[2], C.ca[1], C.cb[1], +1.0);
+  V3 t2 = row_times_lamJr(qrot_inv(P[3], a), W.pair[s + 2], C.lam[3], C.ca[2], C.cb[2], +1.0);
+  j[0] = w0 - vmat_t(t0, W.pair[s + 0].Jrinv);
+  j[1] = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
+  j[2] = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
+  j[3] = vmat(t2, W.pair[s + 2].Jrinv);
+}
+// EvaluateLogRT (so3_spline_view.h:263-321): inverse accumulation as in EvaluateRp (C from so3_chain_rp), but
+// J_helper_i = lambda_i+1 A_post_inv[i] Jr(-lambda delta_i) and d_val_d_knot[0] starts from A_post_inv[0].
+// The value R(t)^T = A_accum_inv R_s^-1 = conj(C.R).
+CLIC_HD void so3_rows_logrt(const WindowView& W, int s, const So3Chain& C, V3 a, V3 j[4]) {
+  V3 w0 = qrot_inv(C.acc[0], a), w1 = qrot_inv(C.acc[1], a), w2 = qrot_inv(C.acc[2], a);
+  V3 t0 = row_times_lamJr(w0, W.pair[s + 0], C.lam[1], C.ca[0], C.cb[0], -1.0);
+  V3 t1 = row_times_lamJr(w1, W.pair[s + 1], C.lam[2], C.ca[1], C.cb[1], -1.0);
+  V3 t2 = row_times_lamJr(w2, W.pair[s + 2], C.lam[3], C.ca[2], C.cb[2], -1.0);
+  j[0] = w0 - vmat_t(t0, W.pair[s + 0].Jrinv);
+  j[1] = vmat(t0, W.pair[s + 0].Jrinv) - vmat_t(t1, W.pair[s + 1].Jrinv);
+  j[2] = vmat(t1, W.pair[s + 1].Jrinv) - vmat_t(t2, W.pair[s + 2].Jrinv);
+  j[3] = vmat(t2, W.pair[s + 2].Jrinv);
+}
+
+// ---- the remaining adders of TrajectoryEstimator: a handful of factors per solve at most, evaluated
+// by ONE thread each into a small dense row set over the global columns the factor touches (small_factors_kernel).
+enum { kSmallPose = 0, kSmallLocalVelocity = 1, kSmallRelativeRotation = 2, kSmallImageDepth = 3 };
+struct SmallFactor {
+  int kind;
+  int landmark;        // image depth
+  long long t_a, t_b;  // measurement time(s) in ns (without offset)
+  double d[16];        // pose: p[3] q[4] info[6] | local velocity: v[3] w | relative rotation: S_BtoA[4] info[3]
+                       // image depth: p_i[3] p_j[3] S_CitoCj[4] p_CiinCj[3] sqrt_info
+  double loss_a;       // Cauchy parameter, <= 0: none
+};
+constexpr int kSmallMaxRows = 6, kSmallMaxCols = 56;
+struct SmallOut {
+  int nres, ncols;
+  double r[kSmallMaxRows];
+  int gcol[kSmallMaxCols];                  // distinct global columns (constant blocks are never entered)
+  double J[kSmallMaxRows][kSmallMaxCols];
+  CLIC_HD void reset(int n) {
+    nres = n;
+    ncols = 0;
+    for (int i = 0; i < kSmallMaxRows; i++) r[i] = 0.0;
+  }
+  CLIC_HD void add(int row, int g, double v) {  // J[row][column of g] += v; a knot shared by two segments accumulates
+    if (g < 0) return;
+    int c = 0;
+    while (c < ncols && gcol[c] != g) c++;
+    if (c == ncols) {
+      if (ncols == kSmallMaxCols) return;
+      gcol[ncols++] = g;
+      for (int i = 0; i < kSmallMaxRows; i++) J[i][c] = 0.0;
+    }
+    J[row][c] += v;
+  }
+};
+struct SmallCols {      // where a factor's parameter blocks sit in H (device copies of the layout)
+  const int* knot_col;  // [K] column of the knot's dtheta (dp = +3), -1 constant
+  int col_toff_imu;     // -1 constant
+  const int* lm_col;    // per landmark, -1 constant (nullptr: none free)
+};
+
+// IMUPoseFactor::Evaluate (trajectory_value_factor.h:323-427).  False: the corrected time left the window.
+CLIC_HD bool small_pose_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K, double toff,
+                             const SmallCols& sc, SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a + (long long)toff, t0_ns, dt_ns, K, &s, &u)) return false;
+  const double inv_dt = 1e9 / double(dt_ns);
+  const V3 p_meas = ldv(f.d);
+  const Q4 q_meas = ldq(f.d + 3);
+  const double* info = f.d + 7;
+  So3Chain C;
+  Q4 P[4];
+  so3_chain_rtp(W, s, u, &C, P);  // forward accumulation: R(t) = P[3]
+  double c[4];
+  blend_plain(u, c);
+  V3 pos = mk(0, 0, 0);
+  for (int k = 0; k < 4; k++) pos = fma3(c[k], ldv(W.kp + 3 * (s + k)), pos);
+  const V3 res_R = so3_log(so3_mul(C.R, qconj(q_meas)));
+  const V3 res_p = pos - p_meas;
+  o->reset(6);
+  const M3 Jrot = left_jacobian_inv(res_R);
+  for (int r = 0; r < 3; r++) {
+    V3 j[4];
+    so3_rows_rot(W, s, C, P, mk(Jrot.m[3 * r], Jrot.m[3 * r + 1], Jrot.m[3 * r + 2]), j);
+    for (int k = 0; k < 4; k++) {
+      const int g = sc.knot_col[s + k];
+      if (g < 0) continue;
+      o->add(r, g + 0, info[r] * j[k].x);
+      o->add(r, g + 1, info[r] * j[k].y);
+      o->add(r, g + 2, info[r] * j[k].z);
+      o->add(3 + r, g + 3 + r, info[3 + r] * c[k]);
+    }
+  }
+  if (sc.col_toff_imu >= 0) {  // ":410-426": as written — a quaternion made from the SKEW matrix of the body rate
+    const V3 gyro = so3_velocity_body(W, s, u, inv_dt);
+    double d1[4];
+    blend_plain_d1(u, inv_dt, d1);
+    V3 vel = mk(0, 0, 0);
+    for (int k = 0; k < 4; k++) vel = fma3(d1[k], ldv(W.kp + 3 * (s + k)), vel);
+    // Eigen::Quaterniond(hat(gyro)): trace 0, zero diagonal -> i = 0: (x, y, z, w) = (1/2, 0, 0, gyro.x), normalised
+    const double nq = sqrt(0.25 + gyro.x * gyro.x);
+    Q4 qg; qg.x = 0.5 / nq; qg.y = 0.0; qg.z = 0.0; qg.w = gyro.x / nq;
+    const V3 jr = so3_log(so3_mul(so3_mul(C.R, qg), qconj(q_meas)));
+    o->add(0, sc.col_toff_imu, 1e-9 * info[0] * jr.x);
+    o->add(1, sc.col_toff_imu, 1e-9 * info[1] * jr.y);
+    o->add(2, sc.col_toff_imu, 1e-9 * info[2] * jr.z);
+    o->add(3, sc.col_toff_imu, 1e-9 * info[3] * vel.x);
+    o->add(4, sc.col_toff_imu, 1e-9 * info[4] * vel.y);
+    o->add(5, sc.col_toff_imu, 1e-9 * info[5] * vel.z);
+  }
+  o->r[0] = info[0] * res_R.x; o->r[1] = info[1] * res_R.y; o->r[2] = info[2] * res_R.z;
+  o->r[3] = info[3] * res_p.x; o->r[4] = info[4] * res_p.y; o->r[5] = info[5] * res_p.z;
+  return true;
+}
+
+// LocalVelocityFactor::Evaluate (trajectory_value_factor.h:464-566)
+CLIC_HD bool small_local_velocity_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                       double toff, const SmallCols& sc, SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a + (long long)toff, t0_ns, dt_ns, K, &s, &u)) return false;
+  const double inv_dt = 1e9 / double(dt_ns);
+  const V3 v = ldv(f.d);
+  const double w = f.d[3];
+  So3Chain C;
+  so3_chain_rp(W, s, u, &C);
+  double d1[4];
+  blend_plain_d1(u, inv_dt, d1);
+  V3 vel = mk(0, 0, 0);
+  for (int k = 0; k < 4; k++) vel = fma3(d1[k], ldv(W.kp + 3 * (s + k)), vel);
+  const V3 res = qrot(C.R, v) - vel;
+  o->reset(3);
+  for (int r = 0; r < 3; r++) {
+    // row r of jac_lhs_R = -R hat(v):  (row r of R) x v negated = v x R_r
+    const V3 Rr = qrot_inv(C.R, mk(r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0));
+    V3 j[4];
+    so3_rows_rp(W, s, C, cross(v, Rr), j);
+    for (int k = 0; k < 4; k++) {
+      const int g = sc.knot_col[s + k];
+      if (g < 0) continue;
+      o->add(r, g + 0, w * j[k].x);
+      o->add(r, g + 1, w * j[k].y);
+      o->add(r, g + 2, w * j[k].z);
+      o->add(r, g + 3 + r, -w * d1[k]);
+    }
+  }
+  if (sc.col_toff_imu >= 0) {  // ":548-563": rot_dot v - accel, rot_dot = R hat(omega)
+    const V3 gyro = so3_velocity_body(W, s, u, inv_dt);
+    double d2[4];
+    blend_plain_d2(u, inv_dt * inv_dt, d2);
+    V3 acc = mk(0, 0, 0);
+    for (int k = 0; k < 4; k++) acc = fma3(d2[k], ldv(W.kp + 3 * (s + k)), acc);
+    const V3 jt = qrot(C.R, cross(gyro, v)) - acc;
+    o->add(0, sc.col_toff_imu, 1e-9 * w * jt.x);
+    o->add(1, sc.col_toff_imu, 1e-9 * w * jt.y);
+    o->add(2, sc.col_toff_imu, 1e-9 * w * jt.z);
+  }
+  o->r[0] = w * res.x; o->r[1] = w * res.y; o->r[2] = w * res.z;
+  return true;
+}
+
+// RelativeOrientationFactor::Evaluate (trajectory_value_factor.h:990-1064).  R(t_b)^T is taken as the quaternion product
+// itself; the reference re-normalises it through a rotation matrix (so3_spline_view.h:303-306): 1e-16 apart.
+CLIC_HD bool small_relative_rotation_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                          const SmallCols& sc, SmallOut* o) {
+  int sa = 0, sb = 0;
+  double ua = 0.0, ub = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &sa, &ua) || !index_ns(f.t_b, t0_ns, dt_ns, K, &sb, &ub)) return false;
+  const Q4 S_BtoA = ldq(f.d);
+  const double* info = f.d + 4;
+  So3Chain Ca, Cb;
+  Q4 Pa[4];
+  so3_chain_rtp(W, sa, ua, &Ca, Pa);  // R(t_a), forward
+  so3_chain_rp(W, sb, ub, &Cb);       // inverse accumulation at t_b
+  const Q4 RbT = qconj(Cb.R);
+  const V3 res = so3_log(so3_mul(so3_mul(RbT, Ca.R), S_BtoA));
+  o->reset(3);
+  const M3 Jrot = left_jacobian_inv(res);
+  for (int r = 0; r < 3; r++) {
+    const V3 Jr = mk(Jrot.m[3 * r], Jrot.m[3 * r + 1], Jrot.m[3 * r + 2]);
+    V3 ja[4], jb[4];
+    so3_rows_rot(W, sa, Ca, Pa, qrot_inv(RbT, Jr), ja);  // row r of Jrot mat(R_b^T)
+    so3_rows_logrt(W, sb, Cb, -Jr, jb);                  // row r of -Jrot
+    for (int k = 0; k < 4; k++) {
+      const int ga = sc.knot_col[sa + k], gb = sc.knot_col[sb + k];
+      if (ga >= 0) {
+        o->add(r, ga + 0, info[r] * ja[k].x);
+        o->add(r, ga + 1, info[r] * ja[k].y);
+        o->add(r, ga + 2, info[r] * ja[k].z);
+      }
+      if (gb >= 0) {
+        o->add(r, gb + 0, info[r] * jb[k].x);
+        o->add(r, gb + 1, info[r] * jb[k].y);
+        o->add(r, gb + 2, info[r] * jb[k].z);
+      }
+    }
+  }
+  o->r[0] = info[0] * res.x; o->r[1] = info[1] * res.y; o->r[2] = info[2] * res.z;
+  return true;
+}
+
+// ImageDepthFactor::Evaluate (image_feature_factor.h:666-693)
+CLIC_HD bool small_image_depth_eval(const SmallFactor& f, double d_inv, const SmallCols& sc, SmallOut* o) {
+  const V3 p_i = ldv(f.d), p_j = ldv(f.d + 3);
+  const Q4 S = ldq(f.d + 6);
+  const V3 p_CiinCj = ldv(f.d + 10);
+  const double sqrt_info = f.d[13];
+  const V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
+  const V3 x_j = qrot(S, x_ci) + p_CiinCj;
+  const double dj = 1.0 / x_j.z;
+  o->reset(2);
+  const int g = sc.lm_col ? sc.lm_col[f.landmark] : -1;
+  if (g >= 0) {
+    const V3 Jd = (-1.0 / d_inv) * qrot(S, x_ci);
+    o->add(0, g, sqrt_info * (dj * Jd.x - dj * dj * x_j.x * Jd.z));
+    o->add(1, g, sqrt_info * (dj * Jd.y - dj * dj * x_j.y * Jd.z));
+  }
+  o->r[0] = sqrt_info * (x_j.x * dj - p_j.x);
+  o->r[1] = sqrt_info * (x_j.y * dj - p_j.y);
+  return true;
 }
 
 struct ImageShared {

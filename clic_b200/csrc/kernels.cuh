@@ -857,6 +857,7 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
   sh.gravity = mk(gr[0], gr[1], gr[2]);
   sh.loss_a = st.loss_a;
   sh.inv_dt = 1e9 / double(pp.dt_ns);
+  sh.want_toff = MARG || st.toff_free;
   const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 0];  // (int64_t)time_offset_in_ns, trajectory_value_factor.h:175
 
   WarpAcc<NT> acc;
@@ -1560,6 +1561,75 @@ __global__ void velocity_factor_kernel(VelFactorDesc vf, const double* state, St
   } else if (t == 60 && col_toff >= 0) {
     H[(size_t)col_toff * D + col_toff] += rp * (jt[0] * jt[0] + jt[1] * jt[1] + jt[2] * jt[2]);
     b[col_toff] += rp * (jt[0] * res[0] + jt[1] * res[1] + jt[2] * res[2]);
+  }
+}
+
+// The remaining adders of TrajectoryEstimator: pose, local-velocity, relative-rotation and image-depth
+// factors — a handful per solve at most.  One CTA walks them in add order: thread 0 evaluates a factor into a small
+// dense row set over the distinct global columns it touches (factor_eval.cuh), then every thread owns some of the
+// (column, column) pairs and adds J~^T J~, J~^T r~ into H, b: no atomics, fixed order.  Runs after the assembly (or
+// into the addend system of the fused pass), like velocity_factor_kernel.
+__global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* fs, int n, PassParams pp, SmallCols sc,
+                                                            double* H, double* b, int D, double* cost2, int jac) {
+  pdl_wait();
+  pdl_trigger();
+  if (pp.ctl && pp.ctl[0]) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  SmallOut* o = reinterpret_cast<SmallOut*>(rest);
+  __shared__ int s_ok;
+  __shared__ double s_cost[2];
+  if (threadIdx.x == 0) s_cost[0] = s_cost[1] = 0.0;
+  const double toff_imu = pp.state[pp.sl.off_toff() + 0];
+  const double* invd = pp.state + pp.sl.off_invd();
+  for (int i = 0; i < n; i++) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const SmallFactor f = fs[i];
+      bool ok = false;
+      switch (f.kind) {
+        case kSmallPose: ok = small_pose_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, toff_imu, sc, o); break;
+        case kSmallLocalVelocity: ok = small_local_velocity_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, toff_imu, sc, o); break;
+        case kSmallRelativeRotation: ok = small_relative_rotation_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, sc, o); break;
+        default: ok = small_image_depth_eval(f, invd[f.landmark], sc, o); break;
+      }
+      if (ok) {
+        double sq = 0.0;
+        for (int r = 0; r < o->nres; r++) sq += o->r[r] * o->r[r];
+        double rho = sq, scale = 1.0;
+        if (f.loss_a > 0.0) scale = cauchy_scale(sq, f.loss_a, &rho);  // Corrector: rho'' < 0 -> pure sqrt(rho') scaling
+        if (scale != 1.0) {
+          for (int r = 0; r < o->nres; r++) {
+            o->r[r] *= scale;
+            for (int c = 0; c < o->ncols; c++) o->J[r][c] *= scale;
+          }
+        }
+        s_cost[o->ncols > 0 ? 0 : 1] += 0.5 * rho;
+      }
+      s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_ok || !jac) continue;
+    const int nc = o->ncols, nr = o->nres;
+    for (int t = threadIdx.x; t < nc * nc + nc; t += blockDim.x) {
+      if (t < nc * nc) {
+        const int a = t / nc, c = t - a * nc;
+        double v = 0.0;
+        for (int r = 0; r < nr; r++) v += o->J[r][a] * o->J[r][c];
+        H[(size_t)o->gcol[a] * D + o->gcol[c]] += v;
+      } else {
+        const int a = t - nc * nc;
+        double v = 0.0;
+        for (int r = 0; r < nr; r++) v += o->J[r][a] * o->r[r];
+        b[o->gcol[a]] += v;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cost2[0] += s_cost[0];
+    cost2[1] += s_cost[1];
   }
 }
 

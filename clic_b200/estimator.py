@@ -218,6 +218,34 @@ class TrajectoryEstimator:
         g, info_vec = f64(gravity), f64(info_vec)
         _check(self.lib, self.lib.clic_add_gravity(self.h, dptr(g), dptr(info_vec), int(bool(marg_this_factor))))
 
+    # ---- trajectory_estimator.h:150-151 (IMUPoseFactor) ----
+    def AddPoseMeasurementAnalytic(self, timestamp, position, orientation, info_vec):
+        """Batched over pose measurements (orientation (n,4) xyzw); returns the number dropped (outside the window)."""
+        t, p, q, info_vec = f64(timestamp), f64(position), f64(orientation), f64(info_vec)
+        nd = C.c_int64(0)
+        _check(self.lib, self.lib.clic_add_pose(self.h, len(t), dptr(t), dptr(p), dptr(q), dptr(info_vec), C.byref(nd)))
+        return nd.value
+
+    # ---- trajectory_estimator.h:183-185 (LocalVelocityFactor) ----
+    def AddLocalVelocityMeasurementAnalytic(self, timestamp, local_v, weight):
+        t, v = f64(timestamp), f64(local_v)
+        nd = C.c_int64(0)
+        _check(self.lib, self.lib.clic_add_local_velocity(self.h, len(t), dptr(t), dptr(v), float(weight), C.byref(nd)))
+        return nd.value
+
+    # ---- trajectory_estimator.h:174-175 (RelativeOrientationFactor) ----
+    def AddRelativeRotationAnalytic(self, ta, tb, S_BtoA, info_vec):
+        S_BtoA, info_vec = f64(S_BtoA), f64(info_vec)
+        added = C.c_int32(0)
+        _check(self.lib, self.lib.clic_add_relative_rotation(self.h, float(ta), float(tb), dptr(S_BtoA), dptr(info_vec),
+                                                             C.byref(added)))
+        return bool(added.value)
+
+    # ---- trajectory_estimator.h:201-204 (ImageDepthFactor) ----
+    def AddImageDepthAnalytic(self, p_i, p_j, S_CitoCj, p_CiinCj, landmark):
+        a = [f64(p_i), f64(p_j), f64(S_CitoCj), f64(p_CiinCj)]
+        _check(self.lib, self.lib.clic_add_image_depth(self.h, *[dptr(x) for x in a], int(landmark)))
+
     # ---- trajectory_estimator.cpp:609-664 ----
     def AddGlobalVelocityMeasurement(self, timestamp, global_v, vel_weight):
         """IMUGlobalVelocityFactor at one timestamp; returns False when it falls outside the window."""

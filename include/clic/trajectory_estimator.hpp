@@ -44,6 +44,11 @@ struct IMUData {  // src/utils/parameter_struct.h:52-58
   double timestamp = 0;
   Vec3d gyro{}, accel{};
 };
+struct PoseData {  // src/utils/parameter_struct.h:60-69
+  double timestamp = 0;
+  Vec3d position{};
+  SO3d orientation;
+};
 struct ExtrinsicParam {  // src/utils/parameter_struct.h:108-150 (the fields the hot path reads)
   SO3d so3;
   Vec3d p{};
@@ -377,6 +382,59 @@ class TrajectoryEstimator {
     if (last > fixed_control_point_index_) fixed_control_point_index_ = last;
   }
 
+  // trajectory_estimator.h:150-151 (IMUPoseFactor); measurements outside the window are dropped like the reference's
+  // early return (trajectory_estimator.cpp:329)
+  void AddPoseMeasurementAnalytic(const PoseData& pose_data, const Vec6d& info_vec) {
+    if (pose_f_.empty() || pose_f_.back().info != info_vec) {
+      PoseBatch b;
+      b.info = info_vec;
+      pose_f_.push_back(b);
+    }
+    PoseBatch& b = pose_f_.back();
+    b.t.push_back(pose_data.timestamp);
+    b.p.insert(b.p.end(), pose_data.position.begin(), pose_data.position.end());
+    b.q.insert(b.q.end(), pose_data.orientation.q.begin(), pose_data.orientation.q.end());
+  }
+  // trajectory_estimator.h:146-147 / .cpp:312-323: the pose at the trajectory's start time, weights 100
+  void AddStartTimePose(const PoseData& pose) {
+    PoseData pose_temp = pose;
+    pose_temp.timestamp = 1e-9 * (double)trajectory_->t0_ns - 1e-9 * trajectory_->EP_StoI[LiDARSensor].t_offset_ns;
+    AddPoseMeasurementAnalytic(pose_temp, Vec6d{{100, 100, 100, 100, 100, 100}});
+  }
+  // trajectory_estimator.h:183-185 (LocalVelocityFactor)
+  void AddLocalVelocityMeasurementAnalytic(const double timestamp, const Vec3d& local_v, double weight) {
+    LocalVel f;
+    f.t = timestamp;
+    f.v = local_v;
+    f.w = weight;
+    lvel_f_.push_back(f);
+  }
+  // trajectory_estimator.h:174-175 (RelativeOrientationFactor)
+  void AddRelativeRotationAnalytic(double ta, double tb, const SO3d& S_BtoA, const Vec3d& info_vec) {
+    RelRot f;
+    f.ta = ta;
+    f.tb = tb;
+    f.S = S_BtoA;
+    f.info = info_vec;
+    relrot_f_.push_back(f);
+  }
+  // trajectory_estimator.h:201-204 (ImageDepthFactor, CauchyLoss(1))
+  void AddImageDepthAnalytic(const Vec3d& p_i, const Vec3d& p_j, const SO3d& S_CitoCj, const Vec3d& p_CiinCj,
+                             double* inv_depth) {
+    auto it = landmark_.find(inv_depth);
+    if (it == landmark_.end()) {
+      it = landmark_.emplace(inv_depth, (int)landmark_ptr_.size()).first;
+      landmark_ptr_.push_back(inv_depth);
+    }
+    ImgDepth f;
+    f.pi = p_i;
+    f.pj = p_j;
+    f.S = S_CitoCj;
+    f.p = p_CiinCj;
+    f.lm = it->second;
+    depth_f_.push_back(f);
+  }
+
   // trajectory_estimator.h:164-165
   void AddGravityFactor(double* gravity, const Vec3d& info_vec, bool marg_this_factor = false) {
     gravity_ = gravity;
@@ -483,6 +541,24 @@ class TrajectoryEstimator {
     Vec3d g0{}, info{};
     bool marg = false;
   };
+  struct PoseBatch {
+    std::vector<double> t, p, q;
+    Vec6d info{};
+  };
+  struct LocalVel {
+    double t = 0, w = 0;
+    Vec3d v{};
+  };
+  struct RelRot {
+    double ta = 0, tb = 0;
+    SO3d S;
+    Vec3d info{};
+  };
+  struct ImgDepth {
+    Vec3d pi{}, pj{}, p{};
+    SO3d S;
+    int lm = 0;
+  };
 
   static void check(int rc) {
     if (rc != CLIC_OK) throw std::runtime_error(std::string("clic: ") + clic_last_error());
@@ -584,6 +660,11 @@ class TrajectoryEstimator {
                                   nullptr));
     for (auto& f : bias_f_) check(clic_add_bias(h_, f.i, f.j, f.dt, f.info.data(), f.marg, f.marg_all));
     for (auto& f : grav_f_) check(clic_add_gravity(h_, f.g0.data(), f.info.data(), f.marg));
+    for (auto& b : pose_f_)
+      check(clic_add_pose(h_, (int64_t)b.t.size(), b.t.data(), b.p.data(), b.q.data(), b.info.data(), nullptr));
+    for (auto& f : lvel_f_) check(clic_add_local_velocity(h_, 1, &f.t, f.v.data(), f.w, nullptr));
+    for (auto& f : relrot_f_) check(clic_add_relative_rotation(h_, f.ta, f.tb, f.S.data(), f.info.data(), nullptr));
+    for (auto& f : depth_f_) check(clic_add_image_depth(h_, f.pi.data(), f.pj.data(), f.S.data(), f.p.data(), f.lm));
     for (auto& f : vel_f_) check(clic_add_global_velocity(h_, f.t, f.v.data(), f.w, nullptr));
     for (auto& b : scans_) {
       int64_t nl = 0, np = 0;
@@ -626,6 +707,10 @@ class TrajectoryEstimator {
   std::vector<ImageBatch> image_;
   std::vector<BiasFac> bias_f_;
   std::vector<GravFac> grav_f_;
+  std::vector<PoseBatch> pose_f_;
+  std::vector<LocalVel> lvel_f_;
+  std::vector<RelRot> relrot_f_;
+  std::vector<ImgDepth> depth_f_;
   std::vector<VelFac> vel_f_;
   std::vector<PriorRef> priors_;
   std::vector<std::pair<double*, double*>> bias_ptr_;

@@ -232,6 +232,30 @@ CLIC_API int clic_add_gravity(clic_estimator* h, const double gravity[3], const 
 CLIC_API int clic_add_global_velocity(clic_estimator* h, double timestamp, const double global_v[3], double vel_weight,
                                       int32_t* added);
 
+/* ---- the remaining adders of TrajectoryEstimator: factors the shipped pipeline adds a handful of
+ * per solve at most; they run on one CTA after the assembly (small_factors_kernel), not through the streaming kernels.
+ * None of them is routed to the marginalization set by the reference's adders (no marg_this_factor argument), so a
+ * marginalization estimator refuses them. ---- */
+/* AddPoseMeasurementAnalytic (trajectory_estimator.cpp:326-368) with IMUPoseFactor (trajectory_value_factor.h:303-433):
+ * r = diag(info_vec) [log(R(t') q_meas^-1); p(t') - p_meas], t' = t + (int64) t_offset_IMU; Jacobians on the 4+4 knots
+ * of the segment and on the IMU time offset; no loss.  orientation: 4n (x,y,z,w). */
+CLIC_API int clic_add_pose(clic_estimator* h, int64_t n, const double* timestamp, const double* position /*3n*/,
+                           const double* orientation /*4n*/, const double info_vec[6], int64_t* n_dropped);
+/* AddLocalVelocityMeasurementAnalytic (trajectory_estimator.cpp:666-708) with LocalVelocityFactor
+ * (trajectory_value_factor.h:435-571): r = weight (R(t') v_local - p'(t')); no loss. */
+CLIC_API int clic_add_local_velocity(clic_estimator* h, int64_t n, const double* timestamp, const double* local_v /*3n*/,
+                                     double weight, int64_t* n_dropped);
+/* AddRelativeRotationAnalytic (trajectory_estimator.cpp:586-607) with RelativeOrientationFactor
+ * (trajectory_value_factor.h:966-1075): r = diag(info_vec) log(R(t_b)^T R(t_a) S_BtoA); rotation knots of both
+ * segments; no loss.  *added = 0 when either time is outside the window. */
+CLIC_API int clic_add_relative_rotation(clic_estimator* h, double ta, double tb, const double S_BtoA[4],
+                                        const double info_vec[3], int32_t* added);
+/* AddImageDepthAnalytic (trajectory_estimator.cpp:830-852) with ImageDepthFactor (image_feature_factor.h:658-707):
+ * reprojection of a feature between two FIXED camera poses, the landmark's inverse depth the only parameter (it
+ * becomes a free parameter of the solve), CauchyLoss(1), sqrt_info = clic_options::image_sqrt_info. */
+CLIC_API int clic_add_image_depth(clic_estimator* h, const double p_i[3], const double p_j[3], const double S_CitoCj[4],
+                                  const double p_CiinCj[3], int32_t landmark);
+
 /* AddImageFeatureAnalytic (trajectory_estimator.cpp:752-829), batched; landmark[i] indexes
  * clic_window_desc::inv_depth.  Loss CauchyLoss(marg ? 1 : 2) (":806-810"). */
 CLIC_API int clic_add_image(clic_estimator* h, int64_t n, const double* t_i, const double* p_i /*3n*/,

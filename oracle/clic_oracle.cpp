@@ -1307,6 +1307,111 @@ CLIC_API int clic_add_gravity(clic_estimator* E, const double gravity[3], const 
   return CLIC_OK;
 }
 
+// One measurement time at the IMU offset -> the (padded) spline meta of the pose / local-velocity adders
+// (trajectory_estimator.cpp:330-344, 671-684) and the time-offset bounds (":355-361, :696-702")
+static void imu_time_meta(clic_estimator* E, int64_t time_ns, SplineMeta& meta) {
+  const int S = CLIC_SENSOR_IMU;
+  int64_t t_corrected_ns = (int64_t)(time_ns + E->x.t_offset_ns[S]);
+  if (E->opt.lock_t_offset[S])
+    E->CaculateSplineMeta({{t_corrected_ns, t_corrected_ns}}, meta);
+  else
+    E->CaculateSplineMeta(
+        {{t_corrected_ns - E->opt.t_offset_padding_ns, t_corrected_ns + E->opt.t_offset_padding_ns}}, meta);
+  if (!E->opt.lock_t_offset[S] && !E->bounds_toff[S]) {
+    double t_ns = (double)E->opt.t_offset_padding_ns;
+    E->bounds_toff[S] = true;
+    E->toff_lo[S] = E->x.t_offset_ns[S] - t_ns;
+    E->toff_hi[S] = E->x.t_offset_ns[S] + t_ns;
+  }
+}
+
+// AddPoseMeasurementAnalytic — trajectory_estimator.cpp:326-368 (IMUPoseFactor, no loss)
+CLIC_API int clic_add_pose(clic_estimator* E, int64_t n, const double* timestamp, const double* position,
+                           const double* orientation, const double info_vec[6], int64_t* n_dropped) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "pose factor in a marginalization estimator");
+  int64_t dropped = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t time_ns;
+    if (!E->MeasuredTimeToNs(CLIC_SENSOR_IMU, timestamp[i], time_ns)) { dropped++; continue; }
+    SplineMeta meta;
+    imu_time_meta(E, time_ns, meta);
+    PoseData pd{timestamp[i], load_v(position + 3 * i), load_q(orientation + 4 * i)};
+    ResidualBlock rb;
+    rb.cost.reset(new IMUPoseFactor(time_ns, pd, meta.segments.at(0), info_vec));
+    E->AddControlPoints(meta, rb.refs, false);
+    E->AddControlPoints(meta, rb.refs, true);
+    rb.refs.push_back({CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU});
+    rb.rtype = 0;
+    E->blocks.push_back(std::move(rb));
+  }
+  if (n_dropped) *n_dropped = dropped;
+  return CLIC_OK;
+}
+
+// AddLocalVelocityMeasurementAnalytic — trajectory_estimator.cpp:666-708 (LocalVelocityFactor, no loss)
+CLIC_API int clic_add_local_velocity(clic_estimator* E, int64_t n, const double* timestamp, const double* local_v,
+                                     double weight, int64_t* n_dropped) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "local velocity factor in a marginalization estimator");
+  int64_t dropped = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t time_ns;
+    if (!E->MeasuredTimeToNs(CLIC_SENSOR_IMU, timestamp[i], time_ns)) { dropped++; continue; }
+    SplineMeta meta;
+    imu_time_meta(E, time_ns, meta);
+    ResidualBlock rb;
+    rb.cost.reset(new LocalVelocityFactor(time_ns, load_v(local_v + 3 * i), meta.segments.at(0), weight));
+    E->AddControlPoints(meta, rb.refs, false);
+    E->AddControlPoints(meta, rb.refs, true);
+    rb.refs.push_back({CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU});
+    rb.rtype = 9;
+    E->blocks.push_back(std::move(rb));
+  }
+  if (n_dropped) *n_dropped = dropped;
+  return CLIC_OK;
+}
+
+// AddRelativeRotationAnalytic — trajectory_estimator.cpp:586-607 (RelativeOrientationFactor, no loss)
+CLIC_API int clic_add_relative_rotation(clic_estimator* E, double ta, double tb, const double S_BtoA[4],
+                                        const double info_vec[3], int32_t* added) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "relative rotation factor in a marginalization estimator");
+  if (added) *added = 0;
+  int64_t time_a_ns, time_b_ns;
+  if (!E->MeasuredTimeToNs(CLIC_SENSOR_IMU, ta, time_a_ns)) return CLIC_OK;
+  if (!E->MeasuredTimeToNs(CLIC_SENSOR_IMU, tb, time_b_ns)) return CLIC_OK;
+  int64_t t_min = std::min(time_a_ns, time_b_ns), t_max = std::max(time_a_ns, time_b_ns);
+  SplineMeta meta;
+  E->CaculateSplineMeta({{t_min, t_min}, {t_max, t_max}}, meta);
+  ResidualBlock rb;
+  rb.cost.reset(new RelativeOrientationFactor(load_q(S_BtoA), time_a_ns, time_b_ns, meta, info_vec));
+  E->AddControlPoints(meta, rb.refs, false);
+  rb.rtype = 0;
+  E->blocks.push_back(std::move(rb));
+  if (added) *added = 1;
+  return CLIC_OK;
+}
+
+// AddImageDepthAnalytic — trajectory_estimator.cpp:830-852 (ImageDepthFactor, CauchyLoss(1); the inverse depth is a
+// free parameter of the solve)
+CLIC_API int clic_add_image_depth(clic_estimator* E, const double p_i[3], const double p_j[3], const double S_CitoCj[4],
+                                  const double p_CiinCj[3], int32_t landmark) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "image depth factor in a marginalization estimator");
+  if (landmark < 0 || landmark >= E->n_lm) return fail(CLIC_ERR_BAD_ARGUMENT, "landmark index out of range");
+  ResidualBlock rb;
+  rb.cost.reset(new ImageDepthFactor(load_v(p_i), load_v(p_j), load_q(S_CitoCj), load_v(p_CiinCj),
+                                     E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450. / 1.5));
+  rb.refs.push_back({CLIC_BLOCK_INV_DEPTH, landmark});
+  E->lm_free[landmark] = 1;
+  rb.has_loss = true;
+  rb.loss_a = 1.0;
+  rb.rtype = 11;
+  E->blocks.push_back(std::move(rb));
+  return CLIC_OK;
+}
+
 CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, const double* p_i, const double* t_j,
                             const double* p_j, const int32_t* landmark, int32_t fixed_depth,
                             int32_t marg_this_feature, int64_t* n_dropped) {

@@ -217,6 +217,241 @@ struct IMUFactor : CostFunction {
 };
 
 // BiasFactor — trajectory_value_factor.h:65-126
+// PoseData — src/utils/parameter_struct.h (timestamp, position, orientation)
+struct PoseData {
+  double timestamp;
+  Vec3 position;
+  Quat orientation;
+};
+
+// IMUPoseFactor — src/estimator/factor/analytic_diff/trajectory_value_factor.h:303-433
+struct IMUPoseFactor : CostFunction {
+  int64_t time_ns_;
+  PoseData pose_data_;
+  SegmentMeta meta_;
+  double info_vec_[6];
+  IMUPoseFactor(int64_t time_ns, const PoseData& pose, const SegmentMeta& meta, const double info_vec[6])
+      : time_ns_(time_ns), pose_data_(pose), meta_(meta) {
+    for (int i = 0; i < 6; i++) info_vec_[i] = info_vec[i];
+    num_residuals = 6;
+    size_t knot_num = meta_.NumParameters();
+    for (size_t i = 0; i < knot_num; ++i) block_sizes.push_back(4);
+    for (size_t i = 0; i < knot_num; ++i) block_sizes.push_back(3);
+    block_sizes.push_back(1);  // time_offset
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    So3Jacobian J_R;
+    RdJacobian J_p;
+    size_t knot_num = meta_.NumParameters();
+    size_t P_offset = knot_num;
+    double time_offset_in_ns = parameters[2 * knot_num][0];
+    int64_t t_corrected = time_ns_ + (int64_t)time_offset_in_ns;
+    Quat S_ItoG = so3_evaluate_rotation(t_corrected, meta_, parameters, jacobians ? &J_R : nullptr);
+    Vec3 p_IinG = rd_evaluate(0, t_corrected, meta_, parameters + P_offset, jacobians ? &J_p : nullptr);
+    Vec3 res_R = so3_log(so3_mul(S_ItoG, qconj(pose_data_.orientation)));
+    Vec3 res_p = p_IinG - pose_data_.position;
+    if (jacobians) {
+      for (size_t i = 0; i < knot_num; ++i) {
+        if (jacobians[i])
+          for (int c = 0; c < 24; c++) jacobians[i][c] = 0;
+        if (jacobians[i + knot_num])
+          for (int c = 0; c < 18; c++) jacobians[i + knot_num][c] = 0;
+      }
+      Mat3 Jrot = left_jacobian_inv_so3(res_R);
+      for (size_t i = 0; i < (size_t)N; i++) {
+        size_t idx = J_R.start_idx + i;
+        if (jacobians[idx]) {
+          Mat3 JJ = Jrot * J_R.d_val_d_knot[i];
+          double* J = jacobians[idx];  // 6x4 row-major
+          for (int c = 0; c < 24; c++) J[c] = 0;
+          for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) J[r * 4 + c] = info_vec_[r] * JJ(r, c);
+        }
+      }
+      for (size_t i = 0; i < (size_t)N; i++) {
+        size_t idx = J_R.start_idx + i;
+        if (jacobians[idx + knot_num]) {
+          double* J = jacobians[idx + knot_num];  // 6x3 row-major
+          for (int c = 0; c < 18; c++) J[c] = 0;
+          for (int r = 0; r < 3; r++) J[(3 + r) * 3 + r] = info_vec_[3 + r] * J_p.d_val_d_knot[i];
+        }
+      }
+      if (jacobians[2 * knot_num]) {  // ":410-426"
+        double* J = jacobians[2 * knot_num];
+        Vec3 gyro = so3_velocity_body(t_corrected, meta_, parameters, nullptr);
+        Vec3 vel = rd_evaluate(1, t_corrected, meta_, parameters + knot_num, nullptr);
+        // SO3d(Eigen::Quaterniond(gyro_hat).normalized()): a quaternion made from the SKEW matrix, as written
+        Quat qg = qnormalized(quat_from_matrix_eigen(hat(gyro)));
+        Quat rot_dot = so3_mul(S_ItoG, qg);
+        Vec3 jr = so3_log(so3_mul(rot_dot, qconj(pose_data_.orientation)));
+        for (int r = 0; r < 3; r++) {
+          J[r] = 1e-9 * info_vec_[r] * jr[r];
+          J[3 + r] = 1e-9 * info_vec_[3 + r] * vel[r];
+        }
+      }
+    }
+    for (int r = 0; r < 3; r++) {
+      residuals[r] = info_vec_[r] * res_R[r];
+      residuals[3 + r] = info_vec_[3 + r] * res_p[r];
+    }
+    return true;
+  }
+};
+
+// LocalVelocityFactor — trajectory_value_factor.h:435-571
+struct LocalVelocityFactor : CostFunction {
+  int64_t time_ns_;
+  Vec3 local_velocity_;
+  SegmentMeta meta_;
+  double weight_;
+  LocalVelocityFactor(int64_t time_ns, const Vec3& local_velocity, const SegmentMeta& meta, double weight)
+      : time_ns_(time_ns), local_velocity_(local_velocity), meta_(meta), weight_(weight) {
+    num_residuals = 3;
+    size_t knot_num = meta_.NumParameters();
+    for (size_t i = 0; i < knot_num; ++i) block_sizes.push_back(4);
+    for (size_t i = 0; i < knot_num; ++i) block_sizes.push_back(3);
+    block_sizes.push_back(1);  // time_offset
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    So3Jacobian J_R;
+    RdJacobian J_p;
+    size_t knot_num = meta_.NumParameters();
+    double time_offset_in_ns = parameters[2 * knot_num][0];
+    int64_t t_corrected = time_ns_ + (int64_t)time_offset_in_ns;
+    Quat S_ItoG = so3_evaluate_Rp(t_corrected, meta_, parameters, jacobians ? &J_R : nullptr);
+    Vec3 v_inG = rd_evaluate(1, t_corrected, meta_, parameters + knot_num, jacobians ? &J_p : nullptr);
+    Vec3 res = so3_rotate(S_ItoG, local_velocity_) - v_inG;
+    for (int r = 0; r < 3; r++) residuals[r] = weight_ * res[r];
+    if (!jacobians) return true;
+    for (size_t i = 0; i < knot_num; ++i) {
+      if (jacobians[i])
+        for (int c = 0; c < 12; c++) jacobians[i][c] = 0;
+      if (jacobians[i + knot_num])
+        for (int c = 0; c < 9; c++) jacobians[i + knot_num][c] = 0;
+    }
+    Mat3 jac_lhs_R = -1.0 * (so3_matrix(S_ItoG) * hat(local_velocity_));
+    for (size_t i = 0; i < (size_t)N; i++) {
+      size_t idx = i + J_R.start_idx;
+      if (jacobians[idx]) {
+        Mat3 JJ = jac_lhs_R * J_R.d_val_d_knot[i];
+        double* J = jacobians[idx];  // 3x4
+        for (int c = 0; c < 12; c++) J[c] = 0;
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) J[r * 4 + c] = weight_ * JJ(r, c);
+      }
+    }
+    for (size_t i = 0; i < (size_t)N; i++) {
+      size_t idx = knot_num + i + J_p.start_idx;
+      if (jacobians[idx]) {
+        double* J = jacobians[idx];  // 3x3
+        for (int c = 0; c < 9; c++) J[c] = 0;
+        for (int r = 0; r < 3; r++) J[r * 3 + r] = weight_ * (J_p.d_val_d_knot[i] * -1.0);
+      }
+    }
+    if (jacobians[2 * knot_num]) {  // ":548-563"
+      double* J = jacobians[2 * knot_num];
+      Vec3 gyro = so3_velocity_body(t_corrected, meta_, parameters, nullptr);
+      Vec3 accel = rd_evaluate(2, t_corrected, meta_, parameters + knot_num, nullptr);
+      Mat3 rot_dot = so3_matrix(S_ItoG) * hat(gyro);
+      Vec3 jt = rot_dot * local_velocity_ - accel;
+      for (int r = 0; r < 3; r++) J[r] = 1e-9 * weight_ * jt[r];
+    }
+    return true;
+  }
+};
+
+// RelativeOrientationFactor — trajectory_value_factor.h:966-1075.  ta_ns_ / tb_ns_ are doubles in the reference
+// (":1073") and go through the templated computeTIndexNs (floor of a double quotient, spline_segment.h:108-118); the
+// times an estimator hands in are whole nanoseconds (MeasuredTimeToNs), for which both index paths agree except exactly
+// on a knot boundary with u = 0 — restated here with the double path.
+struct RelativeOrientationFactor : CostFunction {
+  Quat S_BtoA_;
+  double ta_ns_, tb_ns_;
+  SplineMeta spline_meta_;
+  double sqrt_info_[3];
+  RelativeOrientationFactor(const Quat& S_BtoA, int64_t ta_ns, int64_t tb_ns, const SplineMeta& meta, const double info_vec[3])
+      : S_BtoA_(S_BtoA), ta_ns_((double)ta_ns), tb_ns_((double)tb_ns), spline_meta_(meta) {
+    for (int i = 0; i < 3; i++) sqrt_info_[i] = info_vec[i];
+    num_residuals = 3;
+    size_t knot_num = spline_meta_.NumParameters();
+    for (size_t i = 0; i < knot_num; ++i) block_sizes.push_back(4);
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    So3Jacobian J_R[2];
+    size_t R_offset[2] = {0, 0};
+    size_t seg_idx[2] = {0, 0};
+    {
+      double u;
+      spline_meta_.ComputeSplineIndex((int64_t)ta_ns_, R_offset[0], u);
+      spline_meta_.ComputeSplineIndex((int64_t)tb_ns_, R_offset[1], u);
+      size_t segment0_knot_num = spline_meta_.segments.at(0).NumParameters();
+      for (int i = 0; i < 2; ++i) {
+        if (R_offset[i] >= segment0_knot_num) {
+          seg_idx[i] = 1;
+          R_offset[i] = segment0_knot_num;
+        } else {
+          R_offset[i] = 0;
+        }
+      }
+    }
+    Quat S_IatoG = so3_evaluate_rotation((int64_t)ta_ns_, spline_meta_.segments.at(seg_idx[0]), parameters + R_offset[0],
+                                         jacobians ? &J_R[0] : nullptr);
+    Quat S_GtoIb = so3_evaluate_logRT((int64_t)tb_ns_, spline_meta_.segments.at(seg_idx[1]), parameters + R_offset[1],
+                                      jacobians ? &J_R[1] : nullptr);
+    Vec3 res_R = so3_log(so3_mul(so3_mul(S_GtoIb, S_IatoG), S_BtoA_));
+    for (int r = 0; r < 3; r++) residuals[r] = sqrt_info_[r] * res_R[r];
+    size_t kont_num = spline_meta_.NumParameters();
+    if (jacobians) {
+      for (size_t i = 0; i < kont_num; ++i)
+        if (jacobians[i])
+          for (int c = 0; c < 12; c++) jacobians[i][c] = 0;
+      Mat3 Jrot = left_jacobian_inv_so3(res_R);
+      Mat3 jac_lhs[2] = {Jrot * so3_matrix(S_GtoIb), -1.0 * Jrot};
+      for (int seg = 0; seg < 2; ++seg)
+        for (size_t i = 0; i < (size_t)N; i++) {
+          size_t idx = R_offset[seg] + J_R[seg].start_idx + i;
+          if (jacobians[idx]) {
+            Mat3 JJ = jac_lhs[seg] * J_R[seg].d_val_d_knot[i];
+            double* J = jacobians[idx];  // 3x4, accumulated (":1056": +=)
+            for (int r = 0; r < 3; r++)
+              for (int c = 0; c < 3; c++) J[r * 4 + c] += sqrt_info_[r] * JJ(r, c);
+          }
+        }
+    }
+    return true;
+  }
+};
+
+// ImageDepthFactor — src/estimator/factor/analytic_diff/image_feature_factor.h:658-707
+struct ImageDepthFactor : CostFunction {
+  Vec3 p_i_, p_j_;
+  Quat S_CitoCj_;
+  Vec3 p_CiinCj_;
+  double sqrt_info;  // static 450/1.5 * I2 (":696-697"), overwritten by InitFactorInfo (trajectory_manager.cpp:70)
+  ImageDepthFactor(const Vec3& p_i, const Vec3& p_j, const Quat& S_CitoCj, const Vec3& p_CiinCj, double _sqrt_info)
+      : p_i_(p_i), p_j_(p_j), S_CitoCj_(S_CitoCj), p_CiinCj_(p_CiinCj), sqrt_info(_sqrt_info) {
+    num_residuals = 2;
+    block_sizes = {1};
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+    double d_inv = parameters[0][0];
+    Vec3 x_ci = p_i_ / d_inv;
+    Vec3 x_j = so3_rotate(S_CitoCj_, x_ci) + p_CiinCj_;
+    double depth_j_inv = 1.0 / x_j[2];
+    double r0 = x_j[0] * depth_j_inv - p_j_[0], r1 = x_j[1] * depth_j_inv - p_j_[1];
+    if (jacobians && jacobians[0]) {
+      Vec3 J_Xm_d = -1.0 * (so3_matrix(S_CitoCj_) * x_ci) / d_inv;
+      double j0 = depth_j_inv * J_Xm_d[0] - depth_j_inv * depth_j_inv * x_j[0] * J_Xm_d[2];
+      double j1 = depth_j_inv * J_Xm_d[1] - depth_j_inv * depth_j_inv * x_j[1] * J_Xm_d[2];
+      jacobians[0][0] = sqrt_info * j0;
+      jacobians[0][1] = sqrt_info * j1;
+    }
+    residuals[0] = sqrt_info * r0;
+    residuals[1] = sqrt_info * r1;
+    return true;
+  }
+};
+
 // GravityFactor — src/estimator/factor/analytic_diff/trajectory_value_factor.h:33-62
 struct GravityFactor : CostFunction {
   Vec3 gravity_;

@@ -236,4 +236,52 @@ inline Mat3 right_jacobian_inv_so3(const Vec3& phi) {
   return J;
 }
 
+// leftJacobianInvSO3 — src/utils/sophus_utils.hpp:279-307
+inline Mat3 left_jacobian_inv_so3(const Vec3& phi) {
+  double phi_norm2 = sqnorm(phi);
+  Mat3 phi_hat = hat(phi);
+  Mat3 phi_hat2 = phi_hat * phi_hat;
+  Mat3 J = eye3();
+  J = J - phi_hat / 2;
+  if (phi_norm2 > kEps) {
+    double phi_norm = std::sqrt(phi_norm2);
+    J = J + phi_hat2 * (1 / phi_norm2 - (1 + std::cos(phi_norm)) / (2 * phi_norm * std::sin(phi_norm)));
+  } else {
+    J = J + phi_hat2 / 12;
+  }
+  return J;
+}
+
+// Eigen::Quaterniond(Matrix3d) — Eigen is not vendored in the reference; this is its published conversion
+// (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other, 3, 3>, Shoemake's algorithm), applied as written
+// to WHATEVER 3x3 matrix it is given (the reference feeds it a skew matrix in IMUPoseFactor's time-offset column).
+inline Quat quat_from_matrix_eigen(const Mat3& m) {
+  double q[4];  // x y z w
+  double t = m(0, 0) + m(1, 1) + m(2, 2);
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m(2, 1) - m(1, 2)) * t;
+    q[1] = (m(0, 2) - m(2, 0)) * t;
+    q[2] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (m(k, j) - m(j, k)) * t;
+    q[j] = (m(j, i) + m(i, j)) * t;
+    q[k] = (m(k, i) + m(i, k)) * t;
+  }
+  return Quat{q[0], q[1], q[2], q[3]};
+}
+inline Quat qnormalized(const Quat& a) {
+  double n = std::sqrt(qsqnorm(a));
+  return Quat{a.x / n, a.y / n, a.z / n, a.w / n};
+}
+
 }  // namespace oracle

@@ -250,6 +250,87 @@ inline Quat so3_evaluate_RTp(int64_t time_ns, const SegmentMeta& meta, double co
   return res;
 }
 
+// So3SplineView::EvaluateRotation — so3_spline_view.h:65-117.  d_val_d_knot[k] = d log-right-perturbation of R(t) /
+// d(theta_k), built from the forward products R_tmp[i] = R_s prod_{j<=i} exp(k delta_j).
+inline Quat so3_evaluate_rotation(int64_t time_ns, const SegmentMeta& meta, double const* const* knots, So3Jacobian* J) {
+  size_t s = 0;
+  double u = 0;
+  meta.computeTIndexNs(time_ns, s, u);
+  double p[N], coeff[N];
+  base_coeffs_with_time(0, p, u);
+  matvec4(blend_cumulative(), p, coeff);
+  Quat res = load_q(knots[s]);
+  Mat3 J_helper = eye3();
+  if (J) {
+    J->start_idx = s;
+    J_helper = so3_matrix(res);
+  }
+  Mat3 R_tmp[DEG];
+  Mat3 Jr_inv_delta[DEG], Jr_kdelta[DEG];
+  for (int i = 0; i < DEG; i++) {
+    Quat p0 = load_q(knots[s + i]);
+    Quat p1 = load_q(knots[s + i + 1]);
+    Vec3 delta = so3_log(so3_mul(qconj(p0), p1));
+    Vec3 kdelta = delta * coeff[i + 1];
+    res = so3_mul(res, so3_exp(kdelta));
+    Jr_inv_delta[i] = right_jacobian_inv_so3(delta);
+    Jr_kdelta[i] = right_jacobian_so3(kdelta);
+    R_tmp[i] = so3_matrix(res);
+  }
+  if (J) {
+    J->d_val_d_knot[0] = J_helper;
+    for (int i = 0; i < DEG; i++) {
+      J_helper = coeff[i + 1] * R_tmp[i] * Jr_kdelta[i];
+      J->d_val_d_knot[i] = J->d_val_d_knot[i] - (J_helper * transpose(Jr_inv_delta[i]));
+      J->d_val_d_knot[i + 1] = J_helper * Jr_inv_delta[i];
+    }
+  }
+  return res;
+}
+
+// So3SplineView::EvaluateLogRT — so3_spline_view.h:263-321.  Returns R(t)^T, re-normalised through a rotation matrix
+// and Eigen's matrix -> quaternion conversion exactly as written (":303-306").  One normalisation of the reference's
+// behaviour: it fills A_post_inv[] only when J != nullptr but reads A_post_inv[0] for the value regardless (":290-303"),
+// i.e. a cost-only evaluation reads an uninitialised matrix; here it is always filled.
+inline Quat so3_evaluate_logRT(int64_t time_ns, const SegmentMeta& meta, double const* const* knots, So3Jacobian* J) {
+  size_t s = 0;
+  double u = 0;
+  meta.computeTIndexNs(time_ns, s, u);
+  double p[N], coeff[N];
+  base_coeffs_with_time(0, p, u);
+  matvec4(blend_cumulative(), p, coeff);
+  if (J) J->start_idx = s;
+  Quat Ri = load_q(knots[s]);
+  Quat A_accum_inv{0, 0, 0, 1};
+  Mat3 A_post_inv[DEG + 1];
+  Mat3 Jr_inv_delta[DEG], Jr_kdelta[DEG];
+  A_post_inv[DEG] = eye3();
+  for (int i = DEG - 1; i >= 0; i--) {
+    Quat R0 = load_q(knots[s + i]);
+    Quat R1 = load_q(knots[s + i + 1]);
+    Vec3 delta = so3_log(so3_mul(qconj(R0), R1));
+    Vec3 kdelta = delta * coeff[i + 1];
+    A_accum_inv = so3_mul(A_accum_inv, so3_exp(-kdelta));
+    Jr_inv_delta[i] = right_jacobian_inv_so3(delta);
+    Jr_kdelta[i] = right_jacobian_so3(-kdelta);
+    A_post_inv[i] = so3_matrix(A_accum_inv);
+  }
+  Mat3 R_T = A_post_inv[0] * so3_matrix(qconj(Ri));
+  Quat q_t = qnormalized(quat_from_matrix_eigen(R_T));
+  // SO3(q_t.toRotationMatrix()): Sophus converts the matrix back to a unit quaternion (so3.hpp:165-176)
+  Quat res = qnormalized(quat_from_matrix_eigen(so3_matrix(q_t)));
+  if (J) {
+    Mat3 J_helper = A_post_inv[0];
+    J->d_val_d_knot[0] = J_helper;
+    for (int i = 0; i < DEG; i++) {
+      J_helper = coeff[i + 1] * A_post_inv[i] * Jr_kdelta[i];
+      J->d_val_d_knot[i] = J->d_val_d_knot[i] - (J_helper * transpose(Jr_inv_delta[i]));
+      J->d_val_d_knot[i + 1] = J_helper * Jr_inv_delta[i];
+    }
+  }
+  return res;
+}
+
 // So3SplineView::VelocityBody — so3_spline_view.h:330-394 (J == nullptr is the only use on the hot path,
 // image_feature_factor.h:144-158; the Jacobian part is restated too for completeness).
 inline Vec3 so3_velocity_body(int64_t time_ns, const SegmentMeta& meta, double const* const* knots, So3Jacobian* J) {

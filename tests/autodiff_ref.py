@@ -165,3 +165,49 @@ def image_residual(win, ti_ns, p_i, tj_ns, p_j, S_CtoI, p_CinI, sqrt_info=450.0 
         x_j = qrot(qconj(qc), p_Ij - torch.tensor(p_CinI))
         return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2]))
     return fn
+
+
+def pose_residual(win, t_ns, position, orientation, info_vec):
+    """auto_diff/trajectory_value_factor.h:377-434 (IMUPoseFactor); extras = (t_offset_ns,)."""
+    def fn(dth, dp, toff):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        toff_int = int(toff.detach()[0])
+        s, u = sp.su(t_ns + toff_int, toff[0] - toff.detach()[0])
+        R, _ = sp.rot_vel(s, u)
+        r_R = qlog(qmul(R, qconj(torch.tensor(orientation))))
+        r_p = sp.pos(s, u) - torch.tensor(position)
+        return torch.cat([r_R, r_p]) * torch.tensor(info_vec)
+    return fn
+
+
+def local_velocity_residual(win, t_ns, local_v, weight):
+    """auto_diff/trajectory_value_factor.h:490-547 (IMULocalVelocityFactor); extras = (t_offset_ns,)."""
+    def fn(dth, dp, toff):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        toff_int = int(toff.detach()[0])
+        s, u = sp.su(t_ns + toff_int, toff[0] - toff.detach()[0])
+        R, _ = sp.rot_vel(s, u)
+        return weight * (qrot(R, torch.tensor(local_v)) - sp.pos(s, u, 1))
+    return fn
+
+
+def relative_rotation_residual(win, ta_ns, tb_ns, S_BtoA, info_vec):
+    """auto_diff/trajectory_value_factor.h:770-840 (RelativeOrientationFactor)."""
+    def fn(dth, dp):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        sa, ua = sp.su(ta_ns)
+        sb, ub = sp.su(tb_ns)
+        Ra, _ = sp.rot_vel(sa, ua)
+        Rb, _ = sp.rot_vel(sb, ub)
+        return torch.tensor(info_vec) * qlog(qmul(qmul(qconj(Rb), Ra), torch.tensor(S_BtoA)))
+    return fn
+
+
+def image_depth_residual(p_i, p_j, S_CitoCj, p_CiinCj, sqrt_info):
+    """auto_diff/image_feature_factor.h:310-357 (ImageDepthFactor); extras = (inv_depth,).  No spline involved: the
+    knot arguments are ignored."""
+    def fn(dth, dp, rho):
+        x_ci = torch.tensor(p_i) / rho[0]
+        x_j = qrot(torch.tensor(S_CitoCj), x_ci) + torch.tensor(p_CiinCj)
+        return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2])) + 0.0 * dth.sum() + 0.0 * dp.sum()
+    return fn

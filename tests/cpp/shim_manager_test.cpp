@@ -79,6 +79,22 @@ int main() {
     Vec6d binfo = {1e4, 1e4, 1e4, 1e3, 1e3, 1e3};
     estimator->AddBiasFactor(bg0, bg1, ba0, ba1, 1, binfo);
     estimator->SetTimeoffsetState();  // as InitTrajWithPropagation does (:295)
+    // the remaining adders of the class (trajectory_estimator.h:146-204): pose, local velocity, relative rotation,
+    // image depth
+    PoseData pose;
+    pose.timestamp = 0.4;
+    pose.position = {2 * std::sin(0.28), 1.5 * std::cos(0.2), 0.3 * std::sin(0.44)};
+    pose.orientation.q = {{0.05, 0.04, 0.1, 0.9929}};
+    estimator->AddPoseMeasurementAnalytic(pose, Vec6d{{20, 20, 20, 8, 8, 8}});
+    estimator->AddStartTimePose(pose);
+    estimator->AddLocalVelocityMeasurementAnalytic(0.52, Vec3d{{1.1, 0.2, 0.05}}, 3.0);
+    SO3d S_BtoA;
+    S_BtoA.q = {{0.02, -0.03, 0.15, 0.9881}};
+    estimator->AddRelativeRotationAnalytic(0.31, 0.62, S_BtoA, Vec3d{{12, 14, 16}});
+    SO3d S_CitoCj;
+    S_CitoCj.q = {{0.01, 0.02, -0.01, 0.9997}};
+    estimator->AddImageDepthAnalytic(Vec3d{{0.1, 0.05, 1.0}}, Vec3d{{0.13, 0.03, 1.0}}, S_CitoCj, Vec3d{{0.1, -0.05, 0.02}},
+                                     &inv_depth[0]);
     Summary summary = estimator->Solve(8, false);
     cost1_init = summary.initial_cost;
     cost1_final = summary.final_cost;

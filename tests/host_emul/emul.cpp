@@ -115,3 +115,42 @@ __attribute__((visibility("default"))) int emul_image_packed(int K, const double
   return 0;
 }
 }
+
+extern "C" {
+// The one-thread evaluators of the small factors: kind, the factor's numbers, the layout's column
+// maps; returns r and the dense Jacobian over D global columns.
+__attribute__((visibility("default"))) int emul_small(int K, const double* kq, const double* kp, int64_t t0_ns, int64_t dt_ns,
+                                                       int kind, int64_t t_a, int64_t t_b, const double* d16, double loss_a,
+                                                       int landmark, double toff_imu, double inv_depth, const int* knot_col,
+                                                       int col_toff_imu, const int* lm_col, int D, double* r /*6*/,
+                                                       double* J /*6*D*/, int* nres) {
+  HostWindow W(K, kq, kp);
+  SmallFactor f{};
+  f.kind = kind;
+  f.t_a = t_a;
+  f.t_b = t_b;
+  f.landmark = landmark;
+  f.loss_a = loss_a;
+  for (int i = 0; i < 16; i++) f.d[i] = d16[i];
+  SmallCols sc;
+  sc.knot_col = knot_col;
+  sc.col_toff_imu = col_toff_imu;
+  sc.lm_col = lm_col;
+  SmallOut o;
+  bool ok = false;
+  switch (kind) {
+    case kSmallPose: ok = small_pose_eval(W.view, f, t0_ns, dt_ns, K, toff_imu, sc, &o); break;
+    case kSmallLocalVelocity: ok = small_local_velocity_eval(W.view, f, t0_ns, dt_ns, K, toff_imu, sc, &o); break;
+    case kSmallRelativeRotation: ok = small_relative_rotation_eval(W.view, f, t0_ns, dt_ns, K, sc, &o); break;
+    default: ok = small_image_depth_eval(f, inv_depth, sc, &o); break;
+  }
+  if (!ok) return 1;
+  *nres = o.nres;
+  for (int i = 0; i < o.nres; i++) {
+    r[i] = o.r[i];
+    for (int c = 0; c < D; c++) J[i * D + c] = 0.0;
+    for (int c = 0; c < o.ncols; c++) J[i * D + o.gcol[c]] = o.J[i][c];
+  }
+  return 0;
+}
+}

@@ -30,6 +30,8 @@ def emul():
                                C.c_double, C.c_int, dp, dp, ip, ip]
     lib.emul_image_packed.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp, C.c_double, dp,
                                       dp, C.c_double, C.c_int, dp, dp]
+    lib.emul_small.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int64, dp, C.c_double, C.c_int,
+                               C.c_double, C.c_double, ip, C.c_int, ip, C.c_int, dp, dp, ip]
     return lib
 
 
@@ -174,3 +176,68 @@ def test_image_rows(oracle, emul, unlock_toff, free_depth):
         assert np.allclose(rows[:, 49], r_o, rtol=1e-10, atol=1e-9)
     assert overlaps > 0
     assert worst < 1e-11, worst
+
+
+# ---- the one-thread evaluators of the small factors vs the oracle's factor classes ----
+def _small_case(oracle, emul, kind, seed, unlock_toff=False, fixed=1):
+    from test_oracle_autodiff import reference_test_trajectory
+    w = reference_test_trajectory(seed)
+    rng = np.random.default_rng(100 + seed)
+    opt = E.default_options(oracle)
+    if unlock_toff:
+        opt.lock_t_offset[0] = 0
+        opt.t_offset_padding_ns = 50_000_000
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    est.SetFixedIndex(fixed)
+    d = np.zeros(16)
+    t_a = t_b = 0
+    loss_a, lm = 0.0, 0
+    if kind == 0:
+        t, p, q, info = 0.55, rng.uniform(-5, 5, 3), S.so3_exp(rng.uniform(-np.pi, np.pi, 3)), rng.uniform(0.5, 3, 6)
+        assert est.AddPoseMeasurementAnalytic([t], [p], [q], info) == 0
+        d[:3], d[3:7], d[7:13], t_a = p, q, info, int(t * 1e9)
+    elif kind == 1:
+        t, v, wt = 0.23, np.array([0.2, 0.4, 0.5]), 1.9
+        assert est.AddLocalVelocityMeasurementAnalytic([t], [v], wt) == 0
+        d[:3], d[3], t_a = v, wt, int(t * 1e9)
+    elif kind == 2:
+        ta, tb = [(0.11, 0.33), (0.21, 0.83), (0.52, 0.58)][seed % 3]
+        Sq, info = S.so3_exp(rng.uniform(-np.pi, np.pi, 3)), np.array([0.33, 0.27, 0.11])
+        assert est.AddRelativeRotationAnalytic(ta, tb, Sq, info)
+        d[:4], d[4:7], t_a, t_b = Sq, info, int(ta * 1e9), int(tb * 1e9)
+    else:
+        pi, pj = np.array([1, 2, 1.0]), np.array([4, 5, 1.0])
+        Sq, pc = S.so3_exp(rng.uniform(-0.4, 0.4, 3)), rng.uniform(-0.5, 0.5, 3)
+        est.AddImageDepthAnalytic(pi, pj, Sq, pc, 0)
+        d[:3], d[3:6], d[6:10], d[10:13], d[13], loss_a = pi, pj, Sq, pc, 450.0 / 1.5, 1.0
+    L = est.layout()
+    r_o, J_o = oracle_lib.block_jacobian(oracle, est, 0, apply_loss=True)
+    knot_col = np.array([6 * (k - L.first_free_knot) if k >= L.first_free_knot else -1 for k in range(w.n_knots)], np.int32)
+    lm_col = np.array([L.col_inv_depth if L.n_free_landmarks else -1], np.int32)
+    r = np.zeros(6)
+    J = np.zeros((6, L.D))
+    nres = C.c_int(0)
+    ip = C.POINTER(C.c_int)
+    kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
+    rc = emul.emul_small(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, kind, t_a, t_b, dptr(d), loss_a, lm,
+                         float(w.t_offset_ns[0]), float(w.inv_depth[0]), knot_col.ctypes.data_as(ip), int(L.col_t_offset[0]),
+                         lm_col.ctypes.data_as(ip), L.D, dptr(r), dptr(J), C.byref(nres))
+    assert rc == 0 and nres.value == len(r_o)
+    if loss_a > 0:  # emul_small returns the uncorrected rows; the kernel applies the Corrector's sqrt(rho') afterwards
+        sq = float(r[:nres.value] @ r[:nres.value])
+        sc = np.sqrt(1.0 / (1.0 + sq / loss_a ** 2))
+        r, J = r * sc, J * sc
+    scale = max(1.0, np.abs(J_o).max())
+    assert np.abs(r[:nres.value] - r_o).max() < 1e-11 * max(1.0, np.abs(r_o).max())
+    assert np.abs(J[:nres.value] - J_o).max() < 1e-10 * scale, np.abs(J[:nres.value] - J_o).max()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_small_factor_rows(oracle, emul, kind, seed):
+    _small_case(oracle, emul, kind, seed)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_small_factor_rows_time_offset_free(oracle, emul, kind):
+    _small_case(oracle, emul, kind, 2, unlock_toff=True, fixed=-1)

@@ -175,3 +175,83 @@ def test_synthetic_window_factors(oracle):
         c = L.col_bias_gyro + 3 * slot
         assert np.abs(J[:, c:c + 3] - Jx[0]).max() < TOL * sc
         blk += 1
+
+
+# ---- the remaining adders of TrajectoryEstimator (fixtures of test_analytic_factor.cpp:903-1026) ----
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_imu_pose_factor(oracle, seed):
+    """IMUPoseFactor (test_analytic_factor.cpp:1325-1333: pose at t = 0.55, w_pose 2.3).  Knot blocks against auto-diff;
+    the reference's time-offset column is built from a quaternion made out of a SKEW matrix
+    (trajectory_value_factor.h:419-423) and is not the derivative of anything — restated as written, not compared."""
+    w = reference_test_trajectory(seed)
+    rng = np.random.default_rng(seed)
+    q_meas = S.so3_exp(rng.uniform(-np.pi, np.pi, 3))
+    p_meas = rng.uniform(-5, 5, 3)
+    info = np.array([2.3, 2.3, 2.3, 1.7, 1.7, 1.7])
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    assert est.AddPoseMeasurementAnalytic([0.55], [p_meas], [q_meas], info) == 0
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.pose_residual(win_dict(w), int(0.55 * 1e9), p_meas, q_meas, info)
+    r_ad, Jk, _ = AD.jac(fn, w.n_knots, [[w.t_offset_ns[0]]])
+    assert np.allclose(r, r_ad, atol=1e-9)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * max(1.0, np.abs(Jk).max())
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_local_velocity_factor(oracle, seed):
+    """LocalVelocityFactor (test_analytic_factor.cpp:1224-1232: t = 0.23, v = (0.2, 0.4, 0.5)), time offset unlocked."""
+    w = reference_test_trajectory(seed)
+    opt = E.default_options(oracle)
+    opt.lock_t_offset[0] = 0
+    opt.t_offset_padding_ns = 100_000_000
+    est = E.TrajectoryEstimator(w, opt, oracle)
+    v = np.array([0.2, 0.4, 0.5])
+    assert est.AddLocalVelocityMeasurementAnalytic([0.23], [v], 1.9) == 0
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.local_velocity_residual(win_dict(w), int(0.23 * 1e9), v, 1.9)
+    r_ad, Jk, Jx = AD.jac(fn, w.n_knots, [[w.t_offset_ns[0]]])
+    sc = max(1.0, np.abs(Jk).max())
+    assert np.allclose(r, r_ad, atol=1e-8)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * sc
+    assert np.abs(J[:, L.col_t_offset[0]] - Jx[0][:, 0]).max() < TOL * sc
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("case", [0, 1])
+def test_relative_orientation_factor(oracle, seed, case):
+    """RelativeOrientationFactor (test_analytic_factor.cpp:1192-1202: (ta, tb) = (0.11, 0.33), (0.21, 0.83),
+    sqrt_info (0.33, 0.27, 0.11))."""
+    w = reference_test_trajectory(seed)
+    ta, tb = [(0.11, 0.33), (0.21, 0.83)][case]
+    rng = np.random.default_rng(10 + seed)
+    S_BtoA = S.so3_exp(rng.uniform(-np.pi, np.pi, 3))
+    info = np.array([0.33, 0.27, 0.11])
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    assert est.AddRelativeRotationAnalytic(ta, tb, S_BtoA, info)
+    L = est.layout()
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.relative_rotation_residual(win_dict(w), int(ta * 1e9), int(tb * 1e9), S_BtoA, info)
+    r_ad, Jk, _ = AD.jac(fn, w.n_knots, [])
+    assert np.allclose(r, r_ad, atol=1e-9)
+    assert np.abs(J[:, :6 * L.n_free_knots] - knot_cols(Jk, L)).max() < TOL * max(1.0, np.abs(Jk).max())
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_image_depth_factor(oracle, case):
+    """ImageDepthFactor (test_analytic_factor.cpp:1256-1264: p_i / p_j of the image cases, depth_inv 0.51)."""
+    w = reference_test_trajectory(1)
+    pi, pj = [(np.array([1, 2, 1.0]), np.array([4, 5, 1.0])), (np.array([4, 5, 1.0]), np.array([1, 2, 1.0]))][case]
+    rng = np.random.default_rng(4 + case)
+    S_CitoCj = S.so3_exp(rng.uniform(-0.4, 0.4, 3))
+    p_CiinCj = rng.uniform(-0.5, 0.5, 3)
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    est.AddImageDepthAnalytic(pi, pj, S_CitoCj, p_CiinCj, 0)
+    L = est.layout()
+    assert L.n_free_landmarks == 1
+    r, J = oracle_lib.block_jacobian(oracle, est, 0)
+    fn = AD.image_depth_residual(pi, pj, S_CitoCj, p_CiinCj, 450.0 / 1.5)
+    r_ad, _, Jx = AD.jac(fn, w.n_knots, [[w.inv_depth[0]]])
+    assert np.allclose(r, r_ad, rtol=1e-10, atol=1e-7)
+    assert np.abs(J[:, L.col_inv_depth] - Jx[0][:, 0]).max() < TOL * max(1.0, np.abs(Jx[0]).max())
