@@ -171,6 +171,7 @@ PROTOTYPES = {
     "clic_comm_p2p_disable": (C.c_int, []),
     "clic_linearize_async": (C.c_int, [H, C.c_int32]),
     "clic_synchronize": (C.c_int, [H]),
+    "clic_residual_summary": (C.c_int, [H, c_double_p, c_int64_p]),
     "clic_pass_info": (C.c_int, [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "clic_pass_stamps": (C.c_int, [H, C.c_int32, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "clic_num_kernel_launches": (C.c_int, [H, c_int64_p]),

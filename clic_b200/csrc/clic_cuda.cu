@@ -2708,6 +2708,101 @@ CLIC_API int clic_evaluate(clic_estimator* E, double* H, double* b, double* cost
   return CLIC_OK;
 }
 
+CLIC_API int clic_residual_summary(clic_estimator* E, double cost[16], int64_t count[16]) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  if ((rc = fill_prior_columns(E))) return rc;
+  for (int i = 0; i < 16; i++) { if (cost) cost[i] = 0.0; if (count) count[i] = 0; }
+  DevBuf tmp;
+  CU(tmp.ensure(64 * sizeof(double)));  // [0, 32): per type (cost, fixed cost); [32, 64): per stream
+  CU(cudaMemsetAsync(tmp.p, 0, 64 * sizeof(double), E->stream));
+  double* d_c = tmp.as<double>();
+  const double* state = E->d_state.as<double>();
+  PassParams pp = pass_params(E, state, nullptr);
+  // one residual-only launch per stream + its cost sum (the cost CTA of reduce_all_kernel on that stream's job alone);
+  // jobs are in ensure_layout's order: LiDAR batches, IMU batches, visual batches (marginalization batches skipped)
+  int j = 0;
+  auto sum_job = [&](int type) -> int {
+    CU(launch_pdl(reduce_all_kernel, 1, 256, (size_t)2 * E->max_slots * sizeof(int), E->stream,
+                  E->d_jobs.as<ReduceJob>() + j, 1, 0, E->max_slots, d_c + 32 + 2 * j, (const int*)nullptr));
+    (void)type;
+    if (++j > 16) return fail(CLIC_ERR_UNSUPPORTED, "clic_residual_summary: more than 16 factor streams");
+    return CLIC_OK;
+  };
+  std::vector<int> job_type;
+  for (auto& b : E->loam) {
+    if (b->marg) continue;
+    if ((rc = wait_ready(E, b->ex))) return rc;
+    const size_t smem = loam_smem_bytes(E->K);
+    if (b->st.geo_kind == 1) CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 1>, b->ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, b->ex.slabs_per_warp, b->ex.rb()));
+    else if (b->st.geo_kind == 2) CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 2>, b->ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, b->ex.slabs_per_warp, b->ex.rb()));
+    else CU(launch_pdl(loam_kernel<false, kLoamWarps, kLoamMinB, 0>, b->ex.grid, kLoamWarps * 32, smem, E->stream, b->st, pp, b->ex.slabs_per_warp, b->ex.rb()));
+    job_type.push_back(4);  // RType_LiDAR
+    if (count) count[4] += b->n_input;
+    if ((rc = sum_job(4))) return rc;
+  }
+  for (auto& b : E->imu) {
+    if (b->marg) continue;
+    if ((rc = wait_ready(E, b->ex))) return rc;
+    b->st.toff_free = E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1 : 0;
+    CU(launch_pdl(imu_kernel<false, false>, b->ex.grid, kThreads, factor_smem_bytes(E->K, 4), E->stream, b->st, pp,
+                  b->ex.slabs_per_warp, b->ex.rb()));
+    job_type.push_back(1);  // RType_IMU
+    if (count) count[1] += b->n_input;
+    if ((rc = sum_job(1))) return rc;
+  }
+  for (auto& b : E->image) {
+    if (b->marg) continue;
+    if ((rc = wait_ready(E, b->ex))) return rc;
+    const ImageShared ish = image_shared(E, b.get());
+    image_pass_fields(E, b->st, false);
+    if (b->st.n_packs > 0)
+      CU(launch_pdl(image_kernel<false, true>, b->ex.grid, kThreads, image_smem_bytes(E->K, b->st.n_packs), E->stream, b->st,
+                    pp, b->ex.slabs_per_warp, b->ex.rb(), ish));
+    else
+      CU(launch_pdl(image_kernel<false, false>, b->ex.grid, kThreads, factor_smem_bytes(E->K, 7), E->stream, b->st, pp,
+                    b->ex.slabs_per_warp, b->ex.rb(), ish));
+    job_type.push_back(11);  // RType_Image
+    if (count) count[11] += b->n_input;
+    if ((rc = sum_job(11))) return rc;
+  }
+  
+  double* H_scratch = E->nrm_loc_set(1);  // the kernels below take H, b pointers but do not touch them without jac
+  double* b_scratch = H_scratch + E->off_b();
+  const int D = std::max(1, E->L.D);
+  for (auto& d : solve_bias_descs(E))
+    CU(launch_pdl(bias_factor_kernel, 1, 32, 0, E->stream, d, state, E->sl, H_scratch, b_scratch, D, d_c + 2 * 2, 0,
+                  (const int*)nullptr));
+  if (count) for (auto& bf : E->bias_f) if (!bf.marg) count[2]++;
+  if (!E->opt.is_marg_state)
+    for (auto& pr : E->priors) {
+      if ((rc = launch_prior(E, pr.get(), state, d_c + 2 * 13, false, nullptr, H_scratch, b_scratch))) return rc;
+      if (count) count[13]++;
+    }
+  for (auto& vf : E->vel_factors) {
+    CU(launch_pdl(velocity_factor_kernel, 1, 64, 0, E->stream, vf, state, E->sl, (long long)E->t0_ns, (long long)E->dt_ns,
+                  E->K, (const int*)E->d_knot_col.as<int>(), E->L.col_t_offset[CLIC_SENSOR_IMU], H_scratch, b_scratch, D,
+                  d_c + 2 * 8, 0, (const int*)nullptr));
+    if (count) count[8]++;
+  }
+  if ((rc = launch_small_factors(E, state, H_scratch, b_scratch, d_c + 2 * 14, false, nullptr))) return rc;
+  if (count) count[14] += (int64_t)E->small_f.size();
+  double h[64];
+  CU(cudaMemcpyAsync(h, tmp.p, sizeof(h), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  CU(cudaGetLastError());
+  if (cost) {
+    for (int t : {2, 8, 13, 14}) cost[t] = h[2 * t] + h[2 * t + 1];
+    for (int q = 0; q < j; q++) cost[job_type[q]] += h[32 + 2 * q] + h[32 + 2 * q + 1];
+    cost[3] = E->grav_fixed_cost();
+  }
+  if (count) for (auto& gf : E->grav_f) if (!gf.marg) count[3]++;
+  return CLIC_OK;
+}
+
 CLIC_API int clic_get_indices(clic_estimator* E, int32_t stream, int64_t capacity, int32_t* s_out, double* u_out,
                               int64_t* n_out) {
   if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");

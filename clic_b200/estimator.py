@@ -386,6 +386,12 @@ class TrajectoryEstimator:
         _check(self.lib, self.lib.clic_profile_read(self.h, dptr(ms), cnt.ctypes.data_as(_abi.c_int64_p)))
         return ms, cnt
 
+    def residual_summary(self):
+        """Per-ResidualType cost and factor count of the solve problem at the current state (clic_residual_summary)."""
+        cost, cnt = np.zeros(16), np.zeros(16, np.int64)
+        _check(self.lib, self.lib.clic_residual_summary(self.h, dptr(cost), cnt.ctypes.data_as(_abi.c_int64_p)))
+        return cost, cnt
+
     def pass_info(self):
         """How the pass executes: dict(fused, grid, part_ctas[6]) — see clic_pass_info."""
         fused, grid = C.c_int32(0), C.c_int32(0)

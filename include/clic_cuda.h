@@ -275,6 +275,13 @@ CLIC_API int clic_get_layout(clic_estimator* h, clic_layout* out);
  * parameters are all constant, reported separately as fixed_cost like Ceres).  Any pointer may be NULL. */
 CLIC_API int clic_evaluate(clic_estimator* h, double* H, double* b, double* cost, double* fixed_cost);
 
+/* ResidualSummary-like read-back (trajectory_estimator.h:42-98, what `verbose` prints per update): the cost
+ * 1/2 sum rho(|r|^2) of the solve problem at the current state split by ResidualType (marginalization_factor.h:31-46:
+ * 0 Pose, 1 IMU, 2 Bias, 3 Gravity, 4 LiDAR, ... 8 GlobalVelocity, 11 Image, 13 Prior; slot 14 = the pose / local-velocity /
+ * relative-rotation / image-depth adders together), constant-parameter factors included, and the number of factors added
+ * per type.  A debugging aid: it runs one residual-only launch per stream. */
+CLIC_API int clic_residual_summary(clic_estimator* h, double cost[16], int64_t count[16]);
+
 /* Bit-exact indexing probe (SplineSegmentMeta::computeTIndexNs, spline_segment.h:67-84):
  * for the factors of one stream, in add order: local knot index s (-1 if the factor was dropped) and u.
  * stream: 0 LiDAR, 1 IMU, 2 image time i, 3 image time j.  IMU/image use the current time offset. */

@@ -985,6 +985,29 @@ CLIC_API void clic_default_options(clic_options* o) {
 
 // Test-only knob: number of OpenMP threads of the evaluation loop (the reference runs Ceres with 1 thread,
 // trajectory_estimator.cpp:1004-1007, and marginalization with 4 pthreads, marginalization_factor.h:29).
+// ResidualSummary-like read-back (trajectory_estimator.h:42-98): 1/2 rho(|r|^2) summed per ResidualType
+// (marginalization_factor.h:31-46; slot 14 = the pose / local-velocity / relative-rotation / image-depth adders) over
+// the solve problem at the current state, and the number of residual blocks of each type.
+CLIC_API int clic_residual_summary(clic_estimator* E, double cost[16], int64_t count[16]) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  for (int i = 0; i < 16; i++) { if (cost) cost[i] = 0.0; if (count) count[i] = 0; }
+  for (auto& rb : E->blocks) {
+    const int nres = rb.cost->num_residuals;
+    const size_t np = rb.refs.size();
+    std::vector<const double*> params(np);
+    for (size_t i = 0; i < np; i++) params[i] = E->block_ptr(E->x, rb.refs[i]);
+    std::vector<double> res(nres, 0.0);
+    rb.cost->Evaluate(params.data(), res.data(), nullptr);
+    std::vector<std::vector<double>> nojac;
+    double rho0;
+    correct(rb, nres, res, nojac, rb.cost->block_sizes, &rho0);
+    const int t = rb.rtype >= 0 && rb.rtype < 16 ? rb.rtype : 15;
+    if (cost) cost[t] += 0.5 * rho0;
+    if (count) count[t] += 1;
+  }
+  return CLIC_OK;
+}
+
 CLIC_API int clic_oracle_last_marg_system(double* A, double* b, int32_t* pos, int32_t* m) {
   if (pos) *pos = g_last_marg_pos;
   if (m) *m = g_last_marg_m;
@@ -1259,7 +1282,7 @@ CLIC_API int clic_add_global_velocity(clic_estimator* E, double timestamp, const
   }
   rb.has_loss = true;
   rb.loss_a = 60;  // CauchyLoss(60), ":642"
-  rb.rtype = 3;
+  rb.rtype = 8;  // RType_GlobalVelocity
   E->blocks.push_back(std::move(rb));
   if (added) *added = 1;
   return CLIC_OK;
@@ -1295,7 +1318,7 @@ CLIC_API int clic_add_gravity(clic_estimator* E, const double gravity[3], const 
   ResidualBlock rb;
   rb.cost.reset(new GravityFactor(gravity, info_vec));
   rb.refs = {{CLIC_BLOCK_GRAVITY, 0}};
-  rb.rtype = 5;
+  rb.rtype = 3;  // RType_Gravity
   if (E->opt.is_marg_state && marg_this_factor) {
     std::vector<int> drop = {0};  // ":515-519"
     if (!E->opt.marg_gravity_param) drop.clear();
@@ -1342,7 +1365,7 @@ CLIC_API int clic_add_pose(clic_estimator* E, int64_t n, const double* timestamp
     E->AddControlPoints(meta, rb.refs, false);
     E->AddControlPoints(meta, rb.refs, true);
     rb.refs.push_back({CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU});
-    rb.rtype = 0;
+    rb.rtype = 14;
     E->blocks.push_back(std::move(rb));
   }
   if (n_dropped) *n_dropped = dropped;
@@ -1365,7 +1388,7 @@ CLIC_API int clic_add_local_velocity(clic_estimator* E, int64_t n, const double*
     E->AddControlPoints(meta, rb.refs, false);
     E->AddControlPoints(meta, rb.refs, true);
     rb.refs.push_back({CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_IMU});
-    rb.rtype = 9;
+    rb.rtype = 14;
     E->blocks.push_back(std::move(rb));
   }
   if (n_dropped) *n_dropped = dropped;
@@ -1387,7 +1410,7 @@ CLIC_API int clic_add_relative_rotation(clic_estimator* E, double ta, double tb,
   ResidualBlock rb;
   rb.cost.reset(new RelativeOrientationFactor(load_q(S_BtoA), time_a_ns, time_b_ns, meta, info_vec));
   E->AddControlPoints(meta, rb.refs, false);
-  rb.rtype = 0;
+  rb.rtype = 14;
   E->blocks.push_back(std::move(rb));
   if (added) *added = 1;
   return CLIC_OK;
@@ -1407,7 +1430,7 @@ CLIC_API int clic_add_image_depth(clic_estimator* E, const double p_i[3], const 
   E->lm_free[landmark] = 1;
   rb.has_loss = true;
   rb.loss_a = 1.0;
-  rb.rtype = 11;
+  rb.rtype = 14;
   E->blocks.push_back(std::move(rb));
   return CLIC_OK;
 }

@@ -113,3 +113,22 @@ def test_marginalization_estimator_refuses_them(cuda):
     est = E.TrajectoryEstimator(sw.window, opt, cuda)
     with pytest.raises(Exception):
         est.AddPoseMeasurementAnalytic([0.1], [[0, 0, 0]], [[0, 0, 0, 1.0]], np.ones(6))
+
+
+def test_residual_summary_by_type(cuda, oracle):
+    """clic_residual_summary (ResidualSummary, trajectory_estimator.h:42-98): per-type costs GPU vs oracle, and their sum
+    = cost + fixed cost of the pass."""
+    sw = S.config(3, 0.1)
+    out = {}
+    for name, lib in (("g", cuda), ("o", oracle)):
+        est, _ = build(lib, sw, fixed=2)
+        est.AddGravityFactor(sw.window.gravity + np.array([0.01, 0.0, -0.02]), [40.0, 40.0, 40.0])
+        H, b, c, f = est.Evaluate()
+        cost, cnt = est.residual_summary()
+        out[name] = (cost, cnt, c + f)
+        est.close()
+    (cg, ng, tg), (co, no, to) = out["g"], out["o"]
+    assert abs(cg.sum() - tg) <= 1e-9 * abs(tg) and abs(co.sum() - to) <= 1e-9 * abs(to)
+    for t in (1, 2, 3, 4, 11, 14):
+        assert co[t] > 0 and abs(cg[t] - co[t]) <= 1e-9 * abs(co[t]), (t, cg[t], co[t])
+    assert ng[1] > 0 and ng[4] > 0 and ng[11] > 0 and ng[2] == no[2] == 1 and ng[3] == no[3] == 1 and ng[14] == no[14]
