@@ -274,6 +274,7 @@ struct ImageBatch {
   DevBuf ti, tj, pi[3], pj[2], lm;
   DevBuf raw[4];
   DevBuf id_i, id_j, pack_t;  // pose packs (st.n_packs > 0)
+  DevBuf lm_start, lm_obs;      // landmark -> its observations' stored positions (CSR), for rho_side_kernel
   std::vector<int32_t> gather;  // stored position -> add order, -1 = padding (buckets start on slab boundaries)
   int64_t n_input = 0;          // factors the caller added (st.n counts the padding too)
   std::vector<char> lm_used;  // landmarks referenced by a kept factor (marg batches: their inverse depths are dropped blocks)
@@ -970,12 +971,41 @@ ImageShared image_shared(const clic_estimator* E, const ImageBatch* b) {
 }
 void image_pass_fields(const clic_estimator* E, ImageStream& st, bool jac) {
   const bool free_rho = E->L.n_free_landmarks > 0;
-  st.rho_side = (jac && free_rho) ? E->d_rho_side.as<double>() : nullptr;
+  (void)jac;
+  st.rho_side = nullptr;  // the landmark columns are gathered by rho_side_kernel, not scattered by the factor kernel
   st.lm_col = free_rho ? E->d_lm_col.as<int32_t>() : nullptr;
   st.knot_col = E->d_knot_col.as<int>();
   st.Dtot = E->L.D;
   st.rho0 = E->L.col_inv_depth;
   st.col_toff_cam = E->L.col_t_offset[CLIC_SENSOR_CAMERA];
+}
+
+// The inverse-depth columns of the solve system (free landmarks), one deterministic gather per visual batch into the
+// zeroed side rows; runs before the assembly reads them.
+int launch_rho_side(clic_estimator* E, const double* state, const int* ctl) {
+  if (E->L.n_free_landmarks <= 0) return CLIC_OK;
+  CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.D + 2) * sizeof(double), E->stream));
+  PassParams pp = pass_params(E, state, ctl);
+  int rc;
+  for (auto& b : E->image) {
+    if (b->marg) continue;
+    if ((rc = wait_ready(E, b->ex))) return rc;
+    ImageStream st = b->st;
+    image_pass_fields(E, st, true);
+    st.rho_side = E->d_rho_side.as<double>();
+    const ImageShared ish = image_shared(E, b.get());
+    const size_t smem = rho_side_smem_doubles(E->K, E->L.D) * sizeof(double);
+    static size_t set_smem = 0;
+    if (smem > set_smem) {
+      CU(cudaFuncSetAttribute(rho_side_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_smem = smem;
+    }
+    const int grid = std::max(1, std::min(2 * E->n_sm, (E->n_lm + kRhoWarps - 1) / kRhoWarps));
+    CU(launch_pdl(rho_side_kernel, grid, kRhoWarps * 32, smem, E->stream, st, pp, ish, (const int*)b->lm_start.as<int>(),
+                  (const int*)b->lm_obs.as<int>(), E->n_lm));
+    E->launches++;
+  }
+  return CLIC_OK;
 }
 
 // small_factors_kernel over E->small_f into (Hp, bp, cost2): after the assembly, or into the fused pass's addend system
@@ -1021,7 +1051,7 @@ int run_pass_fused(clic_estimator* E, const double* state, bool jac, double* Hp,
     fa.ish = image_shared(E, F.gb);
   }
   if (jac && E->L.n_free_landmarks > 0) {
-    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.D + 2) * sizeof(double), E->stream));
+    if ((rc = launch_rho_side(E, state, ctl))) return rc;
     fa.rho_side = E->d_rho_side.as<double>();
     fa.rho0 = E->L.col_inv_depth;
     fa.n_rho = E->L.n_free_landmarks;
@@ -1125,8 +1155,8 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   if (E->fused.ok) return run_pass_fused(E, state, jac, Hp, bp, cost2, ctl, set);
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
-  if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: accumulated by the visual kernels
-    CU(cudaMemsetAsync(E->d_rho_side.p, 0, (size_t)E->L.n_free_landmarks * (E->L.D + 2) * sizeof(double), E->stream));
+  if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: gathered per landmark
+    if ((rc = launch_rho_side(E, state, ctl))) return rc;
   pp.pdl_first = 1;  // the first factor kernel of the pass; cleared after each launch
   auto launch_loam = [&](LoamBatch* b) -> int {
     StreamExec& ex = b->ex;
@@ -1724,16 +1754,23 @@ int marginalize_impl(clic_estimator* E, clic_prior** out) {
   }
   for (auto& b : E->image) {
     if (!b->marg) continue;
-    if (n_rho > 0) {  // second run: same records, plus the landmark side rows under the final column layout
-      b->st.rho_side = d_side.as<double>();
-      b->st.lm_col = d_lm_col.as<int32_t>();
-      b->st.knot_col = d_kc.as<int>();
-      b->st.Dtot = pos;
-      b->st.rho0 = rho0;
-      b->st.col_toff_cam = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_CAMERA);
-      if ((rc = launch_image_marg(*b))) return rc;
-      b->st.rho_side = nullptr;
-      b->st.lm_col = nullptr;
+    if (n_rho > 0) {  // the landmark side rows under the final column layout: per-landmark gather (deterministic)
+      ImageStream st = b->st;
+      st.rho_side = d_side.as<double>();
+      st.lm_col = d_lm_col.as<int32_t>();
+      st.knot_col = d_kc.as<int>();
+      st.Dtot = pos;
+      st.rho0 = rho0;
+      st.col_toff_cam = find(CLIC_BLOCK_T_OFFSET, CLIC_SENSOR_CAMERA);
+      const ImageShared ish = image_shared(*b);
+      const size_t smem = rho_side_smem_doubles(K, pos) * sizeof(double);
+      CU(cudaFuncSetAttribute(rho_side_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PassParams ppm = pass_params(E, E->d_state.as<double>(), nullptr);
+      ppm.marg_mode = 1;
+      const int grid = std::max(1, std::min(2 * E->n_sm, (E->n_lm + kRhoWarps - 1) / kRhoWarps));
+      rho_side_kernel<<<grid, kRhoWarps * 32, smem, E->stream>>>(st, ppm, ish, (const int*)b->lm_start.as<int>(),
+                                                                 (const int*)b->lm_obs.as<int>(), E->n_lm);
+      E->launches++;
     }
     StreamDesc d{};
     d.fin = b->ex.fin.as<double>();
@@ -2514,6 +2551,17 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     s_tj[k] = t_j[i];
     for (int c = 0; c < 3; c++) { s_pi[3 * k + c] = p_i[3 * i + c]; s_pj[3 * k + c] = p_j[3 * i + c]; }
     s_lm[k] = landmark[i];
+  }
+  {  // CSR landmark -> stored positions (ascending), for the per-landmark gather of the inverse-depth columns
+    std::vector<int32_t> start((size_t)E->n_lm + 1, 0), obs((size_t)n_in);
+    for (int64_t k = 0; k < n; k++) if (B->gather[k] >= 0) start[s_lm[k] + 1]++;
+    for (int l = 0; l < E->n_lm; l++) start[l + 1] += start[l];
+    std::vector<int32_t> fill(start.begin(), start.end() - 1);
+    for (int64_t k = 0; k < n; k++) if (B->gather[k] >= 0) obs[fill[s_lm[k]]++] = (int32_t)k;
+    int rc2;
+    if ((rc2 = to_device(E, B->lm_start, start.data(), start.size())) || (rc2 = to_device(E, B->lm_obs, obs.data(), obs.size())))
+      return rc2;
+    CU(cudaStreamSynchronize(cs));  // the vectors are locals
   }
   trace.lap("sort+stage");
   // Distinct (timestamp, role) pairs -> pose packs (tiny open-addressing table; abandoned beyond kMaxPosePacks,

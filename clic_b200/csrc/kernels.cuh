@@ -949,8 +949,9 @@ struct ImageStream {
   double loss_a;
   // Pose packs (n_packs > 0): every feature of a camera frame shares its timestamp, so the spline poses and their
   // Jacobian maps are evaluated once per distinct (timestamp, role) by each CTA and the factors only compose them.
-  // Free inverse depths (fixed_depth = false; rho_side != nullptr): the terms that involve a landmark's column are
-  // scattered per factor with atomics into rho_side[rank][col] = H[rho, col] (col < Dtot, any non-rho column),
+  // Free inverse depths (fixed_depth = false): the terms that involve a landmark's column are gathered per LANDMARK by
+  // rho_side_kernel (one warp per landmark over its observations, fixed order: deterministic; round 1 scattered them per
+  // factor with atomics) into rho_side[rank][col] = H[rho, col] (col < Dtot, any non-rho column),
   // [Dtot] = H[rho, rho], [Dtot + 1] = b[rho]  (two factors of one interval key see different landmarks, so these
   // cannot ride in the per-key tiles).  The rho columns are rho0 .. rho0 + n_rho - 1 (last in a solve, among the
   // dropped ones in a marginalization).
@@ -1023,7 +1024,7 @@ __device__ __forceinline__ void image_body(const ImageStream& st, const PassPara
       p_i = mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]);
       p_j = mk(st.pj[0][idx], st.pj[1][idx], 1.0);
       rho_inv = invd[st.landmark[idx]];
-      if (st.rho_side) rho_col = st.lm_col[st.landmark[idx]];
+      if (st.lm_col) rho_col = st.lm_col[st.landmark[idx]];
       if (PACKED) { pack_i = st.id_i[idx]; pack_j = st.id_j[idx]; }
     } else {
       si = sj = 0; ui = uj = 0.0;
@@ -1048,21 +1049,6 @@ __device__ __forceinline__ void image_body(const ImageStream& st, const PassPara
                                                 p_i, p_j, rho_inv, sh, true, sink, row_sel, rho_col >= 0)
                             : image_eval(W, si, ui, sj, uj, p_i, p_j, rho_inv, sh, true, sink, row_sel, rho_col >= 0);
         if (counts) { if (any_free) cost += 0.5 * rho; else fcost += 0.5 * rho; }
-        if (st.rho_side && mine && rho_col >= 0) {  // this lane's row is still in the tile: columns of the landmark
-          double* side = st.rho_side + (size_t)(rho_col - st.rho0) * (st.Dtot + 2);
-          const double jr = Jt[50 * kJtStride + lane];
-          for (int c = 0; c < 49; c++) {
-            const double v = Jt[c * kJtStride + lane];
-            if (v == 0.0) continue;
-            int g;
-            if (c < 24) { const int kc = st.knot_col[si + c / 6]; g = kc < 0 ? -1 : kc + c % 6; }
-            else if (c < 48) { const int kc = st.knot_col[sj + (c - 24) / 6]; g = kc < 0 ? -1 : kc + (c - 24) % 6; }
-            else g = st.col_toff_cam;
-            if (g >= 0) atomicAdd(side + g, jr * v);
-          }
-          atomicAdd(side + st.Dtot, jr * jr);
-          atomicAdd(side + st.Dtot + 1, jr * Jt[49 * kJtStride + lane]);
-        }
         __syncwarp();
       } else {
         NullSink sink;
@@ -1101,6 +1087,92 @@ image_kernel(ImageStream st, PassParams pp, int total_slabs, RecordBuf rb, Image
   WindowView W = stage_window(smem, pp, &rest);
   image_body<JAC, PACKED>(st, pp, total_slabs, rb, sh, W, rest, blockIdx.x, gridDim.x);
   pass_epilogue(pp);
+}
+
+// The inverse-depth columns of the system (free or marginalised landmarks): side[rank][g] = H[rho, g] for every other
+// column g, [Dtot] = H[rho, rho], [Dtot + 1] = b[rho].  One warp per landmark: its observations (lm_obs[lm_start[l] ..
+// lm_start[l+1]) = stored positions, ascending) are evaluated 16 at a time — lanes 2o, 2o + 1 build the two residual rows
+// of observation o in shared memory — and then added observation by observation, lanes over the local columns (window i,
+// then window j, then the time offset: two windows may share a knot), into the warp's shared side row, which goes out
+// with plain stores.  Same order every run; no atomics.
+constexpr int kRhoWarps = 4;
+__host__ __device__ inline size_t rho_side_smem_doubles(int K, int Dtot) {
+  return window_smem_doubles(K) + (size_t)kRhoWarps * (32 * 56 + ((Dtot + 2 + 1) & ~1));
+}
+struct SmemPlainRow {
+  double* row;
+  __device__ __forceinline__ void put(int, int col, double v) { row[col] = v; }
+  __device__ __forceinline__ void row_done(int) {}
+};
+__global__ void __launch_bounds__(kRhoWarps * 32) rho_side_kernel(ImageStream st, PassParams pp, ImageShared sh,
+                                                                   const int* lm_start, const int* lm_obs, int n_lm) {
+  pdl_wait();
+  pdl_trigger();
+  if (pp.ctl && pp.ctl[0]) return;
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int side_n = st.Dtot + 2, side_pad = (side_n + 1) & ~1;
+  double* rows = rest + (size_t)warp * (32 * 56 + side_pad);
+  double* side_s = rows + 32 * 56;
+  const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 2];
+  const double* invd = pp.state + pp.sl.off_invd();
+  for (int l = blockIdx.x * kRhoWarps + warp; l < n_lm; l += gridDim.x * kRhoWarps) {
+    const int col = st.lm_col[l];
+    if (col < 0) continue;
+    for (int c = lane; c < side_n; c += 32) side_s[c] = 0.0;
+    const int o0 = lm_start[l], o1 = lm_start[l + 1];
+    for (int base = o0; base < o1; base += 16) {
+      __syncwarp();
+      const int o = base + (lane >> 1);
+      int si = 0, sj = 0;
+      bool valid = false;
+      if (o < o1) {
+        const int64_t idx = lm_obs[o];
+        const int64_t ti = st.ti_ns[idx], tj = st.tj_ns[idx];
+        double ui = 0.0, uj = 0.0;
+        valid = ti != kDropped && tj != kDropped && index_ns(ti + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &si, &ui) &&
+                index_ns(tj + toff, pp.t0_ns, pp.dt_ns, pp.sl.K, &sj, &uj);
+        if (valid) {
+          SmemPlainRow sink;
+          sink.row = rows + lane * 56;
+          image_eval(W, si, ui, sj, uj, mk(st.pi[0][idx], st.pi[1][idx], st.pi[2][idx]), mk(st.pj[0][idx], st.pj[1][idx], 1.0),
+                     invd[l], sh, true, sink, lane & 1, true);
+        }
+      }
+      __syncwarp();
+      for (int q = 0; q < 16 && base + q < o1; q++) {
+        const int v_q = __shfl_sync(0xffffffffu, valid ? 1 : 0, 2 * q);
+        const int si_q = __shfl_sync(0xffffffffu, si, 2 * q), sj_q = __shfl_sync(0xffffffffu, sj, 2 * q);
+        if (!v_q) continue;
+        for (int rr = 0; rr < 2; rr++) {
+          const double* row = rows + (2 * q + rr) * 56;
+          const double jr = row[50];
+          if (lane < 24) {  // window of t_i
+            const int kc = st.knot_col[si_q + lane / 6];
+            if (kc >= 0) side_s[kc + lane % 6] += jr * row[lane];
+          }
+          __syncwarp();
+          if (lane < 24) {  // window of t_j
+            const int kc = st.knot_col[sj_q + lane / 6];
+            if (kc >= 0) side_s[kc + lane % 6] += jr * row[24 + lane];
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (st.col_toff_cam >= 0) side_s[st.col_toff_cam] += jr * row[48];
+            side_s[st.Dtot] += jr * jr;
+            side_s[st.Dtot + 1] += jr * row[49];
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+    double* side = st.rho_side + (size_t)(col - st.rho0) * side_n;
+    for (int c = lane; c < side_n; c += 32) side[c] += side_s[c];  // (zeroed per pass; batches run one after the other)
+    __syncwarp();
+  }
 }
 
 // ---------------- one-shot all-reduce over NVLink peer memory ----------------

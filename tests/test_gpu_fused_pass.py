@@ -117,6 +117,27 @@ def test_fused_pass_is_deterministic(cuda):
         assert np.array_equal(H, runs[0][0]) and np.array_equal(b, runs[0][1]) and c == runs[0][2] and f == runs[0][3]
 
 
+def test_free_inverse_depth_system_is_deterministic(cuda):
+    """The inverse-depth columns are gathered per landmark in a fixed order (rho_side_kernel), not scattered with
+    atomics: rebuilt estimators and repeated passes give bit-identical systems on both layouts."""
+    sw = S.config(3, 0.5)
+    for ctx in (None, per_stream_kernels):
+        runs = []
+        for _ in range(3):
+            if ctx is None:
+                est, _ = build(cuda, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=True)
+                runs += [est.Evaluate(), est.Evaluate()]
+                est.close()
+            else:
+                with ctx():
+                    est, _ = build(cuda, sw, unlock_bias=True, fixed_depth=False, unlock_cam_toff=True)
+                    runs += [est.Evaluate(), est.Evaluate()]
+                    est.close()
+        assert runs[0][0].shape[0] > 6 * sw.window.knot_q.shape[0] + 90  # the landmark columns are in the system
+        for H, b, c, f in runs[1:]:
+            assert np.array_equal(H, runs[0][0]) and np.array_equal(b, runs[0][1]) and c == runs[0][2]
+
+
 def test_two_batches_of_one_kind_fall_back(cuda, oracle):
     """More than one batch per stream kind is not fused; both layouts give the same system."""
     sw = S.config(1)
