@@ -79,6 +79,10 @@ def main():
                     seg = us[c0:c0 + n, 1]
                     print("    %-14s CTAs %3d..%3d  factor phase ends  min %.2f  mean %.2f  max %.2f us" %
                           (KINDS[kind], c0, c0 + n - 1, seg.min(), seg.mean(), seg.max()))
+                    body = (st[c0:c0 + n, 6:8] - t0) / 1e3  # warp 0 of each CTA: first slab begins, last slab done
+                    print("    %-14s   warp 0: slabs begin mean %.2f  slabs done mean %.2f max %.2f  -> finish + write "
+                          "mean %.2f us" % ("", body[:, 0].mean(), body[:, 1].mean(), body[:, 1].max(),
+                                            (seg - body[:, 1]).mean()))
                     c0 += n
                 print("    phase A per CTA (A end - staged): mean %.2f max %.2f us; staging (staged - barrier) mean %.2f; "
                       "barrier wait of the last CTA %.2f us" % (

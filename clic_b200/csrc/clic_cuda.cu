@@ -534,7 +534,8 @@ int check_p2p(clic_estimator* E) {
 // cost — per-CTA dense system, grid barrier — and always on several ranks, where it carries the exchange).  Read at
 // every layout so that a test can flip it between two estimators.
 int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }
-// Static cost model of the grid partition: a stream on n CTAs takes  f + ceil(slabs / (8 n)) * w  microseconds — w per
+// Static cost model of the grid partition: a stream on n CTAs takes  f + w * max(slabs / (8 n), lat * ceil(slabs / (8 n)))
+// microseconds (t_of in build_fused) — w per
 // 32-factor slab (16 for the visual stream) of one warp with two warps per SM sub-partition, f the stream's fixed part
 // (window staging, pose packs, first-slab latency, the dense finish) — fitted to %globaltimer stamps of the C5 window
 // and of its 1/8 shard on B200 (bench_micro/fused_probe.py; profiles/).  Only the ratios matter, and a wrong model costs
@@ -542,7 +543,7 @@ int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] 
 // CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.7, 3.2, 3.5, 13.8, 9.6, 12.0}, {14.0, 10.8, 17.5, 31.0, 41.6, 50.0}};
+  static FusedModel m = {{3.7, 3.2, 3.4, 13.8, 9.6, 12.0}, {14.0, 10.8, 14.5, 31.0, 41.6, 50.0}};
   static bool init = false;
   if (!init) {
     init = true;
@@ -622,35 +623,39 @@ int build_fused(clic_estimator* E) {
     for (auto& j : js) work += j.w * (double)j.slabs;
     if (work < 6000.0) return CLIC_OK;
   }
+  // Modelled finishing time of stream j on n CTAs.  A CTA's 8 warps share one FP64 pipe, so its time is the larger of
+  // the throughput term (slabs per CTA x w / 8) and the latency term (whole rounds x the time one warp needs for a slab
+  // when it has the SM to itself, lat x w): the second only matters for the heavy bodies at 1-2 slabs per warp (the
+  // 8-GPU shard of C5: IMU 1.14 slabs per warp takes 46 us, not the 59 us two full rounds would).
+  static const double lat = [] { const char* e = getenv("CLIC_FUSED_LAT"); return e ? atof(e) : 0.4; }();
+  auto t_of = [&](const Job& j, int n) {
+    const double per_warp = (double)j.slabs / (double)(kWarpsPerCta * n);
+    const double rounds = (double)((j.slabs + (int64_t)kWarpsPerCta * n - 1) / ((int64_t)kWarpsPerCta * n));
+    return j.f + j.w * std::max(per_warp, lat * rounds);
+  };
   {
-    // exact min-max under the model: the finishing time T is one of  f_j + m w_j;  a stream needs
-    // n_j(T) = ceil(slabs_j / (8 floor((T - f_j) / w_j))) CTAs; smallest T whose CTAs fit the grid
+    // min-max under the model: smallest T for which every stream fits, n_j(T) = fewest CTAs with t_of <= T
     auto need = [&](double T, std::vector<int>& n) -> bool {
       int tot = 0;
       for (size_t i = 0; i < js.size(); i++) {
-        const double room = (T - js[i].f) / js[i].w + 1e-9;
-        if (room < 1.0) return false;
-        const int64_t m = (int64_t)room;  // slabs per warp that fit
-        const int64_t c = (js[i].slabs + kWarpsPerCta * m - 1) / (kWarpsPerCta * m);
-        if (c > js[i].cap) return false;
-        n[i] = (int)std::max<int64_t>(1, c);
-        tot += n[i];
+        if (t_of(js[i], js[i].cap) > T) return false;
+        int lo = 1, hi = js[i].cap;
+        while (lo < hi) {  // t_of is non-increasing in n
+          const int mid = (lo + hi) / 2;
+          if (t_of(js[i], mid) <= T) hi = mid; else lo = mid + 1;
+        }
+        n[i] = lo;
+        tot += lo;
       }
       return tot <= E->n_sm;
     };
-    std::vector<double> cand;
-    for (auto& j : js) {
-      const int64_t m_max = (j.slabs + kWarpsPerCta - 1) / kWarpsPerCta;
-      for (int64_t m = 1; m <= m_max; m = m < 64 ? m + 1 : m + m / 32)  // every m while small, ~3 % steps beyond
-        cand.push_back(j.f + (double)m * j.w);
-      cand.push_back(j.f + (double)m_max * j.w);
-    }
-    std::sort(cand.begin(), cand.end());
+    double lo = 0.0, hi = 0.0;
+    for (auto& j : js) hi = std::max(hi, t_of(j, 1));
     std::vector<int> n(js.size(), 1), best;
-    size_t lo = 0, hi = cand.size();
-    while (lo < hi) {  // feasibility is monotone in T
-      const size_t mid = (lo + hi) / 2;
-      if (need(cand[mid], n)) { best = n; hi = mid; } else { lo = mid + 1; }
+    if (need(hi, n)) best = n;
+    for (int it = 0; it < 48 && !best.empty(); it++) {  // feasibility is monotone in T
+      const double mid = 0.5 * (lo + hi);
+      if (need(mid, n)) { best = n; hi = mid; } else { lo = mid; }
     }
     if (!best.empty())
       for (size_t i = 0; i < js.size(); i++) js[i].n = best[i];
@@ -663,7 +668,7 @@ int build_fused(clic_estimator* E) {
     double worst = 0.0;
     for (size_t i = 0; i < js.size(); i++) {
       if (js[i].n >= js[i].cap) continue;
-      const double t = js[i].f + js[i].w * (double)((js[i].slabs + (int64_t)kWarpsPerCta * js[i].n - 1) / ((int64_t)kWarpsPerCta * js[i].n));
+      const double t = t_of(js[i], js[i].n);
       if (best < 0 || t > worst) { best = (int)i; worst = t; }
     }
     if (best < 0) break;

@@ -228,7 +228,15 @@ struct DenseOut {
   const StreamDesc* sd;    // this stream's column descriptor (a shared-memory copy: it is read per target entry)
   const int* knot_col;     // [K] column of the knot's dtheta, -1 if constant (shared-memory copy)
   int* key_cols;           // shared memory scratch: [1 + 64 * 3] ints (see build_key_cols)
+  unsigned long long* stamp;  // null, or this CTA's phase stamps: [6] = warp 0 starts its slabs, [7] = warp 0 is through them
 };
+__device__ __forceinline__ void dense_stamp(const DenseOut* dn, int i) {
+  if (dn && dn->stamp && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dn->stamp[i] = t;
+  }
+}
 __device__ __forceinline__ int packed_row_start(int D, int gi) { return gi * D - gi * (gi - 1) / 2; }
 
 // The distinct global columns a record of interval key `key` touches, ascending, each with its (<= 2) local logical
@@ -530,6 +538,7 @@ __device__ __forceinline__ void loam_body(const LoamStream& st, const PassParams
 #define CLIC_LOAM_PREFETCH 1
 #endif
   if (CLIC_LOAM_PREFETCH) prefetch(slab0 * 32 + lane);
+  if (DENSE) dense_stamp(dn, 6);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * 32 >= st.n) break;
     if (!CLIC_LOAM_PREFETCH) prefetch((slab0 + sl) * 32 + lane);  // plain load at use (more resident warps hide it)
@@ -598,6 +607,7 @@ __device__ __forceinline__ void loam_body(const LoamStream& st, const PassParams
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
   if (DENSE) {
+    dense_stamp(dn, 7);
     cta_finish_dense<3, 1, WARPS>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
     return;
   }
@@ -867,6 +877,7 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
   const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
   const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
   const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
+  if (DENSE) dense_stamp(dn, 6);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * 32 >= st.n) break;
     const int64_t idx = (slab0 + sl) * 32 + lane;
@@ -915,6 +926,7 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
   if (DENSE) {
+    dense_stamp(dn, 7);
     cta_finish_dense<NT, 0, kWarpsPerCta>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
     return;
   }
@@ -1008,6 +1020,7 @@ __device__ __forceinline__ void image_body(const ImageStream& st, const PassPara
   const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
   const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
   const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
+  if (DENSE) dense_stamp(dn, 6);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * kImageFactorsPerSlab >= st.n) break;
     const int64_t idx = (slab0 + sl) * kImageFactorsPerSlab + (lane & 15);
@@ -1066,6 +1079,7 @@ __device__ __forceinline__ void image_body(const ImageStream& st, const PassPara
     fcost += __shfl_xor_sync(0xffffffffu, fcost, o);
   }
   if (DENSE) {
+    dense_stamp(dn, 7);
     cta_finish_dense<NT, 0, kWarpsPerCta>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
     return;
   }

@@ -256,6 +256,7 @@ pass_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ PassPa
     dn.D = D;
     dn.knot_col = p_knot_col;
     dn.key_cols = reinterpret_cast<int*>(Hs + ((n_tot + 1) & ~1));
+    dn.stamp = stamp;
     if (fa.part[1].n_ctas && cta >= fa.part[1].cta0 && cta < fa.part[1].cta0 + fa.part[1].n_ctas) {
       dn.sd = p_sd;
       loam_body<JAC, kWarpsPerCta, 1, true>(fa.loam[1], pp, fa.part[1].total_slabs, fa.part[1].rb, W, rest,

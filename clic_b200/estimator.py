@@ -401,7 +401,7 @@ class TrajectoryEstimator:
 
     def pass_stamps(self, enable=True):
         """Per-CTA %globaltimer stamps (ns) of the last fused pass recorded while enabled: (grid, 8) uint64 array
-        [start, end of factor phase, after the grid barrier, after key staging, end of assembly, end, -, -], or None;
+        [start, end of factor phase, after the grid barrier, after key staging, end of assembly, end, warp 0 begins its slabs, warp 0 is through its slabs], or None;
         then sets the switch."""
         n = C.c_int32(0)
         buf = np.zeros((1024, 8), np.uint64)
