@@ -94,6 +94,37 @@ class Layout(C.Structure):
     ]
 
 
+class PreIntegration(C.Structure):
+    """clic_preintegration (include/clic_cuda.h): IntegrationBase reduced to what PreIntegrationFactor reads."""
+    _fields_ = [
+        ("sum_dt", C.c_double),
+        ("delta_p", C.c_double * 3),
+        ("delta_q", C.c_double * 4),
+        ("delta_v", C.c_double * 3),
+        ("linearized_ba", C.c_double * 3),
+        ("linearized_bg", C.c_double * 3),
+        ("jacobian", C.c_double * 225),
+        ("sqrt_info", C.c_double * 225),
+        ("gravity_norm", C.c_double),
+    ]
+
+
+class FactorDesc(C.Structure):
+    """clic_factor_desc (include/clic_cuda.h)."""
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("geo_type", C.c_int32),
+        ("t_a_ns", C.c_int64),
+        ("t_b_ns", C.c_int64),
+        ("d", C.c_double * 32),
+        ("x", C.c_double * 16),
+        ("pre", C.POINTER(PreIntegration)),
+    ]
+
+
+(FACTOR_POSE, FACTOR_LOCAL_VELOCITY, FACTOR_RELATIVE_ROTATION, FACTOR_IMAGE_DEPTH, FACTOR_PREINTEGRATION,
+ FACTOR_IMAGE_3D2D, FACTOR_IMAGE_ONE_POSE, FACTOR_EPIPOLAR, FACTOR_LOAM_OPT_MAP_POSE, FACTOR_RELATIVE_LOAM) = range(10)
+
 SENSOR_IMU, SENSOR_LIDAR, SENSOR_CAMERA = 0, 1, 2
 GEO_LINE, GEO_PLANE = 0, 1
 (BLOCK_KNOT_ROT, BLOCK_KNOT_POS, BLOCK_BIAS_GYRO, BLOCK_BIAS_ACCEL, BLOCK_GRAVITY, BLOCK_T_OFFSET,
@@ -130,6 +161,9 @@ PROTOTYPES = {
     "clic_add_local_velocity": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, C.c_double, c_int64_p]),
     "clic_add_relative_rotation": (C.c_int, [H, C.c_double, C.c_double, c_double_p, c_double_p, c_int32_p]),
     "clic_add_image_depth": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32]),
+    "clic_add_preintegration": (C.c_int, [H, C.c_int64, C.c_int64, C.POINTER(PreIntegration), C.c_int32, C.c_int32,
+                                          c_int32_p]),
+    "clic_evaluate_factor": (C.c_int, [H, C.POINTER(FactorDesc), c_int32_p, c_double_p, c_int32_p, c_double_p, C.c_int64]),
     "clic_add_global_velocity": (C.c_int, [H, C.c_double, c_double_p, C.c_double, c_int32_p]),
     "clic_add_image": (C.c_int, [H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.c_int32,
                                  C.c_int32, c_int64_p]),

@@ -341,6 +341,8 @@ struct clic_estimator {
   std::vector<SmallFactor> small_f;        // pose / local velocity / relative rotation / image depth factors (§8f-4)
   DevBuf d_small;
   bool small_dirty = true;
+  std::vector<PreintData> small_pre;       // pre-integration data of the kSmallPreIntegration factors (SmallFactor::ext)
+  DevBuf d_small_pre;
   std::vector<std::unique_ptr<ImageBatch>> image;
   std::vector<BiasFac> bias_f;
   struct GravFac { double g0[3], sqrt_info[3]; int marg; };
@@ -1021,6 +1023,11 @@ int launch_small_factors(clic_estimator* E, const double* state, double* Hp, dou
     CU(E->d_small.ensure(E->small_f.size() * sizeof(SmallFactor)));
     CU(cudaMemcpyAsync(E->d_small.p, E->small_f.data(), E->small_f.size() * sizeof(SmallFactor), cudaMemcpyHostToDevice,
                        E->stream));
+    if (!E->small_pre.empty()) {
+      CU(E->d_small_pre.ensure(E->small_pre.size() * sizeof(PreintData)));
+      CU(cudaMemcpyAsync(E->d_small_pre.p, E->small_pre.data(), E->small_pre.size() * sizeof(PreintData),
+                         cudaMemcpyHostToDevice, E->stream));
+    }
     CU(cudaStreamSynchronize(E->stream));
     E->small_dirty = false;
   }
@@ -1029,9 +1036,11 @@ int launch_small_factors(clic_estimator* E, const double* state, double* Hp, dou
   sc.knot_col = E->d_knot_col.as<int>();
   sc.col_toff_imu = E->L.col_t_offset[CLIC_SENSOR_IMU];
   sc.lm_col = E->L.n_free_landmarks > 0 ? E->d_lm_col.as<int32_t>() : nullptr;
+  sc.col_bias_gyro = E->L.col_bias_gyro;
+  sc.col_bias_accel = E->L.col_bias_accel;
   const size_t smem = window_smem_doubles(E->K) * sizeof(double) + sizeof(SmallOut) + 16;
-  CU(launch_pdl(small_factors_kernel, 1, 128, smem, E->stream, E->d_small.as<SmallFactor>(), (int)E->small_f.size(), pp, sc,
-                Hp, bp, std::max(1, E->L.D), cost2, jac ? 1 : 0));
+  CU(launch_pdl(small_factors_kernel, 1, 128, smem, E->stream, E->d_small.as<SmallFactor>(), (int)E->small_f.size(),
+                (const PreintData*)E->d_small_pre.as<PreintData>(), pp, sc, Hp, bp, std::max(1, E->L.D), cost2, jac ? 1 : 0));
   E->launches++;
   return CLIC_OK;
 }
@@ -2451,6 +2460,111 @@ CLIC_API int clic_add_image_depth(clic_estimator* E, const double p_i[3], const 
   E->lm_free[landmark] = 1;  // the inverse depth is a free parameter of the solve
   E->small_dirty = true;
   E->layout_dirty = true;
+  return CLIC_OK;
+}
+
+namespace {
+PreintData to_preint(const clic_preintegration* p) {
+  PreintData d;
+  d.sum_dt = p->sum_dt;
+  d.gravity_norm = p->gravity_norm;
+  for (int i = 0; i < 3; i++) {
+    d.delta_p[i] = p->delta_p[i]; d.delta_v[i] = p->delta_v[i];
+    d.linearized_ba[i] = p->linearized_ba[i]; d.linearized_bg[i] = p->linearized_bg[i];
+  }
+  for (int i = 0; i < 4; i++) d.delta_q[i] = p->delta_q[i];
+  // StateOrder (integration_base.h:20-26): O_P 0, O_R 3, O_V 6, O_BA 9, O_BG 12
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      d.dp_dba[3 * r + c] = p->jacobian[(0 + r) * 15 + 9 + c];
+      d.dp_dbg[3 * r + c] = p->jacobian[(0 + r) * 15 + 12 + c];
+      d.dq_dbg[3 * r + c] = p->jacobian[(3 + r) * 15 + 12 + c];
+      d.dv_dba[3 * r + c] = p->jacobian[(6 + r) * 15 + 9 + c];
+      d.dv_dbg[3 * r + c] = p->jacobian[(6 + r) * 15 + 12 + c];
+    }
+  for (int i = 0; i < 225; i++) d.sqrt_info[i] = p->sqrt_info[i];
+  return d;
+}
+}  // namespace
+
+CLIC_API int clic_add_preintegration(clic_estimator* E, int64_t ta_ns, int64_t tb_ns, const clic_preintegration* pre,
+                                     int32_t slot_i, int32_t slot_j, int32_t* added) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!pre) return fail(CLIC_ERR_BAD_ARGUMENT, "null pre-integration");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "pre-integration factor in a marginalization estimator");
+  if (slot_i < 0 || slot_j < 0 || slot_i >= E->n_bias || slot_j >= E->n_bias)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bias slot out of range");
+  if (added) *added = 0;
+  if (ta_ns < E->minTimeNs() || ta_ns > E->maxTimeNs() || tb_ns < E->minTimeNs() || tb_ns > E->maxTimeNs()) return CLIC_OK;
+  SmallFactor f{};
+  f.kind = kSmallPreIntegration;
+  f.t_a = ta_ns;
+  f.t_b = tb_ns;
+  f.slot_i = slot_i;
+  f.slot_j = slot_j;
+  f.ext = (int)E->small_pre.size();
+  E->small_pre.push_back(to_preint(pre));
+  E->small_f.push_back(f);
+  E->small_dirty = true;
+  E->layout_dirty = true;
+  if (added) *added = 1;
+  return CLIC_OK;
+}
+
+CLIC_API int clic_evaluate_factor(clic_estimator* E, const clic_factor_desc* fd, int32_t* n_res, double* residual,
+                                  int32_t* n_cols, double* jac, int64_t jac_capacity) {
+  if (!ok_handle(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!fd || !n_res || !residual || !n_cols) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  // tangent widths of the parameter blocks after the knots, per kind (the reference's block order)
+  static const int kWidths[10][4] = {{1, 0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {1, 0, 0, 0}, {3, 3, 3, 3},
+                                     {3, 1, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {3, 3, 0, 0}, {0, 0, 0, 0}};
+  if (fd->kind < 0 || fd->kind > 9) return fail(CLIC_ERR_BAD_ARGUMENT, "unknown factor kind");
+  if (fd->kind == CLIC_FACTOR_PREINTEGRATION && !fd->pre) return fail(CLIC_ERR_BAD_ARGUMENT, "null pre-integration");
+  CU(cudaSetDevice(E->device));
+  AllocScope alloc_scope(E->stream);
+  int rc = ensure_layout(E);
+  if (rc) return rc;
+  SmallFactor f{};
+  f.kind = fd->kind;
+  f.geo_type = fd->geo_type;
+  f.t_a = fd->t_a_ns;
+  f.t_b = fd->t_b_ns;
+  for (int i = 0; i < 24; i++) f.d[i] = fd->d[i];
+  SmallX X;
+  for (int i = 0; i < 16; i++) X.x[i] = fd->x[i];
+  int cols = 6 * E->K;
+  for (int k = 0; k < 4; k++) {
+    X.xcol[k] = kWidths[fd->kind][k] > 0 ? cols : -1;
+    cols += kWidths[fd->kind][k];
+  }
+  DevBuf d_pre, d_out;
+  if (fd->pre) {
+    const PreintData pd = to_preint(fd->pre);
+    CU(d_pre.ensure(sizeof(PreintData)));
+    CU(cudaMemcpyAsync(d_pre.p, &pd, sizeof(PreintData), cudaMemcpyHostToDevice, E->stream));
+    CU(cudaStreamSynchronize(E->stream));  // pd is a local
+  }
+  const size_t n_out = 20 + (size_t)kSmallMaxRows * cols;
+  CU(d_out.ensure(n_out * sizeof(double)));
+  CU(cudaMemsetAsync(d_out.p, 0, 4 * sizeof(double), E->stream));
+  PassParams pp = pass_params(E, E->d_state.as<double>(), nullptr);
+  const size_t smem = window_smem_doubles(E->K) * sizeof(double) + sizeof(SmallOut) + (size_t)E->K * sizeof(int) + 16;
+  factor_jacobian_kernel<<<1, 128, smem, E->stream>>>(f, (const PreintData*)d_pre.as<PreintData>(), pp, ldq(E->S_CtoI),
+                                                      ldv(E->p_CinI), X, cols, d_out.as<double>());
+  CU(cudaGetLastError());
+  E->launches++;
+  std::vector<double> h(n_out);
+  CU(cudaMemcpyAsync(h.data(), d_out.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  if (h[0] == 0.0) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_evaluate_factor: a measurement time is outside the window");
+  const int nr = (int)h[1];
+  *n_res = nr;
+  *n_cols = cols;
+  for (int r = 0; r < nr; r++) residual[r] = h[4 + r];
+  if (jac) {
+    if ((int64_t)nr * cols > jac_capacity) return fail(CLIC_ERR_BAD_ARGUMENT, "Jacobian buffer too small");
+    std::memcpy(jac, h.data() + 20, (size_t)nr * cols * sizeof(double));
+  }
   return CLIC_OK;
 }
 

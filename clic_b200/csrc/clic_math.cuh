@@ -238,6 +238,29 @@ CLIC_HD M3 left_jacobian_inv(V3 phi) {
   return J;
 }
 
+// leftJacobianSO3 (src/utils/sophus_utils.hpp:238-268)
+CLIC_HD M3 left_jacobian(V3 phi) {
+  double n2 = dot(phi, phi);
+  M3 K = hat(phi);
+  M3 K2 = mmul(K, K);
+  double c1, c2;
+  if (n2 > kEps) {
+    double n = sqrt(n2);
+    double s, c;
+    sincos_hd(n, &s, &c);
+    c1 = (1.0 - c) / n2;
+    c2 = (n - s) / (n2 * n);
+  } else {
+    c1 = 0.5;
+    c2 = 1.0 / 6.0;
+  }
+  M3 J;
+#pragma unroll
+  for (int i = 0; i < 9; i++) J.m[i] = c1 * K.m[i] + c2 * K2.m[i];
+  J.m[0] += 1.0; J.m[4] += 1.0; J.m[8] += 1.0;
+  return J;
+}
+
 // ---- uniform cubic B-spline blending (src/spline/spline_common.h:72-138), coefficients in closed form ----
 // cumulative M~ = 1/6 [[6,0,0,0],[5,3,-3,1],[1,3,3,-2],[0,0,0,1]], plain M = 1/6 [[1,-3,3,-1],[4,0,-6,3],[1,3,3,-3],[0,0,0,1]]
 CLIC_HD void blend_cum(double u, double lam[4]) {  // value coefficients lambda~_0..3 (lambda~_0 = 1)

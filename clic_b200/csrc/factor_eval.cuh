@@ -429,16 +429,29 @@ CLIC_HD void so3_rows_logrt(const WindowView& W, int s, const So3Chain& C, V3 a,
 
 // ---- the remaining adders of TrajectoryEstimator: a handful of factors per solve at most, evaluated
 // by ONE thread each into a small dense row set over the global columns the factor touches (small_factors_kernel).
-enum { kSmallPose = 0, kSmallLocalVelocity = 1, kSmallRelativeRotation = 2, kSmallImageDepth = 3 };
+// The kinds are the CLIC_FACTOR_* values of include/clic_cuda.h (clic_evaluate_factor takes them as they are).
+enum {
+  kSmallPose = 0, kSmallLocalVelocity = 1, kSmallRelativeRotation = 2, kSmallImageDepth = 3, kSmallPreIntegration = 4,
+  kSmallImage3D2D = 5, kSmallImageOnePose = 6, kSmallEpipolar = 7, kSmallLoamOptMapPose = 8, kSmallRelativeLoam = 9
+};
 struct SmallFactor {
   int kind;
   int landmark;        // image depth
   long long t_a, t_b;  // measurement time(s) in ns (without offset)
-  double d[16];        // pose: p[3] q[4] info[6] | local velocity: v[3] w | relative rotation: S_BtoA[4] info[3]
-                       // image depth: p_i[3] p_j[3] S_CitoCj[4] p_CiinCj[3] sqrt_info
+  double d[24];        // the factor's constants, laid out as clic_factor_desc::d documents per kind
   double loss_a;       // Cauchy parameter, <= 0: none
+  int geo_type;        // the two LiDAR kinds
+  int ext;             // pre-integration: index into the PreintData array
+  int slot_i, slot_j;  // pre-integration: bias slots of t_a, t_b
 };
-constexpr int kSmallMaxRows = 6, kSmallMaxCols = 56;
+// IntegrationBase as the factor reads it (clic_preintegration), the five 3x3 blocks of its Jacobian pulled out
+struct PreintData {
+  double sum_dt, gravity_norm;
+  double delta_p[3], delta_q[4], delta_v[3], linearized_ba[3], linearized_bg[3];
+  double dp_dba[9], dp_dbg[9], dq_dbg[9], dv_dba[9], dv_dbg[9];
+  double sqrt_info[225];
+};
+constexpr int kSmallMaxRows = 15, kSmallMaxCols = 64;
 struct SmallOut {
   int nres, ncols;
   double r[kSmallMaxRows];
@@ -465,6 +478,7 @@ struct SmallCols {      // where a factor's parameter blocks sit in H (device co
   const int* knot_col;  // [K] column of the knot's dtheta (dp = +3), -1 constant
   int col_toff_imu;     // -1 constant
   const int* lm_col;    // per landmark, -1 constant (nullptr: none free)
+  int col_bias_gyro, col_bias_accel;  // + 3 * slot, -1 constant
 };
 
 // IMUPoseFactor::Evaluate (trajectory_value_factor.h:323-427).  False: the corrected time left the window.
@@ -609,7 +623,8 @@ CLIC_HD bool small_relative_rotation_eval(const WindowView& W, const SmallFactor
 }
 
 // ImageDepthFactor::Evaluate (image_feature_factor.h:666-693)
-CLIC_HD bool small_image_depth_eval(const SmallFactor& f, double d_inv, const SmallCols& sc, SmallOut* o) {
+CLIC_HD bool small_image_depth_eval(const SmallFactor& f, double d_inv, int g /* column of the inverse depth, -1 constant */,
+                                    SmallOut* o) {
   const V3 p_i = ldv(f.d), p_j = ldv(f.d + 3);
   const Q4 S = ldq(f.d + 6);
   const V3 p_CiinCj = ldv(f.d + 10);
@@ -618,7 +633,6 @@ CLIC_HD bool small_image_depth_eval(const SmallFactor& f, double d_inv, const Sm
   const V3 x_j = qrot(S, x_ci) + p_CiinCj;
   const double dj = 1.0 / x_j.z;
   o->reset(2);
-  const int g = sc.lm_col ? sc.lm_col[f.landmark] : -1;
   if (g >= 0) {
     const V3 Jd = (-1.0 / d_inv) * qrot(S, x_ci);
     o->add(0, g, sqrt_info * (dj * Jd.x - dj * dj * x_j.x * Jd.z));
@@ -626,6 +640,356 @@ CLIC_HD bool small_image_depth_eval(const SmallFactor& f, double d_inv, const Sm
   }
   o->r[0] = sqrt_info * (x_j.x * dj - p_j.x);
   o->r[1] = sqrt_info * (x_j.y * dj - p_j.y);
+  return true;
+}
+
+// ---- the factors below take the values of their non-knot parameter blocks in x (the reference's block order) and the
+// first column of each block in xcol (-1: constant); clic_evaluate_factor and the solve both go through them ----
+CLIC_HD V3 m3row(const M3& m, int r) { return mk(m.m[3 * r], m.m[3 * r + 1], m.m[3 * r + 2]); }
+CLIC_HD V3 unit3(int r) { return mk(r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0); }
+CLIC_HD double comp(V3 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+CLIC_HD void small_add3(SmallOut* o, int row, int g, V3 v, double w) {
+  if (g < 0) return;
+  o->add(row, g + 0, w * v.x);
+  o->add(row, g + 1, w * v.y);
+  o->add(row, g + 2, w * v.z);
+}
+CLIC_HD V3 spline_pos(const WindowView& W, int s, const double c[4]) {
+  V3 p = mk(0, 0, 0);
+  for (int k = 0; k < 4; k++) p = fma3(c[k], ldv(W.kp + 3 * (s + k)), p);
+  return p;
+}
+// the two rows of J_v (projection onto the normalised plane) of a camera-frame point
+CLIC_HD V3 proj_row(V3 x_j, double dj, int r) {
+  return r == 0 ? mk(dj, 0.0, -dj * dj * x_j.x) : mk(0.0, dj, -dj * dj * x_j.y);
+}
+
+// Image3D2DFactor::Evaluate (image_feature_factor.h:322-452).  x = p_G[3], t_offset_ns; xcol = {p_G, t_offset}.
+CLIC_HD bool small_image_3d2d_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                   Q4 S_CtoI, V3 p_CinI, const double* x, const int* xcol, const SmallCols& sc, SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a + (long long)x[3], t0_ns, dt_ns, K, &s, &u)) return false;
+  const double inv_dt = 1e9 / double(dt_ns);
+  const V3 p_j = ldv(f.d), p_G = ldv(x);
+  const double sqrt_info = f.d[3];
+  So3Chain C;
+  Q4 P[4];
+  so3_chain_rtp(W, s, u, &C, P);
+  const Q4 S_GtoIj = qconj(C.R), S_ItoC = qconj(S_CtoI);
+  const Q4 S_GtoCj = so3_mul(S_ItoC, S_GtoIj);
+  double c[4];
+  blend_plain(u, c);
+  const V3 rel = p_G - spline_pos(W, s, c);
+  const V3 x_j = qrot(S_GtoCj, rel) - qrot(S_ItoC, p_CinI);
+  const double dj = 1.0 / x_j.z;
+  o->reset(2);
+  for (int r = 0; r < 2; r++) {
+    const V3 b = qrot_inv(S_GtoCj, proj_row(x_j, dj, r));  // row r of J_v mat(S_GtoCj)
+    V3 j[4];
+    so3_rows_rtp(W, s, C, P, cross(b, rel), j);
+    for (int k = 0; k < 4; k++) {
+      const int g = sc.knot_col[s + k];
+      if (g < 0) continue;
+      small_add3(o, r, g, j[k], sqrt_info);
+      small_add3(o, r, g + 3, b, -sqrt_info * c[k]);
+    }
+    small_add3(o, r, xcol[0], b, sqrt_info);
+  }
+  if (xcol[1] >= 0) {  // ":440-451"
+    const V3 gyro = so3_velocity_body(W, s, u, inv_dt);
+    double d1[4];
+    blend_plain_d1(u, inv_dt, d1);
+    const V3 vel = spline_pos(W, s, d1);
+    // Rj_dot^T v = -(gyro x R^T v)
+    const V3 J_tj = qrot(S_ItoC, -cross(gyro, qrot(S_GtoIj, rel))) - qrot(S_GtoCj, vel);
+    for (int r = 0; r < 2; r++) o->add(r, xcol[1], 1e-9 * sqrt_info * dot(proj_row(x_j, dj, r), J_tj));
+  }
+  o->r[0] = sqrt_info * (x_j.x * dj - p_j.x);
+  o->r[1] = sqrt_info * (x_j.y * dj - p_j.y);
+  return true;
+}
+
+// ImageFeatureOnePoseFactor::Evaluate (image_feature_factor.h:511-633).  x = inverse depth; xcol = {inverse depth}.
+CLIC_HD bool small_image_one_pose_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                       Q4 S_CtoI, V3 p_CinI, const double* x, const int* xcol, const SmallCols& sc,
+                                       SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &s, &u)) return false;
+  const V3 p_i = ldv(f.d), p_IiinG = ldv(f.d + 7), p_j = ldv(f.d + 10);
+  const Q4 S_IitoG = ldq(f.d + 3);
+  const double sqrt_info = f.d[13], d_inv = x[0];
+  const V3 x_ci = mk(p_i.x / d_inv, p_i.y / d_inv, p_i.z / d_inv);
+  const V3 p_Ii = qrot(S_CtoI, x_ci) + p_CinI;
+  const V3 p_G = qrot(S_IitoG, p_Ii) + p_IiinG;
+  So3Chain C;
+  Q4 P[4];
+  so3_chain_rtp(W, s, u, &C, P);
+  const Q4 S_GtoIj = qconj(C.R), S_ItoC = qconj(S_CtoI);
+  const Q4 S_GtoCj = so3_mul(S_ItoC, S_GtoIj);
+  double c[4];
+  blend_plain(u, c);
+  const V3 rel = p_G - spline_pos(W, s, c);
+  const V3 x_j = qrot(S_GtoCj, rel) - qrot(S_ItoC, p_CinI);
+  const double dj = 1.0 / x_j.z;
+  o->reset(2);
+  const V3 J_Xm_d = (-1.0 / d_inv) * qrot(so3_mul(so3_mul(S_GtoCj, S_IitoG), S_CtoI), x_ci);
+  for (int r = 0; r < 2; r++) {
+    const V3 Jv = proj_row(x_j, dj, r);
+    const V3 b = qrot_inv(S_GtoCj, Jv);
+    V3 j[4];
+    so3_rows_rtp(W, s, C, P, cross(b, rel), j);
+    for (int k = 0; k < 4; k++) {
+      const int g = sc.knot_col[s + k];
+      if (g < 0) continue;
+      small_add3(o, r, g, j[k], sqrt_info);
+      small_add3(o, r, g + 3, b, -sqrt_info * c[k]);
+    }
+    if (xcol[0] >= 0) o->add(r, xcol[0], sqrt_info * dot(Jv, J_Xm_d));
+  }
+  o->r[0] = sqrt_info * (x_j.x * dj - p_j.x);
+  o->r[1] = sqrt_info * (x_j.y * dj - p_j.y);
+  return true;
+}
+
+// EpipolarFactor::Evaluate (image_feature_factor.h:741-822)
+CLIC_HD bool small_epipolar_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K, Q4 S_CtoI,
+                                 V3 p_CinI, const SmallCols& sc, SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &s, &u)) return false;
+  const V3 x_i = ldv(f.d), x_k = ldv(f.d + 3), p_CkinG = ldv(f.d + 10);
+  const Q4 S_GtoCk = ldq(f.d + 6);
+  const double weight = f.d[13];
+  So3Chain C;
+  so3_chain_rp(W, s, u, &C);
+  const Q4 S_IitoG = C.R;
+  double c[4];
+  blend_plain(u, c);
+  const V3 p_IiinG = spline_pos(W, s, c);
+  const V3 xi_I = qrot(S_CtoI, x_i);
+  const V3 Rxi = qrot(so3_mul(so3_mul(S_GtoCk, S_IitoG), S_CtoI), x_i);
+  const V3 tvec = qrot(S_GtoCk, qrot(S_IitoG, p_CinI) + p_IiinG - p_CkinG);
+  o->reset(1);
+  o->r[0] = weight * dot(cross(x_k, tvec), Rxi);  // (x_k^T hat(t)) Rxi
+  const V3 jac_lhs = qrot_inv(S_GtoCk, cross(x_k, Rxi));  // x_k^T hat(Rxi) mat(S_GtoCk)
+  V3 a = cross(qrot_inv(so3_mul(S_GtoCk, S_IitoG), -cross(x_k, tvec)), xi_I);
+  a = a + cross(qrot_inv(S_IitoG, jac_lhs), p_CinI);
+  V3 j[4];
+  so3_rows_rp(W, s, C, a, j);
+  for (int k = 0; k < 4; k++) {
+    const int g = sc.knot_col[s + k];
+    if (g < 0) continue;
+    small_add3(o, 0, g, j[k], weight);
+    small_add3(o, 0, g + 3, jac_lhs, -weight * c[k]);
+  }
+  return true;
+}
+
+// distance of p to the plane / line of a correspondence and its gradient row (lidar_feature_factor.h:237-250);
+// d = point[3] geo_plane[4] geo_normal[3] geo_point[3]
+CLIC_HD double small_loam_distance(const SmallFactor& f, V3 p, V3* J_pi) {
+  if (f.geo_type == 1) {
+    *J_pi = ldv(f.d + 3);
+    return dot(p, *J_pi) + f.d[6];
+  }
+  const V3 normal = ldv(f.d + 7);
+  const V3 dist_vec = cross(p - ldv(f.d + 10), normal);
+  const double r = sqrt(dot(dist_vec, dist_vec));
+  *J_pi = cross((-1.0 / r) * dist_vec, normal);  // (-dist_vec^T / r) hat(normal)
+  return r;
+}
+
+// LoamFeatureOptMapPoseFactor::Evaluate (lidar_feature_factor.h:206-329).  x = S_ImtoG[4], p_IminG[3];
+// xcol = {map rotation, map position}.
+CLIC_HD bool small_loam_opt_map_pose_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                          const double* x, const int* xcol, const SmallCols& sc, SmallOut* o) {
+  int s = 0;
+  double u = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &s, &u)) return false;
+  const double weight = f.d[13];
+  const Q4 S_LtoI = ldq(f.d + 14), S_ImtoG = ldq(x);
+  const V3 p_LinI = ldv(f.d + 18), p_IminG = ldv(x + 4);
+  So3Chain C;
+  so3_chain_rp(W, s, u, &C);
+  const Q4 S_IktoG = C.R;
+  double c[4];
+  blend_plain(u, c);
+  const V3 p_IkinG = spline_pos(W, s, c);
+  const Q4 S_ItoL = qconj(S_LtoI), S_GtoIm = qconj(S_ImtoG);
+  const Q4 S_GtoM = so3_mul(S_ItoL, S_GtoIm);
+  const V3 p_GinM = qrot(S_ItoL, qrot(S_GtoIm, -p_IminG) - p_LinI);
+  const V3 p_IK = qrot(S_LtoI, ldv(f.d)) + p_LinI;
+  const V3 p_G = qrot(S_IktoG, p_IK) + p_IkinG;
+  const V3 p_M = qrot(S_GtoM, p_G) + p_GinM;
+  V3 J_pi;
+  o->reset(1);
+  o->r[0] = weight * small_loam_distance(f, p_M, &J_pi);
+  const V3 lhs_P = qrot_inv(S_GtoM, J_pi);                        // J_pi^T mat(S_GtoM)
+  const V3 a = cross(qrot_inv(S_IktoG, -lhs_P), p_IK);            // J_pi^T (-mat(S_GtoM) mat(S_IktoG) hat(p_IK))
+  V3 j[4];
+  so3_rows_rp(W, s, C, a, j);
+  for (int k = 0; k < 4; k++) {
+    const int g = sc.knot_col[s + k];
+    if (g < 0) continue;
+    small_add3(o, 0, g, j[k], weight);
+    small_add3(o, 0, g + 3, lhs_P, weight * c[k]);
+  }
+  const V3 Jl = qrot_inv(S_ItoL, J_pi);  // J_pi^T mat(S_ItoL)
+  small_add3(o, 0, xcol[0], cross(Jl, qrot(S_GtoIm, p_G - p_IminG)), weight);
+  small_add3(o, 0, xcol[1], qrot_inv(S_GtoIm, Jl), -weight);
+  return true;
+}
+
+// RalativeLoamFeatureFactor::Evaluate (lidar_feature_factor.h:376-526)
+CLIC_HD bool small_relative_loam_eval(const WindowView& W, const SmallFactor& f, long long t0_ns, long long dt_ns, int K,
+                                      const SmallCols& sc, SmallOut* o) {
+  int si = 0, sj = 0;
+  double ui = 0.0, uj = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &si, &ui) || !index_ns(f.t_b, t0_ns, dt_ns, K, &sj, &uj)) return false;
+  const double weight = f.d[13];
+  const Q4 S_LtoI = ldq(f.d + 14);
+  const V3 p_LinI = ldv(f.d + 18);
+  const V3 p_Ii = qrot(S_LtoI, ldv(f.d)) + p_LinI;
+  So3Chain Ci, Cj;
+  Q4 Pj[4];
+  so3_chain_rp(W, si, ui, &Ci);
+  so3_chain_rtp(W, sj, uj, &Cj, Pj);
+  double ci[4], cj[4];
+  blend_plain(ui, ci);
+  blend_plain(uj, cj);
+  const Q4 S_IitoG = Ci.R, S_GtoIj = qconj(Cj.R), S_ItoC = qconj(S_LtoI);
+  const V3 p_G = qrot(S_IitoG, p_Ii) + spline_pos(W, si, ci);
+  const V3 rel = p_G - spline_pos(W, sj, cj);
+  const Q4 S_GtoCj = so3_mul(S_ItoC, S_GtoIj);
+  const V3 x_j = qrot(S_GtoCj, rel) - qrot(S_ItoC, p_LinI);
+  V3 J_pi;
+  o->reset(1);
+  o->r[0] = weight * small_loam_distance(f, x_j, &J_pi);
+  const V3 b = qrot_inv(S_GtoCj, J_pi);  // J_pi^T mat(S_GtoCj)
+  V3 ji[4], jj[4];
+  so3_rows_rp(W, si, Ci, cross(qrot_inv(S_IitoG, -b), p_Ii), ji);
+  so3_rows_rtp(W, sj, Cj, Pj, cross(b, rel), jj);
+  for (int k = 0; k < 4; k++) {
+    const int gi = sc.knot_col[si + k], gj = sc.knot_col[sj + k];
+    if (gi >= 0) {
+      small_add3(o, 0, gi, ji[k], weight);
+      small_add3(o, 0, gi + 3, b, weight * ci[k]);
+    }
+    if (gj >= 0) {
+      small_add3(o, 0, gj, jj[k], weight);
+      small_add3(o, 0, gj + 3, b, -weight * cj[k]);
+    }
+  }
+  return true;
+}
+
+// PreIntegrationFactor::Evaluate (trajectory_value_factor.h:651-964) with IntegrationBase::evaluate333
+// (integration_base.h:207-252).  x = bg_a[3] bg_b[3] ba_a[3] ba_b[3]; xcol = their first columns.
+CLIC_HD bool small_preintegration_eval(const WindowView& W, const SmallFactor& f, const PreintData& pre, long long t0_ns,
+                                       long long dt_ns, int K, const double* x, const int* xcol, const SmallCols& sc,
+                                       SmallOut* o) {
+  int sa = 0, sb = 0;
+  double ua = 0.0, ub = 0.0;
+  if (!index_ns(f.t_a, t0_ns, dt_ns, K, &sa, &ua) || !index_ns(f.t_b, t0_ns, dt_ns, K, &sb, &ub)) return false;
+  const double inv_dt = 1e9 / double(dt_ns);
+  const V3 bg_a = ldv(x), bg_b = ldv(x + 3), ba_a = ldv(x + 6), ba_b = ldv(x + 9);
+  So3Chain Ca, Cb;
+  Q4 Pa[4];
+  so3_chain_rtp(W, sa, ua, &Ca, Pa);  // EvaluateRTp at t_a
+  so3_chain_rp(W, sb, ub, &Cb);       // EvaluateRp at t_b
+  double ca[4], cb[4], da[4], db[4];
+  blend_plain(ua, ca);
+  blend_plain(ub, cb);
+  blend_plain_d1(ua, inv_dt, da);
+  blend_plain_d1(ub, inv_dt, db);
+  const V3 p_a = spline_pos(W, sa, ca), p_b = spline_pos(W, sb, cb);
+  const V3 v_a = spline_pos(W, sa, da), v_b = spline_pos(W, sb, db);
+  const Q4 S_IatoG = Ca.R, S_GtoIa = qconj(Ca.R), S_IbtoG = Cb.R;
+  const double dt = pre.sum_dt;
+  const V3 gravity = mk(0.0, 0.0, -pre.gravity_norm);
+  // evaluate333
+  const V3 dba = ba_a - ldv(pre.linearized_ba), dbg = bg_a - ldv(pre.linearized_bg);
+  M3 dp_dba, dp_dbg, dq_dbg, dv_dba, dv_dbg;
+  for (int i = 0; i < 9; i++) {
+    dp_dba.m[i] = pre.dp_dba[i]; dp_dbg.m[i] = pre.dp_dbg[i]; dq_dbg.m[i] = pre.dq_dbg[i];
+    dv_dba.m[i] = pre.dv_dba[i]; dv_dbg.m[i] = pre.dv_dbg[i];
+  }
+  const V3 cdp = ldv(pre.delta_p) + mvec(dp_dba, dba) + mvec(dp_dbg, dbg);
+  Q4 cdq = qmul(ldq(pre.delta_q), so3_exp(mvec(dq_dbg, dbg)));
+  {
+    const double n = sqrt(cdq.x * cdq.x + cdq.y * cdq.y + cdq.z * cdq.z + cdq.w * cdq.w);
+    cdq.x /= n; cdq.y /= n; cdq.z /= n; cdq.w /= n;
+  }
+  const V3 cdv = ldv(pre.delta_v) + mvec(dv_dba, dba) + mvec(dv_dbg, dbg);
+  const V3 r_p_part = p_b - p_a - dt * v_a + (0.5 * dt * dt) * gravity;
+  const V3 r_v_part = v_b - v_a + dt * gravity;
+  const V3 res_p = qrot(S_GtoIa, (0.5 * dt * dt) * gravity + p_b - p_a - dt * v_a) - cdp;
+  const V3 res_R = so3_log(so3_mul(so3_mul(qconj(cdq), S_GtoIa), S_IbtoG));
+  const V3 res_v = qrot(S_GtoIa, dt * gravity + v_b - v_a) - cdv;
+  double raw[15];
+  raw[0] = res_p.x; raw[1] = res_p.y; raw[2] = res_p.z;
+  raw[3] = res_R.x; raw[4] = res_R.y; raw[5] = res_R.z;
+  raw[6] = res_v.x; raw[7] = res_v.y; raw[8] = res_v.z;
+  raw[9] = ba_b.x - ba_a.x; raw[10] = ba_b.y - ba_a.y; raw[11] = ba_b.z - ba_a.z;
+  raw[12] = bg_b.x - bg_a.x; raw[13] = bg_b.y - bg_a.y; raw[14] = bg_b.z - bg_a.z;
+  o->reset(15);
+  // unweighted rows
+  const M3 Jrot = right_jacobian_inv(res_R);
+  M3 dR_dbg;
+  {
+    const V3 delta_bg = mvec(dq_dbg, dbg);
+    dR_dbg = mscale(-1.0, mmul(mmul(left_jacobian_inv(res_R), left_jacobian(-delta_bg)), dq_dbg));
+  }
+  for (int r = 0; r < 3; r++) {
+    const V3 b = qrot(S_IatoG, unit3(r));  // row r of mat(S_GtoIa)
+    const V3 Jr = m3row(Jrot, r);
+    V3 jp[4], jra[4], jrb[4], jv[4];
+    so3_rows_rtp(W, sa, Ca, Pa, cross(b, r_p_part), jp);             // [1] position rows, rotation knots of t_a
+    so3_rows_rtp(W, sa, Ca, Pa, -qrot(S_IbtoG, Jr), jra);            // [2] rotation rows: -Jrot mat(S_GtoIb)
+    so3_rows_rp(W, sb, Cb, Jr, jrb);                                 //     ... and +Jrot at t_b
+    so3_rows_rtp(W, sa, Ca, Pa, cross(b, r_v_part), jv);             // [3] velocity rows
+    for (int k = 0; k < 4; k++) {
+      const int ga = sc.knot_col[sa + k], gb = sc.knot_col[sb + k];
+      if (ga >= 0) {
+        small_add3(o, 0 + r, ga, jp[k], 1.0);
+        small_add3(o, 3 + r, ga, jra[k], 1.0);
+        small_add3(o, 6 + r, ga, jv[k], 1.0);
+        small_add3(o, 0 + r, ga + 3, b, -(ca[k] + da[k] * dt));
+        small_add3(o, 6 + r, ga + 3, b, -da[k]);
+      }
+      if (gb >= 0) {
+        small_add3(o, 3 + r, gb, jrb[k], 1.0);
+        small_add3(o, 0 + r, gb + 3, b, cb[k]);
+        small_add3(o, 6 + r, gb + 3, b, db[k]);
+      }
+    }
+    small_add3(o, 0 + r, xcol[0], m3row(dp_dbg, r), -1.0);  // gyro bias t_a
+    small_add3(o, 3 + r, xcol[0], m3row(dR_dbg, r), 1.0);
+    small_add3(o, 6 + r, xcol[0], m3row(dv_dbg, r), -1.0);
+    if (xcol[0] >= 0) o->add(12 + r, xcol[0] + r, -1.0);
+    if (xcol[1] >= 0) o->add(12 + r, xcol[1] + r, 1.0);     // gyro bias t_b
+    small_add3(o, 0 + r, xcol[2], m3row(dp_dba, r), -1.0);  // accel bias t_a
+    small_add3(o, 6 + r, xcol[2], m3row(dv_dba, r), -1.0);
+    if (xcol[2] >= 0) o->add(9 + r, xcol[2] + r, -1.0);
+    if (xcol[3] >= 0) o->add(9 + r, xcol[3] + r, 1.0);      // accel bias t_b
+  }
+  // weight: r <- sqrt_info r, J <- sqrt_info J (":746-748, 940-960")
+  for (int r = 0; r < 15; r++) {
+    double a = 0.0;
+    for (int k = 0; k < 15; k++) a += pre.sqrt_info[15 * r + k] * raw[k];
+    o->r[r] = a;
+  }
+  for (int c = 0; c < o->ncols; c++) {
+    double col[15];
+    for (int k = 0; k < 15; k++) col[k] = o->J[k][c];
+    for (int r = 0; r < 15; r++) {
+      double a = 0.0;
+      for (int k = 0; k < 15; k++) a += pre.sqrt_info[15 * r + k] * col[k];
+      o->J[r][c] = a;
+    }
+  }
   return true;
 }
 

@@ -1655,8 +1655,36 @@ __global__ void velocity_factor_kernel(VelFactorDesc vf, const double* state, St
 // dense row set over the distinct global columns it touches (factor_eval.cuh), then every thread owns some of the
 // (column, column) pairs and adds J~^T J~, J~^T r~ into H, b: no atomics, fixed order.  Runs after the assembly (or
 // into the addend system of the fused pass), like velocity_factor_kernel.
-__global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* fs, int n, PassParams pp, SmallCols sc,
-                                                            double* H, double* b, int D, double* cost2, int jac) {
+// Values (x) and first columns (xcol, -1 = constant) of a small factor's parameter blocks after the knots.
+struct SmallX {
+  double x[16];
+  int xcol[4];
+};
+// One small factor into o (thread 0 of the CTA).  False: a measurement time left the window.
+__device__ __noinline__ bool small_dispatch(const WindowView& W, const SmallFactor& f, const PreintData* pre, const PassParams& pp,
+                                            Q4 S_CtoI, V3 p_CinI, const SmallX& X, SmallCols sc, SmallOut* o) {
+  const long long t0 = pp.t0_ns, dt = pp.dt_ns;
+  const int K = pp.sl.K;
+  switch (f.kind) {
+    case kSmallPose: sc.col_toff_imu = X.xcol[0]; return small_pose_eval(W, f, t0, dt, K, X.x[0], sc, o);
+    case kSmallLocalVelocity: sc.col_toff_imu = X.xcol[0]; return small_local_velocity_eval(W, f, t0, dt, K, X.x[0], sc, o);
+    case kSmallRelativeRotation: return small_relative_rotation_eval(W, f, t0, dt, K, sc, o);
+    case kSmallImageDepth: return small_image_depth_eval(f, X.x[0], X.xcol[0], o);
+    case kSmallPreIntegration: return small_preintegration_eval(W, f, pre[f.ext], t0, dt, K, X.x, X.xcol, sc, o);
+    case kSmallImage3D2D: return small_image_3d2d_eval(W, f, t0, dt, K, S_CtoI, p_CinI, X.x, X.xcol, sc, o);
+    case kSmallImageOnePose: return small_image_one_pose_eval(W, f, t0, dt, K, S_CtoI, p_CinI, X.x, X.xcol, sc, o);
+    case kSmallEpipolar: return small_epipolar_eval(W, f, t0, dt, K, S_CtoI, p_CinI, sc, o);
+    case kSmallLoamOptMapPose: return small_loam_opt_map_pose_eval(W, f, t0, dt, K, X.x, X.xcol, sc, o);
+    case kSmallRelativeLoam: return small_relative_loam_eval(W, f, t0, dt, K, sc, o);
+    default: return false;
+  }
+}
+
+// The factors of the small adders (pose, local velocity, relative rotation, image depth, pre-integration) of a solve:
+// one CTA, thread 0 evaluates a factor into a row set over the columns it touches, then the threads add J^T J, J^T r.
+__global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* fs, int n, const PreintData* pre, PassParams pp,
+                                                            SmallCols sc, double* H, double* b, int D, double* cost2,
+                                                            int jac) {
   pdl_wait();
   pdl_trigger();
   if (pp.ctl && pp.ctl[0]) return;
@@ -1669,17 +1697,31 @@ __global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* f
   if (threadIdx.x == 0) s_cost[0] = s_cost[1] = 0.0;
   const double toff_imu = pp.state[pp.sl.off_toff() + 0];
   const double* invd = pp.state + pp.sl.off_invd();
+  Q4 qid; qid.x = qid.y = qid.z = 0.0; qid.w = 1.0;
   for (int i = 0; i < n; i++) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const SmallFactor f = fs[i];
-      bool ok = false;
-      switch (f.kind) {
-        case kSmallPose: ok = small_pose_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, toff_imu, sc, o); break;
-        case kSmallLocalVelocity: ok = small_local_velocity_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, toff_imu, sc, o); break;
-        case kSmallRelativeRotation: ok = small_relative_rotation_eval(W, f, pp.t0_ns, pp.dt_ns, pp.sl.K, sc, o); break;
-        default: ok = small_image_depth_eval(f, invd[f.landmark], sc, o); break;
+      SmallX X;
+      for (int k = 0; k < 4; k++) X.xcol[k] = -1;
+      if (f.kind == kSmallPose || f.kind == kSmallLocalVelocity) {
+        X.x[0] = toff_imu;
+        X.xcol[0] = sc.col_toff_imu;
+      } else if (f.kind == kSmallImageDepth) {
+        X.x[0] = invd[f.landmark];
+        X.xcol[0] = sc.lm_col ? sc.lm_col[f.landmark] : -1;
+      } else if (f.kind == kSmallPreIntegration) {
+        const double* bi = pp.state + pp.sl.off_bias() + 6 * f.slot_i;
+        const double* bj = pp.state + pp.sl.off_bias() + 6 * f.slot_j;
+        for (int c = 0; c < 3; c++) {
+          X.x[c] = bi[c]; X.x[3 + c] = bj[c]; X.x[6 + c] = bi[3 + c]; X.x[9 + c] = bj[3 + c];
+        }
+        X.xcol[0] = sc.col_bias_gyro >= 0 ? sc.col_bias_gyro + 3 * f.slot_i : -1;
+        X.xcol[1] = sc.col_bias_gyro >= 0 ? sc.col_bias_gyro + 3 * f.slot_j : -1;
+        X.xcol[2] = sc.col_bias_accel >= 0 ? sc.col_bias_accel + 3 * f.slot_i : -1;
+        X.xcol[3] = sc.col_bias_accel >= 0 ? sc.col_bias_accel + 3 * f.slot_j : -1;
       }
+      const bool ok = small_dispatch(W, f, pre, pp, qid, mk(0, 0, 0), X, sc, o);
       if (ok) {
         double sq = 0.0;
         for (int r = 0; r < o->nres; r++) sq += o->r[r] * o->r[r];
@@ -1716,6 +1758,40 @@ __global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* f
   if (threadIdx.x == 0) {
     cost2[0] += s_cost[0];
     cost2[1] += s_cost[1];
+  }
+}
+
+// clic_evaluate_factor: one factor against the window with EVERY knot free (column 6 k of knot k) and the factor's own
+// blocks after them; out = [ok, nres, -, -, r[16], J (nres x n_cols, row-major)].
+__global__ void __launch_bounds__(128) factor_jacobian_kernel(SmallFactor f, const PreintData* pre, PassParams pp, Q4 S_CtoI,
+                                                              V3 p_CinI, SmallX X, int n_cols, double* out) {
+  extern __shared__ double smem[];
+  double* rest;
+  WindowView W = stage_window(smem, pp, &rest);
+  SmallOut* o = reinterpret_cast<SmallOut*>(rest);
+  int* kc = reinterpret_cast<int*>(o + 1);
+  for (int k = threadIdx.x; k < pp.sl.K; k += blockDim.x) kc[k] = 6 * k;
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SmallCols sc;
+    sc.knot_col = kc;
+    sc.col_toff_imu = -1;
+    sc.lm_col = nullptr;
+    sc.col_bias_gyro = sc.col_bias_accel = -1;
+    s_ok = small_dispatch(W, f, pre, pp, S_CtoI, p_CinI, X, sc, o) ? 1 : 0;
+    out[0] = (double)s_ok;
+    out[1] = s_ok ? (double)o->nres : 0.0;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int nr = o->nres;
+  for (int t = threadIdx.x; t < nr; t += blockDim.x) out[4 + t] = o->r[t];
+  for (int t = threadIdx.x; t < nr * n_cols; t += blockDim.x) out[20 + t] = 0.0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < nr * o->ncols; t += blockDim.x) {
+    const int r = t / o->ncols, c = t - r * o->ncols;
+    out[20 + (size_t)r * n_cols + o->gcol[c]] = o->J[r][c];
   }
 }
 

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _abi
-from ._abi import ClicError, Layout, Options, Summary, WindowDesc, dptr, f64, i32, iptr
+from ._abi import ClicError, FactorDesc, Layout, Options, PreIntegration, Summary, WindowDesc, dptr, f64, i32, iptr
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libclic_cuda.so")
 _lib = None
@@ -245,6 +245,35 @@ class TrajectoryEstimator:
     def AddImageDepthAnalytic(self, p_i, p_j, S_CitoCj, p_CiinCj, landmark):
         a = [f64(p_i), f64(p_j), f64(S_CitoCj), f64(p_CiinCj)]
         _check(self.lib, self.lib.clic_add_image_depth(self.h, *[dptr(x) for x in a], int(landmark)))
+
+    # ---- trajectory_estimator.h:168-172 (PreIntegrationFactor) ----
+    def AddPreIntegrationAnalytic(self, ta_ns, tb_ns, pre, slot_i, slot_j):
+        """pre: a PreIntegration struct (make_preintegration).  Times are int64 ns on the trajectory clock."""
+        added = C.c_int32(0)
+        _check(self.lib, self.lib.clic_add_preintegration(self.h, int(ta_ns), int(tb_ns), C.byref(pre), int(slot_i),
+                                                          int(slot_j), C.byref(added)))
+        return bool(added.value)
+
+    # ---- src/app/test_analytic_factor.cpp:846-900: one cost function, residual and Jacobian ----
+    def evaluate_factor(self, kind, t_a_ns=0, t_b_ns=0, d=(), x=(), geo_type=0, pre=None, want_jacobian=True):
+        """Returns (residual (m,), J (m, 6 K + extras)) of one analytic factor at the current window; the layout of d, x
+        and of the Jacobian columns is documented at clic_evaluate_factor in include/clic_cuda.h."""
+        f = FactorDesc()
+        f.kind, f.geo_type, f.t_a_ns, f.t_b_ns = int(kind), int(geo_type), int(t_a_ns), int(t_b_ns)
+        for i, v in enumerate(np.asarray(d, np.float64).ravel()):
+            f.d[i] = v
+        for i, v in enumerate(np.asarray(x, np.float64).ravel()):
+            f.x[i] = v
+        if pre is not None:
+            f.pre = C.pointer(pre)
+        n_res, n_cols = C.c_int32(0), C.c_int32(0)
+        res = np.zeros(15)
+        cap = 15 * (6 * self.window.n_knots + 16)
+        jac = np.zeros(cap)
+        _check(self.lib, self.lib.clic_evaluate_factor(self.h, C.byref(f), C.byref(n_res), dptr(res), C.byref(n_cols),
+                                                       dptr(jac) if want_jacobian else None, cap))
+        m, n = n_res.value, n_cols.value
+        return res[:m].copy(), (jac[:m * n].reshape(m, n).copy() if want_jacobian else None)
 
     # ---- trajectory_estimator.cpp:609-664 ----
     def AddGlobalVelocityMeasurement(self, timestamp, global_v, vel_weight):

@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -48,6 +49,65 @@ struct PoseData {  // src/utils/parameter_struct.h:60-69
   double timestamp = 0;
   Vec3d position{};
   SO3d orientation;
+};
+// The members of IntegrationBase (src/visual_odometry/integration_base.h:254-288) PreIntegrationFactor reads.  The
+// integration itself (push_back / midPointIntegration) stays with the caller's own class, as in the reference; copy its
+// members here.  Matrices are row-major.
+struct IntegrationBase {
+  double sum_dt = 0;
+  Vec3d delta_p{}, delta_v{};
+  std::array<double, 4> delta_q{{0, 0, 0, 1}};  // x, y, z, w
+  Vec3d linearized_ba{}, linearized_bg{};
+  std::array<double, 225> jacobian{};    // 15 x 15, state order P R V BA BG
+  std::array<double, 225> covariance{};  // 15 x 15, symmetric positive definite
+  double gravity_norm = -9.8;            // the global GRAVITY_NORM (parameter_struct.cpp:23)
+
+  // sqrt_info = LLT(covariance^-1).matrixL()^T (trajectory_value_factor.h:744-748), without Eigen: covariance = L L^T,
+  // covariance^-1 = L^-T L^-1 =: M, then the Cholesky factor of M.  Throws if the covariance is not positive definite.
+  clic_preintegration to_abi() const {
+    clic_preintegration p;
+    p.sum_dt = sum_dt;
+    p.gravity_norm = gravity_norm;
+    for (int i = 0; i < 3; i++) {
+      p.delta_p[i] = delta_p[i]; p.delta_v[i] = delta_v[i];
+      p.linearized_ba[i] = linearized_ba[i]; p.linearized_bg[i] = linearized_bg[i];
+    }
+    for (int i = 0; i < 4; i++) p.delta_q[i] = delta_q[i];
+    for (int i = 0; i < 225; i++) p.jacobian[i] = jacobian[i];
+    constexpr int n = 15;
+    auto cholesky = [](const double* A, double* L) {  // lower, row-major
+      for (int i = 0; i < n * n; i++) L[i] = 0.0;
+      for (int j = 0; j < n; j++) {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k];
+        if (!(d > 0.0)) throw std::runtime_error("IntegrationBase: covariance is not positive definite");
+        L[j * n + j] = std::sqrt(d);
+        for (int i = j + 1; i < n; i++) {
+          double v = A[i * n + j];
+          for (int k = 0; k < j; k++) v -= L[i * n + k] * L[j * n + k];
+          L[i * n + j] = v / L[j * n + j];
+        }
+      }
+    };
+    double L[225], Li[225], M[225], C[225];
+    cholesky(covariance.data(), L);
+    for (int c = 0; c < n; c++)  // Li = L^-1 (forward substitution, column by column)
+      for (int r = 0; r < n; r++) {
+        double v = r == c ? 1.0 : 0.0;
+        for (int k = 0; k < r; k++) v -= L[r * n + k] * Li[k * n + c];
+        Li[r * n + c] = v / L[r * n + r];
+      }
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < n; c++) {
+        double v = 0.0;
+        for (int k = 0; k < n; k++) v += Li[k * n + r] * Li[k * n + c];
+        M[r * n + c] = v;
+      }
+    cholesky(M, C);
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < n; c++) p.sqrt_info[r * n + c] = C[c * n + r];  // matrixL().transpose()
+    return p;
+  }
 };
 struct ExtrinsicParam {  // src/utils/parameter_struct.h:108-150 (the fields the hot path reads)
   SO3d so3;
@@ -409,6 +469,37 @@ class TrajectoryEstimator {
     f.w = weight;
     lvel_f_.push_back(f);
   }
+  // trajectory_estimator.h:168-172 (PreIntegrationFactor).  The reference hands its double SECONDS ti / tj to the
+  // factor's int64 nanosecond arguments (trajectory_estimator.cpp:545); here the factor gets the nanosecond values
+  // MeasuredTimeToNs produced (INTEGRATION.md "quirks").  marg_this_factor: the reference routes the factor to the
+  // marginalization set (":564-578"); not supported here (throws), nothing in the pipeline calls this adder.
+  void AddPreIntegrationAnalytic(double ti, double tj, const IntegrationBase* pre_integration, double* gyro_bias_i,
+                                 double* gyro_bias_j, double* accel_bias_i, double* accel_bias_j,
+                                 bool marg_this_factor = false) {
+    if (marg_this_factor && options.is_marg_state)
+      throw std::runtime_error("AddPreIntegrationAnalytic: marg_this_factor is not supported");
+    PreInt f;
+    f.ta_ns = (int64_t)(ti * 1e9);
+    f.tb_ns = (int64_t)(tj * 1e9);
+    f.pre = pre_integration->to_abi();
+    f.i = bias_slot(gyro_bias_i, accel_bias_i);
+    f.j = bias_slot(gyro_bias_j, accel_bias_j);
+    preint_f_.push_back(f);
+  }
+  // One analytic factor's residual and Jacobian at the current window: the surface the reference's
+  // test_analytic_factor.cpp drives (cost_function->Evaluate + GetJacobian, ":846-900"); see clic_evaluate_factor.
+  // jac: row-major n_res x n_cols (resized).  False when a measurement time is outside the window.
+  bool EvaluateFactor(const clic_factor_desc& f, std::vector<double>* residual, std::vector<double>* jac, int* n_cols) {
+    build();
+    int32_t nr = 0, nc = 0;
+    double r[15];
+    std::vector<double> J((size_t)15 * (6 * trajectory_->numKnots() + 16));
+    if (clic_evaluate_factor(h_, &f, &nr, r, &nc, J.data(), (int64_t)J.size()) != CLIC_OK) return false;
+    if (residual) residual->assign(r, r + nr);
+    if (jac) jac->assign(J.begin(), J.begin() + (size_t)nr * nc);
+    if (n_cols) *n_cols = nc;
+    return true;
+  }
   // trajectory_estimator.h:174-175 (RelativeOrientationFactor)
   void AddRelativeRotationAnalytic(double ta, double tb, const SO3d& S_BtoA, const Vec3d& info_vec) {
     RelRot f;
@@ -549,6 +640,11 @@ class TrajectoryEstimator {
     double t = 0, w = 0;
     Vec3d v{};
   };
+  struct PreInt {
+    int64_t ta_ns = 0, tb_ns = 0;
+    clic_preintegration pre;
+    int i = 0, j = 0;
+  };
   struct RelRot {
     double ta = 0, tb = 0;
     SO3d S;
@@ -663,6 +759,7 @@ class TrajectoryEstimator {
     for (auto& b : pose_f_)
       check(clic_add_pose(h_, (int64_t)b.t.size(), b.t.data(), b.p.data(), b.q.data(), b.info.data(), nullptr));
     for (auto& f : lvel_f_) check(clic_add_local_velocity(h_, 1, &f.t, f.v.data(), f.w, nullptr));
+    for (auto& f : preint_f_) check(clic_add_preintegration(h_, f.ta_ns, f.tb_ns, &f.pre, f.i, f.j, nullptr));
     for (auto& f : relrot_f_) check(clic_add_relative_rotation(h_, f.ta, f.tb, f.S.data(), f.info.data(), nullptr));
     for (auto& f : depth_f_) check(clic_add_image_depth(h_, f.pi.data(), f.pj.data(), f.S.data(), f.p.data(), f.lm));
     for (auto& f : vel_f_) check(clic_add_global_velocity(h_, f.t, f.v.data(), f.w, nullptr));
@@ -710,6 +807,7 @@ class TrajectoryEstimator {
   std::vector<PoseBatch> pose_f_;
   std::vector<LocalVel> lvel_f_;
   std::vector<RelRot> relrot_f_;
+  std::vector<PreInt> preint_f_;
   std::vector<ImgDepth> depth_f_;
   std::vector<VelFac> vel_f_;
   std::vector<PriorRef> priors_;

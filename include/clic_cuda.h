@@ -256,6 +256,65 @@ CLIC_API int clic_add_relative_rotation(clic_estimator* h, double ta, double tb,
 CLIC_API int clic_add_image_depth(clic_estimator* h, const double p_i[3], const double p_j[3], const double S_CitoCj[4],
                                   const double p_CiinCj[3], int32_t landmark);
 
+/* IntegrationBase (src/visual_odometry/integration_base.h:36-288) reduced to what PreIntegrationFactor reads.  The
+ * integration itself (propagate / midPointIntegration over the IMU samples) stays with the caller like in the reference;
+ * sqrt_info = LLT(covariance^-1).matrixL()^T, which the reference recomputes with Eigen inside every Evaluate
+ * (trajectory_value_factor.h:744-748), is handed in (the C++ shim computes it from IntegrationBase::covariance). */
+typedef struct {
+  double sum_dt;
+  double delta_p[3], delta_q[4] /* x,y,z,w */, delta_v[3];
+  double linearized_ba[3], linearized_bg[3];
+  double jacobian[225];  /* 15x15 row-major, state order P R V BA BG (integration_base.h:20-26) */
+  double sqrt_info[225]; /* 15x15 row-major (upper triangular) */
+  double gravity_norm;   /* the global GRAVITY_NORM (parameter_struct.cpp:23: -9.8); gravity = (0, 0, -GRAVITY_NORM) */
+} clic_preintegration;
+
+/* AddPreIntegrationAnalytic (trajectory_estimator.cpp:529-586) with PreIntegrationFactor
+ * (trajectory_value_factor.h:618-964): 15 residuals [dp, dR, dv, dba, dbg] between the spline poses / velocities at
+ * t_a < t_b and the integrated IMU deltas, on the 4+4 knots of both intervals and the gyro / accel bias of slots
+ * slot_i (t_a) and slot_j (t_b); no loss.  ta_ns / tb_ns are the factor's constructor arguments (int64 ns on the
+ * trajectory clock).  The reference's adder passes its double SECONDS there (":545", an implicit double -> int64
+ * conversion; nothing in the shipped pipeline calls it) — the C++ shim passes the nanosecond values MeasuredTimeToNs
+ * produced, see INTEGRATION.md "quirks".  *added = 0 when either time is outside the window.  Not routed to the
+ * marginalization set (a marginalization estimator refuses it). */
+CLIC_API int clic_add_preintegration(clic_estimator* h, int64_t ta_ns, int64_t tb_ns, const clic_preintegration* pre,
+                                     int32_t slot_i, int32_t slot_j, int32_t* added);
+
+/* ---- one analytic factor, residual and Jacobian: the surface src/app/test_analytic_factor.cpp drives
+ * (cost_function->Evaluate + GetJacobian, ":846-900").  Covers every small analytic factor of SURVEY.md §8f-4,
+ * including the five the reference never adds to a problem outside that test.  The knots are the estimator's current
+ * window; the factor's other parameter blocks are given in x (the reference's block order after the knots). ---- */
+enum {
+  CLIC_FACTOR_POSE = 0,              /* IMUPoseFactor          t_a; d = position[3] orientation[4] info[6]; x = t_offset_ns */
+  CLIC_FACTOR_LOCAL_VELOCITY = 1,    /* LocalVelocityFactor    t_a; d = local_v[3] weight; x = t_offset_ns */
+  CLIC_FACTOR_RELATIVE_ROTATION = 2, /* RelativeOrientationFactor t_a, t_b; d = S_BtoA[4] info[3] */
+  CLIC_FACTOR_IMAGE_DEPTH = 3,       /* ImageDepthFactor       d = p_i[3] p_j[3] S_CitoCj[4] p_CiinCj[3] sqrt_info; x = inv_depth */
+  CLIC_FACTOR_PREINTEGRATION = 4,    /* PreIntegrationFactor   t_a, t_b; pre; x = bg_a[3] bg_b[3] ba_a[3] ba_b[3] */
+  CLIC_FACTOR_IMAGE_3D2D = 5,        /* Image3D2DFactor (image_feature_factor.h:294-475)  t_a = t_j; d = p_j[3] sqrt_info;
+                                        x = p_G[3] t_offset_ns */
+  CLIC_FACTOR_IMAGE_ONE_POSE = 6,    /* ImageFeatureOnePoseFactor (":477-656")  t_a = t_j; d = p_i[3] S_IitoG[4] p_IiinG[3]
+                                        p_j[3] sqrt_info; x = inv_depth */
+  CLIC_FACTOR_EPIPOLAR = 7,          /* EpipolarFactor (":709-842")  t_a = t_i; d = x_i[3] x_k[3] S_GtoCk[4] p_CkinG[3] weight */
+  CLIC_FACTOR_LOAM_OPT_MAP_POSE = 8, /* LoamFeatureOptMapPoseFactor (lidar_feature_factor.h:174-348)  t_a = t_point; geo_type;
+                                        d = point[3] geo_plane[4] geo_normal[3] geo_point[3] weight S_LtoI[4] p_LinI[3];
+                                        x = S_ImtoG[4] p_IminG[3] */
+  CLIC_FACTOR_RELATIVE_LOAM = 9      /* RalativeLoamFeatureFactor (":350-553")  t_a = t_point, t_b = t_map; d as above */
+};
+typedef struct {
+  int32_t kind;      /* CLIC_FACTOR_* */
+  int32_t geo_type;  /* CLIC_GEO_* (the two LiDAR kinds) */
+  int64_t t_a_ns, t_b_ns; /* measurement times on the trajectory clock, before the time offset */
+  double d[32];      /* the factor's constants, per kind as listed above; camera factors use the window's S_CtoI / p_CinI */
+  double x[16];      /* values of the parameter blocks after the knots */
+  const clic_preintegration* pre; /* CLIC_FACTOR_PREINTEGRATION only */
+} clic_factor_desc;
+/* residual: *n_res values (<= 15).  jac: row-major *n_res x *n_cols, *n_cols = 6 K + the tangent sizes of the blocks in
+ * x; column 6 k + c = d/d(theta_k)[c] (c < 3, right perturbation R <- R exp(dtheta), ceres_local_param.h:141-152) or
+ * d/d(p_k)[c - 3] of window knot k; the columns after 6 K follow x (a rotation block has 3).  Returns
+ * CLIC_ERR_BAD_ARGUMENT when a time is outside the window or jac_capacity (doubles) is too small. */
+CLIC_API int clic_evaluate_factor(clic_estimator* h, const clic_factor_desc* f, int32_t* n_res, double* residual /*[15]*/,
+                                  int32_t* n_cols, double* jac, int64_t jac_capacity);
+
 /* AddImageFeatureAnalytic (trajectory_estimator.cpp:752-829), batched; landmark[i] indexes
  * clic_window_desc::inv_depth.  Loss CauchyLoss(marg ? 1 : 2) (":806-810"). */
 CLIC_API int clic_add_image(clic_estimator* h, int64_t n, const double* t_i, const double* p_i /*3n*/,
@@ -277,7 +336,7 @@ CLIC_API int clic_evaluate(clic_estimator* h, double* H, double* b, double* cost
 
 /* ResidualSummary-like read-back (trajectory_estimator.h:42-98, what `verbose` prints per update): the cost
  * 1/2 sum rho(|r|^2) of the solve problem at the current state split by ResidualType (marginalization_factor.h:31-46:
- * 0 Pose, 1 IMU, 2 Bias, 3 Gravity, 4 LiDAR, ... 8 GlobalVelocity, 11 Image, 13 Prior; slot 14 = the pose / local-velocity /
+ * 0 Pose, 1 IMU, 2 Bias, 3 Gravity, 4 LiDAR, ... 8 GlobalVelocity, 11 Image, 13 Prior; slot 14 = the pose / local-velocity / pre-integration /
  * relative-rotation / image-depth adders together), constant-parameter factors included, and the number of factors added
  * per type.  A debugging aid: it runs one residual-only launch per stream. */
 CLIC_API int clic_residual_summary(clic_estimator* h, double cost[16], int64_t count[16]);

@@ -25,6 +25,7 @@
 
 #include "../include/clic_cuda.h"
 #include "factors.hpp"
+#include "factors_extra.hpp"
 #include "association.hpp"
 
 using namespace oracle;
@@ -1432,6 +1433,215 @@ CLIC_API int clic_add_image_depth(clic_estimator* E, const double p_i[3], const 
   rb.loss_a = 1.0;
   rb.rtype = 14;
   E->blocks.push_back(std::move(rb));
+  return CLIC_OK;
+}
+
+namespace {
+PreIntegrationData load_preintegration(const clic_preintegration* p) {
+  PreIntegrationData d;
+  d.sum_dt = p->sum_dt;
+  d.delta_p = load_v(p->delta_p);
+  d.delta_q = load_q(p->delta_q);
+  d.delta_v = load_v(p->delta_v);
+  d.linearized_ba = load_v(p->linearized_ba);
+  d.linearized_bg = load_v(p->linearized_bg);
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) {
+      d.jacobian[r][c] = p->jacobian[r * 15 + c];
+      d.sqrt_info[r][c] = p->sqrt_info[r * 15 + c];
+    }
+  d.gravity_norm = p->gravity_norm;
+  return d;
+}
+PointCorrespondence load_correspondence(const clic_factor_desc* f) {
+  PointCorrespondence pc;
+  pc.t_point = pc.t_map = 0;
+  pc.point = load_v(f->d);
+  pc.geo_type = f->geo_type;
+  for (int i = 0; i < 4; i++) pc.geo_plane[i] = f->d[3 + i];
+  pc.geo_normal = load_v(f->d + 7);
+  pc.geo_point = load_v(f->d + 10);
+  return pc;
+}
+}  // namespace
+
+// AddPreIntegrationAnalytic — trajectory_estimator.cpp:529-586 (PreIntegrationFactor, no loss); see clic_cuda.h for the
+// time arguments
+CLIC_API int clic_add_preintegration(clic_estimator* E, int64_t ta_ns, int64_t tb_ns, const clic_preintegration* pre,
+                                     int32_t slot_i, int32_t slot_j, int32_t* added) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!pre) return fail(CLIC_ERR_BAD_ARGUMENT, "null pre-integration");
+  if (E->opt.is_marg_state) return fail(CLIC_ERR_UNSUPPORTED, "pre-integration factor in a marginalization estimator");
+  if (slot_i < 0 || slot_j < 0 || slot_i >= E->n_bias || slot_j >= E->n_bias)
+    return fail(CLIC_ERR_BAD_ARGUMENT, "bias slot out of range");
+  if (added) *added = 0;
+  if (ta_ns < E->minTimeNs() || ta_ns > E->maxTimeNs() || tb_ns < E->minTimeNs() || tb_ns > E->maxTimeNs()) return CLIC_OK;
+  int64_t t_min = std::min(ta_ns, tb_ns), t_max = std::max(ta_ns, tb_ns);
+  SplineMeta meta;
+  E->CaculateSplineMeta({{t_min, t_min}, {t_max, t_max}}, meta);
+  ResidualBlock rb;
+  rb.cost.reset(new PreIntegrationFactor(load_preintegration(pre), ta_ns, tb_ns, meta));
+  E->AddControlPoints(meta, rb.refs, false);
+  E->AddControlPoints(meta, rb.refs, true);
+  rb.refs.push_back({CLIC_BLOCK_BIAS_GYRO, slot_i});
+  rb.refs.push_back({CLIC_BLOCK_BIAS_GYRO, slot_j});
+  rb.refs.push_back({CLIC_BLOCK_BIAS_ACCEL, slot_i});
+  rb.refs.push_back({CLIC_BLOCK_BIAS_ACCEL, slot_j});
+  rb.rtype = 14;  // (RType_PreIntegration = 7 in the reference; both libraries report the small adders together in slot 14)
+  E->blocks.push_back(std::move(rb));
+  if (added) *added = 1;
+  return CLIC_OK;
+}
+
+// One analytic factor against the current window: cost_function->Evaluate with the parameter blocks laid out like the
+// reference's test does (src/app/test_analytic_factor.cpp: CaculateSplineMeta over the measurement time(s),
+// AddControlPoints for rotation then position knots, then the factor's own blocks).
+CLIC_API int clic_evaluate_factor(clic_estimator* E, const clic_factor_desc* f, int32_t* n_res, double* residual,
+                                  int32_t* n_cols, double* jac, int64_t jac_capacity) {
+  if (!valid(E)) return fail(CLIC_ERR_BAD_HANDLE, "bad handle");
+  if (!f || !n_res || !residual || !n_cols) return fail(CLIC_ERR_BAD_ARGUMENT, "null argument");
+  const double* d = f->d;
+  double x[16];
+  for (int i = 0; i < 16; i++) x[i] = f->x[i];
+  std::unique_ptr<CostFunction> cost;
+  std::vector<BlockRef> refs;
+  std::vector<std::pair<double*, int>> extra;  // (pointer, size) of the blocks after the knots
+  auto in_window = [&](int64_t t) { return t >= E->minTimeNs() && t <= E->maxTimeNs(); };
+  auto knots_of = [&](const SplineMeta& meta) {
+    E->AddControlPoints(meta, refs, false);
+    E->AddControlPoints(meta, refs, true);
+  };
+  SplineMeta meta;
+  const double sqrt_info_default = E->opt.image_sqrt_info > 0.0 ? E->opt.image_sqrt_info : 450. / 1.5;
+  (void)sqrt_info_default;
+  switch (f->kind) {
+    case CLIC_FACTOR_POSE: {
+      const int64_t tc = f->t_a_ns + (int64_t)x[0];
+      if (!in_window(tc)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{tc, tc}}, meta);
+      PoseData pose;
+      pose.timestamp = 0;
+      pose.position = load_v(d);
+      pose.orientation = load_q(d + 3);
+      cost.reset(new IMUPoseFactor(f->t_a_ns, pose, meta.segments.at(0), d + 7));
+      knots_of(meta);
+      extra.push_back({x, 1});
+      break;
+    }
+    case CLIC_FACTOR_LOCAL_VELOCITY: {
+      const int64_t tc = f->t_a_ns + (int64_t)x[0];
+      if (!in_window(tc)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{tc, tc}}, meta);
+      cost.reset(new LocalVelocityFactor(f->t_a_ns, load_v(d), meta.segments.at(0), d[3]));
+      knots_of(meta);
+      extra.push_back({x, 1});
+      break;
+    }
+    case CLIC_FACTOR_RELATIVE_ROTATION: {
+      if (!in_window(f->t_a_ns) || !in_window(f->t_b_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      const int64_t t_min = std::min(f->t_a_ns, f->t_b_ns), t_max = std::max(f->t_a_ns, f->t_b_ns);
+      E->CaculateSplineMeta({{t_min, t_min}, {t_max, t_max}}, meta);
+      cost.reset(new RelativeOrientationFactor(load_q(d), f->t_a_ns, f->t_b_ns, meta, d + 4));
+      E->AddControlPoints(meta, refs, false);
+      break;
+    }
+    case CLIC_FACTOR_IMAGE_DEPTH:
+      cost.reset(new ImageDepthFactor(load_v(d), load_v(d + 3), load_q(d + 6), load_v(d + 10), d[13]));
+      extra.push_back({x, 1});
+      break;
+    case CLIC_FACTOR_PREINTEGRATION: {
+      if (!f->pre) return fail(CLIC_ERR_BAD_ARGUMENT, "null pre-integration");
+      if (!in_window(f->t_a_ns) || !in_window(f->t_b_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      const int64_t t_min = std::min(f->t_a_ns, f->t_b_ns), t_max = std::max(f->t_a_ns, f->t_b_ns);
+      E->CaculateSplineMeta({{t_min, t_min}, {t_max, t_max}}, meta);
+      cost.reset(new PreIntegrationFactor(load_preintegration(f->pre), f->t_a_ns, f->t_b_ns, meta));
+      knots_of(meta);
+      for (int i = 0; i < 4; i++) extra.push_back({x + 3 * i, 3});
+      break;
+    }
+    case CLIC_FACTOR_IMAGE_3D2D: {
+      const int64_t tc = f->t_a_ns + (int64_t)x[3];
+      if (!in_window(tc)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{tc, tc}}, meta);
+      cost.reset(new Image3D2DFactor(f->t_a_ns, load_v(d), meta, E->S_CtoI, E->p_CinI, d[3]));
+      knots_of(meta);
+      extra.push_back({x, 3});
+      extra.push_back({x + 3, 1});
+      break;
+    }
+    case CLIC_FACTOR_IMAGE_ONE_POSE: {
+      if (!in_window(f->t_a_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{f->t_a_ns, f->t_a_ns}}, meta);
+      cost.reset(new ImageFeatureOnePoseFactor(load_v(d), load_q(d + 3), load_v(d + 7), f->t_a_ns, load_v(d + 10), meta,
+                                               E->S_CtoI, E->p_CinI, d[13]));
+      knots_of(meta);
+      extra.push_back({x, 1});
+      break;
+    }
+    case CLIC_FACTOR_EPIPOLAR: {
+      if (!in_window(f->t_a_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{f->t_a_ns, f->t_a_ns}}, meta);
+      cost.reset(new EpipolarFactor(f->t_a_ns, load_v(d), load_v(d + 3), load_q(d + 6), load_v(d + 10), meta, d[13],
+                                    E->S_CtoI, E->p_CinI));
+      knots_of(meta);
+      break;
+    }
+    case CLIC_FACTOR_LOAM_OPT_MAP_POSE: {
+      if (!in_window(f->t_a_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      E->CaculateSplineMeta({{f->t_a_ns, f->t_a_ns}}, meta);
+      cost.reset(new LoamFeatureOptMapPoseFactor(f->t_a_ns, load_correspondence(f), meta.segments.at(0), d[13],
+                                                 load_q(d + 14), load_v(d + 18)));
+      knots_of(meta);
+      extra.push_back({x, 4});
+      extra.push_back({x + 4, 3});
+      break;
+    }
+    case CLIC_FACTOR_RELATIVE_LOAM: {
+      if (!in_window(f->t_a_ns) || !in_window(f->t_b_ns)) return fail(CLIC_ERR_BAD_ARGUMENT, "time outside the window");
+      const int64_t t_min = std::min(f->t_a_ns, f->t_b_ns), t_max = std::max(f->t_a_ns, f->t_b_ns);
+      E->CaculateSplineMeta({{t_min, t_min}, {t_max, t_max}}, meta);
+      cost.reset(new RalativeLoamFeatureFactor(f->t_a_ns, f->t_b_ns, load_correspondence(f), meta, d[13], load_q(d + 14),
+                                               load_v(d + 18)));
+      knots_of(meta);
+      break;
+    }
+    default: return fail(CLIC_ERR_BAD_ARGUMENT, "unknown factor kind");
+  }
+  const int nres = cost->num_residuals;
+  int ncols = 6 * E->K;
+  for (auto& e : extra) ncols += local_size(e.second);
+  *n_res = nres;
+  *n_cols = ncols;
+  const size_t np = refs.size() + extra.size();
+  if (np != cost->block_sizes.size()) return fail(CLIC_ERR_BAD_ARGUMENT, "parameter block count mismatch");
+  std::vector<const double*> params(np);
+  std::vector<std::vector<double>> jb(np);
+  std::vector<double*> jptr(np);
+  for (size_t i = 0; i < refs.size(); i++) params[i] = E->block_ptr(E->x, refs[i]);
+  for (size_t i = 0; i < extra.size(); i++) params[refs.size() + i] = extra[i].first;
+  for (size_t i = 0; i < np; i++) {
+    jb[i].assign((size_t)nres * cost->block_sizes[i], 0.0);
+    jptr[i] = jb[i].data();
+  }
+  std::vector<double> res(nres, 0.0);
+  cost->Evaluate(params.data(), res.data(), jac ? jptr.data() : nullptr);
+  for (int r = 0; r < nres; r++) residual[r] = res[r];
+  if (!jac) return CLIC_OK;
+  if ((int64_t)nres * ncols > jac_capacity) return fail(CLIC_ERR_BAD_ARGUMENT, "Jacobian buffer too small");
+  for (int64_t i = 0; i < (int64_t)nres * ncols; i++) jac[i] = 0.0;
+  int col = 6 * E->K;
+  for (size_t i = 0; i < np; i++) {
+    const int sz = cost->block_sizes[i], ls = local_size(sz);
+    int c0;
+    if (i < refs.size()) {
+      c0 = 6 * refs[i].id + (refs[i].kind == CLIC_BLOCK_KNOT_POS ? 3 : 0);
+    } else {
+      c0 = col;
+      col += ls;
+    }
+    for (int r = 0; r < nres; r++)
+      for (int c = 0; c < ls; c++) jac[(size_t)r * ncols + c0 + c] += jb[i][(size_t)r * sz + c];
+  }
   return CLIC_OK;
 }
 

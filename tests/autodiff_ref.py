@@ -211,3 +211,120 @@ def image_depth_residual(p_i, p_j, S_CitoCj, p_CiinCj, sqrt_info):
         x_j = qrot(torch.tensor(S_CitoCj), x_ci) + torch.tensor(p_CiinCj)
         return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2])) + 0.0 * dth.sum() + 0.0 * dp.sum()
     return fn
+
+
+# ---- the analytic factors the reference only exercises from its unit test ----
+def _loam_distance(p, geo_type, geo_plane, geo_normal, geo_point):
+    if geo_type == 1:
+        return (p * torch.tensor(geo_plane[:3])).sum() + geo_plane[3]
+    return torch.linalg.norm(torch.linalg.cross(p - torch.tensor(geo_point), torch.tensor(geo_normal)))
+
+
+def preintegration_residual(win, ta_ns, tb_ns, pre):
+    """auto_diff/trajectory_value_factor.h:703-756 + IntegrationBase::evaluate333 (integration_base.h:207-252);
+    pre: dict(sum_dt, delta_p, delta_q, delta_v, linearized_ba, linearized_bg, jacobian (15,15), sqrt_info (15,15),
+    gravity_norm); extras = (bg_a, bg_b, ba_a, ba_b)."""
+    Jm = torch.tensor(pre["jacobian"])
+    O_P, O_R, O_V, O_BA, O_BG = 0, 3, 6, 9, 12
+    dt = float(pre["sum_dt"])
+    g = torch.tensor([0.0, 0.0, -float(pre["gravity_norm"])])
+
+    def fn(dth, dp, bg_a, bg_b, ba_a, ba_b):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        sa, ua = sp.su(ta_ns)
+        sb, ub = sp.su(tb_ns)
+        Ra, _ = sp.rot_vel(sa, ua)
+        Rb, _ = sp.rot_vel(sb, ub)
+        Pa, Pb = sp.pos(sa, ua), sp.pos(sb, ub)
+        Va, Vb = sp.pos(sa, ua, 1), sp.pos(sb, ub, 1)
+        dba = ba_a - torch.tensor(pre["linearized_ba"])
+        dbg = bg_a - torch.tensor(pre["linearized_bg"])
+        cdp = torch.tensor(pre["delta_p"]) + Jm[O_P:O_P + 3, O_BA:O_BA + 3] @ dba + Jm[O_P:O_P + 3, O_BG:O_BG + 3] @ dbg
+        cdq = qmul(torch.tensor(pre["delta_q"]), qexp(Jm[O_R:O_R + 3, O_BG:O_BG + 3] @ dbg))
+        cdq = cdq / torch.linalg.norm(cdq)
+        cdv = torch.tensor(pre["delta_v"]) + Jm[O_V:O_V + 3, O_BA:O_BA + 3] @ dba + Jm[O_V:O_V + 3, O_BG:O_BG + 3] @ dbg
+        r_p = qrot(qconj(Ra), 0.5 * dt * dt * g + Pb - Pa - Va * dt) - cdp
+        r_R = qlog(qmul(qmul(qconj(cdq), qconj(Ra)), Rb))
+        r_v = qrot(qconj(Ra), g * dt + Vb - Va) - cdv
+        r = torch.cat([r_p, r_R, r_v, ba_b - ba_a, bg_b - bg_a])
+        return torch.tensor(pre["sqrt_info"]) @ r
+    return fn
+
+
+def image_3d2d_residual(win, tj_ns, p_j, S_CtoI, p_CinI, sqrt_info):
+    """auto_diff/image_feature_factor.h (Image3D2DFactor); extras = (p_G, t_offset_ns)."""
+    def fn(dth, dp, p_G, toff):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        toff_int = int(toff.detach()[0])
+        sj, uj = sp.su(tj_ns + toff_int, toff[0] - toff.detach()[0])
+        Rj, _ = sp.rot_vel(sj, uj)
+        qc = torch.tensor(S_CtoI)
+        p_Ij = qrot(qconj(Rj), p_G - sp.pos(sj, uj))
+        x_j = qrot(qconj(qc), p_Ij - torch.tensor(p_CinI))
+        return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2]))
+    return fn
+
+
+def image_one_pose_residual(win, p_i, S_IitoG, p_IiinG, tj_ns, p_j, S_CtoI, p_CinI, sqrt_info):
+    """auto_diff/image_feature_factor.h (ImageFeatureOnePoseFactor); extras = (inv_depth,)."""
+    def fn(dth, dp, rho):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        sj, uj = sp.su(tj_ns)
+        Rj, _ = sp.rot_vel(sj, uj)
+        qc = torch.tensor(S_CtoI)
+        p_Ii = qrot(qc, torch.tensor(p_i) / rho[0]) + torch.tensor(p_CinI)
+        p_G = qrot(torch.tensor(S_IitoG), p_Ii) + torch.tensor(p_IiinG)
+        p_Ij = qrot(qconj(Rj), p_G - sp.pos(sj, uj))
+        x_j = qrot(qconj(qc), p_Ij - torch.tensor(p_CinI))
+        return sqrt_info * (x_j[:2] / x_j[2] - torch.tensor(p_j[:2]))
+    return fn
+
+
+def epipolar_residual(win, ti_ns, x_i, x_k, S_GtoCk, p_CkinG, weight, S_CtoI, p_CinI):
+    """auto_diff/image_feature_factor.h (EpipolarFactor): x_k . ([t]x R x_i)."""
+    def fn(dth, dp):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        si, ui = sp.su(ti_ns)
+        Ri, _ = sp.rot_vel(si, ui)
+        qk = torch.tensor(S_GtoCk)
+        Rxi = qrot(qk, qrot(Ri, qrot(torch.tensor(S_CtoI), torch.tensor(x_i))))
+        t = qrot(qk, qrot(Ri, torch.tensor(p_CinI)) + sp.pos(si, ui) - torch.tensor(p_CkinG))
+        return (weight * (torch.tensor(x_k) * torch.linalg.cross(t, Rxi)).sum()).reshape(1)
+    return fn
+
+
+def loam_opt_map_pose_residual(win, t_ns, point, geo_type, geo_plane, geo_normal, geo_point, weight, S_LtoI, p_LinI,
+                               S_ImtoG):
+    """auto_diff/lidar_feature_factor.h (LoamFeatureOptMapPoseFactor); extras = (dtheta_map (right perturbation of
+    S_ImtoG), p_IminG)."""
+    def fn(dth, dp, dth_map, p_map):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        s, u = sp.su(t_ns)
+        R, _ = sp.rot_vel(s, u)
+        ql = torch.tensor(S_LtoI)
+        qm = qmul(torch.tensor(S_ImtoG), qexp(dth_map))
+        p_IK = qrot(ql, torch.tensor(point)) + torch.tensor(p_LinI)
+        p_G = qrot(R, p_IK) + sp.pos(s, u)
+        p_Im = qrot(qconj(qm), p_G - p_map)          # the map IMU frame
+        p_M = qrot(qconj(ql), p_Im - torch.tensor(p_LinI))  # ... and its LiDAR frame
+        return (weight * _loam_distance(p_M, geo_type, geo_plane, geo_normal, geo_point)).reshape(1)
+    return fn
+
+
+def relative_loam_residual(win, t_point_ns, t_map_ns, point, geo_type, geo_plane, geo_normal, geo_point, weight, S_LtoI,
+                           p_LinI):
+    """RalativeLoamFeatureFactor (analytic only in the reference; residual from lidar_feature_factor.h:398-455): the
+    point of scan time t_point expressed in the LiDAR frame of time t_map."""
+    def fn(dth, dp):
+        sp = perturbed_spline(win["t0_ns"], win["dt_ns"], win["knot_q"], win["knot_p"], dth, dp)
+        si, ui = sp.su(t_point_ns)
+        sj, uj = sp.su(t_map_ns)
+        Ri, _ = sp.rot_vel(si, ui)
+        Rj, _ = sp.rot_vel(sj, uj)
+        ql = torch.tensor(S_LtoI)
+        p_Ii = qrot(ql, torch.tensor(point)) + torch.tensor(p_LinI)
+        p_G = qrot(Ri, p_Ii) + sp.pos(si, ui)
+        p_Ij = qrot(qconj(Rj), p_G - sp.pos(sj, uj))
+        x_j = qrot(qconj(ql), p_Ij - torch.tensor(p_LinI))
+        return (weight * _loam_distance(x_j, geo_type, geo_plane, geo_normal, geo_point)).reshape(1)
+    return fn

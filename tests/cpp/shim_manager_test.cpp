@@ -11,6 +11,11 @@
 
 using namespace clic;
 
+static int fail(const char* what) {
+  std::printf("SHIM2_FAIL %s\n", what);
+  return 1;
+}
+
 int main() {
   auto traj = std::make_shared<Trajectory>(0.1);
   std::mt19937 rng(5);
@@ -95,6 +100,36 @@ int main() {
     S_CitoCj.q = {{0.01, 0.02, -0.01, 0.9997}};
     estimator->AddImageDepthAnalytic(Vec3d{{0.1, 0.05, 1.0}}, Vec3d{{0.13, 0.03, 1.0}}, S_CitoCj, Vec3d{{0.1, -0.05, 0.02}},
                                      &inv_depth[0]);
+    // PreIntegrationFactor between the two bias slots (trajectory_estimator.h:168-172); weak, so the solve keeps its shape
+    IntegrationBase pre;
+    pre.sum_dt = 0.3;
+    pre.delta_p = {0.31, -0.02, 0.01};
+    pre.delta_v = {0.1, 0.05, -0.02};
+    pre.delta_q = {{0.01, -0.02, 0.03, 0.9993}};
+    for (int i = 0; i < 15; i++) {
+      pre.jacobian[i * 15 + i] = 1.0;
+      pre.covariance[i * 15 + i] = 4.0 + 0.1 * i;
+    }
+    pre.jacobian[0 * 15 + 9] = -0.04;   // dp/dba
+    pre.jacobian[3 * 15 + 12] = -0.3;   // dq/dbg
+    pre.jacobian[6 * 15 + 9] = -0.3;    // dv/dba
+    pre.covariance[0 * 15 + 1] = pre.covariance[1 * 15 + 0] = 0.5;
+    estimator->AddPreIntegrationAnalytic(0.3, 0.6, &pre, bg0, bg1, ba0, ba1);
+    {  // one factor's residual / Jacobian (the reference's test_analytic_factor.cpp surface): an epipolar constraint
+      clic_factor_desc fd{};
+      fd.kind = CLIC_FACTOR_EPIPOLAR;
+      fd.t_a_ns = 530000000;
+      const double dd[14] = {0.1, 0.2, 1, 1.3, 1.2, 1, 0, 0, 0, 1, 1.3, 1.2, 1.0, 0.11};
+      for (int i = 0; i < 14; i++) fd.d[i] = dd[i];
+      std::vector<double> r, J;
+      int nc = 0;
+      if (!estimator->EvaluateFactor(fd, &r, &J, &nc) || r.size() != 1 || nc != 6 * (int)traj->numKnots() ||
+          J.size() != (size_t)nc)
+        return fail("EvaluateFactor(epipolar)");
+      int nz = 0;
+      for (double v : J) nz += v != 0.0;
+      if (nz != 24) return fail("EvaluateFactor: an epipolar factor touches 4 knots x 6 columns");
+    }
     Summary summary = estimator->Solve(8, false);
     cost1_init = summary.initial_cost;
     cost1_final = summary.final_cost;

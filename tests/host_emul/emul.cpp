@@ -136,13 +136,14 @@ __attribute__((visibility("default"))) int emul_small(int K, const double* kq, c
   sc.knot_col = knot_col;
   sc.col_toff_imu = col_toff_imu;
   sc.lm_col = lm_col;
+  sc.col_bias_gyro = sc.col_bias_accel = -1;
   SmallOut o;
   bool ok = false;
   switch (kind) {
     case kSmallPose: ok = small_pose_eval(W.view, f, t0_ns, dt_ns, K, toff_imu, sc, &o); break;
     case kSmallLocalVelocity: ok = small_local_velocity_eval(W.view, f, t0_ns, dt_ns, K, toff_imu, sc, &o); break;
     case kSmallRelativeRotation: ok = small_relative_rotation_eval(W.view, f, t0_ns, dt_ns, K, sc, &o); break;
-    default: ok = small_image_depth_eval(f, inv_depth, sc, &o); break;
+    default: ok = small_image_depth_eval(f, inv_depth, lm_col ? lm_col[landmark] : -1, &o); break;
   }
   if (!ok) return 1;
   *nres = o.nres;
