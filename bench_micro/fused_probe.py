@@ -24,10 +24,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (code and data)")
+    ap.add_argument("--no-visual", action="store_true", help="LiDAR + IMU only")
     args = ap.parse_args()
     lib = E.cuda_library()
     stream = torch.cuda.Stream()
-    sw = B.shard(B.make_workload(args.scale), 0, args.shard)
+    sw = B.shard(B.make_workload(args.scale, with_visual=not args.no_visual), 0, args.shard)
     split = type(sw)(window=sw.window, gt_knot_q=sw.gt_knot_q, gt_knot_p=sw.gt_knot_p, name=sw.name)
     split.imu, split.image = sw.imu, sw.image
     split.lidar = {k: v for k, v in sw.lidar.items()

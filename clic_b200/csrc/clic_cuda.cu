@@ -463,7 +463,9 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   const int64_t slabs = (n + factors_per_slab - 1) / factors_per_slab;
   const int max_ctas = E->n_sm * ctas_per_sm;
   // a full grid whenever there is at least one slab per warp; the kernels split the slabs evenly over its warps
-  int64_t ctas = std::min<int64_t>(max_ctas, (slabs + kWarpsPerCta - 1) / kWarpsPerCta);
+  // (the visual stream down to 4 slabs per CTA: see the partition model of the fused pass)
+  const int64_t min_per_cta = pair_keys ? std::max(1, kWarpsPerCta / 2) : kWarpsPerCta;
+  int64_t ctas = std::min<int64_t>(max_ctas, (slabs + min_per_cta - 1) / min_per_cta);
   ex.grid = (int)std::max<int64_t>(ctas, 1);
   ex.slabs_per_warp = (int)slabs;  // = total slabs (kernel argument)
   ex.n_warps = ex.grid * kWarpsPerCta;
@@ -543,9 +545,12 @@ int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] 
 // and of its 1/8 shard on B200 (bench_micro/fused_probe.py; profiles/).  Only the ratios matter, and a wrong model costs
 // balance, never correctness: the partition is a pure function of the problem, so results stay bit-reproducible.
 // CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
-struct FusedModel { double w[kFusedKinds], f[kFusedKinds]; };
+// ramp / ramp_to: the first ramp_to slabs of a warp cost `ramp` more each (the visual stream: nearly every early slab of
+// a warp opens a new interval pair, i.e. one more record for the CTA's dense finish; later slabs repeat pairs).
+struct FusedModel { double w[kFusedKinds], f[kFusedKinds], ramp[kFusedKinds], ramp_to[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.7, 3.2, 3.4, 13.8, 9.6, 12.0}, {14.0, 10.8, 14.5, 31.0, 41.6, 50.0}};
+  static FusedModel m = {{3.6, 3.05, 3.34, 12.3, 7.3, 12.0}, {14.0, 12.3, 14.8, 29.1, 31.2, 50.0},
+                         {0.0, 0.0, 0.0, 0.0, 11.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 2.5, 0.0}};
   static bool init = false;
   if (!init) {
     init = true;
@@ -598,7 +603,7 @@ int build_fused(clic_estimator* E) {
   int coop = 0;
   CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, E->device));
   if (!coop) return CLIC_OK;
-  struct Job { int kind; StreamExec* ex; int64_t slabs; int cap, n; double w, f; };
+  struct Job { int kind; StreamExec* ex; int64_t slabs; int cap, n; double w, f, ramp, ramp_to; };
   std::vector<Job> js;
   const FusedModel& M = fused_model();
   auto push = [&](int kind, StreamExec& ex, double scale = 1.0) {
@@ -606,10 +611,15 @@ int build_fused(clic_estimator* E) {
     j.kind = kind;
     j.ex = &ex;
     j.slabs = std::max<int64_t>(1, ex.slabs_per_warp);  // (the field holds the stream's total slab count)
-    j.cap = (int)std::max<int64_t>(1, std::min<int64_t>(ex.grid, (j.slabs + kWarpsPerCta - 1) / kWarpsPerCta));
+    // at most one slab per warp; the visual stream may spread thinner (down to 4 slabs per CTA): its dense finish costs
+    // one scatter per record, i.e. per slab when every slab is its own interval pair
+    const int64_t min_per_cta = kind >= 4 ? kWarpsPerCta / 2 : kWarpsPerCta;
+    j.cap = (int)std::max<int64_t>(1, std::min<int64_t>(ex.grid, (j.slabs + min_per_cta - 1) / min_per_cta));
     j.n = 1;
     j.w = M.w[kind] * scale;
     j.f = M.f[kind];
+    j.ramp = M.ramp[kind];
+    j.ramp_to = M.ramp_to[kind];
     js.push_back(j);
   };
   // same order as the descriptors / reduce jobs of ensure_layout: LiDAR batches in add order, IMU, visual
@@ -633,7 +643,7 @@ int build_fused(clic_estimator* E) {
   auto t_of = [&](const Job& j, int n) {
     const double per_warp = (double)j.slabs / (double)(kWarpsPerCta * n);
     const double rounds = (double)((j.slabs + (int64_t)kWarpsPerCta * n - 1) / ((int64_t)kWarpsPerCta * n));
-    return j.f + j.w * std::max(per_warp, lat * rounds);
+    return j.f + j.w * std::max(per_warp, lat * rounds) + j.ramp * std::min(per_warp, j.ramp_to);
   };
   {
     // min-max under the model: smallest T for which every stream fits, n_j(T) = fewest CTAs with t_of <= T

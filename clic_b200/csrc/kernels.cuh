@@ -18,7 +18,10 @@
 
 namespace clic {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef CLIC_WARPS_PER_CTA
+#define CLIC_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = CLIC_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kJtStride = 36;  // doubles per column of the transposed tile: = 4 (mod 16) => conflict-free fragment loads
 constexpr int kSlotsPerWarp = 4;
