@@ -1653,11 +1653,7 @@ __global__ void velocity_factor_kernel(VelFactorDesc vf, const double* state, St
   }
 }
 
-// The remaining adders of TrajectoryEstimator: pose, local-velocity, relative-rotation and image-depth
-// factors — a handful per solve at most.  One CTA walks them in add order: thread 0 evaluates a factor into a small
-// dense row set over the distinct global columns it touches (factor_eval.cuh), then every thread owns some of the
-// (column, column) pairs and adds J~^T J~, J~^T r~ into H, b: no atomics, fixed order.  Runs after the assembly (or
-// into the addend system of the fused pass), like velocity_factor_kernel.
+// ---- the small analytic factors ----
 // Values (x) and first columns (xcol, -1 = constant) of a small factor's parameter blocks after the knots.
 struct SmallX {
   double x[16];
@@ -1683,8 +1679,11 @@ __device__ __noinline__ bool small_dispatch(const WindowView& W, const SmallFact
   }
 }
 
-// The factors of the small adders (pose, local velocity, relative rotation, image depth, pre-integration) of a solve:
-// one CTA, thread 0 evaluates a factor into a row set over the columns it touches, then the threads add J^T J, J^T r.
+// The remaining adders of TrajectoryEstimator: pose, local-velocity, relative-rotation, image-depth and pre-integration
+// factors — a handful per solve at most.  One CTA walks them in add order: thread 0 evaluates a factor into a small
+// dense row set over the distinct global columns it touches (factor_eval.cuh), then every thread owns some of the
+// (column, column) pairs and adds J~^T J~, J~^T r~ into H, b: no atomics, fixed order.  Runs after the assembly (or
+// into the addend system of the fused pass), like velocity_factor_kernel.
 __global__ void __launch_bounds__(128) small_factors_kernel(const SmallFactor* fs, int n, const PreintData* pre, PassParams pp,
                                                             SmallCols sc, double* H, double* b, int D, double* cost2,
                                                             int jac) {
