@@ -521,7 +521,10 @@ def main():
                 h2d += d[k].nbytes
         setattr(src, name, d)
     h2d += 8 * (7 * sw.window.n_knots + sw.window.bias.size + 6)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
+    import gc
+    gc.collect()
+    gc.disable()  # a collection inside a 2 ms step would be charged to it
     order_small = os.environ.get("CLIC_BENCH_E2E_ORDER", "small") == "small"
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
@@ -539,6 +542,9 @@ def main():
             e2e_each.append((time.perf_counter() - t1) * 1e3)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        # the reported figure is the MEDIAN step (max over ranks): one host hiccup (a 26 ms step was seen once among 1.4 ms
+        # ones on a 2-rank run) otherwise decides a 20-step mean; the mean is kept next to it
+        e2e_med_s = max_over_ranks(float(np.median(e2e_each)) * 1e-3)
         # the call pattern of the reference's TrajectoryManager: upload once, Solve(8), read the state back
         for _ in range(2):
             e = new_estimator(src, small_first=order_small)
@@ -556,7 +562,9 @@ def main():
             solve_each.append((time.perf_counter() - t1) * 1e3)
         barrier()
         e2e_solve_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n_total * e2e_steps / e2e_s
+        e2e_solve_med_s = max_over_ranks(float(np.median(solve_each)) * 1e-3)
+    gc.enable()
+    e2e_value = n_total / e2e_med_s
     d2h = 8 * (D * D + D + 2)
     h2d_all = h2d
     if world > 1:
@@ -564,8 +572,9 @@ def main():
         dist.all_reduce(t)
         h2d_all = int(t.item())
     solve_passes = s8["num_jacobian_evals"]
-    e2e_solve = {"ms_per_solve": e2e_solve_s / e2e_steps * 1e3, "solves_per_s": e2e_steps / e2e_solve_s,
-                 "factor_evals_per_s": n_total * solve_passes * e2e_steps / e2e_solve_s,
+    e2e_solve = {"ms_per_solve": e2e_solve_med_s * 1e3, "ms_per_solve_mean": e2e_solve_s / e2e_steps * 1e3,
+                 "solves_per_s": 1.0 / e2e_solve_med_s,
+                 "factor_evals_per_s": n_total * solve_passes / e2e_solve_med_s,
                  "iterations": s8["iterations"], "jacobian_passes": solve_passes,
                  "ms_each_rank0": [round(x, 2) for x in solve_each],
                  "what": "create estimator + add every factor batch from pinned host memory (H2D once) + Solve(8) + "
@@ -705,7 +714,9 @@ def main():
                    "pass": info, "numa_node_rank0": numa},
         "gn_iterations": gn,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h * world),
-                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_each_rank0": [round(x, 2) for x in e2e_each]},
+                "steps": e2e_steps, "ms_per_step": e2e_med_s * 1e3, "ms_per_step_mean": e2e_s / e2e_steps * 1e3,
+                "statistic": "median step, max over ranks (mean of the same steps in ms_per_step_mean)",
+                "ms_each_rank0": [round(x, 2) for x in e2e_each]},
         "e2e_solve": e2e_solve,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "undistort_scan": undistort, "association": association,
     }
