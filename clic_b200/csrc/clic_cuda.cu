@@ -12,6 +12,7 @@
 #include <memory>
 #include <string>
 #include <utility>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -488,6 +489,26 @@ size_t factor_smem_bytes(int K, int NT) {
   return (window_smem_doubles(K) + jt) * sizeof(double);
 }
 
+size_t imu_smem_bytes(int K) { return factor_smem_bytes(K, 4); }
+
+// ImuCompactXform's expansion table: once per process and device
+int imu_xform_table(int device, const int4** out) {
+  static std::mutex mu;
+  static std::map<int, int4*> tabs;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = tabs.find(device);
+  if (it == tabs.end()) {
+    std::vector<int> h((size_t)kImuRecDoubles * 4);
+    ImuCompactXform::build_host(h.data());
+    int4* d = nullptr;
+    CU(cudaMalloc(&d, h.size() * sizeof(int)));
+    CU(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    it = tabs.emplace(device, d).first;
+  }
+  *out = it->second;
+  return CLIC_OK;
+}
+
 size_t image_smem_bytes(int K, int n_packs) {
   return factor_smem_bytes(K, 7) + (size_t)n_packs * kPackDoubles * sizeof(double);
 }
@@ -549,7 +570,7 @@ int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] 
 // a warp opens a new interval pair, i.e. one more record for the CTA's dense finish; later slabs repeat pairs).
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds], ramp[kFusedKinds], ramp_to[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.6, 3.05, 3.34, 12.3, 7.3, 12.0}, {14.0, 12.3, 14.8, 29.1, 31.2, 50.0},
+  static FusedModel m = {{3.6, 3.05, 3.34, 10.9, 7.3, 12.0}, {14.0, 12.3, 14.8, 27.5, 31.2, 50.0},
                          {0.0, 0.0, 0.0, 0.0, 11.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 2.5, 0.0}};
   static bool init = false;
   if (!init) {
@@ -714,7 +735,7 @@ int build_fused(clic_estimator* E) {
     fa.ovf_doubles[jn] = j.ex->n_keys * j.ex->rd;
     jn++;
     if (j.kind <= 2) body_smem = std::max(body_smem, loam_smem_bytes(E->K));
-    else if (j.kind == 3) body_smem = std::max(body_smem, factor_smem_bytes(E->K, 4));
+    else if (j.kind == 3) body_smem = std::max(body_smem, imu_smem_bytes(E->K));
     else body_smem = std::max(body_smem, image_smem_bytes(E->K, F.gb->st.n_packs));
   }
   fa.n_jobs = jn;
@@ -1208,7 +1229,7 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   auto launch_imu = [&](ImuBatch* b) -> int {
     StreamExec& ex = b->ex;
     if ((rc = wait_ready(E, ex))) return rc;
-    const size_t smem = factor_smem_bytes(E->K, 4);
+    const size_t smem = imu_smem_bytes(E->K);
     b->st.toff_free = E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1 : 0;
     if (jac) {
       E->prof_begin(1);
@@ -2003,7 +2024,7 @@ CLIC_API int clic_create(const clic_window_desc* w, const clic_options* opt, cli
   int rc = upload_state(E.get());
   if (rc) return rc;
   // opt in to > 48 KB dynamic shared memory once
-  size_t smem4 = factor_smem_bytes(E->K, 4), smem5 = factor_smem_bytes(E->K, 5);
+  size_t smem4 = imu_smem_bytes(E->K), smem5 = factor_smem_bytes(E->K, 5);
   static int attr_K = -1, attr_dev = -1;  // the opt-in is per function and device; only grows with K
   if (attr_dev != E->device || E->K > attr_K) {
   if ((rc = set_smem(loam_kernel<true, kLoamWarps, kLoamMinB, 0>, loam_smem_bytes(E->K))) ||
@@ -2306,6 +2327,10 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
   for (int i = 0; i < 6; i++) B->st.info[i] = info_vec[i];
   B->st.loss_a = marg_this_factor ? 3.0 : 10.0;  // trajectory_estimator.cpp:426-430
   B->st.bias_slot = bias_slot;
+  {
+    int rc_tab = imu_xform_table(E->device, &B->st.xform_tab);
+    if (rc_tab) return rc_tab;
+  }
   B->marg = (E->opt.is_marg_state && marg_this_factor) ? 1 : 0;
   B->st.extras_free = (!E->opt.lock_wb || !E->opt.lock_ab || !E->opt.lock_t_offset[S]) ? 1 : 0;
   B->st.marg_always = (E->opt.marg_bias_param || E->opt.marg_gravity_param || E->opt.marg_t_offset_param) ? 1 : 0;
@@ -2925,7 +2950,7 @@ CLIC_API int clic_residual_summary(clic_estimator* E, double cost[16], int64_t c
     if (b->marg) continue;
     if ((rc = wait_ready(E, b->ex))) return rc;
     b->st.toff_free = E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1 : 0;
-    CU(launch_pdl(imu_kernel<false, false>, b->ex.grid, kThreads, factor_smem_bytes(E->K, 4), E->stream, b->st, pp,
+    CU(launch_pdl(imu_kernel<false, false>, b->ex.grid, kThreads, imu_smem_bytes(E->K), E->stream, b->st, pp,
                   b->ex.slabs_per_warp, b->ex.rb()));
     job_type.push_back(1);  // RType_IMU
     if (count) count[1] += b->n_input;

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "factor_eval.cuh"
 
 namespace clic {
@@ -130,6 +132,25 @@ struct WarpAcc {
         }
     }
   }
+  // the same over an arbitrary subset of the column tiles (bit t of MASK: tile t takes part)
+  template <unsigned MASK>
+  __device__ __forceinline__ void accumulate_mask(const double* Jt, int lane) {
+    const int r4 = lane & 3, c8 = lane >> 2;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      double a[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) a[t] = (MASK & (1u << t)) ? Jt[(8 * t + c8) * kJtStride + 4 * ks + r4] : 0.0;
+#pragma unroll
+      for (int ta = 0; ta < NT; ta++)
+#pragma unroll
+        for (int tb = ta; tb < NT; tb++)
+          if ((MASK & (1u << ta)) && (MASK & (1u << tb))) {
+            const int idx = ta * NT - ta * (ta - 1) / 2 + (tb - ta);
+            dmma884(c[idx][0], c[idx][1], a[ta], a[tb]);
+          }
+    }
+  }
   __device__ __forceinline__ void store(double* rec, int lane) const {
 #pragma unroll
     for (int t = 0; t < n_tiles(NT); t++) {
@@ -148,7 +169,7 @@ struct WarpAcc {
   }
 };
 
-__device__ __forceinline__ int tile_index(int NT, int ta, int tb) {  // ta <= tb
+__host__ __device__ __forceinline__ int tile_index(int NT, int ta, int tb) {  // ta <= tb
   return ta * NT - ta * (ta - 1) / 2 + (tb - ta);
 }
 
@@ -175,10 +196,39 @@ __host__ __device__ inline size_t window_smem_doubles(int K) {
   return (((size_t)7 * K + (size_t)kPairDoubles * (K - 1)) + 1) & ~(size_t)1;
 }
 
-template <int NT, int EXTRA = 0>
+// A stream may accumulate in a COMPACT column basis and expand to the record layout everything downstream addresses
+// only when an accumulator leaves the registers (once per interval and warp, not per factor): Xform::entry(rec, e) is
+// element e of the standard record computed from the compact one.
+struct NoXform {
+  static constexpr bool kActive = false;
+  __device__ __forceinline__ double entry(const double* rec, int e) const { return rec[e]; }
+};
+
+// DEFER (dense finish): a record that gets a slot stays compact — only this CTA reads it back, and its finish expands it
+// with all threads instead of one warp inside the slab loop; the atomics fallback always takes expanded values.
+template <int NT, int EXTRA = 0, class Xform = NoXform, bool DEFER = false>
 __device__ __forceinline__ void flush_record(const WarpAcc<NT, EXTRA>& acc, int key, int& slot, int warp_global,
-                                             const RecordBuf& rb, int lane) {
+                                             const RecordBuf& rb, int lane, double* tmp = nullptr,
+                                             const Xform& xf = Xform()) {
   if (key < 0) return;
+  if (Xform::kActive && !(DEFER && slot < kSlotsPerWarp)) {  // tmp: rec_doubles(NT, EXTRA) doubles of the warp's own smem
+    constexpr int RD = rec_doubles(NT, EXTRA);
+    acc.store(tmp, lane);
+    __syncwarp();
+    const bool has_slot = slot < kSlotsPerWarp;
+    const int r = warp_global * kSlotsPerWarp + slot;
+    double* dst = has_slot ? rb.payload + (size_t)r * RD : rb.overflow + (size_t)key * RD;
+    for (int e = lane; e < RD; e += 32) {
+      const double v = xf.entry(tmp, e);
+      if (has_slot) dst[e] = v; else atomicAdd(dst + e, v);
+    }
+    if (lane == 0) {
+      if (has_slot) rb.key[r] = key; else *rb.overflow_flag = 1;
+    }
+    if (has_slot) slot++;
+    __syncwarp();
+    return;
+  }
   if (slot < kSlotsPerWarp) {
     int r = warp_global * kSlotsPerWarp + slot;
     acc.store(rb.payload + (size_t)r * rec_doubles(NT, EXTRA), lane);
@@ -212,7 +262,7 @@ struct ColMaps {
 };
 
 
-__device__ __forceinline__ int block_offset(int NT, int la, int lb) {  // la, lb: PHYSICAL columns of the record tiles
+__host__ __device__ __forceinline__ int block_offset(int NT, int la, int lb) {  // la, lb: PHYSICAL columns of the record tiles
   int ta = la >> 3, tb = lb >> 3;
   if (ta > tb) { int t = ta; ta = tb; tb = t; t = la; la = lb; lb = t; }
   return tile_index(NT, ta, tb) * 64 + (la & 7) * 8 + (lb & 7);
@@ -342,10 +392,10 @@ __device__ __noinline__ void dense_scatter_record(const DenseOut& dn, const doub
 }
 
 // End of a factor body in dense mode (replaces cta_merge_and_flush + the per-warp cost words).
-template <int NT, int EXTRA, int WARPS>
+template <int NT, int EXTRA, int WARPS, class Xform = NoXform>
 __device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, int acc_key, int slot, int warp, int lane,
                                                  int warp_global, const RecordBuf& rb, double* scratch, const DenseOut& dn,
-                                                 double cost, double fcost, bool jac) {
+                                                 double cost, double fcost, bool jac, const Xform& xf = Xform()) {
   constexpr int RD = rec_doubles(NT, EXTRA);
   __shared__ int s_keys[WARPS], s_slot[WARPS];
   __shared__ double s_cost[WARPS][2];
@@ -383,7 +433,14 @@ __device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, 
         scratch[(size_t)w0 * RD + e] = a;
       }
     }
-    dense_scatter_record<WARPS * 32>(dn, scratch + (size_t)w0 * RD, kc);
+    if (Xform::kActive) {  // expand the (merged) compact record behind the parked ones, scatter that
+      double* xbuf = scratch + (size_t)WARPS * RD;
+      __syncthreads();  // the merge is complete; the previous scatter no longer reads xbuf
+      for (int e = threadIdx.x; e < RD; e += WARPS * 32) xbuf[e] = xf.entry(scratch + (size_t)w0 * RD, e);
+      dense_scatter_record<WARPS * 32>(dn, xbuf, kc);
+    } else {
+      dense_scatter_record<WARPS * 32>(dn, scratch + (size_t)w0 * RD, kc);
+    }
   }
   // records flushed in mid-run (a warp whose interval changed): read back from this CTA's own slots, in (warp, slot)
   // order, through the (now free) parking area — every load of a record in flight at once; scattering straight from
@@ -406,7 +463,14 @@ __device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, 
         const int e = q * WARPS * 32 + threadIdx.x;
         if (e < RD) scratch[e] = v[q];
       }
-      dense_scatter_record<WARPS * 32>(dn, scratch, key);
+      if (Xform::kActive) {  // stored compact (flush_record<..., DEFER>): expand next to it
+        double* xbuf = scratch + (size_t)WARPS * RD;
+        __syncthreads();
+        for (int e = threadIdx.x; e < RD; e += WARPS * 32) xbuf[e] = xf.entry(scratch, e);
+        dense_scatter_record<WARPS * 32>(dn, xbuf, key);
+      } else {
+        dense_scatter_record<WARPS * 32>(dn, scratch, key);
+      }
     }
   __syncthreads();
 }
@@ -417,9 +481,10 @@ __device__ __forceinline__ void cta_finish_dense(const WarpAcc<NT, EXTRA>& acc, 
 // (WARPS * rec_doubles doubles; may alias the Jt tiles, dead by now) in parallel, then all threads of the CTA sum
 // their elements over the matching warps in warp order and write the record straight to global memory — two block
 // barriers instead of one per warp (the visual record is 14 KB per warp: the serial variant cost ~8 us there).
-template <int NT, int EXTRA = 0, int WARPS = kWarpsPerCta>
+template <int NT, int EXTRA = 0, int WARPS = kWarpsPerCta, class Xform = NoXform>
 __device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT, EXTRA>& acc, int acc_key, int& slot, int warp, int lane,
-                                                    int warp_global, const RecordBuf& rb, double* scratch) {
+                                                    int warp_global, const RecordBuf& rb, double* scratch,
+                                                    const Xform& xf = Xform()) {
   constexpr int RD = rec_doubles(NT, EXTRA);
   __shared__ int s_keys[WARPS], s_slot[WARPS];
   __syncthreads();  // the Jt tiles under `scratch` are dead for every warp
@@ -431,17 +496,34 @@ __device__ __forceinline__ void cta_merge_and_flush(const WarpAcc<NT, EXTRA>& ac
   for (int w = WARPS - 1; w >= 0; w--)
     if (s_keys[w] >= 0) { kc = s_keys[w]; w_first = w; }
   if (kc < 0) return;
-  if (acc_key >= 0 && acc_key != kc) flush_record<NT, EXTRA>(acc, acc_key, slot, warp_global, rb, lane);
+  if (acc_key >= 0 && acc_key != kc)  // (its own parked slice doubles as the staging area: nobody else reads it)
+    flush_record<NT, EXTRA, Xform>(acc, acc_key, slot, warp_global, rb, lane, scratch + (size_t)warp * RD, xf);
   const int slot_f = s_slot[w_first];
   const bool has_slot = slot_f < kSlotsPerWarp;
   const int r = (warp_global - warp + w_first) * kSlotsPerWarp + slot_f;
   double* dst = has_slot ? rb.payload + (size_t)r * RD : rb.overflow + (size_t)kc * RD;
-  for (int e = threadIdx.x; e < RD; e += WARPS * 32) {
-    double a = 0.0;
+  if (Xform::kActive) {  // merge in the compact basis behind the parked records, expand on the way out
+    double* merged = scratch + (size_t)WARPS * RD;
+    for (int e = threadIdx.x; e < RD; e += WARPS * 32) {
+      double a = 0.0;
 #pragma unroll
-    for (int w = 0; w < WARPS; w++)
-      if (s_keys[w] == kc) a += scratch[(size_t)w * RD + e];
-    if (has_slot) dst[e] = a; else atomicAdd(dst + e, a);
+      for (int w = 0; w < WARPS; w++)
+        if (s_keys[w] == kc) a += scratch[(size_t)w * RD + e];
+      merged[e] = a;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < RD; e += WARPS * 32) {
+      const double v = xf.entry(merged, e);
+      if (has_slot) dst[e] = v; else atomicAdd(dst + e, v);
+    }
+  } else {
+    for (int e = threadIdx.x; e < RD; e += WARPS * 32) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++)
+        if (s_keys[w] == kc) a += scratch[(size_t)w * RD + e];
+      if (has_slot) dst[e] = a; else atomicAdd(dst + e, a);
+    }
   }
   if (warp == w_first) {
     if (has_slot) {
@@ -785,6 +867,7 @@ struct ImuStream {
   int extras_free;  // a bias / time-offset block of these factors is a free parameter (options, known at add time)
   int marg_always;  // marg mode: a non-knot block of these factors is dropped, so they all enter the prior
   int toff_free;    // the IMU time offset has a column in H (set per pass from the layout)
+  const int4* xform_tab;  // ImuCompactXform's expansion table (solve mode)
 };
 
 template <int NT>
@@ -845,10 +928,135 @@ struct ImuRowSink {
     __syncwarp();
   }
 };
+// ---- solve-mode IMU rows in a COMPACT column basis: 9 instead of 13 tile products per factor ----
+// The accel rows' 12 position columns are lambda_k(u) * A with ONE 1x3 row A = s_I * row(R^-1) per residual row and
+// lambda_k = inv_dt^2 * (1 - u, -2 + 3u, 1 - 3u, u) (second derivative of the cubic blend): rank 2 over the four knots.
+// They are accumulated as 6 basis columns  B0 = lambda_0 A + lambda_3 A (= inv_dt^2 A),  B1 = lambda_3 A (= inv_dt^2 u A)
+// and expanded (dp_k = M0[k] B0 + M1[k] B1, M0 = (1, -2, 1, 0), M1 = (-1, 3, -3, 1)) when an accumulator leaves the
+// registers.  Compact physical layout, chosen so that a row type touches as few column tiles as possible:
+//   tile 0: dtheta 0..7        tile 1: dtheta 8..11 | r | bg        (gyro rows)
+//   tile 2: dtheta 8..11 | r | ba   (accel rows)                    tile 3: B0 | B1 | t_off | 0
+// gyro rows multiply tiles {0, 1} (+ 3 when the IMU time offset is free), accel rows tiles {0, 2, 3}; the two copies of
+// dtheta 8..11 and of r are summed by the expansion, tile (1, 2) is never touched.  The expansion is exact algebra; the
+// result differs from the direct accumulation by rounding only (lambda_0 + lambda_3 vs inv_dt^2, order of the sums).
+struct ImuCompactSink {
+  double* Jt;
+  int lane;
+  bool on;
+  bool toff_free;
+  WarpAcc<4>* acc;
+  __device__ __forceinline__ void put(int row, int col, double v) {
+    v = on ? v : 0.0;
+    double* J = Jt + lane;
+    if (col < 24) {
+      const int k = col / 6, c = col % 6;
+      if (c < 3) {
+        const int i = 3 * k + c;
+        J[(i < 8 ? i : (row < 3 ? i : i + 8)) * kJtStride] = v;
+      } else if (row >= 3 || toff_free) {  // (gyro rows: zeros, only read when tile 3 takes part)
+        if (k == 0) J[(24 + c - 3) * kJtStride] = v;
+        if (k == 3) { J[(27 + c - 3) * kJtStride] = v; J[(24 + c - 3) * kJtStride] += v; }
+      }
+    } else if (col < 27) {
+      if (row < 3) J[(13 + col - 24) * kJtStride] = v;
+    } else if (col < 30) {
+      if (row >= 3) J[(21 + col - 27) * kJtStride] = v;
+    } else if (col == 30) {
+      J[30 * kJtStride] = v;
+    } else {
+      J[(row < 3 ? 12 : 20) * kJtStride] = v;
+    }
+  }
+  __device__ __forceinline__ void row_done(int row) {
+    __syncwarp();
+    if (row < 3) {
+      if (toff_free) acc->template accumulate_mask<0xBu>(Jt, lane); else acc->template accumulate_mask<0x3u>(Jt, lane);
+    } else {
+      acc->template accumulate_mask<0xDu>(Jt, lane);
+    }
+    __syncwarp();
+  }
+};
+// standard physical column (imu_phys_col<false>) -> logical column
+__host__ __device__ __forceinline__ int imu_std_logical(int p) {
+  if (p < 12) return (p / 3) * 6 + p % 3;
+  if (p < 15) return 24 + (p - 12);
+  if (p == 15) return 31;
+  if (p == 16) return 30;
+  if (p < 20) return 27 + (p - 17);
+  const int j = p - 20;
+  return (j / 3) * 6 + 3 + j % 3;
+}
+// a logical column as a combination of compact columns: returns the number of terms
+__host__ __device__ __forceinline__ int imu_compact_terms(int l, int col[2], double w[2]) {
+  w[0] = w[1] = 1.0;
+  if (l < 24) {
+    const int k = l / 6, c = l % 6;
+    if (c < 3) {
+      const int i = 3 * k + c;
+      col[0] = i;
+      col[1] = i + 8;
+      return i < 8 ? 1 : 2;
+    }
+    col[0] = 24 + c - 3;
+    col[1] = 27 + c - 3;
+    w[0] = k == 0 ? 1.0 : (k == 1 ? -2.0 : (k == 2 ? 1.0 : 0.0));
+    w[1] = k == 0 ? -1.0 : (k == 1 ? 3.0 : (k == 2 ? -3.0 : 1.0));
+    return 2;
+  }
+  if (l < 27) { col[0] = 13 + l - 24; return 1; }
+  if (l < 30) { col[0] = 21 + l - 27; return 1; }
+  if (l == 30) { col[0] = 30; return 1; }
+  col[0] = 12;
+  col[1] = 20;
+  return 2;
+}
+// Every element of the standard record is a combination of <= 4 elements of the compact one with small integer
+// weights: a table (offset << 8 | weight + 128, four terms per element; weight 0 = unused) built once on the host
+// (ImuStream::xform_tab, 10 KB of global memory), so that an expansion is one 16-byte load + 4 loads + 4 FMAs per element.
+constexpr int kImuRecDoubles = 640;  // rec_doubles(4, 0)
+struct ImuCompactXform {
+  static constexpr bool kActive = true;
+  const int4* tab;
+  __device__ __forceinline__ double entry(const double* cmp, int e) const {
+    const int4 q = __ldg(tab + e);
+    double v = (double)((q.x & 255) - 128) * cmp[q.x >> 8];
+    v += (double)((q.y & 255) - 128) * cmp[q.y >> 8];
+    v += (double)((q.z & 255) - 128) * cmp[q.z >> 8];
+    v += (double)((q.w & 255) - 128) * cmp[q.w >> 8];
+    return v;
+  }
+  static void build_host(int* tab /*[kImuRecDoubles * 4]*/) {
+    for (int e = 0; e < kImuRecDoubles; e++) {
+      const int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+      const int ta = t < 4 ? 0 : (t < 7 ? 1 : (t < 9 ? 2 : 3));
+      const int tb = t < 4 ? t : (t < 7 ? t - 3 : (t < 9 ? t - 5 : 3));
+      int ca[2], cb[2];
+      double wa[2], wb[2];
+      const int na = imu_compact_terms(imu_std_logical(8 * ta + rr), ca, wa);
+      const int nb = imu_compact_terms(imu_std_logical(8 * tb + cc), cb, wb);
+      int term[4] = {128, 128, 128, 128};  // offset 0, weight 0
+      int n = 0;
+      for (int x = 0; x < na; x++)
+        for (int y = 0; y < nb; y++) {
+          const int w = (int)(wa[x] * wb[y]);
+          if (w != 0) term[n++] = (block_offset(4, ca[x], cb[y]) << 8) | (w + 128);
+        }
+      for (int i = 0; i < 4; i++) tab[4 * e + i] = term[i];
+    }
+  }
+};
+
 struct NullSink {
   __device__ __forceinline__ void put(int, int, double) {}
   __device__ __forceinline__ void row_done(int) {}
 };
+
+__device__ __forceinline__ void imu_xform_setup(NoXform&, const int4*) {}
+__device__ __forceinline__ void imu_xform_setup(ImuCompactXform& xf, const int4* tab) { xf.tab = tab; }
+__device__ __forceinline__ void imu_sink_mode(ImuRowSink<true>& s, bool) { s.gyro2 = false; }
+__device__ __forceinline__ void imu_sink_mode(ImuRowSink<false>& s, bool toff_free) { s.gyro2 = !toff_free; }
+__device__ __forceinline__ void imu_sink_mode(ImuCompactSink& s, bool toff_free) { s.toff_free = toff_free; }
 
 // Local columns (solve, NT=4): [knots 0..23 | bg 24..26 | ba 27..29 | toff 30 | r 31]
 //               (marg,  NT=5): [knots 0..23 | bg | ba | gravity 30..32 | toff 33 | r 34 | pad]
@@ -872,6 +1080,19 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
   sh.inv_dt = 1e9 / double(pp.dt_ns);
   sh.want_toff = MARG || st.toff_free;
   const int64_t toff = (int64_t)pp.state[pp.sl.off_toff() + 0];  // (int64_t)time_offset_in_ns, trajectory_value_factor.h:175
+  // The compact accumulation basis pays where the expansion is done by the whole CTA (dense finish of the fused pass);
+  // the per-stream kernels, which serve the small windows, keep the direct layout (an expansion per warp and record cost
+  // them 2-3 us per pass).
+  constexpr bool CMP = !MARG && DENSE;
+  using Xf = typename std::conditional<CMP, ImuCompactXform, NoXform>::type;
+  Xf xf;
+  imu_xform_setup(xf, st.xform_tab);
+  if (CMP && JAC) {
+    if (threadIdx.x < (kImuRecDoubles * 16 + 127) / 128)  // the table is read at the very end: have it in L2 by then
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(st.xform_tab) + 128 * threadIdx.x));
+    Jt[31 * kJtStride + lane] = 0.0;  // the one column of the compact layout nobody writes
+    __syncwarp();
+  }
 
   WarpAcc<NT> acc;
   acc.zero();
@@ -904,13 +1125,19 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
       bool mine = (key == kmin) && ((pending >> lane) & 1);
       if (JAC) {
         if (kmin != acc_key) {
-          flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+          if (CMP) {  // the compact record is staged in the warp's own tile (free between two row sets) and expanded
+            flush_record<NT, 0, Xf, DENSE>(acc, acc_key, slot, warp_global, rb, lane, Jt, xf);
+            Jt[31 * kJtStride + lane] = 0.0;
+            __syncwarp();
+          } else {
+            flush_record<NT>(acc, acc_key, slot, warp_global, rb, lane);
+          }
           acc.zero();
           acc_key = kmin;
         }
-        ImuRowSink<MARG> sink;
+        typename std::conditional<CMP, ImuCompactSink, ImuRowSink<MARG>>::type sink;
         sink.Jt = Jt; sink.lane = lane; sink.on = mine; sink.acc = &acc;
-        sink.gyro2 = !MARG && !st.toff_free;
+        imu_sink_mode(sink, st.toff_free != 0);
         double rho = imu_eval<MARG>(W, mine ? s : kmin, mine ? u : 0.0, gy, ac, sh, true, sink);
         if (mine) { if (s + 3 >= pp.kf || st.extras_free || MARG) cost += 0.5 * rho; else fcost += 0.5 * rho; }
       } else {
@@ -930,11 +1157,11 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
   }
   if (DENSE) {
     dense_stamp(dn, 7);
-    cta_finish_dense<NT, 0, kWarpsPerCta>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC);
+    cta_finish_dense<NT, 0, kWarpsPerCta, Xf>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, *dn, cost, fcost, JAC, xf);
     return;
   }
   if (JAC) {
-    cta_merge_and_flush<NT>(acc, acc_key, slot, warp, lane, warp_global, rb, rest);
+    cta_merge_and_flush<NT, 0, kWarpsPerCta, Xf>(acc, acc_key, slot, warp, lane, warp_global, rb, rest, xf);
     for (int sidx = slot + lane; sidx < kSlotsPerWarp; sidx += 32) rb.key[warp_global * kSlotsPerWarp + sidx] = -1;
   }
   if (lane == 0) {
