@@ -1480,7 +1480,7 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   const int* ctl_res = &B.st->skip_res;
   const int* ctl_jac = &B.st->skip_jac;
   const size_t sm_small = 1024 * sizeof(double);
-  size_t sm_step = (size_t)(512 + 3 * D + ((D + 7) / 8) * 64) * sizeof(double);
+  size_t sm_step = (size_t)(std::max(512 + 3 * D + ((D + 7) / 8) * 64, 1024)) * sizeof(double);  // >= the accept / post scratch
   int a_in_smem = 0;
   if (sm_step + (size_t)(D + 1) * (D | 1) * sizeof(double) <= 200 * 1024) {
     a_in_smem = 1;
@@ -1500,9 +1500,17 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   E->prof_end();
   E->launches++;
   const int max_ls = 20;  // Ceres default max_num_line_search_step_size_iterations
+  // speculative Jacobians (the common case): accept + post of iteration it - 1 can run at the head of lm_step_kernel of
+  // iteration it instead of as two launches of their own.  Measured (bench_micro/solve_time.py, CLIC_LM_TIMELINE): a
+  // production-size window (per-stream kernels; C1) gains 8 % per LM iteration (86 -> 79 us); with the fused pass it
+  // is neutral (C3) to 2 % slower (C5: the step part of the merged kernel takes 52 instead of 47 us), so those keep
+  // the separate launches.  CLIC_LM_FUSE_ACCEPT=0/1 forces.
+  static const int fuse_env = [] { const char* e = getenv("CLIC_LM_FUSE_ACCEPT"); return e ? atoi(e) : -1; }();
+  const bool fuse_accept = speculate && !constrained && (fuse_env < 0 ? !E->fused.ok : fuse_env != 0);
   for (int it = 0; it <= max_iterations; it++) {
     E->prof_begin(5);
-    CU(launch_pdl(lm_step_kernel, 1, 512, sm_step, E->stream, B, L, C, a_in_smem, constrained ? 1 : 0));
+    CU(launch_pdl(lm_step_kernel, 1, 512, sm_step, E->stream, B, L, C, a_in_smem, constrained ? 1 : 0,
+                  (fuse_accept && it > 0) ? (fuse_env == 2 ? 2 : 1) : 0));
     E->prof_end();
     E->launches++;
     if (it == max_iterations) break;  // the last launch only records the max-iterations termination
@@ -1518,15 +1526,17 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
         if (!active) break;
       }
     }
-    E->prof_begin(5);
-    CU(launch_pdl(lm_accept_kernel, 1, 1024, sm_small, E->stream, B, L, C));
-    E->prof_end();
-    E->launches++;
-    if (!speculate && (rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
-    E->prof_begin(5);
-    CU(launch_pdl(lm_post_kernel, 1, 256, sm_small, E->stream, B, L));
-    E->prof_end();
-    E->launches++;
+    if (!fuse_accept) {
+      E->prof_begin(5);
+      CU(launch_pdl(lm_accept_kernel, 1, 1024, sm_small, E->stream, B, L, C));
+      E->prof_end();
+      E->launches++;
+      if (!speculate && (rc = run_pass(E, B.x, true, 0, ctl_jac))) return rc;
+      E->prof_begin(5);
+      CU(launch_pdl(lm_post_kernel, 1, 256, sm_small, E->stream, B, L));
+      E->prof_end();
+      E->launches++;
+    }
     // Long solves (Solve(50) of InitTrajWithPropagation) usually converge within a handful of iterations; every
     // iteration enqueued after that is ~9 launches that exit at once.  One 4-byte poll every 8 iterations stops the
     // enqueueing instead (Solve(8), the inner-iteration solve, never polls).
@@ -1545,6 +1555,15 @@ int lm_solve(clic_estimator* E, int max_iterations, clic_summary* summary) {
   CU(cudaGetLastError());
   if (in_flags[1]) return fail(CLIC_ERR_BAD_ARGUMENT, "clic_add_loam: geometry array missing for a record type that is present");
   if (int prc = check_p2p(E)) return prc;
+#ifdef CLIC_LM_TIMELINE
+  if (getenv("CLIC_LM_TIMELINE")) {  // developer aid: entry / exit of the LM kernels on the device clock
+    fprintf(stderr, "LM timeline (us since the first stamp; 1 init, 10 step entry, 11 after accept, 12 after post, 19 step exit, "
+                    "20/21 accept kernel, 30/31 post kernel):\n");
+    for (int i = 0; i < st.nts && i < 96; i++)
+      fprintf(stderr, "  %2d %9.2f%s", st.tag[i], (double)(st.ts[i] - st.ts[0]) * 1e-3, (i % 6 == 5) ? "\n" : "");
+    fprintf(stderr, "\n");
+  }
+#endif
   if (summary) {
     std::memset(summary, 0, sizeof(*summary));
     summary->iterations = st.iteration;

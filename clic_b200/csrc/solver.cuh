@@ -475,7 +475,25 @@ struct LmState {
   int skip_res;  // control word of the residual-only pass
   int step_valid, max_iterations;
   int ls_active, ls_iter, ls_success;
+  // developer timeline (build with -DCLIC_LM_TIMELINE, run with CLIC_LM_TIMELINE=1): entry / exit %globaltimer of the LM kernels
+  int nts;
+  int tag[96];
+  unsigned long long ts[96];
 };
+// (developer build -DCLIC_LM_TIMELINE: every stamp is a global read-modify-write by thread 0, ~1 us)
+__device__ __forceinline__ void lm_ts(LmState* s, int tag) {
+#ifdef CLIC_LM_TIMELINE
+  if (threadIdx.x == 0 && s->nts < 96) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    s->ts[s->nts] = t;
+    s->tag[s->nts++] = tag;
+  }
+#else
+  (void)s;
+  (void)tag;
+#endif
+}
 
 struct LayoutDev {
   const int* lm_col;  // per landmark: column of its inverse depth, -1 if constant (nullptr: none is free)
@@ -564,23 +582,51 @@ __device__ __forceinline__ void ambient_diff(const double* x, const double* y, c
       dm = fmax(dm, fabs(d));
     }
   };
+  // (the values are loaded whether or not the block is active: one memory round trip instead of two dependent ones)
   for (int k = L.kf + threadIdx.x; k < L.K; k += blockDim.x) {
     const int c = 6 * (k - L.kf);
-    if (active[c]) acc(x + L.sl.off_q() + 4 * k, y + L.sl.off_q() + 4 * k, 4);
-    if (active[c + 3]) acc(x + L.sl.off_p() + 3 * k, y + L.sl.off_p() + 3 * k, 3);
+    const int a0 = active[c], a1 = active[c + 3];
+    double xv[7], yv[7];
+    for (int i = 0; i < 4; i++) { xv[i] = x[L.sl.off_q() + 4 * k + i]; yv[i] = y[L.sl.off_q() + 4 * k + i]; }
+    for (int i = 0; i < 3; i++) { xv[4 + i] = x[L.sl.off_p() + 3 * k + i]; yv[4 + i] = y[L.sl.off_p() + 3 * k + i]; }
+    if (a0) acc(xv, yv, 4);
+    if (a1) acc(xv + 4, yv + 4, 3);
   }
   for (int j = threadIdx.x; j < L.nb; j += blockDim.x) {
-    if (L.col_bias_gyro >= 0 && active[L.col_bias_gyro + 3 * j])
-      acc(x + L.sl.off_bias() + 6 * j, y + L.sl.off_bias() + 6 * j, 3);
-    if (L.col_bias_accel >= 0 && active[L.col_bias_accel + 3 * j])
-      acc(x + L.sl.off_bias() + 6 * j + 3, y + L.sl.off_bias() + 6 * j + 3, 3);
+    const int a0 = L.col_bias_gyro >= 0 ? active[L.col_bias_gyro + 3 * j] : 0;
+    const int a1 = L.col_bias_accel >= 0 ? active[L.col_bias_accel + 3 * j] : 0;
+    double xv[6], yv[6];
+    for (int i = 0; i < 6; i++) { xv[i] = x[L.sl.off_bias() + 6 * j + i]; yv[i] = y[L.sl.off_bias() + 6 * j + i]; }
+    if (a0) acc(xv, yv, 3);
+    if (a1) acc(xv + 3, yv + 3, 3);
   }
   if (threadIdx.x < 3 && L.col_toff[threadIdx.x] >= 0 && active[L.col_toff[threadIdx.x]])
     acc(x + L.sl.off_toff() + threadIdx.x, y + L.sl.off_toff() + threadIdx.x, 1);
   if (L.lm_col)
     for (int l = threadIdx.x; l < L.L; l += blockDim.x)
       if (L.lm_col[l] >= 0 && active[L.lm_col[l]]) acc(x + L.sl.off_invd() + l, y + L.sl.off_invd() + l, 1);
-  double a = block_sum(xs, sh), b = block_sum(ds, sh), c = block_max(dm, sh);
+  // the three reductions share their barriers (same orders as block_sum / block_max: butterfly, then warps in order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xs += __shfl_xor_sync(0xffffffffu, xs, o);
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+  }
+  __syncthreads();
+  const int nw = (int)(blockDim.x >> 5);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = xs;
+    sh[nw + (threadIdx.x >> 5)] = ds;
+    sh[2 * nw + (threadIdx.x >> 5)] = dm;
+  }
+  __syncthreads();
+  double a = 0.0, b = 0.0, c = sh[2 * nw];
+  for (int w = 0; w < nw; w++) {
+    a += sh[w];
+    b += sh[nw + w];
+    c = fmax(c, sh[2 * nw + w]);
+  }
+  __syncthreads();
   if (xs_out) *xs_out = a;
   if (ds_out) *ds_out = b;
   if (dm_out) *dm_out = c;
@@ -606,17 +652,89 @@ struct LmBufs {
 };
 
 // gradient_max_norm = |x - Plus(x, -g)|_inf and |x| (TrustRegionMinimizer::EvaluateGradientAndJacobian)
+// One pass: every thread forms Plus(x, -g) of ITS blocks in registers (the arithmetic of plus_state, block by block) and
+// accumulates |x|^2 and |x - Plus|_inf in ambient_diff's order — the same numbers as plus_state into a scratch state +
+// ambient_diff, in one memory round trip instead of four dependent ones.
 __device__ __forceinline__ void gradient_norms(const LmBufs& B, const LayoutDev& L, double* sh) {
-  for (int i = threadIdx.x; i < L.D; i += blockDim.x) B.step[i] = -B.b[i];  // step is free scratch here
-  __syncthreads();
-  plus_state(B.x, B.step, 1.0, B.tmp, L);
-  double xs, dm;
-  ambient_diff(B.x, B.tmp, B.active, L, sh, &xs, nullptr, &dm);
-  if (threadIdx.x == 0) {
-    B.st->x_norm = sqrt(xs);
-    B.st->gmax = dm;
+  const double* x = B.x;
+  const double* g = B.b;
+  const int* active = B.active;
+  double xs = 0, ds = 0, dm = 0;
+  auto acc = [&](const double* a, const double* b, int n) {
+    for (int i = 0; i < n; i++) {
+      xs += a[i] * a[i];
+      double d = a[i] - b[i];
+      ds += d * d;
+      dm = fmax(dm, fabs(d));
+    }
+  };
+  for (int k = L.kf + threadIdx.x; k < L.K; k += blockDim.x) {
+    const int c = 6 * (k - L.kf);
+    const int a0 = active[c], a1 = active[c + 3];
+    double xv[7], yv[7], d[6];
+    for (int i = 0; i < 4; i++) xv[i] = x[L.sl.off_q() + 4 * k + i];
+    for (int i = 0; i < 3; i++) xv[4 + i] = x[L.sl.off_p() + 3 * k + i];
+    for (int i = 0; i < 6; i++) d[i] = -g[c + i];
+    const Q4 r = so3_mul(ldq(xv), so3_exp(mk(1.0 * d[0], 1.0 * d[1], 1.0 * d[2])));
+    yv[0] = r.x; yv[1] = r.y; yv[2] = r.z; yv[3] = r.w;
+    for (int a = 0; a < 3; a++) yv[4 + a] = xv[4 + a] + 1.0 * d[3 + a];
+    if (a0) acc(xv, yv, 4);
+    if (a1) acc(xv + 4, yv + 4, 3);
+  }
+  for (int j = threadIdx.x; j < L.nb; j += blockDim.x) {
+    const int a0 = L.col_bias_gyro >= 0 ? active[L.col_bias_gyro + 3 * j] : 0;
+    const int a1 = L.col_bias_accel >= 0 ? active[L.col_bias_accel + 3 * j] : 0;
+    double xv[6], yv[6];
+    for (int i = 0; i < 6; i++) xv[i] = yv[i] = x[L.sl.off_bias() + 6 * j + i];
+    if (L.col_bias_gyro >= 0)
+      for (int a = 0; a < 3; a++) yv[a] = xv[a] + 1.0 * (-g[L.col_bias_gyro + 3 * j + a]);
+    if (L.col_bias_accel >= 0)
+      for (int a = 0; a < 3; a++) yv[3 + a] = xv[3 + a] + 1.0 * (-g[L.col_bias_accel + 3 * j + a]);
+    if (a0) acc(xv, yv, 3);
+    if (a1) acc(xv + 3, yv + 3, 3);
+  }
+  if (threadIdx.x < 3 && L.col_toff[threadIdx.x] >= 0 && active[L.col_toff[threadIdx.x]]) {
+    const int sidx = threadIdx.x;
+    const double xv = x[L.sl.off_toff() + sidx];
+    double v = xv + 1.0 * (-g[L.col_toff[sidx]]);
+    if (L.has_bounds[sidx]) {
+      v = fmax(v, L.lo[sidx]);
+      v = fmin(v, L.hi[sidx]);
+    }
+    acc(&xv, &v, 1);
+  }
+  if (L.lm_col)
+    for (int l = threadIdx.x; l < L.L; l += blockDim.x) {
+      const int col = L.lm_col[l];
+      if (col >= 0 && active[col]) {
+        const double xv = x[L.sl.off_invd() + l];
+        const double v = xv + 1.0 * (-g[col]);
+        acc(&xv, &v, 1);
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xs += __shfl_xor_sync(0xffffffffu, xs, o);
+    dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
   }
   __syncthreads();
+  const int nw = (int)(blockDim.x >> 5);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = xs;
+    sh[nw + (threadIdx.x >> 5)] = dm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = sh[nw];
+    for (int w = 0; w < nw; w++) {
+      a += sh[w];
+      c = fmax(c, sh[nw + w]);
+    }
+    B.st->x_norm = sqrt(a);
+    B.st->gmax = c;
+  }
+  __syncthreads();
+  (void)ds;
 }
 
 // IterationZero of a bounded problem: x <- Plus(x, 0) projects the start point onto the feasible set.
@@ -651,6 +769,8 @@ __global__ void lm_init_kernel(LmBufs B, LayoutDev L, LmConst C, int max_iterati
   __syncthreads();
   if (threadIdx.x == 0) {
     LmState* s = B.st;
+  if (threadIdx.x == 0) s->nts = 0;
+  lm_ts(s, 1);
     s->radius = C.initial_radius;
     s->decrease_factor = 2.0;
     s->x_cost = B.cost_x[0];
@@ -719,10 +839,27 @@ __device__ __forceinline__ int lm_factor_solve(double* A, int ld, int D, const L
   return 1;
 }
 
-__global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmConst C, int a_in_smem, int is_constrained) {
+__device__ __forceinline__ void lm_accept_phase(const LmBufs& B, const LayoutDev& L, const LmConst& C, double* sh);
+__device__ __forceinline__ void lm_post_phase(const LmBufs& B, const LayoutDev& L, double* sh);
+
+// with_accept: the launch first closes the PREVIOUS iteration (lm_accept_phase + lm_post_phase on the pass that ran in
+// between) — the unconstrained solve with speculative Jacobians then is two launches per iteration (this kernel, the
+// pass) instead of four.
+__global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmConst C, int a_in_smem, int is_constrained,
+                                                      int with_accept) {
   pdl_wait();
-  pdl_trigger();
+  if (with_accept != 2) pdl_trigger();
   extern __shared__ double sh[];
+  lm_ts(B.st, 10);
+  if (with_accept) {
+    lm_accept_phase(B, L, C, sh);
+    __syncthreads();
+    lm_ts(B.st, 11);
+    lm_post_phase(B, L, sh);
+    __syncthreads();
+    lm_ts(B.st, 12);
+  }
+  if (with_accept == 2) pdl_trigger();
   LmState* s = B.st;
   const int D = L.D;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -842,6 +979,7 @@ __global__ void __launch_bounds__(512) lm_step_kernel(LmBufs B, LayoutDev L, LmC
     s->ls_active = is_constrained;
   }
   LM_STAMP(8);
+  lm_ts(s, 19);
 }
 
 // Projected Armijo line search of bounded problems (TrustRegionMinimizer::DoLineSearch).  Called by the host loop
@@ -895,48 +1033,61 @@ __global__ void lm_linesearch_kernel(LmBufs B, LayoutDev L, int max_ls_iteration
   }
 }
 
-// Second half of the iteration, after the residual-only pass at the candidate.
-__global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ double sh[];
+// Second half of the iteration, after the pass at the candidate (all threads of one CTA; sh: >= 1024 doubles).
+__device__ __forceinline__ void lm_accept_phase(const LmBufs& B, const LayoutDev& L, const LmConst& C, double* sh) {
   LmState* s = B.st;
   __shared__ int go;
+  // thread 0: everything the decision reads, requested together with the go test (not one round trip later)
+  double p_cand = 0, p_xcost = 0, p_mcc = 0, p_radius = 0, p_dec = 0, p_xnorm = 0;
   if (threadIdx.x == 0) {
+    const int done = s->done, valid = s->step_valid;
+    p_cand = B.cost_c[0]; p_xcost = s->x_cost; p_mcc = s->model_cost_change; p_radius = s->radius;
+    p_dec = s->decrease_factor; p_xnorm = s->x_norm;
     s->skip_jac = 1;
-    go = (!s->done && s->step_valid) ? 1 : 0;
+    go = (!done && valid) ? 1 : 0;
   }
   __syncthreads();
   if (!go) return;
+  // the candidate's system is on its way into registers while the decision is made (one memory round trip less on the
+  // accept path; D <= 96: everything, else the first part)
+  constexpr int kPre = 5;
+  double2 pre[kPre];
+  const int n2_pre = B.Hc ? (L.D * L.D) >> 1 : 0;
+#pragma unroll
+  for (int q = 0; q < kPre; q++) {
+    const int i = threadIdx.x + q * blockDim.x;
+    pre[q] = i < n2_pre ? reinterpret_cast<const double2*>(B.Hc)[i] : make_double2(0.0, 0.0);
+  }
   double ds;
   ambient_diff(B.x, B.cand, B.active, L, sh, nullptr, &ds, nullptr);
   __shared__ int accept;
   if (threadIdx.x == 0) {
     accept = 0;
-    double cand_cost = B.cost_c[0];
+    double cand_cost = p_cand;
     if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
     s->cand_cost = cand_cost;
-    s->step_norm = sqrt(ds);
-    const double cost_change = s->x_cost - cand_cost;
-    if (s->step_norm <= C.parameter_tolerance * (s->x_norm + C.parameter_tolerance)) {
+    const double step_norm = sqrt(ds);
+    s->step_norm = step_norm;
+    const double cost_change = p_xcost - cand_cost;
+    if (step_norm <= C.parameter_tolerance * (p_xnorm + C.parameter_tolerance)) {
       s->done = 1; s->termination = 0; s->reason = 2;
-    } else if (fabs(cost_change) <= C.function_tolerance * s->x_cost) {
+    } else if (fabs(cost_change) <= C.function_tolerance * p_xcost) {
       s->done = 1; s->termination = 0; s->reason = 3;
     } else {
-      const double rd = cost_change / s->model_cost_change;
+      const double rd = cost_change / p_mcc;
       if (rd > C.min_relative_decrease) {
         accept = 1;
         s->n_succ++;
-        s->radius = s->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rd - 1.0, 3));
-        s->radius = fmin(C.max_radius, s->radius);
+        const double t = 2.0 * rd - 1.0;  // (pow(t, 3) as Ceres writes it; t * t * t is what pow returns for an integer 3)
+        s->radius = fmin(C.max_radius, p_radius / fmax(1.0 / 3.0, 1.0 - pow(t, 3)));
         s->decrease_factor = 2.0;
         s->reuse_diagonal = 0;
         s->skip_jac = 0;
         s->n_jac++;
       } else {
         s->n_unsucc++;
-        s->radius = s->radius / s->decrease_factor;
-        s->decrease_factor *= 2.0;
+        s->radius = p_radius / p_dec;
+        s->decrease_factor = p_dec * 2.0;
         s->reuse_diagonal = 1;
       }
     }
@@ -950,25 +1101,45 @@ __global__ void lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
       const int n2 = (D * D) >> 1;  // both buffers are 256-byte aligned: copy 16 bytes per thread and step
       const double2* src = reinterpret_cast<const double2*>(B.Hc);
       double2* dst = reinterpret_cast<double2*>(B.H);
+#pragma unroll
+      for (int q = 0; q < kPre; q++) {
+        const int i = threadIdx.x + q * blockDim.x;
+        if (i < n2) dst[i] = pre[q];
+      }
 #pragma unroll 4
-      for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
+      for (int i = threadIdx.x + kPre * blockDim.x; i < n2; i += blockDim.x) dst[i] = src[i];
       if ((D & 1) && threadIdx.x == 0) B.H[D * D - 1] = B.Hc[D * D - 1];
       for (int i = threadIdx.x; i < D; i += blockDim.x) B.b[i] = B.bc[i];
       if (threadIdx.x < 2) B.cost_x[threadIdx.x] = B.cost_c[threadIdx.x];
     }
   }
 }
-
-// After the (conditional) Jacobian pass at the accepted point.
-__global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
+__global__ void __launch_bounds__(1024) lm_accept_kernel(LmBufs B, LayoutDev L, LmConst C) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ double sh[];
+  lm_ts(B.st, 20);
+  lm_accept_phase(B, L, C, sh);
+  __syncthreads();
+  lm_ts(B.st, 21);
+}
+
+// After the (conditional) Jacobian pass at the accepted point.
+__device__ __forceinline__ void lm_post_phase(const LmBufs& B, const LayoutDev& L, double* sh) {
   LmState* s = B.st;
   if (s->done || s->skip_jac) return;
   if (threadIdx.x == 0) s->x_cost = B.cost_x[0];
   __syncthreads();
   gradient_norms(B, L, sh);
+}
+__global__ void lm_post_kernel(LmBufs B, LayoutDev L) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ double sh[];
+  lm_ts(B.st, 30);
+  lm_post_phase(B, L, sh);
+  __syncthreads();
+  lm_ts(B.st, 31);
 }
 
 }  // namespace clic
