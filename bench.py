@@ -273,6 +273,10 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+# the device code of pass_kernel (the host side, the LM solver and the association kernels do not change its counts)
+PASS_KERNEL_SOURCES = ("clic_math.cuh", "factor_eval.cuh", "kernels.cuh", "pass_fused.cuh")
+
+
 def fp64_counts():
     """FP64 instruction counts of one pass of the fused kernel on C5 (ncu capture, profiles/r02_fp64_counts.json), valid
     only for the csrc tree they were captured on."""
@@ -285,7 +289,7 @@ def fp64_counts():
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "clic_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh")):
+        if name in PASS_KERNEL_SOURCES:
             with open(os.path.join(csrc, name), "rb") as f:
                 h.update(f.read())
     if d.get("csrc_sha256") != h.hexdigest():

@@ -19,6 +19,9 @@ METRICS = ("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_threa
            "smsp__cycles_elapsed.sum,sm__cycles_elapsed.avg.per_second,launch__registers_per_thread")
 
 
+PASS_KERNEL_SOURCES = ("clic_math.cuh", "factor_eval.cuh", "kernels.cuh", "pass_fused.cuh")  # as in bench.py
+
+
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
     hdr = next(i for i, r in enumerate(rows) if "Metric Name" in r)
@@ -36,7 +39,7 @@ def main():
     hsh = hashlib.sha256()
     csrc = os.path.join(ROOT, "clic_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh")):
+        if name in PASS_KERNEL_SOURCES:
             hsh.update(open(os.path.join(csrc, name), "rb").read())
     out = {
         "csrc_sha256": hsh.hexdigest(),

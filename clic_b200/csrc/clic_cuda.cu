@@ -276,6 +276,7 @@ struct ImageBatch {
   DevBuf raw[4];
   DevBuf id_i, id_j, pack_t;  // pose packs (st.n_packs > 0)
   DevBuf lm_start, lm_obs;      // landmark -> its observations' stored positions (CSR), for rho_side_kernel
+  std::vector<int32_t> h_lm_start, h_lm_obs;  // (host copies: the source of the asynchronous upload lives with the batch)
   std::vector<int32_t> gather;  // stored position -> add order, -1 = padding (buckets start on slab boundaries)
   int64_t n_input = 0;          // factors the caller added (st.n counts the padding too)
   std::vector<char> lm_used;  // landmarks referenced by a kept factor (marg batches: their inverse depths are dropped blocks)
@@ -2726,7 +2727,10 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     s_lm[k] = landmark[i];
   }
   {  // CSR landmark -> stored positions (ascending), for the per-landmark gather of the inverse-depth columns
-    std::vector<int32_t> start((size_t)E->n_lm + 1, 0), obs((size_t)n_in);
+    std::vector<int32_t>& start = B->h_lm_start;
+    std::vector<int32_t>& obs = B->h_lm_obs;
+    start.assign((size_t)E->n_lm + 1, 0);
+    obs.assign((size_t)n_in, 0);
     for (int64_t k = 0; k < n; k++) if (B->gather[k] >= 0) start[s_lm[k] + 1]++;
     for (int l = 0; l < E->n_lm; l++) start[l + 1] += start[l];
     std::vector<int32_t> fill(start.begin(), start.end() - 1);
@@ -2734,7 +2738,6 @@ CLIC_API int clic_add_image(clic_estimator* E, int64_t n, const double* t_i, con
     int rc2;
     if ((rc2 = to_device(E, B->lm_start, start.data(), start.size())) || (rc2 = to_device(E, B->lm_obs, obs.data(), obs.size())))
       return rc2;
-    CU(cudaStreamSynchronize(cs));  // the vectors are locals
   }
   trace.lap("sort+stage");
   // Distinct (timestamp, role) pairs -> pose packs (tiny open-addressing table; abandoned beyond kMaxPosePacks,
