@@ -232,6 +232,9 @@ struct StreamExec {
   cudaEvent_t ready = nullptr;
   bool ready_waited = true;
   long seq = 0;  // upload order (mark_ready)
+  // slabs at which the knot interval of a time-sorted batch changes (host estimate at add time; a load-balance hint for
+  // the fused pass: a CTA that contains such a slab has more records to finish, see build_fused)
+  std::vector<int32_t> key_change_slab;
   StreamExec() = default;
   StreamExec(const StreamExec&) = delete;
   StreamExec& operator=(const StreamExec&) = delete;
@@ -571,7 +574,7 @@ int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] 
 // a warp opens a new interval pair, i.e. one more record for the CTA's dense finish; later slabs repeat pairs).
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds], ramp[kFusedKinds], ramp_to[kFusedKinds]; };
 const FusedModel& fused_model() {
-  static FusedModel m = {{3.6, 3.05, 3.34, 10.9, 7.3, 12.0}, {14.0, 12.3, 14.8, 27.5, 31.2, 50.0},
+  static FusedModel m = {{3.6, 3.04, 3.32, 11.15, 7.3, 12.0}, {14.0, 12.3, 14.8, 27.5, 31.2, 50.0},
                          {0.0, 0.0, 0.0, 0.0, 11.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 2.5, 0.0}};
   static bool init = false;
   if (!init) {
@@ -648,7 +651,7 @@ int build_fused(clic_estimator* E) {
   for (auto& b : E->loam) if (!b->marg) push(b->st.geo_kind, b->ex);
   if (F.ib) push(3, F.ib->ex, E->L.col_t_offset[CLIC_SENSOR_IMU] >= 0 ? 1.25 : 1.0);
   if (F.gb) push(F.gb->st.n_packs > 0 ? 4 : 5, F.gb->ex);
-  if (js.empty() || (int)js.size() > E->n_sm) return CLIC_OK;
+  if (js.empty() || (int)js.size() > E->n_sm || E->n_sm > kMaxFusedCtas) return CLIC_OK;
   if (fused_mode() < 0 && !E->use_comm) {
     // Small windows (the reference's production size: a few hundred factors, ~30 slabs) are latency-bound and run
     // faster as per-stream launches (measured, bench_micro/small_window.py: C1 85 vs 100 us per LM iteration); from
@@ -731,6 +734,35 @@ int build_fused(clic_estimator* E) {
     P.rb = j.ex->rb();
     P.rb.overflow_flag = reinterpret_cast<int*>(F.d_bar.as<unsigned>() + 1024);  // read back by phase A of the same pass
     F.part_ctas[j.kind] = j.n;
+    {
+      // Slab range of every CTA of the partition.  Even split, except that a CTA which contains an interval boundary of a
+      // time-sorted LiDAR / IMU stream gets fewer slabs: it has a record flushed in mid-run plus a second live group to
+      // finish (measured + 4 us LiDAR, + 7 us IMU: these CTAs were the stragglers of their partitions) — worth `pen`
+      // slabs.  Three fixed-point rounds (the boundaries' CTAs depend on the split).  Deterministic: host data only.
+      const int64_t S = j.ex->slabs_per_warp;
+      const double pen = j.kind <= 2 ? 10.0 : (j.kind == 3 ? 5.0 : 0.0);
+      const std::vector<int32_t>& kb = j.ex->key_change_slab;
+      std::vector<int64_t> end((size_t)j.n);
+      for (int c = 0; c < j.n; c++) end[c] = S * (c + 1) / j.n;
+      if (pen > 0.0 && !kb.empty() && j.n > 1 && S > 4 * (int64_t)j.n) {
+        for (int round = 0; round < 3; round++) {
+          std::vector<int> nb((size_t)j.n, 0);
+          int total = 0;
+          for (int32_t b : kb) {
+            const int c = (int)(std::upper_bound(end.begin(), end.end(), (int64_t)b) - end.begin());
+            if (c < j.n) { nb[c]++; total++; }
+          }
+          const double T = ((double)S + pen * total) / j.n;
+          double acc = 0.0;
+          for (int c = 0; c < j.n; c++) {
+            acc += std::max(1.0, T - pen * nb[c]);
+            end[c] = std::min<int64_t>(S, (int64_t)(acc + 0.5));
+          }
+          end[j.n - 1] = S;
+        }
+      }
+      for (int c = 0; c < j.n; c++) fa.cta_slab_end[cta0 + c] = (int)end[c];
+    }
     cta0 += j.n;
     fa.ovf_blocks[jn] = j.ex->overflow.as<double>();
     fa.ovf_doubles[jn] = j.ex->n_keys * j.ex->rd;
@@ -1381,6 +1413,23 @@ int to_device(clic_estimator* E, DevBuf& buf, const T* src, size_t count) {
 // t_s: the caller's timestamps; shift_ns: what the factor adds before indexing ((int64) time offset for the IMU).
 constexpr int64_t kKeyAlignMax = 1 << 15;
 bool key_align_enabled() { static const bool v = getenv("CLIC_NO_KEY_ALIGN") == nullptr; return v; }
+// Slab indices (factors_per_slab factors each) at which a time-SORTED stream enters the next knot interval: binary search
+// per interval boundary on the caller's timestamps.  Only a hint (an unsorted stream gives meaningless, harmless values).
+void key_change_slabs(const clic_estimator* E, const double* t_s, int64_t n, int64_t toff_ns, int factors_per_slab,
+                      std::vector<int32_t>& out) {
+  out.clear();
+  if (!t_s || n <= 0) return;
+  for (int k = 1; k <= E->K - 4; k++) {
+    const int64_t tb = E->t0_ns + (int64_t)k * E->dt_ns;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if ((int64_t)(t_s[mid] * 1e9) + toff_ns < tb) lo = mid + 1; else hi = mid;
+    }
+    if (lo > 0 && lo < n) out.push_back((int32_t)(lo / factors_per_slab));
+  }
+}
+
 std::vector<int32_t> build_key_gather(const clic_estimator* E, const double* t_s, int64_t n, int64_t t_lo, int64_t t_hi,
                                       int64_t pad, int64_t shift_ns) {
   std::vector<int32_t> g;
@@ -2129,6 +2178,7 @@ CLIC_API int clic_add_loam(clic_estimator* E, int64_t n, const double* t_point, 
     return rc;
   B->n_input = n;
   B->gather = build_key_gather(E, t_point, n, t_min, t_max, 0, 0);
+  if (B->gather.empty()) key_change_slabs(E, t_point, n, 0, 32, B->ex.key_change_slab);
   const int32_t* d_gather = nullptr;
   if (!B->gather.empty()) {
     if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;
@@ -2220,6 +2270,7 @@ int add_loam_records(clic_estimator* E, int geo_kind, int64_t n, const double* t
   const int32_t* d_gather = nullptr;
   if (!device_inputs) {
     B->gather = build_key_gather(E, t_point, n, t_min, t_max, 0, 0);
+    if (B->gather.empty()) key_change_slabs(E, t_point, n, 0, 32, B->ex.key_change_slab);
     if (!B->gather.empty()) {
       if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;
       d_gather = B->d_gather.as<int32_t>();
@@ -2315,6 +2366,8 @@ CLIC_API int clic_add_imu(clic_estimator* E, int64_t n, const double* timestamp,
     return rc;
   B->n_input = n;
   B->gather = build_key_gather(E, timestamp, n, t_min, t_max, pad, (int64_t)E->h_state[E->sl.off_toff() + S]);
+  if (B->gather.empty())
+    key_change_slabs(E, timestamp, n, (int64_t)E->h_state[E->sl.off_toff() + S], 32, B->ex.key_change_slab);
   const int32_t* d_gather = nullptr;
   if (!B->gather.empty()) {
     if ((rc = to_device(E, B->d_gather, B->gather.data(), B->gather.size()))) return rc;

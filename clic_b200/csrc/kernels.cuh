@@ -282,7 +282,21 @@ struct DenseOut {
   const int* knot_col;     // [K] column of the knot's dtheta, -1 if constant (shared-memory copy)
   int* key_cols;           // shared memory scratch: [1 + 64 * 3] ints (see build_key_cols)
   unsigned long long* stamp;  // null, or this CTA's phase stamps: [6] = warp 0 starts its slabs, [7] = warp 0 is through them
+  int slab_lo, slab_hi;       // this CTA's slabs of its stream (the fused pass balances them per CTA, build_fused)
 };
+// The slabs of one warp: an even split of the CTA's range when the caller fixed one, else of the whole stream over the
+// warps of the grid.
+__device__ __forceinline__ void warp_slab_range(const DenseOut* dn, int total_slabs, int warp_global, int warp, int warps_per_cta,
+                                                int64_t n_warps_grid, int64_t* slab0, int* n_slabs) {
+  if (dn) {
+    const int64_t len = dn->slab_hi - dn->slab_lo;
+    *slab0 = dn->slab_lo + len * warp / warps_per_cta;
+    *n_slabs = (int)(dn->slab_lo + len * (warp + 1) / warps_per_cta - *slab0);
+  } else {
+    *slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
+    *n_slabs = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - *slab0);
+  }
+}
 __device__ __forceinline__ void dense_stamp(const DenseOut* dn, int i) {
   if (dn && dn->stamp && threadIdx.x == 0) {
     unsigned long long t;
@@ -602,8 +616,9 @@ __device__ __forceinline__ void loam_body(const LoamStream& st, const PassParams
   double cost = 0.0, fcost = 0.0;
   // balanced contiguous split of the slabs over all warps of the grid (sizes differ by at most one)
   const int64_t n_warps_grid = (int64_t)n_ctas * WARPS;
-  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
-  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
+  int64_t slab0;
+  int slabs_per_warp;
+  warp_slab_range(DENSE ? dn : nullptr, total_slabs, warp_global, warp, WARPS, n_warps_grid, &slab0, &slabs_per_warp);
   // software pipeline registers (next slab)
   int64_t n_t = kDropped;
   double n_p0 = 0, n_p1 = 0, n_p2 = 0, n_g0 = 0, n_g1 = 0, n_g2 = 0, n_g3 = 0, n_g4 = 0, n_g5 = 0;
@@ -1099,8 +1114,9 @@ __device__ __forceinline__ void imu_body(const ImuStream& st, const PassParams& 
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
   const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
-  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
-  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
+  int64_t slab0;
+  int slabs_per_warp;
+  warp_slab_range(DENSE ? dn : nullptr, total_slabs, warp_global, warp, kWarpsPerCta, n_warps_grid, &slab0, &slabs_per_warp);
   if (DENSE) dense_stamp(dn, 6);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * 32 >= st.n) break;
@@ -1248,8 +1264,9 @@ __device__ __forceinline__ void image_body(const ImageStream& st, const PassPara
   int acc_key = -1, slot = 0;
   double cost = 0.0, fcost = 0.0;
   const int64_t n_warps_grid = (int64_t)n_ctas * kWarpsPerCta;
-  const int64_t slab0 = (int64_t)total_slabs * warp_global / n_warps_grid;
-  const int slabs_per_warp = (int)((int64_t)total_slabs * (warp_global + 1) / n_warps_grid - slab0);
+  int64_t slab0;
+  int slabs_per_warp;
+  warp_slab_range(DENSE ? dn : nullptr, total_slabs, warp_global, warp, kWarpsPerCta, n_warps_grid, &slab0, &slabs_per_warp);
   if (DENSE) dense_stamp(dn, 6);
   for (int sl = 0; sl < slabs_per_warp; sl++) {
     if ((slab0 + sl) * kImageFactorsPerSlab >= st.n) break;

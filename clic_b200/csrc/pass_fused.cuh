@@ -39,6 +39,7 @@ struct FusedPart {
   RecordBuf rb;                   // slots of records flushed in mid-run (read back by the same CTA) + atomics fallback
 };
 constexpr int kMaxFusedJobs = 5;
+constexpr int kMaxFusedCtas = 160;  // one CTA per SM (148 on B200)
 constexpr int kKeyColsInts = 1 + 3 * 64;
 constexpr int kMaxFusedBias = 4;
 __host__ __device__ inline size_t fused_persist_bytes(int K, int nb) {
@@ -76,6 +77,8 @@ struct FusedArgs {
   // per-CTA phase stamps (globaltimer ns) when not null: [cta][8] = start, end of F, after the barrier, tile loaded,
   // end of A, end
   unsigned long long* stamps;
+  // last slab (exclusive) of every factor CTA within its stream; a partition's first CTA starts at slab 0 (build_fused)
+  int cta_slab_end[kMaxFusedCtas];
 };
 
 // per-pass arguments
@@ -257,6 +260,13 @@ pass_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ PassPa
     dn.knot_col = p_knot_col;
     dn.key_cols = reinterpret_cast<int*>(Hs + ((n_tot + 1) & ~1));
     dn.stamp = stamp;
+    {
+      bool first = false;
+#pragma unroll
+      for (int k = 0; k < kFusedKinds; k++) first = first || (fa.part[k].n_ctas && cta == fa.part[k].cta0);
+      dn.slab_lo = first ? 0 : fa.cta_slab_end[cta - 1];
+      dn.slab_hi = fa.cta_slab_end[cta];
+    }
     if (fa.part[1].n_ctas && cta >= fa.part[1].cta0 && cta < fa.part[1].cta0 + fa.part[1].n_ctas) {
       dn.sd = p_sd;
       loam_body<JAC, kWarpsPerCta, 1, true>(fa.loam[1], pp, fa.part[1].total_slabs, fa.part[1].rb, W, rest,
