@@ -575,7 +575,7 @@ int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] 
 struct FusedModel { double w[kFusedKinds], f[kFusedKinds], ramp[kFusedKinds], ramp_to[kFusedKinds]; };
 const FusedModel& fused_model() {
   static FusedModel m = {{3.6, 3.04, 3.32, 11.15, 7.3, 12.0}, {14.0, 12.3, 14.8, 27.5, 31.2, 50.0},
-                         {0.0, 0.0, 0.0, 0.0, 11.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 2.5, 0.0}};
+                         {0.0, 0.0, 0.0, 0.0, 15.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 1.8, 0.0}};
   static bool init = false;
   if (!init) {
     init = true;
