@@ -2,8 +2,8 @@
 // exchange step — in ONE persistent launch.
 //
 //   phase F  every factor stream of the pass runs on its own partition of the grid (one CTA per SM; the partition
-//            sizes come from a static cost model on the host, so the grouping of the sums — and with it every bit
-//            of H, b — is a function of the problem alone).  The stream bodies are the ones of loam_kernel /
+//            sizes and every CTA's slab range come from a static cost model on the host, so the grouping of the sums —
+//            and with it every bit of H, b — is a function of the problem alone).  The stream bodies are the ones of loam_kernel /
 //            imu_kernel / image_kernel (kernels.cuh).
 //   barrier  (the only grid-wide one)
 //            ... at the end of which every CTA has added what it accumulated into ITS OWN copy of the packed system
@@ -15,9 +15,10 @@
 //            ~35 us; summing the record entries per target entry directly cost as much in scattered 8-byte sector
 //            traffic.)
 //   phase X  (several ranks, peer memory mapped) the chunk is pushed straight into slot `rank` of every peer's exchange
-//            area over NVLink, a per-(rank, CTA) flag is released, CTA c waits for the flags of CTA c of every peer —
-//            all ranks partition the system identically, so no grid-wide synchronisation is involved — and sums the
-//            slots in rank order: every rank ends up with bit-identical H, b, cost.
+//            area over NVLink, every double as two 8-byte words (32 data bits | 32-bit sequence number): the data is its
+//            own arrival flag.  CTA c polls the words of CTA c of every peer — all ranks partition the system
+//            identically, so no grid-wide synchronisation is involved — and sums the slots in rank order: every rank
+//            ends up with bit-identical H, b, cost.  The wait is bounded in wall-clock time (zeroed result + error).
 //
 // Replaces  loam/imu/image kernels -> reduce_all_kernel -> assemble_kernel -> p2p_allreduce_kernel  (round 1: ~60 us of
 // serial tail that did not shrink with the number of GPUs).  Grid barriers need every CTA resident: the grid never
