@@ -1,3 +1,5 @@
+"""One e2e step (create, add from pinned host buffers, Evaluate, close) on C5 under CLIC_TRACE=1: host time of every
+traced ABI call.  CLIC_TRACE=1 python bench_micro/e2e_trace.py"""
 import os, sys
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch

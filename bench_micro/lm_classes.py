@@ -1,3 +1,5 @@
+"""CUDA-event spans per kernel class (pass / LM kernels) of Solve(8) on C5, with launch counts.
+python bench_micro/lm_classes.py"""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 import numpy as np

@@ -1,3 +1,5 @@
+"""Entry / exit of every LM kernel of one Solve(8) on C5 on the device clock.  Needs the developer build
+(-DCLIC_LM_TIMELINE) loaded through CLIC_CUDA_LIB; prints the timeline on stderr."""
 import os, sys
 sys.path.insert(0, "/root/repo")
 import bench as B
