@@ -3,6 +3,7 @@
 // UpdateLIOPrior's marginalization estimator fed with PrepareMarginalizationInfo(RType_Prior, new
 // MarginalizationFactor(info), NULL, blocks, drop_set) (:346-376) + AddGravityFactor + SaveMarginalizationInfo, and the
 // next solve on the new prior.  Runs on the oracle (CPU) and on libclic_cuda.so; prints "SHIM2_OK <costs...>".
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -114,6 +115,22 @@ int main() {
     pre.jacobian[3 * 15 + 12] = -0.3;   // dq/dbg
     pre.jacobian[6 * 15 + 9] = -0.3;    // dv/dba
     pre.covariance[0 * 15 + 1] = pre.covariance[1 * 15 + 0] = 0.5;
+    {  // IntegrationBase::to_abi: sqrt_info^T sqrt_info = covariance^-1, sqrt_info upper triangular
+      const clic_preintegration abi = pre.to_abi();
+      double worst = 0.0;
+      for (int r = 0; r < 15; r++)
+        for (int c = 0; c < 15; c++) {
+          double m = 0.0;  // (S^T S P)(r, c)
+          for (int k = 0; k < 15; k++) {
+            double sts = 0.0;
+            for (int q = 0; q < 15; q++) sts += abi.sqrt_info[q * 15 + r] * abi.sqrt_info[q * 15 + k];
+            m += sts * pre.covariance[k * 15 + c];
+          }
+          worst = std::max(worst, std::fabs(m - (r == c ? 1.0 : 0.0)));
+          if (r > c && abi.sqrt_info[r * 15 + c] != 0.0) return fail("sqrt_info is not upper triangular");
+        }
+      if (worst > 1e-12) return fail("IntegrationBase::to_abi: sqrt_info^T sqrt_info covariance != I");
+    }
     estimator->AddPreIntegrationAnalytic(0.3, 0.6, &pre, bg0, bg1, ba0, ba1);
     {  // one factor's residual / Jacobian (the reference's test_analytic_factor.cpp surface): an epipolar constraint
       clic_factor_desc fd{};
