@@ -19,6 +19,7 @@
 #include "../../include/clic_cuda.h"
 #include "kernels.cuh"
 #include "pass_fused.cuh"
+#include "partition_model.hpp"
 #include "solver.cuh"
 #include "assoc.cuh"
 
@@ -563,19 +564,10 @@ int check_p2p(clic_estimator* E) {
 // cost — per-CTA dense system, grid barrier — and always on several ranks, where it carries the exchange).  Read at
 // every layout so that a test can flip it between two estimators.
 int fused_mode() { const char* e = getenv("CLIC_FUSED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }
-// Static cost model of the grid partition: a stream on n CTAs takes  f + w * max(slabs / (8 n), lat * ceil(slabs / (8 n)))
-// microseconds (t_of in build_fused) — w per
-// 32-factor slab (16 for the visual stream) of one warp with two warps per SM sub-partition, f the stream's fixed part
-// (window staging, pose packs, first-slab latency, the dense finish) — fitted to %globaltimer stamps of the C5 window
-// and of its 1/8 shard on B200 (bench_micro/fused_probe.py; profiles/).  Only the ratios matter, and a wrong model costs
-// balance, never correctness: the partition is a pure function of the problem, so results stay bit-reproducible.
-// CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual packed,visual chain" override (tuning runs).
-// ramp / ramp_to: the first ramp_to slabs of a warp cost `ramp` more each (the visual stream: nearly every early slab of
-// a warp opens a new interval pair, i.e. one more record for the CTA's dense finish; later slabs repeat pairs).
-struct FusedModel { double w[kFusedKinds], f[kFusedKinds], ramp[kFusedKinds], ramp_to[kFusedKinds]; };
-const FusedModel& fused_model() {
-  static FusedModel m = {{3.6, 3.04, 3.32, 11.15, 7.3, 12.0}, {14.0, 12.3, 14.8, 27.5, 31.2, 50.0},
-                         {0.0, 0.0, 0.0, 0.0, 15.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 1.8, 0.0}};
+// Cost model of the grid partition: partition_model.hpp.  CLIC_FUSED_W / CLIC_FUSED_F = "mixed,planes,lines,imu,visual
+// packed,visual chain" and CLIC_FUSED_LAT override its constants (tuning runs).
+const partition::Model& fused_model() {
+  static partition::Model m = partition::default_model();
   static bool init = false;
   if (!init) {
     init = true;
@@ -586,6 +578,7 @@ const FusedModel& fused_model() {
     if (const char* e = getenv("CLIC_FUSED_F"))
       if (sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == kFusedKinds)
         for (int i = 0; i < kFusedKinds; i++) if (v[i] >= 0) m.f[i] = v[i];
+    if (const char* e = getenv("CLIC_FUSED_LAT")) m.lat = atof(e);
   }
   return m;
 }
@@ -628,24 +621,21 @@ int build_fused(clic_estimator* E) {
   int coop = 0;
   CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, E->device));
   if (!coop) return CLIC_OK;
-  struct Job { int kind; StreamExec* ex; int64_t slabs; int cap, n; double w, f, ramp, ramp_to; };
+  struct Job { int kind; StreamExec* ex; int n; };
   std::vector<Job> js;
-  const FusedModel& M = fused_model();
+  std::vector<partition::Stream> streams;
+  const partition::Model& M = fused_model();
   auto push = [&](int kind, StreamExec& ex, double scale = 1.0) {
-    Job j;
-    j.kind = kind;
-    j.ex = &ex;
-    j.slabs = std::max<int64_t>(1, ex.slabs_per_warp);  // (the field holds the stream's total slab count)
+    partition::Stream s;
+    s.kind = kind;
+    s.slabs = std::max<int64_t>(1, ex.slabs_per_warp);  // (the field holds the stream's total slab count)
     // at most one slab per warp; the visual stream may spread thinner (down to 4 slabs per CTA): its dense finish costs
     // one scatter per record, i.e. per slab when every slab is its own interval pair
     const int64_t min_per_cta = kind >= 4 ? kWarpsPerCta / 2 : kWarpsPerCta;
-    j.cap = (int)std::max<int64_t>(1, std::min<int64_t>(ex.grid, (j.slabs + min_per_cta - 1) / min_per_cta));
-    j.n = 1;
-    j.w = M.w[kind] * scale;
-    j.f = M.f[kind];
-    j.ramp = M.ramp[kind];
-    j.ramp_to = M.ramp_to[kind];
-    js.push_back(j);
+    s.cap = (int)std::max<int64_t>(1, std::min<int64_t>(ex.grid, (s.slabs + min_per_cta - 1) / min_per_cta));
+    s.w_scale = scale;
+    streams.push_back(s);
+    js.push_back(Job{kind, &ex, 1});
   };
   // same order as the descriptors / reduce jobs of ensure_layout: LiDAR batches in add order, IMU, visual
   for (auto& b : E->loam) if (!b->marg) push(b->st.geo_kind, b->ex);
@@ -656,61 +646,11 @@ int build_fused(clic_estimator* E) {
     // Small windows (the reference's production size: a few hundred factors, ~30 slabs) are latency-bound and run
     // faster as per-stream launches (measured, bench_micro/small_window.py: C1 85 vs 100 us per LM iteration); from
     // ~C2's size on the fused pass wins (C3 45.6 vs 54.4 us per pass, C5 204 vs 244 us).  Work = modelled warp-time.
-    double work = 0.0;
-    for (auto& j : js) work += j.w * (double)j.slabs;
-    if (work < 6000.0) return CLIC_OK;
+    if (partition::work(M, streams) < 6000.0) return CLIC_OK;
   }
-  // Modelled finishing time of stream j on n CTAs.  A CTA's 8 warps share one FP64 pipe, so its time is the larger of
-  // the throughput term (slabs per CTA x w / 8) and the latency term (whole rounds x the time one warp needs for a slab
-  // when it has the SM to itself, lat x w): the second only matters for the heavy bodies at 1-2 slabs per warp (the
-  // 8-GPU shard of C5: IMU 1.14 slabs per warp takes 46 us, not the 59 us two full rounds would).
-  static const double lat = [] { const char* e = getenv("CLIC_FUSED_LAT"); return e ? atof(e) : 0.4; }();
-  auto t_of = [&](const Job& j, int n) {
-    const double per_warp = (double)j.slabs / (double)(kWarpsPerCta * n);
-    const double rounds = (double)((j.slabs + (int64_t)kWarpsPerCta * n - 1) / ((int64_t)kWarpsPerCta * n));
-    return j.f + j.w * std::max(per_warp, lat * rounds) + j.ramp * std::min(per_warp, j.ramp_to);
-  };
   {
-    // min-max under the model: smallest T for which every stream fits, n_j(T) = fewest CTAs with t_of <= T
-    auto need = [&](double T, std::vector<int>& n) -> bool {
-      int tot = 0;
-      for (size_t i = 0; i < js.size(); i++) {
-        if (t_of(js[i], js[i].cap) > T) return false;
-        int lo = 1, hi = js[i].cap;
-        while (lo < hi) {  // t_of is non-increasing in n
-          const int mid = (lo + hi) / 2;
-          if (t_of(js[i], mid) <= T) hi = mid; else lo = mid + 1;
-        }
-        n[i] = lo;
-        tot += lo;
-      }
-      return tot <= E->n_sm;
-    };
-    double lo = 0.0, hi = 0.0;
-    for (auto& j : js) hi = std::max(hi, t_of(j, 1));
-    std::vector<int> n(js.size(), 1), best;
-    if (need(hi, n)) best = n;
-    for (int it = 0; it < 48 && !best.empty(); it++) {  // feasibility is monotone in T
-      const double mid = 0.5 * (lo + hi);
-      if (need(mid, n)) { best = n; hi = mid; } else { lo = mid; }
-    }
-    if (!best.empty())
-      for (size_t i = 0; i < js.size(); i++) js[i].n = best[i];
-  }
-  // leftover CTAs (and the whole grid when the model found no fit): to the stream that would finish last
-  int used = 0;
-  for (auto& j : js) used += j.n;
-  while (used < E->n_sm) {
-    int best = -1;
-    double worst = 0.0;
-    for (size_t i = 0; i < js.size(); i++) {
-      if (js[i].n >= js[i].cap) continue;
-      const double t = t_of(js[i], js[i].n);
-      if (best < 0 || t > worst) { best = (int)i; worst = t; }
-    }
-    if (best < 0) break;
-    js[best].n++;
-    used++;
+    const std::vector<int> n = partition::split_grid(M, streams, E->n_sm);
+    for (size_t i = 0; i < js.size(); i++) js[i].n = n[i];
   }
   if ((int)js.size() > kMaxFusedJobs || (int)js.size() != E->n_desc) return CLIC_OK;
   FusedArgs& fa = F.fa;
@@ -734,33 +674,9 @@ int build_fused(clic_estimator* E) {
     P.rb = j.ex->rb();
     P.rb.overflow_flag = reinterpret_cast<int*>(F.d_bar.as<unsigned>() + 1024);  // read back by phase A of the same pass
     F.part_ctas[j.kind] = j.n;
-    {
-      // Slab range of every CTA of the partition.  Even split, except that a CTA which contains an interval boundary of a
-      // time-sorted LiDAR / IMU stream gets fewer slabs: it has a record flushed in mid-run plus a second live group to
-      // finish (measured + 4 us LiDAR, + 7 us IMU: these CTAs were the stragglers of their partitions) — worth `pen`
-      // slabs.  Three fixed-point rounds (the boundaries' CTAs depend on the split).  Deterministic: host data only.
-      const int64_t S = j.ex->slabs_per_warp;
-      const double pen = j.kind <= 2 ? 10.0 : (j.kind == 3 ? 5.0 : 0.0);
-      const std::vector<int32_t>& kb = j.ex->key_change_slab;
-      std::vector<int64_t> end((size_t)j.n);
-      for (int c = 0; c < j.n; c++) end[c] = S * (c + 1) / j.n;
-      if (pen > 0.0 && !kb.empty() && j.n > 1 && S > 4 * (int64_t)j.n) {
-        for (int round = 0; round < 3; round++) {
-          std::vector<int> nb((size_t)j.n, 0);
-          int total = 0;
-          for (int32_t b : kb) {
-            const int c = (int)(std::upper_bound(end.begin(), end.end(), (int64_t)b) - end.begin());
-            if (c < j.n) { nb[c]++; total++; }
-          }
-          const double T = ((double)S + pen * total) / j.n;
-          double acc = 0.0;
-          for (int c = 0; c < j.n; c++) {
-            acc += std::max(1.0, T - pen * nb[c]);
-            end[c] = std::min<int64_t>(S, (int64_t)(acc + 0.5));
-          }
-          end[j.n - 1] = S;
-        }
-      }
+    {  // slab range of every CTA of the partition (partition_model.hpp: boundary-aware)
+      const std::vector<int64_t> end =
+          partition::cta_slab_ends(j.kind, j.ex->slabs_per_warp, j.n, j.ex->key_change_slab);
       for (int c = 0; c < j.n; c++) fa.cta_slab_end[cta0 + c] = (int)end[c];
     }
     cta0 += j.n;

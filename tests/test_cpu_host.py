@@ -139,3 +139,14 @@ def test_oracle_drops_out_of_window_like_reference(oracle):
                                        L["geo_point"][:n], L["S_GtoM"], L["p_GinM"], L["S_LtoI"], L["p_LinI"], 50.0)
     s, u = est.indices(0)
     assert d == 3 and list(s) == [-1, 0, 3, 6, -1, -1]
+
+
+def test_partition_model_of_the_fused_pass(tmp_path):
+    """clic_b200/csrc/partition_model.hpp is plain C++: the grid split among the factor streams and the boundary-aware
+    slab ranges are checked on the CPU (tests/cpp/partition_model_test.cpp)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "partition_model_test.cpp")
+    exe = str(tmp_path / "partition_model_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, src], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "PARTITION_OK" in out.stdout, out.stdout + out.stderr
