@@ -12,7 +12,7 @@ from clic_b200 import synthetic as S
 from golden.make_golden import build
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "c*_small.npz")))
 
 
 def check(lib, path, tol_eval, tol_pose):
@@ -50,3 +50,33 @@ def test_cuda_reproduces_golden(cuda, path):
 
 def test_have_goldens():
     assert len(FILES) >= 4
+
+
+# ---- single analytic factors (clic_evaluate_factor): tests/golden/factors_extra.npz, written by make_golden_factors.py ----
+def check_factors(lib, tol):
+    import factor_cases as FC
+    from clic_b200 import estimator as E
+    from test_oracle_autodiff import reference_test_trajectory
+    g = np.load(os.path.join(HERE, "golden", "factors_extra.npz"), allow_pickle=False)
+    n = 0
+    for seed in (1, 2, 3):
+        w = reference_test_trajectory(seed)
+        est = E.TrajectoryEstimator(w, E.default_options(lib), lib)
+        for c in FC.cases(w, seed):
+            r, J = FC.evaluate(est, c)
+            rg, Jg = g[f"s{seed}/{c['name']}/r"], g[f"s{seed}/{c['name']}/J"]
+            assert r.shape == rg.shape and J.shape == Jg.shape
+            assert np.abs(r - rg).max() <= tol * max(1.0, np.abs(rg).max()), (seed, c["name"])
+            assert np.abs(J - Jg).max() <= 10 * tol * max(1.0, np.abs(Jg).max()), (seed, c["name"])
+            n += 1
+        est.close()
+    assert n == len(g.files) // 2
+
+
+def test_oracle_reproduces_factor_goldens(oracle):
+    check_factors(oracle, 1e-14)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_factor_goldens(cuda):
+    check_factors(cuda, 1e-12)
