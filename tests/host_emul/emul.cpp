@@ -155,3 +155,83 @@ __attribute__((visibility("default"))) int emul_small(int K, const double* kq, c
   return 0;
 }
 }
+
+#include "../../include/clic_cuda.h"
+
+extern "C" {
+// One small analytic factor (any CLIC_FACTOR_* kind) against the window with every knot free: the host-compiled twin of
+// factor_jacobian_kernel (kernels.cuh).  J: row-major nres x n_cols, n_cols = 6 K + the widths of the blocks in x.
+__attribute__((visibility("default"))) int emul_factor(int K, const double* kq, const double* kp, int64_t t0_ns, int64_t dt_ns,
+                                                        const clic_factor_desc* fd, const double* S_CtoI, const double* p_CinI,
+                                                        int n_cols, double* r /*15*/, double* J, int* nres) {
+  static const int kWidths[10][4] = {{1, 0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {1, 0, 0, 0}, {3, 3, 3, 3},
+                                     {3, 1, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {3, 3, 0, 0}, {0, 0, 0, 0}};
+  if (fd->kind < 0 || fd->kind > 9) return 2;
+  HostWindow W(K, kq, kp);
+  SmallFactor f{};
+  f.kind = fd->kind;
+  f.geo_type = fd->geo_type;
+  f.t_a = fd->t_a_ns;
+  f.t_b = fd->t_b_ns;
+  for (int i = 0; i < 24; i++) f.d[i] = fd->d[i];
+  int xcol[4], cols = 6 * K;
+  for (int k = 0; k < 4; k++) {
+    xcol[k] = kWidths[fd->kind][k] > 0 ? cols : -1;
+    cols += kWidths[fd->kind][k];
+  }
+  if (cols != n_cols) return 3;
+  std::vector<int> knot_col(K);
+  for (int k = 0; k < K; k++) knot_col[k] = 6 * k;
+  SmallCols sc;
+  sc.knot_col = knot_col.data();
+  sc.col_toff_imu = -1;
+  sc.lm_col = nullptr;
+  sc.col_bias_gyro = sc.col_bias_accel = -1;
+  PreintData pre{};
+  if (fd->pre) {
+    const clic_preintegration* p = fd->pre;
+    pre.sum_dt = p->sum_dt;
+    pre.gravity_norm = p->gravity_norm;
+    for (int i = 0; i < 3; i++) {
+      pre.delta_p[i] = p->delta_p[i]; pre.delta_v[i] = p->delta_v[i];
+      pre.linearized_ba[i] = p->linearized_ba[i]; pre.linearized_bg[i] = p->linearized_bg[i];
+    }
+    for (int i = 0; i < 4; i++) pre.delta_q[i] = p->delta_q[i];
+    for (int a = 0; a < 3; a++)
+      for (int c = 0; c < 3; c++) {
+        pre.dp_dba[3 * a + c] = p->jacobian[(0 + a) * 15 + 9 + c];
+        pre.dp_dbg[3 * a + c] = p->jacobian[(0 + a) * 15 + 12 + c];
+        pre.dq_dbg[3 * a + c] = p->jacobian[(3 + a) * 15 + 12 + c];
+        pre.dv_dba[3 * a + c] = p->jacobian[(6 + a) * 15 + 9 + c];
+        pre.dv_dbg[3 * a + c] = p->jacobian[(6 + a) * 15 + 12 + c];
+      }
+    for (int i = 0; i < 225; i++) pre.sqrt_info[i] = p->sqrt_info[i];
+  }
+  const Q4 qc = ldq(S_CtoI);
+  const V3 pc = ldv(p_CinI);
+  const double* x = fd->x;
+  std::vector<SmallOut> ob(1);
+  SmallOut& o = ob[0];
+  bool ok = false;
+  switch (f.kind) {
+    case kSmallPose: sc.col_toff_imu = xcol[0]; ok = small_pose_eval(W.view, f, t0_ns, dt_ns, K, x[0], sc, &o); break;
+    case kSmallLocalVelocity: sc.col_toff_imu = xcol[0]; ok = small_local_velocity_eval(W.view, f, t0_ns, dt_ns, K, x[0], sc, &o); break;
+    case kSmallRelativeRotation: ok = small_relative_rotation_eval(W.view, f, t0_ns, dt_ns, K, sc, &o); break;
+    case kSmallImageDepth: ok = small_image_depth_eval(f, x[0], xcol[0], &o); break;
+    case kSmallPreIntegration: ok = fd->pre && small_preintegration_eval(W.view, f, pre, t0_ns, dt_ns, K, x, xcol, sc, &o); break;
+    case kSmallImage3D2D: ok = small_image_3d2d_eval(W.view, f, t0_ns, dt_ns, K, qc, pc, x, xcol, sc, &o); break;
+    case kSmallImageOnePose: ok = small_image_one_pose_eval(W.view, f, t0_ns, dt_ns, K, qc, pc, x, xcol, sc, &o); break;
+    case kSmallEpipolar: ok = small_epipolar_eval(W.view, f, t0_ns, dt_ns, K, qc, pc, sc, &o); break;
+    case kSmallLoamOptMapPose: ok = small_loam_opt_map_pose_eval(W.view, f, t0_ns, dt_ns, K, x, xcol, sc, &o); break;
+    default: ok = small_relative_loam_eval(W.view, f, t0_ns, dt_ns, K, sc, &o); break;
+  }
+  if (!ok) return 1;
+  *nres = o.nres;
+  for (int i = 0; i < o.nres; i++) {
+    r[i] = o.r[i];
+    for (int c = 0; c < n_cols; c++) J[(size_t)i * n_cols + c] = 0.0;
+    for (int c = 0; c < o.ncols; c++) J[(size_t)i * n_cols + o.gcol[c]] = o.J[i][c];
+  }
+  return 0;
+}
+}

@@ -241,3 +241,43 @@ def test_small_factor_rows(oracle, emul, kind, seed):
 @pytest.mark.parametrize("kind", [0, 1])
 def test_small_factor_rows_time_offset_free(oracle, emul, kind):
     _small_case(oracle, emul, kind, 2, unlock_toff=True, fixed=-1)
+
+
+# ---- every small analytic factor: the device evaluators compiled for the host against the oracle ----
+def _factor_names():
+    import factor_cases as FC
+    from test_oracle_autodiff import reference_test_trajectory
+    return [c["name"] for c in FC.cases(reference_test_trajectory(1))]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("name", _factor_names())
+def test_single_factor_evaluators(oracle, emul, name, seed):
+    import factor_cases as FC
+    from clic_b200._abi import FactorDesc
+    from test_oracle_autodiff import reference_test_trajectory
+    w = reference_test_trajectory(seed)
+    est = E.TrajectoryEstimator(w, E.default_options(oracle), oracle)
+    c = next(c for c in FC.cases(w, seed) if c["name"] == name)
+    r_o, J_o = FC.evaluate(est, c)
+    f = FactorDesc()
+    f.kind, f.geo_type, f.t_a_ns, f.t_b_ns = int(c["kind"]), int(c["geo"]), int(c["t_a"]), int(c["t_b"])
+    for i, v in enumerate(np.asarray(c["d"], np.float64).ravel()):
+        f.d[i] = v
+    for i, v in enumerate(np.asarray(c["x"], np.float64).ravel()):
+        f.x[i] = v
+    pre = FC.preintegration_struct(c["pre"]) if c["pre"] is not None else None
+    if pre is not None:
+        f.pre = C.pointer(pre)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    emul.emul_factor.argtypes = [C.c_int, dp, dp, C.c_int64, C.c_int64, C.POINTER(FactorDesc), dp, dp, C.c_int, dp, dp, ip]
+    kq, kp = np.ascontiguousarray(w.knot_q), np.ascontiguousarray(w.knot_p)
+    r = np.zeros(15)
+    J = np.zeros((15, J_o.shape[1]))
+    nres = C.c_int(0)
+    rc = emul.emul_factor(w.n_knots, dptr(kq), dptr(kp), w.t0_ns, w.dt_ns, C.byref(f), dptr(np.ascontiguousarray(w.S_CtoI)),
+                          dptr(np.ascontiguousarray(w.p_CinI)), J_o.shape[1], dptr(r), dptr(J), C.byref(nres))
+    assert rc == 0 and nres.value == len(r_o)
+    m = nres.value
+    assert np.abs(r[:m] - r_o).max() <= 1e-12 * max(1.0, np.abs(r_o).max())
+    assert np.abs(J[:m] - J_o).max() <= 1e-11 * max(1.0, np.abs(J_o).max()), np.abs(J[:m] - J_o).max()
