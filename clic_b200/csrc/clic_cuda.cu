@@ -378,6 +378,7 @@ struct clic_estimator {
   int n_desc = 0;
   DevBuf d_jobs;
   long add_seq = 0;
+  int64_t factors_since_pass = 0;  // uploaded by the adders since the last pass (run_pass: schedule of the first pass)
   bool packs_fit = true;  // the packed visual kernel's shared memory fits this window
   int n_jobs = 0, n_part_ctas = 0, max_slots = 0;
   DevBuf d_bias_descs;
@@ -463,6 +464,7 @@ int plan_stream(clic_estimator* E, StreamExec& ex, int64_t n, int NT, int ctas_p
   const int kWarpsPerCta = warps_per_cta;  // shadows the global default for this stream
   ex.warps_per_cta = warps_per_cta;
   ex.n = n;
+  E->factors_since_pass += n;
   ex.NT = NT;
   ex.rd = rec_doubles(NT, extra);
   ex.n_keys = pair_keys ? (E->K - 3) * (E->K - 3) : E->K - 3;
@@ -1139,6 +1141,7 @@ int set_smem(KernelT k, size_t bytes) {
 // One fused residual (+ Jacobian + normal-equation) pass over the solve problem at `state`.
 // jac = true: H, b, cost2 are produced; false: cost2 only.  ctl: optional device skip word.
 // set = 1 (with jac): the whole system goes to the second buffer set (H_c | b_c | cost_c), cost in its slot 0.
+constexpr int64_t kOverlapFactors = 250000;  // ~16 MB of factor records: 0.3 ms of PCIe to hide a kernel under
 int run_pass(clic_estimator* E, const double* state, bool jac, int which, const int* ctl, int set = 0) {
   int rc = ensure_layout(E);
   if (rc) return rc;
@@ -1146,7 +1149,15 @@ int run_pass(clic_estimator* E, const double* state, bool jac, int which, const 
   double* bp = Hp + E->off_b();
   // slot 0: pass at x, slot 1: pass at the LM candidate (set 0);  set 1 keeps its cost in its own slot 0
   double* cost2 = Hp + E->off_cost() + (set ? 0 : 2 * which);
-  if (E->fused.ok) return run_pass_fused(E, state, jac, Hp, bp, cost2, ctl, set);
+  // The first pass after a large upload (automatic mode, one GPU): the per-stream kernels below are launched in upload
+  // order, run under the copies still in flight and leave only the last batch's kernel exposed, where the fused pass
+  // cannot start before the last byte has arrived (C5 from pinned buffers: 2.03 instead of 2.15 ms per create + add +
+  // evaluate, bench_micro/e2e_modes.py).  Decided from the call sequence, not from event state: the same calls take the
+  // same path, so results stay bit-reproducible.  Ranks of a communicator always take the fused pass (one protocol).
+  static const bool overlap_on = !(getenv("CLIC_OVERLAP_UPLOADS") && getenv("CLIC_OVERLAP_UPLOADS")[0] == '0');
+  const bool overlap_uploads = overlap_on && fused_mode() < 0 && !E->use_comm && E->factors_since_pass >= kOverlapFactors;
+  E->factors_since_pass = 0;
+  if (E->fused.ok && !overlap_uploads) return run_pass_fused(E, state, jac, Hp, bp, cost2, ctl, set);
   PassParams pp = pass_params(E, state, ctl);
   const int D = E->L.D;
   if (jac && E->L.n_free_landmarks > 0)  // side rows of the inverse-depth columns: gathered per landmark

@@ -59,6 +59,11 @@ def compare_eval(cuda, oracle, sw, **kw):
     assert abs(cg - co) <= REL * abs(co)
     assert abs(fg - fo) <= REL * max(abs(fo), 1.0)
     assert np.array_equal(Hg, Hg.T)
+    # a large window takes the per-stream kernels on the first pass after the upload and the fused pass from then on
+    # (run_pass: upload overlap): hold the second pass to the same bar
+    H2, b2, c2, f2 = eg.Evaluate()
+    assert rel(H2, Ho) < REL and rel_scaled(H2, Ho) < REL and rel(b2, bo) < REL and abs(c2 - co) <= REL * abs(co)
+    assert rel(H2, Hg) < 1e-12 and rel(b2, bg) < 1e-12
     return Hg, bg
 
 
